@@ -1,0 +1,138 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes front ends for the two CPU checkers:
+
+  * `Ref`    : oracle/_ref/libdrt_ref.so, the UNMODIFIED reference sources compiled
+               against oracle/eigen_shim (see oracle/ref_driver.cpp);
+  * `Oracle` : oracle/liboracle.so, the from-scratch CPU restatement
+               (oracle/drt_oracle.cpp).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+reference legs import this module.  Nothing under distraytracer_b200/ may.
+"""
+import ctypes as C
+import os
+import tempfile
+
+import numpy as np
+
+from distraytracer_b200 import abi
+from distraytracer_b200.scene import Scene
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_SO = os.environ.get("DRT_REF_SO", os.path.join(HERE, "_ref", "libdrt_ref.so"))
+ORACLE_SO = os.path.join(HERE, "liboracle.so")
+REFERENCE_ROOT = "/root/reference"
+
+
+def ref_available():
+    return os.path.exists(REF_SO)
+
+
+def read_ppm(path):
+    with open(path, "rb") as f:
+        data = f.read()
+    # "P6\n<w> <h>\n255\n" exactly as helpers.h:191 writes it
+    parts = data.split(b"\n", 3)
+    assert parts[0] == b"P6" and parts[2] == b"255"
+    w, h = (int(v) for v in parts[1].split())
+    return np.frombuffer(parts[3], dtype=np.uint8, count=w * h * 3).reshape(h, w, 3).copy()
+
+
+class Ref:
+    """The reference renderer itself.  NOT thread-safe and not re-entrant (global
+    state, like the reference); use one process per instance."""
+
+    def __init__(self, asset_root=None, mocap=False):
+        self.lib = C.CDLL(REF_SO)
+        L = self.lib
+        L.drtref_last_error.restype = C.c_char_p
+        L.drtref_rng_draws.restype = C.c_ulonglong
+        L.drtref_build_scene.argtypes = [C.c_char_p, C.c_float]
+        L.drtref_render_unmodified.argtypes = [C.c_char_p, C.c_int]
+        L.drtref_render_cloud.argtypes = [C.c_char_p, C.c_float]
+        L.drtref_render_loop.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32,
+                                         C.POINTER(C.c_float), C.POINTER(C.c_uint8), C.POINTER(C.c_double)]
+        L.drtref_rng_mode.argtypes = [C.c_int, C.c_uint32, C.c_uint32]
+        L.drtref_mocap_bones.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_int]
+        if asset_root is None and os.path.isdir(REFERENCE_ROOT):
+            asset_root = REFERENCE_ROOT
+        self._check(L.drtref_init((asset_root or "").encode(), int(mocap)))
+        L.drtref_reset_globals()
+
+    def _check(self, rc):
+        if rc < 0:
+            raise RuntimeError(f"reference harness error {rc}: {self.lib.drtref_last_error().decode()}")
+        return rc
+
+    def reset(self):
+        self.lib.drtref_reset_globals()
+
+    def build(self, name, frame=0.0):
+        self._check(self.lib.drtref_build_scene(name.encode(), float(frame)))
+
+    def settings(self):
+        s = abi.Settings()
+        self.lib.drtref_get_settings(C.byref(s))
+        return s
+
+    def set_settings(self, s):
+        self.lib.drtref_set_settings(C.byref(s))
+
+    def export(self):
+        n, nl, nt = C.c_int(), C.c_int(), C.c_int()
+        self.lib.drtref_scene_counts(C.byref(n), C.byref(nl), C.byref(nt))
+        prims = (abi.Prim * max(n.value, 1))()
+        lights = (abi.Light * max(nl.value, 1))()
+        texs = (abi.Texture * max(nt.value, 1))()
+        self._check(self.lib.drtref_export_scene(prims, lights, texs))
+        textures = []
+        for i in range(nt.value):
+            h, w = texs[i].height, texs[i].width
+            textures.append(np.ctypeslib.as_array(texs[i].rgb, shape=(h, w, 3)).copy())
+        return Scene([abi.copy_struct(prims[i]) for i in range(n.value)],
+                     [abi.copy_struct(lights[i]) for i in range(nl.value)], textures)
+
+    def load(self, scene):
+        d = scene.desc()
+        self._check(self.lib.drtref_load_scene(C.byref(d)))
+
+    def rng(self, mode, seed=0, stream_id=0):
+        """mode 0: the reference's own mt19937(random_device); 1: deterministic stream."""
+        self.lib.drtref_rng_mode(int(mode), seed, stream_id)
+
+    def render_unmodified(self, frame=0):
+        """renderImage exactly as shipped -> uint8 (yRes,xRes,3), PPM row order."""
+        with tempfile.TemporaryDirectory() as td:
+            p = os.path.join(td, "o.ppm")
+            self._check(self.lib.drtref_render_unmodified(p.encode(), int(frame)))
+            return read_ppm(p)
+
+    def render_cloud(self, frame=0.0):
+        with tempfile.TemporaryDirectory() as td:
+            p = os.path.join(td, "o.ppm")
+            self._check(self.lib.drtref_render_cloud(p.encode(), float(frame)))
+            return read_ppm(p)
+
+    def render_loop(self, frame=0, y0=0, y1=None, reset_policy=1, seed=0):
+        """Pixel-loop restatement over the reference's rayColor.  Returns
+        (float32 (rows,xRes,3) in PPM row order (top row first),
+         bool (rows,xRes) mask of pixels where the reference itself aborts, seconds)."""
+        s = self.settings()
+        if y1 is None:
+            y1 = s.yRes
+        out = np.zeros(((y1 - y0), s.xRes, 3), dtype=np.float32)
+        ab = np.zeros(((y1 - y0), s.xRes), dtype=np.uint8)
+        sec = C.c_double()
+        self._check(self.lib.drtref_render_loop(int(frame), y0, y1, reset_policy, seed,
+                                                out.ctypes.data_as(C.POINTER(C.c_float)),
+                                                ab.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(sec)))
+        return out[::-1].copy(), ab[::-1].astype(bool), sec.value
+
+    def mocap_bones(self, frame, max_bones=64):
+        buf = (C.c_double * (6 * max_bones))()
+        n = self._check(self.lib.drtref_mocap_bones(int(frame), buf, max_bones))
+        return np.array(buf[:6 * n], dtype=np.float64).reshape(n, 2, 3)
+
+
+def quantize(img_f32):
+    """writePPM's float -> unsigned char truncation (helpers.h:178-179)."""
+    return np.asarray(img_f32, dtype=np.float32).astype(np.uint8)

@@ -1,0 +1,584 @@
+// TEST INFRASTRUCTURE ONLY -- never linked into, imported by or executed from the
+// shipped product (distraytracer_b200/).  Only tests/, __graft_entry__.smoke()
+// and bench.py's cpu_baseline / --impl reference legs may load the library
+// this file builds (oracle/_ref/libdrt_ref.so).
+//
+// Harness around the UNMODIFIED reference renderer.  The reference sources are
+// compiled where they lie (/root/reference/*.cpp, never copied) against
+// oracle/eigen_shim (Eigen is neither vendored nor installed) and
+// oracle/ref_shim/random (RNG hook).  This TU textually includes
+// render_final_project.cpp with `main` renamed, so rayColor, renderImage,
+// renderImageCloud, the scene builders of scene.h and every global are the
+// reference's own code.  What this file adds:
+//   * drtref_build_scene  : call a reference scene builder by name;
+//   * drtref_export_scene : flatten shapes/lights/textures to the drt.h PODs
+//                           (the inverse is drtref_load_scene), so the oracle
+//                           restatement and the CUDA path get bit-identical input;
+//   * drtref_render_unmodified : the reference's renderImage, untouched;
+//   * drtref_render_loop  : a restatement of renderImage's pixel loop
+//                           (render_final_project.cpp:1031-1219) that calls the
+//                           reference's own rayColor/getDOFSamples/shuffle/
+//                           getPerspEyeRay/cloudColor/bumpBVH, adding a row range,
+//                           a per-pixel stream reset, a float output buffer and a
+//                           CLOCK_MONOTONIC timer around the loop only.
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <unistd.h>
+#include <time.h>
+#include <setjmp.h>
+#include <signal.h>
+#include <execinfo.h>
+#include <exception>
+
+#include "drt_rng.h"
+#include "../include/drt.h"
+
+// ---- RNG hook (see ref_shim/random) ------------------------------------------
+static int g_rng_mode = 0;  // 0: the reference's own mt19937; 1: deterministic stream
+static drt_stream g_stream;
+static unsigned long long g_draws = 0;
+extern "C" int drtref_rng_take(double* u) {
+  g_draws++;
+  if (!g_rng_mode) return 0;
+  *u = drt_stream_next(&g_stream);
+  return 1;
+}
+
+// ---- silence the reference's progress chatter (printf per scanline, :1033) ---
+static int g_quiet = 1;
+static int drtref_printf(const char* fmt, ...) {
+  if (g_quiet) return 0;
+  va_list ap; va_start(ap, fmt); int r = vprintf(fmt, ap); va_end(ap); return r;
+}
+#define printf(...) drtref_printf(__VA_ARGS__)
+
+#define main drt_reference_main
+#include "render_final_project.cpp"  // resolved through -I /root/reference
+#undef main
+#undef printf
+
+namespace {
+
+// The reference reports several "cannot happen" states with a bare `throw;`
+// (render_final_project.cpp:637, 876; geometry.cpp:2613), which with no active
+// exception is std::terminate().  Some of them DO happen on its own test scenes
+// (e.g. a hit on a side face of a textured RectPrismV2 yields u > 1 from the top
+// face's getUV and aborts `test checkertexture`).  To get an image at all, the
+// loop harness arms a terminate handler that abandons the current pixel and
+// flags it as "reference aborted here"; parity tests exclude flagged pixels.
+jmp_buf g_jmp;
+volatile bool g_jmp_armed = false;
+void onTerminate() {
+  if (g_jmp_armed) { g_jmp_armed = false; longjmp(g_jmp, 1); }
+  abort();
+}
+
+struct NullBuf : std::streambuf { int overflow(int c) override { return c; } };
+struct QuietCout {
+  NullBuf nb; std::streambuf* old;
+  QuietCout() { old = g_quiet ? std::cout.rdbuf(&nb) : nullptr; }
+  ~QuietCout() { if (old) std::cout.rdbuf(old); }
+};
+
+std::string g_err;
+int fail(int code, const std::string& m) { g_err = m; return code; }
+
+void v3(double* o, const VEC3& v) { o[0] = v[0]; o[1] = v[1]; o[2] = v[2]; }
+VEC3 V3(const double* p) { return VEC3(p[0], p[1], p[2]); }
+
+int materialTag(const std::string& m) {
+  if (m == "glass") return DRT_MAT_GLASS;
+  if (m == "steel") return DRT_MAT_STEEL;
+  if (m == "aluminum") return DRT_MAT_ALUMINUM;
+  if (m == "water") return DRT_MAT_WATER;
+  if (m == "linoleum") return DRT_MAT_LINOLEUM;
+  return DRT_MAT_NONE;
+}
+const char* materialName(int t) {
+  switch (t) {
+    case DRT_MAT_GLASS: return "glass"; case DRT_MAT_STEEL: return "steel";
+    case DRT_MAT_ALUMINUM: return "aluminum"; case DRT_MAT_WATER: return "water";
+    case DRT_MAT_LINOLEUM: return "linoleum"; default: return "";
+  }
+}
+int modelTag(const std::string& m) {
+  if (m == "oren-nayar") return DRT_MODEL_OREN_NAYAR;
+  if (m == "cook-torrance") return DRT_MODEL_COOK_TORRANCE;
+  if (m == "raw") return DRT_MODEL_RAW;
+  return DRT_MODEL_LAMBERT;
+}
+const char* modelName(int t) {
+  switch (t) {
+    case DRT_MODEL_OREN_NAYAR: return "oren-nayar"; case DRT_MODEL_COOK_TORRANCE: return "cook-torrance";
+    case DRT_MODEL_RAW: return "raw"; default: return "lambert";
+  }
+}
+int nameTag(const std::string& n) {
+  if (n == "rectangle") return DRT_NAME_RECTANGLE;
+  if (n == "spherelight") return DRT_NAME_SPHERELIGHT;
+  if (n == "rectanglelight") return DRT_NAME_RECTANGLELIGHT;
+  return DRT_NAME_OTHER;
+}
+
+std::vector<std::vector<uint8_t>> g_tex_bytes;  // exported texture payloads
+bool g_mocap_loaded = false;
+
+void commonFields(drt_prim& p, GeoPrimitive* s) {
+  p.name = nameTag(s->name);
+  p.material = materialTag(s->reflect_params.material);
+  p.model = modelTag(s->model);
+  p.flags = (s->light ? DRT_FLAG_LIGHT : 0) | (s->motion ? DRT_FLAG_MOTION : 0) |
+            (s->texture ? DRT_FLAG_TEXTURE : 0) | (s->reflect_params.glossy ? DRT_FLAG_GLOSSY : 0) |
+            (s->mesh ? DRT_FLAG_MESH : 0) | (s->uv_verts ? DRT_FLAG_UV_VERTS : 0);
+  p.tex_frame = s->texture ? s->tex_frame : -1;
+  v3(p.color, s->color); v3(p.bordercolor, s->bordercolor);
+  // roughness is an uninitialised float for shapes that never set it; only the
+  // Oren-Nayar / Cook-Torrance models read it (render_final_project.cpp:896,925)
+  p.roughness = (p.model == DRT_MODEL_OREN_NAYAR || p.model == DRT_MODEL_COOK_TORRANCE) ? s->reflect_params.roughness : 0.0;
+  p.refr[0] = s->reflect_params.refr[0]; p.refr[1] = s->reflect_params.refr[1];
+  v3(p.center, s->center);
+}
+
+void applyCommon(GeoPrimitive* s, const drt_prim& p) {
+  s->light = (p.flags & DRT_FLAG_LIGHT) != 0;
+  s->texture = (p.flags & DRT_FLAG_TEXTURE) != 0;
+  s->reflect_params.glossy = (p.flags & DRT_FLAG_GLOSSY) != 0;
+  s->mesh = (p.flags & DRT_FLAG_MESH) != 0;
+  s->uv_verts = (p.flags & DRT_FLAG_UV_VERTS) != 0;
+  s->tex_frame = p.tex_frame;
+  s->bordercolor = V3(p.bordercolor);
+  s->reflect_params.roughness = p.roughness;
+  s->reflect_params.refr = VEC2(p.refr[0], p.refr[1]);
+  s->mesh_normal = V3(p.mesh_normal);
+  s->uvA = VEC2(p.uvA[0], p.uvA[1]); s->uvB = VEC2(p.uvB[0], p.uvB[1]); s->uvC = VEC2(p.uvC[0], p.uvC[1]);
+  if (p.name == DRT_NAME_RECTANGLE) s->name = "rectangle";
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* drtref_last_error(void) { return g_err.c_str(); }
+void drtref_set_quiet(int q) { g_quiet = q; }
+unsigned long long drtref_rng_draws(void) { return g_draws; }
+
+void drtref_rng_mode(int mode, uint32_t seed, uint32_t id) {
+  g_rng_mode = mode;
+  drt_stream_reset(&g_stream, seed, id);
+}
+
+// chdir to the directory holding textures/, 90.asf, 90_16_v3.amc (the reference
+// opens them by relative path) and, if present, load the mocap data as main does
+// (render_final_project.cpp:1388-1399).
+static void onSegv(int sig) {
+  void* bt[48];
+  int n = backtrace(bt, 48);
+  const char m[] = "drt_ref: fatal signal inside the reference code; backtrace:\n";
+  (void)!write(2, m, sizeof(m) - 1);
+  backtrace_symbols_fd(bt, n, 2);
+  _exit(128 + sig);
+}
+
+int drtref_init(const char* asset_root, int load_mocap) {
+  if (getenv("DRT_REF_BACKTRACE")) signal(SIGSEGV, onSegv);
+  if (asset_root && *asset_root && chdir(asset_root) != 0) return fail(-1, std::string("chdir failed: ") + asset_root);
+  if (load_mocap && !g_mocap_loaded) {
+    if (access("90.asf", R_OK) != 0 || access("90_16_v3.amc", R_OK) != 0) return fail(-1, "mocap files not found");
+    QuietCout q;
+    skeleton = new Skeleton("90.asf", MOCAP_SCALE);
+    skeleton->setBasePosture();
+    displayer.LoadSkeleton(skeleton);
+    motion = new Motion("90_16_v3.amc", MOCAP_SCALE, skeleton);
+    displayer.LoadMotion(motion);
+    skeleton->setPosture(*(displayer.GetSkeletonMotion(0)->GetPosture(0)));
+    g_mocap_loaded = true;
+  }
+  return 0;
+}
+
+// Restore the globals to their static initialisers (render_final_project.cpp:48-138)
+// so successive scenes do not inherit each other's camera / sampling settings.
+void drtref_reset_globals(void) {
+  xRes = 1920; yRes = 1080;
+  eye = VEC3(-6, 0.5, 1); lookingAt = VEC3(0.5, 0.5, 1); up = VEC3(0, 1, 0);
+  aspect = (float)1920 / (float)1080; near = 1; fov = 45.0; aperture = 0.2; focal_length = 10;
+  use_model = true; nogloss = false; refr_air = 1; refr_glass = 1.5; max_depth = 10; phong = 10;
+  default_col = VEC3(0, 0, 0);
+  antialias_samples = 10; brdf_samples = 2; blur_samples = 2; frame_range = 1;
+  frame_prism = 960; frame_cloud = 1952; frame_blur = 1600;
+  move_per_frame = 0.1 / 8; accel_t = 80 / pow(360, 3);
+  sundir = VEC3(0, 0.1, -1); perlin_cloud = false; saturation = 0.2; clouddist = 10; cloudhoff = 0.2;
+  sun_outer = VEC3(0.9, 0.3, 0.9); sun_inner = VEC3(1.0, 0.7, 0.7); sun_core = VEC3(1, 1, 1);
+  bluesky = VEC3(0.3, 0.55, 0.8); redsky = VEC3(0.8, 0.8, 0.6);
+  reflect = true;
+  shapes.clear(); lights.clear(); texture_frames.clear(); texture_dims.clear();
+}
+
+int drtref_build_scene(const char* name_c, float frame) {
+  std::string n(name_c);
+  QuietCout q;
+  try {
+    if (n == "checkertexture") buildSceneCheckerTexture(frame);
+    else if (n == "texture") BuildSceneRectangleTexture(frame);
+    else if (n == "textureog") BuildSceneRectangleTextureOG(frame);
+    else if (n == "reflectance") buildSceneReflectance((int)frame);
+    else if (n == "dof") buildSceneDOF(frame);
+    else if (n == "spheres") buildSceneSpheres(frame);
+    else if (n == "spherelight") buildSphereLightTest(frame);
+    else if (n == "window") buildAggWall(frame);
+    else if (n == "staircase") buildStaircaseTest(frame);
+    else if (n == "rectprism") buildRectPrismV2Test(frame);
+    else if (n == "checkercylinder") buildSceneCylinder(frame);
+    else if (n == "hw4") buildSceneHW4(frame);
+    else if (n == "chkpt2") { if (!g_mocap_loaded) return fail(-1, "mocap not loaded"); buildSceneChkpt2(frame); }
+    else if (n == "boundary") { if (!g_mocap_loaded) return fail(-1, "mocap not loaded"); buildSceneBoundary(frame); }
+    else if (n == "scene") { if (!g_mocap_loaded) return fail(-1, "mocap not loaded"); buildScene(frame); }
+    else return fail(-1, "unknown scene " + n);
+  } catch (...) { return fail(-5, "reference scene builder threw"); }
+  return 0;
+}
+
+void drtref_get_settings(drt_settings* s) {
+  memset(s, 0, sizeof(*s));
+  s->xRes = xRes; s->yRes = yRes;
+  v3(s->eye, eye); v3(s->lookingAt, lookingAt); v3(s->up, up);
+  s->aspect = aspect; s->near_plane = near; s->fov = fov; s->aperture = aperture; s->focal_length = focal_length;
+  s->nogloss = nogloss; s->refr_air = refr_air; s->refr_glass = refr_glass; s->max_depth = max_depth; s->phong = phong;
+  s->antialias_samples = antialias_samples; s->brdf_samples = brdf_samples; s->blur_samples = blur_samples;
+  s->frame_range = frame_range; s->frame_prism = frame_prism; s->frame_cloud = frame_cloud; s->frame_blur = frame_blur;
+  s->move_per_frame = move_per_frame; s->accel_t = accel_t;
+  v3(s->sundir, sundir); s->perlin_cloud = perlin_cloud; s->saturation = saturation; s->clouddist = clouddist;
+  s->cloudhoff = cloudhoff;
+  v3(s->sun_outer, sun_outer); v3(s->sun_inner, sun_inner); v3(s->sun_core, sun_core);
+  v3(s->bluesky, bluesky); v3(s->redsky, redsky);
+  s->reflect = reflect;
+}
+
+void drtref_set_settings(const drt_settings* s) {
+  xRes = s->xRes; yRes = s->yRes;
+  eye = V3(s->eye); lookingAt = V3(s->lookingAt); up = V3(s->up);
+  aspect = s->aspect; near = s->near_plane; fov = s->fov; aperture = s->aperture; focal_length = s->focal_length;
+  nogloss = s->nogloss != 0; refr_air = s->refr_air; refr_glass = s->refr_glass; max_depth = s->max_depth; phong = s->phong;
+  antialias_samples = s->antialias_samples; brdf_samples = s->brdf_samples; blur_samples = s->blur_samples;
+  frame_range = s->frame_range; frame_prism = s->frame_prism; frame_cloud = s->frame_cloud; frame_blur = s->frame_blur;
+  move_per_frame = s->move_per_frame; accel_t = s->accel_t;
+  sundir = V3(s->sundir); perlin_cloud = s->perlin_cloud != 0; saturation = s->saturation; clouddist = s->clouddist;
+  cloudhoff = s->cloudhoff;
+  sun_outer = V3(s->sun_outer); sun_inner = V3(s->sun_inner); sun_core = V3(s->sun_core);
+  bluesky = V3(s->bluesky); redsky = V3(s->redsky);
+  reflect = s->reflect != 0;
+}
+
+void drtref_scene_counts(int* n_prims, int* n_lights, int* n_textures) {
+  *n_prims = (int)shapes.size(); *n_lights = (int)lights.size(); *n_textures = (int)texture_frames.size();
+}
+
+// Flatten the reference's shapes/lights/textures.  `prims`, `lights`, `textures`
+// must have room for the counts reported by drtref_scene_counts.  Texture byte
+// pointers stay valid until the next export.
+int drtref_export_scene(drt_prim* prims, drt_light* out_lights, drt_texture* textures) {
+  for (size_t i = 0; i < shapes.size(); i++) {
+    GeoPrimitive* s = shapes[i].get();
+    drt_prim& p = prims[i];
+    memset(&p, 0, sizeof(p));
+    commonFields(p, s);
+    if (auto* c = dynamic_cast<CheckerboardWithHole*>(s)) {
+      p.type = DRT_PRIM_CHECKERBOARD_HOLE;
+      v3(p.A, c->A); v3(p.B, c->B); v3(p.C, c->C); v3(p.D, c->D);
+      p.S = c->S; p.borderwidth = c->borderwidth; v3(p.color1, c->color1); v3(p.color2, c->color2);
+      v3(p.hole[0], c->hole->A); v3(p.hole[1], c->hole->B); v3(p.hole[2], c->hole->C); v3(p.hole[3], c->hole->D);
+    } else if (auto* c = dynamic_cast<Checkerboard*>(s)) {
+      p.type = DRT_PRIM_CHECKERBOARD;
+      v3(p.A, c->A); v3(p.B, c->B); v3(p.C, c->C); v3(p.D, c->D);
+      p.S = c->S; v3(p.color1, c->color1); v3(p.color2, c->color2);
+    } else if (dynamic_cast<Rectangle*>(s)) {
+      p.type = DRT_PRIM_RECTANGLE;
+      v3(p.A, s->A); v3(p.B, s->B); v3(p.C, s->C); v3(p.D, s->D);
+    } else if (auto* c = dynamic_cast<CheckerCylinder*>(s)) {
+      p.type = DRT_PRIM_CHECKER_CYLINDER;
+      v3(p.c1, c->c1); v3(p.c2, c->c2); p.radius = c->radius; p.S = c->S; p.borderwidth = c->borderwidth;
+    } else if (dynamic_cast<Cylinder*>(s)) {
+      p.type = DRT_PRIM_CYLINDER;
+      v3(p.c1, s->c1); v3(p.c2, s->c2); p.radius = s->radius;
+    } else if (dynamic_cast<Sphere*>(s)) {
+      p.type = DRT_PRIM_SPHERE; p.radius = s->radius;
+    } else if (dynamic_cast<Triangle*>(s)) {
+      p.type = DRT_PRIM_TRIANGLE;
+      v3(p.A, s->A); v3(p.B, s->B); v3(p.C, s->C);
+      p.uvA[0] = s->uvA[0]; p.uvA[1] = s->uvA[1]; p.uvB[0] = s->uvB[0]; p.uvB[1] = s->uvB[1];
+      p.uvC[0] = s->uvC[0]; p.uvC[1] = s->uvC[1];
+      if (s->mesh) v3(p.mesh_normal, s->mesh_normal);
+    } else if (dynamic_cast<RectPrismV2*>(s)) {
+      p.type = DRT_PRIM_RECTPRISMV2;
+      v3(p.A, s->A); v3(p.B, s->B); v3(p.C, s->C); v3(p.D, s->D);
+      v3(p.E, s->E); v3(p.F, s->F); v3(p.G, s->G); v3(p.H, s->H);
+    } else {
+      return fail(-2, "unsupported primitive class at index " + std::to_string(i) + " (" + s->name + ")");
+    }
+  }
+  for (size_t i = 0; i < lights.size(); i++) {
+    LightPrimitive* l = lights[i].get();
+    drt_light& o = out_lights[i];
+    memset(&o, 0, sizeof(o));
+    o.prim_index = -1;
+    v3(o.color, l->color); v3(o.center, l->center);
+    shared_ptr<void> lv = dynamic_pointer_cast<void>(lights[i]);
+    for (size_t k = 0; k < shapes.size(); k++)
+      if (dynamic_pointer_cast<void>(shapes[k]) == lv) { o.prim_index = (int)k; break; }
+    if (auto* sl = dynamic_cast<sphereLight*>(l)) {
+      o.type = DRT_LIGHT_SPHERE; o.radius = sl->radius; v3(o.baxis, sl->baxis);
+      v3(o.center, sl->Sphere::center);
+    } else if (auto* rl = dynamic_cast<rectangleLight*>(l)) {
+      o.type = DRT_LIGHT_RECT; v3(o.A, rl->A); v3(o.B, rl->B); v3(o.C, rl->C); v3(o.D, rl->D);
+    } else {
+      o.type = DRT_LIGHT_POINT;
+    }
+  }
+  g_tex_bytes.assign(texture_frames.size(), std::vector<uint8_t>());
+  for (size_t i = 0; i < texture_frames.size(); i++) {
+    const std::vector<VEC3>& t = texture_frames[i];
+    g_tex_bytes[i].resize(t.size() * 3);
+    for (size_t k = 0; k < t.size(); k++)
+      for (int c = 0; c < 3; c++) g_tex_bytes[i][3 * k + c] = (uint8_t)lround(t[k][c] * 255.0);
+    textures[i].width = (int)texture_dims[i][0]; textures[i].height = (int)texture_dims[i][1];
+    textures[i].rgb = g_tex_bytes[i].data();
+  }
+  return 0;
+}
+
+// Inverse of drtref_export_scene: rebuild the reference's object graph from PODs
+// through the reference's own constructors.
+int drtref_load_scene(const drt_scene_desc* d) {
+  shapes.clear(); lights.clear(); texture_frames.clear(); texture_dims.clear();
+  for (int i = 0; i < d->n_textures; i++) {
+    const drt_texture& t = d->textures[i];
+    std::vector<VEC3> fr; fr.reserve((size_t)t.width * t.height);
+    for (size_t k = 0; k < (size_t)t.width * t.height; k++)  // helpers.h:102-106
+      fr.push_back(VEC3(t.rgb[3 * k] / 255.0, t.rgb[3 * k + 1] / 255.0, t.rgb[3 * k + 2] / 255.0));
+    texture_frames.push_back(fr);
+    texture_dims.push_back(VEC2(t.width, t.height));
+  }
+  std::vector<shared_ptr<LightPrimitive>> area(d->n_prims);
+  for (int i = 0; i < d->n_prims; i++) {
+    const drt_prim& p = d->prims[i];
+    std::string mat = materialName(p.material), model = modelName(p.model);
+    bool mo = (p.flags & DRT_FLAG_MOTION) != 0;
+    shared_ptr<GeoPrimitive> s;
+    switch (p.type) {
+      case DRT_PRIM_SPHERE:
+        if (p.name == DRT_NAME_SPHERELIGHT) {
+          auto sl = make_shared<sphereLight>(V3(p.center), (float)p.radius, V3(p.color), mat, mo);
+          sl->model = model; s = sl; area[i] = sl;
+        } else s = make_shared<Sphere>(V3(p.center), (float)p.radius, V3(p.color), mat, mo, model);
+        break;
+      case DRT_PRIM_CYLINDER:
+        s = make_shared<Cylinder>(V3(p.c1), V3(p.c2), (float)p.radius, V3(p.color), mat, mo, model); break;
+      case DRT_PRIM_CHECKER_CYLINDER: {
+        auto c = make_shared<CheckerCylinder>(V3(p.c1), V3(p.c2), (float)p.radius, V3(p.color), (float)p.S, mat, mo, model);
+        c->borderwidth = p.borderwidth; s = c; break; }
+      case DRT_PRIM_TRIANGLE:
+        s = make_shared<Triangle>(V3(p.A), V3(p.B), V3(p.C), V3(p.color), mat, mo, model); break;
+      case DRT_PRIM_RECTANGLE:
+        if (p.name == DRT_NAME_RECTANGLELIGHT) {
+          auto rl = make_shared<rectangleLight>(V3(p.A), V3(p.B), V3(p.C), V3(p.D), V3(p.color), mat, mo);
+          rl->model = model; s = rl; area[i] = rl;
+        } else s = make_shared<Rectangle>(V3(p.A), V3(p.B), V3(p.C), V3(p.D), V3(p.color), mat, mo, p.tex_frame, model);
+        break;
+      case DRT_PRIM_RECTPRISMV2:
+        s = make_shared<RectPrismV2>(V3(p.A), V3(p.B), V3(p.C), V3(p.D), V3(p.E), V3(p.F), V3(p.G), V3(p.H),
+                                     V3(p.color), mat, mo, p.tex_frame, model);
+        break;
+      case DRT_PRIM_CHECKERBOARD:
+        s = make_shared<Checkerboard>(V3(p.A), V3(p.B), V3(p.C), V3(p.D), V3(p.color1), V3(p.color2), (float)p.S, mat, mo, model);
+        break;
+      case DRT_PRIM_CHECKERBOARD_HOLE: {
+        auto hole = make_shared<Rectangle>(V3(p.hole[0]), V3(p.hole[1]), V3(p.hole[2]), V3(p.hole[3]), VEC3(0, 0, 0));
+        auto c = make_shared<CheckerboardWithHole>(V3(p.A), V3(p.B), V3(p.C), V3(p.D), V3(p.color1), V3(p.color2),
+                                                   (float)p.S, hole, mat, mo, model);
+        c->borderwidth = p.borderwidth; s = c; break; }
+      default: return fail(-2, "unsupported primitive type");
+    }
+    std::string keep = s->name;
+    applyCommon(s.get(), p);
+    if (p.name != DRT_NAME_RECTANGLE) s->name = keep;
+    shapes.push_back(s);
+  }
+  for (int i = 0; i < d->n_lights; i++) {
+    const drt_light& l = d->lights[i];
+    if (l.type == DRT_LIGHT_POINT) lights.push_back(make_shared<pointLight>(V3(l.center), V3(l.color)));
+    else {
+      if (l.prim_index < 0 || l.prim_index >= d->n_prims || !area[l.prim_index]) return fail(-1, "area light without its shape");
+      if (l.type == DRT_LIGHT_SPHERE) dynamic_cast<sphereLight*>(area[l.prim_index].get())->baxis = V3(l.baxis);
+      area[l.prim_index]->color = V3(l.color);
+      lights.push_back(area[l.prim_index]);
+    }
+  }
+  return 0;
+}
+
+// Bone cylinders of mocap frame `frame` exactly as the scene builders derive them
+// (scene.h:109-128 + 616-659): returns endpoints as 6 doubles per bone.
+int drtref_mocap_bones(int frame, double* out, int max_bones) {
+  if (!g_mocap_loaded) return fail(-1, "mocap not loaded");
+  QuietCout q;
+  setSkeletonsToSpecifiedFrame(frame);
+  displayer.ComputeBonePositions(DisplaySkeleton::BONES_AND_LOCAL_FRAMES);
+  vector<MATRIX4>& rotations = displayer.rotations();
+  vector<MATRIX4>& scalings = displayer.scalings();
+  vector<VEC4>& translations = displayer.translations();
+  vector<float>& lengths = displayer.lengths();
+  int n = 0;
+  for (int x = 1; x < (int)rotations.size() && n < max_bones; x++, n++) {
+    VEC4 leftVertex(0, 0, 0, 1);
+    VEC4 rightVertex(0, 0, lengths[x], 1);
+    leftVertex = rotations[x] * scalings[x] * leftVertex + translations[x];
+    rightVertex = rotations[x] * scalings[x] * rightVertex + translations[x];
+    for (int k = 0; k < 3; k++) { out[6 * n + k] = leftVertex[k]; out[6 * n + 3 + k] = rightVertex[k]; }
+  }
+  return n;
+}
+
+// The reference's renderImage, untouched: writes a P6 PPM to `path`.
+int drtref_render_unmodified(const char* path, int frame) {
+  QuietCout q;
+  try {
+    renderImage(path, frame, [](float) {});
+  } catch (...) { return fail(-5, "reference renderImage threw"); }
+  return 0;
+}
+
+int drtref_render_cloud(const char* path, float frame) {
+  QuietCout q;
+  try { renderImageCloud(path, frame); } catch (...) { return fail(-5, "reference renderImageCloud threw"); }
+  return 0;
+}
+
+// Restatement of the pixel loop of renderImage (render_final_project.cpp:965-1222)
+// over rows [y0,y1), calling the reference's own functions.
+//   reset_policy 0: never reset the stream (bit-compatible with
+//                   drtref_render_unmodified under the same stream);
+//                1: reset the stream at the start of every pixel with id y*xRes+x.
+//   out: (y1-y0)*xRes*3 floats in LOOP order (row y0 first), values in [0,255]
+//        exactly as stored into ppmOut (:1215-1217).
+//   aborted: (y1-y0)*xRes bytes, 1 where the reference itself throws/terminates
+//        while shading the pixel (its output there is undefined; `out` gets 0).
+int drtref_render_loop(int frame, int y0, int y1, int reset_policy, uint32_t seed, float* out, uint8_t* aborted, double* seconds) {
+  QuietCout q;
+  try {
+    if (shapes.size() < 1) return fail(-5, "No shapes to render!");
+    vector<int> range(shapes.size());
+    iota(range.begin(), range.end(), 0);
+    bvh = generateBVH(range);                                        // :980
+
+    const VEC3 cameraZ = -(lookingAt - eye).normalized();            // :989
+    VEC3 cameraX = up.cross(cameraZ).normalized();                   // :991
+    if (cameraX.isApprox(VEC3(0, 0, 0))) return fail(-5, "Gaze direction can't be equal to up vector!");
+    VEC3 cameraY = cameraZ.cross(cameraX).normalized();              // :997
+    VEC3 new_up, newX, newY;
+    if (frame >= frame_cloud) {                                      // :1004-1009
+      new_up = VEC3(-1, 0, 0);
+      newX = new_up.cross(cameraZ).normalized();
+      newY = cameraZ.cross(newX).normalized();
+    }
+    MATRIX4 cob; cob << cameraX.transpose(), 0, cameraY.transpose(), 0, cameraZ.transpose(), 0, 0, 0, 0, 1;
+    MATRIX4 origin = MatrixXd::Identity(4, 4);
+    origin(0, 3) = -eye[0]; origin(1, 3) = -eye[1]; origin(2, 3) = -eye[2];
+    MATRIX4 mcam = cob * origin;
+    MATRIX4 new_cob; new_cob << newX.transpose(), 0, newY.transpose(), 0, cameraZ.transpose(), 0, 0, 0, 0, 1;
+    MATRIX4 new_mcam = new_cob * origin;
+
+    const float t = tan(fov * M_PI / 360.0) * abs(near);             // :1024-1027
+    const float b = -t;
+    const float r = aspect * t;
+    const float l = -r;
+
+    struct timespec ts0, ts1;
+    clock_gettime(CLOCK_MONOTONIC, &ts0);
+    std::terminate_handler old_handler = std::set_terminate(onTerminate);
+    for (int y = y0; y < y1; y++) {
+      for (int x = 0; x < xRes; x++) {
+        float* o = out + 3 * ((size_t)(y - y0) * xRes + x);
+        uint8_t* ab = aborted + ((size_t)(y - y0) * xRes + x);
+        *ab = 0;
+        if (setjmp(g_jmp) != 0) { *ab = 1; o[0] = o[1] = o[2] = 0; continue; }
+        g_jmp_armed = true;
+        try {
+        if (reset_policy == 1) drt_stream_reset(&g_stream, seed, (uint32_t)(y * xRes + x));
+        default_col = VEC3(0, 0, 0);
+        VEC3 color(0, 0, 0);
+        vector<VEC3> eye_samples;
+        getDOFSamples(eye_samples, eye, cameraX, cameraY, antialias_samples);   // :1044
+        int n = int(sqrt(antialias_samples));                                   // :1046
+        vector<VEC2> jitter_pixels;
+        for (int i = 0; i < n; i++)
+          for (int j = 0; j < n; j++) {
+            float adj_x = x + ((float)i + uniform(generator)) / (float)9;       // :1052
+            float adj_y = y + ((float)j + uniform(generator)) / (float)9;       // :1053
+            jitter_pixels.push_back(VEC2(adj_x, adj_y));
+          }
+        shuffle(eye_samples);                                                   // :1059
+        int sampled_n = pow(n, 2);
+        for (int i = 0; i < sampled_n; i++) {
+          VEC3 tmp_color(0, 0, 0);
+          VEC3 eye_sample = eye_samples[i];
+          VEC2 pixel = jitter_pixels[i];
+          const VEC3 rayDir = getPerspEyeRay(l, r, t, b, pixel[0], pixel[1], cameraX, cameraY, cameraZ);
+          VEC3 focalPoint = eye + focal_length * rayDir;
+          bool hit = false;
+          bool motion = false;
+          rayColor(focalPoint - eye_sample, eye_sample, max_depth, tmp_color, hit, motion);   // :1072
+          auto background = [&]() -> VEC3 {                                     // :1076-1093
+            if (perlin_cloud == true) {
+              VEC4 point; point << focalPoint, 1;
+              if (frame >= frame_cloud) point = new_mcam * point; else point = mcam * point;
+              return cloudColor(point.head<3>(), VEC3(0, 0, 0), frame);
+            }
+            return default_col;
+          };
+          if (hit == false) tmp_color = background();
+          if (motion == true) {                                                 // :1095-1210
+            for (int m = 0; m < blur_samples; m++) {
+              float frame_sample = float(frame) + uniform(generator) * frame_range;
+              float val = 0;   // the reference leaves this uninitialised when frame < frame_prism (UB, pinned to 0)
+              bool moved = false;
+              if (frame >= frame_prism) {
+                if (frame >= frame_blur) val = move_per_frame * (frame_sample - frame) + accel_t * pow((frame_sample - frame), 3);
+                else val = move_per_frame * (frame_sample - frame);
+                bumpBVH(bvh, val);
+                for (shared_ptr<GeoPrimitive> shape : shapes)
+                  if (shape->name == "rectangle") { shape->A[1] += val; shape->B[1] += val; shape->C[1] += val; shape->D[1] += val; }
+                moved = true;
+              }
+              VEC3 motion_color(0, 0, 0);
+              rayColor(focalPoint - eye_sample, eye_sample, max_depth, motion_color, hit, motion);
+              if (hit == false) motion_color = background();
+              tmp_color += motion_color;
+              bumpBVH(bvh, -val);
+              for (shared_ptr<GeoPrimitive> shape : shapes)
+                if (shape->name == "rectangle") { shape->A[1] -= val; shape->B[1] -= val; shape->C[1] -= val; shape->D[1] -= val; }
+              (void)moved;
+            }
+            tmp_color /= (blur_samples + 1);
+          }
+          color += tmp_color;
+        }
+        color /= sampled_n;
+        o[0] = clamp(color[0]) * 255.0f;                                        // :1215-1217
+        o[1] = clamp(color[1]) * 255.0f;
+        o[2] = clamp(color[2]) * 255.0f;
+        } catch (...) { *ab = 1; o[0] = o[1] = o[2] = 0; }   // `throw "literal"` sites (:739, geometry.cpp:2788)
+        g_jmp_armed = false;
+      }
+    }
+    std::set_terminate(old_handler);
+    clock_gettime(CLOCK_MONOTONIC, &ts1);
+    if (seconds) *seconds = (ts1.tv_sec - ts0.tv_sec) + 1e-9 * (ts1.tv_nsec - ts0.tv_nsec);
+  } catch (const char* m) { return fail(-5, std::string("reference threw: ") + m);
+  } catch (...) { return fail(-5, "reference threw"); }
+  return 0;
+}
+
+}  // extern "C"
