@@ -136,3 +136,63 @@ class Ref:
 def quantize(img_f32):
     """writePPM's float -> unsigned char truncation (helpers.h:178-179)."""
     return np.asarray(img_f32, dtype=np.float32).astype(np.uint8)
+
+
+ORACLE_KEYED, ORACLE_STREAM = 0, 1
+
+
+class Oracle:
+    """The CPU restatement (oracle/drt_oracle.cpp) over a POD scene."""
+
+    def __init__(self, scene):
+        self.lib = C.CDLL(ORACLE_SO)
+        L = self.lib
+        L.drt_oracle_last_error.restype = C.c_char_p
+        L.drt_oracle_scene_create.argtypes = [C.POINTER(abi.SceneDesc), C.POINTER(C.c_void_p)]
+        L.drt_oracle_scene_destroy.argtypes = [C.c_void_p]
+        L.drt_oracle_render.argtypes = [C.c_void_p, C.POINTER(abi.Settings), C.POINTER(abi.Tile), C.c_int,
+                                        C.POINTER(C.c_float), C.POINTER(C.c_uint8), C.POINTER(abi.Counters),
+                                        C.POINTER(C.c_double)]
+        L.drt_oracle_value_noise.restype = C.c_double
+        L.drt_oracle_value_noise.argtypes = [C.c_double] * 3
+        self.scene = scene
+        self._desc = scene.desc()
+        self.handle = C.c_void_p()
+        rc = L.drt_oracle_scene_create(C.byref(self._desc), C.byref(self.handle))
+        if rc != 0:
+            raise RuntimeError(f"oracle scene_create failed ({rc}): {L.drt_oracle_last_error().decode()}")
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.lib.drt_oracle_scene_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def render(self, settings, tile=None, mode=ORACLE_KEYED):
+        """Returns (float32 (h,w,3) PPM row order in [0,255], bool (h,w) aborted mask,
+        abi.Counters, seconds)."""
+        if tile is None:
+            tile = abi.Tile(0, 0, settings.xRes, settings.yRes, 0)
+        out = np.zeros((tile.height, tile.width, 3), dtype=np.float32)
+        ab = np.zeros((tile.height, tile.width), dtype=np.uint8)
+        cnt = abi.Counters()
+        sec = C.c_double()
+        rc = self.lib.drt_oracle_render(self.handle, C.byref(settings), C.byref(tile), int(mode),
+                                        out.ctypes.data_as(C.POINTER(C.c_float)),
+                                        ab.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(cnt), C.byref(sec))
+        if rc != 0:
+            raise RuntimeError(f"oracle render failed ({rc}): {self.lib.drt_oracle_last_error().decode()}")
+        return out, ab.astype(bool), cnt, sec.value
+
+    def value_noise(self, x, y, z):
+        return self.lib.drt_oracle_value_noise(x, y, z)
+
+
+def compare(a_f32, b_f32):
+    """Parity statistics between two float images in [0,255] after writePPM quantisation."""
+    qa, qb = quantize(a_f32).astype(np.int32), quantize(b_f32).astype(np.int32)
+    d = np.abs(qa - qb).max(axis=-1)
+    return {"frac_within_1": float((d <= 1).mean()), "max": int(d.max()), "mae": float(np.abs(qa - qb).mean()),
+            "n_bad": int((d > 1).sum())}
