@@ -27,6 +27,7 @@ LIGHT_POINT, LIGHT_SPHERE, LIGHT_RECT = range(3)
 # drt_sample_mode / drt_blur_mode
 SAMPLES_KEYED = 0
 BLUR_REFERENCE, BLUR_VELOCITY = 0, 1
+PRECISION_REFERENCE, PRECISION_FP32 = 0, 1
 
 D3 = C.c_double * 3
 D2 = C.c_double * 2
@@ -90,6 +91,7 @@ class Settings(C.Structure):
         ("sun_outer", D3), ("sun_inner", D3), ("sun_core", D3), ("bluesky", D3), ("redsky", D3),
         ("reflect", C.c_int32), ("frame", C.c_int32), ("seed", C.c_uint32),
         ("sample_mode", C.c_int32), ("blur_mode", C.c_int32), ("cloud_only", C.c_int32),
+        ("precision", C.c_int32),
     ]
 
 

@@ -1,0 +1,572 @@
+// C ABI (include/drt.h) of the CUDA hot path: scene flattening + upload, kernel
+// launches, timing, read-back.  Host code only prepares data; every pixel is
+// computed by the kernels in drt_kernels.cuh.  There is no CPU fallback.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/drt.h"
+#include "drt_kernels.cuh"
+
+using namespace drt;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& m) { g_err = m; return code; }
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(DRT_ERR_CUDA, std::string(#call) + " failed: " + cudaGetErrorString(e_));        \
+  } while (0)
+
+typedef Vec<double> D3;
+D3 V(const double* p) { return mk<double>(p[0], p[1], p[2]); }
+template <typename R> Vec<R> cv(const D3& v) { return mk<R>((R)v.x, (R)v.y, (R)v.z); }
+void f3(float* o, const double* p) { o[0] = (float)p[0]; o[1] = (float)p[1]; o[2] = (float)p[2]; }
+
+struct RectD { D3 A, nrm, e1, e2; double len1, len2; };
+RectD makeRect(const D3& A, const D3& B, const D3& C, const D3& D) {
+  RectD r;
+  r.A = A;
+  r.nrm = normalized(normalized(cross(B - A, C - A)));   // getNorm(start).normalized(), geometry.cpp:671,743-749
+  r.e1 = normalized(B - A); r.e2 = normalized(D - A);    // V1.normalized(), V2.normalized()
+  r.len1 = norm(B - A); r.len2 = norm(D - A);
+  return r;
+}
+
+template <typename R>
+Geom<R> rectGeom(int type, int owner, int flags, float eps, const RectD& r, float S, const D3& vel) {
+  Geom<R> g; memset(&g, 0, sizeof(g));
+  g.type = type; g.owner = owner; g.flags = flags; g.eps = eps;
+  g.p0 = cv<R>(r.A); g.p1 = cv<R>(r.nrm); g.p2 = cv<R>(r.e1); g.p3 = cv<R>(r.e2);
+  g.len1 = (R)r.len1; g.len2 = (R)r.len2; g.f0 = (float)r.len1; g.f1 = (float)r.len2; g.f2 = S;
+  g.vel = cv<R>(vel);
+  return g;
+}
+
+template <typename R>
+void objMatrix(R* out, const D3& axis, const D3& c1) {   // buildCOB(axis) * origin(-c1), geometry.cpp:27-40, 2580-2585
+  D3 w = normalized(axis);
+  D3 u = normalized(cross(mk<double>(1, 0, 0), w));
+  if (!(dot(u, u) > 0)) u = normalized(cross(mk<double>(0, 1, 0), w));
+  D3 v = normalized(cross(w, u));
+  const D3 rows[3] = {u, v, w};
+  for (int i = 0; i < 3; i++) {
+    out[4 * i + 0] = (R)rows[i].x; out[4 * i + 1] = (R)rows[i].y; out[4 * i + 2] = (R)rows[i].z;
+    // (cob*origin)(i,3) = (r0*0 + r1*0) + (r2*0 + ...) -> -(row . c1) in the 4-term (a+b)+(c+d) order
+    out[4 * i + 3] = (R)((rows[i].x * -c1.x + rows[i].y * -c1.y) + (rows[i].z * -c1.z + 0.0));
+  }
+}
+
+template <typename R>
+struct HostScene {
+  std::vector<Geom<R>> geoms;
+  std::vector<PrimD<R>> prims;
+  std::vector<LightD<R>> lights;
+};
+
+template <typename R>
+int flatten(const drt_prim* prims, int n_prims, const drt_light* lights, int n_lights, int n_textures, HostScene<R>& hs) {
+  hs.geoms.clear(); hs.prims.clear(); hs.lights.clear();
+  for (int i = 0; i < n_prims; i++) {
+    const drt_prim& p = prims[i];
+    if (p.type < 0 || p.type >= DRT_PRIM_TYPE_COUNT)
+      return fail(DRT_ERR_UNSUPPORTED, "primitive " + std::to_string(i) + ": unsupported type " + std::to_string(p.type));
+    if ((p.flags & DRT_FLAG_TEXTURE) && (p.type == DRT_PRIM_SPHERE || p.type == DRT_PRIM_CYLINDER))
+      return fail(DRT_ERR_UNSUPPORTED, "textured Sphere/Cylinder: GeoPrimitive::getUV has no body (geometry.h:36)");
+    if ((p.flags & DRT_FLAG_TEXTURE) && (p.tex_frame < 0 || p.tex_frame >= n_textures))
+      return fail(DRT_ERR_INVALID, "primitive " + std::to_string(i) + ": tex_frame out of range");
+    PrimD<R> q; memset(&q, 0, sizeof(q));
+    q.type = p.type; q.name = p.name; q.material = p.material; q.model = p.model; q.flags = p.flags; q.tex = p.tex_frame;
+    const float rough = (float)p.roughness;
+    q.roughness = rough;
+    q.on_A = (float)(1.0 - (0.5 * pow((double)rough, 2)) / (pow((double)rough, 2) + 0.33));   // :896
+    q.on_B = (float)((0.45 * pow((double)rough, 2)) / (pow((double)rough, 2) + 0.09));         // :897
+    q.schlick_R0 = (float)((pow(p.refr[0] - 1, 2) + pow(p.refr[1], 2)) / (pow(p.refr[0] + 1, 2) + pow(p.refr[1], 2)));
+    q.radius = (float)p.radius; q.S = (float)p.S; q.borderwidth = (float)p.borderwidth;
+    f3(q.color, p.color); f3(q.bordercolor, p.bordercolor); f3(q.color1, p.color1); f3(q.color2, p.color2);
+    const D3 A = V(p.A), B = V(p.B), C = V(p.C), D = V(p.D), E = V(p.E), F = V(p.F), G = V(p.G), H = V(p.H);
+    const D3 vel = V(p.velocity);
+    q.vel = cv<R>(vel);
+    q.length = (float)norm(B - A); q.width = (float)norm(D - A);
+    q.center = cv<R>(V(p.center));
+    const int gflags = (p.name == DRT_NAME_RECTANGLE) ? GF_NAME_RECTANGLE : 0;
+    auto setUVRect = [&](const D3& a, const D3& c, const D3& d) {       // Rectangle::getUV geometry.cpp:751-759
+      D3 ad = d - a, dc = c - d;
+      q.uvA = cv<R>(a); q.uvD = cv<R>(d); q.uv_ad = cv<R>(ad); q.uv_dc = cv<R>(dc);
+      q.uv_den_u = (R)(norm(ad) * norm(dc)); q.uv_den_v = (R)(norm(dc) * norm(ad));
+    };
+    switch (p.type) {
+      case DRT_PRIM_SPHERE: {
+        q.pA = cv<R>(V(p.center));
+        Geom<R> g; memset(&g, 0, sizeof(g));
+        g.type = G_SPHERE; g.owner = i; g.flags = 0; g.p0 = cv<R>(V(p.center)); g.f0 = (float)p.radius; g.vel = cv<R>(vel);
+        hs.geoms.push_back(g);
+        break; }
+      case DRT_PRIM_CYLINDER: case DRT_PRIM_CHECKER_CYLINDER: {
+        D3 c1 = V(p.c1), c2 = V(p.c2);
+        D3 axis = normalized(c2 - c1);                                   // geometry.cpp:231
+        q.pA = cv<R>(c1); q.pG = cv<R>(axis); q.axis_norm = (float)norm(axis);
+        if (p.type == DRT_PRIM_CHECKER_CYLINDER) objMatrix<R>(q.objM, axis, c1);
+        Geom<R> g; memset(&g, 0, sizeof(g));
+        g.type = G_CYL; g.owner = i; g.p0 = cv<R>(c1); g.p1 = cv<R>(c2); g.p2 = cv<R>(axis); g.f0 = (float)p.radius; g.vel = cv<R>(vel);
+        hs.geoms.push_back(g);
+        break; }
+      case DRT_PRIM_TRIANGLE: {
+        q.n0 = cv<R>(normalized(cross(B - A, C - A)));                   // geometry.cpp:588-594
+        q.tA = cv<R>(A); q.tB = cv<R>(B); q.tC = cv<R>(C);
+        q.tuv[0] = (float)p.uvA[0]; q.tuv[1] = (float)p.uvA[1]; q.tuv[2] = (float)p.uvB[0];
+        q.tuv[3] = (float)p.uvB[1]; q.tuv[4] = (float)p.uvC[0]; q.tuv[5] = (float)p.uvC[1];
+        Geom<R> g; memset(&g, 0, sizeof(g));
+        g.type = G_TRI; g.owner = i; g.flags = (p.flags & DRT_FLAG_MESH) ? GF_MESH : 0;
+        g.p0 = cv<R>(A); g.p1 = cv<R>(B - A); g.p2 = cv<R>(C - A); g.p3 = cv<R>(V(p.mesh_normal)); g.vel = cv<R>(vel);
+        hs.geoms.push_back(g);
+        break; }
+      case DRT_PRIM_RECTANGLE: case DRT_PRIM_CHECKERBOARD: case DRT_PRIM_CHECKERBOARD_HOLE: {
+        RectD r = makeRect(A, B, C, D);
+        q.n0 = cv<R>(normalized(cross(B - A, C - A)));                   // geometry.cpp:743-749
+        setUVRect(A, C, D);
+        q.eA = cv<R>(A); q.eB = cv<R>(B); q.eC = cv<R>(C); q.eD = cv<R>(D);
+        q.e_den = (R)(8 * norm(V(p.center) - A));                        // :786
+        if (p.type == DRT_PRIM_RECTANGLE) {
+          hs.geoms.push_back(rectGeom<R>(G_RECT, i, gflags, 1e-4f, r, 0.f, vel));
+        } else {
+          const bool hole = p.type == DRT_PRIM_CHECKERBOARD_HOLE;
+          hs.geoms.push_back(rectGeom<R>(G_CHECKER, i, gflags | (hole ? GF_HAS_HOLE : 0), 1e-3f, r, (float)p.S, vel));
+          if (hole) {
+            RectD hr = makeRect(V(p.hole[0]), V(p.hole[1]), V(p.hole[2]), V(p.hole[3]));
+            hs.geoms.push_back(rectGeom<R>(G_HOLE, i, 0, 1e-4f, hr, 0.f, vel));
+            q.rA = cv<R>(r.A); q.re1 = cv<R>(r.e1); q.re2 = cv<R>(r.e2); q.rlen1 = (R)r.len1; q.rlen2 = (R)r.len2;
+            q.hA = cv<R>(hr.A); q.hn = cv<R>(hr.nrm); q.he1 = cv<R>(hr.e1); q.he2 = cv<R>(hr.e2);
+            q.hlen1 = (R)hr.len1; q.hlen2 = (R)hr.len2;
+          }
+        }
+        break; }
+      case DRT_PRIM_RECTPRISMV2: {
+        q.n0 = cv<R>(-normalized(cross(F - E, H - E)));                  // normbot   geometry.cpp:866
+        q.n1 = cv<R>(normalized(cross(E - A, D - A)));                   // normright geometry.cpp:867
+        q.n2 = cv<R>(normalized(cross(B - A, E - A)));                   // normfront geometry.cpp:868
+        q.pA = cv<R>(A); q.pG = cv<R>(G);
+        setUVRect(A, C, D);                                              // faces[0]  geometry.cpp:943-948
+        const D3 f[6][4] = {{A, B, C, D}, {E, F, G, H}, {A, B, F, E}, {D, A, E, H}, {B, C, G, F}, {C, D, H, G}};   // :796-801
+        for (int k = 0; k < 6; k++)
+          hs.geoms.push_back(rectGeom<R>(G_RECT, i, 0, 1e-4f, makeRect(f[k][0], f[k][1], f[k][2], f[k][3]), 0.f, vel));
+        break; }
+    }
+    hs.prims.push_back(q);
+  }
+  for (int i = 0; i < n_lights; i++) {
+    const drt_light& l = lights[i];
+    if (l.type < 0 || l.type > DRT_LIGHT_RECT) return fail(DRT_ERR_UNSUPPORTED, "unknown light type");
+    if (l.prim_index >= n_prims) return fail(DRT_ERR_INVALID, "light prim_index out of range");
+    LightD<R> q; memset(&q, 0, sizeof(q));
+    q.type = l.type; q.prim_index = l.prim_index; q.radius = (float)l.radius;
+    D3 bax = V(l.baxis);
+    q.use_baxis = dot(bax, bax) > 0 ? 1 : 0;                             // !baxis.isApprox(0)
+    f3(q.color, l.color);
+    q.center = cv<R>(V(l.center)); q.baxis = cv<R>(bax); q.A = cv<R>(V(l.A)); q.B = cv<R>(V(l.B)); q.D = cv<R>(V(l.D));
+    hs.lights.push_back(q);
+  }
+  return DRT_OK;
+}
+
+template <typename R>
+struct DevScene {
+  Geom<R>* geoms = nullptr; PrimD<R>* prims = nullptr; LightD<R>* lights = nullptr;
+  int n_geoms = 0, n_prims = 0, n_lights = 0;
+};
+
+template <typename R>
+int upload(const HostScene<R>& hs, DevScene<R>& ds) {
+  if ((int)hs.geoms.size() != ds.n_geoms || !ds.geoms) {
+    if (ds.geoms) cudaFree(ds.geoms);
+    CK(cudaMalloc(&ds.geoms, sizeof(Geom<R>) * std::max<size_t>(1, hs.geoms.size())));
+  }
+  if ((int)hs.prims.size() != ds.n_prims || !ds.prims) {
+    if (ds.prims) cudaFree(ds.prims);
+    CK(cudaMalloc(&ds.prims, sizeof(PrimD<R>) * std::max<size_t>(1, hs.prims.size())));
+  }
+  if ((int)hs.lights.size() != ds.n_lights || !ds.lights) {
+    if (ds.lights) cudaFree(ds.lights);
+    CK(cudaMalloc(&ds.lights, sizeof(LightD<R>) * std::max<size_t>(1, hs.lights.size())));
+  }
+  ds.n_geoms = (int)hs.geoms.size(); ds.n_prims = (int)hs.prims.size(); ds.n_lights = (int)hs.lights.size();
+  if (ds.n_geoms) CK(cudaMemcpy(ds.geoms, hs.geoms.data(), sizeof(Geom<R>) * ds.n_geoms, cudaMemcpyHostToDevice));
+  if (ds.n_prims) CK(cudaMemcpy(ds.prims, hs.prims.data(), sizeof(PrimD<R>) * ds.n_prims, cudaMemcpyHostToDevice));
+  if (ds.n_lights) CK(cudaMemcpy(ds.lights, hs.lights.data(), sizeof(LightD<R>) * ds.n_lights, cudaMemcpyHostToDevice));
+  return DRT_OK;
+}
+
+}  // namespace
+
+struct drt_scene {
+  int device = 0;
+  std::vector<drt_prim> prims; std::vector<drt_light> lights; int n_textures = 0;
+  bool any_glass = false;
+  DevScene<double> dd; DevScene<float> df;
+  std::vector<cudaArray_t> tex_arrays; std::vector<cudaTextureObject_t> tex_objs;
+  cudaTextureObject_t* d_tex = nullptr; int2* d_texdims = nullptr;
+  cudaStream_t stream = nullptr; cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // scratch, grown on demand
+  float4* samples = nullptr; size_t samples_cap = 0;
+  unsigned char* need = nullptr; float4* bg = nullptr; size_t corner_cap = 0;
+  unsigned char* out_u8 = nullptr; float* out_f32 = nullptr; size_t out_cap = 0;
+  Counts* counts = nullptr;
+};
+
+namespace {
+
+int flattenAndUpload(drt_scene* s) {
+  HostScene<double> hd; HostScene<float> hf;
+  int rc = flatten<double>(s->prims.data(), (int)s->prims.size(), s->lights.data(), (int)s->lights.size(), s->n_textures, hd);
+  if (rc) return rc;
+  rc = flatten<float>(s->prims.data(), (int)s->prims.size(), s->lights.data(), (int)s->lights.size(), s->n_textures, hf);
+  if (rc) return rc;
+  rc = upload(hd, s->dd); if (rc) return rc;
+  rc = upload(hf, s->df); if (rc) return rc;
+  s->any_glass = false;
+  for (const drt_prim& p : s->prims) if (p.material == DRT_MAT_GLASS) s->any_glass = true;
+  return DRT_OK;
+}
+
+struct CameraD { D3 eye, X, Y, Z; double mcam[12], new_mcam[12], cloud_mcam[12]; float t, b, r, l; };
+
+void rows3x4(double* out, const D3& r0, const D3& r1, const D3& r2, const D3& eye) {   // (cob * origin) rows, :1011-1021
+  const D3 rows[3] = {r0, r1, r2};
+  for (int i = 0; i < 3; i++) {
+    out[4 * i] = rows[i].x; out[4 * i + 1] = rows[i].y; out[4 * i + 2] = rows[i].z;
+    out[4 * i + 3] = (rows[i].x * -eye.x + rows[i].y * -eye.y) + (rows[i].z * -eye.z + 0.0);
+  }
+}
+
+int makeCamera(const drt_settings& st, CameraD& c) {                     // render_final_project.cpp:989-1027
+  D3 eye = V(st.eye), look = V(st.lookingAt), up = V(st.up);
+  c.eye = eye;
+  c.Z = -normalized(look - eye);
+  c.X = normalized(cross(up, c.Z));
+  if (!(dot(c.X, c.X) > 0)) return fail(DRT_ERR_SCENE, "Gaze direction can't be equal to up vector!!!");
+  c.Y = normalized(cross(c.Z, c.X));
+  D3 newX = mk<double>(0, 0, 0), newY = newX;
+  if (st.frame >= st.frame_cloud) {
+    D3 new_up = mk<double>(-1, 0, 0);
+    newX = normalized(cross(new_up, c.Z));
+    newY = normalized(cross(c.Z, newX));
+  }
+  rows3x4(c.mcam, c.X, c.Y, c.Z, eye);
+  rows3x4(c.new_mcam, newX, newY, c.Z, eye);
+  rows3x4(c.cloud_mcam, c.X, c.Y, -c.Z, eye);                           // renderImageCloud :1253-1259
+  c.t = (float)(tan((double)st.fov * M_PI / 360.0) * (double)fabsf(st.near_plane));
+  c.b = -c.t;
+  c.r = st.aspect * c.t;
+  c.l = -c.r;
+  return DRT_OK;
+}
+
+template <typename R>
+void fillParams(Params<R>& P, const drt_scene* s, const DevScene<R>& ds, const drt_settings& st, const CameraD& c, const drt_tile& tile) {
+  memset(&P, 0, sizeof(P));
+  P.eye = cv<R>(c.eye); P.X = cv<R>(c.X); P.Y = cv<R>(c.Y); P.Z = cv<R>(c.Z);
+  for (int i = 0; i < 12; i++) { P.mcam[i] = (R)c.mcam[i]; P.new_mcam[i] = (R)c.new_mcam[i]; P.cloud_mcam[i] = (R)c.cloud_mcam[i]; }
+  P.t = c.t; P.b = c.b; P.r = c.r; P.l = c.l;
+  P.near_plane = st.near_plane; P.focal_length = st.focal_length; P.aperture = st.aperture;
+  P.xRes = st.xRes; P.yRes = st.yRes;
+  P.n = (int)sqrt((double)st.antialias_samples);                        // :1046
+  P.spp = P.n * P.n;                                                    // :1061
+  P.antialias_samples = st.antialias_samples;
+  P.brdf_samples = st.brdf_samples; P.blur_samples = st.blur_samples; P.frame_range = st.frame_range; P.max_depth = st.max_depth;
+  P.reflect = st.reflect; P.nogloss = st.nogloss; P.perlin_cloud = st.perlin_cloud; P.cloud_only = st.cloud_only;
+  P.frame = st.frame; P.frame_prism = st.frame_prism; P.frame_blur = st.frame_blur; P.frame_cloud = st.frame_cloud;
+  P.move_per_frame = st.move_per_frame; P.accel_t = st.accel_t; P.refr_air = st.refr_air; P.refr_glass = st.refr_glass;
+  P.phong = st.phong; P.seed = st.seed; P.blur_mode = st.blur_mode;
+  P.sun = cv<R>(normalized(V(st.sundir)));
+  f3(P.sun_outer, st.sun_outer); f3(P.sun_inner, st.sun_inner); f3(P.sun_core, st.sun_core);
+  f3(P.bluesky, st.bluesky); f3(P.redsky, st.redsky);
+  P.saturation = st.saturation; P.clouddist = st.clouddist; P.cloudhoff = st.cloudhoff;
+  P.x0 = tile.x0; P.y0 = tile.y0; P.w = tile.width; P.h = tile.height;
+  P.geoms = ds.geoms; P.n_geoms = ds.n_geoms; P.prims = ds.prims; P.lights = ds.lights; P.n_lights = ds.n_lights;
+  P.tex = s->d_tex; P.texdims = s->d_texdims;
+}
+
+int ensureScratch(drt_scene* s, size_t n_samples, size_t n_corners, size_t n_out) {
+  if (n_samples > s->samples_cap) {
+    if (s->samples) cudaFree(s->samples);
+    s->samples = nullptr; s->samples_cap = 0;
+    CK(cudaMalloc(&s->samples, n_samples * sizeof(float4)));
+    s->samples_cap = n_samples;
+  }
+  if (n_corners > s->corner_cap) {
+    if (s->need) cudaFree(s->need);
+    if (s->bg) cudaFree(s->bg);
+    s->need = nullptr; s->bg = nullptr; s->corner_cap = 0;
+    CK(cudaMalloc(&s->need, n_corners));
+    CK(cudaMalloc(&s->bg, n_corners * sizeof(float4)));
+    s->corner_cap = n_corners;
+  }
+  if (n_out > s->out_cap) {
+    if (s->out_u8) cudaFree(s->out_u8);
+    if (s->out_f32) cudaFree(s->out_f32);
+    s->out_u8 = nullptr; s->out_f32 = nullptr; s->out_cap = 0;
+    CK(cudaMalloc(&s->out_u8, n_out));
+    CK(cudaMalloc(&s->out_f32, n_out * sizeof(float)));
+    s->out_cap = n_out;
+  }
+  if (!s->counts) CK(cudaMalloc(&s->counts, sizeof(Counts)));
+  return DRT_OK;
+}
+
+// samples held in HBM at once: 2^26 float4 = 1 GiB
+const long long kMaxChunkSamples = 1ll << 26;
+
+template <typename R>
+int launchAll(drt_scene* s, const DevScene<R>& ds, const drt_settings& st, const CameraD& cam, const drt_tile& tile,
+              bool want_f32, drt_counters* counters) {
+  Params<R> P;
+  fillParams<R>(P, s, ds, st, cam, tile);
+  const bool collect = counters && counters->collect;
+  const long long per_row = (long long)tile.width * P.spp;
+  int rows_per_chunk = st.cloud_only ? tile.height : (int)std::max<long long>(1, std::min<long long>(tile.height, kMaxChunkSamples / std::max<long long>(1, per_row)));
+  const size_t n_corners = (size_t)(tile.width + 1) * (tile.height + 1);
+  int rc = ensureScratch(s, st.cloud_only ? 1 : (size_t)rows_per_chunk * per_row, n_corners, (size_t)tile.width * tile.height * 3);
+  if (rc) return rc;
+  P.samples = s->samples; P.need = s->need; P.bg = s->bg; P.out_u8 = s->out_u8; P.out_f32 = want_f32 ? s->out_f32 : nullptr;
+  P.counts = collect ? s->counts : nullptr;
+  cudaStream_t q = s->stream;
+  int launches = 0;
+  if (collect) CK(cudaMemsetAsync(s->counts, 0, sizeof(Counts), q));
+  CK(cudaEventRecord(s->ev0, q));
+  if (st.perlin_cloud && !st.cloud_only) CK(cudaMemsetAsync(s->need, 0, n_corners, q));
+  const int corner_blocks = (int)((n_corners + 127) / 128);
+  if (st.cloud_only) {
+    cloud_corners<R><<<corner_blocks, 128, 0, q>>>(P); launches++;
+    resolve<R><<<(tile.width * tile.height + 255) / 256, 256, 0, q>>>(P, 0, tile.height); launches++;
+  } else {
+    for (int row0 = 0; row0 < tile.height; row0 += rows_per_chunk) {
+      const int rows = std::min(rows_per_chunk, tile.height - row0);
+      P.sample_base = (long long)row0 * per_row;
+      P.sample_count = (long long)rows * per_row;
+      const unsigned blocks = (unsigned)((P.sample_count + 127) / 128);
+      if (collect) render_samples<R, true><<<blocks, 128, 0, q>>>(P);
+      else render_samples<R, false><<<blocks, 128, 0, q>>>(P);
+      launches++;
+      if (st.perlin_cloud) { cloud_corners<R><<<corner_blocks, 128, 0, q>>>(P); launches++; }
+      resolve<R><<<(tile.width * rows + 255) / 256, 256, 0, q>>>(P, row0, rows); launches++;
+    }
+  }
+  CK(cudaEventRecord(s->ev1, q));
+  CK(cudaGetLastError());
+  if (counters) counters->kernel_launches = launches;
+  return DRT_OK;
+}
+
+int renderCommon(const drt_scene* cs, const drt_settings* st, const drt_tile* tile, float* out_f32, uint8_t* out_u8,
+                 drt_counters* counters, bool copy_back) {
+  drt_scene* s = const_cast<drt_scene*>(cs);
+  if (!s || !st || !tile) return fail(DRT_ERR_INVALID, "null argument");
+  if (tile->device != s->device) return fail(DRT_ERR_INVALID, "tile.device differs from the scene's device");
+  if (st->xRes < 1 || st->yRes < 1 || tile->width < 1 || tile->height < 1 || tile->x0 < 0 || tile->y0 < 0 ||
+      tile->x0 + tile->width > st->xRes || tile->y0 + tile->height > st->yRes)
+    return fail(DRT_ERR_INVALID, "tile outside the frame");
+  if (st->antialias_samples < 1) return fail(DRT_ERR_INVALID, "antialias_samples < 1");
+  if (st->sample_mode != DRT_SAMPLES_KEYED) return fail(DRT_ERR_UNSUPPORTED, "unknown sample_mode");
+  if (st->precision != DRT_PRECISION_REFERENCE && st->precision != DRT_PRECISION_FP32) return fail(DRT_ERR_INVALID, "unknown precision");
+  if (st->max_depth < 0 || st->max_depth > 32) return fail(DRT_ERR_UNSUPPORTED, "max_depth outside [0,32]");
+  {  // pending-ray stack bound: DFS over a tree with (brdf_samples [+1 for glass]) children per node
+    int fan = std::max(1, st->nogloss ? 1 : st->brdf_samples) + (s->any_glass ? 1 : 0);
+    if (st->brdf_samples < 1 || 1 + st->max_depth * (fan - 1) > DRT_STACK_MAX)
+      return fail(DRT_ERR_UNSUPPORTED, "brdf_samples * max_depth exceeds the per-thread ray stack");
+  }
+  CameraD cam;
+  int rc = makeCamera(*st, cam);
+  if (rc) return rc;
+  CK(cudaSetDevice(s->device));
+  const bool want_f32 = out_f32 != nullptr;
+  if (st->precision == DRT_PRECISION_FP32) rc = launchAll<float>(s, s->df, *st, cam, *tile, want_f32, counters);
+  else rc = launchAll<double>(s, s->dd, *st, cam, *tile, want_f32, counters);
+  if (rc) return rc;
+  const size_t n_out = (size_t)tile->width * tile->height * 3;
+  if (copy_back) {
+    if (out_u8) CK(cudaMemcpyAsync(out_u8, s->out_u8, n_out, cudaMemcpyDeviceToHost, s->stream));
+    if (out_f32) CK(cudaMemcpyAsync(out_f32, s->out_f32, n_out * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+  }
+  Counts hc; memset(&hc, 0, sizeof(hc));
+  const bool collect = counters && counters->collect;
+  if (collect) CK(cudaMemcpyAsync(&hc, s->counts, sizeof(Counts), cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  if (counters) {
+    float ms = 0; CK(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    counters->kernel_ms = ms;
+    if (collect) {
+      counters->samples = hc.samples; counters->rays = hc.rays; counters->shadow_rays = hc.shadow_rays;
+      counters->shade_evals = hc.shade_evals; counters->noise_evals = hc.noise_evals; counters->node_tests = 0;
+      for (int i = 0; i < DRT_PRIM_TYPE_COUNT; i++) counters->prim_tests[i] = 0;
+      counters->prim_tests[DRT_PRIM_SPHERE] = hc.geom_tests[G_SPHERE];
+      counters->prim_tests[DRT_PRIM_CYLINDER] = hc.geom_tests[G_CYL];
+      counters->prim_tests[DRT_PRIM_TRIANGLE] = hc.geom_tests[G_TRI];
+      counters->prim_tests[DRT_PRIM_RECTANGLE] = hc.geom_tests[G_RECT] + hc.geom_tests[G_CHECKER];   // rectangle tests incl. prism faces
+    }
+  }
+  return DRT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* drt_last_error(void) { return g_err.c_str(); }
+
+int drt_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+void drt_settings_default(drt_settings* s) {                            // render_final_project.cpp:48-138
+  memset(s, 0, sizeof(*s));
+  s->xRes = 1920; s->yRes = 1080;
+  s->eye[0] = -6; s->eye[1] = 0.5; s->eye[2] = 1;
+  s->lookingAt[0] = 0.5; s->lookingAt[1] = 0.5; s->lookingAt[2] = 1;
+  s->up[1] = 1;
+  s->aspect = (float)1920 / (float)1080; s->near_plane = 1; s->fov = 45.0f; s->aperture = 0.2f; s->focal_length = 10;
+  s->nogloss = 0; s->refr_air = 1; s->refr_glass = 1.5f; s->max_depth = 10; s->phong = 10;
+  s->antialias_samples = 10; s->brdf_samples = 2; s->blur_samples = 2; s->frame_range = 1;
+  s->frame_prism = 960; s->frame_cloud = 1952; s->frame_blur = 1600;
+  s->move_per_frame = (float)(0.1 / 8); s->accel_t = (float)(80 / pow(360, 3));
+  s->sundir[1] = 0.1; s->sundir[2] = -1;
+  s->perlin_cloud = 0; s->saturation = 0.2f; s->clouddist = 10; s->cloudhoff = 0.2f;
+  const double so[3] = {0.9, 0.3, 0.9}, si[3] = {1.0, 0.7, 0.7}, sc[3] = {1, 1, 1}, bs[3] = {0.3, 0.55, 0.8}, rs[3] = {0.8, 0.8, 0.6};
+  memcpy(s->sun_outer, so, sizeof(so)); memcpy(s->sun_inner, si, sizeof(si)); memcpy(s->sun_core, sc, sizeof(sc));
+  memcpy(s->bluesky, bs, sizeof(bs)); memcpy(s->redsky, rs, sizeof(rs));
+  s->reflect = 1;
+}
+
+void drt_prim_default(drt_prim* p) {                                    // geometry.h:39-57
+  memset(p, 0, sizeof(*p));
+  p->tex_frame = -1;
+}
+
+int drt_scene_create(const drt_scene_desc* d, int device, drt_scene** out) {
+  if (!d || !out) return fail(DRT_ERR_INVALID, "null argument");
+  if (d->abi_version != DRT_ABI_VERSION) return fail(DRT_ERR_INVALID, "ABI version mismatch");
+  if (d->n_prims < 1 || !d->prims) return fail(DRT_ERR_SCENE, "No shapes to render!");   // render_final_project.cpp:973-977
+  if (d->mesh) return fail(DRT_ERR_UNSUPPORTED, "triangle-mesh scenes are not built yet (SURVEY.md 8 row C5)");
+  int ndev = drt_device_count();
+  if (ndev < 1) return fail(DRT_ERR_NO_DEVICE, "no CUDA device: this library has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(DRT_ERR_INVALID, "device ordinal out of range");
+  CK(cudaSetDevice(device));
+  drt_scene* s = new drt_scene();
+  s->device = device;
+  s->prims.assign(d->prims, d->prims + d->n_prims);
+  if (d->n_lights > 0) s->lights.assign(d->lights, d->lights + d->n_lights);
+  s->n_textures = d->n_textures;
+  auto bail = [&](int rc) { drt_scene_destroy(s); return rc; };
+  if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&s->ev0) != cudaSuccess ||
+      cudaEventCreate(&s->ev1) != cudaSuccess)
+    return bail(fail(DRT_ERR_CUDA, "stream/event creation failed"));
+  // textures -> CUDA arrays + texture objects (point sampled, byte/255 as float)
+  std::vector<int2> dims;
+  for (int i = 0; i < d->n_textures; i++) {
+    const drt_texture& t = d->textures[i];
+    if (t.width < 1 || t.height < 1 || !t.rgb) return bail(fail(DRT_ERR_INVALID, "bad texture"));
+    std::vector<uchar4> rgba((size_t)t.width * t.height);
+    for (size_t k = 0; k < rgba.size(); k++) rgba[k] = make_uchar4(t.rgb[3 * k], t.rgb[3 * k + 1], t.rgb[3 * k + 2], 255);
+    cudaChannelFormatDesc cd = cudaCreateChannelDesc<uchar4>();
+    cudaArray_t arr = nullptr;
+    if (cudaMallocArray(&arr, &cd, t.width, t.height) != cudaSuccess) return bail(fail(DRT_ERR_CUDA, "cudaMallocArray failed"));
+    s->tex_arrays.push_back(arr);
+    if (cudaMemcpy2DToArray(arr, 0, 0, rgba.data(), (size_t)t.width * 4, (size_t)t.width * 4, t.height, cudaMemcpyHostToDevice) != cudaSuccess)
+      return bail(fail(DRT_ERR_CUDA, "texture upload failed"));
+    cudaResourceDesc rd; memset(&rd, 0, sizeof(rd)); rd.resType = cudaResourceTypeArray; rd.res.array.array = arr;
+    cudaTextureDesc td; memset(&td, 0, sizeof(td));
+    td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp; td.filterMode = cudaFilterModePoint;
+    td.readMode = cudaReadModeNormalizedFloat; td.normalizedCoords = 0;
+    cudaTextureObject_t to = 0;
+    if (cudaCreateTextureObject(&to, &rd, &td, nullptr) != cudaSuccess) return bail(fail(DRT_ERR_CUDA, "cudaCreateTextureObject failed"));
+    s->tex_objs.push_back(to);
+    dims.push_back(make_int2(t.width, t.height));
+  }
+  if (d->n_textures > 0) {
+    if (cudaMalloc(&s->d_tex, sizeof(cudaTextureObject_t) * d->n_textures) != cudaSuccess ||
+        cudaMalloc(&s->d_texdims, sizeof(int2) * d->n_textures) != cudaSuccess ||
+        cudaMemcpy(s->d_tex, s->tex_objs.data(), sizeof(cudaTextureObject_t) * d->n_textures, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(s->d_texdims, dims.data(), sizeof(int2) * d->n_textures, cudaMemcpyHostToDevice) != cudaSuccess)
+      return bail(fail(DRT_ERR_CUDA, "texture table upload failed"));
+  }
+  int rc = flattenAndUpload(s);
+  if (rc) return bail(rc);
+  *out = s;
+  return DRT_OK;
+}
+
+int drt_scene_update_prims(drt_scene* s, const drt_prim* prims, int32_t n_prims) {
+  if (!s || !prims) return fail(DRT_ERR_INVALID, "null argument");
+  if (n_prims != (int)s->prims.size()) return fail(DRT_ERR_INVALID, "primitive count changed");
+  for (int i = 0; i < n_prims; i++)
+    if (prims[i].type != s->prims[i].type) return fail(DRT_ERR_INVALID, "primitive type changed");
+  CK(cudaSetDevice(s->device));
+  CK(cudaStreamSynchronize(s->stream));
+  s->prims.assign(prims, prims + n_prims);
+  return flattenAndUpload(s);
+}
+
+void drt_scene_destroy(drt_scene* s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  if (s->stream) cudaStreamSynchronize(s->stream);
+  for (auto t : s->tex_objs) cudaDestroyTextureObject(t);
+  for (auto a : s->tex_arrays) cudaFreeArray(a);
+  void* ptrs[] = {s->dd.geoms, s->dd.prims, s->dd.lights, s->df.geoms, s->df.prims, s->df.lights, s->d_tex, s->d_texdims,
+                  s->samples, s->need, s->bg, s->out_u8, s->out_f32, s->counts};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  if (s->ev0) cudaEventDestroy(s->ev0);
+  if (s->ev1) cudaEventDestroy(s->ev1);
+  if (s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+}
+
+int drt_render(const drt_scene* scene, const drt_settings* settings, const drt_tile* tile, uint8_t* out_rgb, drt_counters* counters) {
+  if (!out_rgb) return fail(DRT_ERR_INVALID, "out_rgb is null");
+  return renderCommon(scene, settings, tile, nullptr, out_rgb, counters, true);
+}
+
+int drt_render_float(const drt_scene* scene, const drt_settings* settings, const drt_tile* tile, float* out_rgb_f32,
+                     uint8_t* out_rgb, drt_counters* counters) {
+  if (!out_rgb_f32 && !out_rgb) return fail(DRT_ERR_INVALID, "both outputs are null");
+  return renderCommon(scene, settings, tile, out_rgb_f32, out_rgb, counters, true);
+}
+
+int drt_render_device(const drt_scene* scene, const drt_settings* settings, const drt_tile* tile, drt_counters* counters) {
+  return renderCommon(scene, settings, tile, nullptr, nullptr, counters, false);
+}
+
+int drt_write_ppm(const char* filename, int32_t width, int32_t height, const uint8_t* rgb) {   // helpers.h:174-195
+  if (!filename || !rgb || width < 1 || height < 1) return fail(DRT_ERR_INVALID, "bad argument");
+  FILE* fp = fopen(filename, "wb");
+  if (!fp) return fail(DRT_ERR_INVALID, std::string("Could not open file \"") + filename + "\" for writing.");
+  fprintf(fp, "P6\n%d %d\n255\n", width, height);
+  fwrite(rgb, 1, (size_t)width * height * 3, fp);
+  fclose(fp);
+  return DRT_OK;
+}
+
+// struct sizes, for the ctypes mirror to verify its layout against
+void drt_abi_sizes(int32_t* out6) {
+  out6[0] = (int32_t)sizeof(drt_prim); out6[1] = (int32_t)sizeof(drt_light); out6[2] = (int32_t)sizeof(drt_scene_desc);
+  out6[3] = (int32_t)sizeof(drt_settings); out6[4] = (int32_t)sizeof(drt_tile); out6[5] = (int32_t)sizeof(drt_counters);
+}
+
+// Evaluates the device sample stream on the HOST copy of the same inline
+// functions (drt_rng.cuh) so tests can compare it with the oracle's copy.
+float drt_debug_rng(uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t child, uint32_t dim) {
+  uint32_t pk = rng_key_pixel(seed, pixel);
+  uint32_t sk = rng_key_sample(pk, sample);
+  return rng_u01(rng_key_child(sk, child), dim);
+}
+
+}  // extern "C"

@@ -1,0 +1,880 @@
+// CUDA kernels of the distributed ray-tracing hot path (sm_100a).
+//
+//   render_samples<R> : one thread per camera sample.  Replaces the sample loop of
+//       renderImage (render_final_project.cpp:1062-1212) and the whole recursive
+//       rayColor (487-961): camera ray with thin-lens DOF, closest-hit search over
+//       the flattened primitives, Fresnel refraction, mirror / glossy reflection
+//       lobes, per-light shadow rays (point / rectangle / sphere lights),
+//       Oren-Nayar / Cook-Torrance / Lambert+Phong shading, nearest-texel texture
+//       fetch through CUDA texture objects, emissive shapes, motion-blur re-traces.
+//       The recursion is an explicit per-thread stack of pending rays: every
+//       rayColor invocation only ever ADDS k-weighted radiance into the sample's
+//       colour, so the order the tree is walked in does not matter.
+//   cloud_corners<R>  : skyColor/cloudColor (146-192) + noise.h per PIXEL CORNER.
+//       getPerspEyeRay takes int pixel coordinates (helpers.h:320, quirk Q1), so
+//       every sample of a pixel that misses the scene asks for the same background
+//       colour; it is evaluated once per corner instead of once per sample.
+//   resolve           : sample average, clamp, *255, float->u8 truncation, y-flip
+//       (render_final_project.cpp:1213-1217 + helpers.h:174-195).
+#pragma once
+#include "drt_device.cuh"
+
+namespace drt {
+
+#define DRT_STACK_MAX 44
+
+template <typename R>
+struct Task {
+  Vec<R> org, dir;
+  float k;
+  uint32_t path;
+  short depth;
+  unsigned char chain;   // on the "last invocation" chain that decides in_motion (quirk Q4)
+  unsigned char pad_;
+};
+
+template <typename R>
+struct Moved {           // per-trace displacement state (motion blur)
+  float val;             // reference mode: y shift of "rectangle" shapes
+  R time;                // velocity mode: time offset
+  int velocity_mode;
+};
+
+template <typename R>
+__device__ inline Vec<R> shiftPoint(const Moved<R>& mv, int gflags, const Vec<R>& vel, Vec<R> p) {
+  if (mv.velocity_mode) return p + vel * mv.time;
+  if (gflags & GF_NAME_RECTANGLE) p.y += (R)mv.val;
+  return p;
+}
+
+// ---- rectangle tests: Rectangle::intersect / intersectShadow (geometry.cpp:640-741)
+template <typename R>
+__device__ inline bool rectHit(const Vec<R>& A, const Vec<R>& nrm, const Vec<R>& e1, const Vec<R>& e2, R rlen1, R rlen2,
+                               float eps, const Vec<R>& ray, const Vec<R>& start, float& t, float& c1o, float& c2o) {
+  float dn = (float)dot(ray, nrm);
+  if (dn == 0.0f) return false;
+  float t_final = (float)dot(A - start, nrm) / dn;
+  if (t_final <= eps) return false;
+  Vec<R> point = start + (R)t_final * ray;
+  Vec<R> V_hit = point - A;
+  float check1 = (float)dot(e1, V_hit);
+  float check2 = (float)dot(e2, V_hit);
+  // `check1 <= V1.norm()` compares a float with a double
+  if (0 <= check1 && (R)check1 <= rlen1 && 0 <= check2 && (R)check2 <= rlen2) {
+    t = t_final; c1o = check1; c2o = check2;
+    return true;
+  }
+  return false;
+}
+
+struct HitRec {
+  float t;
+  int geom;
+  int inside;
+  int checker_sel;  // 0: keep prim colour, 1: color1, 2: color2
+};
+
+// Closest hit over all flattened primitives (the candidate loop of rayColor,
+// render_final_project.cpp:522-538, with each class's intersect()).
+template <typename R, bool COUNT>
+__device__ inline void closestHit(const Params<R>& P, const Moved<R>& mv, const Vec<R>& ray, const Vec<R>& start,
+                                  HitRec& h, Counts& cnt) {
+  h.t = FLT_MAX; h.geom = -1; h.inside = 0; h.checker_sel = 0;
+  const int n = P.n_geoms;
+  for (int gi = 0; gi < n; gi++) {
+    const Geom<R>& g = P.geoms[gi];
+    const int type = g.type;
+    if (type == G_HOLE) continue;
+    if (COUNT) cnt.geom_tests[type]++;
+    float t_hit; int inside = 0; int sel = 0; bool ok = false;
+    if (type == G_RECT || type == G_CHECKER) {
+      Vec<R> A = shiftPoint(mv, g.flags, g.vel, g.p0);
+      if (type == G_CHECKER) {  // exact-zero edge path pinned to "no hit" (quirk Q17)
+        if (dot(g.p1, ray) == R(0)) continue;
+      }
+      float c1, c2;
+      ok = rectHit<R>(A, g.p1, g.p2, g.p3, g.len1, g.len2, g.eps, ray, start, t_hit, c1, c2);
+      if (ok && type == G_CHECKER) {
+        if (g.flags & GF_HAS_HOLE) {  // CheckerboardWithHole: inner Rectangle cancels the hit (geometry.cpp:2408-2414)
+          const Geom<R>& hgeo = P.geoms[gi + 1];
+          float th, d1, d2;
+          if (rectHit<R>(hgeo.p0, hgeo.p1, hgeo.p2, hgeo.p3, hgeo.len1, hgeo.len2, hgeo.eps, ray, start, th, d1, d2))
+            ok = false;
+        }
+        if (ok) {  // checker parity (geometry.cpp:2313-2337)
+          int i = (int)(c1 / g.f2);
+          int j = (int)(c2 / g.f2);
+          int pi = i % 2, pj = j % 2;
+          if (pi == 0) { if (pj == 0) sel = 1; if (pj == 1) sel = 2; }
+          if (pi == 1) { if (pj == 0) sel = 2; if (pj == 1) sel = 1; }
+        }
+      }
+    } else if (type == G_SPHERE) {  // Sphere::intersect geometry.cpp:106-140
+      Vec<R> sc = start - shiftPoint(mv, g.flags, g.vel, g.p0);
+      float A = (float)dot(ray, ray);
+      float B = (float)(R(2) * dot(ray, sc));
+      float C = (float)(dot(sc, sc) - (R)((double)g.f0 * (double)g.f0));
+      float disc = (float)((double)B * (double)B - (double)(4 * A * C));
+      if (disc < 0) continue;
+      float sq = sqrtf(disc);
+      float t0 = (-B + sq) / (2 * A);
+      float t1 = (-B - sq) / (2 * A);
+      if (t0 <= 0.001f && t1 <= 0.001f) continue;
+      else if (t0 <= 0.001f || t1 <= 0.001f) { t_hit = fmaxf(t0, t1); inside = 1; ok = true; }
+      else { t_hit = fminf(t0, t1); inside = 0; ok = true; }
+    } else if (type == G_CYL) {  // Cylinder::intersect geometry.cpp:242-295
+      const float eps = 1e-3f;
+      Vec<R> c1 = shiftPoint(mv, g.flags, g.vel, g.p0), c2 = shiftPoint(mv, g.flags, g.vel, g.p1);
+      const Vec<R> axis = g.p2;
+      Vec<R> ray_a_proj = ray - dot(ray, axis) * axis;
+      Vec<R> sc = start - c1;
+      Vec<R> constant = sc - dot(sc, axis) * axis;
+      float A = (float)dot(ray_a_proj, ray_a_proj);
+      float B = (float)(R(2) * dot(ray_a_proj, constant));
+      float C = (float)(dot(constant, constant) - (R)((double)g.f0 * (double)g.f0));
+      float disc = (float)((double)B * (double)B - (double)(4 * A * C));
+      if (!(disc >= 0)) continue;
+      float sq = sqrtf(disc);
+      float t1_body = (-B + sq) / (2 * A);
+      float t2_body = (-B - sq) / (2 * A);
+      if (t1_body <= eps && t2_body <= eps) continue;
+      float tc; int ins;
+      if (t1_body <= eps || t2_body <= eps) { tc = t1_body; ins = 1; } else { tc = t2_body; ins = 0; }
+      Vec<R> pt = start + (R)tc * ray;
+      if (dot(axis, pt - c1) > R(0) && dot(axis, pt - c2) < R(0)) { t_hit = tc; inside = ins; ok = true; }
+    } else {  // G_TRI: Triangle::intersect geometry.cpp:488-553
+      Vec<R> A = shiftPoint(mv, g.flags, g.vel, g.p0);
+      const Vec<R> r1 = g.p1, r2 = g.p2;
+      Vec<R> hh = cross(ray, r2);
+      float det = (float)dot(r1, hh);
+      float invdet = (float)(1.0 / (double)det);
+      if (det >= -0.0001f && det <= 0.0001f) continue;
+      Vec<R> A0 = start - A;
+      float u = (float)((double)invdet * (double)dot(A0, hh));   // float * double evaluates in double
+      if (u < 0 || u > 1) continue;
+      Vec<R> DA0 = cross(A0, r1);
+      float v = (float)((double)dot(ray, DA0) * (double)invdet);
+      if (v < 0 || u + v > 1) continue;
+      float t_final = (float)((double)dot(r2, DA0) * (double)invdet);
+      if (t_final > 0.0001f) {
+        if (g.flags & GF_MESH) { if (dot(ray, g.p3) > R(0)) inside = 1; }
+        t_hit = t_final; ok = true;
+      }
+    }
+    if (ok && t_hit < h.t) { h.t = t_hit; h.geom = gi; h.inside = inside; h.checker_sel = sel; }
+  }
+}
+
+// Any-hit for shadow rays (render_final_project.cpp:828-851 with each class's
+// intersectShadow).  `ray` is normalised, `start` already offset by 1e-3.
+template <typename R, bool COUNT>
+__device__ inline bool anyHit(const Params<R>& P, const Moved<R>& mv, const Vec<R>& ray, const Vec<R>& start,
+                              float t_max, int skip_owner, Counts& cnt) {
+  const int n = P.n_geoms;
+  for (int gi = 0; gi < n; gi++) {
+    const Geom<R>& g = P.geoms[gi];
+    const int type = g.type;
+    if (type == G_HOLE) continue;
+    if (g.owner == skip_owner) continue;   // an area light never shadows itself (832-837)
+    if (COUNT) cnt.geom_tests[type]++;
+    if (type == G_RECT || type == G_CHECKER) {
+      Vec<R> A = shiftPoint(mv, g.flags, g.vel, g.p0);
+      // Checkerboard inherits Rectangle::intersectShadow (eps 1e-4); CheckerboardWithHole
+      // has its own with eps 1e-3 (geometry.cpp:2446-2498)
+      float eps = (type == G_CHECKER && !(g.flags & GF_HAS_HOLE)) ? 1e-4f : g.eps;
+      float th, c1, c2;
+      if (rectHit<R>(A, g.p1, g.p2, g.p3, g.len1, g.len2, eps, ray, start, th, c1, c2) && th < t_max) {
+        if (g.flags & GF_HAS_HOLE) {
+          const Geom<R>& hgeo = P.geoms[gi + 1];
+          float t2, d1, d2;
+          if (rectHit<R>(hgeo.p0, hgeo.p1, hgeo.p2, hgeo.p3, hgeo.len1, hgeo.len2, hgeo.eps, ray, start, t2, d1, d2) &&
+              t2 < t_max)
+            continue;
+        }
+        return true;
+      }
+    } else if (type == G_SPHERE) {  // geometry.cpp:173-197
+      const float eps = 1e-3f;
+      Vec<R> sc = start - shiftPoint(mv, g.flags, g.vel, g.p0);
+      float A = (float)dot(ray, ray);
+      float B = (float)(R(2) * dot(ray, sc));
+      float C = (float)(dot(sc, sc) - (R)((double)g.f0 * (double)g.f0));
+      float disc = (float)((double)B * (double)B - (double)(4 * A * C));
+      if (disc < 0) continue;
+      float sq = sqrtf(disc);
+      float t0 = (-B + sq) / (2 * A);
+      float t1 = (-B - sq) / (2 * A);
+      if ((t0 <= eps || t0 >= t_max) && (t1 <= eps || t1 >= t_max)) continue;
+      return true;
+    } else if (type == G_CYL) {  // geometry.cpp:368-417
+      const float eps = 1e-3f;
+      Vec<R> c1 = shiftPoint(mv, g.flags, g.vel, g.p0), c2 = shiftPoint(mv, g.flags, g.vel, g.p1);
+      const Vec<R> axis = g.p2;
+      Vec<R> ray_a_proj = ray - dot(ray, axis) * axis;
+      Vec<R> sc = start - c1;
+      Vec<R> constant = sc - dot(sc, axis) * axis;
+      float A = (float)dot(ray_a_proj, ray_a_proj);
+      float B = (float)(R(2) * dot(ray_a_proj, constant));
+      float C = (float)(dot(constant, constant) - (R)((double)g.f0 * (double)g.f0));
+      float disc = (float)((double)B * (double)B - (double)(4 * A * C));
+      if (!(disc >= 0)) continue;
+      float sq = sqrtf(disc);
+      float t1_body = (-B + sq) / (2 * A);
+      float t2_body = (-B - sq) / (2 * A);
+      if ((t1_body <= eps || t1_body >= t_max) && (t2_body <= eps || t2_body >= t_max)) continue;
+      float tc = (t1_body <= eps || t2_body <= eps) ? t1_body : t2_body;
+      Vec<R> pt = start + (R)tc * ray;
+      if (dot(axis, pt - c1) > R(0) && dot(axis, pt - c2) < R(0) && tc < t_max) return true;
+    } else {  // G_TRI geometry.cpp:555-586
+      Vec<R> A = shiftPoint(mv, g.flags, g.vel, g.p0);
+      const Vec<R> r1 = g.p1, r2 = g.p2;
+      Vec<R> hh = cross(ray, r2);
+      float det = (float)dot(r1, hh);
+      float invdet = (float)(1.0 / (double)det);
+      if (det >= -0.0001f && det <= 0.0001f) continue;
+      Vec<R> A0 = start - A;
+      float u = (float)((double)invdet * (double)dot(A0, hh));
+      if (u < 0 || u > 1) continue;
+      Vec<R> DA0 = cross(A0, r1);
+      float v = (float)((double)dot(ray, DA0) * (double)invdet);
+      if (v < 0 || u + v > 1) continue;
+      float t_final = (float)((double)dot(r2, DA0) * (double)invdet);
+      if (t_final > 0.001f && t_final < t_max) return true;
+    }
+  }
+  return false;
+}
+
+// Rectangle::samplePoint (geometry.cpp:772-782)
+template <typename R>
+__device__ inline Vec<R> rectSample(const Vec<R>& A, const Vec<R>& B, const Vec<R>& D, uint32_t key, uint32_t dim) {
+  float x = rng_u01(key, dim);
+  float y = rng_u01(key, dim + 1);
+  return A + (R)x * (B - A) + (R)y * (D - A);
+}
+
+template <typename R>
+__device__ inline Vec<R> mulPoint(const R* m, const Vec<R>& p) {  // (M*(p,1)).head<3>(), 4-term sums as (a+b)+(c+d)
+  return mk<R>((m[0] * p.x + m[1] * p.y) + (m[2] * p.z + m[3]), (m[4] * p.x + m[5] * p.y) + (m[6] * p.z + m[7]),
+               (m[8] * p.x + m[9] * p.y) + (m[10] * p.z + m[11]));
+}
+
+template <typename R>
+__device__ inline Vec<R> eyeRay(const Params<R>& P, int i, int j) {  // getPerspEyeRay helpers.h:320-324
+  float su = P.l + (P.r - P.l) * i / P.xRes;
+  float sv = P.b + (P.t - P.b) * j / P.yRes;
+  return (R)su * P.X + (R)sv * P.Y - (R)P.near_plane * P.Z;
+}
+
+__device__ inline float powi_d(float x, int n) {  // pow(float, int) evaluates in double, result narrowed by the caller
+  return (float)pow((double)x, (double)n);
+}
+
+// One rayColor tree (render_final_project.cpp:487-961) rooted at (dir, org).
+// Returns the colour added, whether the ROOT ray hit anything, and in_motion.
+template <typename R, bool COUNT>
+__device__ void traceTree(const Params<R>& P, const Moved<R>& mv, const Vec<R>& root_dir, const Vec<R>& root_org,
+                          uint32_t root_path, Task<R>* stack, double (&color)[3], bool& root_hit, bool& in_motion,
+                          bool& aborted, Counts& cnt) {
+  int sp = 0;
+  stack[0].org = root_org; stack[0].dir = root_dir; stack[0].k = 1.0f; stack[0].path = root_path;
+  stack[0].depth = (short)P.max_depth; stack[0].chain = 1;
+  sp = 1;
+  root_hit = false; in_motion = false;
+  bool first = true;
+  while (sp > 0 && !aborted) {
+    Task<R> T = stack[--sp];
+    const bool is_root = first; first = false;
+    if (T.depth == 0) continue;                                         // :489
+    if (COUNT) cnt.rays++;
+    const Vec<R> ray = T.dir, eye = T.org;
+    const float k = T.k;
+    HitRec h;
+    closestHit<R, COUNT>(P, mv, ray, eye, h, cnt);
+    if (T.chain) in_motion = false;                                     // :519
+    if (h.geom < 0) continue;                                           // :541-544
+    if (is_root) root_hit = true;
+    const Geom<R>& g = P.geoms[h.geom];
+    const PrimD<R>& pr = P.prims[g.owner];
+    if (T.chain) in_motion = (pr.flags & 2) != 0;                       // DRT_FLAG_MOTION, :564
+
+    const Vec<R> isectP = eye + (R)h.t * ray;                           // :548
+    // ---- getNorm of the hit class ------------------------------------------------
+    Vec<R> normal;
+    if (pr.type == 0) {                                                 // Sphere geometry.cpp:199-204
+      Vec<R> nn = isectP - shiftPoint(mv, 0, pr.vel, pr.pA);
+      normal = nn / norm(nn);
+    } else if (pr.type == 1 || pr.type == 7) {                          // Cylinder geometry.cpp:419-425
+      Vec<R> pc = isectP - shiftPoint(mv, 0, pr.vel, pr.pA);
+      normal = normalized(pc - dot(pc, pr.pG) * pr.pG);
+    } else if (pr.type == 4) {                                          // RectPrismV2 geometry.cpp:863-920
+      const float eps = 1e-3f;
+      Vec<R> dA = normalized(isectP - shiftPoint(mv, 0, pr.vel, pr.pA));
+      Vec<R> dG = normalized(isectP - shiftPoint(mv, 0, pr.vel, pr.pG));
+      float pa_bot = fabsf((float)dot(dA, pr.n0)), pg_bot = fabsf((float)dot(dG, pr.n0));
+      float pa_right = fabsf((float)dot(dA, pr.n1)), pg_right = fabsf((float)dot(dG, pr.n1));
+      float pa_front = fabsf((float)dot(dA, pr.n2)), pg_front = fabsf((float)dot(dG, pr.n2));
+      if (pa_bot <= eps || pg_bot <= eps) normal = pr.n0;
+      else if (pa_right <= eps || pg_right <= eps) normal = pr.n1;
+      else if (pa_front <= eps || pg_front <= eps) normal = pr.n2;
+      else {
+        float min_side = fminf(fminf(fminf(pa_bot, pg_bot), fminf(pa_right, pg_right)), fminf(pa_front, pg_front));
+        if (pa_bot == min_side || pg_bot == min_side) normal = pr.n0;
+        else if (pa_right == min_side || pg_right == min_side) normal = pr.n1;
+        else normal = pr.n2;
+      }
+    } else {
+      normal = pr.n0;                                                   // Triangle / Rectangle family
+    }
+    const Vec<R> in = normalized(ray);
+    if (dot(in * R(1e4), normal) >= R(0)) normal = normal * R(-1);      // fixNorm geometry.cpp:17-24
+
+    float shape_color[3];
+    if (h.checker_sel == 1) { shape_color[0] = pr.color1[0]; shape_color[1] = pr.color1[1]; shape_color[2] = pr.color1[2]; }
+    else if (h.checker_sel == 2) { shape_color[0] = pr.color2[0]; shape_color[1] = pr.color2[1]; shape_color[2] = pr.color2[2]; }
+    else { shape_color[0] = pr.color[0]; shape_color[1] = pr.color[1]; shape_color[2] = pr.color[2]; }
+
+    // ---- reflection / refraction children (:574-769) ---------------------------
+    if (P.reflect && pr.material != 0) {
+      const float eps = 1e-3f;
+      const bool glossy = (pr.flags & 8) != 0;                          // DRT_FLAG_GLOSSY
+      float k_refl = 1, k_refr = 1;
+      int n_children = 0;        // children pushed for this node, in the reference's call order
+      int first_child = sp;
+      if (pr.material == 1) {                                           // glass :592-626
+        float cos_theta = (float)dot(normal, -in);
+        float sin_theta = (float)sqrt(1.0 - (double)cos_theta * (double)cos_theta);
+        float refr_1 = h.inside ? P.refr_glass : P.refr_air;
+        float refr_2 = h.inside ? P.refr_air : P.refr_glass;
+        double din = (double)dot(in, normal);
+        float rr = refr_1 / refr_2;
+        float int_refl_check = (float)(1.0 - (double)rr * (double)rr * (1.0 - din * din));   // helpers.h:286
+        if (!(int_refl_check < 0)) {
+          float s1 = rr * sin_theta;
+          float s2 = 1 / sin_theta;
+          Vec<R> out = (R)s1 * ((R)s2 * (in + normal * (R)cos_theta)) - (R)sqrtf(int_refl_check) * normal;
+          float gg = P.refr_glass / P.refr_air;
+          float cos_phi = (float)sqrt(1.0 - (double)gg * (double)gg * (1.0 - din * din));       // :619
+          // fresnel helpers.h:297-303
+          float rho_par = (P.refr_glass * cos_theta - P.refr_air * cos_phi) / (P.refr_glass * cos_theta + P.refr_air * cos_phi);
+          float rho_perp = (P.refr_air * cos_theta - P.refr_glass * cos_phi) / (P.refr_air * cos_theta + P.refr_glass * cos_phi);
+          k_refl = (float)(0.5 * ((double)rho_par * (double)rho_par + (double)rho_perp * (double)rho_perp));
+          k_refr = 1 - k_refl;
+          if (sp < DRT_STACK_MAX) {
+            Task<R>& c = stack[sp++];
+            c.org = isectP + in * (R)eps; c.dir = out; c.k = k_refr * k; c.path = rng_key_child(T.path, 0);
+            c.depth = T.depth - 1; c.chain = 0; n_children++;
+          }
+        }
+      }
+      Vec<R> refl_ray = in - (R(2) * dot(normal, in)) * normal;         // :628
+      R rdn = dot(refl_ray, normal);
+      if (rdn <= R(0)) { aborted = true; break; }                       // throws :631-638
+      if (rdn > (R)eps) {                                               // :641
+        if (glossy && !P.nogloss) {                                     // :644-762
+          Vec<R> gloss_ray = refl_ray * R(2);
+          const float length = 1, width = 0.5f;
+          Vec<R> length_vector = normalized(cross(gloss_ray, mk<R>(1, 0, 0)));
+          if (isZero(length_vector)) length_vector = cross(gloss_ray, mk<R>(0, 0, 1));
+          Vec<R> cc = gloss_ray + isectP;
+          Vec<R> p1 = (R)(length / 2) * length_vector + cc;
+          Vec<R> width_vector = normalized(cross(-gloss_ray, length_vector));
+          Vec<R> A = width_vector * (R)width / R(2) + p1;
+          Vec<R> B = A - length_vector * (R)length;
+          Vec<R> C = B - width_vector * (R)width;
+          Vec<R> D = A - width_vector * (R)width;
+          Vec<R> width_adj = width_vector;
+          if (dot(width_vector, normal) <= R(0)) width_adj = -width_adj;
+          Vec<R> length_adj = length_vector;
+          if (dot(length_vector, normal) <= R(0)) length_adj = -length_adj;
+          Vec<R> step = width_adj * R(0.1) + length_adj * R(0.1);
+          // the reference loops unboundedly (:697-712); 4096 steps of 0.1 bound a hang
+          for (int it = 0; it < 4096 && dot(A - isectP, normal) <= R(0); it++) A = A + width_adj * R(0.1) + length_adj * R(0.1);
+          for (int it = 0; it < 4096 && dot(B - isectP, normal) <= R(0); it++) B = B + width_adj * R(0.1) + length_adj * R(0.1);
+          for (int it = 0; it < 4096 && dot(C - isectP, normal) <= R(0); it++) C = C + width_adj * R(0.1) + length_adj * R(0.1);
+          for (int it = 0; it < 4096 && dot(D - isectP, normal) <= R(0); it++) D = D + width_adj * R(0.1) + length_adj * R(0.1);
+          (void)step; (void)C;
+          for (int i = 0; i < P.brdf_samples; i++) {                    // :715-761
+            int attempt = 0;
+            Vec<R> sample_refl = rectSample<R>(A, B, D, T.path, rng_dim_gloss(i, attempt)) - isectP;
+            int sample_limit = 10;
+            while (dot(sample_refl, normal) <= R(0)) {
+              if (sample_limit < 0) { aborted = true; break; }          // throws :724-740
+              float multiplier = (float)pow(2.0, (double)(11 - sample_limit));
+              gloss_ray = refl_ray * (R)multiplier;
+              length_vector = normalized(cross(gloss_ray, mk<R>(1, 0, 0)));
+              if (isZero(length_vector)) length_vector = cross(gloss_ray, mk<R>(0, 0, 1));
+              cc = gloss_ray + isectP;
+              p1 = (R)(length / 2) * length_vector + cc;
+              width_vector = normalized(cross(-gloss_ray, length_vector));
+              A = width_vector * (R)width / R(2) + p1;
+              B = A - length_vector * (R)length;
+              D = A - width_vector * (R)width;
+              attempt++;
+              sample_refl = rectSample<R>(A, B, D, T.path, rng_dim_gloss(i, attempt)) - isectP;
+              sample_limit--;
+            }
+            if (aborted) break;
+            if (sp < DRT_STACK_MAX) {
+              Task<R>& c = stack[sp++];
+              c.org = isectP + sample_refl * (R)eps; c.dir = sample_refl; c.k = k_refl * k / P.brdf_samples;
+              c.path = rng_key_child(T.path, 2 + i); c.depth = T.depth - 1; c.chain = 0; n_children++;
+            }
+          }
+          if (aborted) break;
+        } else {                                                        // mirror :765
+          if (sp < DRT_STACK_MAX) {
+            Task<R>& c = stack[sp++];
+            c.org = isectP + refl_ray * (R)eps; c.dir = refl_ray; c.k = k_refl * k; c.path = rng_key_child(T.path, 1);
+            c.depth = T.depth - 1; c.chain = 0; n_children++;
+          }
+        }
+      }
+      // the reference's LAST child call continues the in_motion chain (quirk Q4)
+      if (T.chain && n_children > 0) stack[first_child + n_children - 1].chain = 1;
+    }
+
+    // ---- local shading (:772-960) ------------------------------------------------
+    if (pr.flags & 1) {                                                 // hit a light shape :775-789
+      if (pr.name == 2) {                                               // spherelight
+        float hitdot = (float)dot(in, normalized(shiftPoint(mv, 0, pr.vel, pr.center) - isectP));
+        double f = 0.1 * pow((double)hitdot, 1.0) + 0.05 * pow((double)hitdot, 5.0) + 0.9;
+        for (int c = 0; c < 3; c++) color[c] += ((double)k * (double)shape_color[c]) * f;
+      }
+      if (pr.name == 3) {                                               // rectanglelight
+        float dist = (float)((double)(norm(isectP - pr.eA) + norm(isectP - pr.eB) + norm(isectP - pr.eC) + norm(isectP - pr.eD)) /
+                             (double)pr.e_den);
+        double f = 0.1 * pow((double)dist, 1.0) + 0.05 * pow((double)dist, 5.0) + 0.9;
+        for (int c = 0; c < 3; c++) color[c] += ((double)k * (double)shape_color[c]) * f;
+      }
+      continue;
+    }
+
+    const Vec<R> e = normalized(eye - isectP);                          // :795
+    int hits = 0;
+    double tmp_color[3] = {0, 0, 0};
+    bool early_return = false;
+    bool have_tex = false;
+    for (int li = 0; li < P.n_lights && !early_return; li++) {
+      const LightD<R>& L = P.lights[li];
+      // ---- sampleRay (:802) ---------------------------------------------------
+      Vec<R> sray;
+      if (L.type == 0) sray = L.center - isectP;                        // pointLight geometry.cpp:2751-2754
+      else if (L.type == 2) sray = rectSample<R>(L.A, L.B, L.D, T.path, rng_dim_light(li, 0)) - isectP;   // :2845-2849
+      else {                                                            // sphereLight geometry.cpp:2770-2826 (returns the POINT, Q10)
+        int attempt = 0;
+        double theta = 2 * DRT_PI * (double)rng_u01(T.path, rng_dim_light(li, attempt));
+        double phi = acos(1 - 2 * (double)rng_u01(T.path, rng_dim_light(li, attempt) + 1));
+        Vec<R> dirv = mk<R>((R)(sin(phi) * cos(theta)), (R)(sin(phi) * sin(theta)), (R)cos(phi));
+        Vec<R> tmp = (R)L.radius * dirv + L.center;
+        int sample_limit = 20;
+        const Vec<R> pc = isectP - L.center;
+        for (;;) {
+          Vec<R> d = tmp - L.center;
+          bool bad = dot(d, pc) < R(0) || (L.use_baxis && dot(d, L.baxis) < R(0));
+          if (!bad) break;
+          if (sample_limit < 0) { aborted = true; break; }              // throws geometry.cpp:2785-2789
+          Vec<R> rev = (R)(-L.radius) * dirv + L.center;
+          Vec<R> dr = rev - L.center;
+          bool ok = dot(dr, pc) >= R(0) && (!L.use_baxis || dot(dr, L.baxis) >= R(0));
+          if (ok) { tmp = rev; break; }
+          attempt++;
+          theta = 2 * DRT_PI * (double)rng_u01(T.path, rng_dim_light(li, attempt));
+          phi = acos(1 - 2 * (double)rng_u01(T.path, rng_dim_light(li, attempt) + 1));
+          dirv = mk<R>((R)(sin(phi) * cos(theta)), (R)(sin(phi) * sin(theta)), (R)cos(phi));
+          tmp = (R)L.radius * dirv + L.center;
+          sample_limit--;
+        }
+        if (aborted) break;
+        sray = tmp;
+      }
+      const float t_max = (float)norm(sray);                            // :804
+      const Vec<R> sdir = normalized(sray);
+      if (COUNT) cnt.shadow_rays++;
+      if (anyHit<R, COUNT>(P, mv, sdir, isectP + sdir * R(1e-3), t_max, L.prim_index, cnt)) continue;   // :828-855
+
+      // ---- texture (:859-893) ---------------------------------------------------
+      if (pr.flags & 4) {
+        float u = 0, v = 0; int type = 0;
+        if (pr.type == 3 || pr.type == 5 || pr.type == 4) {            // Rectangle::getUV (prism: top face)
+          Vec<R> uA = shiftPoint(mv, pr.name == 1 ? GF_NAME_RECTANGLE : 0, pr.vel, pr.uvA);
+          Vec<R> uD = shiftPoint(mv, pr.name == 1 ? GF_NAME_RECTANGLE : 0, pr.vel, pr.uvD);
+          u = (float)(norm(cross(isectP - uA, pr.uv_ad)) / pr.uv_den_u);
+          v = (float)(norm(cross(isectP - uD, pr.uv_dc)) / pr.uv_den_v);
+          type = 1;
+        } else if (pr.type == 6) {                                      // CheckerboardWithHole::getUV geometry.cpp:2500-2561
+          Vec<R> V_hit = isectP - pr.rA;
+          float check1 = (float)dot(pr.re1, V_hit), check2 = (float)dot(pr.re2, V_hit);
+          if (0 <= check1 && (R)check1 <= pr.rlen1 && 0 <= check2 && (R)check2 <= pr.rlen2) {
+            // hole->intersectShadow(VEC3(1,1,1), p - VEC3(1,1,1), FLT_MAX)
+            float th, d1, d2;
+            Vec<R> one = mk<R>(1, 1, 1);
+            bool in_hole;
+            {
+              const Vec<R> ray1 = one, start1 = isectP - one;
+              float dn = (float)dot(ray1, pr.hn);
+              in_hole = false;
+              if (dn != 0.0f) {
+                float t_final = (float)dot(pr.hA - start1, pr.hn) / dn;
+                if (!(t_final <= 1e-4f)) {
+                  Vec<R> point = start1 + (R)t_final * ray1;
+                  Vec<R> Vh = point - pr.hA;
+                  float k1 = (float)dot(pr.he1, Vh), k2 = (float)dot(pr.he2, Vh);
+                  if (0 <= k1 && (R)k1 <= pr.hlen1 && 0 <= k2 && (R)k2 <= pr.hlen2 && t_final < FLT_MAX) in_hole = true;
+                }
+              }
+              (void)th; (void)d1; (void)d2;
+            }
+            if (in_hole) type = 0;
+            else {
+              float gu = (float)(norm(cross(isectP - pr.uvA, pr.uv_ad)) / pr.uv_den_u);
+              float gv = (float)(norm(cross(isectP - pr.uvD, pr.uv_dc)) / pr.uv_den_v);
+              float miniu_dist = pr.S / pr.length;
+              float miniv_dist = pr.S / pr.width;
+              float miniu = gu / miniu_dist - (int)(gu / miniu_dist);
+              float miniv = gv / miniv_dist - (int)(gv / miniv_dist);
+              if (miniu < 0) miniu = 0;
+              if (miniv < 0) miniv = 0;
+              u = miniu; v = miniv;
+              float bw = pr.borderwidth / (2 * pr.S);
+              type = ((miniu <= bw || miniu >= 1 - bw) || (miniv <= bw || miniv >= 1 - bw)) ? 2 : 1;
+            }
+          } else type = 0;
+        } else if (pr.type == 2) {                                      // Triangle::getUV geometry.cpp:447-486
+          Vec<R> tA = shiftPoint(mv, 0, pr.vel, pr.tA), tB = shiftPoint(mv, 0, pr.vel, pr.tB), tC = shiftPoint(mv, 0, pr.vel, pr.tC);
+          Vec<R> nn = cross(tB - tA, tC - tA);
+          Vec<R> n_a = cross(tC - tB, isectP - tB), n_b = cross(tA - tC, isectP - tC);
+          float n_sq = (float)dot(nn, nn);
+          float alpha = (float)((double)dot(nn, n_a) / (double)n_sq);
+          float beta = (float)((double)dot(nn, n_b) / (double)n_sq);
+          float gamma = 1 - alpha - beta;
+          if (alpha < 0 || alpha > 1 || beta < 0 || beta > 1 || gamma < 0 || gamma > 1) type = 0;
+          else if (!(pr.flags & 32)) { aborted = true; break; }         // throws geometry.cpp:456-460
+          else {
+            u = (float)(((double)alpha * pr.tuv[0] + (double)beta * pr.tuv[2]) + (double)gamma * pr.tuv[4]);
+            v = (float)(((double)alpha * pr.tuv[1] + (double)beta * pr.tuv[3]) + (double)gamma * pr.tuv[5]);
+            // the reference compares the double UV against [0,1] before narrowing; equivalent here
+            type = 1;
+          }
+        } else if (pr.type == 7) {                                      // CheckerCylinder::getUV geometry.cpp:2588-2630
+          Vec<R> p_obj = mulPoint<R>(pr.objM, isectP);
+          float cu = 0;
+          if (isectP.x != R(0)) cu = (float)((atan2((double)p_obj.y, (double)p_obj.x) + DRT_PI) / (2 * DRT_PI));
+          float cv = (float)((double)p_obj.z / (double)pr.axis_norm);
+          float miniu_dist = (float)((double)pr.S / (2 * DRT_PI * (double)pr.radius));
+          float miniv_dist = (float)((double)pr.S / (double)pr.axis_norm);
+          float miniu = cu / miniu_dist - (int)(cu / miniu_dist);
+          float miniv = cv / miniv_dist - (int)(cv / miniv_dist);
+          if (miniu > 1 || miniu < 0 || miniv > 1 || miniv < 0) { aborted = true; break; }   // throws :2610-2614
+          u = miniu; v = miniv;
+          float bw = pr.borderwidth / (2 * pr.S);
+          type = ((miniu <= bw || miniu >= 1 - bw) || (miniv <= bw || miniv >= 1 - bw)) ? 2 : 1;
+        } else { aborted = true; break; }
+        if (type == 0) { early_return = true; break; }                  // quirk Q7 (:866-869)
+        if (u < 0 || v < 0 || u > 1 || v > 1) { aborted = true; break; }   // throws :870-877
+        if (type == 2) { shape_color[0] = pr.bordercolor[0]; shape_color[1] = pr.bordercolor[1]; shape_color[2] = pr.bordercolor[2]; }
+        else {
+          int2 dims = P.texdims[pr.tex];
+          int x_tex = (int)((dims.x - 1) * u);
+          int y_tex = (int)((dims.y - 1) * v);
+          float4 tx = tex2D<float4>(P.tex[pr.tex], x_tex + 0.5f, y_tex + 0.5f);   // nearest texel, byte/255
+          shape_color[0] = tx.x; shape_color[1] = tx.y; shape_color[2] = tx.z;
+        }
+        have_tex = true;
+      }
+      (void)have_tex;
+      if (COUNT) cnt.shade_evals++;
+      // ---- BRDF (:894-948) ---------------------------------------------------------
+      double ray_color[3];
+      if (pr.model == 1) {                                              // oren-nayar
+        float vn = (float)dot(e, normal);
+        float ln = (float)dot(sdir, normal);
+        float irradiance = fmaxf(0.0f, ln);
+        float vn_theta = acosf(vn);
+        float ln_theta = acosf(ln);
+        float angleDiff = (float)fmax(0.0, (double)dot(normalized(e - normal * (R)vn), normalized(sray - normal * (R)ln)));
+        float alpha = fmaxf(vn_theta, ln_theta);
+        float beta = fminf(vn_theta, ln_theta);
+        float f = pr.on_A + pr.on_B * angleDiff * sinf(alpha) * tanf(beta);
+        for (int c = 0; c < 3; c++) ray_color[c] = (((double)shape_color[c] * (double)L.color[c]) * (double)irradiance) * (double)f;
+      } else if (pr.model == 2) {                                       // cook-torrance
+        Vec<R> H = normalized(e + sray);                                // unnormalised sray (Q9)
+        float hn = (float)fmax(0.0, (double)dot(normal, H));
+        float vh = (float)dot(e, H);
+        float vn = (float)dot(e, normal);
+        float ln = (float)dot(sdir, normal);
+        float alpha = acosf(hn);
+        double r2 = (double)pr.roughness * (double)pr.roughness;
+        double ca = (double)cosf(alpha);
+        double ta = (double)(tanf(alpha) / pr.roughness);
+        float D = (float)(1.0 / (r2 * (ca * ca * ca * ca)) * exp(-(ta * ta)));
+        float G1 = (float)(2.0 * hn * vn / vh);
+        float G2 = (float)(2.0 * hn * ln / vh);
+        float G = fminf(1.0f, fminf(G1, G2));
+        float F = (float)((double)(pr.schlick_R0 + (1 - pr.schlick_R0)) + pow((double)(1 - vn), 5.0));   // helpers.h:316, Q8
+        float FDG = F * D * G;
+        double den = (double)(ln * vn) * DRT_PI;
+        float mx = fmaxf(0.0f, ln);
+        for (int c = 0; c < 3; c++) {
+          double sh = (0.4 * (double)L.color[c]) * (double)mx + ((0.8 * (double)L.color[c]) * (double)FDG) / den;
+          ray_color[c] = (double)shape_color[c] * sh;
+        }
+      } else if (pr.model == 3) {                                       // raw
+        for (int c = 0; c < 3; c++) ray_color[c] = shape_color[c];
+      } else {                                                          // Lambert + Phong :943-948
+        Vec<R> rr = normalized(R(-1) * sray + (R(2) * dot(normal, sray)) * normal);   // :856
+        double lam = fmax(0.0, (double)dot(normal, sdir));
+        double spec = pow(fmax(0.0, (double)dot(rr, e)), (double)P.phong);
+        for (int c = 0; c < 3; c++) {
+          double sh = (double)L.color[c] * lam + (double)L.color[c] * spec;
+          ray_color[c] = (double)shape_color[c] * sh;
+        }
+      }
+      // !ray_color.isApprox(0): exact-zero test; NaN counts as a hit (:950-954, Q6)
+      double sq = ray_color[0] * ray_color[0] + (ray_color[1] * ray_color[1] + ray_color[2] * ray_color[2]);
+      if (!(sq <= 0.0)) { hits++; for (int c = 0; c < 3; c++) tmp_color[c] += (double)k * ray_color[c]; }
+    }
+    if (aborted) break;
+    if (!early_return && hits > 0) for (int c = 0; c < 3; c++) color[c] += tmp_color[c] / hits;   // :956-959
+  }
+}
+
+// ---------------------------------------------------------------------------
+template <typename R, bool COUNT>
+__global__ void __launch_bounds__(128) render_samples(const __grid_constant__ Params<R> P) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= P.sample_count) return;
+  const long long gidx = P.sample_base + idx;          // pixel_in_tile * spp + s
+  const int s = (int)(gidx % P.spp);
+  const int pt = (int)(gidx / P.spp);
+  const int px = pt % P.w, py = pt / P.w;
+  const int x = P.x0 + px, y = P.y0 + py;
+
+  Counts cnt;
+  if (COUNT) { cnt.samples = 1; cnt.rays = 0; cnt.shadow_rays = 0; cnt.shade_evals = 0; cnt.noise_evals = 0;
+               for (int i = 0; i < 6; i++) cnt.geom_tests[i] = 0; }
+
+  const uint32_t pixel = (uint32_t)(y * P.xRes + x);
+  const uint32_t pkey = rng_key_pixel(P.seed, pixel);
+  const uint32_t skey = rng_key_sample(pkey, (uint32_t)s);
+
+  // lens sample (getDOFSamples :195-210); drawn per camera sample, see DESIGN.md
+  Vec<R> eye_sample = P.eye;
+  if (P.aperture > 0) {
+    float r = (float)((double)(P.aperture / 2) * (double)rng_u01(pkey, 4u * s));
+    float theta = (float)(2 * DRT_PI * (double)rng_u01(pkey, 4u * s + 1));
+    eye_sample = P.eye + (R)(r * cosf(theta)) * P.X + (R)(r * sinf(theta)) * P.Y;
+  }
+  // jitter (:1048-1056): computed, then truncated by getPerspEyeRay(int,int) (Q1)
+  const int ii = s / P.n, jj = s % P.n;
+  float adj_x = (float)((double)x + ((double)(float)ii + (double)rng_u01(pkey, 4u * s + 2)) / 9.0);
+  float adj_y = (float)((double)y + ((double)(float)jj + (double)rng_u01(pkey, 4u * s + 3)) / 9.0);
+  const int pi = (int)(double)adj_x, pj = (int)(double)adj_y;
+  const Vec<R> rayDir = eyeRay<R>(P, pi, pj);
+  const Vec<R> focalPoint = P.eye + (R)P.focal_length * rayDir;        // :1069
+  const Vec<R> dir = focalPoint - eye_sample;
+
+  Task<R> stack[DRT_STACK_MAX];
+  double color[3] = {0, 0, 0};
+  bool hit = false, motion = false, aborted = false;
+  Moved<R> mv; mv.val = 0; mv.time = 0; mv.velocity_mode = 0;
+  traceTree<R, COUNT>(P, mv, dir, eye_sample, rng_key_child(skey, 0), stack, color, hit, motion, aborted, cnt);
+
+  uint32_t flags = 0;
+  if (!hit && !aborted) {                                               // :1074-1094
+    color[0] = color[1] = color[2] = 0;                                 // default_col
+    if (P.perlin_cloud) {
+      int cx = pi - P.x0, cy = pj - P.y0;                               // pixel corner inside this tile's (w+1)x(h+1) grid
+      cx = min(max(cx, 0), P.w); cy = min(max(cy, 0), P.h);
+      flags |= SF_MISS | ((uint32_t)((cx - px) | ((cy - py) << 1)) << SF_CORNER_SHIFT);
+      if (P.need[cy * (P.w + 1) + cx] == 0) P.need[cy * (P.w + 1) + cx] = 1;   // benign race: all writers store 1
+    }
+  }
+  if (motion && !aborted) {                                             // :1095-1210
+    mv.velocity_mode = (P.blur_mode == 1);
+    for (int m = 0; m < P.blur_samples && !aborted; m++) {
+      float frame_sample = (float)((double)(float)P.frame + (double)rng_u01(skey, (uint32_t)m) * (double)P.frame_range);
+      float dt = frame_sample - (float)P.frame;
+      float val = 0;                                                    // uninitialised in the reference below frame_prism (Q16)
+      if (P.blur_mode == 0 && P.frame >= P.frame_prism) {
+        if (P.frame >= P.frame_blur) val = (float)((double)(P.move_per_frame * dt) + (double)P.accel_t * pow((double)dt, 3.0));
+        else val = P.move_per_frame * dt;
+      }
+      mv.val = val; mv.time = (R)((double)frame_sample - (double)P.frame);
+      double mc[3] = {0, 0, 0};
+      bool h2, m2;
+      traceTree<R, COUNT>(P, mv, dir, eye_sample, rng_key_child(skey, 1 + m), stack, mc, h2, m2, aborted, cnt);
+      color[0] += mc[0]; color[1] += mc[1]; color[2] += mc[2];
+    }
+    const double inv = (double)(P.blur_samples + 1);
+    color[0] /= inv; color[1] /= inv; color[2] /= inv;
+  }
+  if (aborted) flags |= SF_ABORT;
+  P.samples[idx] = make_float4((float)color[0], (float)color[1], (float)color[2], __uint_as_float(flags));
+
+  if (COUNT) {
+    atomicAdd(&P.counts->samples, cnt.samples); atomicAdd(&P.counts->rays, cnt.rays);
+    atomicAdd(&P.counts->shadow_rays, cnt.shadow_rays); atomicAdd(&P.counts->shade_evals, cnt.shade_evals);
+    for (int i = 0; i < 6; i++) if (cnt.geom_tests[i]) atomicAdd(&P.counts->geom_tests[i], cnt.geom_tests[i]);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// noise.h -- integer-hash value noise.  The 8 Smoothed3D taps of one
+// InterpolatedNoise3D call (noise.h:89-96) read a 4x4x4 block of lattice hashes;
+// they are hashed once (64 instead of 216 Noise3D calls per octave).
+__device__ inline double noise3D(int i_prime, int x, int y, int z) {   // noise.h:31-39, int32 wrap-around explicit
+  const int primes[10][3] = {{995615039, 600173719, 701464987}, {831731269, 162318869, 136250887},
+                             {174329291, 946737083, 245679977}, {362489573, 795918041, 350777237},
+                             {457025711, 880830799, 909678923}, {787070341, 177340217, 593320781},
+                             {405493717, 291031019, 391950901}, {458904767, 676625681, 424452397},
+                             {531736441, 939683957, 810651871}, {997169939, 842027887, 423882827}};
+  int n = (int)((double)(x + y * 57) + (double)z * 3249.0);
+  uint32_t un = (uint32_t)n;
+  un = (un << 13) ^ un;
+  uint32_t a = (uint32_t)primes[i_prime][0], b = (uint32_t)primes[i_prime][1], c = (uint32_t)primes[i_prime][2];
+  int t = (int)((un * (un * un * a + b) + c) & 0x7fffffffu);
+  return 1.0 - (double)t / 1073741823.0;
+}
+
+__device__ inline double cosInterp(double a, double b, double x) {     // noise.h:25-29
+  double f = (1 - cos(x * DRT_PI)) * 0.5;
+  return a * (1 - f) + b * f;
+}
+
+__device__ double interpolatedNoise3D(int ip, double x, double y, double z) {   // noise.h:81-107
+  int iX = (int)x; double fX = x - iX;
+  int iY = (int)y; double fY = y - iY;
+  int iZ = (int)z; double fZ = z - iZ;
+  // lattice block [iX-1, iX+2] x [iY-1, iY+2] x [iZ-1, iZ+2]
+  float lat[4][4][4];
+  for (int a = 0; a < 4; a++)
+    for (int b = 0; b < 4; b++)
+      for (int c = 0; c < 4; c++) lat[a][b][c] = (float)noise3D(ip, iX - 1 + a, iY - 1 + b, iZ - 1 + c);
+  const double alpha = 9.0 / 18, beta = 2.0 / (8 * 18), gamma = 4.0 / (6 * 18), delta = 3.0 / (12 * 18);
+  double v[2][2][2];
+  for (int dx = 0; dx < 2; dx++)
+    for (int dy = 0; dy < 2; dy++)
+      for (int dz = 0; dz < 2; dz++) {   // Smoothed3D(ip, iX+dx, iY+dy, iZ+dz), noise.h:51-70
+        double corners = 0, sides = 0, dg = 0;
+        for (int a = -1; a <= 1; a++)
+          for (int b = -1; b <= 1; b++)
+            for (int c = -1; c <= 1; c++) {
+              double val = lat[1 + dx + a][1 + dy + b][1 + dz + c];
+              int nz = (a != 0) + (b != 0) + (c != 0);
+              if (nz == 3) corners += val; else if (nz == 1) sides += val; else if (nz == 2) dg += val;
+            }
+        double center = lat[1 + dx][1 + dy][1 + dz];
+        v[dx][dy][dz] = alpha * center + beta * corners + gamma * sides + delta * dg;
+      }
+  double w3 = cosInterp(v[0][0][0], v[1][0][0], fX), w4 = cosInterp(v[0][1][0], v[1][1][0], fX);
+  double w1 = cosInterp(v[0][0][1], v[1][0][1], fX), w2 = cosInterp(v[0][1][1], v[1][1][1], fX);
+  double i1 = cosInterp(w3, w4, fY), i2 = cosInterp(w1, w2, fY);
+  return cosInterp(i1, i2, fZ);
+}
+
+__device__ double valueNoise3D(double x, double y, double z) {         // noise.h:124-136
+  double total = 0, frequency = 16, amplitude = 0.0625;
+  for (int i = 0; i < 4; ++i) {
+    frequency /= 2; amplitude /= 0.5;
+    total += interpolatedNoise3D(i % 10, x * frequency, y * frequency, z * frequency) * amplitude;
+  }
+  return total;
+}
+
+template <typename R>
+__device__ void cloudColor(const Params<R>& P, const Vec<R>& ray, float frame, double (&out)[3]) {   // :146-192
+  Vec<R> rnorm = normalized(ray);
+  float sundot = clampf((float)dot(rnorm, P.sun));
+  double sky[3], col[3];
+  double p1 = pow((double)sundot, 1.0), p2 = pow((double)sundot, 2.0), p256 = pow((double)sundot, 256.0), p8 = pow((double)sundot, 8.0);
+  for (int c = 0; c < 3; c++) {
+    double cc = (0.05 * P.sun_outer[c]) * p1 + (0.1 * P.sun_inner[c]) * p2 + (0.9 * P.sun_core[c]) * p256;
+    double sk = P.bluesky[c] * (1 - 1.5 * p8) + (P.redsky[c] * 1.5) * p8;
+    sky[c] = cc + sk * (1.0 - 0.8 * (double)rnorm.y);
+    col[c] = sky[c];
+  }
+  for (float z = P.clouddist; z > 0; z = (float)((double)z - 0.05)) {
+    double px = (double)z * (double)ray.x, py = (double)z * (double)ray.y, pz = (double)z * (double)ray.z;
+    float noise = (float)(0.7 * valueNoise3D(px, py, pz + (double)frame));
+    float clouddistance = (float)((py + (double)noise) + (double)P.cloudhoff);
+    if (clouddistance < 0) {
+      float density = clampf(fabsf(clouddistance));
+      double d4 = (double)density * 0.4;
+      double rev[3] = {sky[2], sky[1], sky[0]};
+      for (int c = 0; c < 3; c++) {
+        double cloudcolor = 1.0 - (double)density * rev[c];
+        col[c] = (1 - d4) * col[c] + d4 * cloudcolor;
+      }
+    }
+  }
+  for (int c = 0; c < 3; c++) {
+    double v = clampf((float)col[c]);
+    col[c] = 3 * pow(v, 2.0) - 2 * pow(v, 3.0);
+  }
+  double s = col[0] + (col[1] + col[2]);
+  for (int c = 0; c < 3; c++) out[c] = (double)(1 + P.saturation) * col[c] - (double)P.saturation * (0.33 * s);
+}
+
+// One thread per pixel corner of the tile's (w+1)x(h+1) grid.
+template <typename R>
+__global__ void __launch_bounds__(128) cloud_corners(const __grid_constant__ Params<R> P) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int gw = P.w + 1, gh = P.h + 1;
+  if (idx >= gw * gh) return;
+  if (!P.cloud_only && P.need[idx] != 1) return;   // 0: not wanted, 2: already computed by an earlier row chunk
+  const int cx = idx % gw, cy = idx / gw;
+  const int x = P.x0 + cx, y = P.y0 + cy;
+  const Vec<R> rayDir = eyeRay<R>(P, x, y);
+  Vec<R> point;
+  if (P.cloud_only) point = mulPoint<R>(P.cloud_mcam, rayDir + P.eye);             // renderImageCloud :1265-1268
+  else {
+    const Vec<R> focalPoint = P.eye + (R)P.focal_length * rayDir;
+    point = (P.frame >= P.frame_cloud) ? mulPoint<R>(P.new_mcam, focalPoint) : mulPoint<R>(P.mcam, focalPoint);   // :1079-1087
+  }
+  double c[3];
+  cloudColor<R>(P, point, (float)P.frame, c);
+  P.bg[idx] = make_float4((float)c[0], (float)c[1], (float)c[2], 0.f);
+  if (!P.cloud_only) P.need[idx] = 2;
+  if (P.counts) atomicAdd(&P.counts->noise_evals, 200ull);
+}
+
+// One thread per pixel: (:1213-1217) + writePPM's truncation (helpers.h:178-179).
+template <typename R>
+__global__ void __launch_bounds__(256) resolve(const __grid_constant__ Params<R> P, int row0, int rows) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= P.w * rows) return;
+  const int px = idx % P.w, py = row0 + idx / P.w;
+  double c[3] = {0, 0, 0};
+  bool aborted = false;
+  if (P.cloud_only) {
+    float4 b = P.bg[py * (P.w + 1) + px];
+    c[0] = b.x; c[1] = b.y; c[2] = b.z;
+  } else {
+    const float4* sp = P.samples + ((long long)(py - row0) * P.w + px) * P.spp;
+    for (int s = 0; s < P.spp; s++) {
+      float4 v = sp[s];
+      uint32_t f = __float_as_uint(v.w);
+      if (f & SF_ABORT) aborted = true;
+      if (f & SF_MISS) {
+        uint32_t corner = f >> SF_CORNER_SHIFT;
+        float4 b = P.bg[(py + (int)((corner >> 1) & 1)) * (P.w + 1) + px + (int)(corner & 1)];
+        v.x = b.x; v.y = b.y; v.z = b.z;
+      }
+      c[0] += (double)v.x; c[1] += (double)v.y; c[2] += (double)v.z;
+    }
+    c[0] /= P.spp; c[1] /= P.spp; c[2] /= P.spp;
+  }
+  float o[3];
+  for (int k = 0; k < 3; k++) o[k] = aborted ? 0.0f : clampf((float)c[k]) * 255.0f;
+  const size_t orow = (size_t)(P.h - 1 - py);                        // rows flipped :1215
+  const size_t oi = (orow * P.w + px) * 3;
+  if (P.out_f32) { P.out_f32[oi] = o[0]; P.out_f32[oi + 1] = o[1]; P.out_f32[oi + 2] = o[2]; }
+  for (int k = 0; k < 3; k++) {
+    // (unsigned char)float on x86-64: cvttss2si then low byte; NaN -> 0x80000000 -> 0
+    int iv = (o[k] == o[k]) ? (int)o[k] : 0;
+    P.out_u8[oi + k] = (unsigned char)iv;
+  }
+}
+
+}  // namespace drt

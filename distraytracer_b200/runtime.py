@@ -1,0 +1,128 @@
+"""ctypes binding of libdrt.so (include/drt.h).  Thin: every call goes straight
+to the C ABI.  If the CUDA library has not been built or there is no GPU, calls
+fail loudly -- there is no CPU fallback in this package.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdrt.so")
+_lib = None
+
+EXPORTS = [
+    "drt_device_count", "drt_settings_default", "drt_prim_default", "drt_scene_create", "drt_scene_update_prims",
+    "drt_scene_destroy", "drt_render", "drt_render_float", "drt_render_device", "drt_write_ppm", "drt_last_error",
+    "drt_abi_sizes", "drt_debug_rng",
+]
+
+
+class DrtError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"drt error {code}: {msg}")
+        self.code = code
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(nvcc, sm_100a).  distraytracer_b200 has no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        L.drt_last_error.restype = C.c_char_p
+        L.drt_device_count.restype = C.c_int
+        L.drt_settings_default.argtypes = [C.POINTER(abi.Settings)]
+        L.drt_prim_default.argtypes = [C.POINTER(abi.Prim)]
+        L.drt_scene_create.argtypes = [C.POINTER(abi.SceneDesc), C.c_int, C.POINTER(C.c_void_p)]
+        L.drt_scene_update_prims.argtypes = [C.c_void_p, C.POINTER(abi.Prim), C.c_int32]
+        L.drt_scene_destroy.argtypes = [C.c_void_p]
+        L.drt_scene_destroy.restype = None
+        L.drt_render.argtypes = [C.c_void_p, C.POINTER(abi.Settings), C.POINTER(abi.Tile), C.c_void_p, C.POINTER(abi.Counters)]
+        L.drt_render_float.argtypes = [C.c_void_p, C.POINTER(abi.Settings), C.POINTER(abi.Tile), C.c_void_p, C.c_void_p,
+                                       C.POINTER(abi.Counters)]
+        L.drt_render_device.argtypes = [C.c_void_p, C.POINTER(abi.Settings), C.POINTER(abi.Tile), C.POINTER(abi.Counters)]
+        L.drt_write_ppm.argtypes = [C.c_char_p, C.c_int32, C.c_int32, C.c_void_p]
+        L.drt_abi_sizes.argtypes = [C.POINTER(C.c_int32)]
+        L.drt_debug_rng.argtypes = [C.c_uint32] * 5
+        L.drt_debug_rng.restype = C.c_float
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise DrtError(rc, lib().drt_last_error().decode())
+
+
+def device_count():
+    return lib().drt_device_count()
+
+
+def default_settings():
+    s = abi.Settings()
+    lib().drt_settings_default(C.byref(s))
+    return s
+
+
+def default_prim():
+    p = abi.Prim()
+    lib().drt_prim_default(C.byref(p))
+    return p
+
+
+class DeviceScene:
+    """drt_scene handle: the scene resident in one GPU's HBM."""
+
+    def __init__(self, scene, device=0):
+        self.scene = scene
+        self.device = device
+        self._desc = scene.desc()
+        self.handle = C.c_void_p()
+        _check(lib().drt_scene_create(C.byref(self._desc), device, C.byref(self.handle)))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            lib().drt_scene_destroy(self.handle)
+            self.handle = None
+
+    __del__ = close
+
+    def update_prims(self, prims):
+        arr = (abi.Prim * len(prims))(*prims)
+        _check(lib().drt_scene_update_prims(self.handle, arr, len(prims)))
+
+    def _tile(self, settings, tile):
+        if tile is None:
+            return abi.Tile(0, 0, settings.xRes, settings.yRes, self.device)
+        return tile
+
+    def render(self, settings, tile=None, out=None, counters=None):
+        """drt_render: uint8 (h,w,3) in PPM row order, written into `out` (host) if given."""
+        tile = self._tile(settings, tile)
+        if out is None:
+            out = np.empty((tile.height, tile.width, 3), dtype=np.uint8)
+        _check(lib().drt_render(self.handle, C.byref(settings), C.byref(tile), out.ctypes.data,
+                                C.byref(counters) if counters is not None else None))
+        return out
+
+    def render_float(self, settings, tile=None, counters=None):
+        tile = self._tile(settings, tile)
+        f = np.empty((tile.height, tile.width, 3), dtype=np.float32)
+        u = np.empty((tile.height, tile.width, 3), dtype=np.uint8)
+        _check(lib().drt_render_float(self.handle, C.byref(settings), C.byref(tile), f.ctypes.data, u.ctypes.data,
+                                      C.byref(counters) if counters is not None else None))
+        return f, u
+
+    def render_device(self, settings, tile=None, counters=None):
+        tile = self._tile(settings, tile)
+        _check(lib().drt_render_device(self.handle, C.byref(settings), C.byref(tile),
+                                       C.byref(counters) if counters is not None else None))
+
+
+def write_ppm(path, rgb):
+    rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+    _check(lib().drt_write_ppm(path.encode(), rgb.shape[1], rgb.shape[0], rgb.ctypes.data))

@@ -187,6 +187,16 @@ typedef enum drt_sample_mode {
   DRT_SAMPLES_KEYED = 0
 } drt_sample_mode;
 
+typedef enum drt_precision {
+  /* double vectors + float scalars, expression by expression like the reference
+   * (SETTINGS.h:13 Real=double; geometry.cpp keeps its scalar temporaries in
+   * float).  B200's FP64 pipe runs at half the FP32 rate, which makes this the
+   * default: it is what parity is asserted on. */
+  DRT_PRECISION_REFERENCE = 0,
+  /* fp32 vectors and scalars */
+  DRT_PRECISION_FP32 = 1
+} drt_precision;
+
 typedef enum drt_blur_mode {
   DRT_BLUR_REFERENCE = 0, /* render_final_project.cpp:1095-1210: re-trace blur_samples
                            * times; primitives named "rectangle" move in y when
@@ -231,6 +241,7 @@ typedef struct drt_settings {
   int32_t sample_mode;         /* drt_sample_mode */
   int32_t blur_mode;           /* drt_blur_mode */
   int32_t cloud_only;          /* 1 = renderImageCloud (:1224-1279): noise-only frame */
+  int32_t precision;           /* drt_precision */
 } drt_settings;
 
 /* A rectangle of pixels of the xRes*yRes frame, rendered on one device.  x0,y0
@@ -300,6 +311,15 @@ int drt_write_ppm(const char* filename, int32_t width, int32_t height, const uin
 
 /* Thread-local message for the last non-OK status. */
 const char* drt_last_error(void);
+
+/* ---- diagnostics (used by the test-suite, harmless in production) ----------- */
+/* sizeof() of drt_prim, drt_light, drt_scene_desc, drt_settings, drt_tile,
+ * drt_counters, for language bindings to verify their struct layout. */
+void drt_abi_sizes(int32_t* out6);
+/* One uniform of the keyed sample stream: key = child `child` of the root path of
+ * camera sample `sample` of pixel `pixel`; evaluated on the host from the same
+ * inline functions the kernels use. */
+float drt_debug_rng(uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t child, uint32_t dim);
 
 #ifdef __cplusplus
 }
