@@ -10,7 +10,8 @@
 #include <vector>
 
 #include "../../include/drt.h"
-#include "drt_kernels.cuh"
+#include "drt_launch.h"
+#include "drt_bvh_order.h"
 
 using namespace drt;
 
@@ -65,8 +66,33 @@ void objMatrix(R* out, const D3& axis, const D3& c1) {   // buildCOB(axis) * ori
   }
 }
 
+// getBounds of each GeoPrimitive class (geometry.cpp:206-210, 427-431, 596-602, 761-770, 922-941)
+void primBounds(const drt_prim& p, double lo[3], double hi[3]) {
+  auto acc = [&](const double* v, bool first) {
+    for (int a = 0; a < 3; a++) { if (first || v[a] < lo[a]) lo[a] = v[a]; if (first || hi[a] < v[a]) hi[a] = v[a]; }
+  };
+  const float radius = (float)p.radius;
+  switch (p.type) {
+    case DRT_PRIM_SPHERE:
+      for (int a = 0; a < 3; a++) { lo[a] = p.center[a] - radius; hi[a] = p.center[a] + radius; }
+      break;
+    case DRT_PRIM_CYLINDER: case DRT_PRIM_CHECKER_CYLINDER:
+      for (int a = 0; a < 3; a++) {
+        lo[a] = std::min(p.c1[a] - radius, p.c2[a] - radius);
+        hi[a] = std::max(p.c1[a] + radius, p.c2[a] + radius);
+      }
+      break;
+    case DRT_PRIM_TRIANGLE: acc(p.A, true); acc(p.B, false); acc(p.C, false); break;
+    case DRT_PRIM_RECTPRISMV2:
+      acc(p.A, true); acc(p.B, false); acc(p.C, false); acc(p.D, false); acc(p.E, false); acc(p.F, false); acc(p.G, false); acc(p.H, false);
+      break;
+    default: acc(p.A, true); acc(p.B, false); acc(p.C, false); acc(p.D, false); break;
+  }
+}
+
 template <typename R>
 struct HostScene {
+  std::vector<NodeD<R>> nodes;
   std::vector<Geom<R>> geoms;
   std::vector<PrimD<R>> prims;
   std::vector<LightD<R>> lights;
@@ -75,7 +101,18 @@ struct HostScene {
 template <typename R>
 int flatten(const drt_prim* prims, int n_prims, const drt_light* lights, int n_lights, int n_textures, HostScene<R>& hs) {
   hs.geoms.clear(); hs.prims.clear(); hs.lights.clear();
-  for (int i = 0; i < n_prims; i++) {
+  hs.prims.assign(n_prims, PrimD<R>());
+  // geoms are emitted in the reference's candidate order so that ties of t between
+  // coplanar shapes resolve to the same shape (see drt_bvh_order.h)
+  std::vector<double> centers(3 * (size_t)n_prims);
+  for (int i = 0; i < n_prims; i++) for (int a = 0; a < 3; a++) centers[3 * i + a] = prims[i].center[a];
+  ReferenceBVH bvh;
+  bvh.build(centers.data(), n_prims, [&](int prim, double lo[3], double hi[3]) { primBounds(prims[prim], lo, hi); });
+  const std::vector<int>& order = bvh.order;
+  std::vector<int> geom_start(n_prims + 1, 0);   // first geom of the oi-th primitive in reference order
+  for (int oi = 0; oi < n_prims; oi++) {
+    const int i = order[oi];
+    geom_start[oi] = (int)hs.geoms.size();
     const drt_prim& p = prims[i];
     if (p.type < 0 || p.type >= DRT_PRIM_TYPE_COUNT)
       return fail(DRT_ERR_UNSUPPORTED, "primitive " + std::to_string(i) + ": unsupported type " + std::to_string(p.type));
@@ -160,7 +197,26 @@ int flatten(const drt_prim* prims, int n_prims, const drt_light* lights, int n_l
           hs.geoms.push_back(rectGeom<R>(G_RECT, i, 0, 1e-4f, makeRect(f[k][0], f[k][1], f[k][2], f[k][3]), 0.f, vel));
         break; }
     }
-    hs.prims.push_back(q);
+    hs.prims[i] = q;
+  }
+  geom_start[n_prims] = (int)hs.geoms.size();
+  hs.nodes.clear();
+  for (const RefNode& rn : bvh.nodes) {
+    NodeD<R> nd; memset(&nd, 0, sizeof(nd));
+    nd.lo = mk<R>((R)rn.lo[0], (R)rn.lo[1], (R)rn.lo[2]); nd.hi = mk<R>((R)rn.hi[0], (R)rn.hi[1], (R)rn.hi[2]);
+    nd.leaf = rn.leaf; nd.left = rn.left; nd.right = rn.right;
+    if (rn.leaf) { nd.first = geom_start[rn.first]; nd.count = geom_start[rn.first + rn.count] - nd.first; }
+    hs.nodes.push_back(nd);
+  }
+  {  // traversal stack bound: depth of the deepest leaf
+    std::vector<int> depth(bvh.nodes.size(), 0);
+    int maxd = 0;
+    for (size_t k = 0; k < bvh.nodes.size(); k++) {   // parents precede children in the node array
+      const RefNode& rn = bvh.nodes[k];
+      if (!rn.leaf) { depth[rn.left] = depth[k] + 1; depth[rn.right] = depth[k] + 1; }
+      maxd = std::max(maxd, depth[k]);
+    }
+    if (maxd + 2 > DRT_NODE_STACK) return fail(DRT_ERR_UNSUPPORTED, "reference BVH deeper than the traversal stack");
   }
   for (int i = 0; i < n_lights; i++) {
     const drt_light& l = lights[i];
@@ -179,8 +235,8 @@ int flatten(const drt_prim* prims, int n_prims, const drt_light* lights, int n_l
 
 template <typename R>
 struct DevScene {
-  Geom<R>* geoms = nullptr; PrimD<R>* prims = nullptr; LightD<R>* lights = nullptr;
-  int n_geoms = 0, n_prims = 0, n_lights = 0;
+  Geom<R>* geoms = nullptr; PrimD<R>* prims = nullptr; LightD<R>* lights = nullptr; NodeD<R>* nodes = nullptr;
+  int n_geoms = 0, n_prims = 0, n_lights = 0, n_nodes = 0;
 };
 
 template <typename R>
@@ -197,6 +253,12 @@ int upload(const HostScene<R>& hs, DevScene<R>& ds) {
     if (ds.lights) cudaFree(ds.lights);
     CK(cudaMalloc(&ds.lights, sizeof(LightD<R>) * std::max<size_t>(1, hs.lights.size())));
   }
+  if ((int)hs.nodes.size() != ds.n_nodes || !ds.nodes) {
+    if (ds.nodes) cudaFree(ds.nodes);
+    CK(cudaMalloc(&ds.nodes, sizeof(NodeD<R>) * std::max<size_t>(1, hs.nodes.size())));
+  }
+  ds.n_nodes = (int)hs.nodes.size();
+  CK(cudaMemcpy(ds.nodes, hs.nodes.data(), sizeof(NodeD<R>) * ds.n_nodes, cudaMemcpyHostToDevice));
   ds.n_geoms = (int)hs.geoms.size(); ds.n_prims = (int)hs.prims.size(); ds.n_lights = (int)hs.lights.size();
   if (ds.n_geoms) CK(cudaMemcpy(ds.geoms, hs.geoms.data(), sizeof(Geom<R>) * ds.n_geoms, cudaMemcpyHostToDevice));
   if (ds.n_prims) CK(cudaMemcpy(ds.prims, hs.prims.data(), sizeof(PrimD<R>) * ds.n_prims, cudaMemcpyHostToDevice));
@@ -290,7 +352,7 @@ void fillParams(Params<R>& P, const drt_scene* s, const DevScene<R>& ds, const d
   f3(P.bluesky, st.bluesky); f3(P.redsky, st.redsky);
   P.saturation = st.saturation; P.clouddist = st.clouddist; P.cloudhoff = st.cloudhoff;
   P.x0 = tile.x0; P.y0 = tile.y0; P.w = tile.width; P.h = tile.height;
-  P.geoms = ds.geoms; P.n_geoms = ds.n_geoms; P.prims = ds.prims; P.lights = ds.lights; P.n_lights = ds.n_lights;
+  P.geoms = ds.geoms; P.n_geoms = ds.n_geoms; P.nodes = ds.nodes; P.n_nodes = ds.n_nodes; P.prims = ds.prims; P.lights = ds.lights; P.n_lights = ds.n_lights;
   P.tex = s->d_tex; P.texdims = s->d_texdims;
 }
 
@@ -342,21 +404,17 @@ int launchAll(drt_scene* s, const DevScene<R>& ds, const drt_settings& st, const
   if (collect) CK(cudaMemsetAsync(s->counts, 0, sizeof(Counts), q));
   CK(cudaEventRecord(s->ev0, q));
   if (st.perlin_cloud && !st.cloud_only) CK(cudaMemsetAsync(s->need, 0, n_corners, q));
-  const int corner_blocks = (int)((n_corners + 127) / 128);
   if (st.cloud_only) {
-    cloud_corners<R><<<corner_blocks, 128, 0, q>>>(P); launches++;
-    resolve<R><<<(tile.width * tile.height + 255) / 256, 256, 0, q>>>(P, 0, tile.height); launches++;
+    launchCloudCorners<R>(P, q); launches++;
+    launchResolve<R>(P, 0, tile.height, q); launches++;
   } else {
     for (int row0 = 0; row0 < tile.height; row0 += rows_per_chunk) {
       const int rows = std::min(rows_per_chunk, tile.height - row0);
       P.sample_base = (long long)row0 * per_row;
       P.sample_count = (long long)rows * per_row;
-      const unsigned blocks = (unsigned)((P.sample_count + 127) / 128);
-      if (collect) render_samples<R, true><<<blocks, 128, 0, q>>>(P);
-      else render_samples<R, false><<<blocks, 128, 0, q>>>(P);
-      launches++;
-      if (st.perlin_cloud) { cloud_corners<R><<<corner_blocks, 128, 0, q>>>(P); launches++; }
-      resolve<R><<<(tile.width * rows + 255) / 256, 256, 0, q>>>(P, row0, rows); launches++;
+      launchRenderSamples<R>(P, collect, q); launches++;
+      if (st.perlin_cloud) { launchCloudCorners<R>(P, q); launches++; }
+      launchResolve<R>(P, row0, rows, q); launches++;
     }
   }
   CK(cudaEventRecord(s->ev1, q));
@@ -404,7 +462,7 @@ int renderCommon(const drt_scene* cs, const drt_settings* st, const drt_tile* ti
     counters->kernel_ms = ms;
     if (collect) {
       counters->samples = hc.samples; counters->rays = hc.rays; counters->shadow_rays = hc.shadow_rays;
-      counters->shade_evals = hc.shade_evals; counters->noise_evals = hc.noise_evals; counters->node_tests = 0;
+      counters->shade_evals = hc.shade_evals; counters->noise_evals = hc.noise_evals; counters->node_tests = hc.node_tests;
       for (int i = 0; i < DRT_PRIM_TYPE_COUNT; i++) counters->prim_tests[i] = 0;
       counters->prim_tests[DRT_PRIM_SPHERE] = hc.geom_tests[G_SPHERE];
       counters->prim_tests[DRT_PRIM_CYLINDER] = hc.geom_tests[G_CYL];
@@ -521,7 +579,7 @@ void drt_scene_destroy(drt_scene* s) {
   if (s->stream) cudaStreamSynchronize(s->stream);
   for (auto t : s->tex_objs) cudaDestroyTextureObject(t);
   for (auto a : s->tex_arrays) cudaFreeArray(a);
-  void* ptrs[] = {s->dd.geoms, s->dd.prims, s->dd.lights, s->df.geoms, s->df.prims, s->df.lights, s->d_tex, s->d_texdims,
+  void* ptrs[] = {s->dd.geoms, s->dd.prims, s->dd.lights, s->dd.nodes, s->df.geoms, s->df.prims, s->df.lights, s->df.nodes, s->d_tex, s->d_texdims,
                   s->samples, s->need, s->bg, s->out_u8, s->out_f32, s->counts};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (s->ev0) cudaEventDestroy(s->ev0);

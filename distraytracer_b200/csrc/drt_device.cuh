@@ -25,6 +25,8 @@
 #include "drt_rng.cuh"
 
 #define DRT_PI 3.14159265358979323846
+#define DRT_STACK_MAX 44   // per-thread pending-ray stack (drt_kernels.cuh)
+#define DRT_NODE_STACK 64  // per-thread BVH traversal stack (node indices)
 
 namespace drt {
 
@@ -75,6 +77,16 @@ struct alignas(16) Geom {
   R len1, len2, pad_;
 };
 
+// One BoundingVolume of the reference's tree (drt_bvh_order.h), 16-byte aligned.
+template <typename R>
+struct alignas(16) NodeD {
+  Vec<R> lo, hi;
+  int leaf;          // 1: geoms [first, first+count)
+  int first, count;
+  int left, right;
+  int pad_[3];
+};
+
 template <typename R>
 struct alignas(16) PrimD {
   int type, name, material, model, flags, tex;
@@ -112,7 +124,7 @@ struct alignas(16) LightD {
 };
 
 struct Counts {
-  unsigned long long samples, rays, shadow_rays, geom_tests[6], shade_evals, noise_evals;
+  unsigned long long samples, rays, shadow_rays, geom_tests[6], shade_evals, noise_evals, node_tests;
 };
 
 template <typename R>
@@ -138,6 +150,7 @@ struct Params {
   int x0, y0, w, h;
   // scene
   const Geom<R>* geoms; int n_geoms;
+  const NodeD<R>* nodes; int n_nodes;
   const PrimD<R>* prims;
   const LightD<R>* lights; int n_lights;
   const cudaTextureObject_t* tex; const int2* texdims;

@@ -21,7 +21,6 @@
 
 namespace drt {
 
-#define DRT_STACK_MAX 44
 
 template <typename R>
 struct Task {
@@ -67,6 +66,41 @@ __device__ inline bool rectHit(const Vec<R>& A, const Vec<R>& nrm, const Vec<R>&
   return false;
 }
 
+// BoundingVolume::intersect (geometry.cpp:2657-2740): slab test on the ray LINE,
+// accepted when tmax > 0.  Leaf boxes are widened in y by the motion-blur
+// displacement exactly as bumpBVH does (helpers.h:530-552; interior nodes are not).
+template <typename R>
+__device__ inline bool boxHit(const NodeD<R>& nd, const Vec<R>& ray, const Vec<R>& inv_ray, const Vec<R>& start,
+                              const Moved<R>& mv) {
+  R loy = nd.lo.y, hiy = nd.hi.y;
+  if (nd.leaf && !mv.velocity_mode) { loy -= (R)mv.val; hiy += (R)mv.val; }
+  float tmin, tmax;
+  if (isinf(inv_ray.x)) {
+    if (!(start.x >= nd.lo.x && start.x <= nd.hi.x)) return false;
+    tmin = FLT_MIN; tmax = FLT_MAX;
+  } else if (ray.x < R(0)) { tmin = (float)((nd.hi.x - start.x) * inv_ray.x); tmax = (float)((nd.lo.x - start.x) * inv_ray.x); }
+  else { tmin = (float)((nd.lo.x - start.x) * inv_ray.x); tmax = (float)((nd.hi.x - start.x) * inv_ray.x); }
+  float tymin, tymax;
+  if (isinf(inv_ray.y)) {
+    if (!(start.y >= loy && start.y <= hiy)) return false;
+    tymin = FLT_MIN; tymax = FLT_MAX;
+  } else if (ray.y < R(0)) { tymin = (float)((hiy - start.y) * inv_ray.y); tymax = (float)((loy - start.y) * inv_ray.y); }
+  else { tymin = (float)((loy - start.y) * inv_ray.y); tymax = (float)((hiy - start.y) * inv_ray.y); }
+  if (tmin > tymax || tymin > tmax) return false;
+  if (tymin > tmin) tmin = tymin;
+  if (tymax < tmax) tmax = tymax;
+  float tzmin, tzmax;
+  if (isinf(inv_ray.z)) {
+    if (!(start.z >= nd.lo.z && start.z <= nd.hi.z)) return false;
+    tzmin = FLT_MIN; tzmax = FLT_MAX;
+  } else if (ray.z < R(0)) { tzmin = (float)((nd.hi.z - start.z) * inv_ray.z); tzmax = (float)((nd.lo.z - start.z) * inv_ray.z); }
+  else { tzmin = (float)((nd.lo.z - start.z) * inv_ray.z); tzmax = (float)((nd.hi.z - start.z) * inv_ray.z); }
+  if (tmin > tzmax || tzmin > tmax) return false;
+  if (tzmin > tmin) tmin = tzmin;
+  if (tzmax < tmax) tmax = tzmax;
+  return tmax > 0;
+}
+
 struct HitRec {
   float t;
   int geom;
@@ -80,8 +114,17 @@ template <typename R, bool COUNT>
 __device__ inline void closestHit(const Params<R>& P, const Moved<R>& mv, const Vec<R>& ray, const Vec<R>& start,
                                   HitRec& h, Counts& cnt) {
   h.t = FLT_MAX; h.geom = -1; h.inside = 0; h.checker_sel = 0;
-  const int n = P.n_geoms;
-  for (int gi = 0; gi < n; gi++) {
+  int stack[DRT_NODE_STACK];
+  int sp = 0;
+  stack[sp++] = 0;
+  const Vec<R> inv_ray = mk<R>(R(1) / ray.x, R(1) / ray.y, R(1) / ray.z);   // ray.cwiseInverse() :499
+  while (sp > 0) {
+    const NodeD<R>& nd = P.nodes[stack[--sp]];
+    if (COUNT) cnt.node_tests++;
+    if (!boxHit<R>(nd, ray, inv_ray, start, mv)) continue;
+    if (!nd.leaf) { stack[sp++] = nd.left; stack[sp++] = nd.right; continue; }   // right child is popped first (:497-509)
+    const int g_end = nd.first + nd.count;
+    for (int gi = nd.first; gi < g_end; gi++) {
     const Geom<R>& g = P.geoms[gi];
     const int type = g.type;
     if (type == G_HOLE) continue;
@@ -162,16 +205,26 @@ __device__ inline void closestHit(const Params<R>& P, const Moved<R>& mv, const 
       }
     }
     if (ok && t_hit < h.t) { h.t = t_hit; h.geom = gi; h.inside = inside; h.checker_sel = sel; }
+    }
   }
 }
 
 // Any-hit for shadow rays (render_final_project.cpp:828-851 with each class's
 // intersectShadow).  `ray` is normalised, `start` already offset by 1e-3.
 template <typename R, bool COUNT>
-__device__ inline bool anyHit(const Params<R>& P, const Moved<R>& mv, const Vec<R>& ray, const Vec<R>& start,
-                              float t_max, int skip_owner, Counts& cnt) {
-  const int n = P.n_geoms;
-  for (int gi = 0; gi < n; gi++) {
+__device__ inline bool anyHit(const Params<R>& P, const Moved<R>& mv, const Vec<R>& gather_ray, const Vec<R>& gather_start,
+                              const Vec<R>& ray, const Vec<R>& start, float t_max, int skip_owner, Counts& cnt) {
+  int stack[DRT_NODE_STACK];
+  int sp = 0;
+  stack[sp++] = 0;
+  const Vec<R> inv_ray = mk<R>(R(1) / gather_ray.x, R(1) / gather_ray.y, R(1) / gather_ray.z);   // sray.cwiseInverse() :813
+  while (sp > 0) {
+    const NodeD<R>& nd = P.nodes[stack[--sp]];
+    if (COUNT) cnt.node_tests++;
+    if (!boxHit<R>(nd, gather_ray, inv_ray, gather_start, mv)) continue;
+    if (!nd.leaf) { stack[sp++] = nd.left; stack[sp++] = nd.right; continue; }
+    const int g_end = nd.first + nd.count;
+    for (int gi = nd.first; gi < g_end; gi++) {
     const Geom<R>& g = P.geoms[gi];
     const int type = g.type;
     if (type == G_HOLE) continue;
@@ -240,6 +293,7 @@ __device__ inline bool anyHit(const Params<R>& P, const Moved<R>& mv, const Vec<
       if (v < 0 || u + v > 1) continue;
       float t_final = (float)((double)dot(r2, DA0) * (double)invdet);
       if (t_final > 0.001f && t_final < t_max) return true;
+    }
     }
   }
   return false;
@@ -491,7 +545,10 @@ __device__ void traceTree(const Params<R>& P, const Moved<R>& mv, const Vec<R>& 
       const float t_max = (float)norm(sray);                            // :804
       const Vec<R> sdir = normalized(sray);
       if (COUNT) cnt.shadow_rays++;
-      if (anyHit<R, COUNT>(P, mv, sdir, isectP + sdir * R(1e-3), t_max, L.prim_index, cnt)) continue;   // :828-855
+      // candidates are gathered along the UNNORMALISED sray from isectP + sray*1e-3 (:814),
+      // occlusion is tested along the normalised one from isectP + s^*1e-3 (:838)
+      if (anyHit<R, COUNT>(P, mv, sray, isectP + sray * R(1e-3), sdir, isectP + sdir * R(1e-3), t_max, L.prim_index, cnt))
+        continue;                                                       // :828-855
 
       // ---- texture (:859-893) ---------------------------------------------------
       if (pr.flags & 4) {
@@ -651,7 +708,7 @@ __global__ void __launch_bounds__(128) render_samples(const __grid_constant__ Pa
   const int x = P.x0 + px, y = P.y0 + py;
 
   Counts cnt;
-  if (COUNT) { cnt.samples = 1; cnt.rays = 0; cnt.shadow_rays = 0; cnt.shade_evals = 0; cnt.noise_evals = 0;
+  if (COUNT) { cnt.samples = 1; cnt.rays = 0; cnt.shadow_rays = 0; cnt.shade_evals = 0; cnt.noise_evals = 0; cnt.node_tests = 0;
                for (int i = 0; i < 6; i++) cnt.geom_tests[i] = 0; }
 
   const uint32_t pixel = (uint32_t)(y * P.xRes + x);
@@ -715,6 +772,7 @@ __global__ void __launch_bounds__(128) render_samples(const __grid_constant__ Pa
   if (COUNT) {
     atomicAdd(&P.counts->samples, cnt.samples); atomicAdd(&P.counts->rays, cnt.rays);
     atomicAdd(&P.counts->shadow_rays, cnt.shadow_rays); atomicAdd(&P.counts->shade_evals, cnt.shade_evals);
+    atomicAdd(&P.counts->node_tests, cnt.node_tests);
     for (int i = 0; i < 6; i++) if (cnt.geom_tests[i]) atomicAdd(&P.counts->geom_tests[i], cnt.geom_tests[i]);
   }
 }
@@ -742,7 +800,7 @@ __device__ inline double cosInterp(double a, double b, double x) {     // noise.
   return a * (1 - f) + b * f;
 }
 
-__device__ double interpolatedNoise3D(int ip, double x, double y, double z) {   // noise.h:81-107
+__device__ inline double interpolatedNoise3D(int ip, double x, double y, double z) {   // noise.h:81-107
   int iX = (int)x; double fX = x - iX;
   int iY = (int)y; double fY = y - iY;
   int iZ = (int)z; double fZ = z - iZ;
@@ -773,7 +831,7 @@ __device__ double interpolatedNoise3D(int ip, double x, double y, double z) {   
   return cosInterp(i1, i2, fZ);
 }
 
-__device__ double valueNoise3D(double x, double y, double z) {         // noise.h:124-136
+__device__ inline double valueNoise3D(double x, double y, double z) {         // noise.h:124-136
   double total = 0, frequency = 16, amplitude = 0.0625;
   for (int i = 0; i < 4; ++i) {
     frequency /= 2; amplitude /= 0.5;

@@ -1,0 +1,17 @@
+// Launch wrappers.  The kernels are instantiated in two translation units so the
+// two precisions can be compiled with different floating-point contraction:
+//   drt_kernels_f64.cu  (R = double, "reference" precision)  -fmad=false
+//       The reference ran on x86-64 without FMA; several of its own scenes put
+//       area-light panels IN the ceiling plane, where shadow-ray plane tests
+//       divide two rounding residues (~1e-17) and the image is decided by the
+//       last bit.  With contraction off, CUDA's double +,-,*,/ and sqrt are the
+//       same IEEE operations in the same order, so those decisions match.
+//   drt_kernels_f32.cu  (R = float)                            default (FMA on)
+#pragma once
+#include "drt_device.cuh"
+
+namespace drt {
+template <typename R> void launchRenderSamples(const Params<R>& P, bool collect, cudaStream_t q);
+template <typename R> void launchCloudCorners(const Params<R>& P, cudaStream_t q);
+template <typename R> void launchResolve(const Params<R>& P, int row0, int rows, cudaStream_t q);
+}  // namespace drt
