@@ -1,0 +1,197 @@
+"""Scene builders for the BASELINE.json configurations, producing the POD scene of
+include/drt.h.  They play the role of the reference's build*() functions in scene.h
+for the synthetic benchmark configurations; parity fixtures for the reference's own
+scenes live in tests/golden/.
+"""
+import math
+import os
+
+import numpy as np
+
+from . import abi
+from .scene import Scene, load_fixture
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(_ROOT, "tests", "golden")
+
+
+def _v(dst, src):
+    dst[0], dst[1], dst[2] = float(src[0]), float(src[1]), float(src[2])
+
+
+def new_prim():
+    p = abi.Prim()
+    p.tex_frame = -1
+    return p
+
+
+def sphere(center, radius, color, material=abi.MAT_NONE, motion=False, model=abi.MODEL_LAMBERT):
+    """Sphere(c, r, col, material, in_motion, shader), geometry.cpp:94-104."""
+    p = new_prim()
+    p.type, p.material, p.model = abi.PRIM_SPHERE, material, model
+    p.flags = abi.FLAG_MOTION if motion else 0
+    _v(p.center, center); _v(p.color, color)
+    p.radius = float(np.float32(radius))
+    return p
+
+
+def cylinder(c1, c2, radius, color, material=abi.MAT_NONE, motion=False, model=abi.MODEL_LAMBERT):
+    """Cylinder(v1, v2, r, col, ...), geometry.cpp:227-240."""
+    p = new_prim()
+    p.type, p.material, p.model = abi.PRIM_CYLINDER, material, model
+    p.flags = abi.FLAG_MOTION if motion else 0
+    _v(p.c1, c1); _v(p.c2, c2); _v(p.color, color)
+    _v(p.center, (np.asarray(c1, float) + np.asarray(c2, float)) / 2)
+    p.radius = float(np.float32(radius))
+    return p
+
+
+def rectangle(a, b, c, d, color, material=abi.MAT_NONE, motion=False, tex_frame=-1, model=abi.MODEL_LAMBERT,
+              name=abi.NAME_RECTANGLE):
+    """Rectangle(a,b,c,d,col,material,in_motion,texframe,shader), geometry.cpp:621-638."""
+    p = new_prim()
+    p.type, p.name, p.material, p.model, p.tex_frame = abi.PRIM_RECTANGLE, name, material, model, tex_frame
+    p.flags = abi.FLAG_MOTION if motion else 0
+    for dst, src in ((p.A, a), (p.B, b), (p.C, c), (p.D, d)):
+        _v(dst, src)
+    _v(p.color, color)
+    _v(p.center, (np.asarray(a, float) + np.asarray(b, float) + np.asarray(c, float) + np.asarray(d, float)) / 4)
+    return p
+
+
+def rectangle_light(a, b, c, d, color, prim_index):
+    """rectangleLight(a,b,c,d,col), geometry.cpp:2828-2843: a Rectangle that is also a light."""
+    p = rectangle(a, b, c, d, color, name=abi.NAME_RECTANGLELIGHT)
+    p.flags |= abi.FLAG_LIGHT
+    l = abi.Light()
+    l.type, l.prim_index = abi.LIGHT_RECT, prim_index
+    _v(l.color, color); _v(l.center, p.center)
+    for dst, src in ((l.A, a), (l.B, b), (l.C, c), (l.D, d)):
+        _v(dst, src)
+    return p, l
+
+
+def point_light(center, color):
+    l = abi.Light()
+    l.type, l.prim_index = abi.LIGHT_POINT, -1
+    _v(l.center, center); _v(l.color, color)
+    return l
+
+
+def sphere_light(center, radius, color, prim_index):
+    """sphereLight(c, r, col), geometry.cpp:2756-2768."""
+    p = sphere(center, radius, color)
+    p.name = abi.NAME_SPHERELIGHT
+    p.flags |= abi.FLAG_LIGHT
+    l = abi.Light()
+    l.type, l.prim_index = abi.LIGHT_SPHERE, prim_index
+    _v(l.center, center); _v(l.color, color)
+    l.radius = float(np.float32(radius))
+    return p, l
+
+
+def triangle(a, b, c, color, material=abi.MAT_NONE, motion=False, model=abi.MODEL_LAMBERT, mesh_normal=None):
+    """Triangle(a,b,c,col,material,in_motion,shader), geometry.cpp:433-445; `mesh_normal` sets
+    GeoPrimitive::mesh / mesh_normal the way the scene builders do for closed meshes (scene.h:3994-3996)."""
+    p = new_prim()
+    p.type, p.material, p.model = abi.PRIM_TRIANGLE, material, model
+    p.flags = abi.FLAG_MOTION if motion else 0
+    for dst, src in ((p.A, a), (p.B, b), (p.C, c)):
+        _v(dst, src)
+    _v(p.color, color)
+    _v(p.center, (np.asarray(a, float) + np.asarray(b, float) + np.asarray(c, float)) / 3)
+    if mesh_normal is not None:
+        p.flags |= abi.FLAG_MESH
+        _v(p.mesh_normal, mesh_normal)
+    return p
+
+
+def glass_block(lo, hi, color=(1.0, 1.0, 1.0)):
+    """Closed axis-aligned block of 12 glass triangles with outward mesh normals."""
+    lo, hi = np.asarray(lo, float), np.asarray(hi, float)
+    c = [np.array([x, y, z]) for x in (lo[0], hi[0]) for y in (lo[1], hi[1]) for z in (lo[2], hi[2])]
+    quads = [((0, 1, 3, 2), (-1, 0, 0)), ((4, 6, 7, 5), (1, 0, 0)), ((0, 4, 5, 1), (0, -1, 0)),
+             ((2, 3, 7, 6), (0, 1, 0)), ((0, 2, 6, 4), (0, 0, -1)), ((1, 5, 7, 3), (0, 0, 1))]
+    tris = []
+    for (i0, i1, i2, i3), n in quads:
+        tris.append(triangle(c[i0], c[i1], c[i2], color, material=abi.MAT_GLASS, mesh_normal=n))
+        tris.append(triangle(c[i0], c[i2], c[i3], color, material=abi.MAT_GLASS, mesh_normal=n))
+    return tris
+
+
+def checkerboard(a, b, c, d, col1, col2, S, material=abi.MAT_NONE, model=abi.MODEL_LAMBERT):
+    """Checkerboard(a,b,c,d,col1,col2,S), geometry.cpp:2248-2267."""
+    p = rectangle(a, b, c, d, col1, material=material, model=model, name=abi.NAME_OTHER)
+    p.type = abi.PRIM_CHECKERBOARD
+    _v(p.color1, col1); _v(p.color2, col2)
+    p.S = float(np.float32(S))
+    return p
+
+
+# ---------------------------------------------------------------------------
+def config1():
+    """BASELINE config 1: `./render test checkertexture` (render_final_project.cpp:1840-1853,
+    scene.h:3052-3163) at 640x480, 1 spp.  The scene is the reference builder's own output
+    (tests/golden/checkertexture.npz, exported by oracle/ref_driver.cpp)."""
+    scene, settings, _ = load_fixture(os.path.join(GOLDEN, "checkertexture.npz"))
+    settings.xRes, settings.yRes, settings.antialias_samples, settings.aperture = 640, 480, 1, 0.0
+    return scene, settings
+
+
+def config2(xres=1920, yres=1080, spp=64):
+    """BASELINE config 2: the same scene at 1080p, 64 spp, with every distributed effect on:
+    depth of field (aperture 0.2, focal length 10), glossy reflection on the floor as well as
+    the doors, soft shadows from a rectangle light, Fresnel refraction through a glass sphere
+    (SURVEY.md 8d C2)."""
+    scene, settings = config1()
+    prims = [abi.copy_struct(p) for p in scene.prims]
+    lights = [abi.copy_struct(l) for l in scene.lights]
+    for p in prims:
+        if p.type == abi.PRIM_CHECKERBOARD_HOLE:
+            p.flags |= abi.FLAG_GLOSSY                           # floor->reflect_params.glossy = true
+    prims.extend(glass_block((2.2, 0.32, 0.7), (3.2, 1.3, 1.7)))
+    lp, ll = rectangle_light((-1.5, 9.0, -1.0), (3.5, 9.0, -1.0), (3.5, 9.0, 3.0), (-1.5, 9.0, 3.0), (1.0, 1.0, 1.0),
+                             prim_index=len(prims))
+    prims.append(lp)
+    lights.append(ll)
+    settings.xRes, settings.yRes, settings.antialias_samples = xres, yres, spp
+    settings.aperture, settings.focal_length = 0.2, 10.0
+    return Scene(prims, lights, scene.textures), settings
+
+
+def config3(xres=1920, yres=1080, spp=256):
+    """BASELINE config 3: Oren-Nayar spheres (buildSceneReflectance, scene.h:3668-3694) in front of
+    the value-noise cloud background (perlin_cloud), 1080p, 256 spp."""
+    scene, settings, _ = load_fixture(os.path.join(GOLDEN, "reflectance.npz"))
+    prims = [abi.copy_struct(p) for p in scene.prims]
+    for p in prims:
+        if p.model != abi.MODEL_OREN_NAYAR and p.material == abi.MAT_NONE:
+            p.model = abi.MODEL_OREN_NAYAR
+            p.roughness = float(np.float32(math.sqrt(0.2)))
+    settings.xRes, settings.yRes, settings.antialias_samples, settings.perlin_cloud = xres, yres, spp, 1
+    return Scene(prims, scene.lights, scene.textures), settings
+
+
+def config4_frame(frame, xres=1920, yres=1080, spp=16, bones=None):
+    """BASELINE config 4: mocap skeleton (29-30 bone cylinders, scene.h:637-659) over a
+    checkerboard floor with two sphere lights (buildSceneChkpt2 layout, scene.h:3557-3666),
+    bones flagged `motion` and given the velocity to their pose one frame later."""
+    scene, settings, _ = load_fixture(os.path.join(GOLDEN, "chkpt2_mocap.npz"))
+    if bones is None:
+        bones = np.load(os.path.join(GOLDEN, "mocap_bones_0_119.npy"))
+    f0 = int(frame) % bones.shape[0]
+    f1 = min(f0 + 1, bones.shape[0] - 1)
+    prims, k = [], 0
+    for p in scene.prims:
+        q = abi.copy_struct(p)
+        if q.type == abi.PRIM_CYLINDER:
+            c1, c2 = bones[f0, k, 0], bones[f0, k, 1]
+            n1, n2 = bones[f1, k, 0], bones[f1, k, 1]
+            _v(q.c1, c1); _v(q.c2, c2); _v(q.center, (c1 + c2) / 2)
+            _v(q.velocity, ((n1 + n2) - (c1 + c2)) / 2)
+            q.flags |= abi.FLAG_MOTION
+            k += 1
+        prims.append(q)
+    settings.xRes, settings.yRes, settings.antialias_samples = xres, yres, spp
+    settings.frame, settings.blur_mode, settings.blur_samples, settings.frame_range = int(frame), abi.BLUR_VELOCITY, 2, 1
+    return Scene(prims, scene.lights, scene.textures), settings

@@ -51,6 +51,8 @@ class Ref:
         L.drtref_render_cloud.argtypes = [C.c_char_p, C.c_float]
         L.drtref_render_loop.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32,
                                          C.POINTER(C.c_float), C.POINTER(C.c_uint8), C.POINTER(C.c_double)]
+        L.drtref_render_loop_x.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32,
+                                           C.POINTER(C.c_float), C.POINTER(C.c_uint8), C.POINTER(C.c_double)]
         L.drtref_rng_mode.argtypes = [C.c_int, C.c_uint32, C.c_uint32]
         L.drtref_mocap_bones.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_int]
         if asset_root is None and os.path.isdir(REFERENCE_ROOT):
@@ -112,7 +114,7 @@ class Ref:
             self._check(self.lib.drtref_render_cloud(p.encode(), float(frame)))
             return read_ppm(p)
 
-    def render_loop(self, frame=0, y0=0, y1=None, reset_policy=1, seed=0):
+    def render_loop(self, frame=0, y0=0, y1=None, reset_policy=1, seed=0, x0=0, x1=None):
         """Pixel-loop restatement over the reference's rayColor.  Returns
         (float32 (rows,xRes,3) in PPM row order (top row first),
          bool (rows,xRes) mask of pixels where the reference itself aborts, seconds)."""
@@ -122,9 +124,11 @@ class Ref:
         out = np.zeros(((y1 - y0), s.xRes, 3), dtype=np.float32)
         ab = np.zeros(((y1 - y0), s.xRes), dtype=np.uint8)
         sec = C.c_double()
-        self._check(self.lib.drtref_render_loop(int(frame), y0, y1, reset_policy, seed,
-                                                out.ctypes.data_as(C.POINTER(C.c_float)),
-                                                ab.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(sec)))
+        if x1 is None:
+            x1 = s.xRes
+        self._check(self.lib.drtref_render_loop_x(int(frame), x0, x1, y0, y1, reset_policy, seed,
+                                                  out.ctypes.data_as(C.POINTER(C.c_float)),
+                                                  ab.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(sec)))
         return out[::-1].copy(), ab[::-1].astype(bool), sec.value
 
     def mocap_bones(self, frame, max_bones=64):
@@ -135,7 +139,9 @@ class Ref:
 
 def quantize(img_f32):
     """writePPM's float -> unsigned char truncation (helpers.h:178-179)."""
-    return np.asarray(img_f32, dtype=np.float32).astype(np.uint8)
+    a = np.asarray(img_f32, dtype=np.float32)
+    # (unsigned char)NaN on x86-64 is the low byte of cvttss2si's 0x80000000 = 0
+    return np.where(np.isnan(a), np.float32(0), a).astype(np.uint8)
 
 
 ORACLE_KEYED, ORACLE_STREAM = 0, 1

@@ -465,7 +465,13 @@ int drtref_render_cloud(const char* path, float frame) {
 //        exactly as stored into ppmOut (:1215-1217).
 //   aborted: (y1-y0)*xRes bytes, 1 where the reference itself throws/terminates
 //        while shading the pixel (its output there is undefined; `out` gets 0).
+int drtref_render_loop_x(int frame, int x0, int x1, int y0, int y1, int reset_policy, uint32_t seed, float* out, uint8_t* aborted, double* seconds);
 int drtref_render_loop(int frame, int y0, int y1, int reset_policy, uint32_t seed, float* out, uint8_t* aborted, double* seconds) {
+  return drtref_render_loop_x(frame, 0, xRes, y0, y1, reset_policy, seed, out, aborted, seconds);
+}
+// Same, restricted to columns [x0,x1) (out/aborted stay full-width buffers; untouched
+// columns keep their previous contents).  Lets the timing harness hand out sub-row tasks.
+int drtref_render_loop_x(int frame, int x0, int x1, int y0, int y1, int reset_policy, uint32_t seed, float* out, uint8_t* aborted, double* seconds) {
   QuietCout q;
   try {
     if (shapes.size() < 1) return fail(-5, "No shapes to render!");
@@ -499,7 +505,7 @@ int drtref_render_loop(int frame, int y0, int y1, int reset_policy, uint32_t see
     clock_gettime(CLOCK_MONOTONIC, &ts0);
     std::terminate_handler old_handler = std::set_terminate(onTerminate);
     for (int y = y0; y < y1; y++) {
-      for (int x = 0; x < xRes; x++) {
+      for (int x = x0; x < x1; x++) {
         float* o = out + 3 * ((size_t)(y - y0) * xRes + x);
         uint8_t* ab = aborted + ((size_t)(y - y0) * xRes + x);
         *ab = 0;
