@@ -3,6 +3,7 @@
 // computed by the kernels in drt_kernels.cuh.  There is no CPU fallback.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -42,6 +43,23 @@ RectD makeRect(const D3& A, const D3& B, const D3& C, const D3& D) {
   return r;
 }
 
+// padded single-precision bounds for the slab filter (drt_kernels.cuh slabMayHit)
+template <typename R>
+void setBounds(Geom<R>& g, const D3* pts, int n, double extra) {
+  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+  for (int i = 0; i < n; i++) {
+    const double v[3] = {pts[i].x, pts[i].y, pts[i].z};
+    for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], v[a] - extra); hi[a] = std::max(hi[a], v[a] + extra); }
+  }
+  float fl[3], fh[3];
+  for (int a = 0; a < 3; a++) {
+    const double pad = 1e-3 + 1e-5 * std::max(std::fabs(lo[a]), std::fabs(hi[a]));
+    fl[a] = std::nextafterf((float)(lo[a] - pad), -INFINITY);
+    fh[a] = std::nextafterf((float)(hi[a] + pad), INFINITY);
+  }
+  g.blo = make_float4(fl[0], fl[1], fl[2], 0.f); g.bhi = make_float4(fh[0], fh[1], fh[2], 0.f);
+}
+
 template <typename R>
 Geom<R> rectGeom(int type, int owner, int flags, float eps, const RectD& r, float S, const D3& vel) {
   Geom<R> g; memset(&g, 0, sizeof(g));
@@ -49,6 +67,9 @@ Geom<R> rectGeom(int type, int owner, int flags, float eps, const RectD& r, floa
   g.p0 = cv<R>(r.A); g.p1 = cv<R>(r.nrm); g.p2 = cv<R>(r.e1); g.p3 = cv<R>(r.e2);
   g.len1 = (R)r.len1; g.len2 = (R)r.len2; g.f0 = (float)r.len1; g.f1 = (float)r.len2; g.f2 = S;
   g.vel = cv<R>(vel);
+  const D3 u = r.e1 * r.len1, v = r.e2 * r.len2;
+  const D3 pts[4] = {r.A, r.A + u, r.A + v, r.A + u + v};
+  setBounds(g, pts, 4, 0.0);
   return g;
 }
 
@@ -145,6 +166,7 @@ int flatten(const drt_prim* prims, int n_prims, const drt_light* lights, int n_l
         q.pA = cv<R>(V(p.center));
         Geom<R> g; memset(&g, 0, sizeof(g));
         g.type = G_SPHERE; g.owner = i; g.flags = 0; g.p0 = cv<R>(V(p.center)); g.f0 = (float)p.radius; g.vel = cv<R>(vel);
+        { const D3 pts[1] = {V(p.center)}; setBounds(g, pts, 1, (double)(float)p.radius); }
         hs.geoms.push_back(g);
         break; }
       case DRT_PRIM_CYLINDER: case DRT_PRIM_CHECKER_CYLINDER: {
@@ -154,6 +176,7 @@ int flatten(const drt_prim* prims, int n_prims, const drt_light* lights, int n_l
         if (p.type == DRT_PRIM_CHECKER_CYLINDER) objMatrix<R>(q.objM, axis, c1);
         Geom<R> g; memset(&g, 0, sizeof(g));
         g.type = G_CYL; g.owner = i; g.p0 = cv<R>(c1); g.p1 = cv<R>(c2); g.p2 = cv<R>(axis); g.f0 = (float)p.radius; g.vel = cv<R>(vel);
+        { const D3 pts[2] = {c1, c2}; setBounds(g, pts, 2, (double)(float)p.radius); }
         hs.geoms.push_back(g);
         break; }
       case DRT_PRIM_TRIANGLE: {
@@ -164,6 +187,7 @@ int flatten(const drt_prim* prims, int n_prims, const drt_light* lights, int n_l
         Geom<R> g; memset(&g, 0, sizeof(g));
         g.type = G_TRI; g.owner = i; g.flags = (p.flags & DRT_FLAG_MESH) ? GF_MESH : 0;
         g.p0 = cv<R>(A); g.p1 = cv<R>(B - A); g.p2 = cv<R>(C - A); g.p3 = cv<R>(V(p.mesh_normal)); g.vel = cv<R>(vel);
+        { const D3 pts[3] = {A, B, C}; setBounds(g, pts, 3, 0.0); }
         hs.geoms.push_back(g);
         break; }
       case DRT_PRIM_RECTANGLE: case DRT_PRIM_CHECKERBOARD: case DRT_PRIM_CHECKERBOARD_HOLE: {
@@ -205,8 +229,14 @@ int flatten(const drt_prim* prims, int n_prims, const drt_light* lights, int n_l
     NodeD<R> nd; memset(&nd, 0, sizeof(nd));
     nd.lo = mk<R>((R)rn.lo[0], (R)rn.lo[1], (R)rn.lo[2]); nd.hi = mk<R>((R)rn.hi[0], (R)rn.hi[1], (R)rn.hi[2]);
     nd.leaf = rn.leaf; nd.left = rn.left; nd.right = rn.right;
+    nd.parent = -1;
     if (rn.leaf) { nd.first = geom_start[rn.first]; nd.count = geom_start[rn.first + rn.count] - nd.first; }
     hs.nodes.push_back(nd);
+  }
+  for (size_t k = 0; k < hs.nodes.size(); k++) {
+    NodeD<R>& nd = hs.nodes[k];
+    if (nd.leaf) { for (int gi = nd.first; gi < nd.first + nd.count; gi++) hs.geoms[gi].leaf = (int)k; }
+    else { hs.nodes[nd.left].parent = (int)k; hs.nodes[nd.right].parent = (int)k; }
   }
   {  // traversal stack bound: depth of the deepest leaf
     std::vector<int> depth(bvh.nodes.size(), 0);
@@ -281,6 +311,9 @@ struct drt_scene {
   unsigned char* need = nullptr; float4* bg = nullptr; size_t corner_cap = 0;
   unsigned char* out_u8 = nullptr; float* out_f32 = nullptr; size_t out_cap = 0;
   Counts* counts = nullptr;
+  void* pool = nullptr; size_t pool_cap = 0;
+  unsigned long long* batch_counter = nullptr; int* overflow = nullptr;
+  int wave_blocks_f64 = 0, wave_blocks_f32 = 0;
 };
 
 namespace {
@@ -380,6 +413,8 @@ int ensureScratch(drt_scene* s, size_t n_samples, size_t n_corners, size_t n_out
     s->out_cap = n_out;
   }
   if (!s->counts) CK(cudaMalloc(&s->counts, sizeof(Counts)));
+  if (!s->batch_counter) CK(cudaMalloc(&s->batch_counter, sizeof(unsigned long long)));
+  if (!s->overflow) { CK(cudaMalloc(&s->overflow, sizeof(int))); CK(cudaMemset(s->overflow, 0, sizeof(int))); }
   return DRT_OK;
 }
 
@@ -399,6 +434,16 @@ int launchAll(drt_scene* s, const DevScene<R>& ds, const drt_settings& st, const
   if (rc) return rc;
   P.samples = s->samples; P.need = s->need; P.bg = s->bg; P.out_u8 = s->out_u8; P.out_f32 = want_f32 ? s->out_f32 : nullptr;
   P.counts = collect ? s->counts : nullptr;
+  int& wave_blocks = sizeof(R) == 8 ? s->wave_blocks_f64 : s->wave_blocks_f32;
+  if (!wave_blocks) wave_blocks = waveGridBlocks<R>();
+  const size_t pool_bytes = wavePoolBytes<R>(wave_blocks);
+  if (!st.cloud_only && pool_bytes > s->pool_cap) {
+    if (s->pool) cudaFree(s->pool);
+    s->pool = nullptr; s->pool_cap = 0;
+    CK(cudaMalloc(&s->pool, pool_bytes));
+    s->pool_cap = pool_bytes;
+  }
+  P.pool_raw = s->pool; P.batch_counter = s->batch_counter; P.overflow = s->overflow;
   cudaStream_t q = s->stream;
   int launches = 0;
   if (collect) CK(cudaMemsetAsync(s->counts, 0, sizeof(Counts), q));
@@ -412,7 +457,8 @@ int launchAll(drt_scene* s, const DevScene<R>& ds, const drt_settings& st, const
       const int rows = std::min(rows_per_chunk, tile.height - row0);
       P.sample_base = (long long)row0 * per_row;
       P.sample_count = (long long)rows * per_row;
-      launchRenderSamples<R>(P, collect, q); launches++;
+      CK(cudaMemsetAsync(s->batch_counter, 0, sizeof(unsigned long long), q));
+      launchRenderSamples<R>(P, collect, wave_blocks, q); launches++;
       if (st.perlin_cloud) { launchCloudCorners<R>(P, q); launches++; }
       launchResolve<R>(P, row0, rows, q); launches++;
     }
@@ -435,10 +481,11 @@ int renderCommon(const drt_scene* cs, const drt_settings* st, const drt_tile* ti
   if (st->sample_mode != DRT_SAMPLES_KEYED) return fail(DRT_ERR_UNSUPPORTED, "unknown sample_mode");
   if (st->precision != DRT_PRECISION_REFERENCE && st->precision != DRT_PRECISION_FP32) return fail(DRT_ERR_INVALID, "unknown precision");
   if (st->max_depth < 0 || st->max_depth > 32) return fail(DRT_ERR_UNSUPPORTED, "max_depth outside [0,32]");
-  {  // pending-ray stack bound: DFS over a tree with (brdf_samples [+1 for glass]) children per node
-    int fan = std::max(1, st->nogloss ? 1 : st->brdf_samples) + (s->any_glass ? 1 : 0);
-    if (st->brdf_samples < 1 || 1 + st->max_depth * (fan - 1) > DRT_STACK_MAX)
-      return fail(DRT_ERR_UNSUPPORTED, "brdf_samples * max_depth exceeds the per-thread ray stack");
+  {  // warp ray-pool bound: LIFO over trees with (brdf_samples [+1 for glass]) children per node
+    const int lobes = std::max(1, st->nogloss ? 1 : st->brdf_samples);
+    const int fan = lobes + (s->any_glass ? 1 : 0);
+    if (st->brdf_samples < 1 || fan > DRT_MAX_CHILDREN || 64 + 32 * (1 + st->max_depth * (fan - 1)) > DRT_POOL_CAP)
+      return fail(DRT_ERR_UNSUPPORTED, "brdf_samples * max_depth exceeds the per-warp ray pool");
   }
   CameraD cam;
   int rc = makeCamera(*st, cam);
@@ -580,7 +627,7 @@ void drt_scene_destroy(drt_scene* s) {
   for (auto t : s->tex_objs) cudaDestroyTextureObject(t);
   for (auto a : s->tex_arrays) cudaFreeArray(a);
   void* ptrs[] = {s->dd.geoms, s->dd.prims, s->dd.lights, s->dd.nodes, s->df.geoms, s->df.prims, s->df.lights, s->df.nodes, s->d_tex, s->d_texdims,
-                  s->samples, s->need, s->bg, s->out_u8, s->out_f32, s->counts};
+                  s->samples, s->need, s->bg, s->out_u8, s->out_f32, s->counts, s->pool, s->batch_counter, s->overflow};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);

@@ -25,7 +25,6 @@
 #include "drt_rng.cuh"
 
 #define DRT_PI 3.14159265358979323846
-#define DRT_STACK_MAX 44   // per-thread pending-ray stack (drt_kernels.cuh)
 #define DRT_NODE_STACK 64  // per-thread BVH traversal stack (node indices)
 
 namespace drt {
@@ -75,6 +74,9 @@ struct alignas(16) Geom {
   float f0, f1, f2, f3;
   Vec<R> vel;   // DRT_BLUR_VELOCITY displacement per unit time
   R len1, len2, pad_;
+  float4 blo, bhi;   // padded single-precision bounds for the slab filter
+  int leaf;          // reference BVH leaf holding this geom
+  int pad2_[3];
 };
 
 // One BoundingVolume of the reference's tree (drt_bvh_order.h), 16-byte aligned.
@@ -84,7 +86,8 @@ struct alignas(16) NodeD {
   int leaf;          // 1: geoms [first, first+count)
   int first, count;
   int left, right;
-  int pad_[3];
+  int parent;        // -1 at the root
+  int pad_[2];
 };
 
 template <typename R>
@@ -163,6 +166,9 @@ struct Params {
   Counts* counts;           // nullptr unless collecting
   long long sample_base;    // first (pixel*spp+s) index handled by this launch (row chunking)
   long long sample_count;
+  void* pool_raw;           // per-warp ray pools (Task<R>[DRT_POOL_CAP] each)
+  unsigned long long* batch_counter;
+  int* overflow;
 };
 
 // sample flag bits stored in samples[].w

@@ -18,18 +18,23 @@
 //       (render_final_project.cpp:1213-1217 + helpers.h:174-195).
 #pragma once
 #include "drt_device.cuh"
+#include "drt_launch.h"
 
 namespace drt {
 
 
 template <typename R>
-struct Task {
+struct alignas(16) Task {
   Vec<R> org, dir;
   float k;
   uint32_t path;
+  float val;             // reference-mode blur: y shift of "rectangle" shapes for this trace
+  float dt;              // time offset of this trace (0 for the primary trace)
   short depth;
   unsigned char chain;   // on the "last invocation" chain that decides in_motion (quirk Q4)
-  unsigned char pad_;
+  unsigned char flags;   // bit0: root ray of the primary trace
+  unsigned short slot;   // sample slot inside the warp's batch
+  unsigned short pad_;
 };
 
 template <typename R>
@@ -108,32 +113,16 @@ struct HitRec {
   int checker_sel;  // 0: keep prim colour, 1: color1, 2: color2
 };
 
-// Closest hit over all flattened primitives (the candidate loop of rayColor,
-// render_final_project.cpp:522-538, with each class's intersect()).
-template <typename R, bool COUNT>
-__device__ inline void closestHit(const Params<R>& P, const Moved<R>& mv, const Vec<R>& ray, const Vec<R>& start,
-                                  HitRec& h, Counts& cnt) {
-  h.t = FLT_MAX; h.geom = -1; h.inside = 0; h.checker_sel = 0;
-  int stack[DRT_NODE_STACK];
-  int sp = 0;
-  stack[sp++] = 0;
-  const Vec<R> inv_ray = mk<R>(R(1) / ray.x, R(1) / ray.y, R(1) / ray.z);   // ray.cwiseInverse() :499
-  while (sp > 0) {
-    const NodeD<R>& nd = P.nodes[stack[--sp]];
-    if (COUNT) cnt.node_tests++;
-    if (!boxHit<R>(nd, ray, inv_ray, start, mv)) continue;
-    if (!nd.leaf) { stack[sp++] = nd.left; stack[sp++] = nd.right; continue; }   // right child is popped first (:497-509)
-    const int g_end = nd.first + nd.count;
-    for (int gi = nd.first; gi < g_end; gi++) {
-    const Geom<R>& g = P.geoms[gi];
-    const int type = g.type;
-    if (type == G_HOLE) continue;
-    if (COUNT) cnt.geom_tests[type]++;
-    float t_hit; int inside = 0; int sel = 0; bool ok = false;
+// One candidate of the closest-hit search: the intersect() of the geom's class.
+template <typename R>
+__device__ inline bool geomIntersect(const Params<R>& P, const Geom<R>& g, int gi, const int type, const Moved<R>& mv,
+                                     const Vec<R>& ray, const Vec<R>& start, float& t_hit, int& inside, int& sel) {
+  bool ok = false;
+  inside = 0; sel = 0;
     if (type == G_RECT || type == G_CHECKER) {
       Vec<R> A = shiftPoint(mv, g.flags, g.vel, g.p0);
       if (type == G_CHECKER) {  // exact-zero edge path pinned to "no hit" (quirk Q17)
-        if (dot(g.p1, ray) == R(0)) continue;
+        if (dot(g.p1, ray) == R(0)) return false;
       }
       float c1, c2;
       ok = rectHit<R>(A, g.p1, g.p2, g.p3, g.len1, g.len2, g.eps, ray, start, t_hit, c1, c2);
@@ -158,11 +147,11 @@ __device__ inline void closestHit(const Params<R>& P, const Moved<R>& mv, const 
       float B = (float)(R(2) * dot(ray, sc));
       float C = (float)(dot(sc, sc) - (R)((double)g.f0 * (double)g.f0));
       float disc = (float)((double)B * (double)B - (double)(4 * A * C));
-      if (disc < 0) continue;
+      if (disc < 0) return false;
       float sq = sqrtf(disc);
       float t0 = (-B + sq) / (2 * A);
       float t1 = (-B - sq) / (2 * A);
-      if (t0 <= 0.001f && t1 <= 0.001f) continue;
+      if (t0 <= 0.001f && t1 <= 0.001f) return false;
       else if (t0 <= 0.001f || t1 <= 0.001f) { t_hit = fmaxf(t0, t1); inside = 1; ok = true; }
       else { t_hit = fminf(t0, t1); inside = 0; ok = true; }
     } else if (type == G_CYL) {  // Cylinder::intersect geometry.cpp:242-295
@@ -176,11 +165,11 @@ __device__ inline void closestHit(const Params<R>& P, const Moved<R>& mv, const 
       float B = (float)(R(2) * dot(ray_a_proj, constant));
       float C = (float)(dot(constant, constant) - (R)((double)g.f0 * (double)g.f0));
       float disc = (float)((double)B * (double)B - (double)(4 * A * C));
-      if (!(disc >= 0)) continue;
+      if (!(disc >= 0)) return false;
       float sq = sqrtf(disc);
       float t1_body = (-B + sq) / (2 * A);
       float t2_body = (-B - sq) / (2 * A);
-      if (t1_body <= eps && t2_body <= eps) continue;
+      if (t1_body <= eps && t2_body <= eps) return false;
       float tc; int ins;
       if (t1_body <= eps || t2_body <= eps) { tc = t1_body; ins = 1; } else { tc = t2_body; ins = 0; }
       Vec<R> pt = start + (R)tc * ray;
@@ -191,45 +180,114 @@ __device__ inline void closestHit(const Params<R>& P, const Moved<R>& mv, const 
       Vec<R> hh = cross(ray, r2);
       float det = (float)dot(r1, hh);
       float invdet = (float)(1.0 / (double)det);
-      if (det >= -0.0001f && det <= 0.0001f) continue;
+      if (det >= -0.0001f && det <= 0.0001f) return false;
       Vec<R> A0 = start - A;
       float u = (float)((double)invdet * (double)dot(A0, hh));   // float * double evaluates in double
-      if (u < 0 || u > 1) continue;
+      if (u < 0 || u > 1) return false;
       Vec<R> DA0 = cross(A0, r1);
       float v = (float)((double)dot(ray, DA0) * (double)invdet);
-      if (v < 0 || u + v > 1) continue;
+      if (v < 0 || u + v > 1) return false;
       float t_final = (float)((double)dot(r2, DA0) * (double)invdet);
       if (t_final > 0.0001f) {
         if (g.flags & GF_MESH) { if (dot(ray, g.p3) > R(0)) inside = 1; }
         t_hit = t_final; ok = true;
       }
     }
-    if (ok && t_hit < h.t) { h.t = t_hit; h.geom = gi; h.inside = inside; h.checker_sel = sel; }
+  return ok;
+}
+
+// Conservative single-precision slab test against the geom's padded bounds: a cheap
+// filter in front of the exact (double) class test.  Never rejects a true hit: the
+// boxes are padded by 1e-3 + 1e-5*|coordinate| on the host and the comparison keeps a
+// relative margin, so only the cost -- not the candidate set -- changes.
+__device__ inline bool slabMayHit(const float4 blo, const float4 bhi, const float ox, const float oy, const float oz,
+                                  const float ix, const float iy, const float iz, const float t_limit) {
+  float t0 = (blo.x - ox) * ix, t1 = (bhi.x - ox) * ix;
+  float tn = fminf(t0, t1), tf = fmaxf(t0, t1);
+  t0 = (blo.y - oy) * iy; t1 = (bhi.y - oy) * iy;
+  tn = fmaxf(tn, fminf(t0, t1)); tf = fminf(tf, fmaxf(t0, t1));
+  t0 = (blo.z - oz) * iz; t1 = (bhi.z - oz) * iz;
+  tn = fmaxf(tn, fminf(t0, t1)); tf = fminf(tf, fmaxf(t0, t1));
+  return !(tn > tf * 1.0001f + 1e-4f) && !(tf < 0.0f) && !(tn > t_limit);
+}
+
+// Closest hit over all flattened primitives (the candidate loop of rayColor,
+// render_final_project.cpp:522-538, with each class's intersect()).
+//
+// The reference gathers candidates through its BVH; for these rays the gather walks the
+// same ray the tests use and its boxes are padded supersets of the shapes, so culling
+// never changes which shape is closest.  The geoms are therefore tested directly, in
+// the reference's candidate order (ties of t keep the first, :531), behind the cheap
+// slab filter.  Only while "rectangle" shapes are displaced by reference-mode motion
+// blur (mv.val != 0) is the reference tree walked node by node: bumpBVH widens leaf
+// boxes but not interior ones (quirk Q14), which can cull a moved rectangle.
+template <typename R, bool COUNT>
+__device__ inline void closestHit(const Params<R>& P, const Moved<R>& mv, const Vec<R>& ray, const Vec<R>& start,
+                                  HitRec& h, Counts& cnt) {
+  h.t = FLT_MAX; h.geom = -1; h.inside = 0; h.checker_sel = 0;
+  if (mv.val == 0.0f) {
+    // Two passes per group of 32 geoms: (1) the slab filter runs over the group in
+    // lock-step (warp-uniform loads) and leaves each lane a bit mask of ITS candidates;
+    // (2) every lane then walks its own mask, so one loop trip runs one exact test per
+    // lane -- whatever geom that is -- instead of one geom for the few lanes that need it.
+    const float ox = (float)start.x, oy = (float)start.y, oz = (float)start.z;
+    const float ix = 1.0f / (float)ray.x, iy = 1.0f / (float)ray.y, iz = 1.0f / (float)ray.z;
+    const bool cull = !mv.velocity_mode;
+    const int n = P.n_geoms;
+    for (int g0 = 0; g0 < n; g0 += 32) {
+      const int g1 = min(n, g0 + 32);
+      unsigned int mask = 0;
+      for (int gi = g0; gi < g1; gi++) {
+        const Geom<R>& g = P.geoms[gi];
+        if (g.type == G_HOLE) continue;
+        if (cull && !slabMayHit(g.blo, g.bhi, ox, oy, oz, ix, iy, iz, FLT_MAX)) continue;
+        mask |= 1u << (gi - g0);
+      }
+      while (mask) {
+        const int gi = g0 + __ffs(mask) - 1;      // ascending = the reference's candidate order
+        mask &= mask - 1;
+        const Geom<R>& g = P.geoms[gi];
+        // a box whose entry lies beyond the best hit cannot hold a closer (or tying) one
+        if (cull && h.t < FLT_MAX && !slabMayHit(g.blo, g.bhi, ox, oy, oz, ix, iy, iz, h.t * 1.0001f + 1e-4f)) continue;
+        const int type = g.type;
+        if (COUNT) cnt.geom_tests[type]++;
+        float t_hit; int inside, sel;
+        if (geomIntersect<R>(P, g, gi, type, mv, ray, start, t_hit, inside, sel) && t_hit < h.t) {
+          h.t = t_hit; h.geom = gi; h.inside = inside; h.checker_sel = sel;
+        }
+      }
+    }
+    return;
+  }
+  int stack[DRT_NODE_STACK];
+  int sp = 0;
+  stack[sp++] = 0;
+  const Vec<R> inv_ray = mk<R>(R(1) / ray.x, R(1) / ray.y, R(1) / ray.z);   // ray.cwiseInverse() :499
+  while (sp > 0) {
+    const NodeD<R>& nd = P.nodes[stack[--sp]];
+    if (COUNT) cnt.node_tests++;
+    if (!boxHit<R>(nd, ray, inv_ray, start, mv)) continue;
+    if (!nd.leaf) { stack[sp++] = nd.left; stack[sp++] = nd.right; continue; }   // right child is popped first (:497-509)
+    const int g_end = nd.first + nd.count;
+    for (int gi = nd.first; gi < g_end; gi++) {
+      const Geom<R>& g = P.geoms[gi];
+      const int type = g.type;
+      if (type == G_HOLE) continue;
+      if (COUNT) cnt.geom_tests[type]++;
+      float t_hit; int inside, sel;
+      if (geomIntersect<R>(P, g, gi, type, mv, ray, start, t_hit, inside, sel) && t_hit < h.t) {
+        h.t = t_hit; h.geom = gi; h.inside = inside; h.checker_sel = sel;
+      }
     }
   }
 }
 
-// Any-hit for shadow rays (render_final_project.cpp:828-851 with each class's
-// intersectShadow).  `ray` is normalised, `start` already offset by 1e-3.
-template <typename R, bool COUNT>
-__device__ inline bool anyHit(const Params<R>& P, const Moved<R>& mv, const Vec<R>& gather_ray, const Vec<R>& gather_start,
-                              const Vec<R>& ray, const Vec<R>& start, float t_max, int skip_owner, Counts& cnt) {
-  int stack[DRT_NODE_STACK];
-  int sp = 0;
-  stack[sp++] = 0;
-  const Vec<R> inv_ray = mk<R>(R(1) / gather_ray.x, R(1) / gather_ray.y, R(1) / gather_ray.z);   // sray.cwiseInverse() :813
-  while (sp > 0) {
-    const NodeD<R>& nd = P.nodes[stack[--sp]];
-    if (COUNT) cnt.node_tests++;
-    if (!boxHit<R>(nd, gather_ray, inv_ray, gather_start, mv)) continue;
-    if (!nd.leaf) { stack[sp++] = nd.left; stack[sp++] = nd.right; continue; }
-    const int g_end = nd.first + nd.count;
-    for (int gi = nd.first; gi < g_end; gi++) {
-    const Geom<R>& g = P.geoms[gi];
-    const int type = g.type;
-    if (type == G_HOLE) continue;
-    if (g.owner == skip_owner) continue;   // an area light never shadows itself (832-837)
-    if (COUNT) cnt.geom_tests[type]++;
+// One candidate of the shadow test: the intersectShadow() of the geom's class.
+// `ray` is normalised, `start` already offset by 1e-3 along it.
+template <typename R>
+__device__ inline bool geomShadow(const Params<R>& P, const Geom<R>& g, int gi, const int type, const Moved<R>& mv,
+                                  const Vec<R>& ray, const Vec<R>& start, const float t_max, float& t_occ) {
+    t_occ = 0.0f;   // on success: a ray parameter at which the ray certainly touches the geom
     if (type == G_RECT || type == G_CHECKER) {
       Vec<R> A = shiftPoint(mv, g.flags, g.vel, g.p0);
       // Checkerboard inherits Rectangle::intersectShadow (eps 1e-4); CheckerboardWithHole
@@ -242,8 +300,9 @@ __device__ inline bool anyHit(const Params<R>& P, const Moved<R>& mv, const Vec<
           float t2, d1, d2;
           if (rectHit<R>(hgeo.p0, hgeo.p1, hgeo.p2, hgeo.p3, hgeo.len1, hgeo.len2, hgeo.eps, ray, start, t2, d1, d2) &&
               t2 < t_max)
-            continue;
+            return false;
         }
+        t_occ = th;
         return true;
       }
     } else if (type == G_SPHERE) {  // geometry.cpp:173-197
@@ -253,11 +312,12 @@ __device__ inline bool anyHit(const Params<R>& P, const Moved<R>& mv, const Vec<
       float B = (float)(R(2) * dot(ray, sc));
       float C = (float)(dot(sc, sc) - (R)((double)g.f0 * (double)g.f0));
       float disc = (float)((double)B * (double)B - (double)(4 * A * C));
-      if (disc < 0) continue;
+      if (disc < 0) return false;
       float sq = sqrtf(disc);
       float t0 = (-B + sq) / (2 * A);
       float t1 = (-B - sq) / (2 * A);
-      if ((t0 <= eps || t0 >= t_max) && (t1 <= eps || t1 >= t_max)) continue;
+      if ((t0 <= eps || t0 >= t_max) && (t1 <= eps || t1 >= t_max)) return false;
+      t_occ = (t0 > eps && t0 < t_max) ? t0 : t1;   // t0 is the far root
       return true;
     } else if (type == G_CYL) {  // geometry.cpp:368-417
       const float eps = 1e-3f;
@@ -270,30 +330,104 @@ __device__ inline bool anyHit(const Params<R>& P, const Moved<R>& mv, const Vec<
       float B = (float)(R(2) * dot(ray_a_proj, constant));
       float C = (float)(dot(constant, constant) - (R)((double)g.f0 * (double)g.f0));
       float disc = (float)((double)B * (double)B - (double)(4 * A * C));
-      if (!(disc >= 0)) continue;
+      if (!(disc >= 0)) return false;
       float sq = sqrtf(disc);
       float t1_body = (-B + sq) / (2 * A);
       float t2_body = (-B - sq) / (2 * A);
-      if ((t1_body <= eps || t1_body >= t_max) && (t2_body <= eps || t2_body >= t_max)) continue;
+      if ((t1_body <= eps || t1_body >= t_max) && (t2_body <= eps || t2_body >= t_max)) return false;
       float tc = (t1_body <= eps || t2_body <= eps) ? t1_body : t2_body;
       Vec<R> pt = start + (R)tc * ray;
-      if (dot(axis, pt - c1) > R(0) && dot(axis, pt - c2) < R(0) && tc < t_max) return true;
+      if (dot(axis, pt - c1) > R(0) && dot(axis, pt - c2) < R(0) && tc < t_max) { t_occ = tc; return true; }
     } else {  // G_TRI geometry.cpp:555-586
       Vec<R> A = shiftPoint(mv, g.flags, g.vel, g.p0);
       const Vec<R> r1 = g.p1, r2 = g.p2;
       Vec<R> hh = cross(ray, r2);
       float det = (float)dot(r1, hh);
       float invdet = (float)(1.0 / (double)det);
-      if (det >= -0.0001f && det <= 0.0001f) continue;
+      if (det >= -0.0001f && det <= 0.0001f) return false;
       Vec<R> A0 = start - A;
       float u = (float)((double)invdet * (double)dot(A0, hh));
-      if (u < 0 || u > 1) continue;
+      if (u < 0 || u > 1) return false;
       Vec<R> DA0 = cross(A0, r1);
       float v = (float)((double)dot(ray, DA0) * (double)invdet);
-      if (v < 0 || u + v > 1) continue;
+      if (v < 0 || u + v > 1) return false;
       float t_final = (float)((double)dot(r2, DA0) * (double)invdet);
-      if (t_final > 0.001f && t_final < t_max) return true;
+      if (t_final > 0.001f && t_final < t_max) { t_occ = t_final; return true; }
     }
+  return false;
+}
+
+// Any-hit for shadow rays (render_final_project.cpp:806-851).
+//
+// The reference gathers candidates along the UNNORMALISED light vector from
+// isectP + sray*1e-3 (:814) but tests occlusion along the normalised one from
+// isectP + s^*1e-3 (:838): with the sphere-light quirk (sampleRay returns a position,
+// |sray| ~ tens of units) occluders within the first centimetres are never gathered.
+// That is reproduced exactly, lazily: geoms are tested directly (slab filter + exact
+// class test) and only a geom that DOES occlude is checked against the reference
+// gather, by running BoundingVolume::intersect on its leaf and every ancestor.
+template <typename R, bool COUNT>
+__device__ inline bool anyHit(const Params<R>& P, const Moved<R>& mv, const Vec<R>& gather_ray, const Vec<R>& gather_start,
+                              const Vec<R>& ray, const Vec<R>& start, float t_max, int skip_owner, Counts& cnt) {
+  const Vec<R> inv_ray = mk<R>(R(1) / gather_ray.x, R(1) / gather_ray.y, R(1) / gather_ray.z);   // sray.cwiseInverse() :813
+  if (mv.val == 0.0f) {
+    const float ox = (float)start.x, oy = (float)start.y, oz = (float)start.z;
+    const float ix = 1.0f / (float)ray.x, iy = 1.0f / (float)ray.y, iz = 1.0f / (float)ray.z;
+    const bool cull = !mv.velocity_mode;
+    // distance by which the reference's gather origin runs ahead of the test origin
+    const float gather_lead = t_max * 1e-3f;
+    const int n = P.n_geoms;
+    for (int g0 = 0; g0 < n; g0 += 32) {
+      const int g1 = min(n, g0 + 32);
+      unsigned int mask = 0;
+      for (int gi = g0; gi < g1; gi++) {           // lock-step slab filter -> per-lane candidate mask
+        const Geom<R>& g = P.geoms[gi];
+        if (g.type == G_HOLE || g.owner == skip_owner) continue;   // an area light never shadows itself (832-837)
+        if (cull && !slabMayHit(g.blo, g.bhi, ox, oy, oz, ix, iy, iz, t_max * 1.0001f + 1e-4f)) continue;
+        mask |= 1u << (gi - g0);
+      }
+      while (mask) {                                // each lane walks its own candidates
+        const int gi = g0 + __ffs(mask) - 1;
+        mask &= mask - 1;
+        const Geom<R>& g = P.geoms[gi];
+        const int type = g.type;
+        if (COUNT) cnt.geom_tests[type]++;
+        float t_occ;
+        if (!geomShadow<R>(P, g, gi, type, mv, ray, start, t_max, t_occ)) continue;
+        if (mv.velocity_mode) return true;          // time-displaced geometry: no reference tree to consult
+        // The occluder touches the ray at distance t_occ from the test origin.  If that point
+        // lies ahead of the gather origin it is inside the geom's leaf box and every ancestor
+        // box (they are padded supersets), so BoundingVolume::intersect returns tmax > 0 for all
+        // of them and the reference does gather this geom.  Only nearer occluders need the
+        // exact replay of the reference's box tests.
+        if (t_occ > gather_lead * 1.001f + 2e-3f) return true;
+        bool gathered = true;
+        for (int ni = g.leaf; ni >= 0 && gathered; ni = P.nodes[ni].parent) {
+          if (COUNT) cnt.node_tests++;
+          gathered = boxHit<R>(P.nodes[ni], gather_ray, inv_ray, gather_start, mv);
+        }
+        if (gathered) return true;
+      }
+    }
+    return false;
+  }
+  int stack[DRT_NODE_STACK];
+  int sp = 0;
+  stack[sp++] = 0;
+  while (sp > 0) {
+    const NodeD<R>& nd = P.nodes[stack[--sp]];
+    if (COUNT) cnt.node_tests++;
+    if (!boxHit<R>(nd, gather_ray, inv_ray, gather_start, mv)) continue;
+    if (!nd.leaf) { stack[sp++] = nd.left; stack[sp++] = nd.right; continue; }
+    const int g_end = nd.first + nd.count;
+    for (int gi = nd.first; gi < g_end; gi++) {
+      const Geom<R>& g = P.geoms[gi];
+      const int type = g.type;
+      if (type == G_HOLE) continue;
+      if (g.owner == skip_owner) continue;
+      if (COUNT) cnt.geom_tests[type]++;
+      float t_occ;
+      if (geomShadow<R>(P, g, gi, type, mv, ray, start, t_max, t_occ)) return true;
     }
   }
   return false;
@@ -324,33 +458,35 @@ __device__ inline float powi_d(float x, int n) {  // pow(float, int) evaluates i
   return (float)pow((double)x, (double)n);
 }
 
-// One rayColor tree (render_final_project.cpp:487-961) rooted at (dir, org).
-// Returns the colour added, whether the ROOT ray hit anything, and in_motion.
+// One rayColor invocation (render_final_project.cpp:487-961) for the ray in `T`.
+// Every invocation ADDS exactly one k-weighted term to the sample's colour (emissive
+// term or the hits-averaged light sum) and spawns up to brdf_samples+1 child rays;
+// the children are returned to the caller, which owns the scheduling.
+//   children[0..n_out) : child tasks in the reference's call order
+//   add / has_add      : the term to accumulate
+//   hit_any            : any_intersect of this invocation
+//   motion             : -1 unless this task is on the "last invocation" chain that
+//                        decides in_motion (quirk Q4), else the new flag value
 template <typename R, bool COUNT>
-__device__ void traceTree(const Params<R>& P, const Moved<R>& mv, const Vec<R>& root_dir, const Vec<R>& root_org,
-                          uint32_t root_path, Task<R>* stack, double (&color)[3], bool& root_hit, bool& in_motion,
-                          bool& aborted, Counts& cnt) {
+__device__ void processRay(const Params<R>& P, const Task<R>& T, Task<R>* stack, int& n_out, double (&add)[3], bool& has_add,
+                           bool& hit_any, int& motion, bool& aborted, Counts& cnt) {
   int sp = 0;
-  stack[0].org = root_org; stack[0].dir = root_dir; stack[0].k = 1.0f; stack[0].path = root_path;
-  stack[0].depth = (short)P.max_depth; stack[0].chain = 1;
-  sp = 1;
-  root_hit = false; in_motion = false;
-  bool first = true;
-  while (sp > 0 && !aborted) {
-    Task<R> T = stack[--sp];
-    const bool is_root = first; first = false;
+  n_out = 0; has_add = false; hit_any = false; motion = -1;
+  add[0] = add[1] = add[2] = 0.0;
+  Moved<R> mv; mv.val = T.val; mv.time = (R)T.dt; mv.velocity_mode = (P.blur_mode == 1 && T.dt != 0.0f);
+  do {
     if (T.depth == 0) continue;                                         // :489
     if (COUNT) cnt.rays++;
     const Vec<R> ray = T.dir, eye = T.org;
     const float k = T.k;
     HitRec h;
     closestHit<R, COUNT>(P, mv, ray, eye, h, cnt);
-    if (T.chain) in_motion = false;                                     // :519
+    if (T.chain) motion = 0;                                       // :519
     if (h.geom < 0) continue;                                           // :541-544
-    if (is_root) root_hit = true;
+    hit_any = true;
     const Geom<R>& g = P.geoms[h.geom];
     const PrimD<R>& pr = P.prims[g.owner];
-    if (T.chain) in_motion = (pr.flags & 2) != 0;                       // DRT_FLAG_MOTION, :564
+    if (T.chain) motion = (pr.flags & 2) ? 1 : 0;                       // DRT_FLAG_MOTION, :564
 
     const Vec<R> isectP = eye + (R)h.t * ray;                           // :548
     // ---- getNorm of the hit class ------------------------------------------------
@@ -414,10 +550,10 @@ __device__ void traceTree(const Params<R>& P, const Moved<R>& mv, const Vec<R>& 
           float rho_perp = (P.refr_air * cos_theta - P.refr_glass * cos_phi) / (P.refr_air * cos_theta + P.refr_glass * cos_phi);
           k_refl = (float)(0.5 * ((double)rho_par * (double)rho_par + (double)rho_perp * (double)rho_perp));
           k_refr = 1 - k_refl;
-          if (sp < DRT_STACK_MAX) {
+          if (sp < DRT_MAX_CHILDREN) {
             Task<R>& c = stack[sp++];
             c.org = isectP + in * (R)eps; c.dir = out; c.k = k_refr * k; c.path = rng_key_child(T.path, 0);
-            c.depth = T.depth - 1; c.chain = 0; n_children++;
+            c.depth = T.depth - 1; c.chain = 0; c.flags = 0; c.slot = T.slot; c.val = T.val; c.dt = T.dt; n_children++;
           }
         }
       }
@@ -469,18 +605,18 @@ __device__ void traceTree(const Params<R>& P, const Moved<R>& mv, const Vec<R>& 
               sample_limit--;
             }
             if (aborted) break;
-            if (sp < DRT_STACK_MAX) {
+            if (sp < DRT_MAX_CHILDREN) {
               Task<R>& c = stack[sp++];
               c.org = isectP + sample_refl * (R)eps; c.dir = sample_refl; c.k = k_refl * k / P.brdf_samples;
-              c.path = rng_key_child(T.path, 2 + i); c.depth = T.depth - 1; c.chain = 0; n_children++;
+              c.path = rng_key_child(T.path, 2 + i); c.depth = T.depth - 1; c.chain = 0; c.flags = 0; c.slot = T.slot; c.val = T.val; c.dt = T.dt; n_children++;
             }
           }
           if (aborted) break;
         } else {                                                        // mirror :765
-          if (sp < DRT_STACK_MAX) {
+          if (sp < DRT_MAX_CHILDREN) {
             Task<R>& c = stack[sp++];
             c.org = isectP + refl_ray * (R)eps; c.dir = refl_ray; c.k = k_refl * k; c.path = rng_key_child(T.path, 1);
-            c.depth = T.depth - 1; c.chain = 0; n_children++;
+            c.depth = T.depth - 1; c.chain = 0; c.flags = 0; c.slot = T.slot; c.val = T.val; c.dt = T.dt; n_children++;
           }
         }
       }
@@ -493,13 +629,15 @@ __device__ void traceTree(const Params<R>& P, const Moved<R>& mv, const Vec<R>& 
       if (pr.name == 2) {                                               // spherelight
         float hitdot = (float)dot(in, normalized(shiftPoint(mv, 0, pr.vel, pr.center) - isectP));
         double f = 0.1 * pow((double)hitdot, 1.0) + 0.05 * pow((double)hitdot, 5.0) + 0.9;
-        for (int c = 0; c < 3; c++) color[c] += ((double)k * (double)shape_color[c]) * f;
+        for (int c = 0; c < 3; c++) add[c] += ((double)k * (double)shape_color[c]) * f;
+        has_add = true;
       }
       if (pr.name == 3) {                                               // rectanglelight
         float dist = (float)((double)(norm(isectP - pr.eA) + norm(isectP - pr.eB) + norm(isectP - pr.eC) + norm(isectP - pr.eD)) /
                              (double)pr.e_den);
         double f = 0.1 * pow((double)dist, 1.0) + 0.05 * pow((double)dist, 5.0) + 0.9;
-        for (int c = 0; c < 3; c++) color[c] += ((double)k * (double)shape_color[c]) * f;
+        for (int c = 0; c < 3; c++) add[c] += ((double)k * (double)shape_color[c]) * f;
+        has_add = true;
       }
       continue;
     }
@@ -692,29 +830,45 @@ __device__ void traceTree(const Params<R>& P, const Moved<R>& mv, const Vec<R>& 
       if (!(sq <= 0.0)) { hits++; for (int c = 0; c < 3; c++) tmp_color[c] += (double)k * ray_color[c]; }
     }
     if (aborted) break;
-    if (!early_return && hits > 0) for (int c = 0; c < 3; c++) color[c] += tmp_color[c] / hits;   // :956-959
-  }
+    if (!early_return && hits > 0) { for (int c = 0; c < 3; c++) add[c] += tmp_color[c] / hits; has_add = true; }   // :956-959
+  } while (0);
+  n_out = sp;
 }
 
 // ---------------------------------------------------------------------------
-template <typename R, bool COUNT>
-__global__ void __launch_bounds__(128) render_samples(const __grid_constant__ Params<R> P) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= P.sample_count) return;
-  const long long gidx = P.sample_base + idx;          // pixel_in_tile * spp + s
+// render_wave: persistent warps + warp-local ray pools.
+//
+// A thread-per-sample walk of the ray tree leaves most lanes idle: tree sizes are
+// heavy-tailed (glossy lobes and glass fan out 2-3 rays per bounce to depth 10), so a
+// warp runs as long as its largest tree (ncu, profiles/r1_*: 7 of 32 lanes active in
+// the object-heavy half of the C2 frame).  Here the unit of scheduling is the RAY:
+//   * each warp repeatedly claims a batch of DRT_BATCH consecutive camera samples
+//     from a global counter (dynamic load balance, no tail of straggler blocks);
+//   * all pending rays of the batch live in the warp's LIFO pool in global memory
+//     (L1/L2 resident); per iteration the top min(count,32) rays are popped, one per
+//     lane, processed with processRay(), and the children are compacted back with a
+//     warp prefix sum (ballot-free shuffle scan);
+//   * per-sample radiance is accumulated in 64-bit fixed point (2^-32) with shared
+//     memory atomics, so the sum does not depend on the order rays are processed in
+//     and the output stays bit-reproducible.
+
+// per-sample state bits (shared memory) -- the low 4 are also the output flag bits
+#define SS_HIT 16u
+#define SS_MOTION 32u
+#define SS_NAN(c) (256u << (c))
+#define SS_PINF(c) (2048u << (c))
+#define SS_NINF(c) (16384u << (c))
+
+template <typename R>
+__device__ inline void primaryRay(const Params<R>& P, long long gidx, Vec<R>& org, Vec<R>& dir, uint32_t& skey, int& pi, int& pj,
+                                  int& px, int& py) {
   const int s = (int)(gidx % P.spp);
   const int pt = (int)(gidx / P.spp);
-  const int px = pt % P.w, py = pt / P.w;
+  px = pt % P.w; py = pt / P.w;
   const int x = P.x0 + px, y = P.y0 + py;
-
-  Counts cnt;
-  if (COUNT) { cnt.samples = 1; cnt.rays = 0; cnt.shadow_rays = 0; cnt.shade_evals = 0; cnt.noise_evals = 0; cnt.node_tests = 0;
-               for (int i = 0; i < 6; i++) cnt.geom_tests[i] = 0; }
-
   const uint32_t pixel = (uint32_t)(y * P.xRes + x);
   const uint32_t pkey = rng_key_pixel(P.seed, pixel);
-  const uint32_t skey = rng_key_sample(pkey, (uint32_t)s);
-
+  skey = rng_key_sample(pkey, (uint32_t)s);
   // lens sample (getDOFSamples :195-210); drawn per camera sample, see DESIGN.md
   Vec<R> eye_sample = P.eye;
   if (P.aperture > 0) {
@@ -726,48 +880,163 @@ __global__ void __launch_bounds__(128) render_samples(const __grid_constant__ Pa
   const int ii = s / P.n, jj = s % P.n;
   float adj_x = (float)((double)x + ((double)(float)ii + (double)rng_u01(pkey, 4u * s + 2)) / 9.0);
   float adj_y = (float)((double)y + ((double)(float)jj + (double)rng_u01(pkey, 4u * s + 3)) / 9.0);
-  const int pi = (int)(double)adj_x, pj = (int)(double)adj_y;
+  pi = (int)(double)adj_x; pj = (int)(double)adj_y;
   const Vec<R> rayDir = eyeRay<R>(P, pi, pj);
   const Vec<R> focalPoint = P.eye + (R)P.focal_length * rayDir;        // :1069
-  const Vec<R> dir = focalPoint - eye_sample;
+  org = eye_sample;
+  dir = focalPoint - eye_sample;
+}
 
-  Task<R> stack[DRT_STACK_MAX];
-  double color[3] = {0, 0, 0};
-  bool hit = false, motion = false, aborted = false;
-  Moved<R> mv; mv.val = 0; mv.time = 0; mv.velocity_mode = 0;
-  traceTree<R, COUNT>(P, mv, dir, eye_sample, rng_key_child(skey, 0), stack, color, hit, motion, aborted, cnt);
+template <typename R, bool COUNT>
+__global__ void __launch_bounds__(128, 3) render_wave(const __grid_constant__ Params<R> P) {
+  __shared__ unsigned long long s_acc[4][DRT_BATCH][3];
+  __shared__ unsigned int s_flags[4][DRT_BATCH];
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  Task<R>* pool = (Task<R>*)P.pool_raw + (size_t)(blockIdx.x * 4 + wib) * DRT_POOL_CAP;
+  unsigned long long(*acc)[3] = s_acc[wib];
+  unsigned int* sfl = s_flags[wib];
+  const long long n_batches = (P.sample_count + DRT_BATCH - 1) / DRT_BATCH;
 
-  uint32_t flags = 0;
-  if (!hit && !aborted) {                                               // :1074-1094
-    color[0] = color[1] = color[2] = 0;                                 // default_col
-    if (P.perlin_cloud) {
-      int cx = pi - P.x0, cy = pj - P.y0;                               // pixel corner inside this tile's (w+1)x(h+1) grid
-      cx = min(max(cx, 0), P.w); cy = min(max(cy, 0), P.h);
-      flags |= SF_MISS | ((uint32_t)((cx - px) | ((cy - py) << 1)) << SF_CORNER_SHIFT);
-      if (P.need[cy * (P.w + 1) + cx] == 0) P.need[cy * (P.w + 1) + cx] = 1;   // benign race: all writers store 1
+  Counts cnt;
+  if (COUNT) { cnt.samples = 0; cnt.rays = 0; cnt.shadow_rays = 0; cnt.shade_evals = 0; cnt.noise_evals = 0; cnt.node_tests = 0;
+               for (int i = 0; i < 6; i++) cnt.geom_tests[i] = 0; }
+
+  for (;;) {
+    long long b = 0;
+    if (lane == 0) b = (long long)atomicAdd(P.batch_counter, 1ull);
+    b = __shfl_sync(FULL, b, 0);
+    if (b >= n_batches) break;
+    const long long idx0 = b * DRT_BATCH;                               // chunk-local sample index of slot 0
+    const int n_valid = (int)min((long long)DRT_BATCH, P.sample_count - idx0);
+    for (int s = lane; s < DRT_BATCH; s += 32) { acc[s][0] = acc[s][1] = acc[s][2] = 0ull; sfl[s] = 0u; }
+    __syncwarp();
+
+    // ---- primary rays -> pool[0..n_valid) -----------------------------------------
+    for (int s = lane; s < n_valid; s += 32) {
+      Task<R> T; uint32_t skey; int pi, pj, px, py;
+      primaryRay<R>(P, P.sample_base + idx0 + s, T.org, T.dir, skey, pi, pj, px, py);
+      T.k = 1.0f; T.path = rng_key_child(skey, 0); T.val = 0.f; T.dt = 0.f; T.depth = (short)P.max_depth;
+      T.chain = 1; T.flags = 1; T.slot = (unsigned short)s; T.pad_ = 0;
+      pool[s] = T;
+      if (COUNT) cnt.samples++;
     }
-  }
-  if (motion && !aborted) {                                             // :1095-1210
-    mv.velocity_mode = (P.blur_mode == 1);
-    for (int m = 0; m < P.blur_samples && !aborted; m++) {
-      float frame_sample = (float)((double)(float)P.frame + (double)rng_u01(skey, (uint32_t)m) * (double)P.frame_range);
-      float dt = frame_sample - (float)P.frame;
-      float val = 0;                                                    // uninitialised in the reference below frame_prism (Q16)
-      if (P.blur_mode == 0 && P.frame >= P.frame_prism) {
-        if (P.frame >= P.frame_blur) val = (float)((double)(P.move_per_frame * dt) + (double)P.accel_t * pow((double)dt, 3.0));
-        else val = P.move_per_frame * dt;
+    __syncwarp();
+    int count = n_valid;
+
+    for (int phase = 0; phase < 2; phase++) {
+      // ---- drain the pool ----------------------------------------------------------
+      while (count > 0) {
+        const int take = min(count, 32);
+        const bool active = lane < take;
+        Task<R> kids[DRT_MAX_CHILDREN];
+        int nk = 0;
+        if (active) {
+          const Task<R> T = pool[count - 1 - lane];
+          const unsigned int f = ((volatile unsigned int*)sfl)[T.slot];
+          if (!(f & SF_ABORT)) {                                        // an aborted sample spawns no more work (Q15)
+            double add[3]; bool has_add, hit_any, aborted = false; int motion;
+            processRay<R, COUNT>(P, T, kids, nk, add, has_add, hit_any, motion, aborted, cnt);
+            if (aborted) { atomicOr(&sfl[T.slot], SF_ABORT); nk = 0; }
+            else {
+              unsigned int orf = 0;
+              if (has_add) {
+                for (int c = 0; c < 3; c++) {
+                  const double v = add[c];
+                  if (v != v) orf |= SS_NAN(c);
+                  else if (v > 1073741824.0) orf |= (isinf(v) ? SS_PINF(c) : 0u), atomicAdd(&acc[T.slot][c], (unsigned long long)(1ll << 62));
+                  else if (v < -1073741824.0) orf |= (isinf(v) ? SS_NINF(c) : 0u), atomicAdd(&acc[T.slot][c], (unsigned long long)(-(1ll << 62)));
+                  else atomicAdd(&acc[T.slot][c], (unsigned long long)__double2ll_rn(v * 4294967296.0));
+                }
+              }
+              if ((T.flags & 1) && hit_any) orf |= SS_HIT;
+              if (motion == 1) orf |= SS_MOTION;
+              if (orf) atomicOr(&sfl[T.slot], orf);
+              if (motion == 0) atomicAnd(&sfl[T.slot], ~SS_MOTION);
+            }
+          }
+        }
+        count -= take;
+        // ---- compact the children back (warp inclusive scan of nk) -----------------
+        int incl = nk;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += v; }
+        const int total = __shfl_sync(FULL, incl, 31);
+        if (count + total > DRT_POOL_CAP) {                             // cannot happen within the validated bounds
+          if (nk) atomicOr(&sfl[kids[0].slot], SF_ABORT);
+          if (lane == 0) *P.overflow = 1;
+        } else {
+          const int base = count + incl - nk;
+          for (int j = 0; j < nk; j++) pool[base + j] = kids[j];
+          count += total;
+        }
+        __syncwarp();
       }
-      mv.val = val; mv.time = (R)((double)frame_sample - (double)P.frame);
-      double mc[3] = {0, 0, 0};
-      bool h2, m2;
-      traceTree<R, COUNT>(P, mv, dir, eye_sample, rng_key_child(skey, 1 + m), stack, mc, h2, m2, aborted, cnt);
-      color[0] += mc[0]; color[1] += mc[1]; color[2] += mc[2];
+      if (phase == 1 || P.blur_samples <= 0) break;
+      // ---- motion blur: re-trace the samples whose in_motion flag ended up set --------
+      // (render_final_project.cpp:1095-1210); the extra traces go through the same pool
+      int any_motion = 0;
+      for (int s = lane; s < n_valid; s += 32) any_motion |= ((sfl[s] & (SS_MOTION | SF_ABORT)) == SS_MOTION);
+      if (!__any_sync(FULL, any_motion)) break;
+      for (int r = 0; r < DRT_BATCH / 32; r++) {
+        const int s = r * 32 + lane;
+        const bool mo = s < n_valid && ((sfl[s] & (SS_MOTION | SF_ABORT)) == SS_MOTION);
+        int nb = mo ? P.blur_samples : 0;
+        int incl = nb;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += v; }
+        const int total = __shfl_sync(FULL, incl, 31);
+        if (mo) {
+          Task<R> T; uint32_t skey; int pi, pj, px, py;
+          primaryRay<R>(P, P.sample_base + idx0 + s, T.org, T.dir, skey, pi, pj, px, py);
+          T.k = 1.0f; T.depth = (short)P.max_depth; T.chain = 0; T.flags = 0; T.slot = (unsigned short)s; T.pad_ = 0;
+          for (int m = 0; m < nb; m++) {
+            float frame_sample = (float)((double)(float)P.frame + (double)rng_u01(skey, (uint32_t)m) * (double)P.frame_range);
+            float dt = frame_sample - (float)P.frame;
+            float val = 0;                                              // uninitialised in the reference below frame_prism (Q16)
+            if (P.blur_mode == 0 && P.frame >= P.frame_prism) {
+              if (P.frame >= P.frame_blur) val = (float)((double)(P.move_per_frame * dt) + (double)P.accel_t * pow((double)dt, 3.0));
+              else val = P.move_per_frame * dt;
+            }
+            T.val = val; T.dt = dt; T.path = rng_key_child(skey, 1 + m);
+            if (count + incl - nb + m < DRT_POOL_CAP) pool[count + incl - nb + m] = T;
+          }
+        }
+        count = min(count + total, DRT_POOL_CAP);
+        __syncwarp();
+      }
     }
-    const double inv = (double)(P.blur_samples + 1);
-    color[0] /= inv; color[1] /= inv; color[2] /= inv;
+
+    // ---- per-sample results ------------------------------------------------------------
+    for (int s = lane; s < n_valid; s += 32) {
+      const unsigned int f = sfl[s];
+      double c[3];
+      for (int k = 0; k < 3; k++) {
+        c[k] = (double)(long long)acc[s][k] * (1.0 / 4294967296.0);
+        const bool pinf = f & SS_PINF(k), ninf = f & SS_NINF(k);
+        if ((f & SS_NAN(k)) || (pinf && ninf)) c[k] = __longlong_as_double(0x7ff8000000000000ll);
+        else if (pinf) c[k] = __longlong_as_double(0x7ff0000000000000ll);
+        else if (ninf) c[k] = __longlong_as_double(0xfff0000000000000ll);
+      }
+      uint32_t flags = 0;
+      if (f & SF_ABORT) flags |= SF_ABORT;
+      else if (!(f & SS_HIT)) {                                         // :1074-1094
+        c[0] = c[1] = c[2] = 0;                                         // default_col
+        if (P.perlin_cloud) {
+          Vec<R> o, d; uint32_t skey; int pi, pj, px, py;
+          primaryRay<R>(P, P.sample_base + idx0 + s, o, d, skey, pi, pj, px, py);
+          int cx = min(max(pi - P.x0, 0), P.w), cy = min(max(pj - P.y0, 0), P.h);   // corner in the tile's (w+1)x(h+1) grid
+          flags |= SF_MISS | ((uint32_t)((cx - px) | ((cy - py) << 1)) << SF_CORNER_SHIFT);
+          if (P.need[cy * (P.w + 1) + cx] == 0) P.need[cy * (P.w + 1) + cx] = 1;   // benign race: all writers store 1
+        }
+      } else if (f & SS_MOTION) {
+        const double inv = (double)(P.blur_samples + 1);
+        c[0] /= inv; c[1] /= inv; c[2] /= inv;
+      }
+      P.samples[idx0 + s] = make_float4((float)c[0], (float)c[1], (float)c[2], __uint_as_float(flags));
+    }
+    __syncwarp();
   }
-  if (aborted) flags |= SF_ABORT;
-  P.samples[idx] = make_float4((float)color[0], (float)color[1], (float)color[2], __uint_as_float(flags));
 
   if (COUNT) {
     atomicAdd(&P.counts->samples, cnt.samples); atomicAdd(&P.counts->rays, cnt.rays);

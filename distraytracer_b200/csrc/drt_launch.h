@@ -10,8 +10,16 @@
 #pragma once
 #include "drt_device.cuh"
 
+#define DRT_BATCH 64          // camera samples per warp batch (render_wave)
+#define DRT_POOL_CAP 2048     // ray-pool records per warp
+#define DRT_MAX_CHILDREN 6    // refraction + max(brdf_samples, 1)
+
 namespace drt {
-template <typename R> void launchRenderSamples(const Params<R>& P, bool collect, cudaStream_t q);
+// persistent grid of render_wave: blocks that are co-resident on the current device
+template <typename R> int waveGridBlocks();
+// bytes of per-warp ray pools a grid of `blocks` needs (Params::pool_raw)
+template <typename R> size_t wavePoolBytes(int blocks);
+template <typename R> void launchRenderSamples(const Params<R>& P, bool collect, int blocks, cudaStream_t q);
 template <typename R> void launchCloudCorners(const Params<R>& P, cudaStream_t q);
 template <typename R> void launchResolve(const Params<R>& P, int row0, int rows, cudaStream_t q);
 }  // namespace drt
