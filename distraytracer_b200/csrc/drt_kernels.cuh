@@ -454,39 +454,143 @@ __device__ inline Vec<R> eyeRay(const Params<R>& P, int i, int j) {  // getPersp
   return (R)su * P.X + (R)sv * P.Y - (R)P.near_plane * P.Z;
 }
 
-__device__ inline float powi_d(float x, int n) {  // pow(float, int) evaluates in double, result narrowed by the caller
-  return (float)pow((double)x, (double)n);
+
+// ---- out-of-line helpers ---------------------------------------------------------
+// render_wave is fetch-bound when everything is inlined (14k SASS instructions = 225 KB,
+// ncu "no_instructions" stalls: profiles/r1_band_wave.txt).  Blocks that are large (double
+// precision pow/exp/acos/sin/cos expansions) or rarely taken are kept out of line so the
+// trace / shadow / shade loops stay compact in the instruction caches.
+static __device__ __noinline__ double drt_pow(double x, double y) { return pow(x, y); }
+__device__ __forceinline__ double pow5(double x) { const double x2 = x * x; return x2 * x2 * x; }
+
+// sphereLight::sampleRay (geometry.cpp:2770-2826); returns the sampled POINT (quirk Q10)
+template <typename R>
+__device__ __noinline__ bool sampleSphereLight(const LightD<R>& L, const Vec<R>& isectP, uint32_t path, int li, Vec<R>& out) {
+  int attempt = 0;
+  double theta = 2 * DRT_PI * (double)rng_u01(path, rng_dim_light(li, attempt));
+  double phi = acos(1 - 2 * (double)rng_u01(path, rng_dim_light(li, attempt) + 1));
+  Vec<R> dirv = mk<R>((R)(sin(phi) * cos(theta)), (R)(sin(phi) * sin(theta)), (R)cos(phi));
+  Vec<R> tmp = (R)L.radius * dirv + L.center;
+  int sample_limit = 20;
+  const Vec<R> pc = isectP - L.center;
+  for (;;) {
+    Vec<R> d = tmp - L.center;
+    bool bad = dot(d, pc) < R(0) || (L.use_baxis && dot(d, L.baxis) < R(0));
+    if (!bad) break;
+    if (sample_limit < 0) return false;                               // throws geometry.cpp:2785-2789
+    Vec<R> rev = (R)(-L.radius) * dirv + L.center;
+    Vec<R> dr = rev - L.center;
+    bool ok = dot(dr, pc) >= R(0) && (!L.use_baxis || dot(dr, L.baxis) >= R(0));
+    if (ok) { tmp = rev; break; }
+    attempt++;
+    theta = 2 * DRT_PI * (double)rng_u01(path, rng_dim_light(li, attempt));
+    phi = acos(1 - 2 * (double)rng_u01(path, rng_dim_light(li, attempt) + 1));
+    dirv = mk<R>((R)(sin(phi) * cos(theta)), (R)(sin(phi) * sin(theta)), (R)cos(phi));
+    tmp = (R)L.radius * dirv + L.center;
+    sample_limit--;
+  }
+  out = tmp;
+  return true;
 }
 
-// One rayColor invocation (render_final_project.cpp:487-961) for the ray in `T`.
+// BRDF switch of rayColor (render_final_project.cpp:894-948) for one unoccluded light.
+template <typename R>
+__device__ __noinline__ void evalBRDF(const PrimD<R>& pr, const float* Lcolor, const float* shape_color, const Vec<R>& e,
+                                      const Vec<R>& normal, const Vec<R>& sray, const Vec<R>& sdir, float phong, double* ray_color) {
+  if (pr.model == 1) {                                              // oren-nayar
+    float vn = (float)dot(e, normal);
+    float ln = (float)dot(sdir, normal);
+    float irradiance = fmaxf(0.0f, ln);
+    float vn_theta = acosf(vn);
+    float ln_theta = acosf(ln);
+    float angleDiff = (float)fmax(0.0, (double)dot(normalized(e - normal * (R)vn), normalized(sray - normal * (R)ln)));
+    float alpha = fmaxf(vn_theta, ln_theta);
+    float beta = fminf(vn_theta, ln_theta);
+    float f = pr.on_A + pr.on_B * angleDiff * sinf(alpha) * tanf(beta);
+    for (int c = 0; c < 3; c++) ray_color[c] = (((double)shape_color[c] * (double)Lcolor[c]) * (double)irradiance) * (double)f;
+  } else if (pr.model == 2) {                                       // cook-torrance
+    Vec<R> H = normalized(e + sray);                                // unnormalised sray (Q9)
+    float hn = (float)fmax(0.0, (double)dot(normal, H));
+    float vh = (float)dot(e, H);
+    float vn = (float)dot(e, normal);
+    float ln = (float)dot(sdir, normal);
+    float alpha = acosf(hn);
+    double r2 = (double)pr.roughness * (double)pr.roughness;
+    double ca = (double)cosf(alpha);
+    double ta = (double)(tanf(alpha) / pr.roughness);
+    float D = (float)(1.0 / (r2 * (ca * ca * ca * ca)) * exp(-(ta * ta)));
+    float G1 = (float)(2.0 * hn * vn / vh);
+    float G2 = (float)(2.0 * hn * ln / vh);
+    float G = fminf(1.0f, fminf(G1, G2));
+    float F = (float)((double)(pr.schlick_R0 + (1 - pr.schlick_R0)) + pow5((double)(1 - vn)));   // helpers.h:316, Q8
+    float FDG = F * D * G;
+    double den = (double)(ln * vn) * DRT_PI;
+    float mx = fmaxf(0.0f, ln);
+    for (int c = 0; c < 3; c++) {
+      double sh = (0.4 * (double)Lcolor[c]) * (double)mx + ((0.8 * (double)Lcolor[c]) * (double)FDG) / den;
+      ray_color[c] = (double)shape_color[c] * sh;
+    }
+  } else if (pr.model == 3) {                                       // raw
+    for (int c = 0; c < 3; c++) ray_color[c] = shape_color[c];
+  } else {                                                          // Lambert + Phong :943-948
+    Vec<R> rr = normalized(R(-1) * sray + (R(2) * dot(normal, sray)) * normal);   // :856
+    double lam = fmax(0.0, (double)dot(normal, sdir));
+    double base = fmax(0.0, (double)dot(rr, e));
+    double spec;
+    if (phong == 10.0f) { const double b2 = base * base, b4 = b2 * b2; spec = b4 * b4 * b2; }   // the reference's fixed exponent (:72)
+    else spec = drt_pow(base, (double)phong);
+    for (int c = 0; c < 3; c++) {
+      double sh = (double)Lcolor[c] * lam + (double)Lcolor[c] * spec;
+      ray_color[c] = (double)shape_color[c] * sh;
+    }
+  }
+}
+
+// A rayColor invocation (render_final_project.cpp:487-961) is processed in two steps so the
+// warp can regroup between them (render_wave): traceRay() finds the closest hit
+// (:491-544), shadeHit() does everything after it (:546-960).
+//
 // Every invocation ADDS exactly one k-weighted term to the sample's colour (emissive
-// term or the hits-averaged light sum) and spawns up to brdf_samples+1 child rays;
-// the children are returned to the caller, which owns the scheduling.
-//   children[0..n_out) : child tasks in the reference's call order
-//   add / has_add      : the term to accumulate
-//   hit_any            : any_intersect of this invocation
-//   motion             : -1 unless this task is on the "last invocation" chain that
-//                        decides in_motion (quirk Q4), else the new flag value
+// term or the hits-averaged light sum) and spawns up to brdf_samples+1 child rays; the
+// children are returned to the caller, which owns the scheduling.
+template <typename R>
+struct alignas(16) HitTask {
+  Task<R> T;
+  float t;
+  int geom;
+  int inside;
+  int checker_sel;
+};
+
+// Returns true when the ray hit something (h filled in).  `motion` is -1 unless this task is
+// on the "last invocation" chain that decides in_motion (quirk Q4), else the new flag value.
 template <typename R, bool COUNT>
-__device__ void processRay(const Params<R>& P, const Task<R>& T, Task<R>* stack, int& n_out, double (&add)[3], bool& has_add,
-                           bool& hit_any, int& motion, bool& aborted, Counts& cnt) {
+__device__ inline bool traceRay(const Params<R>& P, const Task<R>& T, HitRec& h, int& motion, Counts& cnt) {
+  motion = -1;
+  if (T.depth == 0) return false;                                       // :489
+  if (COUNT) cnt.rays++;
+  Moved<R> mv; mv.val = T.val; mv.time = (R)T.dt; mv.velocity_mode = (P.blur_mode == 1 && T.dt != 0.0f);
+  closestHit<R, COUNT>(P, mv, T.dir, T.org, h, cnt);
+  if (T.chain) motion = 0;                                              // :519
+  if (h.geom < 0) return false;                                         // :541-544
+  if (T.chain) motion = (P.prims[P.geoms[h.geom].owner].flags & 2) ? 1 : 0;   // DRT_FLAG_MOTION, :564
+  return true;
+}
+
+//   stack[0..n_out) : child tasks in the reference's call order
+//   add / has_add   : the term to accumulate
+template <typename R, bool COUNT>
+__device__ void shadeHit(const Params<R>& P, const Task<R>& T, const HitRec& h, Task<R>* stack, int& n_out, double (&add)[3],
+                         bool& has_add, bool& aborted, Counts& cnt) {
   int sp = 0;
-  n_out = 0; has_add = false; hit_any = false; motion = -1;
+  n_out = 0; has_add = false;
   add[0] = add[1] = add[2] = 0.0;
   Moved<R> mv; mv.val = T.val; mv.time = (R)T.dt; mv.velocity_mode = (P.blur_mode == 1 && T.dt != 0.0f);
   do {
-    if (T.depth == 0) continue;                                         // :489
-    if (COUNT) cnt.rays++;
     const Vec<R> ray = T.dir, eye = T.org;
     const float k = T.k;
-    HitRec h;
-    closestHit<R, COUNT>(P, mv, ray, eye, h, cnt);
-    if (T.chain) motion = 0;                                       // :519
-    if (h.geom < 0) continue;                                           // :541-544
-    hit_any = true;
     const Geom<R>& g = P.geoms[h.geom];
     const PrimD<R>& pr = P.prims[g.owner];
-    if (T.chain) motion = (pr.flags & 2) ? 1 : 0;                       // DRT_FLAG_MOTION, :564
 
     const Vec<R> isectP = eye + (R)h.t * ray;                           // :548
     // ---- getNorm of the hit class ------------------------------------------------
@@ -590,7 +694,7 @@ __device__ void processRay(const Params<R>& P, const Task<R>& T, Task<R>* stack,
             int sample_limit = 10;
             while (dot(sample_refl, normal) <= R(0)) {
               if (sample_limit < 0) { aborted = true; break; }          // throws :724-740
-              float multiplier = (float)pow(2.0, (double)(11 - sample_limit));
+              float multiplier = ldexpf(1.0f, 11 - sample_limit);                     // pow(2, 11 - sample_limit)
               gloss_ray = refl_ray * (R)multiplier;
               length_vector = normalized(cross(gloss_ray, mk<R>(1, 0, 0)));
               if (isZero(length_vector)) length_vector = cross(gloss_ray, mk<R>(0, 0, 1));
@@ -628,14 +732,14 @@ __device__ void processRay(const Params<R>& P, const Task<R>& T, Task<R>* stack,
     if (pr.flags & 1) {                                                 // hit a light shape :775-789
       if (pr.name == 2) {                                               // spherelight
         float hitdot = (float)dot(in, normalized(shiftPoint(mv, 0, pr.vel, pr.center) - isectP));
-        double f = 0.1 * pow((double)hitdot, 1.0) + 0.05 * pow((double)hitdot, 5.0) + 0.9;
+        double f = 0.1 * (double)hitdot + 0.05 * pow5((double)hitdot) + 0.9;
         for (int c = 0; c < 3; c++) add[c] += ((double)k * (double)shape_color[c]) * f;
         has_add = true;
       }
       if (pr.name == 3) {                                               // rectanglelight
         float dist = (float)((double)(norm(isectP - pr.eA) + norm(isectP - pr.eB) + norm(isectP - pr.eC) + norm(isectP - pr.eD)) /
                              (double)pr.e_den);
-        double f = 0.1 * pow((double)dist, 1.0) + 0.05 * pow((double)dist, 5.0) + 0.9;
+        double f = 0.1 * (double)dist + 0.05 * pow5((double)dist) + 0.9;
         for (int c = 0; c < 3; c++) add[c] += ((double)k * (double)shape_color[c]) * f;
         has_add = true;
       }
@@ -653,32 +757,8 @@ __device__ void processRay(const Params<R>& P, const Task<R>& T, Task<R>* stack,
       Vec<R> sray;
       if (L.type == 0) sray = L.center - isectP;                        // pointLight geometry.cpp:2751-2754
       else if (L.type == 2) sray = rectSample<R>(L.A, L.B, L.D, T.path, rng_dim_light(li, 0)) - isectP;   // :2845-2849
-      else {                                                            // sphereLight geometry.cpp:2770-2826 (returns the POINT, Q10)
-        int attempt = 0;
-        double theta = 2 * DRT_PI * (double)rng_u01(T.path, rng_dim_light(li, attempt));
-        double phi = acos(1 - 2 * (double)rng_u01(T.path, rng_dim_light(li, attempt) + 1));
-        Vec<R> dirv = mk<R>((R)(sin(phi) * cos(theta)), (R)(sin(phi) * sin(theta)), (R)cos(phi));
-        Vec<R> tmp = (R)L.radius * dirv + L.center;
-        int sample_limit = 20;
-        const Vec<R> pc = isectP - L.center;
-        for (;;) {
-          Vec<R> d = tmp - L.center;
-          bool bad = dot(d, pc) < R(0) || (L.use_baxis && dot(d, L.baxis) < R(0));
-          if (!bad) break;
-          if (sample_limit < 0) { aborted = true; break; }              // throws geometry.cpp:2785-2789
-          Vec<R> rev = (R)(-L.radius) * dirv + L.center;
-          Vec<R> dr = rev - L.center;
-          bool ok = dot(dr, pc) >= R(0) && (!L.use_baxis || dot(dr, L.baxis) >= R(0));
-          if (ok) { tmp = rev; break; }
-          attempt++;
-          theta = 2 * DRT_PI * (double)rng_u01(T.path, rng_dim_light(li, attempt));
-          phi = acos(1 - 2 * (double)rng_u01(T.path, rng_dim_light(li, attempt) + 1));
-          dirv = mk<R>((R)(sin(phi) * cos(theta)), (R)(sin(phi) * sin(theta)), (R)cos(phi));
-          tmp = (R)L.radius * dirv + L.center;
-          sample_limit--;
-        }
-        if (aborted) break;
-        sray = tmp;
+      else {                                                            // sphereLight (returns the POINT, Q10)
+        if (!sampleSphereLight<R>(L, isectP, T.path, li, sray)) { aborted = true; break; }
       }
       const float t_max = (float)norm(sray);                            // :804
       const Vec<R> sdir = normalized(sray);
@@ -781,50 +861,7 @@ __device__ void processRay(const Params<R>& P, const Task<R>& T, Task<R>* stack,
       if (COUNT) cnt.shade_evals++;
       // ---- BRDF (:894-948) ---------------------------------------------------------
       double ray_color[3];
-      if (pr.model == 1) {                                              // oren-nayar
-        float vn = (float)dot(e, normal);
-        float ln = (float)dot(sdir, normal);
-        float irradiance = fmaxf(0.0f, ln);
-        float vn_theta = acosf(vn);
-        float ln_theta = acosf(ln);
-        float angleDiff = (float)fmax(0.0, (double)dot(normalized(e - normal * (R)vn), normalized(sray - normal * (R)ln)));
-        float alpha = fmaxf(vn_theta, ln_theta);
-        float beta = fminf(vn_theta, ln_theta);
-        float f = pr.on_A + pr.on_B * angleDiff * sinf(alpha) * tanf(beta);
-        for (int c = 0; c < 3; c++) ray_color[c] = (((double)shape_color[c] * (double)L.color[c]) * (double)irradiance) * (double)f;
-      } else if (pr.model == 2) {                                       // cook-torrance
-        Vec<R> H = normalized(e + sray);                                // unnormalised sray (Q9)
-        float hn = (float)fmax(0.0, (double)dot(normal, H));
-        float vh = (float)dot(e, H);
-        float vn = (float)dot(e, normal);
-        float ln = (float)dot(sdir, normal);
-        float alpha = acosf(hn);
-        double r2 = (double)pr.roughness * (double)pr.roughness;
-        double ca = (double)cosf(alpha);
-        double ta = (double)(tanf(alpha) / pr.roughness);
-        float D = (float)(1.0 / (r2 * (ca * ca * ca * ca)) * exp(-(ta * ta)));
-        float G1 = (float)(2.0 * hn * vn / vh);
-        float G2 = (float)(2.0 * hn * ln / vh);
-        float G = fminf(1.0f, fminf(G1, G2));
-        float F = (float)((double)(pr.schlick_R0 + (1 - pr.schlick_R0)) + pow((double)(1 - vn), 5.0));   // helpers.h:316, Q8
-        float FDG = F * D * G;
-        double den = (double)(ln * vn) * DRT_PI;
-        float mx = fmaxf(0.0f, ln);
-        for (int c = 0; c < 3; c++) {
-          double sh = (0.4 * (double)L.color[c]) * (double)mx + ((0.8 * (double)L.color[c]) * (double)FDG) / den;
-          ray_color[c] = (double)shape_color[c] * sh;
-        }
-      } else if (pr.model == 3) {                                       // raw
-        for (int c = 0; c < 3; c++) ray_color[c] = shape_color[c];
-      } else {                                                          // Lambert + Phong :943-948
-        Vec<R> rr = normalized(R(-1) * sray + (R(2) * dot(normal, sray)) * normal);   // :856
-        double lam = fmax(0.0, (double)dot(normal, sdir));
-        double spec = pow(fmax(0.0, (double)dot(rr, e)), (double)P.phong);
-        for (int c = 0; c < 3; c++) {
-          double sh = (double)L.color[c] * lam + (double)L.color[c] * spec;
-          ray_color[c] = (double)shape_color[c] * sh;
-        }
-      }
+      evalBRDF<R>(pr, L.color, shape_color, e, normal, sray, sdir, P.phong, ray_color);
       // !ray_color.isApprox(0): exact-zero test; NaN counts as a hit (:950-954, Q6)
       double sq = ray_color[0] * ray_color[0] + (ray_color[1] * ray_color[1] + ray_color[2] * ray_color[2]);
       if (!(sq <= 0.0)) { hits++; for (int c = 0; c < 3; c++) tmp_color[c] += (double)k * ray_color[c]; }
@@ -860,7 +897,7 @@ __device__ void processRay(const Params<R>& P, const Task<R>& T, Task<R>* stack,
 #define SS_NINF(c) (16384u << (c))
 
 template <typename R>
-__device__ inline void primaryRay(const Params<R>& P, long long gidx, Vec<R>& org, Vec<R>& dir, uint32_t& skey, int& pi, int& pj,
+__device__ __noinline__ void primaryRay(const Params<R>& P, long long gidx, Vec<R>& org, Vec<R>& dir, uint32_t& skey, int& pi, int& pj,
                                   int& px, int& py) {
   const int s = (int)(gidx % P.spp);
   const int pt = (int)(gidx / P.spp);
@@ -893,7 +930,10 @@ __global__ void __launch_bounds__(128, 3) render_wave(const __grid_constant__ Pa
   __shared__ unsigned int s_flags[4][DRT_BATCH];
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  Task<R>* pool = (Task<R>*)P.pool_raw + (size_t)(blockIdx.x * 4 + wib) * DRT_POOL_CAP;
+  // per-warp scratch in global memory: [ DRT_POOL_CAP ray tasks | 64 hit tasks ]
+  char* wbase = (char*)P.pool_raw + (size_t)(blockIdx.x * 4 + wib) * (DRT_POOL_CAP * sizeof(Task<R>) + 64 * sizeof(HitTask<R>));
+  Task<R>* pool = (Task<R>*)wbase;
+  HitTask<R>* hits = (HitTask<R>*)(wbase + DRT_POOL_CAP * sizeof(Task<R>));
   unsigned long long(*acc)[3] = s_acc[wib];
   unsigned int* sfl = s_flags[wib];
   const long long n_batches = (P.sample_count + DRT_BATCH - 1) / DRT_BATCH;
@@ -926,51 +966,77 @@ __global__ void __launch_bounds__(128, 3) render_wave(const __grid_constant__ Pa
 
     for (int phase = 0; phase < 2; phase++) {
       // ---- drain the pool ----------------------------------------------------------
-      while (count > 0) {
-        const int take = min(count, 32);
-        const bool active = lane < take;
-        Task<R> kids[DRT_MAX_CHILDREN];
-        int nk = 0;
-        if (active) {
-          const Task<R> T = pool[count - 1 - lane];
-          const unsigned int f = ((volatile unsigned int*)sfl)[T.slot];
-          if (!(f & SF_ABORT)) {                                        // an aborted sample spawns no more work (Q15)
-            double add[3]; bool has_add, hit_any, aborted = false; int motion;
-            processRay<R, COUNT>(P, T, kids, nk, add, has_add, hit_any, motion, aborted, cnt);
-            if (aborted) { atomicOr(&sfl[T.slot], SF_ABORT); nk = 0; }
-            else {
+      // Two alternating steps, each run with as many lanes as there is work:
+      //   TRACE: pop <=32 rays, closest hit each, compact the HITS into the warp's hit buffer
+      //          (rays that miss are finished: they only update the in_motion chain flag);
+      //   SHADE: once 32 hits are waiting (or no rays are left), shade 32 of them and compact
+      //          their child rays back into the pool.
+      int nhits = 0;
+      while (count > 0 || nhits > 0) {
+        while (count > 0 && nhits < 32) {                               // TRACE
+          const int take = min(count, 32);
+          const bool active = lane < take;
+          bool hit = false;
+          HitTask<R> H;
+          if (active) {
+            H.T = pool[count - 1 - lane];
+            const unsigned int f = ((volatile unsigned int*)sfl)[H.T.slot];
+            if (!(f & SF_ABORT)) {                                      // an aborted sample spawns no more work (Q15)
+              HitRec h; int motion;
+              hit = traceRay<R, COUNT>(P, H.T, h, motion, cnt);
               unsigned int orf = 0;
-              if (has_add) {
-                for (int c = 0; c < 3; c++) {
-                  const double v = add[c];
-                  if (v != v) orf |= SS_NAN(c);
-                  else if (v > 1073741824.0) orf |= (isinf(v) ? SS_PINF(c) : 0u), atomicAdd(&acc[T.slot][c], (unsigned long long)(1ll << 62));
-                  else if (v < -1073741824.0) orf |= (isinf(v) ? SS_NINF(c) : 0u), atomicAdd(&acc[T.slot][c], (unsigned long long)(-(1ll << 62)));
-                  else atomicAdd(&acc[T.slot][c], (unsigned long long)__double2ll_rn(v * 4294967296.0));
-                }
-              }
-              if ((T.flags & 1) && hit_any) orf |= SS_HIT;
+              if ((H.T.flags & 1) && hit) orf |= SS_HIT;
               if (motion == 1) orf |= SS_MOTION;
-              if (orf) atomicOr(&sfl[T.slot], orf);
-              if (motion == 0) atomicAnd(&sfl[T.slot], ~SS_MOTION);
+              if (orf) atomicOr(&sfl[H.T.slot], orf);
+              if (motion == 0) atomicAnd(&sfl[H.T.slot], ~SS_MOTION);
+              H.t = h.t; H.geom = h.geom; H.inside = h.inside; H.checker_sel = h.checker_sel;
             }
           }
+          count -= take;
+          const unsigned int hm = __ballot_sync(FULL, hit);
+          if (hit) hits[nhits + __popc(hm & ((1u << lane) - 1u))] = H;
+          nhits += __popc(hm);
+          __syncwarp();
         }
-        count -= take;
-        // ---- compact the children back (warp inclusive scan of nk) -----------------
-        int incl = nk;
+        if (nhits > 0) {                                                // SHADE
+          const int take = min(nhits, 32);
+          const bool active = lane < take;
+          Task<R> kids[DRT_MAX_CHILDREN];
+          int nk = 0;
+          if (active) {
+            const HitTask<R> H = hits[nhits - 1 - lane];
+            HitRec h; h.t = H.t; h.geom = H.geom; h.inside = H.inside; h.checker_sel = H.checker_sel;
+            double add[3]; bool has_add, aborted = false;
+            shadeHit<R, COUNT>(P, H.T, h, kids, nk, add, has_add, aborted, cnt);
+            if (aborted) { atomicOr(&sfl[H.T.slot], SF_ABORT); nk = 0; }
+            else if (has_add) {
+              unsigned int orf = 0;
+              for (int c = 0; c < 3; c++) {
+                const double v = add[c];
+                if (v != v) orf |= SS_NAN(c);
+                else if (v > 1073741824.0) orf |= (isinf(v) ? SS_PINF(c) : 0u), atomicAdd(&acc[H.T.slot][c], (unsigned long long)(1ll << 62));
+                else if (v < -1073741824.0) orf |= (isinf(v) ? SS_NINF(c) : 0u), atomicAdd(&acc[H.T.slot][c], (unsigned long long)(-(1ll << 62)));
+                else atomicAdd(&acc[H.T.slot][c], (unsigned long long)__double2ll_rn(v * 4294967296.0));
+              }
+              if (orf) atomicOr(&sfl[H.T.slot], orf);
+            }
+          }
+          nhits -= take;
+          // compact the children back into the pool (warp inclusive scan of nk)
+          int incl = nk;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += v; }
-        const int total = __shfl_sync(FULL, incl, 31);
-        if (count + total > DRT_POOL_CAP) {                             // cannot happen within the validated bounds
-          if (nk) atomicOr(&sfl[kids[0].slot], SF_ABORT);
-          if (lane == 0) *P.overflow = 1;
-        } else {
-          const int base = count + incl - nk;
-          for (int j = 0; j < nk; j++) pool[base + j] = kids[j];
-          count += total;
+          for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += v; }
+          const int total = __shfl_sync(FULL, incl, 31);
+          if (count + total > DRT_POOL_CAP) {                           // cannot happen within the validated bounds
+            if (nk) atomicOr(&sfl[kids[0].slot], SF_ABORT);
+            if (lane == 0) *P.overflow = 1;
+          } else {
+            const int base = count + incl - nk;
+            for (int j = 0; j < nk; j++) pool[base + j] = kids[j];
+            count += total;
+          }
+          __syncwarp();
         }
-        __syncwarp();
       }
       if (phase == 1 || P.blur_samples <= 0) break;
       // ---- motion blur: re-trace the samples whose in_motion flag ended up set --------
@@ -995,7 +1061,7 @@ __global__ void __launch_bounds__(128, 3) render_wave(const __grid_constant__ Pa
             float dt = frame_sample - (float)P.frame;
             float val = 0;                                              // uninitialised in the reference below frame_prism (Q16)
             if (P.blur_mode == 0 && P.frame >= P.frame_prism) {
-              if (P.frame >= P.frame_blur) val = (float)((double)(P.move_per_frame * dt) + (double)P.accel_t * pow((double)dt, 3.0));
+              if (P.frame >= P.frame_blur) val = (float)((double)(P.move_per_frame * dt) + (double)P.accel_t * ((double)dt * (double)dt * (double)dt));
               else val = P.move_per_frame * dt;
             }
             T.val = val; T.dt = dt; T.path = rng_key_child(skey, 1 + m);
