@@ -114,6 +114,7 @@ void primBounds(const drt_prim& p, double lo[3], double hi[3]) {
 template <typename R>
 struct HostScene {
   std::vector<NodeD<R>> nodes;
+  std::vector<float4> gbounds;
   std::vector<Geom<R>> geoms;
   std::vector<PrimD<R>> prims;
   std::vector<LightD<R>> lights;
@@ -233,6 +234,13 @@ int flatten(const drt_prim* prims, int n_prims, const drt_light* lights, int n_l
     if (rn.leaf) { nd.first = geom_start[rn.first]; nd.count = geom_start[rn.first + rn.count] - nd.first; }
     hs.nodes.push_back(nd);
   }
+  hs.gbounds.clear();
+  for (const Geom<R>& g : hs.geoms) {
+    float4 lo = g.blo, hi = g.bhi;
+    const int meta = (g.type & 0xff) | (g.owner << 8);
+    memcpy(&lo.w, &meta, sizeof(int));
+    hs.gbounds.push_back(lo); hs.gbounds.push_back(hi);
+  }
   for (size_t k = 0; k < hs.nodes.size(); k++) {
     NodeD<R>& nd = hs.nodes[k];
     if (nd.leaf) { for (int gi = nd.first; gi < nd.first + nd.count; gi++) hs.geoms[gi].leaf = (int)k; }
@@ -266,6 +274,7 @@ int flatten(const drt_prim* prims, int n_prims, const drt_light* lights, int n_l
 template <typename R>
 struct DevScene {
   Geom<R>* geoms = nullptr; PrimD<R>* prims = nullptr; LightD<R>* lights = nullptr; NodeD<R>* nodes = nullptr;
+  float4* gbounds = nullptr;
   int n_geoms = 0, n_prims = 0, n_lights = 0, n_nodes = 0;
 };
 
@@ -275,6 +284,11 @@ int upload(const HostScene<R>& hs, DevScene<R>& ds) {
     if (ds.geoms) cudaFree(ds.geoms);
     CK(cudaMalloc(&ds.geoms, sizeof(Geom<R>) * std::max<size_t>(1, hs.geoms.size())));
   }
+  if ((int)hs.geoms.size() != ds.n_geoms || !ds.gbounds) {
+    if (ds.gbounds) cudaFree(ds.gbounds);
+    CK(cudaMalloc(&ds.gbounds, sizeof(float4) * std::max<size_t>(2, hs.gbounds.size())));
+  }
+  if (!hs.gbounds.empty()) CK(cudaMemcpy(ds.gbounds, hs.gbounds.data(), sizeof(float4) * hs.gbounds.size(), cudaMemcpyHostToDevice));
   if ((int)hs.prims.size() != ds.n_prims || !ds.prims) {
     if (ds.prims) cudaFree(ds.prims);
     CK(cudaMalloc(&ds.prims, sizeof(PrimD<R>) * std::max<size_t>(1, hs.prims.size())));
@@ -385,7 +399,7 @@ void fillParams(Params<R>& P, const drt_scene* s, const DevScene<R>& ds, const d
   f3(P.bluesky, st.bluesky); f3(P.redsky, st.redsky);
   P.saturation = st.saturation; P.clouddist = st.clouddist; P.cloudhoff = st.cloudhoff;
   P.x0 = tile.x0; P.y0 = tile.y0; P.w = tile.width; P.h = tile.height;
-  P.geoms = ds.geoms; P.n_geoms = ds.n_geoms; P.nodes = ds.nodes; P.n_nodes = ds.n_nodes; P.prims = ds.prims; P.lights = ds.lights; P.n_lights = ds.n_lights;
+  P.geoms = ds.geoms; P.n_geoms = ds.n_geoms; P.gbounds = ds.gbounds; P.nodes = ds.nodes; P.n_nodes = ds.n_nodes; P.prims = ds.prims; P.lights = ds.lights; P.n_lights = ds.n_lights;
   P.tex = s->d_tex; P.texdims = s->d_texdims;
 }
 
@@ -626,7 +640,7 @@ void drt_scene_destroy(drt_scene* s) {
   if (s->stream) cudaStreamSynchronize(s->stream);
   for (auto t : s->tex_objs) cudaDestroyTextureObject(t);
   for (auto a : s->tex_arrays) cudaFreeArray(a);
-  void* ptrs[] = {s->dd.geoms, s->dd.prims, s->dd.lights, s->dd.nodes, s->df.geoms, s->df.prims, s->df.lights, s->df.nodes, s->d_tex, s->d_texdims,
+  void* ptrs[] = {s->dd.gbounds, s->df.gbounds, s->dd.geoms, s->dd.prims, s->dd.lights, s->dd.nodes, s->df.geoms, s->df.prims, s->df.lights, s->df.nodes, s->d_tex, s->d_texdims,
                   s->samples, s->need, s->bg, s->out_u8, s->out_f32, s->counts, s->pool, s->batch_counter, s->overflow};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (s->ev0) cudaEventDestroy(s->ev0);

@@ -41,9 +41,27 @@ template <typename R> __host__ __device__ inline Vec<R> operator/(Vec<R> a, R s)
 // Eigen's unrolled 3-coefficient reduction: c0 + (c1 + c2)
 template <typename R> __host__ __device__ inline R dot(Vec<R> a, Vec<R> b) { return a.x * b.x + (a.y * b.y + a.z * b.z); }
 template <typename R> __host__ __device__ inline R norm(Vec<R> a) { return sqrt(dot(a, a)); }
+// x / s for three numerators sharing one divisor: one IEEE division for the reciprocal, then
+// per numerator q = x*r refined by two fused steps (rem = x - q*s; q += rem*r), which yields
+// the correctly rounded quotient -- the same bits as the reference's three divisions -- at a
+// third of the cost of three software double divides.
+__device__ __forceinline__ double div_shared(double x, double s, double r) {
+  const double q = x * r;
+  const double rem = fma(-q, s, x);
+  return fma(rem, r, q);
+}
 template <typename R> __host__ __device__ inline Vec<R> normalized(Vec<R> a) {  // Eigen >= 3.3 semantics
   R z = dot(a, a);
-  if (z > R(0)) return a / (R)sqrt(z);
+  if (z > R(0)) {
+#if defined(__CUDA_ARCH__) && !defined(DRT_OLD_NORMALIZE)
+    if (sizeof(R) == 8) {
+      const double s = sqrt((double)z);
+      const double r = 1.0 / s;
+      return mk<R>((R)div_shared((double)a.x, s, r), (R)div_shared((double)a.y, s, r), (R)div_shared((double)a.z, s, r));
+    }
+#endif
+    return a / (R)sqrt(z);
+  }
   return a;
 }
 template <typename R> __host__ __device__ inline Vec<R> cross(Vec<R> a, Vec<R> b) {
@@ -153,6 +171,7 @@ struct Params {
   int x0, y0, w, h;
   // scene
   const Geom<R>* geoms; int n_geoms;
+  const float4* gbounds;    // 2 per geom: (lo.xyz, meta) (hi.xyz, -) for the slab filter; meta = type | owner << 8
   const NodeD<R>* nodes; int n_nodes;
   const PrimD<R>* prims;
   const LightD<R>* lights; int n_lights;

@@ -222,8 +222,8 @@ __device__ inline bool slabMayHit(const float4 blo, const float4 bhi, const floa
 // blur (mv.val != 0) is the reference tree walked node by node: bumpBVH widens leaf
 // boxes but not interior ones (quirk Q14), which can cull a moved rectangle.
 template <typename R, bool COUNT>
-__device__ inline void closestHit(const Params<R>& P, const Moved<R>& mv, const Vec<R>& ray, const Vec<R>& start,
-                                  HitRec& h, Counts& cnt) {
+__device__ inline void closestHit(const Params<R>& P, const float4* __restrict__ gb, const Moved<R>& mv, const Vec<R>& ray,
+                                  const Vec<R>& start, HitRec& h, Counts& cnt) {
   h.t = FLT_MAX; h.geom = -1; h.inside = 0; h.checker_sel = 0;
   if (mv.val == 0.0f) {
     // Two passes per group of 32 geoms: (1) the slab filter runs over the group in
@@ -237,11 +237,12 @@ __device__ inline void closestHit(const Params<R>& P, const Moved<R>& mv, const 
     for (int g0 = 0; g0 < n; g0 += 32) {
       const int g1 = min(n, g0 + 32);
       unsigned int mask = 0;
-      for (int gi = g0; gi < g1; gi++) {
-        const Geom<R>& g = P.geoms[gi];
-        if (g.type == G_HOLE) continue;
-        if (cull && !slabMayHit(g.blo, g.bhi, ox, oy, oz, ix, iy, iz, FLT_MAX)) continue;
-        mask |= 1u << (gi - g0);
+#pragma unroll 4
+      for (int gi = g0; gi < g1; gi++) {                                // branch-free: predicate -> mask bit
+        const float4 lo = gb[2 * gi], hi = gb[2 * gi + 1];
+        const int meta = __float_as_int(lo.w);
+        const bool ok = ((meta & 0xff) != G_HOLE) && (!cull || slabMayHit(lo, hi, ox, oy, oz, ix, iy, iz, FLT_MAX));
+        mask |= (ok ? 1u : 0u) << (gi - g0);
       }
       while (mask) {
         const int gi = g0 + __ffs(mask) - 1;      // ascending = the reference's candidate order
@@ -367,8 +368,9 @@ __device__ inline bool geomShadow(const Params<R>& P, const Geom<R>& g, int gi, 
 // class test) and only a geom that DOES occlude is checked against the reference
 // gather, by running BoundingVolume::intersect on its leaf and every ancestor.
 template <typename R, bool COUNT>
-__device__ inline bool anyHit(const Params<R>& P, const Moved<R>& mv, const Vec<R>& gather_ray, const Vec<R>& gather_start,
-                              const Vec<R>& ray, const Vec<R>& start, float t_max, int skip_owner, Counts& cnt) {
+__device__ inline bool anyHit(const Params<R>& P, const float4* __restrict__ gb, const Moved<R>& mv, const Vec<R>& gather_ray,
+                              const Vec<R>& gather_start, const Vec<R>& ray, const Vec<R>& start, float t_max, int skip_owner,
+                              Counts& cnt) {
   const Vec<R> inv_ray = mk<R>(R(1) / gather_ray.x, R(1) / gather_ray.y, R(1) / gather_ray.z);   // sray.cwiseInverse() :813
   if (mv.val == 0.0f) {
     const float ox = (float)start.x, oy = (float)start.y, oz = (float)start.z;
@@ -380,11 +382,15 @@ __device__ inline bool anyHit(const Params<R>& P, const Moved<R>& mv, const Vec<
     for (int g0 = 0; g0 < n; g0 += 32) {
       const int g1 = min(n, g0 + 32);
       unsigned int mask = 0;
-      for (int gi = g0; gi < g1; gi++) {           // lock-step slab filter -> per-lane candidate mask
-        const Geom<R>& g = P.geoms[gi];
-        if (g.type == G_HOLE || g.owner == skip_owner) continue;   // an area light never shadows itself (832-837)
-        if (cull && !slabMayHit(g.blo, g.bhi, ox, oy, oz, ix, iy, iz, t_max * 1.0001f + 1e-4f)) continue;
-        mask |= 1u << (gi - g0);
+      const float t_lim = t_max * 1.0001f + 1e-4f;
+#pragma unroll 4
+      for (int gi = g0; gi < g1; gi++) {           // lock-step, branch-free slab filter -> per-lane candidate mask
+        const float4 lo = gb[2 * gi], hi = gb[2 * gi + 1];
+        const int meta = __float_as_int(lo.w);
+        // an area light never shadows itself (832-837)
+        const bool ok = ((meta & 0xff) != G_HOLE) && ((meta >> 8) != skip_owner) &&
+                        (!cull || slabMayHit(lo, hi, ox, oy, oz, ix, iy, iz, t_lim));
+        mask |= (ok ? 1u : 0u) << (gi - g0);
       }
       while (mask) {                                // each lane walks its own candidates
         const int gi = g0 + __ffs(mask) - 1;
@@ -565,12 +571,13 @@ struct alignas(16) HitTask {
 // Returns true when the ray hit something (h filled in).  `motion` is -1 unless this task is
 // on the "last invocation" chain that decides in_motion (quirk Q4), else the new flag value.
 template <typename R, bool COUNT>
-__device__ inline bool traceRay(const Params<R>& P, const Task<R>& T, HitRec& h, int& motion, Counts& cnt) {
+__device__ inline bool traceRay(const Params<R>& P, const float4* __restrict__ gb, const Task<R>& T, HitRec& h, int& motion,
+                                Counts& cnt) {
   motion = -1;
   if (T.depth == 0) return false;                                       // :489
   if (COUNT) cnt.rays++;
   Moved<R> mv; mv.val = T.val; mv.time = (R)T.dt; mv.velocity_mode = (P.blur_mode == 1 && T.dt != 0.0f);
-  closestHit<R, COUNT>(P, mv, T.dir, T.org, h, cnt);
+  closestHit<R, COUNT>(P, gb, mv, T.dir, T.org, h, cnt);
   if (T.chain) motion = 0;                                              // :519
   if (h.geom < 0) return false;                                         // :541-544
   if (T.chain) motion = (P.prims[P.geoms[h.geom].owner].flags & 2) ? 1 : 0;   // DRT_FLAG_MOTION, :564
@@ -580,8 +587,8 @@ __device__ inline bool traceRay(const Params<R>& P, const Task<R>& T, HitRec& h,
 //   stack[0..n_out) : child tasks in the reference's call order
 //   add / has_add   : the term to accumulate
 template <typename R, bool COUNT>
-__device__ void shadeHit(const Params<R>& P, const Task<R>& T, const HitRec& h, Task<R>* stack, int& n_out, double (&add)[3],
-                         bool& has_add, bool& aborted, Counts& cnt) {
+__device__ void shadeHit(const Params<R>& P, const float4* __restrict__ gb, const Task<R>& T, const HitRec& h, Task<R>* stack,
+                         int& n_out, double (&add)[3], bool& has_add, bool& aborted, Counts& cnt) {
   int sp = 0;
   n_out = 0; has_add = false;
   add[0] = add[1] = add[2] = 0.0;
@@ -765,7 +772,7 @@ __device__ void shadeHit(const Params<R>& P, const Task<R>& T, const HitRec& h, 
       if (COUNT) cnt.shadow_rays++;
       // candidates are gathered along the UNNORMALISED sray from isectP + sray*1e-3 (:814),
       // occlusion is tested along the normalised one from isectP + s^*1e-3 (:838)
-      if (anyHit<R, COUNT>(P, mv, sray, isectP + sray * R(1e-3), sdir, isectP + sdir * R(1e-3), t_max, L.prim_index, cnt))
+      if (anyHit<R, COUNT>(P, gb, mv, sray, isectP + sray * R(1e-3), sdir, isectP + sdir * R(1e-3), t_max, L.prim_index, cnt))
         continue;                                                       // :828-855
 
       // ---- texture (:859-893) ---------------------------------------------------
@@ -924,14 +931,32 @@ __device__ __noinline__ void primaryRay(const Params<R>& P, long long gidx, Vec<
   dir = focalPoint - eye_sample;
 }
 
+// Phase-locked persistent CTA.  All warps of the CTA run the same phase at the same time
+// (GEN -> TRACE -> SHADE, separated by __syncthreads), so the SM's instruction cache only has
+// to hold one phase's code: with free-running warps the 14k-instruction kernel saturated
+// the GPC instruction cache (ncu: gcc__cache_requests_type_instruction 95 % of peak,
+// sm__icc_request_hit_rate 62 %, 43 % of stall samples "no_instructions").
+#ifndef DRT_WAVE_WARPS
+#define DRT_WAVE_WARPS 12
+#endif
 template <typename R, bool COUNT>
-__global__ void __launch_bounds__(128, 3) render_wave(const __grid_constant__ Params<R> P) {
-  __shared__ unsigned long long s_acc[4][DRT_BATCH][3];
-  __shared__ unsigned int s_flags[4][DRT_BATCH];
+__global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, 1) render_wave(const __grid_constant__ Params<R> P) {
+  __shared__ unsigned long long s_acc[DRT_WAVE_WARPS][DRT_BATCH][3];
+  __shared__ unsigned int s_flags[DRT_WAVE_WARPS][DRT_BATCH];
+  // slab-filter table of the whole scene, staged once per persistent CTA (32 B per geom)
+  __shared__ float4 s_gb[2 * DRT_SMEM_GEOMS];
+  const float4* gb = P.gbounds;
+#ifndef DRT_NO_SMEM_GB
+  if (P.n_geoms <= DRT_SMEM_GEOMS) {
+    for (int i = threadIdx.x; i < 2 * P.n_geoms; i += blockDim.x) s_gb[i] = P.gbounds[i];
+    __syncthreads();
+    gb = s_gb;
+  }
+#endif
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   // per-warp scratch in global memory: [ DRT_POOL_CAP ray tasks | 64 hit tasks ]
-  char* wbase = (char*)P.pool_raw + (size_t)(blockIdx.x * 4 + wib) * (DRT_POOL_CAP * sizeof(Task<R>) + 64 * sizeof(HitTask<R>));
+  char* wbase = (char*)P.pool_raw + (size_t)(blockIdx.x * DRT_WAVE_WARPS + wib) * (DRT_POOL_CAP * sizeof(Task<R>) + 64 * sizeof(HitTask<R>));
   Task<R>* pool = (Task<R>*)wbase;
   HitTask<R>* hits = (HitTask<R>*)(wbase + DRT_POOL_CAP * sizeof(Task<R>));
   unsigned long long(*acc)[3] = s_acc[wib];
@@ -942,166 +967,178 @@ __global__ void __launch_bounds__(128, 3) render_wave(const __grid_constant__ Pa
   if (COUNT) { cnt.samples = 0; cnt.rays = 0; cnt.shadow_rays = 0; cnt.shade_evals = 0; cnt.noise_evals = 0; cnt.node_tests = 0;
                for (int i = 0; i < 6; i++) cnt.geom_tests[i] = 0; }
 
+  // warp-uniform state
+  bool have_batch = false, more_batches = true;
+  int count = 0, nhits = 0, phase = 0, n_valid = 0;
+  long long idx0 = 0;
+
   for (;;) {
-    long long b = 0;
-    if (lane == 0) b = (long long)atomicAdd(P.batch_counter, 1ull);
-    b = __shfl_sync(FULL, b, 0);
-    if (b >= n_batches) break;
-    const long long idx0 = b * DRT_BATCH;                               // chunk-local sample index of slot 0
-    const int n_valid = (int)min((long long)DRT_BATCH, P.sample_count - idx0);
-    for (int s = lane; s < DRT_BATCH; s += 32) { acc[s][0] = acc[s][1] = acc[s][2] = 0ull; sfl[s] = 0u; }
-    __syncwarp();
-
-    // ---- primary rays -> pool[0..n_valid) -----------------------------------------
-    for (int s = lane; s < n_valid; s += 32) {
-      Task<R> T; uint32_t skey; int pi, pj, px, py;
-      primaryRay<R>(P, P.sample_base + idx0 + s, T.org, T.dir, skey, pi, pj, px, py);
-      T.k = 1.0f; T.path = rng_key_child(skey, 0); T.val = 0.f; T.dt = 0.f; T.depth = (short)P.max_depth;
-      T.chain = 1; T.flags = 1; T.slot = (unsigned short)s; T.pad_ = 0;
-      pool[s] = T;
-      if (COUNT) cnt.samples++;
-    }
-    __syncwarp();
-    int count = n_valid;
-
-    for (int phase = 0; phase < 2; phase++) {
-      // ---- drain the pool ----------------------------------------------------------
-      // Two alternating steps, each run with as many lanes as there is work:
-      //   TRACE: pop <=32 rays, closest hit each, compact the HITS into the warp's hit buffer
-      //          (rays that miss are finished: they only update the in_motion chain flag);
-      //   SHADE: once 32 hits are waiting (or no rays are left), shade 32 of them and compact
-      //          their child rays back into the pool.
-      int nhits = 0;
-      while (count > 0 || nhits > 0) {
-        while (count > 0 && nhits < 32) {                               // TRACE
-          const int take = min(count, 32);
-          const bool active = lane < take;
-          bool hit = false;
-          HitTask<R> H;
-          if (active) {
-            H.T = pool[count - 1 - lane];
-            const unsigned int f = ((volatile unsigned int*)sfl)[H.T.slot];
-            if (!(f & SF_ABORT)) {                                      // an aborted sample spawns no more work (Q15)
-              HitRec h; int motion;
-              hit = traceRay<R, COUNT>(P, H.T, h, motion, cnt);
-              unsigned int orf = 0;
-              if ((H.T.flags & 1) && hit) orf |= SS_HIT;
-              if (motion == 1) orf |= SS_MOTION;
-              if (orf) atomicOr(&sfl[H.T.slot], orf);
-              if (motion == 0) atomicAnd(&sfl[H.T.slot], ~SS_MOTION);
-              H.t = h.t; H.geom = h.geom; H.inside = h.inside; H.checker_sel = h.checker_sel;
-            }
-          }
-          count -= take;
-          const unsigned int hm = __ballot_sync(FULL, hit);
-          if (hit) hits[nhits + __popc(hm & ((1u << lane) - 1u))] = H;
-          nhits += __popc(hm);
-          __syncwarp();
-        }
-        if (nhits > 0) {                                                // SHADE
-          const int take = min(nhits, 32);
-          const bool active = lane < take;
-          Task<R> kids[DRT_MAX_CHILDREN];
-          int nk = 0;
-          if (active) {
-            const HitTask<R> H = hits[nhits - 1 - lane];
-            HitRec h; h.t = H.t; h.geom = H.geom; h.inside = H.inside; h.checker_sel = H.checker_sel;
-            double add[3]; bool has_add, aborted = false;
-            shadeHit<R, COUNT>(P, H.T, h, kids, nk, add, has_add, aborted, cnt);
-            if (aborted) { atomicOr(&sfl[H.T.slot], SF_ABORT); nk = 0; }
-            else if (has_add) {
-              unsigned int orf = 0;
-              for (int c = 0; c < 3; c++) {
-                const double v = add[c];
-                if (v != v) orf |= SS_NAN(c);
-                else if (v > 1073741824.0) orf |= (isinf(v) ? SS_PINF(c) : 0u), atomicAdd(&acc[H.T.slot][c], (unsigned long long)(1ll << 62));
-                else if (v < -1073741824.0) orf |= (isinf(v) ? SS_NINF(c) : 0u), atomicAdd(&acc[H.T.slot][c], (unsigned long long)(-(1ll << 62)));
-                else atomicAdd(&acc[H.T.slot][c], (unsigned long long)__double2ll_rn(v * 4294967296.0));
-              }
-              if (orf) atomicOr(&sfl[H.T.slot], orf);
-            }
-          }
-          nhits -= take;
-          // compact the children back into the pool (warp inclusive scan of nk)
-          int incl = nk;
+    // ================= GEN: batch bookkeeping (rare) =================================
+    if (have_batch && count == 0 && nhits == 0) {                        // the batch's current trees are drained
+      bool to_blur = false;
+      if (phase == 0 && P.blur_samples > 0) {
+        // motion blur: re-trace the samples whose in_motion flag ended up set
+        // (render_final_project.cpp:1095-1210); the extra traces go through the same pool
+        int any_motion = 0;
+        for (int s2 = lane; s2 < n_valid; s2 += 32) any_motion |= ((sfl[s2] & (SS_MOTION | SF_ABORT)) == SS_MOTION);
+        to_blur = __any_sync(FULL, any_motion);
+      }
+      if (to_blur) {
+        for (int r = 0; r < DRT_BATCH / 32; r++) {
+          const int s2 = r * 32 + lane;
+          const bool mo = s2 < n_valid && ((sfl[s2] & (SS_MOTION | SF_ABORT)) == SS_MOTION);
+          int nb = mo ? P.blur_samples : 0;
+          int incl = nb;
 #pragma unroll
           for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += v; }
           const int total = __shfl_sync(FULL, incl, 31);
-          if (count + total > DRT_POOL_CAP) {                           // cannot happen within the validated bounds
-            if (nk) atomicOr(&sfl[kids[0].slot], SF_ABORT);
-            if (lane == 0) *P.overflow = 1;
-          } else {
-            const int base = count + incl - nk;
-            for (int j = 0; j < nk; j++) pool[base + j] = kids[j];
-            count += total;
+          if (mo) {
+            Task<R> T; uint32_t skey; int pi, pj, px, py;
+            primaryRay<R>(P, P.sample_base + idx0 + s2, T.org, T.dir, skey, pi, pj, px, py);
+            T.k = 1.0f; T.depth = (short)P.max_depth; T.chain = 0; T.flags = 0; T.slot = (unsigned short)s2; T.pad_ = 0;
+            for (int m = 0; m < nb; m++) {
+              float frame_sample = (float)((double)(float)P.frame + (double)rng_u01(skey, (uint32_t)m) * (double)P.frame_range);
+              float dt = frame_sample - (float)P.frame;
+              float val = 0;                                            // uninitialised in the reference below frame_prism (Q16)
+              if (P.blur_mode == 0 && P.frame >= P.frame_prism) {
+                if (P.frame >= P.frame_blur) val = (float)((double)(P.move_per_frame * dt) + (double)P.accel_t * ((double)dt * (double)dt * (double)dt));
+                else val = P.move_per_frame * dt;
+              }
+              T.val = val; T.dt = dt; T.path = rng_key_child(skey, 1 + m);
+              if (count + incl - nb + m < DRT_POOL_CAP) pool[count + incl - nb + m] = T;
+            }
           }
+          count = min(count + total, DRT_POOL_CAP);
           __syncwarp();
         }
-      }
-      if (phase == 1 || P.blur_samples <= 0) break;
-      // ---- motion blur: re-trace the samples whose in_motion flag ended up set --------
-      // (render_final_project.cpp:1095-1210); the extra traces go through the same pool
-      int any_motion = 0;
-      for (int s = lane; s < n_valid; s += 32) any_motion |= ((sfl[s] & (SS_MOTION | SF_ABORT)) == SS_MOTION);
-      if (!__any_sync(FULL, any_motion)) break;
-      for (int r = 0; r < DRT_BATCH / 32; r++) {
-        const int s = r * 32 + lane;
-        const bool mo = s < n_valid && ((sfl[s] & (SS_MOTION | SF_ABORT)) == SS_MOTION);
-        int nb = mo ? P.blur_samples : 0;
-        int incl = nb;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += v; }
-        const int total = __shfl_sync(FULL, incl, 31);
-        if (mo) {
-          Task<R> T; uint32_t skey; int pi, pj, px, py;
-          primaryRay<R>(P, P.sample_base + idx0 + s, T.org, T.dir, skey, pi, pj, px, py);
-          T.k = 1.0f; T.depth = (short)P.max_depth; T.chain = 0; T.flags = 0; T.slot = (unsigned short)s; T.pad_ = 0;
-          for (int m = 0; m < nb; m++) {
-            float frame_sample = (float)((double)(float)P.frame + (double)rng_u01(skey, (uint32_t)m) * (double)P.frame_range);
-            float dt = frame_sample - (float)P.frame;
-            float val = 0;                                              // uninitialised in the reference below frame_prism (Q16)
-            if (P.blur_mode == 0 && P.frame >= P.frame_prism) {
-              if (P.frame >= P.frame_blur) val = (float)((double)(P.move_per_frame * dt) + (double)P.accel_t * ((double)dt * (double)dt * (double)dt));
-              else val = P.move_per_frame * dt;
-            }
-            T.val = val; T.dt = dt; T.path = rng_key_child(skey, 1 + m);
-            if (count + incl - nb + m < DRT_POOL_CAP) pool[count + incl - nb + m] = T;
+        phase = 1;
+      } else {
+        // ---- per-sample results -----------------------------------------------------
+        for (int s2 = lane; s2 < n_valid; s2 += 32) {
+          const unsigned int f = sfl[s2];
+          double c[3];
+          for (int k = 0; k < 3; k++) {
+            c[k] = (double)(long long)acc[s2][k] * (1.0 / 4294967296.0);
+            const bool pinf = f & SS_PINF(k), ninf = f & SS_NINF(k);
+            if ((f & SS_NAN(k)) || (pinf && ninf)) c[k] = __longlong_as_double(0x7ff8000000000000ll);
+            else if (pinf) c[k] = __longlong_as_double(0x7ff0000000000000ll);
+            else if (ninf) c[k] = __longlong_as_double(0xfff0000000000000ll);
           }
+          uint32_t flags = 0;
+          if (f & SF_ABORT) flags |= SF_ABORT;
+          else if (!(f & SS_HIT)) {                                     // :1074-1094
+            c[0] = c[1] = c[2] = 0;                                     // default_col
+            if (P.perlin_cloud) {
+              Vec<R> o, d; uint32_t skey; int pi, pj, px, py;
+              primaryRay<R>(P, P.sample_base + idx0 + s2, o, d, skey, pi, pj, px, py);
+              int cx = min(max(pi - P.x0, 0), P.w), cy = min(max(pj - P.y0, 0), P.h);   // corner in the tile's (w+1)x(h+1) grid
+              flags |= SF_MISS | ((uint32_t)((cx - px) | ((cy - py) << 1)) << SF_CORNER_SHIFT);
+              if (P.need[cy * (P.w + 1) + cx] == 0) P.need[cy * (P.w + 1) + cx] = 1;   // benign race: all writers store 1
+            }
+          } else if (f & SS_MOTION) {
+            const double inv = (double)(P.blur_samples + 1);
+            c[0] /= inv; c[1] /= inv; c[2] /= inv;
+          }
+          P.samples[idx0 + s2] = make_float4((float)c[0], (float)c[1], (float)c[2], __uint_as_float(flags));
         }
-        count = min(count + total, DRT_POOL_CAP);
         __syncwarp();
+        have_batch = false;
       }
     }
-
-    // ---- per-sample results ------------------------------------------------------------
-    for (int s = lane; s < n_valid; s += 32) {
-      const unsigned int f = sfl[s];
-      double c[3];
-      for (int k = 0; k < 3; k++) {
-        c[k] = (double)(long long)acc[s][k] * (1.0 / 4294967296.0);
-        const bool pinf = f & SS_PINF(k), ninf = f & SS_NINF(k);
-        if ((f & SS_NAN(k)) || (pinf && ninf)) c[k] = __longlong_as_double(0x7ff8000000000000ll);
-        else if (pinf) c[k] = __longlong_as_double(0x7ff0000000000000ll);
-        else if (ninf) c[k] = __longlong_as_double(0xfff0000000000000ll);
-      }
-      uint32_t flags = 0;
-      if (f & SF_ABORT) flags |= SF_ABORT;
-      else if (!(f & SS_HIT)) {                                         // :1074-1094
-        c[0] = c[1] = c[2] = 0;                                         // default_col
-        if (P.perlin_cloud) {
-          Vec<R> o, d; uint32_t skey; int pi, pj, px, py;
-          primaryRay<R>(P, P.sample_base + idx0 + s, o, d, skey, pi, pj, px, py);
-          int cx = min(max(pi - P.x0, 0), P.w), cy = min(max(pj - P.y0, 0), P.h);   // corner in the tile's (w+1)x(h+1) grid
-          flags |= SF_MISS | ((uint32_t)((cx - px) | ((cy - py) << 1)) << SF_CORNER_SHIFT);
-          if (P.need[cy * (P.w + 1) + cx] == 0) P.need[cy * (P.w + 1) + cx] = 1;   // benign race: all writers store 1
+    if (!have_batch && more_batches) {                                   // claim the next batch of camera samples
+      long long b = 0;
+      if (lane == 0) b = (long long)atomicAdd(P.batch_counter, 1ull);
+      b = __shfl_sync(FULL, b, 0);
+      if (b >= n_batches) more_batches = false;
+      else {
+        idx0 = b * DRT_BATCH;                                            // chunk-local sample index of slot 0
+        n_valid = (int)min((long long)DRT_BATCH, P.sample_count - idx0);
+        for (int s2 = lane; s2 < DRT_BATCH; s2 += 32) { acc[s2][0] = acc[s2][1] = acc[s2][2] = 0ull; sfl[s2] = 0u; }
+        __syncwarp();
+        for (int s2 = lane; s2 < n_valid; s2 += 32) {                    // primary rays -> pool[0..n_valid)
+          Task<R> T; uint32_t skey; int pi, pj, px, py;
+          primaryRay<R>(P, P.sample_base + idx0 + s2, T.org, T.dir, skey, pi, pj, px, py);
+          T.k = 1.0f; T.path = rng_key_child(skey, 0); T.val = 0.f; T.dt = 0.f; T.depth = (short)P.max_depth;
+          T.chain = 1; T.flags = 1; T.slot = (unsigned short)s2; T.pad_ = 0;
+          pool[s2] = T;
+          if (COUNT) cnt.samples++;
         }
-      } else if (f & SS_MOTION) {
-        const double inv = (double)(P.blur_samples + 1);
-        c[0] /= inv; c[1] /= inv; c[2] /= inv;
+        __syncwarp();
+        count = n_valid; nhits = 0; phase = 0; have_batch = true;
       }
-      P.samples[idx0 + s] = make_float4((float)c[0], (float)c[1], (float)c[2], __uint_as_float(flags));
     }
-    __syncwarp();
+    if (!__syncthreads_or(have_batch ? 1 : 0)) break;                    // every warp idle, no batches left
+
+    // ================= TRACE: closest hits; the HITS are compacted into the hit buffer ====
+    // (rays that miss are finished: they only update the in_motion chain flag)
+    while (count > 0 && nhits < 32) {
+      const int take = min(count, 32);
+      const bool active = lane < take;
+      bool hit = false;
+      HitTask<R> H;
+      if (active) {
+        H.T = pool[count - 1 - lane];
+        const unsigned int f = ((volatile unsigned int*)sfl)[H.T.slot];
+        if (!(f & SF_ABORT)) {                                          // an aborted sample spawns no more work (Q15)
+          HitRec h; int motion;
+          hit = traceRay<R, COUNT>(P, gb, H.T, h, motion, cnt);
+          unsigned int orf = 0;
+          if ((H.T.flags & 1) && hit) orf |= SS_HIT;
+          if (motion == 1) orf |= SS_MOTION;
+          if (orf) atomicOr(&sfl[H.T.slot], orf);
+          if (motion == 0) atomicAnd(&sfl[H.T.slot], ~SS_MOTION);
+          H.t = h.t; H.geom = h.geom; H.inside = h.inside; H.checker_sel = h.checker_sel;
+        }
+      }
+      count -= take;
+      const unsigned int hm = __ballot_sync(FULL, hit);
+      if (hit) hits[nhits + __popc(hm & ((1u << lane) - 1u))] = H;
+      nhits += __popc(hm);
+      __syncwarp();
+    }
+    __syncthreads();
+
+    // ================= SHADE: 32 waiting hits -> radiance terms + child rays ================
+    if (nhits > 0) {
+      const int take = min(nhits, 32);
+      const bool active = lane < take;
+      Task<R> kids[DRT_MAX_CHILDREN];
+      int nk = 0;
+      if (active) {
+        const HitTask<R> H = hits[nhits - 1 - lane];
+        HitRec h; h.t = H.t; h.geom = H.geom; h.inside = H.inside; h.checker_sel = H.checker_sel;
+        double add[3]; bool has_add, aborted = false;
+        shadeHit<R, COUNT>(P, gb, H.T, h, kids, nk, add, has_add, aborted, cnt);
+        if (aborted) { atomicOr(&sfl[H.T.slot], SF_ABORT); nk = 0; }
+        else if (has_add) {
+          unsigned int orf = 0;
+          for (int c = 0; c < 3; c++) {
+            const double v = add[c];
+            if (v != v) orf |= SS_NAN(c);
+            else if (v > 1073741824.0) orf |= (isinf(v) ? SS_PINF(c) : 0u), atomicAdd(&acc[H.T.slot][c], (unsigned long long)(1ll << 62));
+            else if (v < -1073741824.0) orf |= (isinf(v) ? SS_NINF(c) : 0u), atomicAdd(&acc[H.T.slot][c], (unsigned long long)(-(1ll << 62)));
+            else atomicAdd(&acc[H.T.slot][c], (unsigned long long)__double2ll_rn(v * 4294967296.0));
+          }
+          if (orf) atomicOr(&sfl[H.T.slot], orf);
+        }
+      }
+      nhits -= take;
+      // compact the children back into the pool (warp inclusive scan of nk)
+      int incl = nk;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += v; }
+      const int total = __shfl_sync(FULL, incl, 31);
+      if (count + total > DRT_POOL_CAP) {                               // cannot happen within the validated bounds
+        if (nk) atomicOr(&sfl[kids[0].slot], SF_ABORT);
+        if (lane == 0) *P.overflow = 1;
+      } else {
+        const int base = count + incl - nk;
+        for (int j = 0; j < nk; j++) pool[base + j] = kids[j];
+        count += total;
+      }
+      __syncwarp();
+    }
+    __syncthreads();
   }
 
   if (COUNT) {

@@ -10,7 +10,7 @@ import numpy as np
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdrt.so")
+LIB_PATH = os.environ.get("DRT_LIB") or os.path.join(_HERE, "libdrt.so")   # DRT_LIB: A/B builds during tuning
 _lib = None
 
 EXPORTS = [
