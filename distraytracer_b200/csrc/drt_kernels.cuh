@@ -586,13 +586,49 @@ __device__ inline bool traceRay(const Params<R>& P, const float4* __restrict__ g
 
 //   stack[0..n_out) : child tasks in the reference's call order
 //   add / has_add   : the term to accumulate
+//
+// Shading one hit is itself split in three so that the shadow rays -- one per (hit, light)
+// pair -- can be spread over all lanes of the warp:
+//   shadeA     per hit : normal, refraction / reflection / glossy children, emissive term;
+//   shadowPair per pair: LightPrimitive::sampleRay + the occlusion test;
+//   shadeB     per hit : texture lookup + BRDF for the unoccluded lights, `hits` average.
+// The lane that ran shadeA for a hit also runs shadeB for it, so the hit's state stays in
+// registers (ShadeState); only the hit point and the pair results go through memory.
+template <typename R>
+struct ShadeState {
+  Vec<R> isectP, normal, e;
+  Moved<R> mv;
+  float shape_color[3];
+  float k;
+  int prim;
+  bool lights;     // the hit is not a light shape: the light loop has to run
+  bool aborted, early;
+  int hits;
+  double tmp[3];
+};
+
+template <typename R>
+struct alignas(16) PairIn {   // what a shadow pair needs to know about its hit
+  Vec<R> isectP;
+  uint32_t path;
+  float val, dt;
+  int want;
+};
+template <typename R>
+struct alignas(16) PairOut {
+  Vec<R> sray;
+  int state;      // 0 occluded, 1 visible, 2 the light sampler aborted (reference throws)
+  int pad_;
+};
+
 template <typename R, bool COUNT>
-__device__ void shadeHit(const Params<R>& P, const float4* __restrict__ gb, const Task<R>& T, const HitRec& h, Task<R>* stack,
-                         int& n_out, double (&add)[3], bool& has_add, bool& aborted, Counts& cnt) {
+__device__ void shadeA(const Params<R>& P, const Task<R>& T, const HitRec& h, Task<R>* stack, int& n_out, double (&add)[3],
+                       bool& has_add, bool& aborted, ShadeState<R>& S, Counts& cnt) {
   int sp = 0;
   n_out = 0; has_add = false;
   add[0] = add[1] = add[2] = 0.0;
   Moved<R> mv; mv.val = T.val; mv.time = (R)T.dt; mv.velocity_mode = (P.blur_mode == 1 && T.dt != 0.0f);
+  S.lights = false; S.aborted = false; S.early = false; S.hits = 0; S.tmp[0] = S.tmp[1] = S.tmp[2] = 0.0; S.mv = mv;
   do {
     const Vec<R> ray = T.dir, eye = T.org;
     const float k = T.k;
@@ -753,39 +789,54 @@ __device__ void shadeHit(const Params<R>& P, const float4* __restrict__ gb, cons
       continue;
     }
 
-    const Vec<R> e = normalized(eye - isectP);                          // :795
-    int hits = 0;
-    double tmp_color[3] = {0, 0, 0};
-    bool early_return = false;
-    bool have_tex = false;
-    for (int li = 0; li < P.n_lights && !early_return; li++) {
-      const LightD<R>& L = P.lights[li];
-      // ---- sampleRay (:802) ---------------------------------------------------
-      Vec<R> sray;
-      if (L.type == 0) sray = L.center - isectP;                        // pointLight geometry.cpp:2751-2754
-      else if (L.type == 2) sray = rectSample<R>(L.A, L.B, L.D, T.path, rng_dim_light(li, 0)) - isectP;   // :2845-2849
-      else {                                                            // sphereLight (returns the POINT, Q10)
-        if (!sampleSphereLight<R>(L, isectP, T.path, li, sray)) { aborted = true; break; }
-      }
-      const float t_max = (float)norm(sray);                            // :804
-      const Vec<R> sdir = normalized(sray);
-      if (COUNT) cnt.shadow_rays++;
-      // candidates are gathered along the UNNORMALISED sray from isectP + sray*1e-3 (:814),
-      // occlusion is tested along the normalised one from isectP + s^*1e-3 (:838)
-      if (anyHit<R, COUNT>(P, gb, mv, sray, isectP + sray * R(1e-3), sdir, isectP + sdir * R(1e-3), t_max, L.prim_index, cnt))
-        continue;                                                       // :828-855
+    S.isectP = isectP; S.normal = normal; S.e = normalized(eye - isectP);   // :795
+    S.shape_color[0] = shape_color[0]; S.shape_color[1] = shape_color[1]; S.shape_color[2] = shape_color[2];
+    S.k = k; S.prim = g.owner; S.lights = true;
+  } while (0);
+  n_out = sp;
+}
 
+// LightPrimitive::sampleRay (:802) + the shadow test (:806-855) for one (hit, light) pair.
+template <typename R, bool COUNT>
+__device__ void shadowPair(const Params<R>& P, const float4* __restrict__ gb, const PairIn<R>& in, int li, PairOut<R>& out, Counts& cnt) {
+  const LightD<R>& L = P.lights[li];
+  const Vec<R> isectP = in.isectP;
+  Moved<R> mv; mv.val = in.val; mv.time = (R)in.dt; mv.velocity_mode = (P.blur_mode == 1 && in.dt != 0.0f);
+  Vec<R> sray;
+  if (L.type == 0) sray = L.center - isectP;                        // pointLight geometry.cpp:2751-2754
+  else if (L.type == 2) sray = rectSample<R>(L.A, L.B, L.D, in.path, rng_dim_light(li, 0)) - isectP;   // :2845-2849
+  else if (!sampleSphereLight<R>(L, isectP, in.path, li, sray)) { out.state = 2; return; }   // (returns the POINT, Q10)
+  out.sray = sray;
+  const float t_max = (float)norm(sray);                            // :804
+  const Vec<R> sdir = normalized(sray);
+  if (COUNT) cnt.shadow_rays++;
+  // candidates are gathered along the UNNORMALISED sray from isectP + sray*1e-3 (:814),
+  // occlusion is tested along the normalised one from isectP + s^*1e-3 (:838)
+  out.state = anyHit<R, COUNT>(P, gb, mv, sray, isectP + sray * R(1e-3), sdir, isectP + sdir * R(1e-3), t_max, L.prim_index, cnt) ? 0 : 1;
+}
+
+// The rest of the light loop (:856-959) for lights [l0, l1) of one hit, in order.
+template <typename R, bool COUNT>
+__device__ void shadeB(const Params<R>& P, ShadeState<R>& S, const PairOut<R>* res, int l0, int l1, Counts& cnt) {
+  const PrimD<R>& pr = P.prims[S.prim];
+  for (int li = l0; li < l1 && !S.early && !S.aborted; li++) {
+    const PairOut<R> r = res[li - l0];
+    if (r.state == 2) { S.aborted = true; break; }                   // throws geometry.cpp:2785-2789
+    if (r.state == 0) continue;                                       // shadowed :852-855
+    const LightD<R>& L = P.lights[li];
+    const Vec<R> sray = r.sray;
+    const Vec<R> sdir = normalized(sray);
       // ---- texture (:859-893) ---------------------------------------------------
       if (pr.flags & 4) {
         float u = 0, v = 0; int type = 0;
         if (pr.type == 3 || pr.type == 5 || pr.type == 4) {            // Rectangle::getUV (prism: top face)
-          Vec<R> uA = shiftPoint(mv, pr.name == 1 ? GF_NAME_RECTANGLE : 0, pr.vel, pr.uvA);
-          Vec<R> uD = shiftPoint(mv, pr.name == 1 ? GF_NAME_RECTANGLE : 0, pr.vel, pr.uvD);
-          u = (float)(norm(cross(isectP - uA, pr.uv_ad)) / pr.uv_den_u);
-          v = (float)(norm(cross(isectP - uD, pr.uv_dc)) / pr.uv_den_v);
+          Vec<R> uA = shiftPoint(S.mv, pr.name == 1 ? GF_NAME_RECTANGLE : 0, pr.vel, pr.uvA);
+          Vec<R> uD = shiftPoint(S.mv, pr.name == 1 ? GF_NAME_RECTANGLE : 0, pr.vel, pr.uvD);
+          u = (float)(norm(cross(S.isectP - uA, pr.uv_ad)) / pr.uv_den_u);
+          v = (float)(norm(cross(S.isectP - uD, pr.uv_dc)) / pr.uv_den_v);
           type = 1;
         } else if (pr.type == 6) {                                      // CheckerboardWithHole::getUV geometry.cpp:2500-2561
-          Vec<R> V_hit = isectP - pr.rA;
+          Vec<R> V_hit = S.isectP - pr.rA;
           float check1 = (float)dot(pr.re1, V_hit), check2 = (float)dot(pr.re2, V_hit);
           if (0 <= check1 && (R)check1 <= pr.rlen1 && 0 <= check2 && (R)check2 <= pr.rlen2) {
             // hole->intersectShadow(VEC3(1,1,1), p - VEC3(1,1,1), FLT_MAX)
@@ -793,7 +844,7 @@ __device__ void shadeHit(const Params<R>& P, const float4* __restrict__ gb, cons
             Vec<R> one = mk<R>(1, 1, 1);
             bool in_hole;
             {
-              const Vec<R> ray1 = one, start1 = isectP - one;
+              const Vec<R> ray1 = one, start1 = S.isectP - one;
               float dn = (float)dot(ray1, pr.hn);
               in_hole = false;
               if (dn != 0.0f) {
@@ -809,8 +860,8 @@ __device__ void shadeHit(const Params<R>& P, const float4* __restrict__ gb, cons
             }
             if (in_hole) type = 0;
             else {
-              float gu = (float)(norm(cross(isectP - pr.uvA, pr.uv_ad)) / pr.uv_den_u);
-              float gv = (float)(norm(cross(isectP - pr.uvD, pr.uv_dc)) / pr.uv_den_v);
+              float gu = (float)(norm(cross(S.isectP - pr.uvA, pr.uv_ad)) / pr.uv_den_u);
+              float gv = (float)(norm(cross(S.isectP - pr.uvD, pr.uv_dc)) / pr.uv_den_v);
               float miniu_dist = pr.S / pr.length;
               float miniv_dist = pr.S / pr.width;
               float miniu = gu / miniu_dist - (int)(gu / miniu_dist);
@@ -823,15 +874,15 @@ __device__ void shadeHit(const Params<R>& P, const float4* __restrict__ gb, cons
             }
           } else type = 0;
         } else if (pr.type == 2) {                                      // Triangle::getUV geometry.cpp:447-486
-          Vec<R> tA = shiftPoint(mv, 0, pr.vel, pr.tA), tB = shiftPoint(mv, 0, pr.vel, pr.tB), tC = shiftPoint(mv, 0, pr.vel, pr.tC);
+          Vec<R> tA = shiftPoint(S.mv, 0, pr.vel, pr.tA), tB = shiftPoint(S.mv, 0, pr.vel, pr.tB), tC = shiftPoint(S.mv, 0, pr.vel, pr.tC);
           Vec<R> nn = cross(tB - tA, tC - tA);
-          Vec<R> n_a = cross(tC - tB, isectP - tB), n_b = cross(tA - tC, isectP - tC);
+          Vec<R> n_a = cross(tC - tB, S.isectP - tB), n_b = cross(tA - tC, S.isectP - tC);
           float n_sq = (float)dot(nn, nn);
           float alpha = (float)((double)dot(nn, n_a) / (double)n_sq);
           float beta = (float)((double)dot(nn, n_b) / (double)n_sq);
           float gamma = 1 - alpha - beta;
           if (alpha < 0 || alpha > 1 || beta < 0 || beta > 1 || gamma < 0 || gamma > 1) type = 0;
-          else if (!(pr.flags & 32)) { aborted = true; break; }         // throws geometry.cpp:456-460
+          else if (!(pr.flags & 32)) { S.aborted = true; break; }         // throws geometry.cpp:456-460
           else {
             u = (float)(((double)alpha * pr.tuv[0] + (double)beta * pr.tuv[2]) + (double)gamma * pr.tuv[4]);
             v = (float)(((double)alpha * pr.tuv[1] + (double)beta * pr.tuv[3]) + (double)gamma * pr.tuv[5]);
@@ -839,44 +890,38 @@ __device__ void shadeHit(const Params<R>& P, const float4* __restrict__ gb, cons
             type = 1;
           }
         } else if (pr.type == 7) {                                      // CheckerCylinder::getUV geometry.cpp:2588-2630
-          Vec<R> p_obj = mulPoint<R>(pr.objM, isectP);
+          Vec<R> p_obj = mulPoint<R>(pr.objM, S.isectP);
           float cu = 0;
-          if (isectP.x != R(0)) cu = (float)((atan2((double)p_obj.y, (double)p_obj.x) + DRT_PI) / (2 * DRT_PI));
+          if (S.isectP.x != R(0)) cu = (float)((atan2((double)p_obj.y, (double)p_obj.x) + DRT_PI) / (2 * DRT_PI));
           float cv = (float)((double)p_obj.z / (double)pr.axis_norm);
           float miniu_dist = (float)((double)pr.S / (2 * DRT_PI * (double)pr.radius));
           float miniv_dist = (float)((double)pr.S / (double)pr.axis_norm);
           float miniu = cu / miniu_dist - (int)(cu / miniu_dist);
           float miniv = cv / miniv_dist - (int)(cv / miniv_dist);
-          if (miniu > 1 || miniu < 0 || miniv > 1 || miniv < 0) { aborted = true; break; }   // throws :2610-2614
+          if (miniu > 1 || miniu < 0 || miniv > 1 || miniv < 0) { S.aborted = true; break; }   // throws :2610-2614
           u = miniu; v = miniv;
           float bw = pr.borderwidth / (2 * pr.S);
           type = ((miniu <= bw || miniu >= 1 - bw) || (miniv <= bw || miniv >= 1 - bw)) ? 2 : 1;
-        } else { aborted = true; break; }
-        if (type == 0) { early_return = true; break; }                  // quirk Q7 (:866-869)
-        if (u < 0 || v < 0 || u > 1 || v > 1) { aborted = true; break; }   // throws :870-877
-        if (type == 2) { shape_color[0] = pr.bordercolor[0]; shape_color[1] = pr.bordercolor[1]; shape_color[2] = pr.bordercolor[2]; }
+        } else { S.aborted = true; break; }
+        if (type == 0) { S.early = true; break; }                  // quirk Q7 (:866-869)
+        if (u < 0 || v < 0 || u > 1 || v > 1) { S.aborted = true; break; }   // throws :870-877
+        if (type == 2) { S.shape_color[0] = pr.bordercolor[0]; S.shape_color[1] = pr.bordercolor[1]; S.shape_color[2] = pr.bordercolor[2]; }
         else {
           int2 dims = P.texdims[pr.tex];
           int x_tex = (int)((dims.x - 1) * u);
           int y_tex = (int)((dims.y - 1) * v);
           float4 tx = tex2D<float4>(P.tex[pr.tex], x_tex + 0.5f, y_tex + 0.5f);   // nearest texel, byte/255
-          shape_color[0] = tx.x; shape_color[1] = tx.y; shape_color[2] = tx.z;
+          S.shape_color[0] = tx.x; S.shape_color[1] = tx.y; S.shape_color[2] = tx.z;
         }
-        have_tex = true;
       }
-      (void)have_tex;
       if (COUNT) cnt.shade_evals++;
       // ---- BRDF (:894-948) ---------------------------------------------------------
       double ray_color[3];
-      evalBRDF<R>(pr, L.color, shape_color, e, normal, sray, sdir, P.phong, ray_color);
+      evalBRDF<R>(pr, L.color, S.shape_color, S.e, S.normal, sray, sdir, P.phong, ray_color);
       // !ray_color.isApprox(0): exact-zero test; NaN counts as a hit (:950-954, Q6)
       double sq = ray_color[0] * ray_color[0] + (ray_color[1] * ray_color[1] + ray_color[2] * ray_color[2]);
-      if (!(sq <= 0.0)) { hits++; for (int c = 0; c < 3; c++) tmp_color[c] += (double)k * ray_color[c]; }
-    }
-    if (aborted) break;
-    if (!early_return && hits > 0) { for (int c = 0; c < 3; c++) add[c] += tmp_color[c] / hits; has_add = true; }   // :956-959
-  } while (0);
-  n_out = sp;
+      if (!(sq <= 0.0)) { S.hits++; for (int c = 0; c < 3; c++) S.tmp[c] += (double)S.k * ray_color[c]; }
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -931,6 +976,11 @@ __device__ __noinline__ void primaryRay(const Params<R>& P, long long gidx, Vec<
   dir = focalPoint - eye_sample;
 }
 
+template <typename R>
+__host__ __device__ constexpr size_t waveScratchBytes() {
+  return DRT_POOL_CAP * sizeof(Task<R>) + 64 * sizeof(HitTask<R>) + 32 * sizeof(PairIn<R>) + 32 * DRT_PAIR_LIGHTS * sizeof(PairOut<R>);
+}
+
 // Phase-locked persistent CTA.  All warps of the CTA run the same phase at the same time
 // (GEN -> TRACE -> SHADE, separated by __syncthreads), so the SM's instruction cache only has
 // to hold one phase's code: with free-running warps the 14k-instruction kernel saturated
@@ -955,10 +1005,13 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, 1) render_wave(const __gr
 #endif
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  // per-warp scratch in global memory: [ DRT_POOL_CAP ray tasks | 64 hit tasks ]
-  char* wbase = (char*)P.pool_raw + (size_t)(blockIdx.x * DRT_WAVE_WARPS + wib) * (DRT_POOL_CAP * sizeof(Task<R>) + 64 * sizeof(HitTask<R>));
+  // per-warp scratch in global memory (L1/L2 resident):
+  //   [ DRT_POOL_CAP ray tasks | 64 hit tasks | 32 pair inputs | 32 x DRT_PAIR_LIGHTS pair results ]
+  char* wbase = (char*)P.pool_raw + (size_t)(blockIdx.x * DRT_WAVE_WARPS + wib) * waveScratchBytes<R>();
   Task<R>* pool = (Task<R>*)wbase;
   HitTask<R>* hits = (HitTask<R>*)(wbase + DRT_POOL_CAP * sizeof(Task<R>));
+  PairIn<R>* pairin = (PairIn<R>*)(hits + 64);
+  PairOut<R>* pairout = (PairOut<R>*)(pairin + 32);
   unsigned long long(*acc)[3] = s_acc[wib];
   unsigned int* sfl = s_flags[wib];
   const long long n_batches = (P.sample_count + DRT_BATCH - 1) / DRT_BATCH;
@@ -1104,22 +1157,51 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, 1) render_wave(const __gr
       const bool active = lane < take;
       Task<R> kids[DRT_MAX_CHILDREN];
       int nk = 0;
+      ShadeState<R> S; S.lights = false; S.aborted = false;
+      double add[3] = {0, 0, 0}; bool has_add = false, aborted = false;
+      unsigned short slot = 0;
+      // -- step A (lane = hit): normal, children, emissive term
+      {
+        PairIn<R> pin; pin.want = 0;
+        if (active) {
+          const HitTask<R> H = hits[nhits - 1 - lane];
+          HitRec h; h.t = H.t; h.geom = H.geom; h.inside = H.inside; h.checker_sel = H.checker_sel;
+          slot = H.T.slot;
+          shadeA<R, COUNT>(P, H.T, h, kids, nk, add, has_add, aborted, S, cnt);
+          if (!aborted && S.lights) { pin.isectP = S.isectP; pin.path = H.T.path; pin.val = H.T.val; pin.dt = H.T.dt; pin.want = 1; }
+        }
+        pairin[lane] = pin;
+      }
+      __syncwarp();
+      // -- step B (lane = (hit, light) pair): light sample + shadow ray, 8 lights at a time
+      for (int l0 = 0; l0 < P.n_lights; l0 += DRT_PAIR_LIGHTS) {
+        const int nl = min(DRT_PAIR_LIGHTS, P.n_lights - l0);
+        for (int pid = lane; pid < take * nl; pid += 32) {
+          const int hh = pid / nl, lj = pid - hh * nl;
+          const PairIn<R> pin = pairin[hh];
+          if (pin.want) shadowPair<R, COUNT>(P, gb, pin, l0 + lj, pairout[hh * DRT_PAIR_LIGHTS + lj], cnt);
+        }
+        __syncwarp();
+        // -- step C (lane = hit again): texture + BRDF of the unoccluded lights, in light order
+        if (active && !aborted && S.lights) shadeB<R, COUNT>(P, S, pairout + lane * DRT_PAIR_LIGHTS, l0, l0 + nl, cnt);
+        __syncwarp();
+      }
       if (active) {
-        const HitTask<R> H = hits[nhits - 1 - lane];
-        HitRec h; h.t = H.t; h.geom = H.geom; h.inside = H.inside; h.checker_sel = H.checker_sel;
-        double add[3]; bool has_add, aborted = false;
-        shadeHit<R, COUNT>(P, gb, H.T, h, kids, nk, add, has_add, aborted, cnt);
-        if (aborted) { atomicOr(&sfl[H.T.slot], SF_ABORT); nk = 0; }
+        if (S.lights && !aborted) {
+          if (S.aborted) aborted = true;
+          else if (!S.early && S.hits > 0) { for (int c = 0; c < 3; c++) add[c] += S.tmp[c] / S.hits; has_add = true; }   // :956-959
+        }
+        if (aborted) { atomicOr(&sfl[slot], SF_ABORT); nk = 0; }
         else if (has_add) {
           unsigned int orf = 0;
           for (int c = 0; c < 3; c++) {
             const double v = add[c];
             if (v != v) orf |= SS_NAN(c);
-            else if (v > 1073741824.0) orf |= (isinf(v) ? SS_PINF(c) : 0u), atomicAdd(&acc[H.T.slot][c], (unsigned long long)(1ll << 62));
-            else if (v < -1073741824.0) orf |= (isinf(v) ? SS_NINF(c) : 0u), atomicAdd(&acc[H.T.slot][c], (unsigned long long)(-(1ll << 62)));
-            else atomicAdd(&acc[H.T.slot][c], (unsigned long long)__double2ll_rn(v * 4294967296.0));
+            else if (v > 1073741824.0) orf |= (isinf(v) ? SS_PINF(c) : 0u), atomicAdd(&acc[slot][c], (unsigned long long)(1ll << 62));
+            else if (v < -1073741824.0) orf |= (isinf(v) ? SS_NINF(c) : 0u), atomicAdd(&acc[slot][c], (unsigned long long)(-(1ll << 62)));
+            else atomicAdd(&acc[slot][c], (unsigned long long)__double2ll_rn(v * 4294967296.0));
           }
-          if (orf) atomicOr(&sfl[H.T.slot], orf);
+          if (orf) atomicOr(&sfl[slot], orf);
         }
       }
       nhits -= take;
