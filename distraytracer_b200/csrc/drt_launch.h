@@ -10,7 +10,9 @@
 #pragma once
 #include "drt_device.cuh"
 
+#ifndef DRT_BATCH
 #define DRT_BATCH 64          // camera samples per warp batch (render_wave)
+#endif
 #define DRT_POOL_CAP 2048     // ray-pool records per warp
 #define DRT_MAX_CHILDREN 6    // refraction + max(brdf_samples, 1)
 #define DRT_PAIR_LIGHTS 8      // lights whose shadow rays are spread over the warp per pass

@@ -1,0 +1,73 @@
+// Exercises the host-side mirror (distraytracer_b200/host/drt_host.h) the way the reference's
+// main() drives its renderer: a build*() function fills shapes/lights, then renderImage().
+// The scenes restate buildSceneHW4 (scene.h:4451-4477) and buildSceneReflectance
+// (scene.h:3668-3694) through the mirrored constructors.
+//   host_scene dump   <scene> <out.bin>  : flattened drt_prim / drt_light arrays (no GPU needed)
+//   host_scene render <scene> <out.ppm>  : renderImage() on the GPU(s)
+#include <cstring>
+#include <fstream>
+#include "../../distraytracer_b200/host/drt_host.h"
+
+using namespace drt::host;
+using std::make_shared;
+using std::shared_ptr;
+
+static void buildSceneHW4(float) {
+  Globals& g = globals();
+  g.shapes.clear(); g.lights.clear();
+  VEC3 c0(-3.5, 0, -10); float r0 = 3; VEC3 rgb0(1, 0.25, 0.25);
+  VEC3 c1(3.5, 0, -10); float r1 = 3; VEC3 rgb1(0.25, 0.25, 1);
+  VEC3 c2(0, -1000, -10); float r2 = 997; VEC3 rgb2(0.5, 0.5, 0.5);
+  g.shapes.push_back(make_shared<Sphere>(c0, r0, rgb0));
+  g.shapes.push_back(make_shared<Sphere>(c1, r1, rgb1));
+  g.shapes.push_back(make_shared<Sphere>(c2, r2, rgb2));
+  g.lights.push_back(make_shared<pointLight>(VEC3(10, 3, -5), VEC3(1, 1, 1)));
+  g.lights.push_back(make_shared<pointLight>(VEC3(-10, 3, -7.5), VEC3(0.5, 0, 0)));
+}
+
+static void buildSceneReflectance(float framef) {
+  int frame = (int)framef;
+  Globals& g = globals();
+  g.shapes.clear(); g.lights.clear();
+  g.shapes.push_back(make_shared<Sphere>(VEC3(3, 0.5, -4), 1, VEC3(0.5, 0.5, 0.5)));
+  auto marble = make_shared<Sphere>(VEC3(3, 0.5, -1.5), 1, VEC3(0.5, 0.5, 0.5), "marble", false, "oren-nayar");
+  marble->reflect_params.roughness = sqrt(0.2);
+  g.shapes.push_back(marble);
+  auto metal = make_shared<Sphere>(VEC3(3, 0.5, 1), 1, VEC3(0.5, 0.5, 0.5), "aluminum", false, "cook-torrance");
+  metal->reflect_params.roughness = sqrt(0.2); metal->reflect_params.refr = VEC2(0.958, 6.69);
+  g.shapes.push_back(metal);
+  auto glossy = make_shared<Sphere>(VEC3(3, 0.5, 3.5), 1, VEC3(0.5, 0.5, 0.5), "aluminum", false, "cook-torrance");
+  glossy->reflect_params.roughness = sqrt(0.2); glossy->reflect_params.refr = VEC2(0.958, 6.69); glossy->reflect_params.glossy = true;
+  g.shapes.push_back(glossy);
+  g.shapes.push_back(make_shared<Sphere>(VEC3(-7, 0.5, 4), 3, VEC3(1, 0, 0)));
+  VEC3 light_center = VEC3(-6, 5, -10) + VEC3(0, 0, 20) * (float)frame / 150;
+  g.lights.push_back(make_shared<pointLight>(light_center, VEC3(1, 1, 1)));
+}
+
+int main(int argc, char** argv) {
+  if (argc < 4) { fprintf(stderr, "usage: host_scene dump|render hw4|reflectance <out>\n"); return 2; }
+  std::string mode = argv[1], scene = argv[2], out = argv[3];
+  Globals& g = globals();
+  g.xRes = 160; g.yRes = 120; g.seed = 7;
+  int frame = 0;
+  std::function<void(float)> builder;
+  if (scene == "hw4") { g.antialias_samples = 1; builder = buildSceneHW4; }
+  else if (scene == "reflectance") { g.antialias_samples = 4; frame = 40; builder = buildSceneReflectance; }
+  else return 2;
+  builder((float)frame);
+  try {
+    if (mode == "dump") {
+      FlatScene f; flattenScene(f);
+      drt_settings st = flattenSettings(frame);
+      std::ofstream o(out, std::ios::binary);
+      int32_t n[2] = {(int32_t)f.prims.size(), (int32_t)f.lights.size()};
+      o.write((const char*)n, sizeof(n));
+      o.write((const char*)f.prims.data(), f.prims.size() * sizeof(drt_prim));
+      o.write((const char*)f.lights.data(), f.lights.size() * sizeof(drt_light));
+      o.write((const char*)&st, sizeof(st));
+    } else {
+      renderImage(out, frame, builder);
+    }
+  } catch (const std::exception& e) { fprintf(stderr, "host_scene: %s\n", e.what()); return 1; }
+  return 0;
+}

@@ -13,3 +13,8 @@ cnt = abi.Counters()
 for i in range(3):
     dev.render_device(st, tile, cnt)
     print(f"band y0={y0} h={h}: kernel {cnt.kernel_ms:.3f} ms, {1920*h*64/cnt.kernel_ms/1e3:.1f} Msamples/s", flush=True)
+if os.environ.get("BAND_COUNT"):
+    c2 = abi.Counters(); c2.collect = 1
+    dev.render_device(st, tile, c2)
+    pt = list(c2.prim_tests)
+    print(f"samples {c2.samples} rays {c2.rays} shadow {c2.shadow_rays} node {c2.node_tests} rect {pt[abi.PRIM_RECTANGLE]} sph {pt[abi.PRIM_SPHERE]} tri {pt[abi.PRIM_TRIANGLE]} shade {c2.shade_evals} kernel {c2.kernel_ms:.1f} ms")
