@@ -246,9 +246,12 @@ def run_ours(args):
     prims = list(scene.prims)
     h2d_bytes = None
 
+    from distraytracer_b200 import shard
+    my_frames = shard.frames_for_rank(rank, world, (args.warmup + args.steps) * world)
+
     def set_frame(step):
-        # frames are sharded round-robin: rank r renders frames r, r+world, ...
-        settings.frame = rank + step * world
+        # frames are sharded round-robin (SURVEY.md 8e): rank r renders frames r, r+world, ...
+        settings.frame = my_frames[step]
         settings.seed = 1000 + settings.frame
 
     # ---- device-resident leg (value) ------------------------------------------------
@@ -284,11 +287,7 @@ def run_ours(args):
     e2e_ms = 1e3 * (time.perf_counter() - t0)
 
     def maxr(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return shard.max_over_ranks(x, dist if world > 1 else None, device="cuda")
 
     dev_ms, wall_ms, e2e_ms = maxr(dev_ms), maxr(wall_ms), maxr(e2e_ms)
 
