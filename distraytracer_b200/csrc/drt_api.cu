@@ -13,6 +13,7 @@
 #include "../../include/drt.h"
 #include "drt_launch.h"
 #include "drt_bvh_order.h"
+#include "drt_mesh.h"
 
 using namespace drt;
 
@@ -328,9 +329,25 @@ struct drt_scene {
   void* pool = nullptr; size_t pool_cap = 0;
   unsigned long long* batch_counter = nullptr; int* overflow = nullptr;
   int wave_blocks_f64 = 0, wave_blocks_f32 = 0;
+  MeshBuffers mesh; bool has_mesh = false; drt_prim mesh_material;
 };
 
 namespace {
+
+template <typename R>
+int addMeshMaterial(const drt_prim& m, int n_textures, HostScene<R>& hs) {
+  // shading record of the mesh's shared material: flatten it as a stand-alone triangle and keep
+  // only the PrimD (its Geom/tree entries are dropped: mesh triangles live in the LBVH)
+  HostScene<R> tmp;
+  drt_prim p = m;
+  p.type = DRT_PRIM_TRIANGLE;
+  const double A[3] = {0, 0, 0}, B[3] = {1, 0, 0}, C[3] = {0, 1, 0};
+  memcpy(p.A, A, sizeof(A)); memcpy(p.B, B, sizeof(B)); memcpy(p.C, C, sizeof(C));
+  int rc = flatten<R>(&p, 1, nullptr, 0, n_textures, tmp);
+  if (rc) return rc;
+  hs.prims.push_back(tmp.prims[0]);
+  return DRT_OK;
+}
 
 int flattenAndUpload(drt_scene* s) {
   HostScene<double> hd; HostScene<float> hf;
@@ -338,6 +355,10 @@ int flattenAndUpload(drt_scene* s) {
   if (rc) return rc;
   rc = flatten<float>(s->prims.data(), (int)s->prims.size(), s->lights.data(), (int)s->lights.size(), s->n_textures, hf);
   if (rc) return rc;
+  if (s->has_mesh) {
+    rc = addMeshMaterial<double>(s->mesh_material, s->n_textures, hd); if (rc) return rc;
+    rc = addMeshMaterial<float>(s->mesh_material, s->n_textures, hf); if (rc) return rc;
+  }
   rc = upload(hd, s->dd); if (rc) return rc;
   rc = upload(hf, s->df); if (rc) return rc;
   s->any_glass = false;
@@ -401,6 +422,10 @@ void fillParams(Params<R>& P, const drt_scene* s, const DevScene<R>& ds, const d
   P.x0 = tile.x0; P.y0 = tile.y0; P.w = tile.width; P.h = tile.height;
   P.geoms = ds.geoms; P.n_geoms = ds.n_geoms; P.gbounds = ds.gbounds; P.nodes = ds.nodes; P.n_nodes = ds.n_nodes; P.prims = ds.prims; P.lights = ds.lights; P.n_lights = ds.n_lights;
   P.tex = s->d_tex; P.texdims = s->d_texdims;
+  if (s->has_mesh) {
+    P.mesh_nodes = s->mesh.nodes; P.n_mesh_tris = s->mesh.n_tris; P.mesh_prim = (int)s->prims.size();
+    P.mesh_tris = (const MeshTri<R>*)(sizeof(R) == 8 ? s->mesh.tris_f64 : s->mesh.tris_f32);
+  }
 }
 
 int ensureScratch(drt_scene* s, size_t n_samples, size_t n_corners, size_t n_out) {
@@ -573,15 +598,14 @@ void drt_prim_default(drt_prim* p) {                                    // geome
 int drt_scene_create(const drt_scene_desc* d, int device, drt_scene** out) {
   if (!d || !out) return fail(DRT_ERR_INVALID, "null argument");
   if (d->abi_version != DRT_ABI_VERSION) return fail(DRT_ERR_INVALID, "ABI version mismatch");
-  if (d->n_prims < 1 || !d->prims) return fail(DRT_ERR_SCENE, "No shapes to render!");   // render_final_project.cpp:973-977
-  if (d->mesh) return fail(DRT_ERR_UNSUPPORTED, "triangle-mesh scenes are not built yet (SURVEY.md 8 row C5)");
+  if ((d->n_prims < 1 || !d->prims) && !d->mesh) return fail(DRT_ERR_SCENE, "No shapes to render!");   // render_final_project.cpp:973-977
   int ndev = drt_device_count();
   if (ndev < 1) return fail(DRT_ERR_NO_DEVICE, "no CUDA device: this library has no CPU fallback");
   if (device < 0 || device >= ndev) return fail(DRT_ERR_INVALID, "device ordinal out of range");
   CK(cudaSetDevice(device));
   drt_scene* s = new drt_scene();
   s->device = device;
-  s->prims.assign(d->prims, d->prims + d->n_prims);
+  if (d->n_prims > 0) s->prims.assign(d->prims, d->prims + d->n_prims);
   if (d->n_lights > 0) s->lights.assign(d->lights, d->lights + d->n_lights);
   s->n_textures = d->n_textures;
   auto bail = [&](int rc) { drt_scene_destroy(s); return rc; };
@@ -617,6 +641,14 @@ int drt_scene_create(const drt_scene_desc* d, int device, drt_scene** out) {
         cudaMemcpy(s->d_texdims, dims.data(), sizeof(int2) * d->n_textures, cudaMemcpyHostToDevice) != cudaSuccess)
       return bail(fail(DRT_ERR_CUDA, "texture table upload failed"));
   }
+  if (d->mesh) {
+    if ((d->mesh->material.flags & DRT_FLAG_TEXTURE) && !d->mesh->texcoords)
+      return bail(fail(DRT_ERR_INVALID, "textured mesh without texcoords"));
+    std::string err;
+    int mrc = buildMesh(d->mesh, &s->mesh, err);
+    if (mrc) return bail(fail(mrc, err));
+    s->has_mesh = true; s->mesh_material = d->mesh->material;
+  }
   int rc = flattenAndUpload(s);
   if (rc) return bail(rc);
   *out = s;
@@ -643,6 +675,7 @@ void drt_scene_destroy(drt_scene* s) {
   void* ptrs[] = {s->dd.gbounds, s->df.gbounds, s->dd.geoms, s->dd.prims, s->dd.lights, s->dd.nodes, s->df.geoms, s->df.prims, s->df.lights, s->df.nodes, s->d_tex, s->d_texdims,
                   s->samples, s->need, s->bg, s->out_u8, s->out_f32, s->counts, s->pool, s->batch_counter, s->overflow};
   for (void* p : ptrs) if (p) cudaFree(p);
+  freeMesh(&s->mesh);
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
   if (s->stream) cudaStreamDestroy(s->stream);

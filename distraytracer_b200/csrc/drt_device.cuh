@@ -134,6 +134,13 @@ struct alignas(16) PrimD {
   Vec<R> vel;
 };
 
+// one mesh triangle for the exact test + texture coordinates (drt_lbvh.cuh)
+template <typename R>
+struct alignas(16) MeshTri {
+  Vec<R> A, B, C;
+  float uv[6];
+};
+
 template <typename R>
 struct alignas(16) LightD {
   int type, prim_index;
@@ -175,6 +182,8 @@ struct Params {
   const NodeD<R>* nodes; int n_nodes;
   const PrimD<R>* prims;
   const LightD<R>* lights; int n_lights;
+  // triangle mesh (optional): LBVH nodes (4 float4 each), exact-test records, material = prims[mesh_prim]
+  const float4* mesh_nodes; const MeshTri<R>* mesh_tris; int n_mesh_tris; int mesh_prim;
   const cudaTextureObject_t* tex; const int2* texdims;
   // buffers
   float4* samples;          // [pixel_in_tile * spp + s] : rgb + flag bits

@@ -439,6 +439,94 @@ __device__ inline bool anyHit(const Params<R>& P, const float4* __restrict__ gb,
   return false;
 }
 
+// ---- triangle mesh: LBVH traversal (drt_lbvh.cuh) ------------------------------------------
+// Triangle::intersect (geometry.cpp:488-553) on a mesh triangle; returns t or a negative value.
+template <typename R>
+__device__ __forceinline__ float meshTriT(const MeshTri<R>& tr, const Vec<R>& ray, const Vec<R>& start) {
+  const Vec<R> r1 = tr.B - tr.A, r2 = tr.C - tr.A;
+  const Vec<R> hh = cross(ray, r2);
+  const float det = (float)dot(r1, hh);
+  const float invdet = (float)(1.0 / (double)det);
+  if (det >= -0.0001f && det <= 0.0001f) return -1.f;
+  const Vec<R> A0 = start - tr.A;
+  const float u = (float)((double)invdet * (double)dot(A0, hh));
+  if (u < 0 || u > 1) return -1.f;
+  const Vec<R> DA0 = cross(A0, r1);
+  const float v = (float)((double)dot(ray, DA0) * (double)invdet);
+  if (v < 0 || u + v > 1) return -1.f;
+  return (float)((double)dot(r2, DA0) * (double)invdet);
+}
+
+// Ordered, t-pruned stack traversal.  CLOSEST: keeps the nearest hit with t > 1e-4 (strict `<`
+// against the best so far, so analytic primitives -- tested first -- win ties).  !CLOSEST:
+// any hit with 1e-3 < t < t_max (Triangle::intersectShadow geometry.cpp:555-586) that the
+// reference would also have gathered (its gather origin runs ahead by |sray|*1e-3, :814; a
+// mesh triangle stands in its own leaf box: bounds +- 1e-2, geometry.cpp:2653-2654).
+template <typename R, bool COUNT, bool CLOSEST>
+__device__ bool meshTraverse(const Params<R>& P, const Vec<R>& ray, const Vec<R>& start, float t_limit, HitRec* h,
+                             const Vec<R>& gather_ray, const Vec<R>& gather_start, Counts& cnt) {
+  const float ox = (float)start.x, oy = (float)start.y, oz = (float)start.z;
+  const float ix = 1.0f / (float)ray.x, iy = 1.0f / (float)ray.y, iz = 1.0f / (float)ray.z;
+  int stack[DRT_NODE_STACK];
+  int sp = 0;
+  int node = 0;
+  bool found = false;
+  for (;;) {
+    const float4 n0 = __ldg(&P.mesh_nodes[4 * node]), n1 = __ldg(&P.mesh_nodes[4 * node + 1]);
+    const float4 n2 = __ldg(&P.mesh_nodes[4 * node + 2]), n3 = __ldg(&P.mesh_nodes[4 * node + 3]);
+    if (COUNT) cnt.node_tests += 2;
+    const float lim = (t_limit < FLT_MAX) ? t_limit * 1.0001f + 1e-4f : FLT_MAX;
+    float tn[2]; bool hit[2];
+    {
+      float t0 = (n0.x - ox) * ix, t1 = (n1.x - ox) * ix; float a = fminf(t0, t1), b = fmaxf(t0, t1);
+      t0 = (n0.y - oy) * iy; t1 = (n1.y - oy) * iy; a = fmaxf(a, fminf(t0, t1)); b = fminf(b, fmaxf(t0, t1));
+      t0 = (n0.z - oz) * iz; t1 = (n1.z - oz) * iz; a = fmaxf(a, fminf(t0, t1)); b = fminf(b, fmaxf(t0, t1));
+      tn[0] = a; hit[0] = !(a > b * 1.0001f + 1e-4f) && !(b < 0.0f) && !(a > lim);
+    }
+    {
+      float t0 = (n2.x - ox) * ix, t1 = (n3.x - ox) * ix; float a = fminf(t0, t1), b = fmaxf(t0, t1);
+      t0 = (n2.y - oy) * iy; t1 = (n3.y - oy) * iy; a = fmaxf(a, fminf(t0, t1)); b = fminf(b, fmaxf(t0, t1));
+      t0 = (n2.z - oz) * iz; t1 = (n3.z - oz) * iz; a = fmaxf(a, fminf(t0, t1)); b = fminf(b, fmaxf(t0, t1));
+      tn[1] = a; hit[1] = !(a > b * 1.0001f + 1e-4f) && !(b < 0.0f) && !(a > lim);
+    }
+    int ch[2] = {__float_as_int(n0.w), __float_as_int(n1.w)};
+    if (hit[0] && hit[1] && tn[1] < tn[0]) { int c = ch[0]; ch[0] = ch[1]; ch[1] = c; }   // nearer child first
+    else if (!hit[0]) { ch[0] = ch[1]; hit[0] = hit[1]; hit[1] = false; }
+    int next = -0x7fffffff;
+    for (int k = 0; k < 2; k++) {
+      if (!hit[k]) continue;
+      if (ch[k] >= 0) {                                                   // internal child
+        if (next == -0x7fffffff) next = ch[k];
+        else if (sp < DRT_NODE_STACK) stack[sp++] = ch[k];
+      } else {                                                            // leaf: exact test
+        const int tri = -ch[k] - 1;
+        if (COUNT) cnt.geom_tests[G_TRI]++;
+        const MeshTri<R>& tr = P.mesh_tris[tri];
+        const float t = meshTriT<R>(tr, ray, start);
+        if (CLOSEST) {
+          if (t > 0.0001f && t < h->t) { h->t = t; h->geom = P.n_geoms + tri; h->inside = 0; h->checker_sel = 0; t_limit = t; found = true; }
+        } else if (t > 0.001f && t < t_limit) {
+          if (t > t_limit * 1e-3f * 1.001f + 2e-3f) return true;          // touch point ahead of the gather origin
+          NodeD<R> nd;                                                    // its own leaf box, BoundingVolume semantics
+          nd.lo = mk<R>(fmin(fmin(tr.A.x, tr.B.x), tr.C.x) - R(1e-2), fmin(fmin(tr.A.y, tr.B.y), tr.C.y) - R(1e-2),
+                        fmin(fmin(tr.A.z, tr.B.z), tr.C.z) - R(1e-2));
+          nd.hi = mk<R>(fmax(fmax(fmax(tr.A.x, tr.B.x), tr.C.x), (R)FLT_MIN) + R(1e-2),
+                        fmax(fmax(fmax(tr.A.y, tr.B.y), tr.C.y), (R)FLT_MIN) + R(1e-2),
+                        fmax(fmax(fmax(tr.A.z, tr.B.z), tr.C.z), (R)FLT_MIN) + R(1e-2));
+          nd.leaf = 1;
+          Moved<R> still; still.val = 0; still.time = 0; still.velocity_mode = 0;
+          const Vec<R> inv = mk<R>(R(1) / gather_ray.x, R(1) / gather_ray.y, R(1) / gather_ray.z);
+          if (boxHit<R>(nd, gather_ray, inv, gather_start, still)) return true;
+        }
+      }
+    }
+    if (next != -0x7fffffff) { node = next; continue; }
+    if (sp == 0) break;
+    node = stack[--sp];
+  }
+  return found;
+}
+
 // Rectangle::samplePoint (geometry.cpp:772-782)
 template <typename R>
 __device__ inline Vec<R> rectSample(const Vec<R>& A, const Vec<R>& B, const Vec<R>& D, uint32_t key, uint32_t dim) {
@@ -578,9 +666,13 @@ __device__ inline bool traceRay(const Params<R>& P, const float4* __restrict__ g
   if (COUNT) cnt.rays++;
   Moved<R> mv; mv.val = T.val; mv.time = (R)T.dt; mv.velocity_mode = (P.blur_mode == 1 && T.dt != 0.0f);
   closestHit<R, COUNT>(P, gb, mv, T.dir, T.org, h, cnt);
+  if (P.n_mesh_tris > 0) meshTraverse<R, COUNT, true>(P, T.dir, T.org, h.t, &h, T.dir, T.org, cnt);
   if (T.chain) motion = 0;                                              // :519
   if (h.geom < 0) return false;                                         // :541-544
-  if (T.chain) motion = (P.prims[P.geoms[h.geom].owner].flags & 2) ? 1 : 0;   // DRT_FLAG_MOTION, :564
+  if (T.chain) {
+    const int owner = h.geom >= P.n_geoms ? P.mesh_prim : P.geoms[h.geom].owner;
+    motion = (P.prims[owner].flags & 2) ? 1 : 0;                        // DRT_FLAG_MOTION, :564
+  }
   return true;
 }
 
@@ -601,6 +693,7 @@ struct ShadeState {
   float shape_color[3];
   float k;
   int prim;
+  int tri;         // mesh triangle id, or -1
   bool lights;     // the hit is not a light shape: the light loop has to run
   bool aborted, early;
   int hits;
@@ -632,8 +725,9 @@ __device__ void shadeA(const Params<R>& P, const Task<R>& T, const HitRec& h, Ta
   do {
     const Vec<R> ray = T.dir, eye = T.org;
     const float k = T.k;
-    const Geom<R>& g = P.geoms[h.geom];
-    const PrimD<R>& pr = P.prims[g.owner];
+    const int mesh_tri = h.geom >= P.n_geoms ? h.geom - P.n_geoms : -1;
+    const int owner = mesh_tri >= 0 ? P.mesh_prim : P.geoms[h.geom].owner;
+    const PrimD<R>& pr = P.prims[owner];
 
     const Vec<R> isectP = eye + (R)h.t * ray;                           // :548
     // ---- getNorm of the hit class ------------------------------------------------
@@ -660,6 +754,9 @@ __device__ void shadeA(const Params<R>& P, const Task<R>& T, const HitRec& h, Ta
         else if (pa_right == min_side || pg_right == min_side) normal = pr.n1;
         else normal = pr.n2;
       }
+    } else if (mesh_tri >= 0) {                                         // Triangle::getNorm geometry.cpp:588-594
+      const MeshTri<R>& tr = P.mesh_tris[mesh_tri];
+      normal = normalized(cross(tr.B - tr.A, tr.C - tr.A));
     } else {
       normal = pr.n0;                                                   // Triangle / Rectangle family
     }
@@ -791,7 +888,7 @@ __device__ void shadeA(const Params<R>& P, const Task<R>& T, const HitRec& h, Ta
 
     S.isectP = isectP; S.normal = normal; S.e = normalized(eye - isectP);   // :795
     S.shape_color[0] = shape_color[0]; S.shape_color[1] = shape_color[1]; S.shape_color[2] = shape_color[2];
-    S.k = k; S.prim = g.owner; S.lights = true;
+    S.k = k; S.prim = owner; S.tri = mesh_tri; S.lights = true;
   } while (0);
   n_out = sp;
 }
@@ -812,7 +909,10 @@ __device__ void shadowPair(const Params<R>& P, const float4* __restrict__ gb, co
   if (COUNT) cnt.shadow_rays++;
   // candidates are gathered along the UNNORMALISED sray from isectP + sray*1e-3 (:814),
   // occlusion is tested along the normalised one from isectP + s^*1e-3 (:838)
-  out.state = anyHit<R, COUNT>(P, gb, mv, sray, isectP + sray * R(1e-3), sdir, isectP + sdir * R(1e-3), t_max, L.prim_index, cnt) ? 0 : 1;
+  bool occluded = anyHit<R, COUNT>(P, gb, mv, sray, isectP + sray * R(1e-3), sdir, isectP + sdir * R(1e-3), t_max, L.prim_index, cnt);
+  if (!occluded && P.n_mesh_tris > 0)
+    occluded = meshTraverse<R, COUNT, false>(P, sdir, isectP + sdir * R(1e-3), t_max, nullptr, sray, isectP + sray * R(1e-3), cnt);
+  out.state = occluded ? 0 : 1;
 }
 
 // The rest of the light loop (:856-959) for lights [l0, l1) of one hit, in order.
@@ -875,6 +975,8 @@ __device__ void shadeB(const Params<R>& P, ShadeState<R>& S, const PairOut<R>* r
           } else type = 0;
         } else if (pr.type == 2) {                                      // Triangle::getUV geometry.cpp:447-486
           Vec<R> tA = shiftPoint(S.mv, 0, pr.vel, pr.tA), tB = shiftPoint(S.mv, 0, pr.vel, pr.tB), tC = shiftPoint(S.mv, 0, pr.vel, pr.tC);
+          const float* tuv = pr.tuv;
+          if (S.tri >= 0) { const MeshTri<R>& tr = P.mesh_tris[S.tri]; tA = tr.A; tB = tr.B; tC = tr.C; tuv = tr.uv; }
           Vec<R> nn = cross(tB - tA, tC - tA);
           Vec<R> n_a = cross(tC - tB, S.isectP - tB), n_b = cross(tA - tC, S.isectP - tC);
           float n_sq = (float)dot(nn, nn);
@@ -884,8 +986,8 @@ __device__ void shadeB(const Params<R>& P, ShadeState<R>& S, const PairOut<R>* r
           if (alpha < 0 || alpha > 1 || beta < 0 || beta > 1 || gamma < 0 || gamma > 1) type = 0;
           else if (!(pr.flags & 32)) { S.aborted = true; break; }         // throws geometry.cpp:456-460
           else {
-            u = (float)(((double)alpha * pr.tuv[0] + (double)beta * pr.tuv[2]) + (double)gamma * pr.tuv[4]);
-            v = (float)(((double)alpha * pr.tuv[1] + (double)beta * pr.tuv[3]) + (double)gamma * pr.tuv[5]);
+            u = (float)(((double)alpha * tuv[0] + (double)beta * tuv[2]) + (double)gamma * tuv[4]);
+            v = (float)(((double)alpha * tuv[1] + (double)beta * tuv[3]) + (double)gamma * tuv[5]);
             // the reference compares the double UV against [0,1] before narrowing; equivalent here
             type = 1;
           }

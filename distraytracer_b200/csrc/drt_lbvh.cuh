@@ -1,0 +1,153 @@
+// Device-built LBVH over an indexed triangle mesh (BASELINE config 5: ~1 M triangles).
+//
+// Replaces, for meshes, the reference's generateBVH (helpers.h:381-472), whose SAH sweep copies
+// both index vectors for every candidate split -- O(n^2) per node, infeasible beyond ~10^4
+// primitives.  Build = Morton codes of triangle centroids (30 bit), radix sort
+// (cub::DeviceRadixSort -- the one library call, build-time plumbing, never per ray), Karras
+// 2012 binary radix tree, bottom-up refit with one atomic counter per internal node, then a
+// repack into 64-byte nodes that hold BOTH children's boxes so one node fetch (4 x LDG.128)
+// decides both descents.
+//
+// Node layout (float4 x 4):  { lo0.xyz, child0 } { hi0.xyz, child1 } { lo1.xyz, - } { hi1.xyz, - }
+// child >= 0: internal node index; child < 0: leaf, triangle id = -child - 1.
+#pragma once
+#include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
+#include <stdint.h>
+
+#include "drt_device.cuh"
+
+namespace drt {
+
+__device__ __forceinline__ uint32_t expandBits10(uint32_t v) {   // 10 bits -> every third bit
+  v = (v * 0x00010001u) & 0xFF0000FFu;
+  v = (v * 0x00000101u) & 0x0F00F00Fu;
+  v = (v * 0x00000011u) & 0xC30C30C3u;
+  v = (v * 0x00000005u) & 0x49249249u;
+  return v;
+}
+
+// per triangle: fp32 bounds (padded like the analytic geoms) + Morton code of the centroid
+__global__ void lbvh_tri_setup(int n, const float* __restrict__ verts, const int* __restrict__ idx, float3 slo, float3 sinv,
+                               float4* __restrict__ tlo, float4* __restrict__ thi, uint32_t* __restrict__ codes,
+                               int* __restrict__ ids) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f}, c[3] = {0, 0, 0};
+  for (int k = 0; k < 3; k++) {
+    const int v = idx[3 * i + k];
+    for (int a = 0; a < 3; a++) {
+      const float x = verts[3 * v + a];
+      lo[a] = fminf(lo[a], x); hi[a] = fmaxf(hi[a], x); c[a] += x * (1.0f / 3.0f);
+    }
+  }
+  for (int a = 0; a < 3; a++) {
+    const float pad = 1e-3f + 1e-5f * fmaxf(fabsf(lo[a]), fabsf(hi[a]));
+    lo[a] -= pad; hi[a] += pad;
+  }
+  tlo[i] = make_float4(lo[0], lo[1], lo[2], 0.f);
+  thi[i] = make_float4(hi[0], hi[1], hi[2], 0.f);
+  const float fx = fminf(fmaxf((c[0] - slo.x) * sinv.x * 1024.0f, 0.0f), 1023.0f);
+  const float fy = fminf(fmaxf((c[1] - slo.y) * sinv.y * 1024.0f, 0.0f), 1023.0f);
+  const float fz = fminf(fmaxf((c[2] - slo.z) * sinv.z * 1024.0f, 0.0f), 1023.0f);
+  codes[i] = (expandBits10((uint32_t)fx) << 2) | (expandBits10((uint32_t)fy) << 1) | expandBits10((uint32_t)fz);
+  ids[i] = i;
+}
+
+// Karras: common-prefix length of keys i and j (ties broken by index)
+__device__ __forceinline__ int lbvh_delta(const uint32_t* __restrict__ codes, int n, int i, int j) {
+  if (j < 0 || j >= n) return -1;
+  const uint32_t a = codes[i], b = codes[j];
+  if (a == b) return 32 + __clz((uint32_t)i ^ (uint32_t)j);
+  return __clz(a ^ b);
+}
+
+// one thread per internal node i in [0, n-1): children + parent links
+__global__ void lbvh_karras(int n, const uint32_t* __restrict__ codes, int* __restrict__ left, int* __restrict__ right,
+                            int* __restrict__ parent_internal, int* __restrict__ parent_leaf) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n - 1) return;
+  const int d = (lbvh_delta(codes, n, i, i + 1) - lbvh_delta(codes, n, i, i - 1)) >= 0 ? 1 : -1;
+  const int dmin = lbvh_delta(codes, n, i, i - d);
+  int lmax = 2;
+  while (lbvh_delta(codes, n, i, i + lmax * d) > dmin) lmax *= 2;
+  int l = 0;
+  for (int t = lmax / 2; t >= 1; t /= 2)
+    if (lbvh_delta(codes, n, i, i + (l + t) * d) > dmin) l += t;
+  const int j = i + l * d;
+  const int dnode = lbvh_delta(codes, n, i, j);
+  int s = 0;
+  int t = l;
+  do {
+    t = (t + 1) >> 1;
+    if (lbvh_delta(codes, n, i, i + (s + t) * d) > dnode) s += t;
+  } while (t > 1);
+  const int gamma = i + s * d + min(d, 0);
+  const int lo = min(i, j), hi = max(i, j);
+  // child encoding: >= 0 internal node, < 0 leaf (sorted position = -c - 1)
+  const int lc = (lo == gamma) ? -(gamma + 1) : gamma;
+  const int rc = (hi == gamma + 1) ? -(gamma + 2) : gamma + 1;
+  left[i] = lc; right[i] = rc;
+  if (lc >= 0) parent_internal[lc] = i; else parent_leaf[gamma] = i;
+  if (rc >= 0) parent_internal[rc] = i; else parent_leaf[gamma + 1] = i;
+}
+
+// one thread per leaf: climb, the second arrival at a node merges its children's boxes
+__global__ void lbvh_refit(int n, const int* __restrict__ ids, const float4* __restrict__ tlo, const float4* __restrict__ thi,
+                           const int* __restrict__ left, const int* __restrict__ right, const int* __restrict__ parent_internal,
+                           const int* __restrict__ parent_leaf, float4* nlo, float4* nhi, int* __restrict__ visits) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int node = parent_leaf[i];
+  while (node >= 0) {
+    if (atomicAdd(&visits[node], 1) == 0) return;          // first arrival: the sibling subtree is not done yet
+    __threadfence();
+    float4 lo[2], hi[2];
+    const int ch[2] = {left[node], right[node]};
+    for (int k = 0; k < 2; k++) {
+      if (ch[k] >= 0) { lo[k] = __ldcg(&nlo[ch[k]]); hi[k] = __ldcg(&nhi[ch[k]]); }   // L2 reads: written by another SM
+      else { const int t = ids[-ch[k] - 1]; lo[k] = tlo[t]; hi[k] = thi[t]; }
+    }
+    nlo[node] = make_float4(fminf(lo[0].x, lo[1].x), fminf(lo[0].y, lo[1].y), fminf(lo[0].z, lo[1].z), 0.f);
+    nhi[node] = make_float4(fmaxf(hi[0].x, hi[1].x), fmaxf(hi[0].y, hi[1].y), fmaxf(hi[0].z, hi[1].z), 0.f);
+    __threadfence();
+    node = (node == 0) ? -1 : parent_internal[node];
+  }
+}
+
+// repack into the 64-byte traversal nodes
+__global__ void lbvh_pack(int n, const int* __restrict__ ids, const float4* __restrict__ tlo, const float4* __restrict__ thi,
+                          const int* __restrict__ left, const int* __restrict__ right, const float4* __restrict__ nlo,
+                          const float4* __restrict__ nhi, float4* __restrict__ nodes) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n - 1) return;
+  const int ch[2] = {left[i], right[i]};
+  float4 lo[2], hi[2]; int ref[2];
+  for (int k = 0; k < 2; k++) {
+    if (ch[k] >= 0) { lo[k] = nlo[ch[k]]; hi[k] = nhi[ch[k]]; ref[k] = ch[k]; }
+    else { const int t = ids[-ch[k] - 1]; lo[k] = tlo[t]; hi[k] = thi[t]; ref[k] = -(t + 1); }
+  }
+  nodes[4 * i + 0] = make_float4(lo[0].x, lo[0].y, lo[0].z, __int_as_float(ref[0]));
+  nodes[4 * i + 1] = make_float4(hi[0].x, hi[0].y, hi[0].z, __int_as_float(ref[1]));
+  nodes[4 * i + 2] = make_float4(lo[1].x, lo[1].y, lo[1].z, 0.f);
+  nodes[4 * i + 3] = make_float4(hi[1].x, hi[1].y, hi[1].z, 0.f);
+}
+
+// exact-test records: the three vertices in the vector scalar R (the reference recomputes B-A,
+// C-A per call, geometry.cpp:516-517), plus per-vertex UVs
+template <typename R>
+__global__ void lbvh_tri_records(int n, const float* __restrict__ verts, const int* __restrict__ idx, const float* __restrict__ tc,
+                                 MeshTri<R>* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  MeshTri<R> t;
+  Vec<R>* P[3] = {&t.A, &t.B, &t.C};
+  for (int k = 0; k < 3; k++) {
+    const int v = idx[3 * i + k];
+    *P[k] = mk<R>((R)verts[3 * v], (R)verts[3 * v + 1], (R)verts[3 * v + 2]);
+    t.uv[2 * k] = tc ? tc[2 * v] : 0.f; t.uv[2 * k + 1] = tc ? tc[2 * v + 1] : 0.f;
+  }
+  out[i] = t;
+}
+
+}  // namespace drt

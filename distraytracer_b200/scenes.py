@@ -195,3 +195,67 @@ def config4_frame(frame, xres=1920, yres=1080, spp=16, bones=None):
     settings.xRes, settings.yRes, settings.antialias_samples = xres, yres, spp
     settings.frame, settings.blur_mode, settings.blur_samples, settings.frame_range = int(frame), abi.BLUR_VELOCITY, 2, 1
     return Scene(prims, scene.lights, scene.textures), settings
+
+
+# ---------------------------------------------------------------------------
+def terrain_mesh(n=708, size=12.0, height=1.2, origin=(-6.0, -0.5, -6.0)):
+    """Procedural grid mesh for BASELINE config 5: n x n vertices -> 2 (n-1)^2 triangles
+    (n = 708 gives 999 698), heights from a fixed analytic function (no RNG), UV = grid / (n-1)
+    (SURVEY.md 8d C5).  Returns dict(vertices float32 (V,3), indices int32 (T,3), texcoords float32 (V,2))."""
+    i, j = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+    u, v = i / (n - 1), j / (n - 1)
+    x = origin[0] + size * u
+    z = origin[2] + size * v
+    y = origin[1] + height * (0.5 * np.sin(3.1 * u * np.pi) * np.cos(2.3 * v * np.pi) + 0.25 * np.sin(9.0 * u + 4.0 * v) +
+                              0.1 * np.cos(23.0 * u * v))
+    verts = np.stack([x, y, z], axis=-1).reshape(-1, 3).astype(np.float32)
+    tc = np.stack([u, v], axis=-1).reshape(-1, 2).astype(np.float32)
+    vid = (i * n + j)
+    a, b, c, d = vid[:-1, :-1], vid[1:, :-1], vid[1:, 1:], vid[:-1, 1:]
+    tris = np.concatenate([np.stack([a, b, c], axis=-1).reshape(-1, 3), np.stack([a, c, d], axis=-1).reshape(-1, 3)])
+    return {"vertices": verts, "indices": tris.astype(np.int32), "texcoords": tc}
+
+
+def mesh_material(tex_frame=-1, model=abi.MODEL_OREN_NAYAR, roughness=0.5, color=(0.8, 0.8, 0.8)):
+    """"marble" / oren-nayar roughness 0.5 as the reference's model meshes use (scene.h:564-569)."""
+    p = new_prim()
+    p.type, p.model, p.material = abi.PRIM_TRIANGLE, model, abi.MAT_NONE
+    p.roughness = float(np.float32(roughness))
+    _v(p.color, color)
+    if tex_frame >= 0:
+        p.tex_frame = tex_frame
+        p.flags |= abi.FLAG_TEXTURE | abi.FLAG_UV_VERTS
+    return p
+
+
+def mesh_to_prims(mesh):
+    """The same triangles as individual Triangle primitives (what the reference's loadObj path
+    produces, scene.h:322-386) -- used to feed the CPU oracle, which has no mesh type."""
+    V = mesh["vertices"].astype(np.float64)
+    T = mesh["indices"]
+    tc = mesh.get("texcoords")
+    mat = mesh["material"]
+    out = []
+    for t in T:
+        p = abi.copy_struct(mat)
+        p.type = abi.PRIM_TRIANGLE
+        _v(p.A, V[t[0]]); _v(p.B, V[t[1]]); _v(p.C, V[t[2]])
+        _v(p.center, (V[t[0]] + V[t[1]] + V[t[2]]) / 3)
+        if tc is not None:
+            for dst, k in ((p.uvA, 0), (p.uvB, 1), (p.uvC, 2)):
+                dst[0], dst[1] = float(tc[t[k]][0]), float(tc[t[k]][1])
+        out.append(p)
+    return out
+
+
+def config5(n=708, xres=3840, yres=2160, spp=64):
+    """BASELINE config 5: textured ~1M-triangle terrain, DOF + point light at the eye, 4K 64 spp."""
+    base, settings, _ = load_fixture(os.path.join(GOLDEN, "checkertexture.npz"))
+    mesh = terrain_mesh(n)
+    mesh["material"] = mesh_material(tex_frame=2)            # textures/floor.jpeg of the fixture
+    prims = [sphere((0.0, 1.6, 0.0), 0.7, (1.0, 0.2, 0.2))]
+    s = abi.copy_struct(settings)
+    s.eye[:] = [0.0, 7.0, 9.0]; s.lookingAt[:] = [0.0, 0.0, 0.0]; s.up[:] = [0, 1, 0]
+    s.xRes, s.yRes, s.antialias_samples, s.aperture, s.focal_length = xres, yres, spp, 0.2, 10.0
+    lights = [point_light(tuple(s.eye), (1.0, 1.0, 1.0))]
+    return Scene(prims, lights, base.textures, mesh=mesh), s
