@@ -1226,7 +1226,11 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, 1) render_wave(const __gr
 
     // ================= TRACE: closest hits; the HITS are compacted into the hit buffer ====
     // (rays that miss are finished: they only update the in_motion chain flag)
+#ifdef DRT_ONE_ROUND_PER_PHASE
+    if (count > 0 && nhits < 32) {
+#else
     while (count > 0 && nhits < 32) {
+#endif
       const int take = min(count, 32);
       const bool active = lane < take;
       bool hit = false;
@@ -1254,7 +1258,11 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, 1) render_wave(const __gr
     __syncthreads();
 
     // ================= SHADE: 32 waiting hits -> radiance terms + child rays ================
+#ifdef DRT_ONE_ROUND_PER_PHASE
+    if (nhits >= 32 || (count == 0 && nhits > 0)) {
+#else
     if (nhits > 0) {
+#endif
       const int take = min(nhits, 32);
       const bool active = lane < take;
       Task<R> kids[DRT_MAX_CHILDREN];
@@ -1337,18 +1345,23 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, 1) render_wave(const __gr
 // noise.h -- integer-hash value noise.  The 8 Smoothed3D taps of one
 // InterpolatedNoise3D call (noise.h:89-96) read a 4x4x4 block of lattice hashes;
 // they are hashed once (64 instead of 216 Noise3D calls per octave).
+// prime table of noise.h:12-23 (constant bank: a local array would be re-initialised per call)
+__constant__ int kNoisePrimes[10][3] = {{995615039, 600173719, 701464987}, {831731269, 162318869, 136250887},
+                                        {174329291, 946737083, 245679977}, {362489573, 795918041, 350777237},
+                                        {457025711, 880830799, 909678923}, {787070341, 177340217, 593320781},
+                                        {405493717, 291031019, 391950901}, {458904767, 676625681, 424452397},
+                                        {531736441, 939683957, 810651871}, {997169939, 842027887, 423882827}};
+
 __device__ inline double noise3D(int i_prime, int x, int y, int z) {   // noise.h:31-39, int32 wrap-around explicit
-  const int primes[10][3] = {{995615039, 600173719, 701464987}, {831731269, 162318869, 136250887},
-                             {174329291, 946737083, 245679977}, {362489573, 795918041, 350777237},
-                             {457025711, 880830799, 909678923}, {787070341, 177340217, 593320781},
-                             {405493717, 291031019, 391950901}, {458904767, 676625681, 424452397},
-                             {531736441, 939683957, 810651871}, {997169939, 842027887, 423882827}};
   int n = (int)((double)(x + y * 57) + (double)z * 3249.0);
   uint32_t un = (uint32_t)n;
   un = (un << 13) ^ un;
-  uint32_t a = (uint32_t)primes[i_prime][0], b = (uint32_t)primes[i_prime][1], c = (uint32_t)primes[i_prime][2];
+  uint32_t a = (uint32_t)kNoisePrimes[i_prime][0], b = (uint32_t)kNoisePrimes[i_prime][1], c = (uint32_t)kNoisePrimes[i_prime][2];
   int t = (int)((un * (un * un * a + b) + c) & 0x7fffffffu);
-  return 1.0 - (double)t / 1073741823.0;
+  // the reference divides by denom = 1073741823; the product with the reciprocal differs from the
+  // correctly rounded quotient by at most an ulp of a value that is then narrowed to float below,
+  // and spares a software double division per lattice hash (204 800 per background evaluation)
+  return 1.0 - (double)t * (1.0 / 1073741823.0);
 }
 
 __device__ inline double cosInterp(double a, double b, double x) {     // noise.h:25-29
@@ -1362,17 +1375,26 @@ __device__ inline double interpolatedNoise3D(int ip, double x, double y, double 
   int iZ = (int)z; double fZ = z - iZ;
   // lattice block [iX-1, iX+2] x [iY-1, iY+2] x [iZ-1, iZ+2]
   float lat[4][4][4];
+#pragma unroll
   for (int a = 0; a < 4; a++)
+#pragma unroll
     for (int b = 0; b < 4; b++)
+#pragma unroll
       for (int c = 0; c < 4; c++) lat[a][b][c] = (float)noise3D(ip, iX - 1 + a, iY - 1 + b, iZ - 1 + c);
   const double alpha = 9.0 / 18, beta = 2.0 / (8 * 18), gamma = 4.0 / (6 * 18), delta = 3.0 / (12 * 18);
   double v[2][2][2];
+#pragma unroll
   for (int dx = 0; dx < 2; dx++)
+#pragma unroll
     for (int dy = 0; dy < 2; dy++)
+#pragma unroll
       for (int dz = 0; dz < 2; dz++) {   // Smoothed3D(ip, iX+dx, iY+dy, iZ+dz), noise.h:51-70
         double corners = 0, sides = 0, dg = 0;
+#pragma unroll
         for (int a = -1; a <= 1; a++)
+#pragma unroll
           for (int b = -1; b <= 1; b++)
+#pragma unroll
             for (int c = -1; c <= 1; c++) {
               double val = lat[1 + dx + a][1 + dy + b][1 + dz + c];
               int nz = (a != 0) + (b != 0) + (c != 0);
@@ -1381,10 +1403,13 @@ __device__ inline double interpolatedNoise3D(int ip, double x, double y, double 
         double center = lat[1 + dx][1 + dy][1 + dz];
         v[dx][dy][dz] = alpha * center + beta * corners + gamma * sides + delta * dg;
       }
-  double w3 = cosInterp(v[0][0][0], v[1][0][0], fX), w4 = cosInterp(v[0][1][0], v[1][1][0], fX);
-  double w1 = cosInterp(v[0][0][1], v[1][0][1], fX), w2 = cosInterp(v[0][1][1], v[1][1][1], fX);
-  double i1 = cosInterp(w3, w4, fY), i2 = cosInterp(w1, w2, fY);
-  return cosInterp(i1, i2, fZ);
+  // cosInterpolate (noise.h:25-29): the blend factor depends only on the axis fraction, so it is
+  // evaluated once per axis (3 cosines) instead of once per call (7)
+  const double gx = (1 - cos(fX * DRT_PI)) * 0.5, gy = (1 - cos(fY * DRT_PI)) * 0.5, gz = (1 - cos(fZ * DRT_PI)) * 0.5;
+  const double w3 = v[0][0][0] * (1 - gx) + v[1][0][0] * gx, w4 = v[0][1][0] * (1 - gx) + v[1][1][0] * gx;
+  const double w1 = v[0][0][1] * (1 - gx) + v[1][0][1] * gx, w2 = v[0][1][1] * (1 - gx) + v[1][1][1] * gx;
+  const double i1 = w3 * (1 - gy) + w4 * gy, i2 = w1 * (1 - gy) + w2 * gy;
+  return i1 * (1 - gz) + i2 * gz;
 }
 
 __device__ inline double valueNoise3D(double x, double y, double z) {         // noise.h:124-136
