@@ -520,11 +520,14 @@ int renderCommon(const drt_scene* cs, const drt_settings* st, const drt_tile* ti
   if (st->sample_mode != DRT_SAMPLES_KEYED) return fail(DRT_ERR_UNSUPPORTED, "unknown sample_mode");
   if (st->precision != DRT_PRECISION_REFERENCE && st->precision != DRT_PRECISION_FP32) return fail(DRT_ERR_INVALID, "unknown precision");
   if (st->max_depth < 0 || st->max_depth > 32) return fail(DRT_ERR_UNSUPPORTED, "max_depth outside [0,32]");
-  {  // warp ray-pool bound: LIFO over trees with (brdf_samples [+1 for glass]) children per node
+  {  // CTA ray-pool bound (render_wave): LIFO over trees with (lobes [+1 for glass]) children per node; one
+     // TRACE pass turns at most ~1.5 x DRT_CTA_SLOTS rays into hits, each hit spawns at most `fan` children
     const int lobes = std::max(1, st->nogloss ? 1 : st->brdf_samples);
     const int fan = lobes + (s->any_glass ? 1 : 0);
-    if (st->brdf_samples < 1 || fan > DRT_MAX_CHILDREN || 64 + 32 * (1 + st->max_depth * (fan - 1)) > DRT_POOL_CAP)
-      return fail(DRT_ERR_UNSUPPORTED, "brdf_samples * max_depth exceeds the per-warp ray pool");
+    const long long slots = 12 * 64, per_pass = slots + 32 * 12;
+    if (st->brdf_samples < 1 || fan > DRT_MAX_CHILDREN || st->blur_samples > 4 ||
+        slots * std::max(1, st->blur_samples) + per_pass * (1 + (long long)st->max_depth * (fan - 1)) > 12ll * 4096)
+      return fail(DRT_ERR_UNSUPPORTED, "brdf_samples * max_depth exceeds the per-CTA ray pool");
   }
   CameraD cam;
   int rc = makeCamera(*st, cam);

@@ -179,7 +179,7 @@ __device__ inline bool geomIntersect(const Params<R>& P, const Geom<R>& g, int g
       const Vec<R> r1 = g.p1, r2 = g.p2;
       Vec<R> hh = cross(ray, r2);
       float det = (float)dot(r1, hh);
-      float invdet = (float)(1.0 / (double)det);
+      float invdet = 1.0f / det;   // == (float)(1.0 / (double)det) up to double rounding on float ties
       if (det >= -0.0001f && det <= 0.0001f) return false;
       Vec<R> A0 = start - A;
       float u = (float)((double)invdet * (double)dot(A0, hh));   // float * double evaluates in double
@@ -200,15 +200,18 @@ __device__ inline bool geomIntersect(const Params<R>& P, const Geom<R>& g, int g
 // filter in front of the exact (double) class test.  Never rejects a true hit: the
 // boxes are padded by 1e-3 + 1e-5*|coordinate| on the host and the comparison keeps a
 // relative margin, so only the cost -- not the candidate set -- changes.
-__device__ inline bool slabMayHit(const float4 blo, const float4 bhi, const float ox, const float oy, const float oz,
-                                  const float ix, const float iy, const float iz, const float t_limit) {
-  float t0 = (blo.x - ox) * ix, t1 = (bhi.x - ox) * ix;
+__device__ inline bool slabMayHit(const float4 blo, const float4 bhi, const float nox, const float noy, const float noz,
+                                  const float ix, const float iy, const float iz, const float t_limit, const float err) {
+  // nox = -ox*ix etc. are hoisted per ray: each slab bound is one FFMA.  `err` bounds the
+  // cancellation error of b*i - o*i (a few ulps of |o*i|); inf/NaN (axis-parallel rays) make
+  // every comparison below false, i.e. never reject.
+  float t0 = fmaf(blo.x, ix, nox), t1 = fmaf(bhi.x, ix, nox);
   float tn = fminf(t0, t1), tf = fmaxf(t0, t1);
-  t0 = (blo.y - oy) * iy; t1 = (bhi.y - oy) * iy;
+  t0 = fmaf(blo.y, iy, noy); t1 = fmaf(bhi.y, iy, noy);
   tn = fmaxf(tn, fminf(t0, t1)); tf = fminf(tf, fmaxf(t0, t1));
-  t0 = (blo.z - oz) * iz; t1 = (bhi.z - oz) * iz;
+  t0 = fmaf(blo.z, iz, noz); t1 = fmaf(bhi.z, iz, noz);
   tn = fmaxf(tn, fminf(t0, t1)); tf = fminf(tf, fmaxf(t0, t1));
-  return !(tn > tf * 1.0001f + 1e-4f) && !(tf < 0.0f) && !(tn > t_limit);
+  return !(tn > tf * 1.0001f + 1e-4f + err) && !(tf < -err) && !(tn > t_limit + err);
 }
 
 // Closest hit over all flattened primitives (the candidate loop of rayColor,
@@ -230,8 +233,9 @@ __device__ inline void closestHit(const Params<R>& P, const float4* __restrict__
     // lock-step (warp-uniform loads) and leaves each lane a bit mask of ITS candidates;
     // (2) every lane then walks its own mask, so one loop trip runs one exact test per
     // lane -- whatever geom that is -- instead of one geom for the few lanes that need it.
-    const float ox = (float)start.x, oy = (float)start.y, oz = (float)start.z;
     const float ix = 1.0f / (float)ray.x, iy = 1.0f / (float)ray.y, iz = 1.0f / (float)ray.z;
+    const float ox = -(float)start.x * ix, oy = -(float)start.y * iy, oz = -(float)start.z * iz;   // slabMayHit's hoisted terms
+    const float serr = 4e-7f * (fabsf(ox) + fabsf(oy) + fabsf(oz));
     const bool cull = !mv.velocity_mode;
     const int n = P.n_geoms;
     for (int g0 = 0; g0 < n; g0 += 32) {
@@ -241,7 +245,7 @@ __device__ inline void closestHit(const Params<R>& P, const float4* __restrict__
       for (int gi = g0; gi < g1; gi++) {                                // branch-free: predicate -> mask bit
         const float4 lo = gb[2 * gi], hi = gb[2 * gi + 1];
         const int meta = __float_as_int(lo.w);
-        const bool ok = ((meta & 0xff) != G_HOLE) && (!cull || slabMayHit(lo, hi, ox, oy, oz, ix, iy, iz, FLT_MAX));
+        const bool ok = ((meta & 0xff) != G_HOLE) && (!cull || slabMayHit(lo, hi, ox, oy, oz, ix, iy, iz, FLT_MAX, serr));
         mask |= (ok ? 1u : 0u) << (gi - g0);
       }
       while (mask) {
@@ -249,7 +253,7 @@ __device__ inline void closestHit(const Params<R>& P, const float4* __restrict__
         mask &= mask - 1;
         const Geom<R>& g = P.geoms[gi];
         // a box whose entry lies beyond the best hit cannot hold a closer (or tying) one
-        if (cull && h.t < FLT_MAX && !slabMayHit(g.blo, g.bhi, ox, oy, oz, ix, iy, iz, h.t * 1.0001f + 1e-4f)) continue;
+        if (cull && h.t < FLT_MAX && !slabMayHit(g.blo, g.bhi, ox, oy, oz, ix, iy, iz, h.t * 1.0001f + 1e-4f, serr)) continue;
         const int type = g.type;
         if (COUNT) cnt.geom_tests[type]++;
         float t_hit; int inside, sel;
@@ -344,7 +348,7 @@ __device__ inline bool geomShadow(const Params<R>& P, const Geom<R>& g, int gi, 
       const Vec<R> r1 = g.p1, r2 = g.p2;
       Vec<R> hh = cross(ray, r2);
       float det = (float)dot(r1, hh);
-      float invdet = (float)(1.0 / (double)det);
+      float invdet = 1.0f / det;   // == (float)(1.0 / (double)det) up to double rounding on float ties
       if (det >= -0.0001f && det <= 0.0001f) return false;
       Vec<R> A0 = start - A;
       float u = (float)((double)invdet * (double)dot(A0, hh));
@@ -373,8 +377,9 @@ __device__ inline bool anyHit(const Params<R>& P, const float4* __restrict__ gb,
                               Counts& cnt) {
   const Vec<R> inv_ray = mk<R>(R(1) / gather_ray.x, R(1) / gather_ray.y, R(1) / gather_ray.z);   // sray.cwiseInverse() :813
   if (mv.val == 0.0f) {
-    const float ox = (float)start.x, oy = (float)start.y, oz = (float)start.z;
     const float ix = 1.0f / (float)ray.x, iy = 1.0f / (float)ray.y, iz = 1.0f / (float)ray.z;
+    const float ox = -(float)start.x * ix, oy = -(float)start.y * iy, oz = -(float)start.z * iz;   // slabMayHit's hoisted terms
+    const float serr = 4e-7f * (fabsf(ox) + fabsf(oy) + fabsf(oz));
     const bool cull = !mv.velocity_mode;
     // distance by which the reference's gather origin runs ahead of the test origin
     const float gather_lead = t_max * 1e-3f;
@@ -389,7 +394,7 @@ __device__ inline bool anyHit(const Params<R>& P, const float4* __restrict__ gb,
         const int meta = __float_as_int(lo.w);
         // an area light never shadows itself (832-837)
         const bool ok = ((meta & 0xff) != G_HOLE) && ((meta >> 8) != skip_owner) &&
-                        (!cull || slabMayHit(lo, hi, ox, oy, oz, ix, iy, iz, t_lim));
+                        (!cull || slabMayHit(lo, hi, ox, oy, oz, ix, iy, iz, t_lim, serr));
         mask |= (ok ? 1u : 0u) << (gi - g0);
       }
       while (mask) {                                // each lane walks its own candidates
@@ -446,7 +451,7 @@ __device__ __forceinline__ float meshTriT(const MeshTri<R>& tr, const Vec<R>& ra
   const Vec<R> r1 = tr.B - tr.A, r2 = tr.C - tr.A;
   const Vec<R> hh = cross(ray, r2);
   const float det = (float)dot(r1, hh);
-  const float invdet = (float)(1.0 / (double)det);
+  const float invdet = 1.0f / det;   // == (float)(1.0 / (double)det) up to double rounding on float ties
   if (det >= -0.0001f && det <= 0.0001f) return -1.f;
   const Vec<R> A0 = start - tr.A;
   const float u = (float)((double)invdet * (double)dot(A0, hh));
@@ -1078,80 +1083,88 @@ __device__ __noinline__ void primaryRay(const Params<R>& P, long long gidx, Vec<
   dir = focalPoint - eye_sample;
 }
 
-template <typename R>
-__host__ __device__ constexpr size_t waveScratchBytes() {
-  return DRT_POOL_CAP * sizeof(Task<R>) + 64 * sizeof(HitTask<R>) + 32 * sizeof(PairIn<R>) + 32 * DRT_PAIR_LIGHTS * sizeof(PairOut<R>);
-}
-
-// Phase-locked persistent CTA.  All warps of the CTA run the same phase at the same time
-// (GEN -> TRACE -> SHADE, separated by __syncthreads), so the SM's instruction cache only has
-// to hold one phase's code: with free-running warps the 14k-instruction kernel saturated
-// the GPC instruction cache (ncu: gcc__cache_requests_type_instruction 95 % of peak,
-// sm__icc_request_hit_rate 62 %, 43 % of stall samples "no_instructions").
+// Scratch of one persistent CTA in global memory (L1/L2 resident):
+//   [ DRT_CTA_POOL ray tasks | DRT_CTA_HITS hit tasks | per warp: 32 pair inputs + 32 x DRT_PAIR_LIGHTS pair results ]
 #ifndef DRT_WAVE_WARPS
 #define DRT_WAVE_WARPS 12
 #endif
+#define DRT_CTA_SLOTS (DRT_WAVE_WARPS * DRT_BATCH)   // camera samples per CTA batch
+#define DRT_CTA_POOL (DRT_WAVE_WARPS * 4096)         // pending rays
+#define DRT_CTA_HITS (DRT_CTA_SLOTS + 32 * DRT_WAVE_WARPS + 64)
+template <typename R>
+__host__ __device__ constexpr size_t waveScratchBytes() {
+  return DRT_CTA_POOL * sizeof(Task<R>) + DRT_CTA_HITS * sizeof(HitTask<R>) +
+         DRT_WAVE_WARPS * (32 * sizeof(PairIn<R>) + 32 * DRT_PAIR_LIGHTS * sizeof(PairOut<R>));
+}
+
+// render_wave -- phase-locked persistent CTA with CTA-wide work pools.
+//
+// One CTA of DRT_WAVE_WARPS warps per SM.  All warps run the same phase at the same time
+// (GEN -> TRACE -> SHADE, separated by __syncthreads), so the SM's instruction cache only has to
+// hold one phase's code: with free-running warps the 14k-instruction kernel saturated the GPC
+// instruction cache (ncu: gcc__cache_requests_type_instruction 95 % of peak,
+// sm__icc_request_hit_rate 62 %, 43 % of stall samples "no_instructions").
+// Pending rays and hits of the CTA's current batch (DRT_CTA_SLOTS camera samples) live in ONE
+// LIFO pool / hit buffer per CTA; inside a phase every warp keeps grabbing the next 32 items
+// from the top through a shared-memory cursor until the phase's work is gone, so all lanes of
+// all warps stay busy and a phase ends within one 32-item chunk of the last warp (with
+// warp-private pools 27 % of the stall samples were barrier waits).
 template <typename R, bool COUNT>
 __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, 1) render_wave(const __grid_constant__ Params<R> P) {
-  __shared__ unsigned long long s_acc[DRT_WAVE_WARPS][DRT_BATCH][3];
-  __shared__ unsigned int s_flags[DRT_WAVE_WARPS][DRT_BATCH];
+  __shared__ unsigned long long s_acc[DRT_CTA_SLOTS][3];
+  __shared__ unsigned int s_flags[DRT_CTA_SLOTS];
+  __shared__ int s_count, s_nhits, s_grab, s_state, s_nvalid;
+  __shared__ long long s_idx0;
   // slab-filter table of the whole scene, staged once per persistent CTA (32 B per geom)
   __shared__ float4 s_gb[2 * DRT_SMEM_GEOMS];
   const float4* gb = P.gbounds;
 #ifndef DRT_NO_SMEM_GB
   if (P.n_geoms <= DRT_SMEM_GEOMS) {
     for (int i = threadIdx.x; i < 2 * P.n_geoms; i += blockDim.x) s_gb[i] = P.gbounds[i];
-    __syncthreads();
     gb = s_gb;
   }
 #endif
   const unsigned FULL = 0xffffffffu;
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  // per-warp scratch in global memory (L1/L2 resident):
-  //   [ DRT_POOL_CAP ray tasks | 64 hit tasks | 32 pair inputs | 32 x DRT_PAIR_LIGHTS pair results ]
-  char* wbase = (char*)P.pool_raw + (size_t)(blockIdx.x * DRT_WAVE_WARPS + wib) * waveScratchBytes<R>();
-  Task<R>* pool = (Task<R>*)wbase;
-  HitTask<R>* hits = (HitTask<R>*)(wbase + DRT_POOL_CAP * sizeof(Task<R>));
-  PairIn<R>* pairin = (PairIn<R>*)(hits + 64);
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, tid = threadIdx.x;
+  char* cbase = (char*)P.pool_raw + (size_t)blockIdx.x * waveScratchBytes<R>();
+  Task<R>* pool = (Task<R>*)cbase;
+  HitTask<R>* hits = (HitTask<R>*)(cbase + DRT_CTA_POOL * sizeof(Task<R>));
+  char* wbase = (char*)(hits + DRT_CTA_HITS) + (size_t)wib * (32 * sizeof(PairIn<R>) + 32 * DRT_PAIR_LIGHTS * sizeof(PairOut<R>));
+  PairIn<R>* pairin = (PairIn<R>*)wbase;
   PairOut<R>* pairout = (PairOut<R>*)(pairin + 32);
-  unsigned long long(*acc)[3] = s_acc[wib];
-  unsigned int* sfl = s_flags[wib];
-  const long long n_batches = (P.sample_count + DRT_BATCH - 1) / DRT_BATCH;
+  unsigned long long(*acc)[3] = s_acc;
+  unsigned int* sfl = s_flags;
+  const long long n_batches = (P.sample_count + DRT_CTA_SLOTS - 1) / DRT_CTA_SLOTS;
 
   Counts cnt;
   if (COUNT) { cnt.samples = 0; cnt.rays = 0; cnt.shadow_rays = 0; cnt.shade_evals = 0; cnt.noise_evals = 0; cnt.node_tests = 0;
                for (int i = 0; i < 6; i++) cnt.geom_tests[i] = 0; }
 
-  // warp-uniform state
-  bool have_batch = false, more_batches = true;
-  int count = 0, nhits = 0, phase = 0, n_valid = 0;
-  long long idx0 = 0;
+  // s_state: 0 = no batch, 1 = primary trees in flight, 2 = blur re-traces in flight, 3 = all batches done
+  if (tid == 0) { s_count = 0; s_nhits = 0; s_state = 0; s_nvalid = 0; s_idx0 = 0; }
+  __syncthreads();
 
   for (;;) {
     // ================= GEN: batch bookkeeping (rare) =================================
-    if (have_batch && count == 0 && nhits == 0) {                        // the batch's current trees are drained
-      bool to_blur = false;
-      if (phase == 0 && P.blur_samples > 0) {
+    if (s_count == 0 && s_nhits == 0) {                                  // CTA-uniform: the current trees are drained
+      const int state = s_state;
+      const int n_valid = s_nvalid;
+      const long long idx0 = s_idx0;
+      __syncthreads();
+      bool finalize = false;
+      if (state == 1 && P.blur_samples > 0) {
         // motion blur: re-trace the samples whose in_motion flag ended up set
         // (render_final_project.cpp:1095-1210); the extra traces go through the same pool
-        int any_motion = 0;
-        for (int s2 = lane; s2 < n_valid; s2 += 32) any_motion |= ((sfl[s2] & (SS_MOTION | SF_ABORT)) == SS_MOTION);
-        to_blur = __any_sync(FULL, any_motion);
-      }
-      if (to_blur) {
-        for (int r = 0; r < DRT_BATCH / 32; r++) {
-          const int s2 = r * 32 + lane;
-          const bool mo = s2 < n_valid && ((sfl[s2] & (SS_MOTION | SF_ABORT)) == SS_MOTION);
-          int nb = mo ? P.blur_samples : 0;
-          int incl = nb;
-#pragma unroll
-          for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += v; }
-          const int total = __shfl_sync(FULL, incl, 31);
-          if (mo) {
+        int mine = 0;
+        for (int s2 = tid; s2 < n_valid; s2 += blockDim.x) mine |= ((sfl[s2] & (SS_MOTION | SF_ABORT)) == SS_MOTION);
+        if (__syncthreads_or(mine)) {
+          for (int s2 = tid; s2 < n_valid; s2 += blockDim.x) {
+            if ((sfl[s2] & (SS_MOTION | SF_ABORT)) != SS_MOTION) continue;
             Task<R> T; uint32_t skey; int pi, pj, px, py;
             primaryRay<R>(P, P.sample_base + idx0 + s2, T.org, T.dir, skey, pi, pj, px, py);
             T.k = 1.0f; T.depth = (short)P.max_depth; T.chain = 0; T.flags = 0; T.slot = (unsigned short)s2; T.pad_ = 0;
-            for (int m = 0; m < nb; m++) {
+            const int at = atomicAdd(&s_count, P.blur_samples);
+            for (int m = 0; m < P.blur_samples; m++) {
               float frame_sample = (float)((double)(float)P.frame + (double)rng_u01(skey, (uint32_t)m) * (double)P.frame_range);
               float dt = frame_sample - (float)P.frame;
               float val = 0;                                            // uninitialised in the reference below frame_prism (Q16)
@@ -1160,16 +1173,15 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, 1) render_wave(const __gr
                 else val = P.move_per_frame * dt;
               }
               T.val = val; T.dt = dt; T.path = rng_key_child(skey, 1 + m);
-              if (count + incl - nb + m < DRT_POOL_CAP) pool[count + incl - nb + m] = T;
+              pool[at + m] = T;                                         // <= DRT_CTA_SLOTS * blur_samples, validated on the host
             }
           }
-          count = min(count + total, DRT_POOL_CAP);
-          __syncwarp();
-        }
-        phase = 1;
-      } else {
+          if (tid == 0) s_state = 2;
+        } else finalize = true;
+      } else if (state == 1 || state == 2) finalize = true;
+      if (finalize) {
         // ---- per-sample results -----------------------------------------------------
-        for (int s2 = lane; s2 < n_valid; s2 += 32) {
+        for (int s2 = tid; s2 < n_valid; s2 += blockDim.x) {
           const unsigned int f = sfl[s2];
           double c[3];
           for (int k = 0; k < 3; k++) {
@@ -1196,47 +1208,53 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, 1) render_wave(const __gr
           }
           P.samples[idx0 + s2] = make_float4((float)c[0], (float)c[1], (float)c[2], __uint_as_float(flags));
         }
-        __syncwarp();
-        have_batch = false;
+        if (tid == 0) s_state = 0;
       }
-    }
-    if (!have_batch && more_batches) {                                   // claim the next batch of camera samples
-      long long b = 0;
-      if (lane == 0) b = (long long)atomicAdd(P.batch_counter, 1ull);
-      b = __shfl_sync(FULL, b, 0);
-      if (b >= n_batches) more_batches = false;
-      else {
-        idx0 = b * DRT_BATCH;                                            // chunk-local sample index of slot 0
-        n_valid = (int)min((long long)DRT_BATCH, P.sample_count - idx0);
-        for (int s2 = lane; s2 < DRT_BATCH; s2 += 32) { acc[s2][0] = acc[s2][1] = acc[s2][2] = 0ull; sfl[s2] = 0u; }
-        __syncwarp();
-        for (int s2 = lane; s2 < n_valid; s2 += 32) {                    // primary rays -> pool[0..n_valid)
+      __syncthreads();
+      if (s_state == 0) {                                                // claim the next batch of camera samples
+        if (tid == 0) {
+          const long long b = (long long)atomicAdd(P.batch_counter, 1ull);
+          if (b >= n_batches) s_state = 3;
+          else {
+            s_idx0 = b * DRT_CTA_SLOTS;                                  // chunk-local sample index of slot 0
+            s_nvalid = (int)min((long long)DRT_CTA_SLOTS, P.sample_count - s_idx0);
+            s_state = 1;
+          }
+        }
+        __syncthreads();
+        if (s_state == 3) break;
+        const int nv = s_nvalid;
+        const long long i0 = s_idx0;
+        for (int s2 = tid; s2 < DRT_CTA_SLOTS; s2 += blockDim.x) { acc[s2][0] = acc[s2][1] = acc[s2][2] = 0ull; sfl[s2] = 0u; }
+        for (int s2 = tid; s2 < nv; s2 += blockDim.x) {                  // primary rays -> pool[0..nv)
           Task<R> T; uint32_t skey; int pi, pj, px, py;
-          primaryRay<R>(P, P.sample_base + idx0 + s2, T.org, T.dir, skey, pi, pj, px, py);
+          primaryRay<R>(P, P.sample_base + i0 + s2, T.org, T.dir, skey, pi, pj, px, py);
           T.k = 1.0f; T.path = rng_key_child(skey, 0); T.val = 0.f; T.dt = 0.f; T.depth = (short)P.max_depth;
           T.chain = 1; T.flags = 1; T.slot = (unsigned short)s2; T.pad_ = 0;
           pool[s2] = T;
           if (COUNT) cnt.samples++;
         }
-        __syncwarp();
-        count = n_valid; nhits = 0; phase = 0; have_batch = true;
+        if (tid == 0) s_count = nv;
       }
+      __syncthreads();
     }
-    if (!__syncthreads_or(have_batch ? 1 : 0)) break;                    // every warp idle, no batches left
 
     // ================= TRACE: closest hits; the HITS are compacted into the hit buffer ====
     // (rays that miss are finished: they only update the in_motion chain flag)
-#ifdef DRT_ONE_ROUND_PER_PHASE
-    if (count > 0 && nhits < 32) {
-#else
-    while (count > 0 && nhits < 32) {
-#endif
-      const int take = min(count, 32);
-      const bool active = lane < take;
+    if (tid == 0) s_grab = s_count;
+    __syncthreads();
+    for (;;) {
+      if (((volatile int*)&s_nhits)[0] >= DRT_CTA_SLOTS) break;          // hit buffer has a full SHADE pass waiting
+      int end = 0;
+      if (lane == 0) end = atomicSub(&s_grab, 32);
+      end = __shfl_sync(FULL, end, 0);
+      if (end <= 0) break;
+      const int begin = max(end - 32, 0);
+      const bool active = begin + lane < end;
       bool hit = false;
       HitTask<R> H;
       if (active) {
-        H.T = pool[count - 1 - lane];
+        H.T = pool[end - 1 - lane];
         const unsigned int f = ((volatile unsigned int*)sfl)[H.T.slot];
         if (!(f & SF_ABORT)) {                                          // an aborted sample spawns no more work (Q15)
           HitRec h; int motion;
@@ -1249,21 +1267,24 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, 1) render_wave(const __gr
           H.t = h.t; H.geom = h.geom; H.inside = h.inside; H.checker_sel = h.checker_sel;
         }
       }
-      count -= take;
       const unsigned int hm = __ballot_sync(FULL, hit);
-      if (hit) hits[nhits + __popc(hm & ((1u << lane) - 1u))] = H;
-      nhits += __popc(hm);
-      __syncwarp();
+      int hbase = 0;
+      if (lane == 0 && hm) hbase = atomicAdd(&s_nhits, __popc(hm));
+      hbase = __shfl_sync(FULL, hbase, 0);
+      if (hit) hits[hbase + __popc(hm & ((1u << lane) - 1u))] = H;
     }
     __syncthreads();
+    if (tid == 0) { s_count = max(s_grab, 0); s_grab = s_nhits; }        // untouched rays stay at the bottom of the pool
+    __syncthreads();
 
-    // ================= SHADE: 32 waiting hits -> radiance terms + child rays ================
-#ifdef DRT_ONE_ROUND_PER_PHASE
-    if (nhits >= 32 || (count == 0 && nhits > 0)) {
-#else
-    if (nhits > 0) {
-#endif
-      const int take = min(nhits, 32);
+    // ================= SHADE: waiting hits -> radiance terms + child rays ====================
+    for (;;) {
+      int end = 0;
+      if (lane == 0) end = atomicSub(&s_grab, 32);
+      end = __shfl_sync(FULL, end, 0);
+      if (end <= 0) break;
+      const int begin = max(end - 32, 0);
+      const int take = end - begin;
       const bool active = lane < take;
       Task<R> kids[DRT_MAX_CHILDREN];
       int nk = 0;
@@ -1274,7 +1295,7 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, 1) render_wave(const __gr
       {
         PairIn<R> pin; pin.want = 0;
         if (active) {
-          const HitTask<R> H = hits[nhits - 1 - lane];
+          const HitTask<R> H = hits[end - 1 - lane];
           HitRec h; h.t = H.t; h.geom = H.geom; h.inside = H.inside; h.checker_sel = H.checker_sel;
           slot = H.T.slot;
           shadeA<R, COUNT>(P, H.T, h, kids, nk, add, has_add, aborted, S, cnt);
@@ -1314,22 +1335,24 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, 1) render_wave(const __gr
           if (orf) atomicOr(&sfl[slot], orf);
         }
       }
-      nhits -= take;
-      // compact the children back into the pool (warp inclusive scan of nk)
+      // compact the children onto the top of the CTA pool (warp inclusive scan of nk)
       int incl = nk;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += v; }
       const int total = __shfl_sync(FULL, incl, 31);
-      if (count + total > DRT_POOL_CAP) {                               // cannot happen within the validated bounds
+      int pbase = 0;
+      if (lane == 31 && total) pbase = atomicAdd(&s_count, total);
+      pbase = __shfl_sync(FULL, pbase, 31);
+      if (pbase + total > DRT_CTA_POOL) {                               // cannot happen within the validated bounds
         if (nk) atomicOr(&sfl[kids[0].slot], SF_ABORT);
-        if (lane == 0) *P.overflow = 1;
+        if (lane == 0) { *P.overflow = 1; atomicSub(&s_count, total); }
       } else {
-        const int base = count + incl - nk;
+        const int base = pbase + incl - nk;
         for (int j = 0; j < nk; j++) pool[base + j] = kids[j];
-        count += total;
       }
-      __syncwarp();
     }
+    __syncthreads();
+    if (tid == 0) s_nhits = 0;
     __syncthreads();
   }
 
