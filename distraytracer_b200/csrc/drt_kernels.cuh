@@ -1,15 +1,14 @@
 // CUDA kernels of the distributed ray-tracing hot path (sm_100a).
 //
-//   render_samples<R> : one thread per camera sample.  Replaces the sample loop of
-//       renderImage (render_final_project.cpp:1062-1212) and the whole recursive
-//       rayColor (487-961): camera ray with thin-lens DOF, closest-hit search over
-//       the flattened primitives, Fresnel refraction, mirror / glossy reflection
-//       lobes, per-light shadow rays (point / rectangle / sphere lights),
-//       Oren-Nayar / Cook-Torrance / Lambert+Phong shading, nearest-texel texture
-//       fetch through CUDA texture objects, emissive shapes, motion-blur re-traces.
-//       The recursion is an explicit per-thread stack of pending rays: every
-//       rayColor invocation only ever ADDS k-weighted radiance into the sample's
-//       colour, so the order the tree is walked in does not matter.
+//   render_wave<R>    : persistent, phase-locked CTAs working through ray pools.  Replaces the
+//       sample loop of renderImage (render_final_project.cpp:1062-1212) and the whole recursive
+//       rayColor (487-961): camera ray with thin-lens DOF, closest-hit search over the flattened
+//       primitives (+ LBVH traversal for triangle meshes), Fresnel refraction, mirror / glossy
+//       reflection lobes, per-light shadow rays (point / rectangle / sphere lights),
+//       Oren-Nayar / Cook-Torrance / Lambert+Phong shading, nearest-texel texture fetch through
+//       CUDA texture objects, emissive shapes, motion-blur re-traces.  Every rayColor invocation
+//       only ever ADDS a k-weighted term to the sample's colour, so the order the tree is
+//       walked in does not matter.
 //   cloud_corners<R>  : skyColor/cloudColor (146-192) + noise.h per PIXEL CORNER.
 //       getPerspEyeRay takes int pixel coordinates (helpers.h:320, quirk Q1), so
 //       every sample of a pixel that misses the scene asks for the same background
@@ -1032,21 +1031,20 @@ __device__ void shadeB(const Params<R>& P, ShadeState<R>& S, const PairOut<R>* r
 }
 
 // ---------------------------------------------------------------------------
-// render_wave: persistent warps + warp-local ray pools.
+// render_wave: why the unit of scheduling is the RAY, not the camera sample.
 //
-// A thread-per-sample walk of the ray tree leaves most lanes idle: tree sizes are
-// heavy-tailed (glossy lobes and glass fan out 2-3 rays per bounce to depth 10), so a
-// warp runs as long as its largest tree (ncu, profiles/r1_*: 7 of 32 lanes active in
-// the object-heavy half of the C2 frame).  Here the unit of scheduling is the RAY:
-//   * each warp repeatedly claims a batch of DRT_BATCH consecutive camera samples
+// A thread-per-sample walk of the ray tree leaves most lanes idle: tree sizes are heavy-tailed
+// (glossy lobes and glass fan out 2-3 rays per bounce to depth 10), so a warp runs as long as
+// its largest tree (ncu, profiles/r1_ncu_full_bench_chunk0_thread_per_sample.txt: 7 of 32 lanes
+// active in the object-heavy half of the C2 frame).  Here
+//   * a persistent CTA repeatedly claims a batch of DRT_CTA_SLOTS consecutive camera samples
 //     from a global counter (dynamic load balance, no tail of straggler blocks);
-//   * all pending rays of the batch live in the warp's LIFO pool in global memory
-//     (L1/L2 resident); per iteration the top min(count,32) rays are popped, one per
-//     lane, processed with processRay(), and the children are compacted back with a
-//     warp prefix sum (ballot-free shuffle scan);
-//   * per-sample radiance is accumulated in 64-bit fixed point (2^-32) with shared
-//     memory atomics, so the sum does not depend on the order rays are processed in
-//     and the output stays bit-reproducible.
+//   * all pending rays of the batch live in the CTA's LIFO pool in global memory; hits wait in
+//     a hit buffer; warps grab 32-item chunks of either, one item per lane;
+//   * children are compacted back with a warp prefix sum (shuffle scan);
+//   * per-sample radiance is accumulated in 64-bit fixed point (2^-32) with shared-memory
+//     atomics, so the sum does not depend on the order rays are processed in and the output
+//     stays bit-reproducible.
 
 // per-sample state bits (shared memory) -- the low 4 are also the output flag bits
 #define SS_HIT 16u
@@ -1090,7 +1088,12 @@ __device__ __noinline__ void primaryRay(const Params<R>& P, long long gidx, Vec<
 #endif
 #define DRT_CTA_SLOTS (DRT_WAVE_WARPS * DRT_BATCH)   // camera samples per CTA batch
 #define DRT_CTA_POOL (DRT_WAVE_WARPS * 4096)         // pending rays
-#define DRT_CTA_HITS (DRT_CTA_SLOTS + 32 * DRT_WAVE_WARPS + 64)
+// TRACE stops feeding the hit buffer at this many hits: larger = fewer phase switches and fuller
+// SHADE passes, smaller = shallower LIFO pool.
+#ifndef DRT_TRACE_HITS_TARGET
+#define DRT_TRACE_HITS_TARGET DRT_CTA_SLOTS
+#endif
+#define DRT_CTA_HITS (DRT_TRACE_HITS_TARGET + 32 * DRT_WAVE_WARPS + 64)
 template <typename R>
 __host__ __device__ constexpr size_t waveScratchBytes() {
   return DRT_CTA_POOL * sizeof(Task<R>) + DRT_CTA_HITS * sizeof(HitTask<R>) +
@@ -1244,7 +1247,7 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, 1) render_wave(const __gr
     if (tid == 0) s_grab = s_count;
     __syncthreads();
     for (;;) {
-      if (((volatile int*)&s_nhits)[0] >= DRT_CTA_SLOTS) break;          // hit buffer has a full SHADE pass waiting
+      if (((volatile int*)&s_nhits)[0] >= DRT_TRACE_HITS_TARGET) break;  // enough hits for a full SHADE pass are waiting
       int end = 0;
       if (lane == 0) end = atomicSub(&s_grab, 32);
       end = __shfl_sync(FULL, end, 0);
