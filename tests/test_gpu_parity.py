@@ -168,3 +168,45 @@ def test_cuda_mesh_full_size_builds_and_is_deterministic(oracle_lib):
     a = dev.render(s, band)
     b = dev.render(s, band)
     assert np.array_equal(a, b) and a.std() > 5
+
+
+def test_production_spp_mae_against_high_spp_reference(oracle_lib):
+    """North-star statistical bar: at production spp (64) the image must be within a mean absolute
+    error of 0.5/255 of a high-spp reference render.  The reference render is the oracle in
+    DRT_ORACLE_STREAM mode -- the sequential sample stream in the reference's own draw order,
+    bit-identical to the compiled reference (tests/test_oracle_golden.py) -- i.e. a different sample
+    set drawn a different way (per-pixel lens shuffle included), so this checks that the keyed
+    sampler of the CUDA path is unbiased, not just that it repeats the oracle.
+    "High spp" is 32 independent 64-spp frames averaged (2048 spp): the reference's own jitter is
+    `(i + u)/9` with a hard-coded 9 and int truncation (render_final_project.cpp:1052, quirk Q1), so
+    a single frame with n = sqrt(spp) > 9 samples neighbouring PIXELS and is a different image."""
+    from distraytracer_b200 import abi
+    from oracle.harness import Oracle, ORACLE_STREAM
+    # (case, overrides, single 64-spp frame must meet the bar).  On the area-light scenes the
+    # reference's OWN 64-spp frame is 1.2-1.3/255 away from its converged mean (Monte Carlo noise,
+    # measured with the oracle), so there the bar is asserted on the mean of 16 frames (noise / 4)
+    # and the single frame only has to be as close as the reference's own single frame is.
+    for case, extra, single in (("reflectance", {}, True), ("boundary_mocap", {"aperture": 0.2}, False),
+                                ("spherelight", {"aperture": 0.2}, False)):
+        scene, settings, _ = load_case(case)
+        s = abi.copy_struct(settings)
+        s.xRes, s.yRes, s.antialias_samples = 64, 36, 64
+        for k, v in extra.items():
+            setattr(s, k, v)
+        o = Oracle(scene)
+        dev = _gpu(scene)
+        ref_frames, our_frames = [], []
+        for k in range(16):
+            q = abi.copy_struct(s); q.seed = 100 + k
+            ref_frames.append(np.clip(o.render(q, mode=ORACLE_STREAM)[0], 0, 255))
+            q.seed = 5000 + k
+            our_frames.append(np.clip(dev.render_float(q)[0], 0, 255))
+        ref = np.mean(ref_frames, axis=0)
+        mae_mean = float(np.abs(np.mean(our_frames, axis=0) - ref).mean())
+        assert mae_mean <= 0.5, (case, "mean of 16 frames", mae_mean)
+        q = abi.copy_struct(s); q.seed = 777
+        ref_self = float(np.abs(np.clip(o.render(q, mode=ORACLE_STREAM)[0], 0, 255) - ref).mean())
+        ours_single = float(np.abs(our_frames[0] - ref).mean())
+        if single:
+            assert ours_single <= 0.5, (case, ours_single)
+        assert ours_single <= 1.2 * ref_self + 0.05, (case, ours_single, ref_self)
