@@ -716,6 +716,19 @@ void drt_abi_sizes(int32_t* out6) {
   out6[3] = (int32_t)sizeof(drt_settings); out6[4] = (int32_t)sizeof(drt_tile); out6[5] = (int32_t)sizeof(drt_counters);
 }
 
+// The candidate order the scene flattener derives from its replay of the reference's BVH build
+// (drt_bvh_order.h): primitive indices, `cap` entries at most; returns the count.  Host only.
+int drt_debug_candidate_order(const drt_prim* prims, int32_t n_prims, int32_t* out, int32_t cap) {
+  if (!prims || n_prims < 1 || !out) return 0;
+  std::vector<double> centers(3 * (size_t)n_prims);
+  for (int i = 0; i < n_prims; i++) for (int a = 0; a < 3; a++) centers[3 * i + a] = prims[i].center[a];
+  ReferenceBVH bvh;
+  bvh.build(centers.data(), n_prims, [&](int prim, double lo[3], double hi[3]) { primBounds(prims[prim], lo, hi); });
+  int n = 0;
+  for (int i : bvh.order) { if (n < cap) out[n] = i; n++; }
+  return n;
+}
+
 // Evaluates the device sample stream on the HOST copy of the same inline
 // functions (drt_rng.cuh) so tests can compare it with the oracle's copy.
 float drt_debug_rng(uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t child, uint32_t dim) {

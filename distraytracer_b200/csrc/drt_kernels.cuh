@@ -19,6 +19,10 @@
 #include "drt_device.cuh"
 #include "drt_launch.h"
 
+#ifndef DRT_FORCE_TREE
+#define DRT_FORCE_TREE 0   // diagnostic: 1 walks the replayed reference tree for every ray
+#endif
+
 namespace drt {
 
 
@@ -56,7 +60,7 @@ __device__ inline bool rectHit(const Vec<R>& A, const Vec<R>& nrm, const Vec<R>&
                                float eps, const Vec<R>& ray, const Vec<R>& start, float& t, float& c1o, float& c2o) {
   float dn = (float)dot(ray, nrm);
   if (dn == 0.0f) return false;
-  float t_final = (float)dot(A - start, nrm) / dn;
+  float t_final = (float)(dot(A - start, nrm) / (R)dn);   // double / float -> double, then narrowed (geometry.cpp:676)
   if (t_final <= eps) return false;
   Vec<R> point = start + (R)t_final * ray;
   Vec<R> V_hit = point - A;
@@ -227,7 +231,7 @@ template <typename R, bool COUNT>
 __device__ inline void closestHit(const Params<R>& P, const float4* __restrict__ gb, const Moved<R>& mv, const Vec<R>& ray,
                                   const Vec<R>& start, HitRec& h, Counts& cnt) {
   h.t = FLT_MAX; h.geom = -1; h.inside = 0; h.checker_sel = 0;
-  if (mv.val == 0.0f) {
+  if (mv.val == 0.0f && !DRT_FORCE_TREE) {
     // Two passes per group of 32 geoms: (1) the slab filter runs over the group in
     // lock-step (warp-uniform loads) and leaves each lane a bit mask of ITS candidates;
     // (2) every lane then walks its own mask, so one loop trip runs one exact test per
@@ -375,7 +379,7 @@ __device__ inline bool anyHit(const Params<R>& P, const float4* __restrict__ gb,
                               const Vec<R>& gather_start, const Vec<R>& ray, const Vec<R>& start, float t_max, int skip_owner,
                               Counts& cnt) {
   const Vec<R> inv_ray = mk<R>(R(1) / gather_ray.x, R(1) / gather_ray.y, R(1) / gather_ray.z);   // sray.cwiseInverse() :813
-  if (mv.val == 0.0f) {
+  if (mv.val == 0.0f && !DRT_FORCE_TREE) {
     const float ix = 1.0f / (float)ray.x, iy = 1.0f / (float)ray.y, iz = 1.0f / (float)ray.z;
     const float ox = -(float)start.x * ix, oy = -(float)start.y * iy, oz = -(float)start.z * iz;   // slabMayHit's hoisted terms
     const float serr = 4e-7f * (fabsf(ox) + fabsf(oy) + fabsf(oz));
@@ -952,7 +956,7 @@ __device__ void shadeB(const Params<R>& P, ShadeState<R>& S, const PairOut<R>* r
               float dn = (float)dot(ray1, pr.hn);
               in_hole = false;
               if (dn != 0.0f) {
-                float t_final = (float)dot(pr.hA - start1, pr.hn) / dn;
+                float t_final = (float)(dot(pr.hA - start1, pr.hn) / (R)dn);
                 if (!(t_final <= 1e-4f)) {
                   Vec<R> point = start1 + (R)t_final * ray1;
                   Vec<R> Vh = point - pr.hA;

@@ -16,7 +16,7 @@ _lib = None
 EXPORTS = [
     "drt_device_count", "drt_settings_default", "drt_prim_default", "drt_scene_create", "drt_scene_update_prims",
     "drt_scene_destroy", "drt_render", "drt_render_float", "drt_render_device", "drt_write_ppm", "drt_last_error",
-    "drt_abi_sizes", "drt_debug_rng",
+    "drt_abi_sizes", "drt_debug_rng", "drt_debug_candidate_order",
 ]
 
 
@@ -49,6 +49,7 @@ def lib():
         L.drt_abi_sizes.argtypes = [C.POINTER(C.c_int32)]
         L.drt_debug_rng.argtypes = [C.c_uint32] * 5
         L.drt_debug_rng.restype = C.c_float
+        L.drt_debug_candidate_order.argtypes = [C.POINTER(abi.Prim), C.c_int32, C.POINTER(C.c_int32), C.c_int32]
         _lib = L
     return _lib
 

@@ -320,6 +320,9 @@ void drt_abi_sizes(int32_t* out6);
  * camera sample `sample` of pixel `pixel`; evaluated on the host from the same
  * inline functions the kernels use. */
 float drt_debug_rng(uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t child, uint32_t dim);
+/* Primitive indices in the candidate order the library derives from its host-side replay of the
+ * reference's generateBVH (helpers.h:381-472); ties of t between shapes resolve in this order. */
+int drt_debug_candidate_order(const drt_prim* prims, int32_t n_prims, int32_t* out, int32_t cap);
 
 #ifdef __cplusplus
 }

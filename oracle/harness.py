@@ -192,6 +192,14 @@ class Oracle:
             raise RuntimeError(f"oracle render failed ({rc}): {self.lib.drt_oracle_last_error().decode()}")
         return out, ab.astype(bool), cnt, sec.value
 
+    def candidate_order(self):
+        n = len(self.scene.prims)
+        buf = (C.c_int * n)()
+        self.lib.drt_oracle_candidate_order.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_int]
+        got = self.lib.drt_oracle_candidate_order(self.handle, buf, n)
+        assert got == n
+        return list(buf)
+
     def value_noise(self, x, y, z):
         return self.lib.drt_oracle_value_noise(x, y, z)
 

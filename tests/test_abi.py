@@ -78,3 +78,18 @@ def test_rng_matches_oracle_copy(lib, oracle_lib):
         for _ in range(2000):
             a = [int(v) for v in rng.integers(0, 2**32, size=5, dtype=np.uint64)]
             assert float(lib.drt_debug_rng(*a)) == P.probe(*a)
+
+
+def test_host_bvh_replay_gives_the_reference_candidate_order(lib, oracle_lib):
+    """drt_bvh_order.h (product, host side) replays the reference's SAH build; its leaf visiting
+    order must equal the oracle's (which is pinned bit-exactly against the compiled reference)."""
+    from conftest import GOLDEN_CASES, load_case
+    from distraytracer_b200 import abi
+    from oracle.harness import Oracle
+    for case in GOLDEN_CASES:
+        scene, _, _ = load_case(case)
+        n = len(scene.prims)
+        arr = (abi.Prim * n)(*scene.prims)
+        out = (C.c_int32 * n)()
+        assert lib.drt_debug_candidate_order(arr, n, out, n) == n
+        assert list(out) == Oracle(scene).candidate_order(), case

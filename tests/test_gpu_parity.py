@@ -210,3 +210,58 @@ def test_production_spp_mae_against_high_spp_reference(oracle_lib):
         if single:
             assert ours_single <= 0.5, (case, ours_single)
         assert ours_single <= 1.2 * ref_self + 0.05, (case, ours_single, ref_self)
+
+
+@pytest.mark.parametrize("variant", ["one_pixel", "edge_tile", "depth1", "noreflect", "nogloss", "no_lights", "aa2", "blur_ref_mode"])
+def test_cuda_edge_cases_match_oracle(oracle_lib, variant):
+    """Edge cases of the settings surface: degenerate tiles, depth / switch extremes, spp that is not
+    a square, a light-less scene, and the reference's own motion-blur mode with moving "rectangle"
+    shapes after frame_prism (bumpBVH path, render_final_project.cpp:1095-1210)."""
+    from distraytracer_b200 import abi
+    from distraytracer_b200.scene import Scene
+    from oracle.harness import Oracle, ORACLE_KEYED, compare
+    scene, settings, _ = load_case("boundary_mocap" if variant == "blur_ref_mode" else "checkertexture")
+    s = abi.copy_struct(settings)
+    s.xRes, s.yRes = 96, 72
+    tile = None
+    if variant == "one_pixel":
+        tile = abi.Tile(47, 30, 1, 1, 0)
+    elif variant == "edge_tile":
+        tile = abi.Tile(90, 66, 6, 6, 0)          # top-right corner of the frame in loop coordinates
+    elif variant == "depth1":
+        s.max_depth = 1
+    elif variant == "noreflect":
+        s.reflect = 0
+    elif variant == "nogloss":
+        s.nogloss = 1
+    elif variant == "no_lights":
+        scene = Scene(scene.prims, [], scene.textures)
+    elif variant == "aa2":
+        s.antialias_samples, s.aperture = 2, 0.2   # n = int(sqrt(2)) = 1 -> 1 spp
+    elif variant == "blur_ref_mode":
+        # frame >= frame_prism: shapes named "rectangle" move in y for the blur re-traces; flag them
+        prims = [abi.copy_struct(p) for p in scene.prims]
+        for p in prims:
+            if p.name == abi.NAME_RECTANGLE:
+                p.flags |= abi.FLAG_MOTION
+        scene = Scene(prims, scene.lights, scene.textures)
+        s.frame, s.frame_prism, s.frame_blur, s.frame_range, s.blur_samples = 1700, 960, 1600, 8, 2
+        s.antialias_samples = 4
+    want, _, _, _ = Oracle(scene).render(s, tile, mode=ORACLE_KEYED)
+    got, _ = _gpu(scene).render_float(s, tile)
+    st = compare(want, got)
+    assert st["frac_within_1"] >= TOL_FRAC, (variant, st)
+
+
+def test_video_frames_through_scene_update(oracle_lib):
+    """BASELINE config 4 mechanics: one resident scene, per frame only the bone cylinders are re-posed
+    (drt_scene_update_prims) -- must equal building the scene from scratch for that frame."""
+    from distraytracer_b200 import scenes
+    scene0, s0 = scenes.config4_frame(10, 160, 90, 4)
+    dev = _gpu(scene0)
+    for f in (11, 57, 119):
+        scene_f, s_f = scenes.config4_frame(f, 160, 90, 4)
+        dev.update_prims(scene_f.prims)
+        a = dev.render(s_f)
+        b = _gpu(scene_f).render(s_f)
+        assert np.array_equal(a, b), f
