@@ -235,12 +235,28 @@ int flatten(const drt_prim* prims, int n_prims, const drt_light* lights, int n_l
     if (rn.leaf) { nd.first = geom_start[rn.first]; nd.count = geom_start[rn.first + rn.count] - nd.first; }
     hs.nodes.push_back(nd);
   }
+  // slab-filter table (drt_kernels.cuh: slabMask): centre / half-extent of the padded fp32 boxes, two geoms per
+  // record of three float4 {cx0 cx1 cy0 cy1} {cz0 cz1 hx0 hx1} {hy0 hy1 hz0 hz1}; holes and the odd-count padding
+  // entry get a negative half-extent so that they never pass
   hs.gbounds.clear();
-  for (const Geom<R>& g : hs.geoms) {
-    float4 lo = g.blo, hi = g.bhi;
-    const int meta = (g.type & 0xff) | (g.owner << 8);
-    memcpy(&lo.w, &meta, sizeof(int));
-    hs.gbounds.push_back(lo); hs.gbounds.push_back(hi);
+  for (size_t p = 0; p < (hs.geoms.size() + 1) / 2; p++) {
+    float c[2][3], h[2][3];
+    for (int k = 0; k < 2; k++) {
+      const size_t gi = 2 * p + k;
+      const bool live = gi < hs.geoms.size() && hs.geoms[gi].type != G_HOLE;
+      for (int a = 0; a < 3; a++) {
+        if (!live) { c[k][a] = 0.f; h[k][a] = -1e30f; continue; }
+        const float lo = (&hs.geoms[gi].blo.x)[a], hi = (&hs.geoms[gi].bhi.x)[a];
+        const float cf = (float)(0.5 * ((double)lo + (double)hi));
+        const double hd = std::max((double)hi - (double)cf, (double)cf - (double)lo);
+        float hf = (float)hd;
+        if ((double)hf < hd) hf = nextafterf(hf, INFINITY);
+        c[k][a] = cf; h[k][a] = nextafterf(hf, INFINITY);              // [c - h, c + h] contains [lo, hi]
+      }
+    }
+    hs.gbounds.push_back(make_float4(c[0][0], c[1][0], c[0][1], c[1][1]));
+    hs.gbounds.push_back(make_float4(c[0][2], c[1][2], h[0][0], h[1][0]));
+    hs.gbounds.push_back(make_float4(h[0][1], h[1][1], h[0][2], h[1][2]));
   }
   for (size_t k = 0; k < hs.nodes.size(); k++) {
     NodeD<R>& nd = hs.nodes[k];
@@ -287,7 +303,7 @@ int upload(const HostScene<R>& hs, DevScene<R>& ds) {
   }
   if ((int)hs.geoms.size() != ds.n_geoms || !ds.gbounds) {
     if (ds.gbounds) cudaFree(ds.gbounds);
-    CK(cudaMalloc(&ds.gbounds, sizeof(float4) * std::max<size_t>(2, hs.gbounds.size())));
+    CK(cudaMalloc(&ds.gbounds, sizeof(float4) * std::max<size_t>(3, hs.gbounds.size())));
   }
   if (!hs.gbounds.empty()) CK(cudaMemcpy(ds.gbounds, hs.gbounds.data(), sizeof(float4) * hs.gbounds.size(), cudaMemcpyHostToDevice));
   if ((int)hs.prims.size() != ds.n_prims || !ds.prims) {

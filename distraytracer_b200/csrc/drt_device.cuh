@@ -178,7 +178,7 @@ struct Params {
   int x0, y0, w, h;
   // scene
   const Geom<R>* geoms; int n_geoms;
-  const float4* gbounds;    // 2 per geom: (lo.xyz, meta) (hi.xyz, -) for the slab filter; meta = type | owner << 8
+  const float4* gbounds;    // slab-filter table: 3 float4 per PAIR of geoms (centre / half-extent, see slabMask)
   const NodeD<R>* nodes; int n_nodes;
   const PrimD<R>* prims;
   const LightD<R>* lights; int n_lights;

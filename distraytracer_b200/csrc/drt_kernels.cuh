@@ -217,6 +217,72 @@ __device__ inline bool slabMayHit(const float4 blo, const float4 bhi, const floa
   return !(tn > tf * 1.0001f + 1e-4f + err) && !(tf < -err) && !(tn > t_limit + err);
 }
 
+// ---- packed slab filter over the whole scene -------------------------------------------------
+// The per-scene filter table holds the padded boxes as CENTRE / HALF-EXTENT, two geoms per
+// record of three float4:  {cx0 cx1 cy0 cy1} {cz0 cz1 hx0 hx1} {hy0 hy1 hz0 hz1}.
+// Per axis  t_near = (c*i - o*i) - h*|i|,  t_far = (c*i - o*i) + h*|i|  are three fused
+// multiply-adds, and sm_100's packed FFMA2 (fma.rn.f32x2) evaluates them for both geoms of the
+// record at once: 9 FFMA2 + 4 FMNMX3 per PAIR instead of 12 FFMA + 12 FMNMX + 4 FMNMX3.
+// Holes and the padding entry of an odd count carry h = -1e30 and never pass.
+struct SlabRay {
+  float2 i[3], no[3], ai[3], nai[3];   // 1/d, -o/d, |1/d|, -|1/d|, each duplicated into both halves
+  float2 grow, slack;                  // t_far * 1.0001 + (1e-4 + err)
+  float floor_t, lim;                  // t_far >= -err  and  t_near <= t_limit + err, folded into one compare
+};
+__device__ __forceinline__ SlabRay slabRay(const float ix, const float iy, const float iz, const float nox, const float noy,
+                                           const float noz, const float t_limit) {
+  SlabRay r;
+  const float err = 4e-7f * (fabsf(nox) + fabsf(noy) + fabsf(noz));   // cancellation error of c*i - o*i
+  r.i[0] = make_float2(ix, ix); r.i[1] = make_float2(iy, iy); r.i[2] = make_float2(iz, iz);
+  r.no[0] = make_float2(nox, nox); r.no[1] = make_float2(noy, noy); r.no[2] = make_float2(noz, noz);
+  const float ax = fabsf(ix), ay = fabsf(iy), az = fabsf(iz);
+  r.ai[0] = make_float2(ax, ax); r.ai[1] = make_float2(ay, ay); r.ai[2] = make_float2(az, az);
+  r.nai[0] = make_float2(-ax, -ax); r.nai[1] = make_float2(-ay, -ay); r.nai[2] = make_float2(-az, -az);
+  const float c = 1e-4f + err;
+  r.grow = make_float2(1.0001f, 1.0001f); r.slack = make_float2(c, c);
+  r.floor_t = fmaf(-1.0002f, err, c);   // t_far' >= floor_t  <=>  t_far >= -err (a hair looser)
+  r.lim = t_limit + err;
+  return r;
+}
+__device__ __forceinline__ unsigned int slabAll(const int g0, const int g1) {   // every geom of the group [g0, g1)
+  return (g1 - g0 >= 32) ? 0xffffffffu : ((1u << (g1 - g0)) - 1u);
+}
+template <bool SMEM>
+__device__ __forceinline__ float4 slabLoad(const float4* p) {
+  if (SMEM) {
+    float4 v;
+    // volatile: must not be speculated above the `smem` test (the pointer is a global address otherwise)
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"((unsigned)__cvta_generic_to_shared(p)));
+    return v;
+  }
+  return __ldg(p);
+}
+// Bit k of the result: geom g0 + k may be hit.  inf/NaN terms (axis-parallel rays) drop out of
+// the min/max chains or make the final compare false, i.e. never reject.
+template <bool SMEM>
+__device__ __forceinline__ unsigned int slabMask(const float4* __restrict__ tab, const int g0, const int g1, const SlabRay& r) {
+  unsigned int mask = 0;
+  const int p0 = g0 >> 1, p1 = (g1 + 1) >> 1;
+#pragma unroll 4
+  for (int p = p0; p < p1; p++) {
+    const float4 A = slabLoad<SMEM>(tab + 3 * p), B = slabLoad<SMEM>(tab + 3 * p + 1), C = slabLoad<SMEM>(tab + 3 * p + 2);
+    const float2 mx = __ffma2_rn(make_float2(A.x, A.y), r.i[0], r.no[0]);
+    const float2 my = __ffma2_rn(make_float2(A.z, A.w), r.i[1], r.no[1]);
+    const float2 mz = __ffma2_rn(make_float2(B.x, B.y), r.i[2], r.no[2]);
+    const float2 hx = make_float2(B.z, B.w), hy = make_float2(C.x, C.y), hz = make_float2(C.z, C.w);
+    const float2 nx = __ffma2_rn(hx, r.nai[0], mx), fx = __ffma2_rn(hx, r.ai[0], mx);
+    const float2 ny = __ffma2_rn(hy, r.nai[1], my), fy = __ffma2_rn(hy, r.ai[1], my);
+    const float2 nz = __ffma2_rn(hz, r.nai[2], mz), fz = __ffma2_rn(hz, r.ai[2], mz);
+    const float tn0 = fmaxf(fmaxf(nx.x, ny.x), nz.x), tn1 = fmaxf(fmaxf(nx.y, ny.y), nz.y);
+    const float2 tf = __ffma2_rn(make_float2(fminf(fminf(fx.x, fy.x), fz.x), fminf(fminf(fx.y, fy.y), fz.y)), r.grow, r.slack);
+    const bool ok0 = !(fmaxf(tn0, r.floor_t) > fminf(tf.x, r.lim));
+    const bool ok1 = !(fmaxf(tn1, r.floor_t) > fminf(tf.y, r.lim));
+    mask |= ((ok0 ? 1u : 0u) | (ok1 ? 2u : 0u)) << (2 * (p - p0));
+  }
+  // a ray with an infinite error bound (exactly axis-parallel) passes everything, the padding entry included
+  return mask & slabAll(g0, g1);
+}
+
 // Closest hit over all flattened primitives (the candidate loop of rayColor,
 // render_final_project.cpp:522-538, with each class's intersect()).
 //
@@ -240,24 +306,20 @@ __device__ inline void closestHit(const Params<R>& P, const float4* __restrict__
     const float ox = -(float)start.x * ix, oy = -(float)start.y * iy, oz = -(float)start.z * iz;   // slabMayHit's hoisted terms
     const float serr = 4e-7f * (fabsf(ox) + fabsf(oy) + fabsf(oz));
     const bool cull = !mv.velocity_mode;
+    const bool smem = P.n_geoms <= DRT_SMEM_GEOMS;                      // CTA-uniform: the table is staged in shared memory
+    const SlabRay sr = slabRay(ix, iy, iz, ox, oy, oz, FLT_MAX);
     const int n = P.n_geoms;
     for (int g0 = 0; g0 < n; g0 += 32) {
       const int g1 = min(n, g0 + 32);
-      unsigned int mask = 0;
-#pragma unroll 4
-      for (int gi = g0; gi < g1; gi++) {                                // branch-free: predicate -> mask bit
-        const float4 lo = gb[2 * gi], hi = gb[2 * gi + 1];
-        const int meta = __float_as_int(lo.w);
-        const bool ok = ((meta & 0xff) != G_HOLE) && (!cull || slabMayHit(lo, hi, ox, oy, oz, ix, iy, iz, FLT_MAX, serr));
-        mask |= (ok ? 1u : 0u) << (gi - g0);
-      }
+      unsigned int mask = !cull ? slabAll(g0, g1) : smem ? slabMask<true>(gb, g0, g1, sr) : slabMask<false>(gb, g0, g1, sr);
       while (mask) {
         const int gi = g0 + __ffs(mask) - 1;      // ascending = the reference's candidate order
         mask &= mask - 1;
         const Geom<R>& g = P.geoms[gi];
+        const int type = g.type;
+        if (type == G_HOLE) continue;
         // a box whose entry lies beyond the best hit cannot hold a closer (or tying) one
         if (cull && h.t < FLT_MAX && !slabMayHit(g.blo, g.bhi, ox, oy, oz, ix, iy, iz, h.t * 1.0001f + 1e-4f, serr)) continue;
-        const int type = g.type;
         if (COUNT) cnt.geom_tests[type]++;
         float t_hit; int inside, sel;
         if (geomIntersect<R>(P, g, gi, type, mv, ray, start, t_hit, inside, sel) && t_hit < h.t) {
@@ -382,29 +444,22 @@ __device__ inline bool anyHit(const Params<R>& P, const float4* __restrict__ gb,
   if (mv.val == 0.0f && !DRT_FORCE_TREE) {
     const float ix = 1.0f / (float)ray.x, iy = 1.0f / (float)ray.y, iz = 1.0f / (float)ray.z;
     const float ox = -(float)start.x * ix, oy = -(float)start.y * iy, oz = -(float)start.z * iz;   // slabMayHit's hoisted terms
-    const float serr = 4e-7f * (fabsf(ox) + fabsf(oy) + fabsf(oz));
     const bool cull = !mv.velocity_mode;
     // distance by which the reference's gather origin runs ahead of the test origin
     const float gather_lead = t_max * 1e-3f;
     const int n = P.n_geoms;
+    const bool smem = n <= DRT_SMEM_GEOMS;
+    const SlabRay sr = slabRay(ix, iy, iz, ox, oy, oz, t_max * 1.0001f + 1e-4f);
     for (int g0 = 0; g0 < n; g0 += 32) {
       const int g1 = min(n, g0 + 32);
-      unsigned int mask = 0;
-      const float t_lim = t_max * 1.0001f + 1e-4f;
-#pragma unroll 4
-      for (int gi = g0; gi < g1; gi++) {           // lock-step, branch-free slab filter -> per-lane candidate mask
-        const float4 lo = gb[2 * gi], hi = gb[2 * gi + 1];
-        const int meta = __float_as_int(lo.w);
-        // an area light never shadows itself (832-837)
-        const bool ok = ((meta & 0xff) != G_HOLE) && ((meta >> 8) != skip_owner) &&
-                        (!cull || slabMayHit(lo, hi, ox, oy, oz, ix, iy, iz, t_lim, serr));
-        mask |= (ok ? 1u : 0u) << (gi - g0);
-      }
+      // lock-step, branch-free slab filter -> per-lane candidate mask
+      unsigned int mask = !cull ? slabAll(g0, g1) : smem ? slabMask<true>(gb, g0, g1, sr) : slabMask<false>(gb, g0, g1, sr);
       while (mask) {                                // each lane walks its own candidates
         const int gi = g0 + __ffs(mask) - 1;
         mask &= mask - 1;
         const Geom<R>& g = P.geoms[gi];
         const int type = g.type;
+        if (type == G_HOLE || g.owner == skip_owner) continue;   // an area light never shadows itself (832-837)
         if (COUNT) cnt.geom_tests[type]++;
         float t_occ;
         if (!geomShadow<R>(P, g, gi, type, mv, ray, start, t_max, t_occ)) continue;
@@ -1091,7 +1146,12 @@ __device__ __noinline__ void primaryRay(const Params<R>& P, long long gidx, Vec<
 #define DRT_WAVE_WARPS 12
 #endif
 #define DRT_CTA_SLOTS (DRT_WAVE_WARPS * DRT_BATCH)   // camera samples per CTA batch
+#ifndef DRT_CTA_POOL
 #define DRT_CTA_POOL (DRT_WAVE_WARPS * 4096)         // pending rays
+#endif
+#ifndef DRT_WAVE_CTAS_PER_SM
+#define DRT_WAVE_CTAS_PER_SM 1
+#endif
 // TRACE stops feeding the hit buffer at this many hits: larger = fewer phase switches and fuller
 // SHADE passes, smaller = shallower LIFO pool.
 #ifndef DRT_TRACE_HITS_TARGET
@@ -1117,20 +1177,18 @@ __host__ __device__ constexpr size_t waveScratchBytes() {
 // all warps stay busy and a phase ends within one 32-item chunk of the last warp (with
 // warp-private pools 27 % of the stall samples were barrier waits).
 template <typename R, bool COUNT>
-__global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, 1) render_wave(const __grid_constant__ Params<R> P) {
+__global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) render_wave(const __grid_constant__ Params<R> P) {
   __shared__ unsigned long long s_acc[DRT_CTA_SLOTS][3];
   __shared__ unsigned int s_flags[DRT_CTA_SLOTS];
   __shared__ int s_count, s_nhits, s_grab, s_state, s_nvalid;
   __shared__ long long s_idx0;
-  // slab-filter table of the whole scene, staged once per persistent CTA (32 B per geom)
-  __shared__ float4 s_gb[2 * DRT_SMEM_GEOMS];
+  // slab-filter table of the whole scene, staged once per persistent CTA (48 B per pair of geoms)
+  __shared__ float4 s_gb[3 * DRT_SMEM_GEOMS / 2];
   const float4* gb = P.gbounds;
-#ifndef DRT_NO_SMEM_GB
   if (P.n_geoms <= DRT_SMEM_GEOMS) {
-    for (int i = threadIdx.x; i < 2 * P.n_geoms; i += blockDim.x) s_gb[i] = P.gbounds[i];
+    for (int i = threadIdx.x; i < 3 * ((P.n_geoms + 1) / 2); i += blockDim.x) s_gb[i] = P.gbounds[i];
     gb = s_gb;
   }
-#endif
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, tid = threadIdx.x;
   char* cbase = (char*)P.pool_raw + (size_t)blockIdx.x * waveScratchBytes<R>();
