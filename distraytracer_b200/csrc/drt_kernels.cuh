@@ -1158,6 +1158,7 @@ __device__ __noinline__ void primaryRay(const Params<R>& P, long long gidx, Vec<
 #define DRT_TRACE_HITS_TARGET DRT_CTA_SLOTS
 #endif
 #define DRT_CTA_HITS (DRT_TRACE_HITS_TARGET + 32 * DRT_WAVE_WARPS + 64)
+#define DRT_HIT_BUCKETS 64     // hits are grouped by min(geom, 63) before SHADE
 template <typename R>
 __host__ __device__ constexpr size_t waveScratchBytes() {
   return DRT_CTA_POOL * sizeof(Task<R>) + DRT_CTA_HITS * sizeof(HitTask<R>) +
@@ -1181,6 +1182,9 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
   __shared__ unsigned long long s_acc[DRT_CTA_SLOTS][3];
   __shared__ unsigned int s_flags[DRT_CTA_SLOTS];
   __shared__ int s_count, s_nhits, s_grab, s_state, s_nvalid;
+  __shared__ int s_hist[DRT_HIT_BUCKETS];                 // SHADE order: counting sort of the hit buffer by geom
+  __shared__ unsigned short s_order[DRT_CTA_HITS];
+  __shared__ unsigned char s_hkey[DRT_CTA_HITS];
   __shared__ long long s_idx0;
   // slab-filter table of the whole scene, staged once per persistent CTA (48 B per pair of geoms)
   __shared__ float4 s_gb[3 * DRT_SMEM_GEOMS / 2];
@@ -1336,10 +1340,44 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
       int hbase = 0;
       if (lane == 0 && hm) hbase = atomicAdd(&s_nhits, __popc(hm));
       hbase = __shfl_sync(FULL, hbase, 0);
-      if (hit) hits[hbase + __popc(hm & ((1u << lane) - 1u))] = H;
+      if (hit) {
+        const int at = hbase + __popc(hm & ((1u << lane) - 1u));
+        hits[at] = H;
+        s_hkey[at] = (unsigned char)min(H.geom, DRT_HIT_BUCKETS - 1);
+      }
     }
     __syncthreads();
-    if (tid == 0) { s_count = max(s_grab, 0); s_grab = s_nhits; }        // untouched rays stay at the bottom of the pool
+    const int nh = s_nhits;
+    if (tid == 0) { s_count = max(s_grab, 0); s_grab = nh; }             // untouched rays stay at the bottom of the pool
+    // ---- counting sort of the waiting hits by geom: the 32 hits a warp shades together then share
+    // the material / model / texture branches of shadeA, evalBRDF and shadeB, and their shadow rays
+    // leave from the same surface
+    for (int i = tid; i < DRT_HIT_BUCKETS; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    int rank[(DRT_CTA_HITS + 32 * DRT_WAVE_WARPS - 1) / (32 * DRT_WAVE_WARPS)];
+#pragma unroll
+    for (int k = 0; k < (DRT_CTA_HITS + 32 * DRT_WAVE_WARPS - 1) / (32 * DRT_WAVE_WARPS); k++) {
+      const int i = tid + k * 32 * DRT_WAVE_WARPS;
+      rank[k] = (i < nh) ? atomicAdd(&s_hist[s_hkey[i]], 1) : 0;
+    }
+    __syncthreads();
+    if (wib == 0) {                                                      // exclusive scan of the bucket counts
+      int run = 0;
+      for (int b0 = 0; b0 < DRT_HIT_BUCKETS; b0 += 32) {
+        const int c = s_hist[b0 + lane];
+        int incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += v; }
+        s_hist[b0 + lane] = run + incl - c;
+        run += __shfl_sync(FULL, incl, 31);
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < (DRT_CTA_HITS + 32 * DRT_WAVE_WARPS - 1) / (32 * DRT_WAVE_WARPS); k++) {
+      const int i = tid + k * 32 * DRT_WAVE_WARPS;
+      if (i < nh) s_order[s_hist[s_hkey[i]] + rank[k]] = (unsigned short)i;
+    }
     __syncthreads();
 
     // ================= SHADE: waiting hits -> radiance terms + child rays ====================
@@ -1360,7 +1398,7 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
       {
         PairIn<R> pin; pin.want = 0;
         if (active) {
-          const HitTask<R> H = hits[end - 1 - lane];
+          const HitTask<R> H = hits[s_order[end - 1 - lane]];
           HitRec h; h.t = H.t; h.geom = H.geom; h.inside = H.inside; h.checker_sel = H.checker_sel;
           slot = H.T.slot;
           shadeA<R, COUNT>(P, H.T, h, kids, nk, add, has_add, aborted, S, cnt);
