@@ -297,7 +297,11 @@ def run_ours(args):
         e2e_value = total / (e2e_ms * 1e-3) / 1e6
         # one untimed instrumented frame for the roofline accounting
         c2 = abi.Counters(); c2.collect = 1
-        dev.render_device(settings, tile, c2)
+        events_note = None
+        try:
+            dev.render_device(settings, tile, c2)
+        except Exception as e:      # the timed numbers above stand on their own; report the accounting as missing
+            c2 = abi.Counters(); events_note = f"instrumented frame failed: {e}"
         pt = list(c2.prim_tests)
         ops = (c2.node_tests * COST["node"] + pt[abi.PRIM_SPHERE] * COST["sphere"] + pt[abi.PRIM_TRIANGLE] * COST["triangle"]
                + pt[abi.PRIM_RECTANGLE] * COST["rectangle"] + pt[abi.PRIM_CYLINDER] * COST["cylinder"]
@@ -335,7 +339,7 @@ def run_ours(args):
                          "note": "kernel render_wave<double> (2 launches per step); the path is issue/latency bound in the FP64+ALU pipes, not HBM bound: see roofline_fp; traffic = ray-pool spill, 0.4 TB/s"},
             "roofline_fp": {"bound": "fp64_pipe", "achieved": ops / step_s / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
                             "frac": ops / step_s / 1e12 / fp64_peak,
-                            "note": "algorithmic ops = event counters x SURVEY.md 8(d) cost table; peak = SMs x 64 DFMA x 2 x observed SM clock",
+                            "note": events_note or "algorithmic ops = event counters x SURVEY.md 8(d) cost table; peak = SMs x 64 DFMA x 2 x observed SM clock",
                             "events": {"samples": c2.samples, "rays": c2.rays, "shadow_rays": c2.shadow_rays, "node_tests": c2.node_tests,
                                        "rect_tests": pt[abi.PRIM_RECTANGLE], "sphere_tests": pt[abi.PRIM_SPHERE],
                                        "tri_tests": pt[abi.PRIM_TRIANGLE], "cyl_tests": pt[abi.PRIM_CYLINDER], "shade_evals": c2.shade_evals}},

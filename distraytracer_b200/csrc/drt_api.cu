@@ -477,7 +477,7 @@ int ensureScratch(drt_scene* s, size_t n_samples, size_t n_corners, size_t n_out
 const long long kMaxChunkSamples = 1ll << 26;
 
 template <typename R>
-int launchAll(drt_scene* s, const DevScene<R>& ds, const drt_settings& st, const CameraD& cam, const drt_tile& tile,
+int launchAll(drt_scene* s, const DevScene<R>& ds, const drt_settings& st, const CameraD& cam, const drt_tile& tile, int pool_cap,
               bool want_f32, drt_counters* counters) {
   Params<R> P;
   fillParams<R>(P, s, ds, st, cam, tile);
@@ -491,14 +491,18 @@ int launchAll(drt_scene* s, const DevScene<R>& ds, const drt_settings& st, const
   P.counts = collect ? s->counts : nullptr;
   int& wave_blocks = sizeof(R) == 8 ? s->wave_blocks_f64 : s->wave_blocks_f32;
   if (!wave_blocks) wave_blocks = waveGridBlocks<R>();
-  const size_t pool_bytes = wavePoolBytes<R>(wave_blocks);
+  const size_t pool_bytes = wavePoolBytes<R>(wave_blocks, pool_cap);
   if (!st.cloud_only && pool_bytes > s->pool_cap) {
     if (s->pool) cudaFree(s->pool);
     s->pool = nullptr; s->pool_cap = 0;
-    CK(cudaMalloc(&s->pool, pool_bytes));
+    if (cudaMalloc(&s->pool, pool_bytes) != cudaSuccess) {
+      cudaGetLastError();
+      s->pool = nullptr;
+      return fail(DRT_ERR_CUDA, "out of device memory for the ray pools (brdf_samples * max_depth too large)");
+    }
     s->pool_cap = pool_bytes;
   }
-  P.pool_raw = s->pool; P.batch_counter = s->batch_counter; P.overflow = s->overflow;
+  P.pool_raw = s->pool; P.pool_cap = pool_cap; P.batch_counter = s->batch_counter; P.overflow = s->overflow;
   cudaStream_t q = s->stream;
   int launches = 0;
   if (collect) CK(cudaMemsetAsync(s->counts, 0, sizeof(Counts), q));
@@ -536,22 +540,26 @@ int renderCommon(const drt_scene* cs, const drt_settings* st, const drt_tile* ti
   if (st->sample_mode != DRT_SAMPLES_KEYED) return fail(DRT_ERR_UNSUPPORTED, "unknown sample_mode");
   if (st->precision != DRT_PRECISION_REFERENCE && st->precision != DRT_PRECISION_FP32) return fail(DRT_ERR_INVALID, "unknown precision");
   if (st->max_depth < 0 || st->max_depth > 32) return fail(DRT_ERR_UNSUPPORTED, "max_depth outside [0,32]");
-  {  // CTA ray-pool bound (render_wave): LIFO over trees with (lobes [+1 for glass]) children per node; one
-     // TRACE pass turns at most ~1.5 x DRT_CTA_SLOTS rays into hits, each hit spawns at most `fan` children
+  int pool_cap = 0;
+  {  // CTA ray-pool bound (render_wave): the pool is a LIFO over the trees of one batch of DRT_CTA_SLOTS samples.  A
+     // TRACE pass turns at most DRT_HITS_PER_PASS rays into hits, a hit spawns at most `fan` children (lobes [+1 for
+     // glass]), and only the rays on top are traced next, so at most per_pass x (fan - 1) rays are left behind per level.
     const int lobes = std::max(1, st->nogloss ? 1 : st->brdf_samples);
     const int fan = lobes + (s->any_glass ? 1 : 0);
-    const long long slots = 12 * 64, per_pass = slots + 32 * 12;
-    if (st->brdf_samples < 1 || fan > DRT_MAX_CHILDREN || st->blur_samples > 4 ||
-        slots * std::max(1, st->blur_samples) + per_pass * (1 + (long long)st->max_depth * (fan - 1)) > 12ll * 4096)
-      return fail(DRT_ERR_UNSUPPORTED, "brdf_samples * max_depth exceeds the per-CTA ray pool");
+    if (st->brdf_samples < 1 || fan > DRT_MAX_CHILDREN) return fail(DRT_ERR_UNSUPPORTED, "brdf_samples outside [1, 5]");
+    if (st->blur_samples < 0 || st->blur_samples > 64) return fail(DRT_ERR_UNSUPPORTED, "blur_samples outside [0, 64]");
+    const long long need = (long long)DRT_CTA_SLOTS * std::max(1, st->blur_samples) +
+                           (long long)DRT_HITS_PER_PASS * (1 + (long long)st->max_depth * (fan - 1));
+    if (need > (1ll << 22)) return fail(DRT_ERR_UNSUPPORTED, "brdf_samples * max_depth needs more than 4 M rays per CTA pool");
+    pool_cap = (int)((need + 1023) / 1024 * 1024);
   }
   CameraD cam;
   int rc = makeCamera(*st, cam);
   if (rc) return rc;
   CK(cudaSetDevice(s->device));
   const bool want_f32 = out_f32 != nullptr;
-  if (st->precision == DRT_PRECISION_FP32) rc = launchAll<float>(s, s->df, *st, cam, *tile, want_f32, counters);
-  else rc = launchAll<double>(s, s->dd, *st, cam, *tile, want_f32, counters);
+  if (st->precision == DRT_PRECISION_FP32) rc = launchAll<float>(s, s->df, *st, cam, *tile, pool_cap, want_f32, counters);
+  else rc = launchAll<double>(s, s->dd, *st, cam, *tile, pool_cap, want_f32, counters);
   if (rc) return rc;
   const size_t n_out = (size_t)tile->width * tile->height * 3;
   if (copy_back) {
@@ -561,7 +569,13 @@ int renderCommon(const drt_scene* cs, const drt_settings* st, const drt_tile* ti
   Counts hc; memset(&hc, 0, sizeof(hc));
   const bool collect = counters && counters->collect;
   if (collect) CK(cudaMemcpyAsync(&hc, s->counts, sizeof(Counts), cudaMemcpyDeviceToHost, s->stream));
+  int overflowed = 0;
+  if (!st->cloud_only) CK(cudaMemcpyAsync(&overflowed, s->overflow, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
   CK(cudaStreamSynchronize(s->stream));
+  if (overflowed) {   // the kernel dropped rays instead of writing past its pool: the frame is not valid
+    CK(cudaMemset(s->overflow, 0, sizeof(int)));
+    return fail(DRT_ERR_UNSUPPORTED, "a CTA ray pool overflowed (brdf_samples * max_depth beyond the sized bound)");
+  }
   if (counters) {
     float ms = 0; CK(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
     counters->kernel_ms = ms;

@@ -194,7 +194,8 @@ struct Params {
   Counts* counts;           // nullptr unless collecting
   long long sample_base;    // first (pixel*spp+s) index handled by this launch (row chunking)
   long long sample_count;
-  void* pool_raw;           // per-warp ray pools (Task<R>[DRT_POOL_CAP] each)
+  void* pool_raw;           // per-CTA scratch: ray pool, hit buffer, shadow-pair buffers (waveScratchBytes)
+  int pool_cap;             // ray tasks per CTA pool
   unsigned long long* batch_counter;
   int* overflow;
 };

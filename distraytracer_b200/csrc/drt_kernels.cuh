@@ -1141,27 +1141,15 @@ __device__ __noinline__ void primaryRay(const Params<R>& P, long long gidx, Vec<
 }
 
 // Scratch of one persistent CTA in global memory (L1/L2 resident):
-//   [ DRT_CTA_POOL ray tasks | DRT_CTA_HITS hit tasks | per warp: 32 pair inputs + 32 x DRT_PAIR_LIGHTS pair results ]
-#ifndef DRT_WAVE_WARPS
-#define DRT_WAVE_WARPS 12
-#endif
-#define DRT_CTA_SLOTS (DRT_WAVE_WARPS * DRT_BATCH)   // camera samples per CTA batch
-#ifndef DRT_CTA_POOL
-#define DRT_CTA_POOL (DRT_WAVE_WARPS * 4096)         // pending rays
-#endif
+//   [ pool_cap ray tasks | DRT_CTA_HITS hit tasks | per warp: 32 pair inputs + 32 x DRT_PAIR_LIGHTS pair results ]
+// pool_cap (Params::pool_cap) is sized per render on the host from brdf_samples / max_depth / blur_samples.
 #ifndef DRT_WAVE_CTAS_PER_SM
 #define DRT_WAVE_CTAS_PER_SM 1
 #endif
-// TRACE stops feeding the hit buffer at this many hits: larger = fewer phase switches and fuller
-// SHADE passes, smaller = shallower LIFO pool.
-#ifndef DRT_TRACE_HITS_TARGET
-#define DRT_TRACE_HITS_TARGET DRT_CTA_SLOTS
-#endif
-#define DRT_CTA_HITS (DRT_TRACE_HITS_TARGET + 32 * DRT_WAVE_WARPS + 64)
 #define DRT_HIT_BUCKETS 64     // hits are grouped by min(geom, 63) before SHADE
 template <typename R>
-__host__ __device__ constexpr size_t waveScratchBytes() {
-  return DRT_CTA_POOL * sizeof(Task<R>) + DRT_CTA_HITS * sizeof(HitTask<R>) +
+__host__ __device__ constexpr size_t waveScratchBytes(int pool_cap) {
+  return (size_t)pool_cap * sizeof(Task<R>) + DRT_CTA_HITS * sizeof(HitTask<R>) +
          DRT_WAVE_WARPS * (32 * sizeof(PairIn<R>) + 32 * DRT_PAIR_LIGHTS * sizeof(PairOut<R>));
 }
 
@@ -1195,9 +1183,9 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
   }
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, tid = threadIdx.x;
-  char* cbase = (char*)P.pool_raw + (size_t)blockIdx.x * waveScratchBytes<R>();
+  char* cbase = (char*)P.pool_raw + (size_t)blockIdx.x * waveScratchBytes<R>(P.pool_cap);
   Task<R>* pool = (Task<R>*)cbase;
-  HitTask<R>* hits = (HitTask<R>*)(cbase + DRT_CTA_POOL * sizeof(Task<R>));
+  HitTask<R>* hits = (HitTask<R>*)(cbase + (size_t)P.pool_cap * sizeof(Task<R>));
   char* wbase = (char*)(hits + DRT_CTA_HITS) + (size_t)wib * (32 * sizeof(PairIn<R>) + 32 * DRT_PAIR_LIGHTS * sizeof(PairOut<R>));
   PairIn<R>* pairin = (PairIn<R>*)wbase;
   PairOut<R>* pairout = (PairOut<R>*)(pairin + 32);
@@ -1411,7 +1399,7 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
       for (int l0 = 0; l0 < P.n_lights; l0 += DRT_PAIR_LIGHTS) {
         const int nl = min(DRT_PAIR_LIGHTS, P.n_lights - l0);
         for (int pid = lane; pid < take * nl; pid += 32) {
-          const int hh = pid / nl, lj = pid - hh * nl;
+          const int lj = pid / take, hh = pid - lj * take;              // light-major: one pass of the warp heads for one light
           const PairIn<R> pin = pairin[hh];
           if (pin.want) shadowPair<R, COUNT>(P, gb, pin, l0 + lj, pairout[hh * DRT_PAIR_LIGHTS + lj], cnt);
         }
@@ -1438,20 +1426,26 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
           if (orf) atomicOr(&sfl[slot], orf);
         }
       }
-      // compact the children onto the top of the CTA pool (warp inclusive scan of nk)
-      int incl = nk;
+      // compact the children onto the top of the CTA pool, child-index-major: the j-th children of the
+      // warp's 32 (geom-sorted) hits -- the same kind of ray leaving the same surface -- end up adjacent,
+      // so a later TRACE warp works on rays with similar candidates
+      unsigned int kb[DRT_MAX_CHILDREN];
+      int total = 0;
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += v; }
-      const int total = __shfl_sync(FULL, incl, 31);
+      for (int j = 0; j < DRT_MAX_CHILDREN; j++) { kb[j] = __ballot_sync(FULL, nk > j); total += __popc(kb[j]); }
       int pbase = 0;
-      if (lane == 31 && total) pbase = atomicAdd(&s_count, total);
-      pbase = __shfl_sync(FULL, pbase, 31);
-      if (pbase + total > DRT_CTA_POOL) {                               // cannot happen within the validated bounds
+      if (lane == 0 && total) pbase = atomicAdd(&s_count, total);
+      pbase = __shfl_sync(FULL, pbase, 0);
+      if (pbase + total > P.pool_cap) {                               // cannot happen within the validated bounds
         if (nk) atomicOr(&sfl[kids[0].slot], SF_ABORT);
         if (lane == 0) { *P.overflow = 1; atomicSub(&s_count, total); }
       } else {
-        const int base = pbase + incl - nk;
-        for (int j = 0; j < nk; j++) pool[base + j] = kids[j];
+        int base = pbase;
+#pragma unroll
+        for (int j = 0; j < DRT_MAX_CHILDREN; j++) {
+          if (nk > j) pool[base + __popc(kb[j] & ((1u << lane) - 1u))] = kids[j];
+          base += __popc(kb[j]);
+        }
       }
     }
     __syncthreads();

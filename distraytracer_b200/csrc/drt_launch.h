@@ -10,10 +10,21 @@
 #pragma once
 #include "drt_device.cuh"
 
-#ifndef DRT_BATCH
-#define DRT_BATCH 64          // camera samples per warp batch (render_wave)
+// ---- shape of one persistent render_wave CTA (shared by the kernels and the host-side pool sizing)
+#ifndef DRT_WAVE_WARPS
+#define DRT_WAVE_WARPS 12
 #endif
-#define DRT_POOL_CAP 2048     // ray-pool records per warp
+#ifndef DRT_BATCH
+#define DRT_BATCH 64          // camera samples per warp in a CTA batch
+#endif
+#define DRT_CTA_SLOTS (DRT_WAVE_WARPS * DRT_BATCH)   // camera samples per CTA batch
+// TRACE stops feeding the hit buffer at this many hits.  Larger = fewer phase switches, more 32-hit bites
+// per warp and pass (shorter barrier tails) and bigger geom buckets in the SHADE sort; costs a deeper ray pool.
+#ifndef DRT_TRACE_HITS_TARGET
+#define DRT_TRACE_HITS_TARGET 3072
+#endif
+#define DRT_HITS_PER_PASS (DRT_TRACE_HITS_TARGET + 32 * DRT_WAVE_WARPS)   // a TRACE pass can overshoot by one bite per warp
+#define DRT_CTA_HITS (DRT_HITS_PER_PASS + 64)
 #define DRT_MAX_CHILDREN 6    // refraction + max(brdf_samples, 1)
 #define DRT_PAIR_LIGHTS 8      // lights whose shadow rays are spread over the warp per pass
 #define DRT_SMEM_GEOMS 256     // slab-filter entries staged in shared memory per CTA
@@ -21,8 +32,8 @@
 namespace drt {
 // persistent grid of render_wave: blocks that are co-resident on the current device
 template <typename R> int waveGridBlocks();
-// bytes of per-warp ray pools a grid of `blocks` needs (Params::pool_raw)
-template <typename R> size_t wavePoolBytes(int blocks);
+// bytes of scratch (ray pools of `pool_cap` tasks, hit buffers, shadow-pair buffers) a grid of `blocks` CTAs needs
+template <typename R> size_t wavePoolBytes(int blocks, int pool_cap);
 template <typename R> void launchRenderSamples(const Params<R>& P, bool collect, int blocks, cudaStream_t q);
 template <typename R> void launchCloudCorners(const Params<R>& P, cudaStream_t q);
 template <typename R> void launchResolve(const Params<R>& P, int row0, int rows, cudaStream_t q);

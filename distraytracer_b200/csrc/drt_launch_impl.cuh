@@ -11,7 +11,7 @@ template <> int waveGridBlocks<DRT_REAL>() {
   if (per_sm < 1) per_sm = 1;
   return sms * per_sm;   // a whole multiple of the SM count: every SM holds the same number of persistent CTAs
 }
-template <> size_t wavePoolBytes<DRT_REAL>(int blocks) { return (size_t)blocks * waveScratchBytes<DRT_REAL>(); }
+template <> size_t wavePoolBytes<DRT_REAL>(int blocks, int pool_cap) { return (size_t)blocks * waveScratchBytes<DRT_REAL>(pool_cap); }
 template <> void launchRenderSamples<DRT_REAL>(const Params<DRT_REAL>& P, bool collect, int blocks, cudaStream_t q) {
   if (collect) render_wave<DRT_REAL, true><<<blocks, 32 * DRT_WAVE_WARPS, 0, q>>>(P);
   else render_wave<DRT_REAL, false><<<blocks, 32 * DRT_WAVE_WARPS, 0, q>>>(P);
