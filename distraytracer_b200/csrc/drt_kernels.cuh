@@ -1147,6 +1147,7 @@ __device__ __noinline__ void primaryRay(const Params<R>& P, long long gidx, Vec<
 #define DRT_WAVE_CTAS_PER_SM 1
 #endif
 #define DRT_HIT_BUCKETS 64     // hits are grouped by min(geom, 63) before SHADE
+__host__ __device__ constexpr size_t waveDynSmemBytes() { return (size_t)DRT_CTA_SLOTS * 28 + (size_t)DRT_CTA_HITS * 3; }
 template <typename R>
 __host__ __device__ constexpr size_t waveScratchBytes(int pool_cap) {
   return (size_t)pool_cap * sizeof(Task<R>) + DRT_CTA_HITS * sizeof(HitTask<R>) +
@@ -1167,12 +1168,14 @@ __host__ __device__ constexpr size_t waveScratchBytes(int pool_cap) {
 // warp-private pools 27 % of the stall samples were barrier waits).
 template <typename R, bool COUNT>
 __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) render_wave(const __grid_constant__ Params<R> P) {
-  __shared__ unsigned long long s_acc[DRT_CTA_SLOTS][3];
-  __shared__ unsigned int s_flags[DRT_CTA_SLOTS];
+  // dynamic shared memory (waveDynSmemBytes): [ acc: slots x 3 x u64 | flags: slots x u32 | order: hits x u16 | hkey: hits x u8 ]
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  unsigned long long(*s_acc)[3] = (unsigned long long(*)[3])s_dyn;
+  unsigned int* s_flags = (unsigned int*)(s_dyn + (size_t)DRT_CTA_SLOTS * 24);
+  unsigned short* s_order = (unsigned short*)(s_dyn + (size_t)DRT_CTA_SLOTS * 28);
+  unsigned char* s_hkey = s_dyn + (size_t)DRT_CTA_SLOTS * 28 + (size_t)DRT_CTA_HITS * 2;
   __shared__ int s_count, s_nhits, s_grab, s_state, s_nvalid;
   __shared__ int s_hist[DRT_HIT_BUCKETS];                 // SHADE order: counting sort of the hit buffer by geom
-  __shared__ unsigned short s_order[DRT_CTA_HITS];
-  __shared__ unsigned char s_hkey[DRT_CTA_HITS];
   __shared__ long long s_idx0;
   // slab-filter table of the whole scene, staged once per persistent CTA (48 B per pair of geoms)
   __shared__ float4 s_gb[3 * DRT_SMEM_GEOMS / 2];
