@@ -318,10 +318,12 @@ def run_ours(args):
         # algorithmic bytes per frame: 16 B sample record written by render_samples and read once by
         # resolve, plus the 3 B/pixel frame (the scene itself lives in L1/L2)
         alg_bytes = samples_per_step * 32 + frame_bytes
-        # dram__bytes_read.sum + dram__bytes_write.sum of the two render_wave launches of one step, from the ncu
-        # capture of this same command (profiles/r1_dram_icc_bench_cta_pools.csv): 5.15+114.12 GB and 0.29+23.99 GB.
-        # The excess over the algorithmic bytes is the LIFO ray pool (80 B per pushed ray, written through to HBM).
-        measured_traffic = 5152876288 + 114119239424 + 288642816 + 23992949504
+        # dram__bytes_read.sum + dram__bytes_write.sum of the two render_wave launches of one step, from the ncu launch
+        # list of this same command (profiles/r1_launches_dram_bench_sorted_ffma2.csv): 78.66+132.52 GB and 1.73+27.79 GB.
+        # The excess over the algorithmic bytes is the CTA ray pools and hit buffers (80 B per pushed ray, 96 B per hit,
+        # each written once and read once): with 6144-hit passes the 148 CTAs' working set (~270 MB) exceeds the L2.
+        wave_launches_per_step = 2
+        measured_traffic = (78658798592 + 132524755456 + 1726821632 + 27787432192) // wave_launches_per_step
         fp64_peak = props.multi_processor_count * 64 * 2 * sm_mhz * 1e6 / 1e12     # TFLOP/s at the observed clock
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -336,7 +338,8 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": alg_bytes / step_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                          "frac": alg_bytes / step_s / 1e9 / hbm_peak, "traffic": measured_traffic,
                          "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
-                         "note": "kernel render_wave<double> (2 launches per step); the path is issue/latency bound in the FP64+ALU pipes, not HBM bound: see roofline_fp; traffic = ray-pool spill, 0.4 TB/s"},
+                         "launches_per_step": wave_launches_per_step,
+                         "note": "kernel render_wave<double>, 2 launches per step (row chunks of <= 2^26 samples): achieved = algorithmic bytes of a step / device time of a step (= per-launch bytes / mean launch time), traffic = mean DRAM bytes per launch (ncu). The path is issue/latency bound in the FP64+ALU pipes, not HBM bound: see roofline_fp; traffic = ray-pool and hit-buffer spill, 0.9 TB/s"},
             "roofline_fp": {"bound": "fp64_pipe", "achieved": ops / step_s / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
                             "frac": ops / step_s / 1e12 / fp64_peak,
                             "note": events_note or "algorithmic ops = event counters x SURVEY.md 8(d) cost table; peak = SMs x 64 DFMA x 2 x observed SM clock",
