@@ -258,6 +258,27 @@ int flatten(const drt_prim* prims, int n_prims, const drt_light* lights, int n_l
     hs.gbounds.push_back(make_float4(c[0][2], c[1][2], h[0][0], h[1][0]));
     hs.gbounds.push_back(make_float4(h[0][1], h[1][1], h[0][2], h[1][2]));
   }
+  // ... followed by one box per group of 8 consecutive geoms: {cx cy cz hx} {hy hz - -}
+  for (size_t g0 = 0; g0 < hs.geoms.size(); g0 += 8) {
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    bool any = false;
+    for (size_t gi = g0; gi < std::min(hs.geoms.size(), g0 + 8); gi++) {
+      if (hs.geoms[gi].type == G_HOLE) continue;
+      any = true;
+      for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], (&hs.geoms[gi].blo.x)[a]); hi[a] = std::max(hi[a], (&hs.geoms[gi].bhi.x)[a]); }
+    }
+    float c[3], h[3];
+    for (int a = 0; a < 3; a++) {
+      if (!any) { c[a] = 0.f; h[a] = -1e30f; continue; }
+      c[a] = (float)(0.5 * ((double)lo[a] + (double)hi[a]));
+      const double hd = std::max((double)hi[a] - (double)c[a], (double)c[a] - (double)lo[a]);
+      float hf = (float)hd;
+      if ((double)hf < hd) hf = nextafterf(hf, INFINITY);
+      h[a] = nextafterf(nextafterf(hf, INFINITY), INFINITY) * 1.000001f;   // also covers the members' own rounded-up half-extents
+    }
+    hs.gbounds.push_back(make_float4(c[0], c[1], c[2], h[0]));
+    hs.gbounds.push_back(make_float4(h[1], h[2], 0.f, 0.f));
+  }
   for (size_t k = 0; k < hs.nodes.size(); k++) {
     NodeD<R>& nd = hs.nodes[k];
     if (nd.leaf) { for (int gi = nd.first; gi < nd.first + nd.count; gi++) hs.geoms[gi].leaf = (int)k; }

@@ -259,12 +259,38 @@ __device__ __forceinline__ float4 slabLoad(const float4* p) {
 }
 // Bit k of the result: geom g0 + k may be hit.  inf/NaN terms (axis-parallel rays) drop out of
 // the min/max chains or make the final compare false, i.e. never reject.
+// Two-level form: the table also holds one box per GROUP of 8 consecutive geoms (4 pair records; consecutive geoms are
+// neighbours in the reference's BVH order, and a prism's 6 faces are consecutive).  A lane runs a group's records only
+// if its ray may hit the group box -- the branch is per lane, so the warp skips the block when no lane needs it, which
+// is the common case now that a warp's rays leave from one surface (geom-sorted SHADE, child-index-major pushes).
+#ifndef DRT_GROUP_SKIP
+#define DRT_GROUP_SKIP 1
+#endif
+__device__ __forceinline__ bool slabGroupMayHit(const float4 G0, const float4 G1, const SlabRay& r) {
+  const float mx = fmaf(G0.x, r.i[0].x, r.no[0].x), my = fmaf(G0.y, r.i[1].x, r.no[1].x), mz = fmaf(G0.z, r.i[2].x, r.no[2].x);
+  const float tn = fmaxf(fmaxf(fmaf(G0.w, r.nai[0].x, mx), fmaf(G1.x, r.nai[1].x, my)), fmaf(G1.y, r.nai[2].x, mz));
+  const float tf = fminf(fminf(fmaf(G0.w, r.ai[0].x, mx), fmaf(G1.x, r.ai[1].x, my)), fmaf(G1.y, r.ai[2].x, mz));
+  return !(fmaxf(tn, r.floor_t) > fminf(fmaf(tf, r.grow.x, r.slack.x), r.lim));
+}
 template <bool SMEM>
-__device__ __forceinline__ unsigned int slabMask(const float4* __restrict__ tab, const int g0, const int g1, const SlabRay& r) {
+__device__ __forceinline__ unsigned int slabMask(const float4* __restrict__ tab, const int n_geoms, const int g0, const int g1,
+                                                 const SlabRay& r) {
   unsigned int mask = 0;
+#if DRT_GROUP_SKIP
+  const float4* gtab = tab + 3 * ((n_geoms + 1) >> 1);            // group boxes follow the pair records
+  for (int q0 = g0; q0 < g1; q0 += 8) {
+    const float4 G0 = slabLoad<SMEM>(gtab + 2 * (q0 >> 3)), G1 = slabLoad<SMEM>(gtab + 2 * (q0 >> 3) + 1);
+    if (!slabGroupMayHit(G0, G1, r)) continue;
+    const int p0 = q0 >> 1, p1 = (min(q0 + 8, g1) + 1) >> 1;
+    unsigned int sub = 0;
+#pragma unroll
+    for (int p = p0; p < p0 + 4; p++) {
+      if (p >= p1) break;
+#else
   const int p0 = g0 >> 1, p1 = (g1 + 1) >> 1;
 #pragma unroll 4
   for (int p = p0; p < p1; p++) {
+#endif
     const float4 A = slabLoad<SMEM>(tab + 3 * p), B = slabLoad<SMEM>(tab + 3 * p + 1), C = slabLoad<SMEM>(tab + 3 * p + 2);
     const float2 mx = __ffma2_rn(make_float2(A.x, A.y), r.i[0], r.no[0]);
     const float2 my = __ffma2_rn(make_float2(A.z, A.w), r.i[1], r.no[1]);
@@ -277,8 +303,15 @@ __device__ __forceinline__ unsigned int slabMask(const float4* __restrict__ tab,
     const float2 tf = __ffma2_rn(make_float2(fminf(fminf(fx.x, fy.x), fz.x), fminf(fminf(fx.y, fy.y), fz.y)), r.grow, r.slack);
     const bool ok0 = !(fmaxf(tn0, r.floor_t) > fminf(tf.x, r.lim));
     const bool ok1 = !(fmaxf(tn1, r.floor_t) > fminf(tf.y, r.lim));
+#if DRT_GROUP_SKIP
+      sub |= ((ok0 ? 1u : 0u) | (ok1 ? 2u : 0u)) << (2 * (p - p0));
+    }
+    mask |= sub << (q0 - g0);
+  }
+#else
     mask |= ((ok0 ? 1u : 0u) | (ok1 ? 2u : 0u)) << (2 * (p - p0));
   }
+#endif
   // a ray with an infinite error bound (exactly axis-parallel) passes everything, the padding entry included
   return mask & slabAll(g0, g1);
 }
@@ -311,7 +344,7 @@ __device__ inline void closestHit(const Params<R>& P, const float4* __restrict__
     const int n = P.n_geoms;
     for (int g0 = 0; g0 < n; g0 += 32) {
       const int g1 = min(n, g0 + 32);
-      unsigned int mask = !cull ? slabAll(g0, g1) : smem ? slabMask<true>(gb, g0, g1, sr) : slabMask<false>(gb, g0, g1, sr);
+      unsigned int mask = !cull ? slabAll(g0, g1) : smem ? slabMask<true>(gb, n, g0, g1, sr) : slabMask<false>(gb, n, g0, g1, sr);
       while (mask) {
         const int gi = g0 + __ffs(mask) - 1;      // ascending = the reference's candidate order
         mask &= mask - 1;
@@ -453,7 +486,7 @@ __device__ inline bool anyHit(const Params<R>& P, const float4* __restrict__ gb,
     for (int g0 = 0; g0 < n; g0 += 32) {
       const int g1 = min(n, g0 + 32);
       // lock-step, branch-free slab filter -> per-lane candidate mask
-      unsigned int mask = !cull ? slabAll(g0, g1) : smem ? slabMask<true>(gb, g0, g1, sr) : slabMask<false>(gb, g0, g1, sr);
+      unsigned int mask = !cull ? slabAll(g0, g1) : smem ? slabMask<true>(gb, n, g0, g1, sr) : slabMask<false>(gb, n, g0, g1, sr);
       while (mask) {                                // each lane walks its own candidates
         const int gi = g0 + __ffs(mask) - 1;
         mask &= mask - 1;
@@ -1178,10 +1211,10 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
   __shared__ int s_hist[DRT_HIT_BUCKETS];                 // SHADE order: counting sort of the hit buffer by geom
   __shared__ long long s_idx0;
   // slab-filter table of the whole scene, staged once per persistent CTA (48 B per pair of geoms)
-  __shared__ float4 s_gb[3 * DRT_SMEM_GEOMS / 2];
+  __shared__ float4 s_gb[3 * DRT_SMEM_GEOMS / 2 + 2 * DRT_SMEM_GEOMS / 8];
   const float4* gb = P.gbounds;
   if (P.n_geoms <= DRT_SMEM_GEOMS) {
-    for (int i = threadIdx.x; i < 3 * ((P.n_geoms + 1) / 2); i += blockDim.x) s_gb[i] = P.gbounds[i];
+    for (int i = threadIdx.x; i < 3 * ((P.n_geoms + 1) / 2) + 2 * ((P.n_geoms + 7) / 8); i += blockDim.x) s_gb[i] = P.gbounds[i];
     gb = s_gb;
   }
   const unsigned FULL = 0xffffffffu;
