@@ -212,7 +212,8 @@ def test_production_spp_mae_against_high_spp_reference(oracle_lib):
         assert ours_single <= 1.2 * ref_self + 0.05, (case, ours_single, ref_self)
 
 
-@pytest.mark.parametrize("variant", ["one_pixel", "edge_tile", "depth1", "noreflect", "nogloss", "no_lights", "aa2", "blur_ref_mode"])
+@pytest.mark.parametrize("variant", ["one_pixel", "edge_tile", "depth1", "noreflect", "nogloss", "no_lights", "aa2", "blur_ref_mode",
+                                     "brdf5_depth4", "depth32"])
 def test_cuda_edge_cases_match_oracle(oracle_lib, variant):
     """Edge cases of the settings surface: degenerate tiles, depth / switch extremes, spp that is not
     a square, a light-less scene, and the reference's own motion-blur mode with moving "rectangle"
@@ -238,6 +239,10 @@ def test_cuda_edge_cases_match_oracle(oracle_lib, variant):
         scene = Scene(scene.prims, [], scene.textures)
     elif variant == "aa2":
         s.antialias_samples, s.aperture = 2, 0.2   # n = int(sqrt(2)) = 1 -> 1 spp
+    elif variant == "brdf5_depth4":
+        s.brdf_samples, s.max_depth = 5, 4         # widest glossy fan the ray pool is sized for
+    elif variant == "depth32":
+        s.max_depth = 32                           # deepest recursion the boundary accepts
     elif variant == "blur_ref_mode":
         # frame >= frame_prism: shapes named "rectangle" move in y for the blur re-traces; flag them
         prims = [abi.copy_struct(p) for p in scene.prims]
