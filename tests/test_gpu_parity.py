@@ -159,6 +159,19 @@ def test_cuda_mesh_lbvh_matches_oracle(oracle_lib):
     assert st["frac_within_1"] >= TOL_FRAC, st
 
 
+def test_cuda_obj_ingest_renders_like_the_direct_mesh(oracle_lib):
+    """A mesh that went through the OBJ text format and `ingest.mesh_from_obj` (vertex unification, no
+    UV rewrite) renders byte-identically to the mesh it was written from."""
+    from distraytracer_b200 import scenes, ingest
+    from distraytracer_b200.scene import Scene
+    scene, s = scenes.config5(n=16, xres=96, yres=54, spp=4)
+    obj = ingest.parse_obj(ingest.mesh_to_obj(scene.mesh))
+    mesh2 = ingest.mesh_from_obj(obj, scene.mesh["material"], wrap_uv=False, flip_v=False)
+    a = _gpu(scene).render(s)
+    b = _gpu(Scene(scene.prims, scene.lights, scene.textures, mesh=mesh2)).render(s)
+    assert np.array_equal(a, b) and a.std() > 5
+
+
 def test_cuda_mesh_full_size_builds_and_is_deterministic(oracle_lib):
     """999 698 triangles: the LBVH builds on the device, a 4K/64spp band renders, twice the same."""
     from distraytracer_b200 import scenes, abi
