@@ -720,6 +720,17 @@ int drt_scene_update_prims(drt_scene* s, const drt_prim* prims, int32_t n_prims)
   return flattenAndUpload(s);
 }
 
+int drt_scene_update_lights(drt_scene* s, const drt_light* lights, int32_t n_lights) {
+  if (!s || (n_lights > 0 && !lights) || n_lights < 0) return fail(DRT_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(s->device));
+  CK(cudaStreamSynchronize(s->stream));
+  const std::vector<drt_light> before = s->lights;
+  s->lights.assign(lights, lights + n_lights);
+  const int rc = flattenAndUpload(s);
+  if (rc) s->lights = before;     // the device copy is untouched when validation fails
+  return rc;
+}
+
 void drt_scene_destroy(drt_scene* s) {
   if (!s) return;
   cudaSetDevice(s->device);

@@ -27,6 +27,12 @@
 #include <stdexcept>
 #include <string>
 #include <thread>
+#include <condition_variable>
+#include <deque>
+#include <fstream>
+#include <map>
+#include <mutex>
+#include <sstream>
 #include <vector>
 
 #include "../../include/drt.h"
@@ -241,6 +247,11 @@ struct Globals {
   int blur_mode = DRT_BLUR_REFERENCE;
   int precision = DRT_PRECISION_REFERENCE;
   int devices = 0;   // 0 = all visible GPUs (single frames are cut into one horizontal band per GPU)
+  // optional indexed triangle mesh (what loadObj + the scene builders' triangle loop produce, scene.h:296-386),
+  // kept as arrays and traversed through the device-built LBVH instead of 10^6 Triangle shapes
+  std::vector<float> mesh_vertices, mesh_texcoords;
+  std::vector<int32_t> mesh_indices;
+  std::shared_ptr<GeoPrimitive> mesh_material;
 };
 inline Globals& globals() { static Globals g; return g; }
 
@@ -302,6 +313,7 @@ struct FlatScene {
   std::vector<drt_prim> prims;
   std::vector<drt_light> lights;
   std::vector<drt_texture> textures;
+  drt_mesh mesh;
   drt_scene_desc desc;
 };
 
@@ -329,6 +341,13 @@ inline void flattenScene(FlatScene& f) {
   f.desc.n_lights = (int)f.lights.size(); f.desc.lights = f.lights.data();
   f.desc.n_textures = (int)f.textures.size(); f.desc.textures = f.textures.data();
   f.desc.mesh = nullptr;
+  if (!g.mesh_indices.empty() && g.mesh_material) {
+    f.mesh.n_vertices = (int64_t)g.mesh_vertices.size() / 3; f.mesh.n_triangles = (int64_t)g.mesh_indices.size() / 3;
+    f.mesh.vertices = g.mesh_vertices.data(); f.mesh.indices = g.mesh_indices.data();
+    f.mesh.texcoords = g.mesh_texcoords.empty() ? nullptr : g.mesh_texcoords.data();
+    f.mesh.material = flattenPrim(*g.mesh_material);
+    f.desc.mesh = &f.mesh;
+  }
 }
 
 inline drt_settings flattenSettings(int frame) {
@@ -353,7 +372,7 @@ inline drt_settings flattenSettings(int frame) {
 // "final gather" is the device-to-host copy of each band).
 inline void renderFrame(int frame, std::vector<uint8_t>& rgb) {
   Globals& g = globals();
-  if (g.shapes.size() < 1) throw std::runtime_error("No shapes to render!");   // render_final_project.cpp:973-977
+  if (g.shapes.size() < 1 && g.mesh_indices.empty()) throw std::runtime_error("No shapes to render!");   // render_final_project.cpp:973-977
   FlatScene f;
   flattenScene(f);
   const drt_settings st = flattenSettings(frame);
@@ -388,6 +407,162 @@ inline void renderImage(const std::string& filename, const int frame, const std:
   renderFrame(frame, rgb);
   Globals& g = globals();
   if (drt_write_ppm(filename.c_str(), g.xRes, g.yRes, rgb.data()) != DRT_OK) throw std::runtime_error(drt_last_error());
+}
+
+// ---- mesh ingest ------------------------------------------------------
+struct VEC3I { int v[3]; int& operator[](int i) { return v[i]; } int operator[](int i) const { return v[i]; } };
+
+// loadObj (objHelper.h:6-85) without tiny_obj_loader: positions, texcoords and per-face index
+// triples, polygons as triangle fans (tiny_obj_loader's default triangulation), indices 0-based,
+// -1 where a face corner has no texcoord.  Normals are not read: the path shades flat normals
+// (geometry.cpp:588-594) and the reference fills `normals` from positions anyway (quirk Q13).
+inline void loadObj(const std::string& path, std::vector<VEC3>& vertices, std::vector<VEC3I>& v_indices,
+                    std::vector<VEC2>& texcoords, std::vector<VEC3I>& t_indices) {
+  std::ifstream in(path);
+  if (!in) throw std::runtime_error("loadObj: cannot open " + path);
+  std::string line;
+  while (std::getline(in, line)) {
+    const size_t hash = line.find('#');
+    if (hash != std::string::npos) line.resize(hash);
+    std::istringstream ls(line);
+    std::string key;
+    if (!(ls >> key)) continue;
+    if (key == "v") { double x, y, z; if (!(ls >> x >> y >> z)) throw std::runtime_error("loadObj: bad vertex"); vertices.push_back(VEC3(x, y, z)); }
+    else if (key == "vt") { double u, v = 0; if (!(ls >> u)) throw std::runtime_error("loadObj: bad texcoord"); ls >> v; texcoords.push_back(VEC2(u, v)); }
+    else if (key == "f") {
+      std::vector<std::pair<int, int>> corners;
+      std::string c;
+      while (ls >> c) {
+        int vi = 0, ti = 0; bool has_t = false;
+        const size_t s1 = c.find('/');
+        vi = std::stoi(c.substr(0, s1));
+        if (s1 != std::string::npos) {
+          const size_t s2 = c.find('/', s1 + 1);
+          const std::string t = c.substr(s1 + 1, s2 == std::string::npos ? std::string::npos : s2 - s1 - 1);
+          if (!t.empty()) { ti = std::stoi(t); has_t = true; }
+        }
+        vi = vi > 0 ? vi - 1 : (int)vertices.size() + vi;
+        ti = !has_t ? -1 : (ti > 0 ? ti - 1 : (int)texcoords.size() + ti);
+        if (vi < 0 || vi >= (int)vertices.size() || (has_t && (ti < 0 || ti >= (int)texcoords.size())))
+          throw std::runtime_error("loadObj: face index out of range");
+        corners.push_back({vi, ti});
+      }
+      if (corners.size() < 3) throw std::runtime_error("loadObj: face with fewer than 3 corners");
+      for (size_t k = 1; k + 1 < corners.size(); k++) {
+        v_indices.push_back(VEC3I{{corners[0].first, corners[k].first, corners[k + 1].first}});
+        t_indices.push_back(VEC3I{{corners[0].second, corners[k].second, corners[k + 1].second}});
+      }
+    }
+  }
+}
+
+// The scene builders' triangle loop (scene.h:296-386) for a whole model at once: positions through
+// the 3x4 object transform `M` (row major, or nullptr), texcoords above 1 wrapped by dropping the
+// integer part, the bounds check that makes the reference throw, V flipped -- then (position,
+// texcoord) index pairs unified into vertices, because drt_mesh carries one texcoord per vertex.
+// `material` is the Triangle the reference would copy per face (colour, model, roughness, texture).
+inline void setMesh(const std::vector<VEC3>& vertices, const std::vector<VEC3I>& v_indices, const std::vector<VEC2>& texcoords,
+                    const std::vector<VEC3I>& t_indices, std::shared_ptr<GeoPrimitive> material, const double* M = nullptr,
+                    bool wrap_uv = true, bool flip_v = true) {
+  Globals& g = globals();
+  g.mesh_vertices.clear(); g.mesh_texcoords.clear(); g.mesh_indices.clear();
+  bool has_uv = !texcoords.empty();
+  for (const VEC3I& t : t_indices) for (int k = 0; k < 3; k++) if (t[k] < 0) has_uv = false;
+  std::vector<VEC2> uv = texcoords;
+  if (has_uv) {
+    for (VEC2& t : uv) {
+      if (wrap_uv) for (int k = 0; k < 2; k++) if (t[k] > 1) t[k] = t[k] - (int)t[k];
+    }
+    for (const VEC3I& t : t_indices) for (int k = 0; k < 3; k++)
+      if (!(uv[t[k]][0] >= 0 && uv[t[k]][1] <= 1)) throw std::runtime_error("Texcoords out of bounds");   // scene.h:343-354
+    if (flip_v) for (VEC2& t : uv) t[1] = 1 - t[1];
+  }
+  std::map<std::pair<int, int>, int> unified;
+  for (size_t f = 0; f < v_indices.size(); f++)
+    for (int k = 0; k < 3; k++) {
+      const std::pair<int, int> key{v_indices[f][k], has_uv ? t_indices[f][k] : -1};
+      auto it = unified.find(key);
+      if (it == unified.end()) {
+        it = unified.emplace(key, (int)(g.mesh_vertices.size() / 3)).first;
+        VEC3 p = vertices[key.first];
+        if (M) p = VEC3(M[0] * p[0] + M[1] * p[1] + M[2] * p[2] + M[3], M[4] * p[0] + M[5] * p[1] + M[6] * p[2] + M[7],
+                        M[8] * p[0] + M[9] * p[1] + M[10] * p[2] + M[11]);
+        for (int a = 0; a < 3; a++) g.mesh_vertices.push_back((float)p[a]);
+        if (has_uv) { g.mesh_texcoords.push_back((float)uv[key.second][0]); g.mesh_texcoords.push_back((float)uv[key.second][1]); }
+      }
+      g.mesh_indices.push_back(it->second);
+    }
+  g.mesh_material = std::move(material);
+}
+
+// ---- video (SURVEY.md 8(e) + 8(f)3) -----------------------------------------------------
+// Frames [first, last) of an animation: frame f goes to GPU (f - first) mod G; every GPU keeps ONE
+// resident scene and only re-uploads the primitives and lights `pose(f)` produced (the re-posed mocap
+// bones, scene.h:637-659; a light that moves with the frame, scene.h:3690-3692).  PPM files are written by a separate thread from a queue of finished frames, so
+// the 6 MB-per-frame file I/O overlaps the next renders (the reference's shell loop runs build,
+// render and writePPM back to back per frame).  `pose` is called under a lock, in frame order per GPU;
+// it must leave the number and types of shapes unchanged.  Returns the number of frames written.
+inline int renderVideo(int first, int last, const std::function<void(float)>& pose, const std::function<std::string(int)>& filename) {
+  Globals& g = globals();
+  int ndev = drt_device_count();
+  if (ndev < 1) throw std::runtime_error("no CUDA device: distraytracer-b200 has no CPU fallback");
+  if (g.devices > 0 && g.devices < ndev) ndev = g.devices;
+  if (last - first < ndev) ndev = std::max(1, last - first);
+  struct Done { int frame; std::vector<uint8_t> rgb; };
+  std::mutex pose_mu, q_mu;
+  std::condition_variable q_cv;
+  std::deque<Done> queue;
+  bool finished = false;
+  std::string write_err;
+  int written = 0;
+  std::thread writer([&]() {
+    for (;;) {
+      Done d;
+      {
+        std::unique_lock<std::mutex> lk(q_mu);
+        q_cv.wait(lk, [&] { return finished || !queue.empty(); });
+        if (queue.empty()) return;
+        d = std::move(queue.front()); queue.pop_front();
+      }
+      q_cv.notify_all();
+      if (drt_write_ppm(filename(d.frame).c_str(), g.xRes, g.yRes, d.rgb.data()) != DRT_OK) write_err = drt_last_error();
+      else written++;
+    }
+  });
+  std::vector<std::string> errs(ndev);
+  std::vector<std::thread> th;
+  for (int d = 0; d < ndev; d++)
+    th.emplace_back([&, d]() {
+      drt_scene* sc = nullptr;
+      for (int f = first + d; f < last; f += ndev) {
+        FlatScene fs; drt_settings st;
+        {
+          std::lock_guard<std::mutex> lk(pose_mu);        // the builders mutate the shared globals
+          pose((float)f);
+          flattenScene(fs); st = flattenSettings(f);
+          if (!sc && drt_scene_create(&fs.desc, d, &sc) != DRT_OK) { errs[d] = drt_last_error(); return; }
+        }
+        if (drt_scene_update_prims(sc, fs.prims.data(), (int)fs.prims.size()) != DRT_OK ||
+            drt_scene_update_lights(sc, fs.lights.data(), (int)fs.lights.size()) != DRT_OK) { errs[d] = drt_last_error(); break; }
+        Done out; out.frame = f; out.rgb.assign((size_t)st.xRes * st.yRes * 3, 0);
+        drt_tile tile{0, 0, st.xRes, st.yRes, d};
+        if (drt_render(sc, &st, &tile, out.rgb.data(), nullptr) != DRT_OK) { errs[d] = drt_last_error(); break; }
+        {
+          std::unique_lock<std::mutex> lk(q_mu);
+          q_cv.wait(lk, [&] { return queue.size() < 8; });   // bound the host memory held by unwritten frames
+          queue.push_back(std::move(out));
+        }
+        q_cv.notify_all();
+      }
+      if (sc) drt_scene_destroy(sc);
+    });
+  for (auto& t : th) t.join();
+  { std::lock_guard<std::mutex> lk(q_mu); finished = true; }
+  q_cv.notify_all();
+  writer.join();
+  for (auto& e : errs) if (!e.empty()) throw std::runtime_error(e);
+  if (!write_err.empty()) throw std::runtime_error(write_err);
+  return written;
 }
 
 }  // namespace host

@@ -15,6 +15,7 @@ _lib = None
 
 EXPORTS = [
     "drt_device_count", "drt_settings_default", "drt_prim_default", "drt_scene_create", "drt_scene_update_prims",
+    "drt_scene_update_lights",
     "drt_scene_destroy", "drt_render", "drt_render_float", "drt_render_device", "drt_write_ppm", "drt_last_error",
     "drt_abi_sizes", "drt_debug_rng", "drt_debug_candidate_order",
 ]
@@ -39,6 +40,7 @@ def lib():
         L.drt_prim_default.argtypes = [C.POINTER(abi.Prim)]
         L.drt_scene_create.argtypes = [C.POINTER(abi.SceneDesc), C.c_int, C.POINTER(C.c_void_p)]
         L.drt_scene_update_prims.argtypes = [C.c_void_p, C.POINTER(abi.Prim), C.c_int32]
+        L.drt_scene_update_lights.argtypes = [C.c_void_p, C.POINTER(abi.Light), C.c_int32]
         L.drt_scene_destroy.argtypes = [C.c_void_p]
         L.drt_scene_destroy.restype = None
         L.drt_render.argtypes = [C.c_void_p, C.POINTER(abi.Settings), C.POINTER(abi.Tile), C.c_void_p, C.POINTER(abi.Counters)]
@@ -95,6 +97,10 @@ class DeviceScene:
     def update_prims(self, prims):
         arr = (abi.Prim * len(prims))(*prims)
         _check(lib().drt_scene_update_prims(self.handle, arr, len(prims)))
+
+    def update_lights(self, lights):
+        arr = (abi.Light * max(1, len(lights)))(*lights)
+        _check(lib().drt_scene_update_lights(self.handle, arr, len(lights)))
 
     def _tile(self, settings, tile):
         if tile is None:

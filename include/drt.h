@@ -285,6 +285,10 @@ int drt_scene_create(const drt_scene_desc* desc, int device, drt_scene** out);
 /* Replace the analytic primitives in place (same count and types), e.g. the
  * re-posed bone cylinders of the next mocap frame (scene.h:637-659). */
 int drt_scene_update_prims(drt_scene* scene, const drt_prim* prims, int32_t n_prims);
+/* Replace the lights (any count), e.g. a light a scene builder moves with the
+ * frame number (scene.h:3690-3692).  Area lights keep pointing at their shapes
+ * through prim_index. */
+int drt_scene_update_lights(drt_scene* scene, const drt_light* lights, int32_t n_lights);
 void drt_scene_destroy(drt_scene* scene);
 
 /* Render `tile` of the frame into `out_rgb`: a tightly packed HOST buffer of

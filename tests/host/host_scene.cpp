@@ -44,9 +44,32 @@ static void buildSceneReflectance(float framef) {
   g.lights.push_back(make_shared<pointLight>(light_center, VEC3(1, 1, 1)));
 }
 
+// host_scene mesh <in.obj> <out.bin>: loadObj + setMesh (column transform of scene.h:296-299), dumps the
+// unified arrays: int64 n_vertices, n_triangles, has_uv; float vertices[3V]; int32 indices[3T]; float texcoords[2V]
+static int meshMode(const std::string& in, const std::string& out) {
+  std::vector<VEC3> vertices; std::vector<VEC3I> v_inds, t_inds; std::vector<VEC2> texcoords;
+  loadObj(in, vertices, v_inds, texcoords, t_inds);
+  const double M[12] = {3, 0, 0, 3, 0, 3, 0, -1, 0, 0, 3, 5};
+  auto mat = make_shared<Triangle>(VEC3(0, 0, 0), VEC3(1, 0, 0), VEC3(0, 1, 0), VEC3(0.75, 0.75, 0.75), "marble", false, "oren-nayar");
+  setMesh(vertices, v_inds, texcoords, t_inds, mat, M);
+  Globals& g = globals();
+  FlatScene f; flattenScene(f);
+  if (!f.desc.mesh) return 1;
+  std::ofstream o(out, std::ios::binary);
+  int64_t hdr[3] = {f.mesh.n_vertices, f.mesh.n_triangles, f.mesh.texcoords ? 1 : 0};
+  o.write((const char*)hdr, sizeof(hdr));
+  o.write((const char*)g.mesh_vertices.data(), g.mesh_vertices.size() * sizeof(float));
+  o.write((const char*)g.mesh_indices.data(), g.mesh_indices.size() * sizeof(int32_t));
+  o.write((const char*)g.mesh_texcoords.data(), g.mesh_texcoords.size() * sizeof(float));
+  return 0;
+}
+
 int main(int argc, char** argv) {
-  if (argc < 4) { fprintf(stderr, "usage: host_scene dump|render hw4|reflectance <out>\n"); return 2; }
+  if (argc < 4) { fprintf(stderr, "usage: host_scene dump|render|video hw4|reflectance <out> | mesh <in.obj> <out.bin>\n"); return 2; }
   std::string mode = argv[1], scene = argv[2], out = argv[3];
+  if (mode == "mesh") {
+    try { return meshMode(scene, out); } catch (const std::exception& e) { fprintf(stderr, "host_scene: %s\n", e.what()); return 1; }
+  }
   Globals& g = globals();
   g.xRes = 160; g.yRes = 120; g.seed = 7;
   int frame = 0;
@@ -65,6 +88,10 @@ int main(int argc, char** argv) {
       o.write((const char*)f.prims.data(), f.prims.size() * sizeof(drt_prim));
       o.write((const char*)f.lights.data(), f.lights.size() * sizeof(drt_light));
       o.write((const char*)&st, sizeof(st));
+    } else if (mode == "video") {
+      // frames 40..43 of the moving-light animation, `out` is a prefix: <out>.0040.ppm ...
+      const int n = renderVideo(40, 44, builder, [&](int f) { char b[32]; snprintf(b, sizeof(b), ".%04d.ppm", f); return out + b; });
+      if (n != 4) return 1;
     } else {
       renderImage(out, frame, builder);
     }

@@ -283,3 +283,19 @@ def test_video_frames_through_scene_update(oracle_lib):
         a = dev.render(s_f)
         b = _gpu(scene_f).render(s_f)
         assert np.array_equal(a, b), f
+
+
+def test_update_lights_equals_a_fresh_scene(oracle_lib):
+    """drt_scene_update_lights: moving the light of a resident scene gives the frame a newly created scene gives."""
+    from distraytracer_b200 import abi
+    from distraytracer_b200.scene import Scene
+    scene, settings, _ = load_case("reflectance")
+    s = abi.copy_struct(settings); s.xRes, s.yRes = 96, 72
+    dev = _gpu(scene)
+    a0 = dev.render(s)
+    lights = [abi.copy_struct(l) for l in scene.lights]
+    lights[0].center[2] += 7.0
+    dev.update_lights(lights)
+    a1 = dev.render(s)
+    b1 = _gpu(Scene(scene.prims, lights, scene.textures)).render(s)
+    assert np.array_equal(a1, b1) and not np.array_equal(a0, a1)

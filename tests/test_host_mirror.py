@@ -57,3 +57,38 @@ def test_renderImage_through_host_mirror(host_bin, tmp_path, oracle_lib):
     want, _, _, _ = Oracle(scene).render(settings, mode=ORACLE_KEYED)
     d = np.abs(got.astype(int) - quantize(want).astype(int)).max(axis=-1)
     assert (d <= 1).mean() >= 0.999
+
+
+def test_host_obj_ingest_matches_python_ingest(host_bin, tmp_path):
+    """loadObj + setMesh of the C++ mirror and distraytracer_b200.ingest agree triangle by triangle."""
+    from distraytracer_b200 import ingest
+    from test_ingest import CUBE_FACE
+    obj_path = str(tmp_path / "m.obj")
+    open(obj_path, "w").write(CUBE_FACE)
+    out = str(tmp_path / "mesh.bin")
+    subprocess.check_call([host_bin, "mesh", obj_path, out])
+    raw = open(out, "rb").read()
+    nv, nt, has_uv = np.frombuffer(raw[:24], dtype=np.int64)
+    off = 24
+    V = np.frombuffer(raw[off: off + 12 * nv], dtype=np.float32).reshape(-1, 3); off += 12 * nv
+    T = np.frombuffer(raw[off: off + 12 * nt], dtype=np.int32).reshape(-1, 3); off += 12 * nt
+    UV = np.frombuffer(raw[off: off + 8 * nv], dtype=np.float32).reshape(-1, 2)
+    want = ingest.mesh_from_obj(ingest.parse_obj(CUBE_FACE), None, transform=[[3, 0, 0, 3], [0, 3, 0, -1], [0, 0, 3, 5], [0, 0, 0, 1]])
+    assert has_uv == 1 and nt == len(want["indices"]) and nv == len(want["vertices"])
+    assert np.array_equal(V[T], want["vertices"][want["indices"]])
+    assert np.array_equal(UV[T], want["texcoords"][want["indices"]])
+
+
+@pytest.mark.gpu
+def test_renderVideo_writes_the_frames_renderImage_would(host_bin, tmp_path):
+    """renderVideo (frames round-robin over GPUs, one resident scene per GPU updated in place, PPMs written by a
+    background thread) produces, frame for frame, the file renderImage writes for that frame."""
+    from oracle.harness import read_ppm
+    prefix = str(tmp_path / "vid")
+    subprocess.check_call([host_bin, "video", "reflectance", prefix])
+    single = str(tmp_path / "single.ppm")
+    subprocess.check_call([host_bin, "render", "reflectance", single])          # renders frame 40
+    assert np.array_equal(read_ppm(prefix + ".0040.ppm"), read_ppm(single))
+    frames = [read_ppm(prefix + ".%04d.ppm" % f) for f in range(40, 44)]
+    assert all(f.shape == (120, 160, 3) for f in frames)
+    assert any(not np.array_equal(frames[0], f) for f in frames[1:])             # the light moves between frames
