@@ -19,6 +19,7 @@
 #ifndef DRT_HOST_H
 #define DRT_HOST_H
 
+#include <atomic>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -246,7 +247,9 @@ struct Globals {
   uint32_t seed = 0;
   int blur_mode = DRT_BLUR_REFERENCE;
   int precision = DRT_PRECISION_REFERENCE;
-  int devices = 0;   // 0 = all visible GPUs (single frames are cut into one horizontal band per GPU)
+  int devices = 0;   // 0 = all visible GPUs
+  int block_rows = 30;   // multi-GPU single frames: rows per dynamically claimed block (renderFrame)
+  bool always_blocks = false;   // cut into blocks even on one GPU (tests)
   // optional indexed triangle mesh (what loadObj + the scene builders' triangle loop produce, scene.h:296-386),
   // kept as arrays and traversed through the device-built LBVH instead of 10^6 Triangle shapes
   std::vector<float> mesh_vertices, mesh_texcoords;
@@ -367,9 +370,11 @@ inline drt_settings flattenSettings(int frame) {
   return s;
 }
 
-// Renders the frame into `rgb` (xRes*yRes*3 bytes, PPM row order).  One horizontal band per
-// GPU, each driven by its own host thread; the bands are written straight into `rgb` (the
-// "final gather" is the device-to-host copy of each band).
+// Renders the frame into `rgb` (xRes*yRes*3 bytes, PPM row order) on all visible GPUs.  The frame is cut into
+// blocks of `globals().block_rows` rows that the per-GPU host threads claim from a shared counter: sky rows and
+// object rows differ in cost by orders of magnitude, so equal bands would leave GPUs idle.  Every block
+// is written straight into `rgb` by its own drt_render (the "final gather" is that device-to-host copy); samples are
+// keyed by pixel, so the picture does not depend on how the frame was cut.
 inline void renderFrame(int frame, std::vector<uint8_t>& rgb) {
   Globals& g = globals();
   if (g.shapes.size() < 1 && g.mesh_indices.empty()) throw std::runtime_error("No shapes to render!");   // render_final_project.cpp:973-977
@@ -379,19 +384,24 @@ inline void renderFrame(int frame, std::vector<uint8_t>& rgb) {
   int ndev = drt_device_count();
   if (ndev < 1) throw std::runtime_error("no CUDA device: distraytracer-b200 has no CPU fallback");
   if (g.devices > 0 && g.devices < ndev) ndev = g.devices;
-  if (ndev > st.yRes) ndev = st.yRes;
+  const int rows = (ndev == 1 && !g.always_blocks) ? st.yRes : std::max(1, std::min(g.block_rows, st.yRes));   // one GPU: one launch sequence
+  const int n_blocks = (st.yRes + rows - 1) / rows;
+  if (ndev > n_blocks) ndev = n_blocks;
   rgb.assign((size_t)st.xRes * st.yRes * 3, 0);
   std::vector<std::string> errs(ndev);
+  std::atomic<int> next{0};
   std::vector<std::thread> th;
   for (int d = 0; d < ndev; d++)
     th.emplace_back([&, d]() {
       drt_scene* sc = nullptr;
       if (drt_scene_create(&f.desc, d, &sc) != DRT_OK) { errs[d] = drt_last_error(); return; }
-      // loop rows [y0,y1) of device d; buffer row 0 of the band is loop row y1-1
-      const int y0 = (int)((long long)st.yRes * d / ndev), y1 = (int)((long long)st.yRes * (d + 1) / ndev);
-      drt_tile tile{0, y0, st.xRes, y1 - y0, d};
-      uint8_t* dst = rgb.data() + (size_t)(st.yRes - y1) * st.xRes * 3;
-      if (drt_render(sc, &st, &tile, dst, nullptr) != DRT_OK) errs[d] = drt_last_error();
+      for (int b = next.fetch_add(1); b < n_blocks; b = next.fetch_add(1)) {
+        // loop rows [y0,y1) of block b; buffer row 0 of the block is loop row y1-1
+        const int y0 = b * rows, y1 = std::min(st.yRes, y0 + rows);
+        drt_tile tile{0, y0, st.xRes, y1 - y0, d};
+        uint8_t* dst = rgb.data() + (size_t)(st.yRes - y1) * st.xRes * 3;
+        if (drt_render(sc, &st, &tile, dst, nullptr) != DRT_OK) { errs[d] = drt_last_error(); break; }
+      }
       drt_scene_destroy(sc);
     });
   for (auto& t : th) t.join();

@@ -4,6 +4,7 @@
 // (scene.h:3668-3694) through the mirrored constructors.
 //   host_scene dump   <scene> <out.bin>  : flattened drt_prim / drt_light arrays (no GPU needed)
 //   host_scene render <scene> <out.ppm>  : renderImage() on the GPU(s)
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include "../../distraytracer_b200/host/drt_host.h"
@@ -72,6 +73,7 @@ int main(int argc, char** argv) {
   }
   Globals& g = globals();
   g.xRes = 160; g.yRes = 120; g.seed = 7;
+  if (getenv("DRT_HOST_BLOCKS")) { g.always_blocks = true; g.block_rows = atoi(getenv("DRT_HOST_BLOCKS")); }
   int frame = 0;
   std::function<void(float)> builder;
   if (scene == "hw4") { g.antialias_samples = 1; builder = buildSceneHW4; }

@@ -92,3 +92,13 @@ def test_renderVideo_writes_the_frames_renderImage_would(host_bin, tmp_path):
     frames = [read_ppm(prefix + ".%04d.ppm" % f) for f in range(40, 44)]
     assert all(f.shape == (120, 160, 3) for f in frames)
     assert any(not np.array_equal(frames[0], f) for f in frames[1:])             # the light moves between frames
+
+
+@pytest.mark.gpu
+def test_renderFrame_in_row_blocks_is_the_same_picture(host_bin, tmp_path):
+    """The multi-GPU cut of a single frame (row blocks claimed dynamically) does not change the image."""
+    from oracle.harness import read_ppm
+    a, b = str(tmp_path / "whole.ppm"), str(tmp_path / "blocks.ppm")
+    subprocess.check_call([host_bin, "render", "reflectance", a])
+    subprocess.check_call([host_bin, "render", "reflectance", b], env=dict(os.environ, DRT_HOST_BLOCKS="7"))
+    assert np.array_equal(read_ppm(a), read_ppm(b))
