@@ -12,16 +12,16 @@
 
 // ---- shape of one persistent render_wave CTA (shared by the kernels and the host-side pool sizing)
 #ifndef DRT_WAVE_WARPS
-#define DRT_WAVE_WARPS 12
+#define DRT_WAVE_WARPS 16
 #endif
 #ifndef DRT_BATCH
-#define DRT_BATCH 96          // camera samples per warp in a CTA batch
+#define DRT_BATCH 64          // camera samples per warp in a CTA batch
 #endif
 #define DRT_CTA_SLOTS (DRT_WAVE_WARPS * DRT_BATCH)   // camera samples per CTA batch
 // TRACE stops feeding the hit buffer at this many hits.  Larger = fewer phase switches, more 32-hit bites
 // per warp and pass (shorter barrier tails) and bigger geom buckets in the SHADE sort; costs a deeper ray pool.
 #ifndef DRT_TRACE_HITS_TARGET
-#define DRT_TRACE_HITS_TARGET 6144
+#define DRT_TRACE_HITS_TARGET 8192
 #endif
 #define DRT_HITS_PER_PASS (DRT_TRACE_HITS_TARGET + 32 * DRT_WAVE_WARPS)   // a TRACE pass can overshoot by one bite per warp
 #define DRT_CTA_HITS (DRT_HITS_PER_PASS + 64)
