@@ -40,6 +40,35 @@ struct alignas(16) Task {
   unsigned short pad_;
 };
 
+// Ray-pool and hit-buffer records are written once and read once: stream them past the L1 (ld/st.global.cs), which
+// is better spent on the geom / material records and the local-memory frames every ray keeps coming back to.
+#ifndef DRT_STREAM_RECORDS
+#define DRT_STREAM_RECORDS 1
+#endif
+template <typename T>
+__device__ __forceinline__ void loadRecord(T& dst, const T* src) {
+  static_assert(sizeof(T) % 16 == 0, "records are whole 16-byte words");
+#if DRT_STREAM_RECORDS
+  uint4* d = reinterpret_cast<uint4*>(&dst);
+  const uint4* q = reinterpret_cast<const uint4*>(src);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(T) / 16); i++) d[i] = __ldcs(q + i);
+#else
+  dst = *src;
+#endif
+}
+template <typename T>
+__device__ __forceinline__ void storeRecord(T* dst, const T& src) {
+#if DRT_STREAM_RECORDS
+  uint4* d = reinterpret_cast<uint4*>(dst);
+  const uint4* q = reinterpret_cast<const uint4*>(&src);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(T) / 16); i++) __stcs(d + i, q[i]);
+#else
+  *dst = src;
+#endif
+}
+
 template <typename R>
 struct Moved {           // per-trace displacement state (motion blur)
   float val;             // reference mode: y shift of "rectangle" shapes
@@ -1347,7 +1376,7 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
       bool hit = false;
       HitTask<R> H;
       if (active) {
-        H.T = pool[end - 1 - lane];
+        loadRecord(H.T, &pool[end - 1 - lane]);
         const unsigned int f = ((volatile unsigned int*)sfl)[H.T.slot];
         if (!(f & SF_ABORT)) {                                          // an aborted sample spawns no more work (Q15)
           HitRec h; int motion;
@@ -1366,7 +1395,7 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
       hbase = __shfl_sync(FULL, hbase, 0);
       if (hit) {
         const int at = hbase + __popc(hm & ((1u << lane) - 1u));
-        hits[at] = H;
+        storeRecord(&hits[at], H);
         s_hkey[at] = (unsigned char)min(H.geom, DRT_HIT_BUCKETS - 1);
       }
     }
@@ -1422,7 +1451,8 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
       {
         PairIn<R> pin; pin.want = 0;
         if (active) {
-          const HitTask<R> H = hits[s_order[end - 1 - lane]];
+          HitTask<R> H;
+          loadRecord(H, &hits[s_order[end - 1 - lane]]);
           HitRec h; h.t = H.t; h.geom = H.geom; h.inside = H.inside; h.checker_sel = H.checker_sel;
           slot = H.T.slot;
           shadeA<R, COUNT>(P, H.T, h, kids, nk, add, has_add, aborted, S, cnt);
@@ -1479,7 +1509,7 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
         int base = pbase;
 #pragma unroll
         for (int j = 0; j < DRT_MAX_CHILDREN; j++) {
-          if (nk > j) pool[base + __popc(kb[j] & ((1u << lane) - 1u))] = kids[j];
+          if (nk > j) storeRecord(&pool[base + __popc(kb[j] & ((1u << lane) - 1u))], kids[j]);
           base += __popc(kb[j]);
         }
       }
