@@ -26,19 +26,22 @@
 namespace drt {
 
 
+// One pending rayColor invocation: 64 bytes in the reference precision (48 in single), four 16-byte words.  Every ray
+// is written to the CTA pool once and read once, and again inside its hit record, so the record size is DRAM traffic.
 template <typename R>
 struct alignas(16) Task {
   Vec<R> org, dir;
   float k;
   uint32_t path;
-  float val;             // reference-mode blur: y shift of "rectangle" shapes for this trace
-  float dt;              // time offset of this trace (0 for the primary trace)
-  short depth;
-  unsigned char chain;   // on the "last invocation" chain that decides in_motion (quirk Q4)
-  unsigned char flags;   // bit0: root ray of the primary trace
-  unsigned short slot;   // sample slot inside the warp's batch
-  unsigned short pad_;
+  float dt;              // time offset of this trace (0 for the primary trace); the y shift of "rectangle" shapes in a
+                         // reference-mode blur re-trace is a function of it (blurVal)
+  unsigned char depth;   // remaining recursion depth (<= 32)
+  unsigned char bits;    // bit0: on the "last invocation" chain that decides in_motion (quirk Q4); bit1: root ray of the primary trace
+  unsigned short slot;   // sample slot inside the CTA's batch
 };
+#define TASK_CHAIN 1
+#define TASK_ROOT 2
+static_assert(sizeof(Task<double>) == 64 && sizeof(Task<float>) == 48, "ray records are whole 16-byte words");
 
 // Ray-pool and hit-buffer records are written once and read once: stream them past the L1 (ld/st.global.cs), which
 // is better spent on the geom / material records and the local-memory frames every ray keeps coming back to.
@@ -75,6 +78,15 @@ struct Moved {           // per-trace displacement state (motion blur)
   R time;                // velocity mode: time offset
   int velocity_mode;
 };
+
+// render_final_project.cpp:1104-1188: shapes named "rectangle" move in y by `val` during a blur re-trace at time
+// offset dt, once frame >= frame_prism (below that the reference's `val` is uninitialised, quirk Q16: 0 here).
+template <typename R>
+__device__ __forceinline__ float blurVal(const Params<R>& P, const float dt) {
+  if (dt == 0.0f || P.blur_mode != 0 || P.frame < P.frame_prism) return 0.0f;
+  if (P.frame >= P.frame_blur) return (float)((double)(P.move_per_frame * dt) + (double)P.accel_t * ((double)dt * (double)dt * (double)dt));
+  return P.move_per_frame * dt;
+}
 
 template <typename R>
 __device__ inline Vec<R> shiftPoint(const Moved<R>& mv, int gflags, const Vec<R>& vel, Vec<R> p) {
@@ -789,12 +801,12 @@ __device__ inline bool traceRay(const Params<R>& P, const float4* __restrict__ g
   motion = -1;
   if (T.depth == 0) return false;                                       // :489
   if (COUNT) cnt.rays++;
-  Moved<R> mv; mv.val = T.val; mv.time = (R)T.dt; mv.velocity_mode = (P.blur_mode == 1 && T.dt != 0.0f);
+  Moved<R> mv; mv.val = blurVal(P, T.dt); mv.time = (R)T.dt; mv.velocity_mode = (P.blur_mode == 1 && T.dt != 0.0f);
   closestHit<R, COUNT>(P, gb, mv, T.dir, T.org, h, cnt);
   if (P.n_mesh_tris > 0) meshTraverse<R, COUNT, true>(P, T.dir, T.org, h.t, &h, T.dir, T.org, cnt);
-  if (T.chain) motion = 0;                                              // :519
+  if (T.bits & TASK_CHAIN) motion = 0;                                              // :519
   if (h.geom < 0) return false;                                         // :541-544
-  if (T.chain) {
+  if (T.bits & TASK_CHAIN) {
     const int owner = h.geom >= P.n_geoms ? P.mesh_prim : P.geoms[h.geom].owner;
     motion = (P.prims[owner].flags & 2) ? 1 : 0;                        // DRT_FLAG_MOTION, :564
   }
@@ -845,7 +857,7 @@ __device__ void shadeA(const Params<R>& P, const Task<R>& T, const HitRec& h, Ta
   int sp = 0;
   n_out = 0; has_add = false;
   add[0] = add[1] = add[2] = 0.0;
-  Moved<R> mv; mv.val = T.val; mv.time = (R)T.dt; mv.velocity_mode = (P.blur_mode == 1 && T.dt != 0.0f);
+  Moved<R> mv; mv.val = blurVal(P, T.dt); mv.time = (R)T.dt; mv.velocity_mode = (P.blur_mode == 1 && T.dt != 0.0f);
   S.lights = false; S.aborted = false; S.early = false; S.hits = 0; S.tmp[0] = S.tmp[1] = S.tmp[2] = 0.0; S.mv = mv;
   do {
     const Vec<R> ray = T.dir, eye = T.org;
@@ -922,7 +934,7 @@ __device__ void shadeA(const Params<R>& P, const Task<R>& T, const HitRec& h, Ta
           if (sp < DRT_MAX_CHILDREN) {
             Task<R>& c = stack[sp++];
             c.org = isectP + in * (R)eps; c.dir = out; c.k = k_refr * k; c.path = rng_key_child(T.path, 0);
-            c.depth = T.depth - 1; c.chain = 0; c.flags = 0; c.slot = T.slot; c.val = T.val; c.dt = T.dt; n_children++;
+            c.depth = (unsigned char)(T.depth - 1); c.bits = 0; c.slot = T.slot; c.dt = T.dt; n_children++;
           }
         }
       }
@@ -977,7 +989,7 @@ __device__ void shadeA(const Params<R>& P, const Task<R>& T, const HitRec& h, Ta
             if (sp < DRT_MAX_CHILDREN) {
               Task<R>& c = stack[sp++];
               c.org = isectP + sample_refl * (R)eps; c.dir = sample_refl; c.k = k_refl * k / P.brdf_samples;
-              c.path = rng_key_child(T.path, 2 + i); c.depth = T.depth - 1; c.chain = 0; c.flags = 0; c.slot = T.slot; c.val = T.val; c.dt = T.dt; n_children++;
+              c.path = rng_key_child(T.path, 2 + i); c.depth = (unsigned char)(T.depth - 1); c.bits = 0; c.slot = T.slot; c.dt = T.dt; n_children++;
             }
           }
           if (aborted) break;
@@ -985,12 +997,12 @@ __device__ void shadeA(const Params<R>& P, const Task<R>& T, const HitRec& h, Ta
           if (sp < DRT_MAX_CHILDREN) {
             Task<R>& c = stack[sp++];
             c.org = isectP + refl_ray * (R)eps; c.dir = refl_ray; c.k = k_refl * k; c.path = rng_key_child(T.path, 1);
-            c.depth = T.depth - 1; c.chain = 0; c.flags = 0; c.slot = T.slot; c.val = T.val; c.dt = T.dt; n_children++;
+            c.depth = (unsigned char)(T.depth - 1); c.bits = 0; c.slot = T.slot; c.dt = T.dt; n_children++;
           }
         }
       }
       // the reference's LAST child call continues the in_motion chain (quirk Q4)
-      if (T.chain && n_children > 0) stack[first_child + n_children - 1].chain = 1;
+      if ((T.bits & TASK_CHAIN) && n_children > 0) stack[first_child + n_children - 1].bits = TASK_CHAIN;
     }
 
     // ---- local shading (:772-960) ------------------------------------------------
@@ -1284,17 +1296,12 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
             if ((sfl[s2] & (SS_MOTION | SF_ABORT)) != SS_MOTION) continue;
             Task<R> T; uint32_t skey; int pi, pj, px, py;
             primaryRay<R>(P, P.sample_base + idx0 + s2, T.org, T.dir, skey, pi, pj, px, py);
-            T.k = 1.0f; T.depth = (short)P.max_depth; T.chain = 0; T.flags = 0; T.slot = (unsigned short)s2; T.pad_ = 0;
+            T.k = 1.0f; T.depth = (unsigned char)P.max_depth; T.bits = 0; T.slot = (unsigned short)s2;
             const int at = atomicAdd(&s_count, P.blur_samples);
             for (int m = 0; m < P.blur_samples; m++) {
               float frame_sample = (float)((double)(float)P.frame + (double)rng_u01(skey, (uint32_t)m) * (double)P.frame_range);
-              float dt = frame_sample - (float)P.frame;
-              float val = 0;                                            // uninitialised in the reference below frame_prism (Q16)
-              if (P.blur_mode == 0 && P.frame >= P.frame_prism) {
-                if (P.frame >= P.frame_blur) val = (float)((double)(P.move_per_frame * dt) + (double)P.accel_t * ((double)dt * (double)dt * (double)dt));
-                else val = P.move_per_frame * dt;
-              }
-              T.val = val; T.dt = dt; T.path = rng_key_child(skey, 1 + m);
+              T.dt = frame_sample - (float)P.frame;
+              T.path = rng_key_child(skey, 1 + m);
               pool[at + m] = T;                                         // <= DRT_CTA_SLOTS * blur_samples, validated on the host
             }
           }
@@ -1351,8 +1358,8 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
         for (int s2 = tid; s2 < nv; s2 += blockDim.x) {                  // primary rays -> pool[0..nv)
           Task<R> T; uint32_t skey; int pi, pj, px, py;
           primaryRay<R>(P, P.sample_base + i0 + s2, T.org, T.dir, skey, pi, pj, px, py);
-          T.k = 1.0f; T.path = rng_key_child(skey, 0); T.val = 0.f; T.dt = 0.f; T.depth = (short)P.max_depth;
-          T.chain = 1; T.flags = 1; T.slot = (unsigned short)s2; T.pad_ = 0;
+          T.k = 1.0f; T.path = rng_key_child(skey, 0); T.dt = 0.f; T.depth = (unsigned char)P.max_depth;
+          T.bits = TASK_CHAIN | TASK_ROOT; T.slot = (unsigned short)s2;
           pool[s2] = T;
           if (COUNT) cnt.samples++;
         }
@@ -1382,7 +1389,7 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
           HitRec h; int motion;
           hit = traceRay<R, COUNT>(P, gb, H.T, h, motion, cnt);
           unsigned int orf = 0;
-          if ((H.T.flags & 1) && hit) orf |= SS_HIT;
+          if ((H.T.bits & TASK_ROOT) && hit) orf |= SS_HIT;
           if (motion == 1) orf |= SS_MOTION;
           if (orf) atomicOr(&sfl[H.T.slot], orf);
           if (motion == 0) atomicAnd(&sfl[H.T.slot], ~SS_MOTION);
@@ -1456,7 +1463,7 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
           HitRec h; h.t = H.t; h.geom = H.geom; h.inside = H.inside; h.checker_sel = H.checker_sel;
           slot = H.T.slot;
           shadeA<R, COUNT>(P, H.T, h, kids, nk, add, has_add, aborted, S, cnt);
-          if (!aborted && S.lights) { pin.isectP = S.isectP; pin.path = H.T.path; pin.val = H.T.val; pin.dt = H.T.dt; pin.want = 1; }
+          if (!aborted && S.lights) { pin.isectP = S.isectP; pin.path = H.T.path; pin.val = S.mv.val; pin.dt = H.T.dt; pin.want = 1; }
         }
         pairin[lane] = pin;
       }
