@@ -1057,7 +1057,7 @@ template <typename R, bool COUNT>
 __device__ void shadeB(const Params<R>& P, ShadeState<R>& S, const PairOut<R>* res, int l0, int l1, Counts& cnt) {
   const PrimD<R>& pr = P.prims[S.prim];
   for (int li = l0; li < l1 && !S.early && !S.aborted; li++) {
-    const PairOut<R> r = res[li - l0];
+    const PairOut<R> r = res[(li - l0) * 32];                          // light-major: [light][hit]
     if (r.state == 2) { S.aborted = true; break; }                   // throws geometry.cpp:2785-2789
     if (r.state == 0) continue;                                       // shadowed :852-855
     const LightD<R>& L = P.lights[li];
@@ -1474,11 +1474,11 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
         for (int pid = lane; pid < take * nl; pid += 32) {
           const int lj = pid / take, hh = pid - lj * take;              // light-major: one pass of the warp heads for one light
           const PairIn<R> pin = pairin[hh];
-          if (pin.want) shadowPair<R, COUNT>(P, gb, pin, l0 + lj, pairout[hh * DRT_PAIR_LIGHTS + lj], cnt);
+          if (pin.want) shadowPair<R, COUNT>(P, gb, pin, l0 + lj, pairout[lj * 32 + hh], cnt);   // lanes write neighbours
         }
         __syncwarp();
         // -- step C (lane = hit again): texture + BRDF of the unoccluded lights, in light order
-        if (active && !aborted && S.lights) shadeB<R, COUNT>(P, S, pairout + lane * DRT_PAIR_LIGHTS, l0, l0 + nl, cnt);
+        if (active && !aborted && S.lights) shadeB<R, COUNT>(P, S, pairout + lane, l0, l0 + nl, cnt);
         __syncwarp();
       }
       if (active) {

@@ -26,7 +26,9 @@
 #define DRT_HITS_PER_PASS (DRT_TRACE_HITS_TARGET + 32 * DRT_WAVE_WARPS)   // a TRACE pass can overshoot by one bite per warp
 #define DRT_CTA_HITS (DRT_HITS_PER_PASS + 64)
 #define DRT_MAX_CHILDREN 6    // refraction + max(brdf_samples, 1)
+#ifndef DRT_PAIR_LIGHTS
 #define DRT_PAIR_LIGHTS 8      // lights whose shadow rays are spread over the warp per pass
+#endif
 #define DRT_SMEM_GEOMS 256     // slab-filter entries staged in shared memory per CTA
 
 namespace drt {
