@@ -838,18 +838,22 @@ struct ShadeState {
 };
 
 template <typename R>
-struct alignas(16) PairIn {   // what a shadow pair needs to know about its hit
+struct PairIn {   // what a shadow pair needs to know about its hit (kept in the hit lane's registers, fetched by shuffle)
   Vec<R> isectP;
   uint32_t path;
   float val, dt;
   int want;
 };
+// Results of the (hit, light) pairs of one warp pass, structure-of-arrays in the warp's global scratch, index
+// light * 32 + hit: the 32 pair lanes of a pass write neighbouring words of each array and the 32 hit lanes read
+// neighbouring words back (as 32-byte records at a 256-byte stride 70-85 % of the sectors moved were waste).
 template <typename R>
-struct alignas(16) PairOut {
-  Vec<R> sray;
-  int state;      // 0 occluded, 1 visible, 2 the light sampler aborted (reference throws)
-  int pad_;
+struct PairOut {
+  R* x; R* y; R* z;   // sray
+  int* state;         // 0 occluded, 1 visible, 2 the light sampler aborted (reference throws)
 };
+template <typename R>
+__host__ __device__ constexpr size_t pairOutBytes() { return (size_t)32 * DRT_PAIR_LIGHTS * (3 * sizeof(R) + sizeof(int)); }
 
 template <typename R, bool COUNT>
 __device__ void shadeA(const Params<R>& P, const Task<R>& T, const HitRec& h, Task<R>* stack, int& n_out, double (&add)[3],
@@ -1032,15 +1036,16 @@ __device__ void shadeA(const Params<R>& P, const Task<R>& T, const HitRec& h, Ta
 
 // LightPrimitive::sampleRay (:802) + the shadow test (:806-855) for one (hit, light) pair.
 template <typename R, bool COUNT>
-__device__ void shadowPair(const Params<R>& P, const float4* __restrict__ gb, const PairIn<R>& in, int li, PairOut<R>& out, Counts& cnt) {
+__device__ void shadowPair(const Params<R>& P, const float4* __restrict__ gb, const PairIn<R>& in, int li, const PairOut<R>& out, const int oi,
+                           Counts& cnt) {
   const LightD<R>& L = P.lights[li];
   const Vec<R> isectP = in.isectP;
   Moved<R> mv; mv.val = in.val; mv.time = (R)in.dt; mv.velocity_mode = (P.blur_mode == 1 && in.dt != 0.0f);
   Vec<R> sray;
   if (L.type == 0) sray = L.center - isectP;                        // pointLight geometry.cpp:2751-2754
   else if (L.type == 2) sray = rectSample<R>(L.A, L.B, L.D, in.path, rng_dim_light(li, 0)) - isectP;   // :2845-2849
-  else if (!sampleSphereLight<R>(L, isectP, in.path, li, sray)) { out.state = 2; return; }   // (returns the POINT, Q10)
-  out.sray = sray;
+  else if (!sampleSphereLight<R>(L, isectP, in.path, li, sray)) { out.state[oi] = 2; return; }   // (returns the POINT, Q10)
+  out.x[oi] = sray.x; out.y[oi] = sray.y; out.z[oi] = sray.z;
   const float t_max = (float)norm(sray);                            // :804
   const Vec<R> sdir = normalized(sray);
   if (COUNT) cnt.shadow_rays++;
@@ -1049,19 +1054,20 @@ __device__ void shadowPair(const Params<R>& P, const float4* __restrict__ gb, co
   bool occluded = anyHit<R, COUNT>(P, gb, mv, sray, isectP + sray * R(1e-3), sdir, isectP + sdir * R(1e-3), t_max, L.prim_index, cnt);
   if (!occluded && P.n_mesh_tris > 0)
     occluded = meshTraverse<R, COUNT, false>(P, sdir, isectP + sdir * R(1e-3), t_max, nullptr, sray, isectP + sray * R(1e-3), cnt);
-  out.state = occluded ? 0 : 1;
+  out.state[oi] = occluded ? 0 : 1;
 }
 
 // The rest of the light loop (:856-959) for lights [l0, l1) of one hit, in order.
 template <typename R, bool COUNT>
-__device__ void shadeB(const Params<R>& P, ShadeState<R>& S, const PairOut<R>* res, int l0, int l1, Counts& cnt) {
+__device__ void shadeB(const Params<R>& P, ShadeState<R>& S, const PairOut<R>& res, const int hit_lane, int l0, int l1, Counts& cnt) {
   const PrimD<R>& pr = P.prims[S.prim];
   for (int li = l0; li < l1 && !S.early && !S.aborted; li++) {
-    const PairOut<R> r = res[(li - l0) * 32];                          // light-major: [light][hit]
-    if (r.state == 2) { S.aborted = true; break; }                   // throws geometry.cpp:2785-2789
-    if (r.state == 0) continue;                                       // shadowed :852-855
+    const int oi = (li - l0) * 32 + hit_lane;                          // light-major: [light][hit]
+    const int state = res.state[oi];
+    if (state == 2) { S.aborted = true; break; }                     // throws geometry.cpp:2785-2789
+    if (state == 0) continue;                                         // shadowed :852-855
     const LightD<R>& L = P.lights[li];
-    const Vec<R> sray = r.sray;
+    const Vec<R> sray = mk<R>(res.x[oi], res.y[oi], res.z[oi]);
     const Vec<R> sdir = normalized(sray);
       // ---- texture (:859-893) ---------------------------------------------------
       if (pr.flags & 4) {
@@ -1215,7 +1221,7 @@ __device__ __noinline__ void primaryRay(const Params<R>& P, long long gidx, Vec<
 }
 
 // Scratch of one persistent CTA in global memory (L1/L2 resident):
-//   [ pool_cap ray tasks | DRT_CTA_HITS hit tasks | per warp: 32 pair inputs + 32 x DRT_PAIR_LIGHTS pair results ]
+//   [ pool_cap ray tasks | DRT_CTA_HITS hit tasks | per warp: 32 x DRT_PAIR_LIGHTS shadow-pair results ]
 // pool_cap (Params::pool_cap) is sized per render on the host from brdf_samples / max_depth / blur_samples.
 #ifndef DRT_WAVE_CTAS_PER_SM
 #define DRT_WAVE_CTAS_PER_SM 1
@@ -1225,7 +1231,7 @@ __host__ __device__ constexpr size_t waveDynSmemBytes() { return (size_t)DRT_CTA
 template <typename R>
 __host__ __device__ constexpr size_t waveScratchBytes(int pool_cap) {
   return (size_t)pool_cap * sizeof(Task<R>) + DRT_CTA_HITS * sizeof(HitTask<R>) +
-         DRT_WAVE_WARPS * (32 * sizeof(PairIn<R>) + 32 * DRT_PAIR_LIGHTS * sizeof(PairOut<R>));
+         DRT_WAVE_WARPS * pairOutBytes<R>();
 }
 
 // render_wave -- phase-locked persistent CTA with CTA-wide work pools.
@@ -1263,9 +1269,10 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
   char* cbase = (char*)P.pool_raw + (size_t)blockIdx.x * waveScratchBytes<R>(P.pool_cap);
   Task<R>* pool = (Task<R>*)cbase;
   HitTask<R>* hits = (HitTask<R>*)(cbase + (size_t)P.pool_cap * sizeof(Task<R>));
-  char* wbase = (char*)(hits + DRT_CTA_HITS) + (size_t)wib * (32 * sizeof(PairIn<R>) + 32 * DRT_PAIR_LIGHTS * sizeof(PairOut<R>));
-  PairIn<R>* pairin = (PairIn<R>*)wbase;
-  PairOut<R>* pairout = (PairOut<R>*)(pairin + 32);
+  char* wbase = (char*)(hits + DRT_CTA_HITS) + (size_t)wib * pairOutBytes<R>();
+  PairOut<R> pairout;
+  pairout.x = (R*)wbase; pairout.y = pairout.x + 32 * DRT_PAIR_LIGHTS; pairout.z = pairout.y + 32 * DRT_PAIR_LIGHTS;
+  pairout.state = (int*)(pairout.z + 32 * DRT_PAIR_LIGHTS);
   unsigned long long(*acc)[3] = s_acc;
   unsigned int* sfl = s_flags;
   const long long n_batches = (P.sample_count + DRT_CTA_SLOTS - 1) / DRT_CTA_SLOTS;
@@ -1455,30 +1462,32 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
       double add[3] = {0, 0, 0}; bool has_add = false, aborted = false;
       unsigned short slot = 0;
       // -- step A (lane = hit): normal, children, emissive term
-      {
-        PairIn<R> pin; pin.want = 0;
-        if (active) {
-          HitTask<R> H;
-          loadRecord(H, &hits[s_order[end - 1 - lane]]);
-          HitRec h; h.t = H.t; h.geom = H.geom; h.inside = H.inside; h.checker_sel = H.checker_sel;
-          slot = H.T.slot;
-          shadeA<R, COUNT>(P, H.T, h, kids, nk, add, has_add, aborted, S, cnt);
-          if (!aborted && S.lights) { pin.isectP = S.isectP; pin.path = H.T.path; pin.val = S.mv.val; pin.dt = H.T.dt; pin.want = 1; }
-        }
-        pairin[lane] = pin;
+      PairIn<R> pin; pin.want = 0; pin.isectP = mk<R>(R(0), R(0), R(0)); pin.path = 0u; pin.val = 0.f; pin.dt = 0.f;
+      if (active) {
+        HitTask<R> H;
+        loadRecord(H, &hits[s_order[end - 1 - lane]]);
+        HitRec h; h.t = H.t; h.geom = H.geom; h.inside = H.inside; h.checker_sel = H.checker_sel;
+        slot = H.T.slot;
+        shadeA<R, COUNT>(P, H.T, h, kids, nk, add, has_add, aborted, S, cnt);
+        if (!aborted && S.lights) { pin.isectP = S.isectP; pin.path = H.T.path; pin.val = S.mv.val; pin.dt = H.T.dt; pin.want = 1; }
       }
-      __syncwarp();
-      // -- step B (lane = (hit, light) pair): light sample + shadow ray, 8 lights at a time
+      // -- step B (lane = (hit, light) pair): light sample + shadow ray, DRT_PAIR_LIGHTS lights at a time; a pair lane
+      //    fetches its hit's point from the hit lane by shuffle
       for (int l0 = 0; l0 < P.n_lights; l0 += DRT_PAIR_LIGHTS) {
         const int nl = min(DRT_PAIR_LIGHTS, P.n_lights - l0);
-        for (int pid = lane; pid < take * nl; pid += 32) {
-          const int lj = pid / take, hh = pid - lj * take;              // light-major: one pass of the warp heads for one light
-          const PairIn<R> pin = pairin[hh];
-          if (pin.want) shadowPair<R, COUNT>(P, gb, pin, l0 + lj, pairout[lj * 32 + hh], cnt);   // lanes write neighbours
+        for (int p0 = 0; p0 < take * nl; p0 += 32) {
+          const int pid = p0 + lane;
+          const bool on = pid < take * nl;
+          const int lj = on ? pid / take : 0, hh = on ? pid - lj * take : 0;   // light-major: one pass of the warp heads for one light
+          PairIn<R> q;
+          q.isectP = mk<R>(__shfl_sync(FULL, pin.isectP.x, hh), __shfl_sync(FULL, pin.isectP.y, hh), __shfl_sync(FULL, pin.isectP.z, hh));
+          q.path = __shfl_sync(FULL, pin.path, hh); q.val = __shfl_sync(FULL, pin.val, hh); q.dt = __shfl_sync(FULL, pin.dt, hh);
+          q.want = __shfl_sync(FULL, pin.want, hh);
+          if (on && q.want) shadowPair<R, COUNT>(P, gb, q, l0 + lj, pairout, lj * 32 + hh, cnt);
         }
         __syncwarp();
         // -- step C (lane = hit again): texture + BRDF of the unoccluded lights, in light order
-        if (active && !aborted && S.lights) shadeB<R, COUNT>(P, S, pairout + lane, l0, l0 + nl, cnt);
+        if (active && !aborted && S.lights) shadeB<R, COUNT>(P, S, pairout, lane, l0, l0 + nl, cnt);
         __syncwarp();
       }
       if (active) {
