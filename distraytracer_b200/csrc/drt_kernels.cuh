@@ -72,6 +72,22 @@ __device__ __forceinline__ void storeRecord(T* dst, const T& src) {
 #endif
 }
 
+// The CTA ray pool is stored as planes of 16-byte words: word w of ray i lives at plane w, slot i.  Warps pop and
+// push runs of neighbouring slots, so every load / store instruction of a warp covers 512 contiguous bytes (whole
+// sectors) instead of 32 half-used sectors at a 64-byte stride.
+template <typename T>
+__device__ __forceinline__ void poolLoad(T& dst, const uint4* planes, const size_t cap, const int i) {
+  uint4* d = reinterpret_cast<uint4*>(&dst);
+#pragma unroll
+  for (int w = 0; w < (int)(sizeof(T) / 16); w++) d[w] = __ldcs(planes + w * cap + i);
+}
+template <typename T>
+__device__ __forceinline__ void poolStore(uint4* planes, const size_t cap, const int i, const T& src) {
+  const uint4* q = reinterpret_cast<const uint4*>(&src);
+#pragma unroll
+  for (int w = 0; w < (int)(sizeof(T) / 16); w++) __stcs(planes + w * cap + i, q[w]);
+}
+
 template <typename R>
 struct Moved {           // per-trace displacement state (motion blur)
   float val;             // reference mode: y shift of "rectangle" shapes
@@ -1267,7 +1283,7 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, tid = threadIdx.x;
   char* cbase = (char*)P.pool_raw + (size_t)blockIdx.x * waveScratchBytes<R>(P.pool_cap);
-  Task<R>* pool = (Task<R>*)cbase;
+  uint4* pool = (uint4*)cbase;                                         // planes of 16-byte words, see poolLoad
   HitTask<R>* hits = (HitTask<R>*)(cbase + (size_t)P.pool_cap * sizeof(Task<R>));
   char* wbase = (char*)(hits + DRT_CTA_HITS) + (size_t)wib * pairOutBytes<R>();
   PairOut<R> pairout;
@@ -1309,7 +1325,7 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
               float frame_sample = (float)((double)(float)P.frame + (double)rng_u01(skey, (uint32_t)m) * (double)P.frame_range);
               T.dt = frame_sample - (float)P.frame;
               T.path = rng_key_child(skey, 1 + m);
-              pool[at + m] = T;                                         // <= DRT_CTA_SLOTS * blur_samples, validated on the host
+              poolStore(pool, (size_t)P.pool_cap, at + m, T);                                         // <= DRT_CTA_SLOTS * blur_samples, validated on the host
             }
           }
           if (tid == 0) s_state = 2;
@@ -1367,7 +1383,7 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
           primaryRay<R>(P, P.sample_base + i0 + s2, T.org, T.dir, skey, pi, pj, px, py);
           T.k = 1.0f; T.path = rng_key_child(skey, 0); T.dt = 0.f; T.depth = (unsigned char)P.max_depth;
           T.bits = TASK_CHAIN | TASK_ROOT; T.slot = (unsigned short)s2;
-          pool[s2] = T;
+          poolStore(pool, (size_t)P.pool_cap, s2, T);
           if (COUNT) cnt.samples++;
         }
         if (tid == 0) s_count = nv;
@@ -1390,7 +1406,7 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
       bool hit = false;
       HitTask<R> H;
       if (active) {
-        loadRecord(H.T, &pool[end - 1 - lane]);
+        poolLoad(H.T, pool, (size_t)P.pool_cap, end - 1 - lane);
         const unsigned int f = ((volatile unsigned int*)sfl)[H.T.slot];
         if (!(f & SF_ABORT)) {                                          // an aborted sample spawns no more work (Q15)
           HitRec h; int motion;
@@ -1525,7 +1541,7 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
         int base = pbase;
 #pragma unroll
         for (int j = 0; j < DRT_MAX_CHILDREN; j++) {
-          if (nk > j) storeRecord(&pool[base + __popc(kb[j] & ((1u << lane) - 1u))], kids[j]);
+          if (nk > j) poolStore(pool, (size_t)P.pool_cap, base + __popc(kb[j] & ((1u << lane) - 1u)), kids[j]);
           base += __popc(kb[j]);
         }
       }
