@@ -1425,7 +1425,7 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
       hbase = __shfl_sync(FULL, hbase, 0);
       if (hit) {
         const int at = hbase + __popc(hm & ((1u << lane) - 1u));
-        storeRecord(&hits[at], H);
+        poolStore((uint4*)hits, (size_t)DRT_CTA_HITS, at, H);
         s_hkey[at] = (unsigned char)min(H.geom, DRT_HIT_BUCKETS - 1);
       }
     }
@@ -1481,7 +1481,7 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
       PairIn<R> pin; pin.want = 0; pin.isectP = mk<R>(R(0), R(0), R(0)); pin.path = 0u; pin.val = 0.f; pin.dt = 0.f;
       if (active) {
         HitTask<R> H;
-        loadRecord(H, &hits[s_order[end - 1 - lane]]);
+        poolLoad(H, (const uint4*)hits, (size_t)DRT_CTA_HITS, (int)s_order[end - 1 - lane]);
         HitRec h; h.t = H.t; h.geom = H.geom; h.inside = H.inside; h.checker_sel = H.checker_sel;
         slot = H.T.slot;
         shadeA<R, COUNT>(P, H.T, h, kids, nk, add, has_add, aborted, S, cnt);
