@@ -75,17 +75,23 @@ __device__ __forceinline__ void storeRecord(T* dst, const T& src) {
 // The CTA ray pool is stored as planes of 16-byte words: word w of ray i lives at plane w, slot i.  Warps pop and
 // push runs of neighbouring slots, so every load / store instruction of a warp covers 512 contiguous bytes (whole
 // sectors) instead of 32 half-used sectors at a 64-byte stride.
+// stores keep the record in the L2 under the normal policy (it is read back within a pass or two), the one load
+// marks it evict-first; neither allocates in the L1
+#ifndef DRT_POOL_LD
+#define DRT_POOL_LD __ldcs
+#define DRT_POOL_ST __stcg
+#endif
 template <typename T>
 __device__ __forceinline__ void poolLoad(T& dst, const uint4* planes, const size_t cap, const int i) {
   uint4* d = reinterpret_cast<uint4*>(&dst);
 #pragma unroll
-  for (int w = 0; w < (int)(sizeof(T) / 16); w++) d[w] = __ldcs(planes + w * cap + i);
+  for (int w = 0; w < (int)(sizeof(T) / 16); w++) d[w] = DRT_POOL_LD(planes + w * cap + i);
 }
 template <typename T>
 __device__ __forceinline__ void poolStore(uint4* planes, const size_t cap, const int i, const T& src) {
   const uint4* q = reinterpret_cast<const uint4*>(&src);
 #pragma unroll
-  for (int w = 0; w < (int)(sizeof(T) / 16); w++) __stcs(planes + w * cap + i, q[w]);
+  for (int w = 0; w < (int)(sizeof(T) / 16); w++) DRT_POOL_ST(planes + w * cap + i, q[w]);
 }
 
 template <typename R>
