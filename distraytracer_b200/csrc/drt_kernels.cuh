@@ -43,38 +43,10 @@ struct alignas(16) Task {
 #define TASK_ROOT 2
 static_assert(sizeof(Task<double>) == 64 && sizeof(Task<float>) == 48, "ray records are whole 16-byte words");
 
-// Ray-pool and hit-buffer records are written once and read once: stream them past the L1 (ld/st.global.cs), which
-// is better spent on the geom / material records and the local-memory frames every ray keeps coming back to.
-#ifndef DRT_STREAM_RECORDS
-#define DRT_STREAM_RECORDS 1
-#endif
-template <typename T>
-__device__ __forceinline__ void loadRecord(T& dst, const T* src) {
-  static_assert(sizeof(T) % 16 == 0, "records are whole 16-byte words");
-#if DRT_STREAM_RECORDS
-  uint4* d = reinterpret_cast<uint4*>(&dst);
-  const uint4* q = reinterpret_cast<const uint4*>(src);
-#pragma unroll
-  for (int i = 0; i < (int)(sizeof(T) / 16); i++) d[i] = __ldcs(q + i);
-#else
-  dst = *src;
-#endif
-}
-template <typename T>
-__device__ __forceinline__ void storeRecord(T* dst, const T& src) {
-#if DRT_STREAM_RECORDS
-  uint4* d = reinterpret_cast<uint4*>(dst);
-  const uint4* q = reinterpret_cast<const uint4*>(&src);
-#pragma unroll
-  for (int i = 0; i < (int)(sizeof(T) / 16); i++) __stcs(d + i, q[i]);
-#else
-  *dst = src;
-#endif
-}
-
-// The CTA ray pool is stored as planes of 16-byte words: word w of ray i lives at plane w, slot i.  Warps pop and
-// push runs of neighbouring slots, so every load / store instruction of a warp covers 512 contiguous bytes (whole
-// sectors) instead of 32 half-used sectors at a 64-byte stride.
+// The CTA ray pool and hit buffer are stored as planes of 16-byte words: word w of record i lives at plane w, slot i.
+// Warps pop and push runs of neighbouring slots, so every load / store instruction of a warp covers 512 contiguous
+// bytes (whole sectors) instead of 32 half-used sectors at a 64-byte stride.  The records are written once and read
+// once, so they bypass the L1, which is better spent on the geom / material records and the local-memory frames.
 // stores keep the record in the L2 under the normal policy (it is read back within a pass or two), the one load
 // marks it evict-first; neither allocates in the L1
 #ifndef DRT_POOL_LD
