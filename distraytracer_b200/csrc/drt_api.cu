@@ -14,6 +14,7 @@
 #include "drt_launch.h"
 #include "drt_bvh_order.h"
 #include "drt_mesh.h"
+#include "drt_skeleton.h"
 
 using namespace drt;
 
@@ -745,6 +746,86 @@ void drt_scene_destroy(drt_scene* s) {
   if (s->ev1) cudaEventDestroy(s->ev1);
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
+}
+
+// ---- mocap skeletons: parse + device forward kinematics live in drt_skeleton.cu ------------
+struct drt_skeleton { drt::Skeleton* impl = nullptr; };
+
+int drt_skeleton_create(const char* asf_text, size_t asf_len, const char* amc_text, size_t amc_len, double scale, int device,
+                        drt_skeleton** out) {
+  if (!out) return fail(DRT_ERR_INVALID, "null argument");
+  drt::Skeleton* impl = nullptr;
+  const int rc = skeletonCreate(asf_text, asf_len, amc_text, amc_len, scale, device, &impl);
+  if (rc) return fail(rc, skeletonError());
+  *out = new drt_skeleton();
+  (*out)->impl = impl;
+  return DRT_OK;
+}
+
+int drt_skeleton_load(const char* asf_path, const char* amc_path, double scale, int device, drt_skeleton** out) {
+  if (!asf_path || !amc_path) return fail(DRT_ERR_INVALID, "null argument");
+  std::string text[2];
+  const char* paths[2] = {asf_path, amc_path};
+  for (int i = 0; i < 2; i++) {
+    FILE* f = fopen(paths[i], "rb");
+    if (!f) return fail(DRT_ERR_INVALID, std::string("cannot open ") + paths[i]);   // the reference throws 1 (skeleton.cpp:575-577)
+    char buf[65536]; size_t n;
+    while ((n = fread(buf, 1, sizeof(buf), f)) > 0) text[i].append(buf, n);
+    fclose(f);
+  }
+  return drt_skeleton_create(text[0].data(), text[0].size(), text[1].data(), text[1].size(), scale, device, out);
+}
+
+int drt_skeleton_info(const drt_skeleton* skel, int32_t* n_cylinders, int32_t* n_frames, float* fk_ms) {
+  if (!skel || !skel->impl) return fail(DRT_ERR_INVALID, "null skeleton");
+  if (n_cylinders) *n_cylinders = skeletonCylinders(skel->impl);
+  if (n_frames) *n_frames = skeletonFrames(skel->impl);
+  if (fk_ms) *fk_ms = skeletonFkMs(skel->impl);
+  return DRT_OK;
+}
+
+int drt_skeleton_bones(const drt_skeleton* skel, int32_t frame0, int32_t n_frames, double* out) {
+  if (!skel || !skel->impl) return fail(DRT_ERR_INVALID, "null skeleton");
+  const int rc = skeletonReadBones(skel->impl, frame0, n_frames, out);
+  return rc ? fail(rc, skeletonError()) : DRT_OK;
+}
+
+int drt_scene_pose_skeleton(drt_scene* s, const drt_skeleton* skel, int32_t frame, int32_t first_prim, double drop_y,
+                            int32_t set_velocity) {
+  if (!s || !skel || !skel->impl) return fail(DRT_ERR_INVALID, "null argument");
+  if (frame < 0) return fail(DRT_ERR_INVALID, "frameIndex is illegal");                      // scene.h:111-115
+  const int nc = skeletonCylinders(skel->impl), nf = skeletonFrames(skel->impl);
+  if (first_prim < 0 || first_prim + nc > (int)s->prims.size()) return fail(DRT_ERR_INVALID, "bone cylinders outside the scene's primitives");
+  for (int k = 0; k < nc; k++)
+    if (s->prims[first_prim + k].type != DRT_PRIM_CYLINDER) return fail(DRT_ERR_INVALID, "primitive to re-pose is not a cylinder");
+  const int f0 = std::min(frame, nf - 1), f1 = std::min(f0 + 1, nf - 1);                     // scene.h:117-121
+  const double* tab = skeletonHostTable(skel->impl);
+  CK(cudaSetDevice(s->device));
+  CK(cudaStreamSynchronize(s->stream));
+  const std::vector<drt_prim> before = s->prims;
+  for (int k = 0; k < nc; k++) {
+    drt_prim& p = s->prims[first_prim + k];
+    const double* a = tab + ((size_t)f0 * nc + k) * 6;
+    const double* b = tab + ((size_t)f1 * nc + k) * 6;
+    double c1[3], c2[3], n1[3], n2[3];
+    for (int i = 0; i < 3; i++) { c1[i] = a[i]; c2[i] = a[3 + i]; n1[i] = b[i]; n2[i] = b[3 + i]; }
+    if (drop_y != 0.0) { c1[1] -= drop_y; c2[1] -= drop_y; n1[1] -= drop_y; n2[1] -= drop_y; }   // scene.h:646-650
+    for (int i = 0; i < 3; i++) {
+      p.c1[i] = c1[i]; p.c2[i] = c2[i];
+      p.center[i] = (c1[i] + c2[i]) / 2;
+      p.velocity[i] = set_velocity ? ((n1[i] + n2[i]) - (c1[i] + c2[i])) / 2 : 0.0;
+    }
+    if (set_velocity) p.flags |= DRT_FLAG_MOTION;
+  }
+  const int rc = flattenAndUpload(s);
+  if (rc) s->prims = before;
+  return rc;
+}
+
+void drt_skeleton_destroy(drt_skeleton* skel) {
+  if (!skel) return;
+  skeletonDestroy(skel->impl);
+  delete skel;
 }
 
 int drt_render(const drt_scene* scene, const drt_settings* settings, const drt_tile* tile, uint8_t* out_rgb, drt_counters* counters) {

@@ -18,6 +18,8 @@ EXPORTS = [
     "drt_scene_update_lights",
     "drt_scene_destroy", "drt_render", "drt_render_float", "drt_render_device", "drt_write_ppm", "drt_last_error",
     "drt_abi_sizes", "drt_debug_rng", "drt_debug_candidate_order",
+    "drt_skeleton_create", "drt_skeleton_load", "drt_skeleton_info", "drt_skeleton_bones", "drt_scene_pose_skeleton",
+    "drt_skeleton_destroy",
 ]
 
 
@@ -52,6 +54,13 @@ def lib():
         L.drt_debug_rng.argtypes = [C.c_uint32] * 5
         L.drt_debug_rng.restype = C.c_float
         L.drt_debug_candidate_order.argtypes = [C.POINTER(abi.Prim), C.c_int32, C.POINTER(C.c_int32), C.c_int32]
+        L.drt_skeleton_create.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_double, C.c_int, C.POINTER(C.c_void_p)]
+        L.drt_skeleton_load.argtypes = [C.c_char_p, C.c_char_p, C.c_double, C.c_int, C.POINTER(C.c_void_p)]
+        L.drt_skeleton_info.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_float)]
+        L.drt_skeleton_bones.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+        L.drt_scene_pose_skeleton.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_int32]
+        L.drt_skeleton_destroy.argtypes = [C.c_void_p]
+        L.drt_skeleton_destroy.restype = None
         _lib = L
     return _lib
 
@@ -102,6 +111,11 @@ class DeviceScene:
         arr = (abi.Light * max(1, len(lights)))(*lights)
         _check(lib().drt_scene_update_lights(self.handle, arr, len(lights)))
 
+    def pose_skeleton(self, skeleton, frame, first_prim, drop_y=0.0, set_velocity=True):
+        """drt_scene_pose_skeleton: bone cylinders prims[first_prim...] take the pose of mocap frame `frame`."""
+        _check(lib().drt_scene_pose_skeleton(self.handle, skeleton.handle, int(frame), int(first_prim), float(drop_y),
+                                             int(bool(set_velocity))))
+
     def _tile(self, settings, tile):
         if tile is None:
             return abi.Tile(0, 0, settings.xRes, settings.yRes, self.device)
@@ -128,6 +142,38 @@ class DeviceScene:
         tile = self._tile(settings, tile)
         _check(lib().drt_render_device(self.handle, C.byref(settings), C.byref(tile),
                                        C.byref(counters) if counters is not None else None))
+
+
+MOCAP_SCALE = 0.06   # types.h:6
+
+
+class DeviceSkeleton:
+    """drt_skeleton handle: an ASF/AMC clip posed for all frames on one GPU (table of bone cylinders in HBM)."""
+
+    def __init__(self, asf, amc, scale=MOCAP_SCALE, device=0):
+        """`asf` / `amc`: file contents as bytes, or paths (str)."""
+        self.handle = C.c_void_p()
+        if isinstance(asf, str) and isinstance(amc, str):
+            _check(lib().drt_skeleton_load(asf.encode(), amc.encode(), scale, device, C.byref(self.handle)))
+        else:
+            _check(lib().drt_skeleton_create(asf, len(asf), amc, len(amc), scale, device, C.byref(self.handle)))
+        nc, nf, ms = C.c_int32(), C.c_int32(), C.c_float()
+        _check(lib().drt_skeleton_info(self.handle, C.byref(nc), C.byref(nf), C.byref(ms)))
+        self.n_cylinders, self.n_frames, self.fk_ms = nc.value, nf.value, ms.value
+
+    def bones(self, frame0=0, n_frames=None):
+        """(n_frames, n_cylinders, 2, 3) float64 end points, copied from the device table."""
+        n = self.n_frames - frame0 if n_frames is None else n_frames
+        out = np.empty((n, self.n_cylinders, 2, 3), dtype=np.float64)
+        _check(lib().drt_skeleton_bones(self.handle, int(frame0), int(n), out.ctypes.data))
+        return out
+
+    def close(self):
+        if getattr(self, "handle", None):
+            lib().drt_skeleton_destroy(self.handle)
+            self.handle = None
+
+    __del__ = close
 
 
 def write_ppm(path, rgb):

@@ -291,6 +291,37 @@ int drt_scene_update_prims(drt_scene* scene, const drt_prim* prims, int32_t n_pr
 int drt_scene_update_lights(drt_scene* scene, const drt_light* lights, int32_t n_lights);
 void drt_scene_destroy(drt_scene* scene);
 
+/* ---- mocap skeletons (BASELINE config 4) ------------------------------------------------
+ * ASF skeleton + AMC motion -> bone cylinders, for every frame of the clip at once, on the
+ * device.  Replaces the host-side chain the reference runs per rendered frame:
+ *   Skeleton(asf, scale) / Motion(amc, scale, skeleton)    skeleton.cpp:545-590, motion.cpp:28-38
+ *   setSkeletonsToSpecifiedFrame(frame)                    scene.h:109-128
+ *   DisplaySkeleton::ComputeBonePositions                  displaySkeleton.cpp:229-270
+ *   rotations/scalings/translations/lengths -> end points  scene.h:616-659
+ * `scale` is MOCAP_SCALE (types.h:6, 0.06).  The table of end points stays in HBM; results
+ * are bit-identical to the reference's. */
+typedef struct drt_skeleton drt_skeleton;
+
+int drt_skeleton_create(const char* asf_text, size_t asf_len, const char* amc_text, size_t amc_len,
+                        double scale, int device, drt_skeleton** out);
+/* Same, reading the two files (the reference opens "90.asf" / "90_16_v3.amc",
+ * render_final_project.cpp main). */
+int drt_skeleton_load(const char* asf_path, const char* amc_path, double scale, int device, drt_skeleton** out);
+/* n_cylinders = bones without the root (the reference skips bone 0, scene.h:631-633);
+ * fk_ms = device time of the forward-kinematics kernel over the whole clip.  Any output may be NULL. */
+int drt_skeleton_info(const drt_skeleton* skel, int32_t* n_cylinders, int32_t* n_frames, float* fk_ms);
+/* Copies frames [frame0, frame0+n_frames) of the device table to `out`:
+ * n_frames * n_cylinders * 6 doubles (left x,y,z, right x,y,z per bone). */
+int drt_skeleton_bones(const drt_skeleton* skel, int32_t frame0, int32_t n_frames, double* out);
+/* Re-pose the n_cylinders DRT_PRIM_CYLINDER primitives prims[first_prim ...] of `scene` to mocap
+ * frame `frame` (clamped to the last frame like scene.h:117-121; negative is an error like
+ * scene.h:111-115) and re-upload the scene.  Every end point is lowered by `drop_y`
+ * (scene.h:646-650 drops the figure by frame-frame_cloud).  With set_velocity != 0 each
+ * cylinder also gets drt_prim.velocity = its displacement to frame+1 (DRT_BLUR_VELOCITY). */
+int drt_scene_pose_skeleton(drt_scene* scene, const drt_skeleton* skel, int32_t frame, int32_t first_prim,
+                            double drop_y, int32_t set_velocity);
+void drt_skeleton_destroy(drt_skeleton* skel);
+
 /* Render `tile` of the frame into `out_rgb`: a tightly packed HOST buffer of
  * tile.width*tile.height*3 bytes laid out like the PPM payload writePPM emits
  * (helpers.h:174-195): rows top to bottom (row 0 of the buffer is loop row

@@ -210,3 +210,35 @@ def compare(a_f32, b_f32):
     d = np.abs(qa - qb).max(axis=-1)
     return {"frac_within_1": float((d <= 1).mean()), "max": int(d.max()), "mae": float(np.abs(qa - qb).mean()),
             "n_bad": int((d > 1).sum())}
+
+
+class SkeletonOracle:
+    """oracle/drt_skeleton_oracle.cpp: CPU restatement of the reference's ASF/AMC parse + forward kinematics."""
+
+    def __init__(self, asf_bytes, amc_bytes, scale=0.06):
+        L = self.lib = C.CDLL(ORACLE_SO)
+        L.drt_oracle_skeleton_error.restype = C.c_char_p
+        L.drt_oracle_skeleton_create.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_double, C.POINTER(C.c_void_p)]
+        L.drt_oracle_skeleton_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.drt_oracle_skeleton_bones.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.drt_oracle_skeleton_destroy.argtypes = [C.c_void_p]
+        L.drt_oracle_skeleton_destroy.restype = None
+        self.handle = C.c_void_p()
+        if L.drt_oracle_skeleton_create(asf_bytes, len(asf_bytes), amc_bytes, len(amc_bytes), scale, C.byref(self.handle)) != 0:
+            raise RuntimeError("skeleton oracle: " + L.drt_oracle_skeleton_error().decode())
+        nc, nf = C.c_int(), C.c_int()
+        L.drt_oracle_skeleton_info(self.handle, C.byref(nc), C.byref(nf))
+        self.n_cylinders, self.n_frames = nc.value, nf.value
+
+    def bones(self, frame):
+        out = np.empty((self.n_cylinders, 2, 3), dtype=np.float64)
+        if self.lib.drt_oracle_skeleton_bones(self.handle, int(frame), out.ctypes.data) < 0:
+            raise RuntimeError("skeleton oracle: " + self.lib.drt_oracle_skeleton_error().decode())
+        return out
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.drt_oracle_skeleton_destroy(self.handle)
+            self.handle = None
+
+    __del__ = close

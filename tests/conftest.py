@@ -24,8 +24,8 @@ def pytest_configure(config):
 def oracle_lib():
     """Build (if needed) and return the path of oracle/liboracle.so -- the checker, never the product."""
     so = os.path.join(ROOT, "oracle", "liboracle.so")
-    src = os.path.join(ROOT, "oracle", "drt_oracle.cpp")
-    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    srcs = [os.path.join(ROOT, "oracle", f) for f in ("drt_oracle.cpp", "drt_skeleton_oracle.cpp")]
+    if not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(src) for src in srcs):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "liboracle.so"])
     return so
 

@@ -71,6 +71,17 @@ def main():
     bones = np.stack([r.mocap_bones(f) for f in range(120)])
     np.save(os.path.join(OUT, "mocap_bones_0_119.npy"), bones.astype(np.float64))
     print("mocap bones", bones.shape)
+    # the clip itself for the ASF/AMC ingest tests: the skeleton file and the first 121 frames of the motion
+    # (3 header lines + 121 x 30 lines), copied as DATA fixtures
+    from oracle.harness import REFERENCE_ROOT
+    with open(os.path.join(REFERENCE_ROOT, "90.asf"), "rb") as f:
+        asf = f.read()
+    with open(os.path.join(REFERENCE_ROOT, "90_16_v3.amc"), "rb") as f:
+        amc_lines = f.read().split(b"\n")
+    with open(os.path.join(OUT, "mocap_90.asf"), "wb") as f:
+        f.write(asf)
+    with open(os.path.join(OUT, "mocap_90_16_first121.amc"), "wb") as f:
+        f.write(b"\n".join(amc_lines[:3 + 121 * 30]) + b"\n")
 
     # value-noise known answers (noise.h) through the reference's renderImageCloud
     r.reset()
