@@ -575,6 +575,57 @@ inline int renderVideo(int first, int last, const std::function<void(float)>& po
   return written;
 }
 
+// ---- mocap: the `displayer` / `skeleton` / `motion` globals of render_final_project.cpp --------------------
+// The reference loads "90.asf" / "90_16_v3.amc" once in main(), then every build*() function calls
+// setSkeletonsToSpecifiedFrame(int(frame)) + displayer.ComputeBonePositions() and turns the per-bone
+// rotation / scaling / translation / length into cylinder end points (scene.h:109-128, 616-644, 3560-3610).
+// Here the clip is posed for ALL frames on the GPU when it is loaded (drt_skeleton_create, kernel skeleton_fk);
+// a builder asks for the end points of a frame and constructs its Cylinders as before:
+//     Mocap mocap("90.asf", "90_16_v3.amc");
+//     mocap.setSkeletonsToSpecifiedFrame(int(frame));
+//     for (int x = 1; x < mocap.totalBones(); x++)
+//       shapes.push_back(make_shared<Cylinder>(mocap.leftVertex(x), mocap.rightVertex(x), 0.05, VEC3(1,0,0)));
+constexpr double MOCAP_SCALE = 0.06;            // types.h:6
+
+class Mocap {
+ public:
+  Mocap(const std::string& asf_path, const std::string& amc_path, double scale = MOCAP_SCALE, int device = 0) {
+    if (drt_skeleton_load(asf_path.c_str(), amc_path.c_str(), scale, device, &skel_) != DRT_OK)
+      throw std::runtime_error(drt_last_error());            // the reference throws 1 (skeleton.cpp:575-577)
+    int32_t nc = 0, nf = 0;
+    drt_skeleton_info(skel_, &nc, &nf, &fk_ms_);
+    cylinders_ = nc; frames_ = nf;
+    table_.resize((size_t)nf * nc * 6);
+    if (drt_skeleton_bones(skel_, 0, nf, table_.data()) != DRT_OK) throw std::runtime_error(drt_last_error());
+  }
+  ~Mocap() { drt_skeleton_destroy(skel_); }
+  Mocap(const Mocap&) = delete;
+  Mocap& operator=(const Mocap&) = delete;
+  int GetNumFrames() const { return frames_; }               // Motion::GetNumFrames
+  int totalBones() const { return cylinders_ + 1; }          // rotations.size(): bone 0 is the origin and is skipped
+  float fkMilliseconds() const { return fk_ms_; }
+  const drt_skeleton* handle() const { return skel_; }
+  // scene.h:109-128: clamps past the last frame, a negative index is fatal
+  void setSkeletonsToSpecifiedFrame(int frameIndex) {
+    if (frameIndex < 0) throw std::runtime_error("Error in SetSkeletonsToSpecifiedFrame: frameIndex is illegal.");
+    frame_ = frameIndex >= frames_ ? frames_ - 1 : frameIndex;
+  }
+  // end points of bone x (1 <= x < totalBones()) at the current frame: what
+  // rotation * scaling * (0,0,0|length,1) + translation evaluates to (scene.h:637-644)
+  VEC3 leftVertex(int x) const { const double* p = at(x); return VEC3(p[0], p[1], p[2]); }
+  VEC3 rightVertex(int x) const { const double* p = at(x); return VEC3(p[3], p[4], p[5]); }
+
+ private:
+  const double* at(int x) const {
+    if (x < 1 || x > cylinders_) throw std::out_of_range("bone index");
+    return &table_[((size_t)frame_ * cylinders_ + (x - 1)) * 6];
+  }
+  drt_skeleton* skel_ = nullptr;
+  int cylinders_ = 0, frames_ = 0, frame_ = 0;
+  float fk_ms_ = 0;
+  std::vector<double> table_;
+};
+
 }  // namespace host
 }  // namespace drt
 #endif

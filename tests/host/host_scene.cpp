@@ -45,6 +45,25 @@ static void buildSceneReflectance(float framef) {
   g.lights.push_back(make_shared<pointLight>(light_center, VEC3(1, 1, 1)));
 }
 
+// The mocap part of buildSceneChkpt2 (scene.h:3557-3625): bone cylinders of int(frame) + the checkerboard floor,
+// lit by a point light (the reference's two orbiting sphere lights are not needed for what this checks).
+static Mocap* g_mocap = nullptr;
+static void buildSceneMocap(float frame) {
+  Globals& g = globals();
+  g_mocap->setSkeletonsToSpecifiedFrame(int(frame));
+  g.shapes.clear(); g.lights.clear();
+  float min_y = 0.251897;
+  for (int x = 1; x < g_mocap->totalBones(); x++)
+    g.shapes.push_back(make_shared<Cylinder>(g_mocap->leftVertex(x), g_mocap->rightVertex(x), 0.05, VEC3(1, 0, 0)));
+  min_y = min_y + 0.05;
+  float s = 1;
+  VEC3 checker_rgb0(0.58, 0.82, 1), checker_rgb1(1, 0.416, 0.835);
+  g.shapes.push_back(make_shared<Checkerboard>(VEC3(-6, min_y, -6), VEC3(-6, min_y, 6), VEC3(6, min_y, 6), VEC3(6, min_y, -6),
+                                               checker_rgb0, checker_rgb1, s));
+  g.lights.push_back(make_shared<pointLight>(VEC3(-3, 4, 2), VEC3(1, 1, 1)));
+  g.eye = VEC3(-6, 0.5, 1) + (VEC3(0.49, 10, 1) - VEC3(-6, 0.5, 1)) * (float)(frame / 320);
+}
+
 // host_scene mesh <in.obj> <out.bin>: loadObj + setMesh (column transform of scene.h:296-299), dumps the
 // unified arrays: int64 n_vertices, n_triangles, has_uv; float vertices[3V]; int32 indices[3T]; float texcoords[2V]
 static int meshMode(const std::string& in, const std::string& out) {
@@ -76,6 +95,13 @@ int main(int argc, char** argv) {
   if (getenv("DRT_HOST_BLOCKS")) { g.always_blocks = true; g.block_rows = atoi(getenv("DRT_HOST_BLOCKS")); }
   int frame = 0;
   std::function<void(float)> builder;
+  std::unique_ptr<Mocap> mocap;
+  if (scene == "mocap") {       // host_scene dump|render|video mocap <out> <asf> <amc>   (needs a GPU: the clip is posed on the device)
+    if (argc < 6) return 2;
+    try { mocap.reset(new Mocap(argv[4], argv[5])); } catch (const std::exception& e) { fprintf(stderr, "host_scene: %s\n", e.what()); return 1; }
+    g_mocap = mocap.get();
+    g.antialias_samples = 4; frame = 30; builder = buildSceneMocap;
+  } else
   if (scene == "hw4") { g.antialias_samples = 1; builder = buildSceneHW4; }
   else if (scene == "reflectance") { g.antialias_samples = 4; frame = 40; builder = buildSceneReflectance; }
   else return 2;
@@ -92,7 +118,8 @@ int main(int argc, char** argv) {
       o.write((const char*)&st, sizeof(st));
     } else if (mode == "video") {
       // frames 40..43 of the moving-light animation, `out` is a prefix: <out>.0040.ppm ...
-      const int n = renderVideo(40, 44, builder, [&](int f) { char b[32]; snprintf(b, sizeof(b), ".%04d.ppm", f); return out + b; });
+      const int f0 = scene == "mocap" ? 30 : 40;
+      const int n = renderVideo(f0, f0 + 4, builder, [&](int f) { char b[32]; snprintf(b, sizeof(b), ".%04d.ppm", f); return out + b; });
       if (n != 4) return 1;
     } else {
       renderImage(out, frame, builder);

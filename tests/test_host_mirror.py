@@ -102,3 +102,31 @@ def test_renderFrame_in_row_blocks_is_the_same_picture(host_bin, tmp_path):
     subprocess.check_call([host_bin, "render", "reflectance", a])
     subprocess.check_call([host_bin, "render", "reflectance", b], env=dict(os.environ, DRT_HOST_BLOCKS="7"))
     assert np.array_equal(read_ppm(a), read_ppm(b))
+
+
+@pytest.mark.gpu
+def test_mocap_through_host_mirror(host_bin, tmp_path):
+    """ASF/AMC -> device forward kinematics -> Cylinder constructors of the C++ mirror: the flattened bone cylinders and
+    floor are byte for byte what the reference's buildSceneChkpt2 exported (fixture chkpt2_mocap, frame 30), and the
+    mocap video loop writes the frames renderImage would."""
+    from distraytracer_b200 import abi
+    from oracle.harness import read_ppm
+    from conftest import GOLDEN
+    clip = [os.path.join(GOLDEN, "mocap_90.asf"), os.path.join(GOLDEN, "mocap_90_16_first121.amc")]
+    out = str(tmp_path / "dump.bin")
+    subprocess.check_call([host_bin, "dump", "mocap", out] + clip)
+    raw = open(out, "rb").read()
+    n_prims, n_lights = np.frombuffer(raw[:8], dtype=np.int32)
+    sz = C.sizeof(abi.Prim)
+    prims = [raw[8 + i * sz: 8 + (i + 1) * sz] for i in range(n_prims)]
+    ref_scene, _, _ = load_case("chkpt2_mocap")
+    assert n_prims == 31 and len(ref_scene.prims) == 33        # the fixture also holds the two sphere lights
+    for a, b in zip(prims, ref_scene.prims[:31]):
+        assert a == bytes(b)
+    prefix = str(tmp_path / "vid")
+    subprocess.check_call([host_bin, "video", "mocap", prefix] + clip)
+    single = str(tmp_path / "single.ppm")
+    subprocess.check_call([host_bin, "render", "mocap", single] + clip)
+    frames = [read_ppm(prefix + ".%04d.ppm" % f) for f in range(30, 34)]
+    assert np.array_equal(frames[0], read_ppm(single))
+    assert any(not np.array_equal(frames[0], f) for f in frames[1:])             # the figure moves
