@@ -66,17 +66,6 @@ __device__ __forceinline__ void poolStore(uint4* planes, const size_t cap, const
   for (int w = 0; w < (int)(sizeof(T) / 16); w++) DRT_POOL_ST(planes + w * cap + i, q[w]);
 }
 
-// A popped ray / a shaded hit is dead, but its L2 line is dirty: left alone, every record pushed is eventually written
-// back to HBM (ncu: ~100 GB of DRAM writes per frame = the bytes pushed) and the dead lines crowd the live ones out of
-// the L2.  discard.global.L2 drops a 128-byte line without the write-back.  Only whole lines of dead records are
-// discarded: TRACE pops chunks whose boundaries are multiples of 8 records (8 x 16-byte words = one line per plane).
-#ifndef DRT_DISCARD
-#define DRT_DISCARD 3
-#endif
-__device__ __forceinline__ void l2Discard128(const void* p) {
-  asm volatile("discard.global.L2 [%0], 128;" ::"l"(__cvta_generic_to_global(p)) : "memory");
-}
-
 template <typename R>
 struct Moved {           // per-trace displacement state (motion blur)
   float val;             // reference mode: y shift of "rectangle" shapes
@@ -1382,9 +1371,7 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
 
     // ================= TRACE: closest hits; the HITS are compacted into the hit buffer ====
     // (rays that miss are finished: they only update the in_motion chain flag)
-    const int npool = s_count;                                           // CTA-uniform (barrier above)
-    __syncthreads();
-    if (tid == 0) s_grab = (DRT_DISCARD & 1) ? ((npool + 7) & ~7) : npool;     // chunk boundaries on whole 128-byte lines
+    if (tid == 0) s_grab = s_count;
     __syncthreads();
     for (;;) {
       if (((volatile int*)&s_nhits)[0] >= DRT_TRACE_HITS_TARGET) break;  // enough hits for a full SHADE pass are waiting
@@ -1392,7 +1379,8 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
       if (lane == 0) end = atomicSub(&s_grab, 32);
       end = __shfl_sync(FULL, end, 0);
       if (end <= 0) break;
-      const bool active = end - 1 - lane >= 0 && end - 1 - lane < npool;
+      const int begin = max(end - 32, 0);
+      const bool active = begin + lane < end;
       bool hit = false;
       HitTask<R> H;
       if (active) {
@@ -1410,12 +1398,6 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
         }
       }
       const unsigned int hm = __ballot_sync(FULL, hit);
-      if (DRT_DISCARD & 1) {
-        // the chunk's records have been consumed by every lane (the ballot follows their use): drop its lines
-        constexpr int W = (int)(sizeof(Task<R>) / 16);
-        const int w = lane >> 2, first = end - 32 + 8 * (lane & 3);
-        if (w < W && first >= 0) l2Discard128(pool + (size_t)w * P.pool_cap + first);
-      }
       int hbase = 0;
       if (lane == 0 && hm) hbase = atomicAdd(&s_nhits, __popc(hm));
       hbase = __shfl_sync(FULL, hbase, 0);
@@ -1427,7 +1409,7 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
     }
     __syncthreads();
     const int nh = s_nhits;
-    if (tid == 0) { s_count = min(max(s_grab, 0), npool); s_grab = nh; } // untouched rays stay at the bottom of the pool
+    if (tid == 0) { s_count = max(s_grab, 0); s_grab = nh; }             // untouched rays stay at the bottom of the pool
     // ---- counting sort of the waiting hits by geom: the 32 hits a warp shades together then share
     // the material / model / texture branches of shadeA, evalBRDF and shadeB, and their shadow rays
     // leave from the same surface
@@ -1543,14 +1525,6 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
       }
     }
     __syncthreads();
-    if (DRT_DISCARD & 2) {                                               // every waiting hit has been shaded: the hit buffer is dead
-      constexpr int W = (int)(sizeof(HitTask<R>) / 16);
-      const int lines = (nh + 7) >> 3;
-      for (int i = tid; i < lines * W; i += blockDim.x) {
-        const int w = i / lines, l = i - w * lines;
-        l2Discard128((const uint4*)hits + (size_t)w * DRT_CTA_HITS + 8 * l);
-      }
-    }
     if (tid == 0) s_nhits = 0;
     __syncthreads();
   }
