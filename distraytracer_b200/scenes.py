@@ -249,12 +249,16 @@ def mesh_to_prims(mesh):
 
 
 def config5(n=708, xres=3840, yres=2160, spp=64):
-    """BASELINE config 5: textured ~1M-triangle terrain, DOF + point light at the eye, 4K 64 spp."""
+    """BASELINE config 5: textured ~1M-triangle terrain, DOF + motion blur (a moving sphere over the static mesh,
+    blur_samples 2) + point light at the eye, 4K 64 spp."""
     base, settings, _ = load_fixture(os.path.join(GOLDEN, "checkertexture.npz"))
     mesh = terrain_mesh(n)
     mesh["material"] = mesh_material(tex_frame=2)            # textures/floor.jpeg of the fixture
-    prims = [sphere((0.0, 1.6, 0.0), 0.7, (1.0, 0.2, 0.2))]
+    ball = sphere((0.0, 1.6, 0.0), 0.7, (1.0, 0.2, 0.2), motion=True)
+    _v(ball.velocity, (0.6, 0.0, 0.25))
+    prims = [ball]
     s = abi.copy_struct(settings)
+    s.blur_mode, s.blur_samples, s.frame_range = abi.BLUR_VELOCITY, 2, 1
     s.eye[:] = [0.0, 7.0, 9.0]; s.lookingAt[:] = [0.0, 0.0, 0.0]; s.up[:] = [0, 1, 0]
     s.xRes, s.yRes, s.antialias_samples, s.aperture, s.focal_length = xres, yres, spp, 0.2, 10.0
     lights = [point_light(tuple(s.eye), (1.0, 1.0, 1.0))]
