@@ -250,6 +250,7 @@ struct Globals {
   int devices = 0;   // 0 = all visible GPUs
   int block_rows = 30;   // multi-GPU single frames: rows per dynamically claimed block (renderFrame)
   bool always_blocks = false;   // cut into blocks even on one GPU (tests)
+  int streams_per_gpu = 2;      // renderFrame: scene handles per GPU when the frame is cut into blocks
   // optional indexed triangle mesh (what loadObj + the scene builders' triangle loop produce, scene.h:296-386),
   // kept as arrays and traversed through the device-built LBVH instead of 10^6 Triangle shapes
   std::vector<float> mesh_vertices, mesh_texcoords;
@@ -387,20 +388,26 @@ inline void renderFrame(int frame, std::vector<uint8_t>& rgb) {
   const int rows = (ndev == 1 && !g.always_blocks) ? st.yRes : std::max(1, std::min(g.block_rows, st.yRes));   // one GPU: one launch sequence
   const int n_blocks = (st.yRes + rows - 1) / rows;
   if (ndev > n_blocks) ndev = n_blocks;
+  // Two scene handles (streams) per GPU when the frame is cut: render_wave is a persistent kernel whose last batches
+  // drain with few warps busy; with a second stream the SMs a finished block frees start on the next block at once
+  // (measured: a 1080p 64 spp frame in 36 blocks on one GPU 248.7 ms with one stream, 208.1 ms with two; whole frame 210).
+  const int per_dev = (n_blocks > ndev) ? std::max(1, g.streams_per_gpu) : 1;
+  const int nth = ndev * per_dev;
   rgb.assign((size_t)st.xRes * st.yRes * 3, 0);
-  std::vector<std::string> errs(ndev);
+  std::vector<std::string> errs(nth);
   std::atomic<int> next{0};
   std::vector<std::thread> th;
-  for (int d = 0; d < ndev; d++)
-    th.emplace_back([&, d]() {
+  for (int w = 0; w < nth; w++)
+    th.emplace_back([&, w]() {
+      const int d = w / per_dev;
       drt_scene* sc = nullptr;
-      if (drt_scene_create(&f.desc, d, &sc) != DRT_OK) { errs[d] = drt_last_error(); return; }
+      if (drt_scene_create(&f.desc, d, &sc) != DRT_OK) { errs[w] = drt_last_error(); return; }
       for (int b = next.fetch_add(1); b < n_blocks; b = next.fetch_add(1)) {
         // loop rows [y0,y1) of block b; buffer row 0 of the block is loop row y1-1
         const int y0 = b * rows, y1 = std::min(st.yRes, y0 + rows);
         drt_tile tile{0, y0, st.xRes, y1 - y0, d};
         uint8_t* dst = rgb.data() + (size_t)(st.yRes - y1) * st.xRes * 3;
-        if (drt_render(sc, &st, &tile, dst, nullptr) != DRT_OK) { errs[d] = drt_last_error(); break; }
+        if (drt_render(sc, &st, &tile, dst, nullptr) != DRT_OK) { errs[w] = drt_last_error(); break; }
       }
       drt_scene_destroy(sc);
     });

@@ -57,6 +57,7 @@ def main():
     ap.add_argument("config", nargs="?", default="c5")
     ap.add_argument("--rows", type=int, default=30)
     ap.add_argument("--gpus", type=int, default=0)
+    ap.add_argument("--streams", type=int, default=2, help="scene handles (streams) per GPU: the drain of one block overlaps the ramp of the next")
     args = ap.parse_args()
     scene, st = {"c2": scenes.config2, "c3": scenes.config3, "c5": scenes.config5}[args.config]()
     n = args.gpus or runtime.device_count()
@@ -64,14 +65,14 @@ def main():
     samples = st.xRes * st.yRes * spp
     import torch
     frame = torch.empty((st.yRes, st.xRes, 3), dtype=torch.uint8).pin_memory().numpy()
-    devs = [runtime.DeviceScene(scene, d) for d in range(n)]
+    devs = [runtime.DeviceScene(scene, d) for d in range(n) for _ in range(args.streams)]   # GPU-major
     ref = None
     for use in ([1, n] if n > 1 else [1]):
-        frame_on(devs[:use], st, args.rows, frame)                      # warm-up (scratch allocation, clocks)
-        dt = min(frame_on(devs[:use], st, args.rows, frame) for _ in range(2))
+        frame_on(devs[:use * args.streams], st, args.rows, frame)       # warm-up (scratch allocation, clocks)
+        dt = min(frame_on(devs[:use * args.streams], st, args.rows, frame) for _ in range(2))
         if use == 1:
             ref = frame.copy(); t1 = dt
-        print(json.dumps({"config": args.config, "res": [st.xRes, st.yRes], "spp": spp, "gpus": use, "rows_per_block": args.rows,
+        print(json.dumps({"config": args.config, "res": [st.xRes, st.yRes], "spp": spp, "gpus": use, "streams_per_gpu": args.streams, "rows_per_block": args.rows,
                           "ms_per_frame": 1e3 * dt, "frames_per_s": 1 / dt, "Msamples_per_s": samples / dt / 1e6,
                           "speedup_vs_1gpu": t1 / dt, "same_image_as_1gpu": bool(np.array_equal(ref, frame))}), flush=True)
 
