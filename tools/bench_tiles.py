@@ -5,7 +5,7 @@ counter -- sky rows and object rows differ in cost by orders of magnitude -- and
 place in the pinned host frame.  The scene is replicated; there is no collective.  The same partition is what
 drt_host.h::renderFrame does in C++.  Wall clock around the whole frame, after one warm-up frame, for 1 GPU and for all.
 
-  python tools/bench_tiles.py [c2|c3|c5] [--rows 30] [--gpus N]
+  python tools/bench_tiles.py [c2|c3|c5] [--rows 15] [--streams 2] [--gpus N]
 """
 import argparse
 import json
@@ -55,7 +55,7 @@ def frame_on(devs, st, rows, frame):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("config", nargs="?", default="c5")
-    ap.add_argument("--rows", type=int, default=30)
+    ap.add_argument("--rows", type=int, default=15)
     ap.add_argument("--gpus", type=int, default=0)
     ap.add_argument("--streams", type=int, default=2, help="scene handles (streams) per GPU: the drain of one block overlaps the ramp of the next")
     args = ap.parse_args()
