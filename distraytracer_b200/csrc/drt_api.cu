@@ -822,6 +822,12 @@ int drt_scene_pose_skeleton(drt_scene* s, const drt_skeleton* skel, int32_t fram
   return rc;
 }
 
+int drt_debug_skeleton_parse(const char* asf_text, size_t asf_len, const char* amc_text, size_t amc_len, double scale,
+                             int32_t* n_bones, int32_t* n_frames, int32_t* parents, int32_t* dofs, int32_t cap) {
+  const int rc = skeletonParseInfo(asf_text, asf_len, amc_text, amc_len, scale, n_bones, n_frames, parents, dofs, cap);
+  return rc ? fail(rc, skeletonError()) : DRT_OK;
+}
+
 void drt_skeleton_destroy(drt_skeleton* skel) {
   if (!skel) return;
   skeletonDestroy(skel->impl);

@@ -157,7 +157,7 @@ struct Tokens {           // lines -> words; the reference splits on ' ' for dof
     auto flush = [&]() {
       if (!line.empty() && line.back() == '\r') line.pop_back();
       std::vector<std::string> w; std::string cur;
-      for (char ch : line) { if (ch == ' ' || ch == '\t') { if (!cur.empty()) w.push_back(cur); cur.clear(); } else cur.push_back(ch); }
+      for (char ch : line) { if (ch == ' ' || ch == '\t' || ch == '\r') { if (!cur.empty()) w.push_back(cur); cur.clear(); } else cur.push_back(ch); }
       if (!cur.empty()) w.push_back(cur);
       rows.push_back(w); line.clear();
     };
@@ -310,6 +310,28 @@ struct Skeleton {
 };
 
 const std::string& skeletonError() { return g_skel_err; }
+
+// Host half only (no device needed): structure of the parsed clip, for bindings and tests.
+int skeletonParseInfo(const char* asf, size_t asf_len, const char* amc, size_t amc_len, double scale, int* n_bones, int* n_frames,
+                      int* parents, int* dofs, int cap) {
+  std::string& err = g_skel_err;
+  if (!asf || !amc) { err = "null argument"; return DRT_ERR_INVALID; }
+  std::vector<BoneH> bones;
+  int rc = parseAsf(asf, asf_len, scale, bones, err);
+  if (rc) return rc;
+  int nf = 0;
+  std::vector<double> rot, trans;
+  rc = parseAmc(amc, amc_len, scale, bones, nf, rot, trans, err);
+  if (rc) return rc;
+  if (n_bones) *n_bones = (int)bones.size();
+  if (n_frames) *n_frames = nf;
+  for (int i = 0; i < (int)bones.size() && i < cap; i++) {
+    if (parents) parents[i] = bones[i].parent;
+    if (dofs) dofs[i] = (bones[i].rot[0] ? DOF_RX : 0) | (bones[i].rot[1] ? DOF_RY : 0) | (bones[i].rot[2] ? DOF_RZ : 0) |
+                        (bones[i].trans[0] ? DOF_TX : 0) | (bones[i].trans[1] ? DOF_TY : 0) | (bones[i].trans[2] ? DOF_TZ : 0);
+  }
+  return DRT_OK;
+}
 
 int skeletonCreate(const char* asf, size_t asf_len, const char* amc, size_t amc_len, double scale, int device, Skeleton** out) {
   std::string& err = g_skel_err;

@@ -13,5 +13,8 @@ int skeletonFrames(const Skeleton* s);
 float skeletonFkMs(const Skeleton* s);             // device time of the forward-kinematics kernel (CUDA events)
 const double* skeletonHostTable(const Skeleton* s);   // [frame][cylinder][6], copied back from the device table once
 int skeletonReadBones(const Skeleton* s, int frame0, int n, double* out);   // device table -> host
+// parse only (host): bone count incl. the root, frame count, parent index and DOF bit mask (rx ry rz tx ty tz = bits 0..5) per bone
+int skeletonParseInfo(const char* asf, size_t asf_len, const char* amc, size_t amc_len, double scale, int* n_bones, int* n_frames,
+                      int* parents, int* dofs, int cap);
 const std::string& skeletonError();
 }  // namespace drt

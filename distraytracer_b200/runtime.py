@@ -19,7 +19,7 @@ EXPORTS = [
     "drt_scene_destroy", "drt_render", "drt_render_float", "drt_render_device", "drt_write_ppm", "drt_last_error",
     "drt_abi_sizes", "drt_debug_rng", "drt_debug_candidate_order",
     "drt_skeleton_create", "drt_skeleton_load", "drt_skeleton_info", "drt_skeleton_bones", "drt_scene_pose_skeleton",
-    "drt_skeleton_destroy",
+    "drt_skeleton_destroy", "drt_debug_skeleton_parse",
 ]
 
 
@@ -59,6 +59,8 @@ def lib():
         L.drt_skeleton_info.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_float)]
         L.drt_skeleton_bones.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
         L.drt_scene_pose_skeleton.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_int32]
+        L.drt_debug_skeleton_parse.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_double, C.POINTER(C.c_int32),
+                                               C.POINTER(C.c_int32), C.c_void_p, C.c_void_p, C.c_int32]
         L.drt_skeleton_destroy.argtypes = [C.c_void_p]
         L.drt_skeleton_destroy.restype = None
         _lib = L
@@ -145,6 +147,15 @@ class DeviceScene:
 
 
 MOCAP_SCALE = 0.06   # types.h:6
+
+
+def parse_skeleton(asf, amc, scale=MOCAP_SCALE):
+    """Host half of the mocap ingest (no GPU): (n_bones incl. root, n_frames, parents[int32], dofs[int32 bit masks])."""
+    nb, nf = C.c_int32(), C.c_int32()
+    parents = np.full(256, -2, dtype=np.int32); dofs = np.zeros(256, dtype=np.int32)
+    _check(lib().drt_debug_skeleton_parse(asf, len(asf), amc, len(amc), scale, C.byref(nb), C.byref(nf),
+                                          parents.ctypes.data, dofs.ctypes.data, 256))
+    return nb.value, nf.value, parents[:nb.value].copy(), dofs[:nb.value].copy()
 
 
 class DeviceSkeleton:

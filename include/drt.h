@@ -358,6 +358,11 @@ float drt_debug_rng(uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t chi
 /* Primitive indices in the candidate order the library derives from its host-side replay of the
  * reference's generateBVH (helpers.h:381-472); ties of t between shapes resolve in this order. */
 int drt_debug_candidate_order(const drt_prim* prims, int32_t n_prims, int32_t* out, int32_t cap);
+/* Host half of drt_skeleton_create only (needs no device): bone count including the root, frame count
+ * ((non-empty lines - 3) / (moving bones + 1), motion.cpp:113-121), and per bone (up to `cap`) the parent index
+ * (-1 for the root) and the degrees of freedom as bits rx ry rz tx ty tz = 1 2 4 8 16 32 (skeleton.cpp:207-231). */
+int drt_debug_skeleton_parse(const char* asf_text, size_t asf_len, const char* amc_text, size_t amc_len, double scale,
+                             int32_t* n_bones, int32_t* n_frames, int32_t* parents, int32_t* dofs, int32_t cap);
 
 #ifdef __cplusplus
 }

@@ -407,6 +407,17 @@ int drt_oracle_skeleton_info(const drt_oracle_skeleton* s, int* n_cylinders, int
   *n_cylinders = s->sk.num_bones - 1; *n_frames = s->sk.n_frames; return 0;
 }
 
+// parent index and DOF bits (rx ry rz tx ty tz = 1 2 4 8 16 32) per bone, root included
+int drt_oracle_skeleton_structure(const drt_oracle_skeleton* s, int* parents, int* dofs, int cap) {
+  const Skel& sk = s->sk;
+  for (int i = 0; i < sk.num_bones && i < cap; i++) {
+    const Bone& b = sk.bones[i];
+    parents[i] = b.parent;
+    dofs[i] = (b.dofr[0] ? 1 : 0) | (b.dofr[1] ? 2 : 0) | (b.dofr[2] ? 4 : 0) | (b.doft[0] ? 8 : 0) | (b.doft[1] ? 16 : 0) | (b.doft[2] ? 32 : 0);
+  }
+  return sk.num_bones;
+}
+
 // end points of the bone cylinders of `frame`: 6 doubles per bone (left xyz, right xyz)
 int drt_oracle_skeleton_bones(drt_oracle_skeleton* s, int frame, double* out) {
   if (frame < 0) { g_err = "frameIndex is illegal"; return -1; }             // scene.h:111-115

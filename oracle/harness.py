@@ -221,6 +221,7 @@ class SkeletonOracle:
         L.drt_oracle_skeleton_create.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_double, C.POINTER(C.c_void_p)]
         L.drt_oracle_skeleton_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.drt_oracle_skeleton_bones.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.drt_oracle_skeleton_structure.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.drt_oracle_skeleton_destroy.argtypes = [C.c_void_p]
         L.drt_oracle_skeleton_destroy.restype = None
         self.handle = C.c_void_p()
@@ -229,6 +230,11 @@ class SkeletonOracle:
         nc, nf = C.c_int(), C.c_int()
         L.drt_oracle_skeleton_info(self.handle, C.byref(nc), C.byref(nf))
         self.n_cylinders, self.n_frames = nc.value, nf.value
+
+    def structure(self):
+        parents = np.full(256, -2, dtype=np.int32); dofs = np.zeros(256, dtype=np.int32)
+        n = self.lib.drt_oracle_skeleton_structure(self.handle, parents.ctypes.data_as(C.c_void_p), dofs.ctypes.data_as(C.c_void_p), 256)
+        return parents[:n].copy(), dofs[:n].copy()
 
     def bones(self, frame):
         out = np.empty((self.n_cylinders, 2, 3), dtype=np.float64)

@@ -139,3 +139,76 @@ def test_cuda_skeleton_rejects_malformed_clips():
         runtime.DeviceSkeleton(asf, b":FULLY-SPECIFIED\n:DEGREES\n")
     with pytest.raises(runtime.DrtError):
         runtime.DeviceSkeleton("/nonexistent.asf", "/nonexistent.amc")
+
+
+def _force_3dof(lines):
+    """The clip re-written as a :FORCE-ALL-JOINTS-BE-3DOF file: every moving joint carries three rotations, the ones
+    the skeleton does not declare appended as zeros (the order enableAllRotationalDOFs gives them)."""
+    out = [lines[0], lines[1], b":FORCE-ALL-JOINTS-BE-3DOF", lines[2]]
+    for ln in lines[3:3 + 121 * 30]:
+        w = ln.split()
+        if len(w) > 1 and w[0] != b"root":
+            w += [b"0"] * (3 - (len(w) - 1))
+        out.append(b" ".join(w))
+    return b"\n".join(out) + b"\n"
+
+
+def _variants():
+    asf, amc = _clip()                      # 90.asf has CRLF line ends, the .amc LF
+    lines = amc.split(b"\n")
+    asf_lf = asf.replace(b"\r\n", b"\n")
+    assert asf_lf != asf
+    return {
+        "fixture": (asf, amc),
+        "lf": (asf_lf, amc),
+        "crlf": (asf, amc.replace(b"\n", b"\r\n")),                                            # both written on Windows (removeCR)
+        "force3dof": (asf, _force_3dof(lines)),                                                  # skeleton.cpp:467-499
+        "truncated": (asf, b"\n".join(lines[:3 + 100 * 30 + 7]) + b"\n"),                         # 100 whole frames + 7 stray lines
+        # a blank line re-runs the previous keyword on an empty string (sscanf leaves `keyword` alone): harmless after "begin"
+        # (after "end" the reference would start a phantom bone and index out of bounds; the library rejects that)
+        "blank_lines": (asf_lf.replace(b"  begin\n", b"  begin\n\n"), amc),                               # sscanf keeps the last keyword
+    }
+
+
+@pytest.mark.parametrize("name", ["fixture", "lf", "crlf", "force3dof", "truncated", "blank_lines"])
+def test_host_parser_agrees_with_the_oracle_on_structure(oracle_lib, name):
+    """The library's host-side ASF/AMC parser (no GPU needed) and the oracle's agree on bones, hierarchy, degrees of
+    freedom and the reference's frame-count formula, for the fixture clip and for awkward spellings of it."""
+    from distraytracer_b200 import runtime
+    from oracle.harness import SkeletonOracle
+    asf, amc = _variants()[name]
+    nb, nf, parents, dofs = runtime.parse_skeleton(asf, amc)
+    orc = SkeletonOracle(asf, amc)
+    op, od = orc.structure()
+    assert (nb, nf) == (orc.n_cylinders + 1, orc.n_frames)
+    assert np.array_equal(parents, op) and np.array_equal(dofs, od)
+    assert nb == 31 and parents[0] == -1 and (parents[1:] >= 0).all()
+    assert nf == {"truncated": 100}.get(name, 121)         # force3dof: (4 + 121*30 - 3) // 30 is still 121
+    if name == "force3dof":
+        assert all((d & 7) == 7 for d in dofs if d)        # every moving bone has all three rotations
+    else:
+        assert dofs[0] == 63 and dofs[3] == 1               # root: 6 DOF; ltibia: rx only
+
+
+def test_host_parser_rejects_malformed_clips():
+    from distraytracer_b200 import runtime, abi
+    asf, amc = _clip()
+    for bad_asf, bad_amc in [(b"no bone data here\n", amc), (asf.replace(b"lfemur ltibia", b"lfemur nosuchbone"), amc),
+                             (asf, amc.replace(b"lowerback", b"lowerbach", 1)), (asf, b":FULLY-SPECIFIED\n:DEGREES\n"),
+                             (asf.replace(b"    lfemur ltibia\r\n", b""), amc),
+                             (asf.replace(b"  end\r\n", b"  end\r\n\r\n", 1), amc)]:          # phantom bone after a blank line          # ltibia (and its subtree) detached from the root
+        with pytest.raises(runtime.DrtError) as e:
+            runtime.parse_skeleton(bad_asf, bad_amc)
+        assert e.value.code == abi.ERR_INVALID
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["lf", "crlf", "force3dof", "truncated", "blank_lines"])
+def test_cuda_fk_matches_oracle_on_awkward_clips(oracle_lib, name):
+    from distraytracer_b200 import runtime
+    from oracle.harness import SkeletonOracle
+    asf, amc = _variants()[name]
+    dev = runtime.DeviceSkeleton(asf, amc)
+    orc = SkeletonOracle(asf, amc)
+    assert dev.n_frames == orc.n_frames
+    assert np.array_equal(dev.bones(), np.stack([orc.bones(f) for f in range(orc.n_frames)]))
