@@ -35,6 +35,50 @@ def place_band(frame_rgb, band_rgb, y0, y1):
     frame_rgb[yres - y1: yres - y0] = band_rgb
 
 
+def row_blocks(yres, rows):
+    """Single frame, dynamic partition: loop-row ranges [(y0, y1), ...] of at most `rows` rows, bottom to top."""
+    rows = max(1, int(rows))
+    return [(y0, min(y0 + rows, yres)) for y0 in range(0, yres, rows)]
+
+
+def render_frame_blocks(handles, settings, frame_rgb, rows=15):
+    """Render one frame on several GPUs: one host thread per handle claims row blocks from a shared counter and
+    renders each block straight into its place in `frame_rgb` ((yRes, xRes, 3) uint8, PPM row order; pinned memory
+    makes the device-to-host copies asynchronous).  `handles` are runtime.DeviceScene objects of the SAME scene --
+    pass two per GPU: render_wave is a persistent kernel whose last batches drain with few warps busy, and a second
+    stream lets the SMs a finished block frees start on the next block at once.  ctypes releases the GIL inside
+    drt_render, so the threads overlap.  This is drt_host.h::renderFrame in Python.  Returns the wall-clock seconds."""
+    import threading
+    import time
+    yres, xres = settings.yRes, settings.xRes
+    if frame_rgb.shape != (yres, xres, 3):
+        raise ValueError("frame_rgb must be (yRes, xRes, 3)")
+    blocks = row_blocks(yres, rows)
+    nxt, lock, errs = [0], threading.Lock(), []
+
+    def work(h):
+        try:
+            while True:
+                with lock:
+                    k = nxt[0]; nxt[0] += 1
+                if k >= len(blocks):
+                    return
+                y0, y1 = blocks[k]
+                h.render(settings, abi.Tile(0, y0, xres, y1 - y0, h.device), out=frame_rgb[yres - y1: yres - y0])
+        except Exception as e:      # noqa: BLE001  (re-raised on the caller's thread)
+            errs.append(e)
+
+    threads = [threading.Thread(target=work, args=(h,)) for h in handles]
+    t0 = time.perf_counter()
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errs:
+        raise errs[0]
+    return time.perf_counter() - t0
+
+
 def max_over_ranks(value, dist=None, device=None):
     """Timing contract of bench.py: the slowest rank defines the step time."""
     if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:

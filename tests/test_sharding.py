@@ -54,3 +54,39 @@ def test_bands_and_tiles_cover_the_frame():
     frame = np.zeros((8, 4, 3), dtype=np.uint8)
     shard.place_band(frame, np.full((3, 4, 3), 7, dtype=np.uint8), 2, 5)    # loop rows 2..4 -> PPM rows 3..5
     assert (frame[3:6] == 7).all() and frame[:3].sum() == 0 and frame[6:].sum() == 0
+
+
+def test_render_frame_blocks_places_every_block_once():
+    """The dynamic single-frame partition (host threads claiming row blocks) with stand-in renderers: every row is
+    rendered exactly once, lands at its PPM position whatever handle claimed it, and errors surface on the caller."""
+    import threading
+    from distraytracer_b200 import shard, abi
+
+    class Fake:
+        def __init__(self, device, fail_at=None):
+            self.device, self.fail_at, self.calls = device, fail_at, []
+
+        def render(self, settings, tile, out=None):
+            assert tile.device == self.device and tile.x0 == 0 and tile.width == settings.xRes
+            assert out.shape == (tile.height, settings.xRes, 3)
+            if self.fail_at is not None and tile.y0 >= self.fail_at:
+                raise RuntimeError("boom")
+            self.calls.append((tile.y0, tile.height))
+            for r in range(tile.height):                      # buffer row r of a tile is loop row y0 + height - 1 - r
+                out[r] += np.uint8(1 + (tile.y0 + tile.height - 1 - r) % 200)
+            return out
+
+    st = abi.Settings(); st.xRes, st.yRes = 16, 101
+    assert shard.row_blocks(101, 15)[-1] == (90, 101) and len(shard.row_blocks(101, 15)) == 7
+    frame = np.zeros((101, 16, 3), dtype=np.uint8)
+    handles = [Fake(d) for d in (0, 0, 1, 1, 2)]
+    dt = shard.render_frame_blocks(handles, st, frame, rows=15)
+    assert dt >= 0 and sum(len(h.calls) for h in handles) == 7
+    want = np.array([1 + (101 - 1 - y) % 200 for y in range(101)], dtype=np.uint8)   # PPM row y is loop row yRes-1-y
+    assert (frame == want[:, None, None]).all()
+    import pytest
+    with pytest.raises(RuntimeError):
+        shard.render_frame_blocks([Fake(0, fail_at=30)], st, frame, rows=15)
+    with pytest.raises(ValueError):
+        shard.render_frame_blocks(handles, st, np.zeros((5, 5, 3), dtype=np.uint8))
+    assert threading.active_count() >= 1

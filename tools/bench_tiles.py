@@ -11,7 +11,6 @@ import argparse
 import json
 import os
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -21,35 +20,7 @@ from distraytracer_b200 import runtime, abi, scenes, shard  # noqa: E402
 
 
 def frame_on(devs, st, rows, frame):
-    yres = st.yRes
-    blocks = [(y0, min(y0 + rows, yres)) for y0 in range(0, yres, rows)]
-    nxt = [0]
-    lock = threading.Lock()
-    errs = []
-
-    def work(dev):
-        try:
-            while True:
-                with lock:
-                    k = nxt[0]; nxt[0] += 1
-                if k >= len(blocks):
-                    return
-                y0, y1 = blocks[k]
-                out = frame[yres - y1: yres - y0]                       # PPM row order (shard.place_band)
-                dev.render(st, abi.Tile(0, y0, st.xRes, y1 - y0, dev.device), out=out)
-        except Exception as e:                                          # noqa: BLE001
-            errs.append(e)
-
-    th = [threading.Thread(target=work, args=(d,)) for d in devs]
-    t0 = time.perf_counter()
-    for t in th:
-        t.start()
-    for t in th:
-        t.join()
-    dt = time.perf_counter() - t0
-    if errs:
-        raise errs[0]
-    return dt
+    return shard.render_frame_blocks(devs, st, frame, rows)
 
 
 def main():
