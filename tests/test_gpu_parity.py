@@ -299,3 +299,33 @@ def test_update_lights_equals_a_fresh_scene(oracle_lib):
     a1 = dev.render(s)
     b1 = _gpu(Scene(scene.prims, lights, scene.textures)).render(s)
     assert np.array_equal(a1, b1) and not np.array_equal(a0, a1)
+
+
+@pytest.mark.gpu
+def test_out_of_scope_inputs_are_rejected_not_rendered(oracle_lib):
+    """What the hot path does not cover fails loudly with DRT_ERR_UNSUPPORTED (never a silent approximation): primitive
+    classes outside drt_prim_type (RectPrism / RectPrismWithCylinder / RectPrismWithHoles), a textured
+    sphere (GeoPrimitive::getUV has no body, geometry.h:36), recursion deeper than 32, more glossy lobes than the ray
+    pool is sized for."""
+    from distraytracer_b200 import abi, runtime
+    from distraytracer_b200.scene import Scene
+    scene, settings, _ = load_case("checkertexture")
+    prims = [abi.copy_struct(p) for p in scene.prims]
+    prims[0].type = abi.PRIM_TYPE_COUNT                     # e.g. a RectPrismWithCylinder
+    with pytest.raises(runtime.DrtError) as e:
+        runtime.DeviceScene(Scene(prims, scene.lights, scene.textures), 0)
+    assert e.value.code == abi.ERR_UNSUPPORTED
+    prims = [abi.copy_struct(p) for p in scene.prims]
+    ball = next(p for p in prims if p.type == abi.PRIM_SPHERE)
+    ball.flags |= abi.FLAG_TEXTURE; ball.tex_frame = 0
+    with pytest.raises(runtime.DrtError) as e:
+        runtime.DeviceScene(Scene(prims, scene.lights, scene.textures), 0)
+    assert e.value.code == abi.ERR_UNSUPPORTED
+    dev = _gpu(scene)
+    for field, value in (("max_depth", 33), ("brdf_samples", 7), ("blur_samples", 65)):
+        s = abi.copy_struct(settings)
+        s.xRes, s.yRes = 32, 24
+        setattr(s, field, value)
+        with pytest.raises(runtime.DrtError) as e:
+            dev.render(s)
+        assert e.value.code == abi.ERR_UNSUPPORTED, field

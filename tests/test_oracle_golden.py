@@ -49,3 +49,21 @@ def test_value_noise_known_answers(oracle_lib):
     vals = [o.value_noise(0.1, 0.2, 0.3), o.value_noise(-3.7, 12.25, 100.5), o.value_noise(5.0, 5.0, 5.0)]
     assert all(np.isfinite(v) and abs(v) < 2.0 for v in vals)
     assert len({round(v, 9) for v in vals}) == 3
+
+
+def test_oracle_rejects_what_the_path_does_not_cover(oracle_lib):
+    """The checker refuses the same out-of-scope inputs the library refuses (geometry.h:36)."""
+    from distraytracer_b200 import abi
+    from distraytracer_b200.scene import Scene
+    from oracle.harness import Oracle
+    from conftest import load_case
+    scene, _, _ = load_case("checkertexture")
+    prims = [abi.copy_struct(p) for p in scene.prims]
+    prims[0].type = abi.PRIM_TYPE_COUNT
+    with pytest.raises(RuntimeError, match="unknown primitive type"):
+        Oracle(Scene(prims, scene.lights, scene.textures))
+    prims = [abi.copy_struct(p) for p in scene.prims]
+    ball = next(p for p in prims if p.type == abi.PRIM_SPHERE)
+    ball.flags |= abi.FLAG_TEXTURE; ball.tex_frame = 0
+    with pytest.raises(RuntimeError, match="getUV"):
+        Oracle(Scene(prims, scene.lights, scene.textures))
