@@ -329,13 +329,13 @@ def run_ours(args):
         # algorithmic bytes per frame: 16 B sample record written by render_samples and read once by
         # resolve, plus the 3 B/pixel frame (the scene itself lives in L1/L2)
         alg_bytes = samples_per_step * 32 + frame_bytes
-        # dram__bytes_read.sum + dram__bytes_write.sum of the two render_wave launches of one step, from the ncu launch
-        # list of this same command (profiles/r1_launches_dram_bench_final.csv): 91.13+98.91 GB and 7.14+23.69 GB.
+        # dram__bytes_read.sum + dram__bytes_write.sum of the render_wave launch of one step, from the ncu launch list of
+        # this same command (profiles/r1_launches_dram_bench_one_launch.csv): 64.44 GB read + 146.65 GB written.
         # The excess over the algorithmic bytes is the CTA ray pools and hit buffers (64 B per pushed ray, 80 B per hit,
         # each written once and read once, streamed with .cs): with 8192-hit passes the 148 CTAs' working set (~350 MB)
         # exceeds the L2.
-        wave_launches_per_step = 2
-        measured_traffic = (91130186496 + 98913068032 + 7140624128 + 23686555904) // wave_launches_per_step
+        wave_launches_per_step = max(1, launches // max(1, args.steps) // 2)     # render_wave + resolve per row chunk
+        measured_traffic = (64438689536 + 146654461952) // wave_launches_per_step
         fp64_peak = props.multi_processor_count * 64 * 2 * sm_mhz * 1e6 / 1e12     # TFLOP/s at the observed clock
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -351,7 +351,7 @@ def run_ours(args):
                          "frac": alg_bytes / step_s / 1e9 / hbm_peak, "traffic": measured_traffic,
                          "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                          "launches_per_step": wave_launches_per_step,
-                         "note": "kernel render_wave<double>, 2 launches per step (row chunks of <= 2^26 samples): achieved = algorithmic bytes of a step / device time of a step (= per-launch bytes / mean launch time), traffic = mean DRAM bytes per launch (ncu). The path is issue/latency bound in the FP64+ALU pipes, not HBM bound: see roofline_fp; traffic = ray-pool and hit-buffer spill, 1.0 TB/s"},
+                         "note": "kernel render_wave<double>, one launch per step (a frame fits one row chunk of <= 2^28 samples): achieved = algorithmic bytes of the launch / its device time (CUDA events on the library's stream; resolve is 0.5 ms of the 207), traffic = DRAM bytes of the launch (ncu). The path is issue/latency bound in the FP64+ALU pipes, not HBM bound: see roofline_fp; traffic = ray-pool and hit-buffer spill, 1.0 TB/s"},
             "fp32_variant": fp32_info,
             "roofline_fp": {"bound": "fp64_pipe", "achieved": ops / step_s / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
                             "frac": ops / step_s / 1e12 / fp64_peak,

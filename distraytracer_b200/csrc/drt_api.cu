@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -495,8 +496,15 @@ int ensureScratch(drt_scene* s, size_t n_samples, size_t n_corners, size_t n_out
   return DRT_OK;
 }
 
-// samples held in HBM at once: 2^26 float4 = 1 GiB
-const long long kMaxChunkSamples = 1ll << 26;
+// Samples held in HBM at once: 2^28 float4 = 4 GiB, so that a 1080p 64 spp frame (132.7 M samples) is ONE launch of the
+// persistent kernel -- every extra launch pays one more drain (the last batches finish with few warps busy) and ramp.
+// DRT_CHUNK_LOG2 overrides the bound (tuning / tests of the multi-chunk path).
+long long maxChunkSamples() {
+  const char* e = getenv("DRT_CHUNK_LOG2");
+  int b = e ? atoi(e) : 28;
+  b = std::max(12, std::min(30, b));
+  return 1ll << b;
+}
 
 template <typename R>
 int launchAll(drt_scene* s, const DevScene<R>& ds, const drt_settings& st, const CameraD& cam, const drt_tile& tile, int pool_cap,
@@ -505,7 +513,7 @@ int launchAll(drt_scene* s, const DevScene<R>& ds, const drt_settings& st, const
   fillParams<R>(P, s, ds, st, cam, tile);
   const bool collect = counters && counters->collect;
   const long long per_row = (long long)tile.width * P.spp;
-  int rows_per_chunk = st.cloud_only ? tile.height : (int)std::max<long long>(1, std::min<long long>(tile.height, kMaxChunkSamples / std::max<long long>(1, per_row)));
+  int rows_per_chunk = st.cloud_only ? tile.height : (int)std::max<long long>(1, std::min<long long>(tile.height, maxChunkSamples() / std::max<long long>(1, per_row)));
   const size_t n_corners = (size_t)(tile.width + 1) * (tile.height + 1);
   int rc = ensureScratch(s, st.cloud_only ? 1 : (size_t)rows_per_chunk * per_row, n_corners, (size_t)tile.width * tile.height * 3);
   if (rc) return rc;

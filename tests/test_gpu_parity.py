@@ -329,3 +329,24 @@ def test_out_of_scope_inputs_are_rejected_not_rendered(oracle_lib):
         with pytest.raises(runtime.DrtError) as e:
             dev.render(s)
         assert e.value.code == abi.ERR_UNSUPPORTED, field
+
+
+@pytest.mark.gpu
+def test_row_chunking_does_not_change_the_image(oracle_lib):
+    """A frame larger than the per-launch sample bound is rendered in row chunks (one render_wave launch each); the
+    picture is the same however it is chunked (DRT_CHUNK_LOG2 shrinks the bound so a small frame needs many launches)."""
+    import os
+    from distraytracer_b200 import abi
+    scene, settings, _ = load_case("checkertexture")
+    s = abi.copy_struct(settings)
+    s.xRes, s.yRes, s.antialias_samples, s.aperture = 96, 72, 16, 0.2
+    dev = _gpu(scene)
+    one, many = abi.Counters(), abi.Counters()
+    a = dev.render(s, counters=one)
+    os.environ["DRT_CHUNK_LOG2"] = "12"            # 4096 samples = 2 rows of this frame per launch
+    try:
+        b = dev.render(s, counters=many)
+    finally:
+        del os.environ["DRT_CHUNK_LOG2"]
+    assert np.array_equal(a, b) and a.std() > 5
+    assert one.kernel_launches == 2 and many.kernel_launches == 2 * 36
