@@ -30,28 +30,42 @@ if "c5" in which: run("C5 999698-triangle terrain 4K 64spp", *scenes.config5())
 
 def mocap_video(n_frames=120, xres=1920, yres=1080, spp=16):
     """C4 end to end on one GPU: ASF/AMC -> drt_skeleton (all frames posed by skeleton_fk) -> per frame
-    drt_scene_pose_skeleton + drt_render into a host frame (wall clock, includes H2D of the scene and D2H of the frame)."""
+    drt_scene_pose_skeleton + drt_render into a host frame (wall clock, includes H2D of the scene and D2H of the frame).
+    Measured with one scene handle, and with two handles on two host threads taking alternate frames (what
+    drt_host.h::renderVideo does): while one frame drains and is copied back, the other keeps the SMs busy."""
+    import threading
     golden = os.path.join(ROOT, "tests", "golden")
     t0 = time.time()
     skel = runtime.DeviceSkeleton(os.path.join(golden, "mocap_90.asf"), os.path.join(golden, "mocap_90_16_first121.amc"))
     t_load = time.time() - t0
-    scene, st = scenes.config4_frame(0, xres, yres, spp)
+    scene, st0 = scenes.config4_frame(0, xres, yres, spp)
     first = next(i for i, p in enumerate(scene.prims) if p.type == abi.PRIM_CYLINDER)
-    dev = runtime.DeviceScene(scene, 0)
-    out = np.empty((yres, xres, 3), dtype=np.uint8)
-    for f in range(3):                                   # warm-up
-        dev.pose_skeleton(skel, f, first); dev.render(st, out=out)
-    t0 = time.time(); t_pose = 0.0
-    for f in range(n_frames):
-        st.frame = f; st.seed = 1000 + f
-        tp = time.time(); dev.pose_skeleton(skel, f, first); t_pose += time.time() - tp
-        dev.render(st, out=out)
-    dt = time.time() - t0
     n = xres * yres * (int(np.sqrt(spp)) ** 2)
-    print(json.dumps({"config": f"C4 mocap video {n_frames} frames {xres}x{yres} {spp}spp velocity blur, skeleton path, e2e wall clock",
-                      "frames_per_s": n_frames / dt, "Msamples_per_s": n * n_frames / dt / 1e6, "ms_per_frame": 1e3 * dt / n_frames,
-                      "pose_ms_per_frame": 1e3 * t_pose / n_frames, "skeleton_load_s": t_load, "fk_kernel_ms": skel.fk_ms,
-                      "clip_frames": skel.n_frames, "bones": skel.n_cylinders}), flush=True)
+    for handles in (1, 2):
+        devs = [runtime.DeviceScene(scene, 0) for _ in range(handles)]
+        outs = [np.empty((yres, xres, 3), dtype=np.uint8) for _ in range(handles)]
+        pose_s = [0.0] * handles
+
+        def work(k, frames):
+            st = abi.copy_struct(st0)
+            for f in frames:
+                st.frame = f; st.seed = 1000 + f
+                tp = time.time(); devs[k].pose_skeleton(skel, f, first); pose_s[k] += time.time() - tp
+                devs[k].render(st, out=outs[k])
+
+        for k in range(handles):
+            work(k, range(3))                              # warm-up
+        pose_s = [0.0] * handles
+        th = [threading.Thread(target=work, args=(k, range(k, n_frames, handles))) for k in range(handles)]
+        t0 = time.time()
+        for t in th: t.start()
+        for t in th: t.join()
+        dt = time.time() - t0
+        print(json.dumps({"config": f"C4 mocap video {n_frames} frames {xres}x{yres} {spp}spp velocity blur, skeleton path, e2e wall clock",
+                          "scene_handles": handles, "frames_per_s": n_frames / dt, "Msamples_per_s": n * n_frames / dt / 1e6,
+                          "ms_per_frame": 1e3 * dt / n_frames, "pose_ms_per_frame": 1e3 * sum(pose_s) / n_frames,
+                          "skeleton_load_s": t_load, "fk_kernel_ms": skel.fk_ms, "clip_frames": skel.n_frames,
+                          "bones": skel.n_cylinders}), flush=True)
 
 
 if "c4video" in which: mocap_video()
