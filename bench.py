@@ -49,7 +49,7 @@ def config_dict(n_gpus):
                     "rectangle-light soft shadows, glass block (Fresnel refraction), max_depth 10, brdf_samples 2",
         "samples_per_step": XRES * YRES * SPP,
         "partition": f"frames round-robin over {n_gpus} rank(s), no collective; scene replicated",
-        "precision": "reference (f64 vectors, f32 scalars, no FMA contraction)",
+        "precision": "reference: f64 vectors, f32 scalar temporaries where the reference narrows, no FMA contraction",
         "l2": "working set is the 2.1 GB per-frame sample buffer (> 126 MB L2); no explicit flush",
     }
 
@@ -206,7 +206,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64 vectors / f32 scalars", "data": "synthetic", "config": config_dict(args.gpus),
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args.gpus),
         "frames_per_s": value * 1e6 / (XRES * YRES * SPP),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": ref.cores, "kind": ref.kind, "sample": ref.describe()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -340,7 +340,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64 vectors / f32 scalars", "data": "synthetic", "config": config_dict(world),
+            "dtype": "f64", "data": "synthetic", "config": config_dict(world),
             "frames_per_s": value * 1e6 / samples_per_step,
             "wall_ms_per_step": wall_ms / args.steps,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_scene_bytes(dev, scene)),
