@@ -353,6 +353,13 @@ def run_ours(args):
                          "launches_per_step": wave_launches_per_step,
                          "note": "kernel render_wave<double>, one launch per step (a frame fits one row chunk of <= 2^28 samples): achieved = algorithmic bytes of the launch / its device time (CUDA events on the library's stream; resolve is 0.5 ms of the 207), traffic = DRAM bytes of the launch (ncu). The path is issue/latency bound in the FP64+ALU pipes, not HBM bound: see roofline_fp; traffic = ray-pool and hit-buffer spill, 1.0 TB/s"},
             "fp32_variant": fp32_info,
+            # what actually bounds the kernel: warp-instruction issue.  Instructions per frame from the same ncu launch list
+            # as `traffic` (smsp__inst_executed.sum = 96.2 G for render_wave<double>), time measured live.
+            "roofline_issue": {"bound": "warp_issue", "achieved": 96205331080 / step_s / 1e9,
+                               "peak": props.multi_processor_count * 4 * sm_mhz * 1e6 / 1e9, "unit": "Gwarp-inst/s",
+                               "frac": 96205331080 / step_s / (props.multi_processor_count * 4 * sm_mhz * 1e6),
+                               "note": "peak = SMs x 4 schedulers x observed SM clock (one warp instruction per scheduler per "
+                                       "cycle); 26 of 32 lanes are active per instruction (profiles/r1_ncu_full_band_wave_final.txt)"},
             "roofline_fp": {"bound": "fp64_pipe", "achieved": ops / step_s / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
                             "frac": ops / step_s / 1e12 / fp64_peak,
                             "note": events_note or "algorithmic ops = event counters x SURVEY.md 8(d) cost table; peak = SMs x 64 DFMA x 2 x observed SM clock",
