@@ -153,6 +153,72 @@ def _force_3dof(lines):
     return b"\n".join(out) + b"\n"
 
 
+SYNTH_ASF = b"""# hand-written skeleton: translational and mixed degrees of freedom on inner bones (90.asf has them on the root only),
+# a bone without a length line (the reference carries the previous bone's length over), a branching hierarchy
+:version 1.10
+:name synth
+:units
+  mass 1.0
+  length 0.45
+  angle deg
+:root
+   order TX TY TZ RX RY RZ
+   axis XYZ
+   position 0 0 0
+   orientation 0 0 0
+:bonedata
+  begin
+     id 1
+     name hip
+     direction 0.6 -0.7 0.387298
+     length 2.5
+     axis 10 -20 30  XYZ
+    dof rx ry rz
+  end
+  begin
+     id 2
+     name slider
+     direction 0 -1 0
+     length 4.25
+     axis 0 45 -15  XYZ
+    dof tx ty tz rx
+  end
+  begin
+     id 3
+     name tip
+     direction 0.267261 0.534522 0.801784
+     axis -90 5 20  XYZ
+  end
+  begin
+     id 4
+     name arm
+     direction -1 0 0
+     length 3
+     axis 0 0 90  XYZ
+    dof rz ty
+  end
+:hierarchy
+  begin
+    root hip arm
+    hip slider
+    slider tip
+  end
+"""
+
+
+def _synth_amc(n_frames=40):
+    rng = np.random.default_rng(7)
+    out = [b"# synthetic motion", b":FULLY-SPECIFIED", b":DEGREES"]
+    for f in range(n_frames):
+        v = rng.uniform(-1, 1, 16)
+        out.append(b"%d" % (f + 1))
+        out.append(b"root %.6g %.6g %.6g %.6g %.6g %.6g" % (tuple(v[:3] * 20) + tuple(v[3:6] * 180)))
+        out.append(b"hip %.6g %.6g %.6g" % tuple(v[6:9] * 120))
+        out.append(b"slider %.6g %.6g %.6g %.6g" % (v[9] * 3, v[10] * 3, v[11] * 3, v[12] * 90))
+        out.append(b"arm %.6g %.6g" % (v[13] * 170, v[14] * 2))
+    return b"\n".join(out) + b"\n"
+
+
 def _variants():
     asf, amc = _clip()                      # 90.asf has CRLF line ends, the .amc LF
     lines = amc.split(b"\n")
@@ -166,7 +232,8 @@ def _variants():
         "truncated": (asf, b"\n".join(lines[:3 + 100 * 30 + 7]) + b"\n"),                         # 100 whole frames + 7 stray lines
         # a blank line re-runs the previous keyword on an empty string (sscanf leaves `keyword` alone): harmless after "begin"
         # (after "end" the reference would start a phantom bone and index out of bounds; the library rejects that)
-        "blank_lines": (asf_lf.replace(b"  begin\n", b"  begin\n\n"), amc),                               # sscanf keeps the last keyword
+        "blank_lines": (asf_lf.replace(b"  begin\n", b"  begin\n\n"), amc),
+        "synthetic": (SYNTH_ASF, _synth_amc()),
     }
 
 
@@ -203,7 +270,7 @@ def test_host_parser_rejects_malformed_clips():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["lf", "crlf", "force3dof", "truncated", "blank_lines"])
+@pytest.mark.parametrize("name", ["lf", "crlf", "force3dof", "truncated", "blank_lines", "synthetic"])
 def test_cuda_fk_matches_oracle_on_awkward_clips(oracle_lib, name):
     from distraytracer_b200 import runtime
     from oracle.harness import SkeletonOracle
@@ -212,3 +279,29 @@ def test_cuda_fk_matches_oracle_on_awkward_clips(oracle_lib, name):
     orc = SkeletonOracle(asf, amc)
     assert dev.n_frames == orc.n_frames
     assert np.array_equal(dev.bones(), np.stack([orc.bones(f) for f in range(orc.n_frames)]))
+
+
+@pytest.mark.parametrize("name", ["lf", "crlf", "force3dof", "truncated", "blank_lines", "synthetic"])
+def test_oracle_matches_compiled_reference_on_awkward_clips(oracle_lib, tmp_path, name):
+    """Pins the restatement's handling of line ends, :FORCE-ALL-JOINTS-BE-3DOF (enableAllRotationalDOFs), the
+    frame-count formula and blank lines on the compiled reference itself: the variant is written out as 90.asf /
+    90_16_v3.amc, the reference loads it the way its main() does (fresh process: its mocap state is global)."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    from oracle.harness import SkeletonOracle, ref_available
+    if not ref_available():
+        pytest.skip("oracle/_ref not built")
+    asf, amc = _variants()[name]
+    (tmp_path / "90.asf").write_bytes(asf)
+    (tmp_path / "90_16_v3.amc").write_bytes(amc)
+    orc = SkeletonOracle(asf, amc)
+    frames = [0, 1, orc.n_frames // 2, orc.n_frames - 1, orc.n_frames + 5]
+    out = tmp_path / "bones.npy"
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); from oracle.harness import Ref; "
+            "r = Ref(asset_root=%r, mocap=True); np.save(%r, np.stack([r.mocap_bones(f) for f in %r]))"
+            % (ROOT, str(tmp_path), str(out), frames))
+    subprocess.check_call([sys.executable, "-c", code], stdout=subprocess.DEVNULL)
+    want = np.load(out)
+    got = np.stack([orc.bones(f) for f in frames])
+    assert np.array_equal(got, want)
