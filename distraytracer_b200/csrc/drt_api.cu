@@ -318,8 +318,40 @@ struct DevScene {
   int n_geoms = 0, n_prims = 0, n_lights = 0, n_nodes = 0;
 };
 
+// Scene tables go to the device through one pinned staging buffer and cudaMemcpyAsync on the scene's own stream: the
+// per-frame update of one scene handle then neither waits for nor stalls another handle's kernel on the same GPU
+// (a synchronous cudaMemcpy from pageable memory did), and the render launches that follow are ordered behind the
+// copies by the stream.  The caller synchronises the stream before the stage is filled again.
+struct PinnedStage {
+  char* base = nullptr; size_t cap = 0, used = 0;
+  int reserve(size_t bytes) {
+    used = 0;
+    if (bytes <= cap) return DRT_OK;
+    if (base) cudaFreeHost(base);
+    base = nullptr; cap = 0;
+    CK(cudaMallocHost((void**)&base, bytes));
+    cap = bytes;
+    return DRT_OK;
+  }
+  int push(void* dst, const void* src, size_t bytes, cudaStream_t q) {
+    if (!bytes) return DRT_OK;
+    if (used + bytes > cap) return fail(DRT_ERR_INVALID, "internal: upload stage too small");
+    memcpy(base + used, src, bytes);
+    CK(cudaMemcpyAsync(dst, base + used, bytes, cudaMemcpyHostToDevice, q));
+    used += (bytes + 255) & ~(size_t)255;
+    return DRT_OK;
+  }
+};
+
 template <typename R>
-int upload(const HostScene<R>& hs, DevScene<R>& ds) {
+size_t uploadBytes(const HostScene<R>& hs) {
+  auto pad = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  return pad(sizeof(float4) * hs.gbounds.size()) + pad(sizeof(NodeD<R>) * hs.nodes.size()) + pad(sizeof(Geom<R>) * hs.geoms.size()) +
+         pad(sizeof(PrimD<R>) * hs.prims.size()) + pad(sizeof(LightD<R>) * hs.lights.size());
+}
+
+template <typename R>
+int upload(const HostScene<R>& hs, DevScene<R>& ds, PinnedStage& stage, cudaStream_t q) {
   if ((int)hs.geoms.size() != ds.n_geoms || !ds.geoms) {
     if (ds.geoms) cudaFree(ds.geoms);
     CK(cudaMalloc(&ds.geoms, sizeof(Geom<R>) * std::max<size_t>(1, hs.geoms.size())));
@@ -328,7 +360,7 @@ int upload(const HostScene<R>& hs, DevScene<R>& ds) {
     if (ds.gbounds) cudaFree(ds.gbounds);
     CK(cudaMalloc(&ds.gbounds, sizeof(float4) * std::max<size_t>(3, hs.gbounds.size())));
   }
-  if (!hs.gbounds.empty()) CK(cudaMemcpy(ds.gbounds, hs.gbounds.data(), sizeof(float4) * hs.gbounds.size(), cudaMemcpyHostToDevice));
+  { int rc = stage.push(ds.gbounds, hs.gbounds.data(), sizeof(float4) * hs.gbounds.size(), q); if (rc) return rc; }
   if ((int)hs.prims.size() != ds.n_prims || !ds.prims) {
     if (ds.prims) cudaFree(ds.prims);
     CK(cudaMalloc(&ds.prims, sizeof(PrimD<R>) * std::max<size_t>(1, hs.prims.size())));
@@ -342,11 +374,11 @@ int upload(const HostScene<R>& hs, DevScene<R>& ds) {
     CK(cudaMalloc(&ds.nodes, sizeof(NodeD<R>) * std::max<size_t>(1, hs.nodes.size())));
   }
   ds.n_nodes = (int)hs.nodes.size();
-  CK(cudaMemcpy(ds.nodes, hs.nodes.data(), sizeof(NodeD<R>) * ds.n_nodes, cudaMemcpyHostToDevice));
+  { int rc = stage.push(ds.nodes, hs.nodes.data(), sizeof(NodeD<R>) * ds.n_nodes, q); if (rc) return rc; }
   ds.n_geoms = (int)hs.geoms.size(); ds.n_prims = (int)hs.prims.size(); ds.n_lights = (int)hs.lights.size();
-  if (ds.n_geoms) CK(cudaMemcpy(ds.geoms, hs.geoms.data(), sizeof(Geom<R>) * ds.n_geoms, cudaMemcpyHostToDevice));
-  if (ds.n_prims) CK(cudaMemcpy(ds.prims, hs.prims.data(), sizeof(PrimD<R>) * ds.n_prims, cudaMemcpyHostToDevice));
-  if (ds.n_lights) CK(cudaMemcpy(ds.lights, hs.lights.data(), sizeof(LightD<R>) * ds.n_lights, cudaMemcpyHostToDevice));
+  { int rc = stage.push(ds.geoms, hs.geoms.data(), sizeof(Geom<R>) * ds.n_geoms, q); if (rc) return rc; }
+  { int rc = stage.push(ds.prims, hs.prims.data(), sizeof(PrimD<R>) * ds.n_prims, q); if (rc) return rc; }
+  { int rc = stage.push(ds.lights, hs.lights.data(), sizeof(LightD<R>) * ds.n_lights, q); if (rc) return rc; }
   return DRT_OK;
 }
 
@@ -369,6 +401,7 @@ struct drt_scene {
   unsigned long long* batch_counter = nullptr; int* overflow = nullptr;
   int wave_blocks_f64 = 0, wave_blocks_f32 = 0;
   MeshBuffers mesh; bool has_mesh = false; drt_prim mesh_material;
+  PinnedStage stage;
 };
 
 namespace {
@@ -398,8 +431,10 @@ int flattenAndUpload(drt_scene* s) {
     rc = addMeshMaterial<double>(s->mesh_material, s->n_textures, hd); if (rc) return rc;
     rc = addMeshMaterial<float>(s->mesh_material, s->n_textures, hf); if (rc) return rc;
   }
-  rc = upload(hd, s->dd); if (rc) return rc;
-  rc = upload(hf, s->df); if (rc) return rc;
+  CK(cudaStreamSynchronize(s->stream));                     // the stage may still feed the previous update's copies
+  rc = s->stage.reserve(uploadBytes(hd) + uploadBytes(hf)); if (rc) return rc;
+  rc = upload(hd, s->dd, s->stage, s->stream); if (rc) return rc;
+  rc = upload(hf, s->df, s->stage, s->stream); if (rc) return rc;
   s->any_glass = false;
   for (const drt_prim& p : s->prims) if (p.material == DRT_MAT_GLASS) s->any_glass = true;
   return DRT_OK;
@@ -750,6 +785,7 @@ void drt_scene_destroy(drt_scene* s) {
                   s->samples, s->need, s->bg, s->out_u8, s->out_f32, s->counts, s->pool, s->batch_counter, s->overflow};
   for (void* p : ptrs) if (p) cudaFree(p);
   freeMesh(&s->mesh);
+  if (s->stage.base) cudaFreeHost(s->stage.base);
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
   if (s->stream) cudaStreamDestroy(s->stream);
