@@ -350,3 +350,18 @@ def test_row_chunking_does_not_change_the_image(oracle_lib):
         del os.environ["DRT_CHUNK_LOG2"]
     assert np.array_equal(a, b) and a.std() > 5
     assert one.kernel_launches == 2 and many.kernel_launches == 2 * 36
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(14))
+def test_cuda_matches_oracle_on_mutated_scenes(oracle_lib, seed):
+    """Fuzz: fixture scenes with random motion flags, BRDF models, roughness, reflective materials, glossy flags and
+    settings (tests/fuzz_cases.py); the oracle is pinned on the compiled reference for the same kind of mutations by
+    tests/test_oracle_fuzz.py.  On B200 all 14 are bit-identical in u8; the bar asserted is the north-star one."""
+    from fuzz_cases import mutated_case
+    from oracle.harness import Oracle, ORACLE_KEYED, compare
+    case, scene, s = mutated_case(seed)
+    want, _, _, _ = Oracle(scene).render(s, mode=ORACLE_KEYED)
+    got, _ = _gpu(scene).render_float(s)
+    st = compare(want, got)
+    assert st["frac_within_1"] >= TOL_FRAC, (case, st)
