@@ -97,3 +97,63 @@ def test_restatement_matches_reference_on_mutated_scenes(oracle_lib, seed):
     img, ab, _, _ = Oracle(scene).render(s, mode=ORACLE_STREAM)
     assert (ab == ref_ab).all(), (builder, frame, "abort masks differ")
     assert np.array_equal(ref_img, img, equal_nan=True), (builder, frame, float(np.nanmax(np.abs(ref_img - img))))
+
+
+@pytest.mark.parametrize("cfg", ["config1", "config2", "config3"])
+def test_restatement_matches_reference_on_the_bench_workloads(oracle_lib, cfg):
+    """The BASELINE configurations themselves (distraytracer_b200.scenes: config 2 is what bench.py times -- glass
+    triangles, rectangle light, glossy floor, DOF) loaded INTO the compiled reference at reduced size: the restatement
+    reproduces the reference's image to the bit -- except where the reference's own result is undefined (glass, Q3).  (Configs 4 and 5 use per-primitive velocities / a mesh type, which the
+    reference does not have; their oracle paths are the same code driven by other inputs.)"""
+    if not _have_reference():
+        pytest.skip("reference tree not present (GPU box): pinned by the stored fixtures instead")
+    from distraytracer_b200 import scenes
+    from oracle.harness import Ref, Oracle, ORACLE_STREAM
+    scene, s = {"config1": scenes.config1, "config2": lambda: scenes.config2(64, 36, 4),
+                "config3": lambda: scenes.config3(64, 36, 4)}[cfg]()
+    if cfg == "config1":
+        s.xRes, s.yRes = 64, 48
+    s.seed = 4242
+    r = Ref(mocap=True)
+    r.reset()
+    r.load(scene)
+    r.set_settings(s)
+    r.rng(1, s.seed, 0)
+    ref_img, ref_ab, _ = r.render_loop(s.frame, reset_policy=1, seed=s.seed)
+    img, ab, cnt, _ = Oracle(scene).render(s, mode=ORACLE_STREAM)
+    assert np.nanstd(img) > 5 and cnt.rays > s.xRes * s.yRes
+    same = (ab == ref_ab) & (np.nan_to_num(ref_img, nan=-1.0) == np.nan_to_num(img, nan=-1.0)).all(axis=-1)
+    if cfg != "config2":
+        assert same.all()
+        return
+    # config 2 holds glass.  Where a ray tree reaches a glass surface the reference reads an UNINITIALISED variable
+    # (`inside = inside_tmp`, render_final_project.cpp:524,534 -- quirk Q3): what it renders there depends on the compiler, and
+    # the restatement implements the evident intent (the inside flag of the closest hit).  Everywhere else: to the bit.
+    from distraytracer_b200 import abi
+    from distraytracer_b200.scene import Scene
+    def recoloured(rgb):                             # the glass triangles as plain "raw"-shaded surfaces of one colour
+        out = [abi.copy_struct(p) for p in scene.prims]
+        for p in out:
+            if p.material == abi.MAT_GLASS:
+                p.material, p.model = abi.MAT_NONE, abi.MODEL_RAW
+                p.color[:] = rgb
+        return out
+    plain = recoloured((1.0, 0.0, 1.0))
+    no_glass, nab, _, _ = Oracle(Scene(plain, scene.lights, scene.textures)).render(s, mode=ORACLE_STREAM)
+    other, oab, _, _ = Oracle(Scene(recoloured((0.0, 1.0, 0.0)), scene.lights, scene.textures)).render(s, mode=ORACLE_STREAM)
+    # a pixel whose ray trees reach those triangles (directly or by reflection) changes with their colour
+    touches_glass = (nab != oab) | (np.nan_to_num(no_glass, nan=-1.0) != np.nan_to_num(other, nan=-1.0)).any(axis=-1)
+    # (+ their 8 neighbours: on the block's silhouette both colourings saturate to white under the light panel)
+    grown = touches_glass.copy()
+    for dy in (-1, 0, 1):
+        for dx in (-1, 0, 1):
+            grown |= np.roll(np.roll(touches_glass, dy, axis=0), dx, axis=1)
+    assert same[~grown].all()
+    assert 0 < grown.mean() < 0.25 and 0 < (~same).sum() <= grown.sum()
+    # and with the glass taken out of the material the whole frame is bit-identical again
+    r.reset()
+    r.load(Scene(plain, scene.lights, scene.textures))
+    r.set_settings(s)
+    r.rng(1, s.seed, 0)
+    ref2, ref2_ab, _ = r.render_loop(s.frame, reset_policy=1, seed=s.seed)
+    assert (ref2_ab == nab).all() and np.array_equal(ref2, no_glass, equal_nan=True)
