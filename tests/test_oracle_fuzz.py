@@ -219,3 +219,44 @@ def test_glass_divergence_is_the_uninitialised_inside_flag(oracle_lib, tmp_path)
 
     pinned, emulated = differing(None), differing("last_tested")
     assert 20 <= pinned <= 120 and emulated <= pinned // 4, (pinned, emulated)
+
+
+def test_restatement_equals_the_reference_with_the_inside_flag_fixed(oracle_lib, tmp_path):
+    """The other half of the Q3 evidence: compile the reference once more with the one-word fix
+    `shape->intersect(ray, eye, t_dist, inside_tmp)` (render_final_project.cpp:526) applied to a temporary copy outside the
+    repository, and the restatement reproduces BASELINE config 2 -- the bench workload, glass included -- to the bit,
+    abort masks included.  (~40 s: one more build of the reference.)"""
+    if not _have_reference():
+        pytest.skip("reference tree not present (GPU box)")
+    import subprocess
+    import sys
+    from conftest import ROOT
+    from oracle.harness import REFERENCE_ROOT
+    src = open(os.path.join(REFERENCE_ROOT, "render_final_project.cpp")).read()
+    broken = "bool intersect = shape->intersect(ray, eye, t_dist, inside);"
+    assert src.count(broken) == 1
+    (tmp_path / "render_final_project.cpp").write_text(src.replace(broken, "bool intersect = shape->intersect(ray, eye, t_dist, inside_tmp);"))
+    so = str(tmp_path / "libdrt_ref_fixed.so")
+    orc = os.path.join(ROOT, "oracle")
+    subprocess.check_call(["/usr/bin/g++", "-O3", "-std=c++17", "-fPIC", "-w", "-shared", "-I" + os.path.join(orc, "ref_shim"),
+                           "-I" + os.path.join(orc, "eigen_shim"), "-I" + str(tmp_path), "-I" + REFERENCE_ROOT,
+                           os.path.join(orc, "ref_driver.cpp")] +
+                          [os.path.join(REFERENCE_ROOT, f) for f in ("geometry.cpp", "skeleton.cpp", "motion.cpp", "displaySkeleton.cpp")] +
+                          ["-o", so])
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r)\n"
+        "from distraytracer_b200 import scenes\n"
+        "from oracle.harness import Ref, Oracle, ORACLE_STREAM\n"
+        "for res in ((64, 36, 4), (120, 68, 9)):\n"
+        "    scene, s = scenes.config2(*res); s.seed = 4242\n"
+        "    r = Ref(mocap=True); r.reset(); r.load(scene); r.set_settings(s); r.rng(1, s.seed, 0)\n"
+        "    ref, rab, _ = r.render_loop(s.frame, reset_policy=1, seed=s.seed)\n"
+        "    img, ab, _, _ = Oracle(scene).render(s, mode=ORACLE_STREAM)\n"
+        "    same = (ab == rab) & (np.nan_to_num(ref, nan=-1.0) == np.nan_to_num(img, nan=-1.0)).all(axis=-1)\n"
+        "    print('DIFF', int((~same).sum()), int(np.isnan(img).any(-1).sum()))\n" % ROOT)
+    env = dict(os.environ, DRT_REF_SO=so)
+    env.pop("DRT_ORACLE_Q3", None)
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True).stdout
+    rows = [ln.split() for ln in out.splitlines() if ln.startswith("DIFF")]
+    assert len(rows) == 2 and all(int(r[1]) == 0 for r in rows), rows
+    assert all(int(r[2]) > 0 for r in rows)            # the glass block is in the picture (its NaN Fresnel terms are)
