@@ -102,7 +102,7 @@ class Tile(C.Structure):
 
 class Counters(C.Structure):
     _fields_ = [
-        ("collect", C.c_int32), ("kernel_ms", C.c_float), ("kernel_launches", C.c_int32),
+        ("collect", C.c_int32), ("kernel_ms", C.c_float), ("kernel_launches", C.c_int32), ("kernel_variant", C.c_int32),
         ("samples", C.c_uint64), ("rays", C.c_uint64), ("shadow_rays", C.c_uint64),
         ("node_tests", C.c_uint64), ("prim_tests", C.c_uint64 * PRIM_TYPE_COUNT),
         ("shade_evals", C.c_uint64), ("noise_evals", C.c_uint64),

@@ -384,10 +384,24 @@ int upload(const HostScene<R>& hs, DevScene<R>& ds, PinnedStage& stage, cudaStre
 
 }  // namespace
 
+namespace drt {
+static const int kWaveFeats[] = DRT_WAVE_FEATS;
+const int* waveFeatList(int* n) { *n = (int)(sizeof(kWaveFeats) / sizeof(int)); return kWaveFeats; }
+int waveFeatPick(int need) {
+  int best = FT_ALL, best_bits = 99;
+  for (int f : kWaveFeats) {
+    if ((f & need) != need) continue;
+    const int bits = __builtin_popcount((unsigned)f);
+    if (bits < best_bits) { best = f; best_bits = bits; }
+  }
+  return best;
+}
+}  // namespace drt
+
 struct drt_scene {
   int device = 0;
   std::vector<drt_prim> prims; std::vector<drt_light> lights; int n_textures = 0;
-  bool any_glass = false;
+  bool any_glass = false, any_tex = false, any_motion = false;
   DevScene<double> dd; DevScene<float> df;
   std::vector<cudaArray_t> tex_arrays; std::vector<cudaTextureObject_t> tex_objs;
   cudaTextureObject_t* d_tex = nullptr; int2* d_texdims = nullptr;
@@ -435,8 +449,14 @@ int flattenAndUpload(drt_scene* s) {
   rc = s->stage.reserve(uploadBytes(hd) + uploadBytes(hf)); if (rc) return rc;
   rc = upload(hd, s->dd, s->stage, s->stream); if (rc) return rc;
   rc = upload(hf, s->df, s->stage, s->stream); if (rc) return rc;
-  s->any_glass = false;
-  for (const drt_prim& p : s->prims) if (p.material == DRT_MAT_GLASS) s->any_glass = true;
+  s->any_glass = s->any_tex = s->any_motion = false;
+  auto scan = [&](const drt_prim& p) {
+    if (p.material == DRT_MAT_GLASS) s->any_glass = true;
+    if (p.flags & DRT_FLAG_TEXTURE) s->any_tex = true;
+    if (p.flags & DRT_FLAG_MOTION) s->any_motion = true;
+  };
+  for (const drt_prim& p : s->prims) scan(p);
+  if (s->has_mesh) scan(s->mesh_material);
   return DRT_OK;
 }
 
@@ -527,7 +547,7 @@ int ensureScratch(drt_scene* s, size_t n_samples, size_t n_corners, size_t n_out
   }
   if (!s->counts) CK(cudaMalloc(&s->counts, sizeof(Counts)));
   if (!s->batch_counter) CK(cudaMalloc(&s->batch_counter, sizeof(unsigned long long)));
-  if (!s->overflow) { CK(cudaMalloc(&s->overflow, sizeof(int))); CK(cudaMemset(s->overflow, 0, sizeof(int))); }
+  if (!s->overflow) { CK(cudaMalloc(&s->overflow, sizeof(int))); CK(cudaMemsetAsync(s->overflow, 0, sizeof(int), s->stream)); }
   return DRT_OK;
 }
 
@@ -568,6 +588,15 @@ int launchAll(drt_scene* s, const DevScene<R>& ds, const drt_settings& st, const
     s->pool_cap = pool_bytes;
   }
   P.pool_raw = s->pool; P.pool_cap = pool_cap; P.batch_counter = s->batch_counter; P.overflow = s->overflow;
+  // what this call can reach decides the render_wave instantiation (drt_launch.h WaveFeat)
+  int feat = 0;
+  if (s->has_mesh) feat |= FT_MESH;
+  if (st.blur_samples > 0 && s->any_motion) feat |= (st.blur_mode == DRT_BLUR_VELOCITY) ? FT_VEL : FT_REFBLUR;
+  if (s->any_glass && st.reflect) feat |= FT_GLASS;
+  if (s->any_tex) feat |= FT_TEX;
+  if (ds.n_geoms > DRT_SMEM_GEOMS) feat |= FT_BIG;
+  if (const char* e = getenv("DRT_WAVE_FEAT")) feat |= atoi(e);      // tuning: force a larger instantiation (63 = generic)
+  int variant = -1;
   cudaStream_t q = s->stream;
   int launches = 0;
   if (collect) CK(cudaMemsetAsync(s->counts, 0, sizeof(Counts), q));
@@ -582,14 +611,14 @@ int launchAll(drt_scene* s, const DevScene<R>& ds, const drt_settings& st, const
       P.sample_base = (long long)row0 * per_row;
       P.sample_count = (long long)rows * per_row;
       CK(cudaMemsetAsync(s->batch_counter, 0, sizeof(unsigned long long), q));
-      launchRenderSamples<R>(P, collect, wave_blocks, q); launches++;
+      variant = launchRenderSamples<R>(P, collect, feat, wave_blocks, q); launches++;
       if (st.perlin_cloud) { launchCloudCorners<R>(P, q); launches++; }
       launchResolve<R>(P, row0, rows, q); launches++;
     }
   }
   CK(cudaEventRecord(s->ev1, q));
   CK(cudaGetLastError());
-  if (counters) counters->kernel_launches = launches;
+  if (counters) { counters->kernel_launches = launches; counters->kernel_variant = variant; }
   return DRT_OK;
 }
 
@@ -605,6 +634,10 @@ int renderCommon(const drt_scene* cs, const drt_settings* st, const drt_tile* ti
   if (st->sample_mode != DRT_SAMPLES_KEYED) return fail(DRT_ERR_UNSUPPORTED, "unknown sample_mode");
   if (st->precision != DRT_PRECISION_REFERENCE && st->precision != DRT_PRECISION_FP32) return fail(DRT_ERR_INVALID, "unknown precision");
   if (st->max_depth < 0 || st->max_depth > 32) return fail(DRT_ERR_UNSUPPORTED, "max_depth outside [0,32]");
+  // the background of a missed sample is looked up at pixel corner (x + (i+u)/9, y + (j+u)/9) truncated (:1052-1053, Q1); the
+  // per-sample record encodes that corner as an offset of 0 or 1, which holds while sqrt(antialias_samples) <= 18
+  if (st->perlin_cloud && !st->cloud_only && (int)sqrt((double)st->antialias_samples) > 18)
+    return fail(DRT_ERR_UNSUPPORTED, "perlin_cloud with more than 18 x 18 samples per pixel");
   int pool_cap = 0;
   {  // CTA ray-pool bound (render_wave): the pool is a LIFO over the trees of one batch of DRT_CTA_SLOTS samples.  A
      // TRACE pass turns at most DRT_HITS_PER_PASS rays into hits, a hit spawns at most `fan` children (lobes [+1 for
@@ -638,7 +671,8 @@ int renderCommon(const drt_scene* cs, const drt_settings* st, const drt_tile* ti
   if (!st->cloud_only) CK(cudaMemcpyAsync(&overflowed, s->overflow, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
   CK(cudaStreamSynchronize(s->stream));
   if (overflowed) {   // the kernel dropped rays instead of writing past its pool: the frame is not valid
-    CK(cudaMemset(s->overflow, 0, sizeof(int)));
+    CK(cudaMemsetAsync(s->overflow, 0, sizeof(int), s->stream));
+    CK(cudaStreamSynchronize(s->stream));
     return fail(DRT_ERR_UNSUPPORTED, "a CTA ray pool overflowed (brdf_samples * max_depth beyond the sized bound)");
   }
   if (counters) {
@@ -760,8 +794,11 @@ int drt_scene_update_prims(drt_scene* s, const drt_prim* prims, int32_t n_prims)
     if (prims[i].type != s->prims[i].type) return fail(DRT_ERR_INVALID, "primitive type changed");
   CK(cudaSetDevice(s->device));
   CK(cudaStreamSynchronize(s->stream));
+  const std::vector<drt_prim> before = s->prims;
   s->prims.assign(prims, prims + n_prims);
-  return flattenAndUpload(s);
+  const int rc = flattenAndUpload(s);
+  if (rc) s->prims = before;      // the device copy is untouched when validation fails
+  return rc;
 }
 
 int drt_scene_update_lights(drt_scene* s, const drt_light* lights, int32_t n_lights) {

@@ -82,11 +82,22 @@ __device__ __forceinline__ float blurVal(const Params<R>& P, const float dt) {
   return P.move_per_frame * dt;
 }
 
-template <typename R>
-__device__ inline Vec<R> shiftPoint(const Moved<R>& mv, int gflags, const Vec<R>& vel, Vec<R> p) {
-  if (mv.velocity_mode) return p + vel * mv.time;
-  if (gflags & GF_NAME_RECTANGLE) p.y += (R)mv.val;
+template <typename R, int F>
+__device__ __forceinline__ Vec<R> shiftPoint(const Moved<R>& mv, int gflags, const Vec<R>& vel, Vec<R> p) {
+  if ((F & FT_VEL) && mv.velocity_mode) return p + vel * mv.time;
+  if ((F & FT_REFBLUR) && (gflags & GF_NAME_RECTANGLE)) p.y += (R)mv.val;
   return p;
+}
+
+// The displacement state of one trace.  An instantiation without FT_VEL / FT_REFBLUR never re-traces (the host selects it
+// when blur_samples == 0 or no primitive carries the motion flag), so every field is a compile-time zero there.
+template <typename R, int F>
+__device__ __forceinline__ Moved<R> makeMoved(const Params<R>& P, const float dt) {
+  Moved<R> mv;
+  mv.val = (F & FT_REFBLUR) ? blurVal(P, dt) : 0.0f;
+  mv.time = (F & FT_VEL) ? (R)dt : R(0);
+  mv.velocity_mode = (F & FT_VEL) ? ((((F & FT_REFBLUR) ? P.blur_mode == 1 : true) && dt != 0.0f) ? 1 : 0) : 0;
+  return mv;
 }
 
 // ---- rectangle tests: Rectangle::intersect / intersectShadow (geometry.cpp:640-741)
@@ -112,11 +123,11 @@ __device__ inline bool rectHit(const Vec<R>& A, const Vec<R>& nrm, const Vec<R>&
 // BoundingVolume::intersect (geometry.cpp:2657-2740): slab test on the ray LINE,
 // accepted when tmax > 0.  Leaf boxes are widened in y by the motion-blur
 // displacement exactly as bumpBVH does (helpers.h:530-552; interior nodes are not).
-template <typename R>
+template <typename R, int F>
 __device__ inline bool boxHit(const NodeD<R>& nd, const Vec<R>& ray, const Vec<R>& inv_ray, const Vec<R>& start,
                               const Moved<R>& mv) {
   R loy = nd.lo.y, hiy = nd.hi.y;
-  if (nd.leaf && !mv.velocity_mode) { loy -= (R)mv.val; hiy += (R)mv.val; }
+  if ((F & FT_REFBLUR) && nd.leaf && !mv.velocity_mode) { loy -= (R)mv.val; hiy += (R)mv.val; }
   float tmin, tmax;
   if (isinf(inv_ray.x)) {
     if (!(start.x >= nd.lo.x && start.x <= nd.hi.x)) return false;
@@ -152,13 +163,13 @@ struct HitRec {
 };
 
 // One candidate of the closest-hit search: the intersect() of the geom's class.
-template <typename R>
+template <typename R, int F>
 __device__ inline bool geomIntersect(const Params<R>& P, const Geom<R>& g, int gi, const int type, const Moved<R>& mv,
                                      const Vec<R>& ray, const Vec<R>& start, float& t_hit, int& inside, int& sel) {
   bool ok = false;
   inside = 0; sel = 0;
     if (type == G_RECT || type == G_CHECKER) {
-      Vec<R> A = shiftPoint(mv, g.flags, g.vel, g.p0);
+      Vec<R> A = shiftPoint<R, F>(mv, g.flags, g.vel, g.p0);
       if (type == G_CHECKER) {  // exact-zero edge path pinned to "no hit" (quirk Q17)
         if (dot(g.p1, ray) == R(0)) return false;
       }
@@ -180,7 +191,7 @@ __device__ inline bool geomIntersect(const Params<R>& P, const Geom<R>& g, int g
         }
       }
     } else if (type == G_SPHERE) {  // Sphere::intersect geometry.cpp:106-140
-      Vec<R> sc = start - shiftPoint(mv, g.flags, g.vel, g.p0);
+      Vec<R> sc = start - shiftPoint<R, F>(mv, g.flags, g.vel, g.p0);
       float A = (float)dot(ray, ray);
       float B = (float)(R(2) * dot(ray, sc));
       float C = (float)(dot(sc, sc) - (R)((double)g.f0 * (double)g.f0));
@@ -194,7 +205,7 @@ __device__ inline bool geomIntersect(const Params<R>& P, const Geom<R>& g, int g
       else { t_hit = fminf(t0, t1); inside = 0; ok = true; }
     } else if (type == G_CYL) {  // Cylinder::intersect geometry.cpp:242-295
       const float eps = 1e-3f;
-      Vec<R> c1 = shiftPoint(mv, g.flags, g.vel, g.p0), c2 = shiftPoint(mv, g.flags, g.vel, g.p1);
+      Vec<R> c1 = shiftPoint<R, F>(mv, g.flags, g.vel, g.p0), c2 = shiftPoint<R, F>(mv, g.flags, g.vel, g.p1);
       const Vec<R> axis = g.p2;
       Vec<R> ray_a_proj = ray - dot(ray, axis) * axis;
       Vec<R> sc = start - c1;
@@ -213,7 +224,7 @@ __device__ inline bool geomIntersect(const Params<R>& P, const Geom<R>& g, int g
       Vec<R> pt = start + (R)tc * ray;
       if (dot(axis, pt - c1) > R(0) && dot(axis, pt - c2) < R(0)) { t_hit = tc; inside = ins; ok = true; }
     } else {  // G_TRI: Triangle::intersect geometry.cpp:488-553
-      Vec<R> A = shiftPoint(mv, g.flags, g.vel, g.p0);
+      Vec<R> A = shiftPoint<R, F>(mv, g.flags, g.vel, g.p0);
       const Vec<R> r1 = g.p1, r2 = g.p2;
       Vec<R> hh = cross(ray, r2);
       float det = (float)dot(r1, hh);
@@ -361,11 +372,11 @@ __device__ __forceinline__ unsigned int slabMask(const float4* __restrict__ tab,
 // slab filter.  Only while "rectangle" shapes are displaced by reference-mode motion
 // blur (mv.val != 0) is the reference tree walked node by node: bumpBVH widens leaf
 // boxes but not interior ones (quirk Q14), which can cull a moved rectangle.
-template <typename R, bool COUNT>
+template <typename R, int F, bool COUNT>
 __device__ inline void closestHit(const Params<R>& P, const float4* __restrict__ gb, const Moved<R>& mv, const Vec<R>& ray,
                                   const Vec<R>& start, HitRec& h, Counts& cnt) {
   h.t = FLT_MAX; h.geom = -1; h.inside = 0; h.checker_sel = 0;
-  if (mv.val == 0.0f && !DRT_FORCE_TREE) {
+  if ((!(F & FT_REFBLUR) || mv.val == 0.0f) && !DRT_FORCE_TREE) {
     // Two passes per group of 32 geoms: (1) the slab filter runs over the group in
     // lock-step (warp-uniform loads) and leaves each lane a bit mask of ITS candidates;
     // (2) every lane then walks its own mask, so one loop trip runs one exact test per
@@ -373,8 +384,8 @@ __device__ inline void closestHit(const Params<R>& P, const float4* __restrict__
     const float ix = 1.0f / (float)ray.x, iy = 1.0f / (float)ray.y, iz = 1.0f / (float)ray.z;
     const float ox = -(float)start.x * ix, oy = -(float)start.y * iy, oz = -(float)start.z * iz;   // slabMayHit's hoisted terms
     const float serr = 4e-7f * (fabsf(ox) + fabsf(oy) + fabsf(oz));
-    const bool cull = !mv.velocity_mode;
-    const bool smem = P.n_geoms <= DRT_SMEM_GEOMS;                      // CTA-uniform: the table is staged in shared memory
+    const bool cull = !((F & FT_VEL) && mv.velocity_mode);
+    const bool smem = !(F & FT_BIG) || P.n_geoms <= DRT_SMEM_GEOMS;     // CTA-uniform: the table is staged in shared memory
     const SlabRay sr = slabRay(ix, iy, iz, ox, oy, oz, FLT_MAX);
     const int n = P.n_geoms;
     for (int g0 = 0; g0 < n; g0 += 32) {
@@ -390,7 +401,7 @@ __device__ inline void closestHit(const Params<R>& P, const float4* __restrict__
         if (cull && h.t < FLT_MAX && !slabMayHit(g.blo, g.bhi, ox, oy, oz, ix, iy, iz, h.t * 1.0001f + 1e-4f, serr)) continue;
         if (COUNT) cnt.geom_tests[type]++;
         float t_hit; int inside, sel;
-        if (geomIntersect<R>(P, g, gi, type, mv, ray, start, t_hit, inside, sel) && t_hit < h.t) {
+        if (geomIntersect<R, F>(P, g, gi, type, mv, ray, start, t_hit, inside, sel) && t_hit < h.t) {
           h.t = t_hit; h.geom = gi; h.inside = inside; h.checker_sel = sel;
         }
       }
@@ -404,7 +415,7 @@ __device__ inline void closestHit(const Params<R>& P, const float4* __restrict__
   while (sp > 0) {
     const NodeD<R>& nd = P.nodes[stack[--sp]];
     if (COUNT) cnt.node_tests++;
-    if (!boxHit<R>(nd, ray, inv_ray, start, mv)) continue;
+    if (!boxHit<R, F>(nd, ray, inv_ray, start, mv)) continue;
     if (!nd.leaf) { stack[sp++] = nd.left; stack[sp++] = nd.right; continue; }   // right child is popped first (:497-509)
     const int g_end = nd.first + nd.count;
     for (int gi = nd.first; gi < g_end; gi++) {
@@ -413,7 +424,7 @@ __device__ inline void closestHit(const Params<R>& P, const float4* __restrict__
       if (type == G_HOLE) continue;
       if (COUNT) cnt.geom_tests[type]++;
       float t_hit; int inside, sel;
-      if (geomIntersect<R>(P, g, gi, type, mv, ray, start, t_hit, inside, sel) && t_hit < h.t) {
+      if (geomIntersect<R, F>(P, g, gi, type, mv, ray, start, t_hit, inside, sel) && t_hit < h.t) {
         h.t = t_hit; h.geom = gi; h.inside = inside; h.checker_sel = sel;
       }
     }
@@ -422,12 +433,12 @@ __device__ inline void closestHit(const Params<R>& P, const float4* __restrict__
 
 // One candidate of the shadow test: the intersectShadow() of the geom's class.
 // `ray` is normalised, `start` already offset by 1e-3 along it.
-template <typename R>
+template <typename R, int F>
 __device__ inline bool geomShadow(const Params<R>& P, const Geom<R>& g, int gi, const int type, const Moved<R>& mv,
                                   const Vec<R>& ray, const Vec<R>& start, const float t_max, float& t_occ) {
     t_occ = 0.0f;   // on success: a ray parameter at which the ray certainly touches the geom
     if (type == G_RECT || type == G_CHECKER) {
-      Vec<R> A = shiftPoint(mv, g.flags, g.vel, g.p0);
+      Vec<R> A = shiftPoint<R, F>(mv, g.flags, g.vel, g.p0);
       // Checkerboard inherits Rectangle::intersectShadow (eps 1e-4); CheckerboardWithHole
       // has its own with eps 1e-3 (geometry.cpp:2446-2498)
       float eps = (type == G_CHECKER && !(g.flags & GF_HAS_HOLE)) ? 1e-4f : g.eps;
@@ -445,7 +456,7 @@ __device__ inline bool geomShadow(const Params<R>& P, const Geom<R>& g, int gi, 
       }
     } else if (type == G_SPHERE) {  // geometry.cpp:173-197
       const float eps = 1e-3f;
-      Vec<R> sc = start - shiftPoint(mv, g.flags, g.vel, g.p0);
+      Vec<R> sc = start - shiftPoint<R, F>(mv, g.flags, g.vel, g.p0);
       float A = (float)dot(ray, ray);
       float B = (float)(R(2) * dot(ray, sc));
       float C = (float)(dot(sc, sc) - (R)((double)g.f0 * (double)g.f0));
@@ -459,7 +470,7 @@ __device__ inline bool geomShadow(const Params<R>& P, const Geom<R>& g, int gi, 
       return true;
     } else if (type == G_CYL) {  // geometry.cpp:368-417
       const float eps = 1e-3f;
-      Vec<R> c1 = shiftPoint(mv, g.flags, g.vel, g.p0), c2 = shiftPoint(mv, g.flags, g.vel, g.p1);
+      Vec<R> c1 = shiftPoint<R, F>(mv, g.flags, g.vel, g.p0), c2 = shiftPoint<R, F>(mv, g.flags, g.vel, g.p1);
       const Vec<R> axis = g.p2;
       Vec<R> ray_a_proj = ray - dot(ray, axis) * axis;
       Vec<R> sc = start - c1;
@@ -477,7 +488,7 @@ __device__ inline bool geomShadow(const Params<R>& P, const Geom<R>& g, int gi, 
       Vec<R> pt = start + (R)tc * ray;
       if (dot(axis, pt - c1) > R(0) && dot(axis, pt - c2) < R(0) && tc < t_max) { t_occ = tc; return true; }
     } else {  // G_TRI geometry.cpp:555-586
-      Vec<R> A = shiftPoint(mv, g.flags, g.vel, g.p0);
+      Vec<R> A = shiftPoint<R, F>(mv, g.flags, g.vel, g.p0);
       const Vec<R> r1 = g.p1, r2 = g.p2;
       Vec<R> hh = cross(ray, r2);
       float det = (float)dot(r1, hh);
@@ -504,19 +515,19 @@ __device__ inline bool geomShadow(const Params<R>& P, const Geom<R>& g, int gi, 
 // That is reproduced exactly, lazily: geoms are tested directly (slab filter + exact
 // class test) and only a geom that DOES occlude is checked against the reference
 // gather, by running BoundingVolume::intersect on its leaf and every ancestor.
-template <typename R, bool COUNT>
+template <typename R, int F, bool COUNT>
 __device__ inline bool anyHit(const Params<R>& P, const float4* __restrict__ gb, const Moved<R>& mv, const Vec<R>& gather_ray,
                               const Vec<R>& gather_start, const Vec<R>& ray, const Vec<R>& start, float t_max, int skip_owner,
                               Counts& cnt) {
   const Vec<R> inv_ray = mk<R>(R(1) / gather_ray.x, R(1) / gather_ray.y, R(1) / gather_ray.z);   // sray.cwiseInverse() :813
-  if (mv.val == 0.0f && !DRT_FORCE_TREE) {
+  if ((!(F & FT_REFBLUR) || mv.val == 0.0f) && !DRT_FORCE_TREE) {
     const float ix = 1.0f / (float)ray.x, iy = 1.0f / (float)ray.y, iz = 1.0f / (float)ray.z;
     const float ox = -(float)start.x * ix, oy = -(float)start.y * iy, oz = -(float)start.z * iz;   // slabMayHit's hoisted terms
-    const bool cull = !mv.velocity_mode;
+    const bool cull = !((F & FT_VEL) && mv.velocity_mode);
     // distance by which the reference's gather origin runs ahead of the test origin
     const float gather_lead = t_max * 1e-3f;
     const int n = P.n_geoms;
-    const bool smem = n <= DRT_SMEM_GEOMS;
+    const bool smem = !(F & FT_BIG) || n <= DRT_SMEM_GEOMS;
     const SlabRay sr = slabRay(ix, iy, iz, ox, oy, oz, t_max * 1.0001f + 1e-4f);
     for (int g0 = 0; g0 < n; g0 += 32) {
       const int g1 = min(n, g0 + 32);
@@ -530,8 +541,8 @@ __device__ inline bool anyHit(const Params<R>& P, const float4* __restrict__ gb,
         if (type == G_HOLE || g.owner == skip_owner) continue;   // an area light never shadows itself (832-837)
         if (COUNT) cnt.geom_tests[type]++;
         float t_occ;
-        if (!geomShadow<R>(P, g, gi, type, mv, ray, start, t_max, t_occ)) continue;
-        if (mv.velocity_mode) return true;          // time-displaced geometry: no reference tree to consult
+        if (!geomShadow<R, F>(P, g, gi, type, mv, ray, start, t_max, t_occ)) continue;
+        if ((F & FT_VEL) && mv.velocity_mode) return true;          // time-displaced geometry: no reference tree to consult
         // The occluder touches the ray at distance t_occ from the test origin.  If that point
         // lies ahead of the gather origin it is inside the geom's leaf box and every ancestor
         // box (they are padded supersets), so BoundingVolume::intersect returns tmax > 0 for all
@@ -541,7 +552,7 @@ __device__ inline bool anyHit(const Params<R>& P, const float4* __restrict__ gb,
         bool gathered = true;
         for (int ni = g.leaf; ni >= 0 && gathered; ni = P.nodes[ni].parent) {
           if (COUNT) cnt.node_tests++;
-          gathered = boxHit<R>(P.nodes[ni], gather_ray, inv_ray, gather_start, mv);
+          gathered = boxHit<R, F>(P.nodes[ni], gather_ray, inv_ray, gather_start, mv);
         }
         if (gathered) return true;
       }
@@ -554,7 +565,7 @@ __device__ inline bool anyHit(const Params<R>& P, const float4* __restrict__ gb,
   while (sp > 0) {
     const NodeD<R>& nd = P.nodes[stack[--sp]];
     if (COUNT) cnt.node_tests++;
-    if (!boxHit<R>(nd, gather_ray, inv_ray, gather_start, mv)) continue;
+    if (!boxHit<R, F>(nd, gather_ray, inv_ray, gather_start, mv)) continue;
     if (!nd.leaf) { stack[sp++] = nd.left; stack[sp++] = nd.right; continue; }
     const int g_end = nd.first + nd.count;
     for (int gi = nd.first; gi < g_end; gi++) {
@@ -564,7 +575,7 @@ __device__ inline bool anyHit(const Params<R>& P, const float4* __restrict__ gb,
       if (g.owner == skip_owner) continue;
       if (COUNT) cnt.geom_tests[type]++;
       float t_occ;
-      if (geomShadow<R>(P, g, gi, type, mv, ray, start, t_max, t_occ)) return true;
+      if (geomShadow<R, F>(P, g, gi, type, mv, ray, start, t_max, t_occ)) return true;
     }
   }
   return false;
@@ -593,7 +604,7 @@ __device__ __forceinline__ float meshTriT(const MeshTri<R>& tr, const Vec<R>& ra
 // any hit with 1e-3 < t < t_max (Triangle::intersectShadow geometry.cpp:555-586) that the
 // reference would also have gathered (its gather origin runs ahead by |sray|*1e-3, :814; a
 // mesh triangle stands in its own leaf box: bounds +- 1e-2, geometry.cpp:2653-2654).
-template <typename R, bool COUNT, bool CLOSEST>
+template <typename R, int F, bool COUNT, bool CLOSEST>
 __device__ bool meshTraverse(const Params<R>& P, const Vec<R>& ray, const Vec<R>& start, float t_limit, HitRec* h,
                              const Vec<R>& gather_ray, const Vec<R>& gather_start, Counts& cnt) {
   const float ox = (float)start.x, oy = (float)start.y, oz = (float)start.z;
@@ -647,7 +658,7 @@ __device__ bool meshTraverse(const Params<R>& P, const Vec<R>& ray, const Vec<R>
           nd.leaf = 1;
           Moved<R> still; still.val = 0; still.time = 0; still.velocity_mode = 0;
           const Vec<R> inv = mk<R>(R(1) / gather_ray.x, R(1) / gather_ray.y, R(1) / gather_ray.z);
-          if (boxHit<R>(nd, gather_ray, inv, gather_start, still)) return true;
+          if (boxHit<R, F>(nd, gather_ray, inv, gather_start, still)) return true;
         }
       }
     }
@@ -789,18 +800,19 @@ struct alignas(16) HitTask {
 
 // Returns true when the ray hit something (h filled in).  `motion` is -1 unless this task is
 // on the "last invocation" chain that decides in_motion (quirk Q4), else the new flag value.
-template <typename R, bool COUNT>
+template <typename R, int F, bool COUNT>
 __device__ inline bool traceRay(const Params<R>& P, const float4* __restrict__ gb, const Task<R>& T, HitRec& h, int& motion,
                                 Counts& cnt) {
   motion = -1;
   if (T.depth == 0) return false;                                       // :489
   if (COUNT) cnt.rays++;
-  Moved<R> mv; mv.val = blurVal(P, T.dt); mv.time = (R)T.dt; mv.velocity_mode = (P.blur_mode == 1 && T.dt != 0.0f);
-  closestHit<R, COUNT>(P, gb, mv, T.dir, T.org, h, cnt);
-  if (P.n_mesh_tris > 0) meshTraverse<R, COUNT, true>(P, T.dir, T.org, h.t, &h, T.dir, T.org, cnt);
-  if (T.bits & TASK_CHAIN) motion = 0;                                              // :519
+  const Moved<R> mv = makeMoved<R, F>(P, T.dt);
+  closestHit<R, F, COUNT>(P, gb, mv, T.dir, T.org, h, cnt);
+  if ((F & FT_MESH) && P.n_mesh_tris > 0) meshTraverse<R, F, COUNT, true>(P, T.dir, T.org, h.t, &h, T.dir, T.org, cnt);
+  // the in_motion chain only matters when a blur re-trace can follow
+  if ((F & (FT_VEL | FT_REFBLUR)) && (T.bits & TASK_CHAIN)) motion = 0;             // :519
   if (h.geom < 0) return false;                                         // :541-544
-  if (T.bits & TASK_CHAIN) {
+  if ((F & (FT_VEL | FT_REFBLUR)) && (T.bits & TASK_CHAIN)) {
     const int owner = h.geom >= P.n_geoms ? P.mesh_prim : P.geoms[h.geom].owner;
     motion = (P.prims[owner].flags & 2) ? 1 : 0;                        // DRT_FLAG_MOTION, :564
   }
@@ -849,18 +861,18 @@ struct PairOut {
 template <typename R>
 __host__ __device__ constexpr size_t pairOutBytes() { return (size_t)32 * DRT_PAIR_LIGHTS * (3 * sizeof(R) + sizeof(int)); }
 
-template <typename R, bool COUNT>
+template <typename R, int F, bool COUNT>
 __device__ void shadeA(const Params<R>& P, const Task<R>& T, const HitRec& h, Task<R>* stack, int& n_out, double (&add)[3],
                        bool& has_add, bool& aborted, ShadeState<R>& S, Counts& cnt) {
   int sp = 0;
   n_out = 0; has_add = false;
   add[0] = add[1] = add[2] = 0.0;
-  Moved<R> mv; mv.val = blurVal(P, T.dt); mv.time = (R)T.dt; mv.velocity_mode = (P.blur_mode == 1 && T.dt != 0.0f);
+  const Moved<R> mv = makeMoved<R, F>(P, T.dt);
   S.lights = false; S.aborted = false; S.early = false; S.hits = 0; S.tmp[0] = S.tmp[1] = S.tmp[2] = 0.0; S.mv = mv;
   do {
     const Vec<R> ray = T.dir, eye = T.org;
     const float k = T.k;
-    const int mesh_tri = h.geom >= P.n_geoms ? h.geom - P.n_geoms : -1;
+    const int mesh_tri = ((F & FT_MESH) && h.geom >= P.n_geoms) ? h.geom - P.n_geoms : -1;
     const int owner = mesh_tri >= 0 ? P.mesh_prim : P.geoms[h.geom].owner;
     const PrimD<R>& pr = P.prims[owner];
 
@@ -868,15 +880,15 @@ __device__ void shadeA(const Params<R>& P, const Task<R>& T, const HitRec& h, Ta
     // ---- getNorm of the hit class ------------------------------------------------
     Vec<R> normal;
     if (pr.type == 0) {                                                 // Sphere geometry.cpp:199-204
-      Vec<R> nn = isectP - shiftPoint(mv, 0, pr.vel, pr.pA);
+      Vec<R> nn = isectP - shiftPoint<R, F>(mv, 0, pr.vel, pr.pA);
       normal = nn / norm(nn);
     } else if (pr.type == 1 || pr.type == 7) {                          // Cylinder geometry.cpp:419-425
-      Vec<R> pc = isectP - shiftPoint(mv, 0, pr.vel, pr.pA);
+      Vec<R> pc = isectP - shiftPoint<R, F>(mv, 0, pr.vel, pr.pA);
       normal = normalized(pc - dot(pc, pr.pG) * pr.pG);
     } else if (pr.type == 4) {                                          // RectPrismV2 geometry.cpp:863-920
       const float eps = 1e-3f;
-      Vec<R> dA = normalized(isectP - shiftPoint(mv, 0, pr.vel, pr.pA));
-      Vec<R> dG = normalized(isectP - shiftPoint(mv, 0, pr.vel, pr.pG));
+      Vec<R> dA = normalized(isectP - shiftPoint<R, F>(mv, 0, pr.vel, pr.pA));
+      Vec<R> dG = normalized(isectP - shiftPoint<R, F>(mv, 0, pr.vel, pr.pG));
       float pa_bot = fabsf((float)dot(dA, pr.n0)), pg_bot = fabsf((float)dot(dG, pr.n0));
       float pa_right = fabsf((float)dot(dA, pr.n1)), pg_right = fabsf((float)dot(dG, pr.n1));
       float pa_front = fabsf((float)dot(dA, pr.n2)), pg_front = fabsf((float)dot(dG, pr.n2));
@@ -910,7 +922,7 @@ __device__ void shadeA(const Params<R>& P, const Task<R>& T, const HitRec& h, Ta
       float k_refl = 1, k_refr = 1;
       int n_children = 0;        // children pushed for this node, in the reference's call order
       int first_child = sp;
-      if (pr.material == 1) {                                           // glass :592-626
+      if ((F & FT_GLASS) && pr.material == 1) {                         // glass :592-626
         float cos_theta = (float)dot(normal, -in);
         float sin_theta = (float)sqrt(1.0 - (double)cos_theta * (double)cos_theta);
         float refr_1 = h.inside ? P.refr_glass : P.refr_air;
@@ -1006,7 +1018,7 @@ __device__ void shadeA(const Params<R>& P, const Task<R>& T, const HitRec& h, Ta
     // ---- local shading (:772-960) ------------------------------------------------
     if (pr.flags & 1) {                                                 // hit a light shape :775-789
       if (pr.name == 2) {                                               // spherelight
-        float hitdot = (float)dot(in, normalized(shiftPoint(mv, 0, pr.vel, pr.center) - isectP));
+        float hitdot = (float)dot(in, normalized(shiftPoint<R, F>(mv, 0, pr.vel, pr.center) - isectP));
         double f = 0.1 * (double)hitdot + 0.05 * pow5((double)hitdot) + 0.9;
         for (int c = 0; c < 3; c++) add[c] += ((double)k * (double)shape_color[c]) * f;
         has_add = true;
@@ -1029,12 +1041,15 @@ __device__ void shadeA(const Params<R>& P, const Task<R>& T, const HitRec& h, Ta
 }
 
 // LightPrimitive::sampleRay (:802) + the shadow test (:806-855) for one (hit, light) pair.
-template <typename R, bool COUNT>
+template <typename R, int F, bool COUNT>
 __device__ void shadowPair(const Params<R>& P, const float4* __restrict__ gb, const PairIn<R>& in, int li, const PairOut<R>& out, const int oi,
                            Counts& cnt) {
   const LightD<R>& L = P.lights[li];
   const Vec<R> isectP = in.isectP;
-  Moved<R> mv; mv.val = in.val; mv.time = (R)in.dt; mv.velocity_mode = (P.blur_mode == 1 && in.dt != 0.0f);
+  Moved<R> mv;                                      // makeMoved, with blurVal(P, dt) as shadeA evaluated it
+  mv.val = (F & FT_REFBLUR) ? in.val : 0.0f;
+  mv.time = (F & FT_VEL) ? (R)in.dt : R(0);
+  mv.velocity_mode = (F & FT_VEL) ? ((((F & FT_REFBLUR) ? P.blur_mode == 1 : true) && in.dt != 0.0f) ? 1 : 0) : 0;
   Vec<R> sray;
   if (L.type == 0) sray = L.center - isectP;                        // pointLight geometry.cpp:2751-2754
   else if (L.type == 2) sray = rectSample<R>(L.A, L.B, L.D, in.path, rng_dim_light(li, 0)) - isectP;   // :2845-2849
@@ -1045,14 +1060,14 @@ __device__ void shadowPair(const Params<R>& P, const float4* __restrict__ gb, co
   if (COUNT) cnt.shadow_rays++;
   // candidates are gathered along the UNNORMALISED sray from isectP + sray*1e-3 (:814),
   // occlusion is tested along the normalised one from isectP + s^*1e-3 (:838)
-  bool occluded = anyHit<R, COUNT>(P, gb, mv, sray, isectP + sray * R(1e-3), sdir, isectP + sdir * R(1e-3), t_max, L.prim_index, cnt);
-  if (!occluded && P.n_mesh_tris > 0)
-    occluded = meshTraverse<R, COUNT, false>(P, sdir, isectP + sdir * R(1e-3), t_max, nullptr, sray, isectP + sray * R(1e-3), cnt);
+  bool occluded = anyHit<R, F, COUNT>(P, gb, mv, sray, isectP + sray * R(1e-3), sdir, isectP + sdir * R(1e-3), t_max, L.prim_index, cnt);
+  if ((F & FT_MESH) && !occluded && P.n_mesh_tris > 0)
+    occluded = meshTraverse<R, F, COUNT, false>(P, sdir, isectP + sdir * R(1e-3), t_max, nullptr, sray, isectP + sray * R(1e-3), cnt);
   out.state[oi] = occluded ? 0 : 1;
 }
 
 // The rest of the light loop (:856-959) for lights [l0, l1) of one hit, in order.
-template <typename R, bool COUNT>
+template <typename R, int F, bool COUNT>
 __device__ void shadeB(const Params<R>& P, ShadeState<R>& S, const PairOut<R>& res, const int hit_lane, int l0, int l1, Counts& cnt) {
   const PrimD<R>& pr = P.prims[S.prim];
   for (int li = l0; li < l1 && !S.early && !S.aborted; li++) {
@@ -1064,11 +1079,11 @@ __device__ void shadeB(const Params<R>& P, ShadeState<R>& S, const PairOut<R>& r
     const Vec<R> sray = mk<R>(res.x[oi], res.y[oi], res.z[oi]);
     const Vec<R> sdir = normalized(sray);
       // ---- texture (:859-893) ---------------------------------------------------
-      if (pr.flags & 4) {
+      if ((F & FT_TEX) && (pr.flags & 4)) {
         float u = 0, v = 0; int type = 0;
         if (pr.type == 3 || pr.type == 5 || pr.type == 4) {            // Rectangle::getUV (prism: top face)
-          Vec<R> uA = shiftPoint(S.mv, pr.name == 1 ? GF_NAME_RECTANGLE : 0, pr.vel, pr.uvA);
-          Vec<R> uD = shiftPoint(S.mv, pr.name == 1 ? GF_NAME_RECTANGLE : 0, pr.vel, pr.uvD);
+          Vec<R> uA = shiftPoint<R, F>(S.mv, pr.name == 1 ? GF_NAME_RECTANGLE : 0, pr.vel, pr.uvA);
+          Vec<R> uD = shiftPoint<R, F>(S.mv, pr.name == 1 ? GF_NAME_RECTANGLE : 0, pr.vel, pr.uvD);
           u = (float)(norm(cross(S.isectP - uA, pr.uv_ad)) / pr.uv_den_u);
           v = (float)(norm(cross(S.isectP - uD, pr.uv_dc)) / pr.uv_den_v);
           type = 1;
@@ -1111,9 +1126,9 @@ __device__ void shadeB(const Params<R>& P, ShadeState<R>& S, const PairOut<R>& r
             }
           } else type = 0;
         } else if (pr.type == 2) {                                      // Triangle::getUV geometry.cpp:447-486
-          Vec<R> tA = shiftPoint(S.mv, 0, pr.vel, pr.tA), tB = shiftPoint(S.mv, 0, pr.vel, pr.tB), tC = shiftPoint(S.mv, 0, pr.vel, pr.tC);
+          Vec<R> tA = shiftPoint<R, F>(S.mv, 0, pr.vel, pr.tA), tB = shiftPoint<R, F>(S.mv, 0, pr.vel, pr.tB), tC = shiftPoint<R, F>(S.mv, 0, pr.vel, pr.tC);
           const float* tuv = pr.tuv;
-          if (S.tri >= 0) { const MeshTri<R>& tr = P.mesh_tris[S.tri]; tA = tr.A; tB = tr.B; tC = tr.C; tuv = tr.uv; }
+          if ((F & FT_MESH) && S.tri >= 0) { const MeshTri<R>& tr = P.mesh_tris[S.tri]; tA = tr.A; tB = tr.B; tC = tr.C; tuv = tr.uv; }
           Vec<R> nn = cross(tB - tA, tC - tA);
           Vec<R> n_a = cross(tC - tB, S.isectP - tB), n_b = cross(tA - tC, S.isectP - tC);
           float n_sq = (float)dot(nn, nn);
@@ -1240,7 +1255,7 @@ __host__ __device__ constexpr size_t waveScratchBytes(int pool_cap) {
 // from the top through a shared-memory cursor until the phase's work is gone, so all lanes of
 // all warps stay busy and a phase ends within one 32-item chunk of the last warp (with
 // warp-private pools 27 % of the stall samples were barrier waits).
-template <typename R, bool COUNT>
+template <typename R, int F, bool COUNT>
 __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) render_wave(const __grid_constant__ Params<R> P) {
   // dynamic shared memory (waveDynSmemBytes): [ acc: slots x 3 x u64 | flags: slots x u32 | order: hits x u16 | hkey: hits x u8 ]
   extern __shared__ __align__(16) unsigned char s_dyn[];
@@ -1254,7 +1269,7 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
   // slab-filter table of the whole scene, staged once per persistent CTA (48 B per pair of geoms)
   __shared__ float4 s_gb[3 * DRT_SMEM_GEOMS / 2 + 2 * DRT_SMEM_GEOMS / 8];
   const float4* gb = P.gbounds;
-  if (P.n_geoms <= DRT_SMEM_GEOMS) {
+  if (!(F & FT_BIG) || P.n_geoms <= DRT_SMEM_GEOMS) {
     for (int i = threadIdx.x; i < 3 * ((P.n_geoms + 1) / 2) + 2 * ((P.n_geoms + 7) / 8); i += blockDim.x) s_gb[i] = P.gbounds[i];
     gb = s_gb;
   }
@@ -1287,7 +1302,7 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
       const long long idx0 = s_idx0;
       __syncthreads();
       bool finalize = false;
-      if (state == 1 && P.blur_samples > 0) {
+      if ((F & (FT_VEL | FT_REFBLUR)) && state == 1 && P.blur_samples > 0) {
         // motion blur: re-trace the samples whose in_motion flag ended up set
         // (render_final_project.cpp:1095-1210); the extra traces go through the same pool
         int mine = 0;
@@ -1388,7 +1403,7 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
         const unsigned int f = ((volatile unsigned int*)sfl)[H.T.slot];
         if (!(f & SF_ABORT)) {                                          // an aborted sample spawns no more work (Q15)
           HitRec h; int motion;
-          hit = traceRay<R, COUNT>(P, gb, H.T, h, motion, cnt);
+          hit = traceRay<R, F, COUNT>(P, gb, H.T, h, motion, cnt);
           unsigned int orf = 0;
           if ((H.T.bits & TASK_ROOT) && hit) orf |= SS_HIT;
           if (motion == 1) orf |= SS_MOTION;
@@ -1462,7 +1477,7 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
         poolLoad(H, (const uint4*)hits, (size_t)DRT_CTA_HITS, (int)s_order[end - 1 - lane]);
         HitRec h; h.t = H.t; h.geom = H.geom; h.inside = H.inside; h.checker_sel = H.checker_sel;
         slot = H.T.slot;
-        shadeA<R, COUNT>(P, H.T, h, kids, nk, add, has_add, aborted, S, cnt);
+        shadeA<R, F, COUNT>(P, H.T, h, kids, nk, add, has_add, aborted, S, cnt);
         if (!aborted && S.lights) { pin.isectP = S.isectP; pin.path = H.T.path; pin.val = S.mv.val; pin.dt = H.T.dt; pin.want = 1; }
       }
       // -- step B (lane = (hit, light) pair): light sample + shadow ray, DRT_PAIR_LIGHTS lights at a time; a pair lane
@@ -1475,13 +1490,15 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
           const int lj = on ? pid / take : 0, hh = on ? pid - lj * take : 0;   // light-major: one pass of the warp heads for one light
           PairIn<R> q;
           q.isectP = mk<R>(__shfl_sync(FULL, pin.isectP.x, hh), __shfl_sync(FULL, pin.isectP.y, hh), __shfl_sync(FULL, pin.isectP.z, hh));
-          q.path = __shfl_sync(FULL, pin.path, hh); q.val = __shfl_sync(FULL, pin.val, hh); q.dt = __shfl_sync(FULL, pin.dt, hh);
+          q.path = __shfl_sync(FULL, pin.path, hh);
+          q.val = (F & FT_REFBLUR) ? __shfl_sync(FULL, pin.val, hh) : 0.f;
+          q.dt = (F & (FT_VEL | FT_REFBLUR)) ? __shfl_sync(FULL, pin.dt, hh) : 0.f;
           q.want = __shfl_sync(FULL, pin.want, hh);
-          if (on && q.want) shadowPair<R, COUNT>(P, gb, q, l0 + lj, pairout, lj * 32 + hh, cnt);
+          if (on && q.want) shadowPair<R, F, COUNT>(P, gb, q, l0 + lj, pairout, lj * 32 + hh, cnt);
         }
         __syncwarp();
         // -- step C (lane = hit again): texture + BRDF of the unoccluded lights, in light order
-        if (active && !aborted && S.lights) shadeB<R, COUNT>(P, S, pairout, lane, l0, l0 + nl, cnt);
+        if (active && !aborted && S.lights) shadeB<R, F, COUNT>(P, S, pairout, lane, l0, l0 + nl, cnt);
         __syncwarp();
       }
       if (active) {
@@ -1495,8 +1512,10 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
           for (int c = 0; c < 3; c++) {
             const double v = add[c];
             if (v != v) orf |= SS_NAN(c);
-            else if (v > 1073741824.0) orf |= (isinf(v) ? SS_PINF(c) : 0u), atomicAdd(&acc[slot][c], (unsigned long long)(1ll << 62));
-            else if (v < -1073741824.0) orf |= (isinf(v) ? SS_NINF(c) : 0u), atomicAdd(&acc[slot][c], (unsigned long long)(-(1ll << 62)));
+            // beyond the fixed-point range: recorded like an infinity (the output clamps to [0, 1] anyway), never added --
+            // two saturated terms would wrap the 64-bit sum
+            else if (v > 1073741824.0) orf |= SS_PINF(c);
+            else if (v < -1073741824.0) orf |= SS_NINF(c);
             else atomicAdd(&acc[slot][c], (unsigned long long)__double2ll_rn(v * 4294967296.0));
           }
           if (orf) atomicOr(&sfl[slot], orf);

@@ -1,0 +1,5 @@
+// R = float: single-precision variant (FMA contraction on).
+// render_wave instantiations of group 0 (drt_launch_impl.cuh).
+#define DRT_REAL float
+#define DRT_GROUP 0
+#include "drt_launch_impl.cuh"

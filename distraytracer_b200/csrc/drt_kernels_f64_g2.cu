@@ -1,0 +1,5 @@
+// R = double: reference precision.  Compile with -fmad=false (see drt_launch.h).
+// render_wave instantiations of group 2 (drt_launch_impl.cuh).
+#define DRT_REAL double
+#define DRT_GROUP 2
+#include "drt_launch_impl.cuh"

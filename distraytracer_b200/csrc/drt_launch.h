@@ -31,12 +31,38 @@
 #endif
 #define DRT_SMEM_GEOMS 256     // slab-filter entries staged in shared memory per CTA
 
+// ---- feature mask of a render_wave instantiation ------------------------------------------------------------------
+// render_wave is compiled once per feature set and the host picks the smallest instantiation that covers the scene and
+// settings of a render call: code a scene cannot reach (mesh traversal, time-displaced geometry, the replayed reference
+// tree of reference-mode blur, glass, textures) costs registers and instruction-cache space even when it never runs
+// (ncu round 1: 11.9 % of the stall samples "no_instructions" at 16 k SASS instructions, 0.5 G spill instructions per band).
+enum WaveFeat {
+  FT_MESH = 1,      // a triangle mesh (LBVH traversal, drt_lbvh.cuh) is present
+  FT_VEL = 2,       // blur re-traces with per-primitive velocities (DRT_BLUR_VELOCITY) can occur
+  FT_REFBLUR = 4,   // reference-mode blur re-traces can occur: "rectangle" shapes move, the reference tree is walked
+  FT_GLASS = 8,     // some primitive is glass (refraction children)
+  FT_TEX = 16,      // some primitive is textured
+  FT_BIG = 32,      // more geoms than the shared-memory slab table holds (DRT_SMEM_GEOMS)
+  FT_ALL = 63
+};
+
+// the instantiated masks (drt_launch_impl.cuh must hold one DRT_WAVE_CASE per entry); FT_ALL last
+#define DRT_WAVE_FEATS {FT_GLASS | FT_TEX, 0, FT_TEX, FT_VEL, FT_MESH | FT_TEX, FT_MESH | FT_VEL | FT_TEX, FT_REFBLUR | FT_GLASS | FT_TEX, FT_ALL}
+
 namespace drt {
+// feature masks this precision's translation units instantiate, `n` of them; the last one is FT_ALL
+const int* waveFeatList(int* n);
+// smallest instantiated superset of `need`
+int waveFeatPick(int need);
 // persistent grid of render_wave: blocks that are co-resident on the current device
 template <typename R> int waveGridBlocks();
 // bytes of scratch (ray pools of `pool_cap` tasks, hit buffers, shadow-pair buffers) a grid of `blocks` CTAs needs
 template <typename R> size_t wavePoolBytes(int blocks, int pool_cap);
-template <typename R> void launchRenderSamples(const Params<R>& P, bool collect, int blocks, cudaStream_t q);
+// `feat`: what the call needs (any mask; the launcher maps it to an instantiation).  Returns the mask launched.
+template <typename R> int launchRenderSamples(const Params<R>& P, bool collect, int feat, int blocks, cudaStream_t q);
+// one translation unit per (precision, group) instantiates part of the list: kernel of mask `feat`, or nullptr
+template <typename R> using WaveFnT = void (*)(Params<R>);
+template <typename R, int GROUP> WaveFnT<R> waveKernelOfGroup(int feat, bool collect);
 template <typename R> void launchCloudCorners(const Params<R>& P, cudaStream_t q);
 template <typename R> void launchResolve(const Params<R>& P, int row0, int rows, cudaStream_t q);
 }  // namespace drt

@@ -88,6 +88,15 @@ def default_prim():
     return p
 
 
+def check_frame_buffer(out, height, width):
+    """The C side writes height*width*3 bytes through a raw pointer: anything but a C-contiguous uint8
+    (height, width, 3) array would be silent memory corruption."""
+    if not isinstance(out, np.ndarray) or out.dtype != np.uint8 or out.shape != (height, width, 3) or not out.flags["C_CONTIGUOUS"]:
+        raise ValueError(f"output buffer must be a C-contiguous uint8 array of shape ({height}, {width}, 3)")
+    if not out.flags["WRITEABLE"]:
+        raise ValueError("output buffer is read-only")
+
+
 class DeviceScene:
     """drt_scene handle: the scene resident in one GPU's HBM."""
 
@@ -128,6 +137,7 @@ class DeviceScene:
         tile = self._tile(settings, tile)
         if out is None:
             out = np.empty((tile.height, tile.width, 3), dtype=np.uint8)
+        check_frame_buffer(out, tile.height, tile.width)
         _check(lib().drt_render(self.handle, C.byref(settings), C.byref(tile), out.ctypes.data,
                                 C.byref(counters) if counters is not None else None))
         return out

@@ -1,7 +1,7 @@
 """Scene builders for the BASELINE.json configurations, producing the POD scene of
 include/drt.h.  They play the role of the reference's build*() functions in scene.h
-for the synthetic benchmark configurations; parity fixtures for the reference's own
-scenes live in tests/golden/.
+for the synthetic benchmark configurations.  The exported reference scenes they start
+from are package data (distraytracer_b200/data/).
 """
 import math
 import os
@@ -11,8 +11,13 @@ import numpy as np
 from . import abi
 from .scene import Scene, load_fixture
 
-_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-GOLDEN = os.path.join(_ROOT, "tests", "golden")
+DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
+
+
+def data_path(name):
+    """A file of the package's own data directory (written by tools/make_package_data.py): the reference builders'
+    exported scenes the configurations start from, and the mocap clip."""
+    return os.path.join(DATA, name)
 
 
 def _v(dst, src):
@@ -132,8 +137,8 @@ def checkerboard(a, b, c, d, col1, col2, S, material=abi.MAT_NONE, model=abi.MOD
 def config1():
     """BASELINE config 1: `./render test checkertexture` (render_final_project.cpp:1840-1853,
     scene.h:3052-3163) at 640x480, 1 spp.  The scene is the reference builder's own output
-    (tests/golden/checkertexture.npz, exported by oracle/ref_driver.cpp)."""
-    scene, settings, _ = load_fixture(os.path.join(GOLDEN, "checkertexture.npz"))
+    (data/checkertexture_scene.npz, exported by oracle/ref_driver.cpp)."""
+    scene, settings, _ = load_fixture(data_path("checkertexture_scene.npz"))
     settings.xRes, settings.yRes, settings.antialias_samples, settings.aperture = 640, 480, 1, 0.0
     return scene, settings
 
@@ -162,7 +167,7 @@ def config2(xres=1920, yres=1080, spp=64):
 def config3(xres=1920, yres=1080, spp=256):
     """BASELINE config 3: Oren-Nayar spheres (buildSceneReflectance, scene.h:3668-3694) in front of
     the value-noise cloud background (perlin_cloud), 1080p, 256 spp."""
-    scene, settings, _ = load_fixture(os.path.join(GOLDEN, "reflectance.npz"))
+    scene, settings, _ = load_fixture(data_path("reflectance_scene.npz"))
     prims = [abi.copy_struct(p) for p in scene.prims]
     for p in prims:
         if p.model != abi.MODEL_OREN_NAYAR and p.material == abi.MAT_NONE:
@@ -176,9 +181,9 @@ def config4_frame(frame, xres=1920, yres=1080, spp=16, bones=None):
     """BASELINE config 4: mocap skeleton (29-30 bone cylinders, scene.h:637-659) over a
     checkerboard floor with two sphere lights (buildSceneChkpt2 layout, scene.h:3557-3666),
     bones flagged `motion` and given the velocity to their pose one frame later."""
-    scene, settings, _ = load_fixture(os.path.join(GOLDEN, "chkpt2_mocap.npz"))
+    scene, settings, _ = load_fixture(data_path("chkpt2_mocap_scene.npz"))
     if bones is None:
-        bones = np.load(os.path.join(GOLDEN, "mocap_bones_0_119.npy"))
+        bones = np.load(data_path("mocap_bones_0_119.npy"))
     f0 = int(frame) % bones.shape[0]
     f1 = min(f0 + 1, bones.shape[0] - 1)
     prims, k = [], 0
@@ -251,7 +256,7 @@ def mesh_to_prims(mesh):
 def config5(n=708, xres=3840, yres=2160, spp=64):
     """BASELINE config 5: textured ~1M-triangle terrain, DOF + motion blur (a moving sphere over the static mesh,
     blur_samples 2) + point light at the eye, 4K 64 spp."""
-    base, settings, _ = load_fixture(os.path.join(GOLDEN, "checkertexture.npz"))
+    base, settings, _ = load_fixture(data_path("checkertexture_scene.npz"))
     mesh = terrain_mesh(n)
     mesh["material"] = mesh_material(tex_frame=2)            # textures/floor.jpeg of the fixture
     ball = sphere((0.0, 1.6, 0.0), 0.7, (1.0, 0.2, 0.2), motion=True)

@@ -51,8 +51,8 @@ def render_frame_blocks(handles, settings, frame_rgb, rows=15):
     import threading
     import time
     yres, xres = settings.yRes, settings.xRes
-    if frame_rgb.shape != (yres, xres, 3):
-        raise ValueError("frame_rgb must be (yRes, xRes, 3)")
+    from .runtime import check_frame_buffer
+    check_frame_buffer(frame_rgb, yres, xres)
     blocks = row_blocks(yres, rows)
     nxt, lock, errs = [0], threading.Lock(), []
 
@@ -77,6 +77,30 @@ def render_frame_blocks(handles, settings, frame_rgb, rows=15):
     if errs:
         raise errs[0]
     return time.perf_counter() - t0
+
+
+class FrameGroup:
+    """One scene replicated on several GPUs of a box, for rendering single frames on all of them (BASELINE configs 3 and 5;
+    SURVEY.md 8e).  `render` returns the wall-clock seconds of one frame, written into `frame_rgb` ((yRes, xRes, 3) uint8,
+    PPM row order; pinned memory keeps the device-to-host copies asynchronous)."""
+
+    def __init__(self, scene, devices, streams_per_gpu=2, rows=15):
+        from .runtime import DeviceScene
+        self.devices = list(devices)
+        self.rows = rows
+        self.handles = [[DeviceScene(scene, d) for _ in range(streams_per_gpu)] for d in self.devices]
+        self.method = (f"row blocks of {rows} rows claimed dynamically by one host thread per scene handle, "
+                       f"{streams_per_gpu} handles (streams) per GPU")
+
+    def render(self, settings, frame_rgb, gpus=None):
+        use = self.handles[:gpus] if gpus else self.handles
+        return render_frame_blocks([h for g in use for h in g], settings, frame_rgb, self.rows)
+
+    def close(self):
+        for g in self.handles:
+            for h in g:
+                h.close()
+        self.handles = []
 
 
 def max_over_ranks(value, dist=None, device=None):

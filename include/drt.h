@@ -258,6 +258,7 @@ typedef struct drt_counters {
   int32_t collect;
   float kernel_ms;        /* CUDA-event time of the render kernels on their stream */
   int32_t kernel_launches;
+  int32_t kernel_variant; /* feature mask of the render_wave instantiation that ran (csrc/drt_launch.h WaveFeat), -1: none */
   uint64_t samples;       /* camera samples (primary rays incl. blur re-traces are separate) */
   uint64_t rays;          /* rayColor invocations that traversed (primary+secondary) */
   uint64_t shadow_rays;
@@ -267,6 +268,9 @@ typedef struct drt_counters {
   uint64_t noise_evals;   /* ValueNoise_3D evaluations */
 } drt_counters;
 
+/* A scene handle owns one CUDA stream, its scratch buffers and its timing events: calls on the SAME handle (render,
+ * update, pose) must not overlap -- drive one handle from one thread at a time.  Different handles, on the same or on
+ * different devices, are independent. */
 typedef struct drt_scene drt_scene;
 
 /* Number of usable CUDA devices (0 if none; never negative). */
