@@ -967,4 +967,11 @@ float drt_debug_rng(uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t chi
   return rng_u01(rng_key_child(sk, child), dim);
 }
 
+// Step i of the keyed lens-sample shuffle of a pixel (j = round(u*i), helpers.h:274), and the lens point that ends up at
+// position `sample` of `n_lens`, from the same inline functions the kernels use.
+int drt_debug_shuffle_j(uint32_t seed, uint32_t pixel, int32_t i) { return rng_shuffle_j(rng_key_pixel(seed, pixel), i); }
+int drt_debug_lens_index(uint32_t seed, uint32_t pixel, int32_t sample, int32_t n_lens) {
+  return lensIndexScan(rng_key_pixel(seed, pixel), sample, n_lens);
+}
+
 }  // extern "C"

@@ -1201,9 +1201,48 @@ __device__ void shadeB(const Params<R>& P, ShadeState<R>& S, const PairOut<R>& r
 #define SS_PINF(c) (2048u << (c))
 #define SS_NINF(c) (16384u << (c))
 
+// ---- the per-pixel shuffle of the lens samples (helpers.h:270-279, render_final_project.cpp:1059) -------------------
+// The reference draws antialias_samples lens points per pixel (getDOFSamples), shuffles them with
+// `for i = size-1 .. 1: j = round(u * i); swap(v[i], v[j])` and hands point i of the shuffled list to camera sample i.
+// Here every draw is keyed, so camera sample s only needs to know WHICH lens point ended up at position s.
+//
+// lensIndexScan: that index for one sample, by undoing the swaps in reverse order (only steps i >= s can move it).
 template <typename R>
-__device__ __noinline__ void primaryRay(const Params<R>& P, long long gidx, Vec<R>& org, Vec<R>& dir, uint32_t& skey, int& pi, int& pj,
-                                  int& px, int& py) {
+__device__ __forceinline__ uint32_t pixelKeyOf(const Params<R>& P, const int pt) {
+  const int x = P.x0 + pt % P.w, y = P.y0 + pt / P.w;
+  return rng_key_pixel(P.seed, (uint32_t)(y * P.xRes + x));
+}
+// lensPermsFill: the whole permutation of every pixel the CTA's batch [g0, g0 + nv) touches, into `perm` (shared memory,
+// `cap` 16-bit entries: permutations in the lower half, the swap targets j_i in the upper half).  All threads hash the
+// j_i in parallel, then one thread per pixel applies its swaps in order.  Returns false (CTA-uniform) when the batch's
+// permutations do not fit; primaryRay then falls back to lensIndexScan.  Ends with a barrier.
+template <typename R>
+__device__ inline bool lensPermsFill(const Params<R>& P, const long long g0, const int nv, unsigned short* perm, const int cap) {
+  if (!(P.aperture > 0) || nv <= 0) return false;
+  const int A = P.antialias_samples;
+  const int pt0 = (int)(g0 / P.spp), npx = (int)((g0 + nv - 1) / P.spp) - pt0 + 1;
+  if ((long long)npx * A > cap / 2 || A > 65535) return false;
+  unsigned short* jt = perm + cap / 2;
+  for (int e = threadIdx.x; e < npx * A; e += blockDim.x) {
+    const int q = e / A, i = e - q * A;
+    jt[e] = (unsigned short)(i ? rng_shuffle_j(pixelKeyOf(P, pt0 + q), i) : 0);
+    perm[e] = (unsigned short)i;
+  }
+  __syncthreads();
+  for (int q = threadIdx.x; q < npx; q += blockDim.x) {
+    unsigned short* v = perm + q * A;
+    const unsigned short* j = jt + q * A;
+    for (int i = A - 1; i > 0; i--) { const unsigned short a = v[i], b = v[j[i]]; v[i] = b; v[j[i]] = a; }
+  }
+  __syncthreads();
+  return true;
+}
+
+// `perm`: lensPermsFill's table for the batch starting at pixel `perm_pt0`, or nullptr (scan per sample).
+// `lens` false: only the pixel / corner outputs are wanted.
+template <typename R>
+__device__ __noinline__ void primaryRay(const Params<R>& P, long long gidx, const unsigned short* perm, const int perm_pt0, const bool lens,
+                                        Vec<R>& org, Vec<R>& dir, uint32_t& skey, int& pi, int& pj, int& px, int& py) {
   const int s = (int)(gidx % P.spp);
   const int pt = (int)(gidx / P.spp);
   px = pt % P.w; py = pt / P.w;
@@ -1211,11 +1250,12 @@ __device__ __noinline__ void primaryRay(const Params<R>& P, long long gidx, Vec<
   const uint32_t pixel = (uint32_t)(y * P.xRes + x);
   const uint32_t pkey = rng_key_pixel(P.seed, pixel);
   skey = rng_key_sample(pkey, (uint32_t)s);
-  // lens sample (getDOFSamples :195-210); drawn per camera sample, see DESIGN.md
+  // lens sample (getDOFSamples :195-210): point `li` of the pixel's shuffled list
   Vec<R> eye_sample = P.eye;
-  if (P.aperture > 0) {
-    float r = (float)((double)(P.aperture / 2) * (double)rng_u01(pkey, 4u * s));
-    float theta = (float)(2 * DRT_PI * (double)rng_u01(pkey, 4u * s + 1));
+  if (lens && P.aperture > 0) {
+    const uint32_t li = (uint32_t)(perm ? (int)perm[(pt - perm_pt0) * P.antialias_samples + s] : lensIndexScan(pkey, s, P.antialias_samples));
+    float r = (float)((double)(P.aperture / 2) * (double)rng_u01(pkey, 4u * li));
+    float theta = (float)(2 * DRT_PI * (double)rng_u01(pkey, 4u * li + 1));
     eye_sample = P.eye + (R)(r * cosf(theta)) * P.X + (R)(r * sinf(theta)) * P.Y;
   }
   // jitter (:1048-1056): computed, then truncated by getPerspEyeRay(int,int) (Q1)
@@ -1308,10 +1348,12 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
         int mine = 0;
         for (int s2 = tid; s2 < n_valid; s2 += blockDim.x) mine |= ((sfl[s2] & (SS_MOTION | SF_ABORT)) == SS_MOTION);
         if (__syncthreads_or(mine)) {
+          const bool have_perm = lensPermsFill<R>(P, P.sample_base + idx0, n_valid, s_order, DRT_CTA_HITS);
+          const int perm_pt0 = (int)((P.sample_base + idx0) / P.spp);
           for (int s2 = tid; s2 < n_valid; s2 += blockDim.x) {
             if ((sfl[s2] & (SS_MOTION | SF_ABORT)) != SS_MOTION) continue;
             Task<R> T; uint32_t skey; int pi, pj, px, py;
-            primaryRay<R>(P, P.sample_base + idx0 + s2, T.org, T.dir, skey, pi, pj, px, py);
+            primaryRay<R>(P, P.sample_base + idx0 + s2, have_perm ? s_order : nullptr, perm_pt0, true, T.org, T.dir, skey, pi, pj, px, py);
             T.k = 1.0f; T.depth = (unsigned char)P.max_depth; T.bits = 0; T.slot = (unsigned short)s2;
             const int at = atomicAdd(&s_count, P.blur_samples);
             for (int m = 0; m < P.blur_samples; m++) {
@@ -1342,7 +1384,7 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
             c[0] = c[1] = c[2] = 0;                                     // default_col
             if (P.perlin_cloud) {
               Vec<R> o, d; uint32_t skey; int pi, pj, px, py;
-              primaryRay<R>(P, P.sample_base + idx0 + s2, o, d, skey, pi, pj, px, py);
+              primaryRay<R>(P, P.sample_base + idx0 + s2, nullptr, 0, false, o, d, skey, pi, pj, px, py);
               int cx = min(max(pi - P.x0, 0), P.w), cy = min(max(pj - P.y0, 0), P.h);   // corner in the tile's (w+1)x(h+1) grid
               flags |= SF_MISS | ((uint32_t)((cx - px) | ((cy - py) << 1)) << SF_CORNER_SHIFT);
               if (P.need[cy * (P.w + 1) + cx] == 0) P.need[cy * (P.w + 1) + cx] = 1;   // benign race: all writers store 1
@@ -1371,9 +1413,12 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
         const int nv = s_nvalid;
         const long long i0 = s_idx0;
         for (int s2 = tid; s2 < DRT_CTA_SLOTS; s2 += blockDim.x) { acc[s2][0] = acc[s2][1] = acc[s2][2] = 0ull; sfl[s2] = 0u; }
+        // the hit-sort scratch is idle while the pool is empty: it holds the batch's lens-sample permutations
+        const bool have_perm = lensPermsFill<R>(P, P.sample_base + i0, nv, s_order, DRT_CTA_HITS);
+        const int perm_pt0 = (int)((P.sample_base + i0) / P.spp);
         for (int s2 = tid; s2 < nv; s2 += blockDim.x) {                  // primary rays -> pool[0..nv)
           Task<R> T; uint32_t skey; int pi, pj, px, py;
-          primaryRay<R>(P, P.sample_base + i0 + s2, T.org, T.dir, skey, pi, pj, px, py);
+          primaryRay<R>(P, P.sample_base + i0 + s2, have_perm ? s_order : nullptr, perm_pt0, true, T.org, T.dir, skey, pi, pj, px, py);
           T.k = 1.0f; T.path = rng_key_child(skey, 0); T.dt = 0.f; T.depth = (unsigned char)P.max_depth;
           T.bits = TASK_CHAIN | TASK_ROOT; T.slot = (unsigned short)s2;
           poolStore(pool, (size_t)P.pool_cap, s2, T);

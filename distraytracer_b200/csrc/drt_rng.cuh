@@ -38,6 +38,24 @@ __host__ __device__ inline float rng_u01(uint32_t base, uint32_t dim) {
 //   pixel key : lens sample i -> 4i (radius), 4i+1 (angle); jitter -> 4i+2, 4i+3
 //   sample key: blur sample m -> m
 //   path key  : gloss child s, attempt a -> 64s + 2a (+1); light l, attempt a -> 4096 + 64l + 2a (+1)
+//   pixel key : step i of the lens-sample shuffle (helpers.h:270-279) -> 0x40000000 + i
+#define DRT_RNG_DIM_SHUFFLE 0x40000000u
+// j = round(u * i) of shuffle step i, u the 24-bit uniform k / 2^24: exact in integers (round half away from zero)
+__host__ __device__ inline int rng_shuffle_j(uint32_t pixel_key, int i) {
+  const uint64_t k = rng_hash(pixel_key + (DRT_RNG_DIM_SHUFFLE + (uint32_t)i) * DRT_RNG_GOLDEN) >> 8;
+  return (int)((k * (uint64_t)i + (1ull << 23)) >> 24);
+}
+// which lens point the shuffle leaves at position s of n_lens (see lensPermsFill in drt_kernels.cuh): the swaps are undone in
+// reverse order, and only steps i >= s can move the element that ends up at s
+__host__ __device__ inline int lensIndexScan(const uint32_t pkey, const int s, const int n_lens) {
+  int idx = s;
+  for (int i = s > 1 ? s : 1; i < n_lens; i++) {
+    const int j = rng_shuffle_j(pkey, i);
+    if (idx == i) idx = j;
+    else if (idx == j) idx = i;
+  }
+  return idx;
+}
 __host__ __device__ inline uint32_t rng_dim_gloss(int s, int a) { return 64u * (uint32_t)s + 2u * (uint32_t)a; }
 __host__ __device__ inline uint32_t rng_dim_light(int l, int a) { return 4096u + 64u * (uint32_t)l + 2u * (uint32_t)a; }
 

@@ -17,7 +17,7 @@ EXPORTS = [
     "drt_device_count", "drt_settings_default", "drt_prim_default", "drt_scene_create", "drt_scene_update_prims",
     "drt_scene_update_lights",
     "drt_scene_destroy", "drt_render", "drt_render_float", "drt_render_device", "drt_write_ppm", "drt_last_error",
-    "drt_abi_sizes", "drt_debug_rng", "drt_debug_candidate_order",
+    "drt_abi_sizes", "drt_debug_rng", "drt_debug_candidate_order", "drt_debug_shuffle_j", "drt_debug_lens_index",
     "drt_skeleton_create", "drt_skeleton_load", "drt_skeleton_info", "drt_skeleton_bones", "drt_scene_pose_skeleton",
     "drt_skeleton_destroy", "drt_debug_skeleton_parse",
 ]
@@ -53,6 +53,8 @@ def lib():
         L.drt_abi_sizes.argtypes = [C.POINTER(C.c_int32)]
         L.drt_debug_rng.argtypes = [C.c_uint32] * 5
         L.drt_debug_rng.restype = C.c_float
+        L.drt_debug_shuffle_j.argtypes = [C.c_uint32, C.c_uint32, C.c_int32]
+        L.drt_debug_lens_index.argtypes = [C.c_uint32, C.c_uint32, C.c_int32, C.c_int32]
         L.drt_debug_candidate_order.argtypes = [C.POINTER(abi.Prim), C.c_int32, C.POINTER(C.c_int32), C.c_int32]
         L.drt_skeleton_create.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_double, C.c_int, C.POINTER(C.c_void_p)]
         L.drt_skeleton_load.argtypes = [C.c_char_p, C.c_char_p, C.c_double, C.c_int, C.POINTER(C.c_void_p)]

@@ -359,6 +359,10 @@ void drt_abi_sizes(int32_t* out6);
  * camera sample `sample` of pixel `pixel`; evaluated on the host from the same
  * inline functions the kernels use. */
 float drt_debug_rng(uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t child, uint32_t dim);
+/* The keyed form of the reference's per-pixel lens-sample shuffle (helpers.h:270-279): swap target j of step i, and the
+ * index of the lens point the shuffle leaves at position `sample` of a pixel's n_lens points. */
+int drt_debug_shuffle_j(uint32_t seed, uint32_t pixel, int32_t i);
+int drt_debug_lens_index(uint32_t seed, uint32_t pixel, int32_t sample, int32_t n_lens);
 /* Primitive indices in the candidate order the library derives from its host-side replay of the
  * reference's generateBVH (helpers.h:381-472); ties of t between shapes resolve in this order. */
 int drt_debug_candidate_order(const drt_prim* prims, int32_t n_prims, int32_t* out, int32_t cap);

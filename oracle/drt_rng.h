@@ -47,6 +47,8 @@ static inline double drt_keyed_u01(uint32_t base, uint32_t dim) {
 // sample key:  blur sample m -> dim m (time)
 // path key:    gloss child s attempt a -> dims 64*s + 2a, +1          (a <= 11)
 //              light l attempt a       -> dims 4096 + 64*l + 2a, +1   (a <= 21)
+//              step i of the lens-sample shuffle (helpers.h:270-279) -> dim 0x40000000 + i
+#define DRT_DIM_SHUFFLE(i) (0x40000000u + (uint32_t)(i))
 #define DRT_DIM_GLOSS(s, a) (64u * (uint32_t)(s) + 2u * (uint32_t)(a))
 #define DRT_DIM_LIGHT(l, a) (4096u + 64u * (uint32_t)(l) + 2u * (uint32_t)(a))
 

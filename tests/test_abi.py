@@ -80,6 +80,37 @@ def test_rng_matches_oracle_copy(lib, oracle_lib):
             assert float(lib.drt_debug_rng(*a)) == P.probe(*a)
 
 
+def test_keyed_lens_shuffle_matches_oracle_copy_and_the_reference_algorithm(lib, oracle_lib):
+    """The reference shuffles a pixel's lens samples with `for i = n-1..1: j = round(u*i); swap(v[i], v[j])`
+    (helpers.h:270-279).  The kernels draw u keyed by (pixel, step), evaluate j in integers and ask which lens point ends up
+    at position s (lensIndexScan / lensPermsFill); the oracle performs the swaps with `round(double)` on its own copy of
+    the stream."""
+    import numpy as np
+    src = r'''
+    #include <math.h>
+    #include "drt_rng.h"
+    int probe_j(unsigned seed, unsigned pixel, int i) {
+      return (int)round(drt_keyed_u01(drt_key_pixel(seed, pixel), DRT_DIM_SHUFFLE(i)) * i); }
+    '''
+    import subprocess, tempfile
+    with tempfile.TemporaryDirectory() as td:
+        open(td + "/p.c", "w").write(src)
+        subprocess.check_call(["/usr/bin/gcc", "-O1", "-shared", "-fPIC", "-I", os.path.join(ROOT, "oracle"), td + "/p.c", "-o", td + "/p.so", "-lm"])
+        P = C.CDLL(td + "/p.so")
+        P.probe_j.argtypes = [C.c_uint, C.c_uint, C.c_int]
+        rng = np.random.default_rng(1)
+        for n_lens in (1, 2, 3, 10, 64, 100, 256):
+            seed, pixel = (int(v) for v in rng.integers(0, 2**32, size=2, dtype=np.uint64))
+            js = [0] + [P.probe_j(seed, pixel, i) for i in range(1, n_lens)]
+            assert js == [0] + [lib.drt_debug_shuffle_j(seed, pixel, i) for i in range(1, n_lens)]
+            assert all(0 <= j <= i for i, j in enumerate(js))
+            v = list(range(n_lens))
+            for i in range(n_lens - 1, 0, -1):
+                v[i], v[js[i]] = v[js[i]], v[i]
+            assert v == [lib.drt_debug_lens_index(seed, pixel, s, n_lens) for s in range(n_lens)]
+            assert sorted(v) == list(range(n_lens))
+
+
 def test_host_bvh_replay_gives_the_reference_candidate_order(lib, oracle_lib):
     """drt_bvh_order.h (product, host side) replays the reference's SAH build; its leaf visiting
     order must equal the oracle's (which is pinned bit-exactly against the compiled reference)."""

@@ -226,7 +226,7 @@ def test_production_spp_mae_against_high_spp_reference(oracle_lib):
 
 
 @pytest.mark.parametrize("variant", ["one_pixel", "edge_tile", "depth1", "noreflect", "nogloss", "no_lights", "aa2", "blur_ref_mode",
-                                     "brdf5_depth4", "depth32"])
+                                     "brdf5_depth4", "depth32", "dof_aa10", "dof_aa24", "dof_scan_fallback"])
 def test_cuda_edge_cases_match_oracle(oracle_lib, variant):
     """Edge cases of the settings surface: degenerate tiles, depth / switch extremes, spp that is not
     a square, a light-less scene, and the reference's own motion-blur mode with moving "rectangle"
@@ -252,6 +252,15 @@ def test_cuda_edge_cases_match_oracle(oracle_lib, variant):
         scene = Scene(scene.prims, [], scene.textures)
     elif variant == "aa2":
         s.antialias_samples, s.aperture = 2, 0.2   # n = int(sqrt(2)) = 1 -> 1 spp
+    elif variant == "dof_aa10":
+        # 10 lens points shuffled, 9 used (sampled_n = int(sqrt(10))^2): the shuffle decides WHICH nine (helpers.h:270-279)
+        s.antialias_samples, s.aperture = 10, 0.3
+    elif variant == "dof_aa24":
+        # 16 spp of 24 lens points: batches of 1024 samples are not pixel aligned (1024 % 16 == 0 but 24-entry permutations)
+        s.antialias_samples, s.aperture = 24, 0.3
+    elif variant == "dof_scan_fallback":
+        # 4400 lens points per pixel do not fit the shared-memory permutation table: per-sample scan (lensIndexScan)
+        s.antialias_samples, s.aperture, s.xRes, s.yRes, s.nogloss, s.max_depth = 4400, 0.3, 8, 6, 1, 2
     elif variant == "brdf5_depth4":
         s.brdf_samples, s.max_depth = 5, 4         # widest glossy fan the ray pool is sized for
     elif variant == "depth32":
