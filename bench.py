@@ -349,6 +349,13 @@ def run_tiles(n_gpus):
             spp = int(np.sqrt(st.antialias_samples)) ** 2
             samples = st.xRes * st.yRes * spp
             group = shard.FrameGroup(scene, list(range(n_gpus)))
+            try:
+                group.render(st, frame, gpus=n_gpus)
+            except runtime.DrtError as e:
+                if e.code != -2:                                        # DRT_ERR_UNSUPPORTED: no peer access on this box
+                    raise
+                group.close()
+                group = shard.FrameGroup(scene, list(range(n_gpus)), method="blocks")
             res = {"res": [st.xRes, st.yRes], "spp": spp, "method": group.method}
             ref = None
             for use in (1, n_gpus):

@@ -413,6 +413,9 @@ struct drt_scene {
   Counts* counts = nullptr;
   void* pool = nullptr; size_t pool_cap = 0;
   unsigned long long* batch_counter = nullptr; int* overflow = nullptr;
+  unsigned long long* steal_counters = nullptr;                 // drt_render_multi: one counter per row chunk, claimed by every device
+  unsigned char* owned = nullptr; size_t owned_cap = 0;         // drt_render_multi: units of the current chunk this device rendered
+  cudaEvent_t ev_sync = nullptr;                                // cross-device ordering (drt_render_multi)
   int wave_blocks_f64 = 0, wave_blocks_f32 = 0;
   MeshBuffers mesh; bool has_mesh = false; drt_prim mesh_material;
   PinnedStage stage;
@@ -561,9 +564,16 @@ long long maxChunkSamples() {
   return 1ll << b;
 }
 
+// One frame on several devices (drt_render_multi): where the shared claim counters and the gathered frame live.
+#define DRT_MULTI_MAX_CHUNKS 1024
+struct MultiCtx {
+  unsigned long long* counters;   // DRT_MULTI_MAX_CHUNKS counters in the gathering device's memory, zeroed
+  unsigned char* gather_u8;       // the gathering device's frame buffer: every device's resolve writes its own pixels there
+};
+
 template <typename R>
 int launchAll(drt_scene* s, const DevScene<R>& ds, const drt_settings& st, const CameraD& cam, const drt_tile& tile, int pool_cap,
-              bool want_f32, drt_counters* counters) {
+              bool want_f32, drt_counters* counters, const MultiCtx* mc = nullptr) {
   Params<R> P;
   fillParams<R>(P, s, ds, st, cam, tile);
   const bool collect = counters && counters->collect;
@@ -573,6 +583,21 @@ int launchAll(drt_scene* s, const DevScene<R>& ds, const drt_settings& st, const
   int rc = ensureScratch(s, st.cloud_only ? 1 : (size_t)rows_per_chunk * per_row, n_corners, (size_t)tile.width * tile.height * 3);
   if (rc) return rc;
   P.samples = s->samples; P.need = s->need; P.bg = s->bg; P.out_u8 = s->out_u8; P.out_f32 = want_f32 ? s->out_f32 : nullptr;
+  // claim units: one batch on a single device; whole pixels (at least one batch's worth) when devices share the frame
+  P.unit_samples = DRT_CTA_SLOTS;
+  if (mc) {
+    const int unit_pixels = std::max(1, (DRT_CTA_SLOTS + P.spp - 1) / P.spp);
+    P.unit_samples = unit_pixels * P.spp;
+    const size_t n_units = ((size_t)rows_per_chunk * per_row + P.unit_samples - 1) / P.unit_samples;
+    if ((tile.height + rows_per_chunk - 1) / rows_per_chunk > DRT_MULTI_MAX_CHUNKS) return fail(DRT_ERR_UNSUPPORTED, "frame cut into too many row chunks");
+    if (n_units > s->owned_cap) {
+      if (s->owned) cudaFree(s->owned);
+      s->owned = nullptr; s->owned_cap = 0;
+      CK(cudaMalloc(&s->owned, n_units));
+      s->owned_cap = n_units;
+    }
+    P.steal = 1; P.owned = s->owned; P.out_u8 = mc->gather_u8; P.out_f32 = nullptr;
+  }
   P.counts = collect ? s->counts : nullptr;
   int& wave_blocks = sizeof(R) == 8 ? s->wave_blocks_f64 : s->wave_blocks_f32;
   if (!wave_blocks) wave_blocks = waveGridBlocks<R>();
@@ -610,7 +635,10 @@ int launchAll(drt_scene* s, const DevScene<R>& ds, const drt_settings& st, const
       const int rows = std::min(rows_per_chunk, tile.height - row0);
       P.sample_base = (long long)row0 * per_row;
       P.sample_count = (long long)rows * per_row;
-      CK(cudaMemsetAsync(s->batch_counter, 0, sizeof(unsigned long long), q));
+      if (mc) {
+        P.batch_counter = mc->counters + row0 / rows_per_chunk;
+        CK(cudaMemsetAsync(s->owned, 0, ((size_t)P.sample_count + P.unit_samples - 1) / P.unit_samples, q));
+      } else CK(cudaMemsetAsync(s->batch_counter, 0, sizeof(unsigned long long), q));
       variant = launchRenderSamples<R>(P, collect, feat, wave_blocks, q); launches++;
       if (st.perlin_cloud) { launchCloudCorners<R>(P, q); launches++; }
       launchResolve<R>(P, row0, rows, q); launches++;
@@ -622,11 +650,9 @@ int launchAll(drt_scene* s, const DevScene<R>& ds, const drt_settings& st, const
   return DRT_OK;
 }
 
-int renderCommon(const drt_scene* cs, const drt_settings* st, const drt_tile* tile, float* out_f32, uint8_t* out_u8,
-                 drt_counters* counters, bool copy_back) {
-  drt_scene* s = const_cast<drt_scene*>(cs);
+// Validation shared by every render entry point; sizes the CTA ray pools and builds the camera.
+int planRender(drt_scene* s, const drt_settings* st, const drt_tile* tile, int& pool_cap, CameraD& cam) {
   if (!s || !st || !tile) return fail(DRT_ERR_INVALID, "null argument");
-  if (tile->device != s->device) return fail(DRT_ERR_INVALID, "tile.device differs from the scene's device");
   if (st->xRes < 1 || st->yRes < 1 || tile->width < 1 || tile->height < 1 || tile->x0 < 0 || tile->y0 < 0 ||
       tile->x0 + tile->width > st->xRes || tile->y0 + tile->height > st->yRes)
     return fail(DRT_ERR_INVALID, "tile outside the frame");
@@ -638,7 +664,6 @@ int renderCommon(const drt_scene* cs, const drt_settings* st, const drt_tile* ti
   // per-sample record encodes that corner as an offset of 0 or 1, which holds while sqrt(antialias_samples) <= 18
   if (st->perlin_cloud && !st->cloud_only && (int)sqrt((double)st->antialias_samples) > 18)
     return fail(DRT_ERR_UNSUPPORTED, "perlin_cloud with more than 18 x 18 samples per pixel");
-  int pool_cap = 0;
   {  // CTA ray-pool bound (render_wave): the pool is a LIFO over the trees of one batch of DRT_CTA_SLOTS samples.  A
      // TRACE pass turns at most DRT_HITS_PER_PASS rays into hits, a hit spawns at most `fan` children (lobes [+1 for
      // glass]), and only the rays on top are traced next, so at most per_pass x (fan - 1) rays are left behind per level.
@@ -651,13 +676,50 @@ int renderCommon(const drt_scene* cs, const drt_settings* st, const drt_tile* ti
     if (need > (1ll << 22)) return fail(DRT_ERR_UNSUPPORTED, "brdf_samples * max_depth needs more than 4 M rays per CTA pool");
     pool_cap = (int)((need + 1023) / 1024 * 1024);
   }
+  return makeCamera(*st, cam);
+}
+
+int launchFor(drt_scene* s, const drt_settings* st, const CameraD& cam, const drt_tile* tile, int pool_cap, bool want_f32,
+              drt_counters* counters, const MultiCtx* mc) {
+  if (st->precision == DRT_PRECISION_FP32) return launchAll<float>(s, s->df, *st, cam, *tile, pool_cap, want_f32, counters, mc);
+  return launchAll<double>(s, s->dd, *st, cam, *tile, pool_cap, want_f32, counters, mc);
+}
+
+// After the scene's stream has been synchronised: overflow flag, timing, event counters (`hc` already copied back).
+int finishRender(drt_scene* s, const drt_settings* st, drt_counters* counters, const Counts& hc, int overflowed) {
+  if (overflowed) {   // the kernel dropped rays instead of writing past its pool: the frame is not valid
+    CK(cudaMemsetAsync(s->overflow, 0, sizeof(int), s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return fail(DRT_ERR_UNSUPPORTED, "a CTA ray pool overflowed (brdf_samples * max_depth beyond the sized bound)");
+  }
+  (void)st;
+  if (counters) {
+    float ms = 0; CK(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    counters->kernel_ms = ms;
+    if (counters->collect) {
+      counters->samples = hc.samples; counters->rays = hc.rays; counters->shadow_rays = hc.shadow_rays;
+      counters->shade_evals = hc.shade_evals; counters->noise_evals = hc.noise_evals; counters->node_tests = hc.node_tests;
+      for (int i = 0; i < DRT_PRIM_TYPE_COUNT; i++) counters->prim_tests[i] = 0;
+      counters->prim_tests[DRT_PRIM_SPHERE] = hc.geom_tests[G_SPHERE];
+      counters->prim_tests[DRT_PRIM_CYLINDER] = hc.geom_tests[G_CYL];
+      counters->prim_tests[DRT_PRIM_TRIANGLE] = hc.geom_tests[G_TRI];
+      counters->prim_tests[DRT_PRIM_RECTANGLE] = hc.geom_tests[G_RECT] + hc.geom_tests[G_CHECKER];   // rectangle tests incl. prism faces
+    }
+  }
+  return DRT_OK;
+}
+
+int renderCommon(const drt_scene* cs, const drt_settings* st, const drt_tile* tile, float* out_f32, uint8_t* out_u8,
+                 drt_counters* counters, bool copy_back) {
+  drt_scene* s = const_cast<drt_scene*>(cs);
+  int pool_cap = 0;
   CameraD cam;
-  int rc = makeCamera(*st, cam);
+  int rc = planRender(s, st, tile, pool_cap, cam);
   if (rc) return rc;
+  if (tile->device != s->device) return fail(DRT_ERR_INVALID, "tile.device differs from the scene's device");
   CK(cudaSetDevice(s->device));
   const bool want_f32 = out_f32 != nullptr;
-  if (st->precision == DRT_PRECISION_FP32) rc = launchAll<float>(s, s->df, *st, cam, *tile, pool_cap, want_f32, counters);
-  else rc = launchAll<double>(s, s->dd, *st, cam, *tile, pool_cap, want_f32, counters);
+  rc = launchFor(s, st, cam, tile, pool_cap, want_f32, counters, nullptr);
   if (rc) return rc;
   const size_t n_out = (size_t)tile->width * tile->height * 3;
   if (copy_back) {
@@ -670,25 +732,80 @@ int renderCommon(const drt_scene* cs, const drt_settings* st, const drt_tile* ti
   int overflowed = 0;
   if (!st->cloud_only) CK(cudaMemcpyAsync(&overflowed, s->overflow, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
   CK(cudaStreamSynchronize(s->stream));
-  if (overflowed) {   // the kernel dropped rays instead of writing past its pool: the frame is not valid
-    CK(cudaMemsetAsync(s->overflow, 0, sizeof(int), s->stream));
+  return finishRender(s, st, counters, hc, overflowed);
+}
+
+// One frame on several devices at once (include/drt.h drt_render_multi).
+int renderMulti(drt_scene* const* scenes, int n, const drt_settings* st, const drt_tile* tile, uint8_t* out_u8, drt_counters* counters) {
+  if (!scenes || n < 1 || !out_u8) return fail(DRT_ERR_INVALID, "null argument");
+  if (n > 64) return fail(DRT_ERR_INVALID, "more than 64 scene handles");
+  for (int i = 0; i < n; i++) {
+    if (!scenes[i]) return fail(DRT_ERR_INVALID, "null scene handle");
+    for (int k = 0; k < i; k++) if (scenes[k] == scenes[i]) return fail(DRT_ERR_INVALID, "the same scene handle twice");
+  }
+  if (st && st->cloud_only) return fail(DRT_ERR_UNSUPPORTED, "cloud_only frames are rendered on one device (drt_render)");
+  int pool_cap[64]; CameraD cam;
+  for (int i = 0; i < n; i++) { int rc = planRender(scenes[i], st, tile, pool_cap[i], cam); if (rc) return rc; }
+  drt_scene* g = scenes[0];                                     // the gathering device
+  // every other device claims from, and resolves into, the gathering device's memory
+  for (int i = 1; i < n; i++) {
+    if (scenes[i]->device == g->device) continue;
+    int can = 0;
+    CK(cudaDeviceCanAccessPeer(&can, scenes[i]->device, g->device));
+    if (!can) return fail(DRT_ERR_UNSUPPORTED, "no peer access between the devices (cut the frame into tiles and use drt_render)");
+    CK(cudaSetDevice(scenes[i]->device));
+    const cudaError_t e = cudaDeviceEnablePeerAccess(g->device, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(DRT_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+    cudaGetLastError();
+  }
+  CK(cudaSetDevice(g->device));
+  const size_t n_out = (size_t)tile->width * tile->height * 3;
+  {
+    const int spp = (int)sqrt((double)st->antialias_samples) * (int)sqrt((double)st->antialias_samples);
+    const long long per_row = (long long)tile->width * spp;
+    const int rows_per_chunk = (int)std::max<long long>(1, std::min<long long>(tile->height, maxChunkSamples() / std::max<long long>(1, per_row)));
+    int rc = ensureScratch(g, (size_t)rows_per_chunk * per_row, (size_t)(tile->width + 1) * (tile->height + 1), n_out);
+    if (rc) return rc;
+  }
+  if (!g->steal_counters) CK(cudaMalloc(&g->steal_counters, sizeof(unsigned long long) * DRT_MULTI_MAX_CHUNKS));
+  CK(cudaMemsetAsync(g->steal_counters, 0, sizeof(unsigned long long) * DRT_MULTI_MAX_CHUNKS, g->stream));
+  for (int i = 0; i < n; i++) if (!scenes[i]->ev_sync) { CK(cudaSetDevice(scenes[i]->device)); CK(cudaEventCreateWithFlags(&scenes[i]->ev_sync, cudaEventDisableTiming)); }
+  CK(cudaSetDevice(g->device));
+  CK(cudaEventRecord(g->ev_sync, g->stream));                  // counters zeroed, frame buffer allocated
+  MultiCtx mc; mc.counters = g->steal_counters; mc.gather_u8 = g->out_u8;
+  for (int i = 0; i < n; i++) {
+    drt_scene* s = scenes[i];
+    CK(cudaSetDevice(s->device));
+    if (i) CK(cudaStreamWaitEvent(s->stream, g->ev_sync, 0));
+    drt_tile t = *tile; t.device = s->device;
+    int rc = launchFor(s, st, cam, &t, pool_cap[i], false, counters ? &counters[i] : nullptr, &mc);
+    if (rc) return rc;
+  }
+  // the gathering stream waits for everyone's pixels, then one copy to the host
+  Counts hc[64]; int overflowed[64];
+  for (int i = 1; i < n; i++) {
+    CK(cudaSetDevice(scenes[i]->device));
+    CK(cudaEventRecord(scenes[i]->ev_sync, scenes[i]->stream));
+  }
+  CK(cudaSetDevice(g->device));
+  for (int i = 1; i < n; i++) CK(cudaStreamWaitEvent(g->stream, scenes[i]->ev_sync, 0));
+  CK(cudaMemcpyAsync(out_u8, g->out_u8, n_out, cudaMemcpyDeviceToHost, g->stream));
+  for (int i = 0; i < n; i++) {
+    drt_scene* s = scenes[i];
+    CK(cudaSetDevice(s->device));
+    memset(&hc[i], 0, sizeof(Counts)); overflowed[i] = 0;
+    if (counters && counters[i].collect) CK(cudaMemcpyAsync(&hc[i], s->counts, sizeof(Counts), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaMemcpyAsync(&overflowed[i], s->overflow, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+  }
+  int rc_all = DRT_OK;
+  for (int i = n - 1; i >= 0; i--) {                            // the gathering stream (0) last: it waits for the others
+    drt_scene* s = scenes[i];
+    CK(cudaSetDevice(s->device));
     CK(cudaStreamSynchronize(s->stream));
-    return fail(DRT_ERR_UNSUPPORTED, "a CTA ray pool overflowed (brdf_samples * max_depth beyond the sized bound)");
+    const int rc = finishRender(s, st, counters ? &counters[i] : nullptr, hc[i], overflowed[i]);
+    if (rc) rc_all = rc;
   }
-  if (counters) {
-    float ms = 0; CK(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
-    counters->kernel_ms = ms;
-    if (collect) {
-      counters->samples = hc.samples; counters->rays = hc.rays; counters->shadow_rays = hc.shadow_rays;
-      counters->shade_evals = hc.shade_evals; counters->noise_evals = hc.noise_evals; counters->node_tests = hc.node_tests;
-      for (int i = 0; i < DRT_PRIM_TYPE_COUNT; i++) counters->prim_tests[i] = 0;
-      counters->prim_tests[DRT_PRIM_SPHERE] = hc.geom_tests[G_SPHERE];
-      counters->prim_tests[DRT_PRIM_CYLINDER] = hc.geom_tests[G_CYL];
-      counters->prim_tests[DRT_PRIM_TRIANGLE] = hc.geom_tests[G_TRI];
-      counters->prim_tests[DRT_PRIM_RECTANGLE] = hc.geom_tests[G_RECT] + hc.geom_tests[G_CHECKER];   // rectangle tests incl. prism faces
-    }
-  }
-  return DRT_OK;
+  return rc_all;
 }
 
 }  // namespace
@@ -819,12 +936,14 @@ void drt_scene_destroy(drt_scene* s) {
   for (auto t : s->tex_objs) cudaDestroyTextureObject(t);
   for (auto a : s->tex_arrays) cudaFreeArray(a);
   void* ptrs[] = {s->dd.gbounds, s->df.gbounds, s->dd.geoms, s->dd.prims, s->dd.lights, s->dd.nodes, s->df.geoms, s->df.prims, s->df.lights, s->df.nodes, s->d_tex, s->d_texdims,
-                  s->samples, s->need, s->bg, s->out_u8, s->out_f32, s->counts, s->pool, s->batch_counter, s->overflow};
+                  s->samples, s->need, s->bg, s->out_u8, s->out_f32, s->counts, s->pool, s->batch_counter, s->overflow,
+                  s->steal_counters, s->owned};
   for (void* p : ptrs) if (p) cudaFree(p);
   freeMesh(&s->mesh);
   if (s->stage.base) cudaFreeHost(s->stage.base);
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
+  if (s->ev_sync) cudaEventDestroy(s->ev_sync);
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
 }
@@ -928,6 +1047,11 @@ int drt_render_float(const drt_scene* scene, const drt_settings* settings, const
 
 int drt_render_device(const drt_scene* scene, const drt_settings* settings, const drt_tile* tile, drt_counters* counters) {
   return renderCommon(scene, settings, tile, nullptr, nullptr, counters, false);
+}
+
+int drt_render_multi(drt_scene* const* scenes, int32_t n_scenes, const drt_settings* settings, const drt_tile* tile, uint8_t* out_rgb,
+                     drt_counters* counters) {
+  return renderMulti(scenes, n_scenes, settings, tile, out_rgb, counters);
 }
 
 int drt_write_ppm(const char* filename, int32_t width, int32_t height, const uint8_t* rgb) {   // helpers.h:174-195

@@ -196,7 +196,15 @@ struct Params {
   long long sample_count;
   void* pool_raw;           // per-CTA scratch: ray pool, hit buffer, shadow-pair buffers (waveScratchBytes)
   int pool_cap;             // ray tasks per CTA pool
+  // work distribution: persistent CTAs claim UNITS of `unit_samples` consecutive camera samples of the launch from
+  // `batch_counter` and work through a unit in batches of DRT_CTA_SLOTS.  One GPU: unit = one batch, the counter is local.
+  // One frame on several GPUs (drt_render_multi): every GPU's kernel claims from the SAME counter in the gathering GPU's
+  // memory (system-scope atomics over NVLink), units cover whole pixels, and `owned` (local, one byte per unit) records
+  // which units this GPU rendered so that its resolve pass writes exactly those pixels.
   unsigned long long* batch_counter;
+  int unit_samples;
+  int steal;                // 1: batch_counter is shared between devices
+  unsigned char* owned;     // nullptr unless stealing
   int* overflow;
 };
 

@@ -1204,41 +1204,40 @@ __device__ void shadeB(const Params<R>& P, ShadeState<R>& S, const PairOut<R>& r
 // ---- the per-pixel shuffle of the lens samples (helpers.h:270-279, render_final_project.cpp:1059) -------------------
 // The reference draws antialias_samples lens points per pixel (getDOFSamples), shuffles them with
 // `for i = size-1 .. 1: j = round(u * i); swap(v[i], v[j])` and hands point i of the shuffled list to camera sample i.
-// Here every draw is keyed, so camera sample s only needs to know WHICH lens point ended up at position s.
-//
-// lensIndexScan: that index for one sample, by undoing the swaps in reverse order (only steps i >= s can move it).
+// Here every draw is keyed, so camera sample s only needs to know WHICH lens point ended up at position s: it undoes the
+// swaps in reverse order (lensIndexScan in drt_rng.cuh; only steps i >= s can move the element that ends up at s).
 template <typename R>
 __device__ __forceinline__ uint32_t pixelKeyOf(const Params<R>& P, const int pt) {
   const int x = P.x0 + pt % P.w, y = P.y0 + pt / P.w;
   return rng_key_pixel(P.seed, (uint32_t)(y * P.xRes + x));
 }
-// lensPermsFill: the whole permutation of every pixel the CTA's batch [g0, g0 + nv) touches, into `perm` (shared memory,
-// `cap` 16-bit entries: permutations in the lower half, the swap targets j_i in the upper half).  All threads hash the
-// j_i in parallel, then one thread per pixel applies its swaps in order.  Returns false (CTA-uniform) when the batch's
-// permutations do not fit; primaryRay then falls back to lensIndexScan.  Ends with a barrier.
+// lensSwapTargetsFill: the swap targets j_i of every pixel the CTA's batch [g0, g0 + nv) touches, hashed once by all threads
+// into `jt` (shared memory, `cap` 16-bit entries, A per pixel); the samples of a pixel then share them.  Returns false
+// (CTA-uniform) when they do not fit; primaryRay then hashes per sample (lensIndexScan).  Ends with a barrier.
 template <typename R>
-__device__ inline bool lensPermsFill(const Params<R>& P, const long long g0, const int nv, unsigned short* perm, const int cap) {
+__device__ inline bool lensSwapTargetsFill(const Params<R>& P, const long long g0, const int nv, unsigned short* jt, const int cap) {
   if (!(P.aperture > 0) || nv <= 0) return false;
   const int A = P.antialias_samples;
   const int pt0 = (int)(g0 / P.spp), npx = (int)((g0 + nv - 1) / P.spp) - pt0 + 1;
-  if ((long long)npx * A > cap / 2 || A > 65535) return false;
-  unsigned short* jt = perm + cap / 2;
+  if ((long long)npx * A > cap || A > 65535) return false;
   for (int e = threadIdx.x; e < npx * A; e += blockDim.x) {
     const int q = e / A, i = e - q * A;
     jt[e] = (unsigned short)(i ? rng_shuffle_j(pixelKeyOf(P, pt0 + q), i) : 0);
-    perm[e] = (unsigned short)i;
-  }
-  __syncthreads();
-  for (int q = threadIdx.x; q < npx; q += blockDim.x) {
-    unsigned short* v = perm + q * A;
-    const unsigned short* j = jt + q * A;
-    for (int i = A - 1; i > 0; i--) { const unsigned short a = v[i], b = v[j[i]]; v[i] = b; v[j[i]] = a; }
   }
   __syncthreads();
   return true;
 }
+// lensIndexScan (drt_rng.cuh) over a pixel's table of swap targets
+__device__ __forceinline__ int lensIndexFromTable(const unsigned short* j, const int s, const int n_lens) {
+  int idx = s;
+  for (int i = s > 1 ? s : 1; i < n_lens; i++) {
+    const int ji = j[i];
+    idx = (idx == i) ? ji : ((idx == ji) ? i : idx);
+  }
+  return idx;
+}
 
-// `perm`: lensPermsFill's table for the batch starting at pixel `perm_pt0`, or nullptr (scan per sample).
+// `perm`: lensSwapTargetsFill's table for the batch starting at pixel `perm_pt0`, or nullptr (hash per sample).
 // `lens` false: only the pixel / corner outputs are wanted.
 template <typename R>
 __device__ __noinline__ void primaryRay(const Params<R>& P, long long gidx, const unsigned short* perm, const int perm_pt0, const bool lens,
@@ -1253,7 +1252,8 @@ __device__ __noinline__ void primaryRay(const Params<R>& P, long long gidx, cons
   // lens sample (getDOFSamples :195-210): point `li` of the pixel's shuffled list
   Vec<R> eye_sample = P.eye;
   if (lens && P.aperture > 0) {
-    const uint32_t li = (uint32_t)(perm ? (int)perm[(pt - perm_pt0) * P.antialias_samples + s] : lensIndexScan(pkey, s, P.antialias_samples));
+    const uint32_t li = (uint32_t)(perm ? lensIndexFromTable(perm + (pt - perm_pt0) * P.antialias_samples, s, P.antialias_samples)
+                                        : lensIndexScan(pkey, s, P.antialias_samples));
     float r = (float)((double)(P.aperture / 2) * (double)rng_u01(pkey, 4u * li));
     float theta = (float)(2 * DRT_PI * (double)rng_u01(pkey, 4u * li + 1));
     eye_sample = P.eye + (R)(r * cosf(theta)) * P.X + (R)(r * sinf(theta)) * P.Y;
@@ -1305,7 +1305,7 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
   unsigned char* s_hkey = s_dyn + (size_t)DRT_CTA_SLOTS * 28 + (size_t)DRT_CTA_HITS * 2;
   __shared__ int s_count, s_nhits, s_grab, s_state, s_nvalid;
   __shared__ int s_hist[DRT_HIT_BUCKETS];                 // SHADE order: counting sort of the hit buffer by geom
-  __shared__ long long s_idx0;
+  __shared__ long long s_idx0, s_unit_next, s_unit_end;
   // slab-filter table of the whole scene, staged once per persistent CTA (48 B per pair of geoms)
   __shared__ float4 s_gb[3 * DRT_SMEM_GEOMS / 2 + 2 * DRT_SMEM_GEOMS / 8];
   const float4* gb = P.gbounds;
@@ -1324,14 +1324,14 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
   pairout.state = (int*)(pairout.z + 32 * DRT_PAIR_LIGHTS);
   unsigned long long(*acc)[3] = s_acc;
   unsigned int* sfl = s_flags;
-  const long long n_batches = (P.sample_count + DRT_CTA_SLOTS - 1) / DRT_CTA_SLOTS;
+  const long long n_units = (P.sample_count + P.unit_samples - 1) / P.unit_samples;
 
   Counts cnt;
   if (COUNT) { cnt.samples = 0; cnt.rays = 0; cnt.shadow_rays = 0; cnt.shade_evals = 0; cnt.noise_evals = 0; cnt.node_tests = 0;
                for (int i = 0; i < 6; i++) cnt.geom_tests[i] = 0; }
 
   // s_state: 0 = no batch, 1 = primary trees in flight, 2 = blur re-traces in flight, 3 = all batches done
-  if (tid == 0) { s_count = 0; s_nhits = 0; s_state = 0; s_nvalid = 0; s_idx0 = 0; }
+  if (tid == 0) { s_count = 0; s_nhits = 0; s_state = 0; s_nvalid = 0; s_idx0 = 0; s_unit_next = 0; s_unit_end = 0; }
   __syncthreads();
 
   for (;;) {
@@ -1348,7 +1348,7 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
         int mine = 0;
         for (int s2 = tid; s2 < n_valid; s2 += blockDim.x) mine |= ((sfl[s2] & (SS_MOTION | SF_ABORT)) == SS_MOTION);
         if (__syncthreads_or(mine)) {
-          const bool have_perm = lensPermsFill<R>(P, P.sample_base + idx0, n_valid, s_order, DRT_CTA_HITS);
+          const bool have_perm = lensSwapTargetsFill<R>(P, P.sample_base + idx0, n_valid, s_order, DRT_CTA_HITS);
           const int perm_pt0 = (int)((P.sample_base + idx0) / P.spp);
           for (int s2 = tid; s2 < n_valid; s2 += blockDim.x) {
             if ((sfl[s2] & (SS_MOTION | SF_ABORT)) != SS_MOTION) continue;
@@ -1400,11 +1400,21 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
       __syncthreads();
       if (s_state == 0) {                                                // claim the next batch of camera samples
         if (tid == 0) {
-          const long long b = (long long)atomicAdd(P.batch_counter, 1ull);
-          if (b >= n_batches) s_state = 3;
-          else {
-            s_idx0 = b * DRT_CTA_SLOTS;                                  // chunk-local sample index of slot 0
-            s_nvalid = (int)min((long long)DRT_CTA_SLOTS, P.sample_count - s_idx0);
+          long long next = s_unit_next, end = s_unit_end;
+          if (next >= end) {                                             // the CTA's unit is used up: claim another one
+            const long long u = (long long)(P.steal ? atomicAdd_system(P.batch_counter, 1ull) : atomicAdd(P.batch_counter, 1ull));
+            if (u >= n_units) s_state = 3;
+            else {
+              next = u * P.unit_samples;
+              end = min(next + P.unit_samples, P.sample_count);
+              s_unit_end = end;
+              if (P.owned) P.owned[u] = 1;
+            }
+          }
+          if (next < end) {
+            s_idx0 = next;                                               // chunk-local sample index of slot 0
+            s_nvalid = (int)min((long long)DRT_CTA_SLOTS, end - next);
+            s_unit_next = next + s_nvalid;
             s_state = 1;
           }
         }
@@ -1413,8 +1423,8 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
         const int nv = s_nvalid;
         const long long i0 = s_idx0;
         for (int s2 = tid; s2 < DRT_CTA_SLOTS; s2 += blockDim.x) { acc[s2][0] = acc[s2][1] = acc[s2][2] = 0ull; sfl[s2] = 0u; }
-        // the hit-sort scratch is idle while the pool is empty: it holds the batch's lens-sample permutations
-        const bool have_perm = lensPermsFill<R>(P, P.sample_base + i0, nv, s_order, DRT_CTA_HITS);
+        // the hit-sort scratch is idle while the pool is empty: it holds the swap targets of the batch's lens-sample shuffles
+        const bool have_perm = lensSwapTargetsFill<R>(P, P.sample_base + i0, nv, s_order, DRT_CTA_HITS);
         const int perm_pt0 = (int)((P.sample_base + i0) / P.spp);
         for (int s2 = tid; s2 < nv; s2 += blockDim.x) {                  // primary rays -> pool[0..nv)
           Task<R> T; uint32_t skey; int pi, pj, px, py;
@@ -1744,6 +1754,8 @@ __global__ void __launch_bounds__(256) resolve(const __grid_constant__ Params<R>
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= P.w * rows) return;
   const int px = idx % P.w, py = row0 + idx / P.w;
+  // one frame on several GPUs: this GPU writes the pixels of the units it claimed (units cover whole pixels)
+  if (P.owned && !P.owned[((long long)idx * P.spp) / P.unit_samples]) return;
   double c[3] = {0, 0, 0};
   bool aborted = false;
   if (P.cloud_only) {

@@ -16,7 +16,7 @@ _lib = None
 EXPORTS = [
     "drt_device_count", "drt_settings_default", "drt_prim_default", "drt_scene_create", "drt_scene_update_prims",
     "drt_scene_update_lights",
-    "drt_scene_destroy", "drt_render", "drt_render_float", "drt_render_device", "drt_write_ppm", "drt_last_error",
+    "drt_scene_destroy", "drt_render", "drt_render_float", "drt_render_device", "drt_render_multi", "drt_write_ppm", "drt_last_error",
     "drt_abi_sizes", "drt_debug_rng", "drt_debug_candidate_order", "drt_debug_shuffle_j", "drt_debug_lens_index",
     "drt_skeleton_create", "drt_skeleton_load", "drt_skeleton_info", "drt_skeleton_bones", "drt_scene_pose_skeleton",
     "drt_skeleton_destroy", "drt_debug_skeleton_parse",
@@ -49,6 +49,8 @@ def lib():
         L.drt_render_float.argtypes = [C.c_void_p, C.POINTER(abi.Settings), C.POINTER(abi.Tile), C.c_void_p, C.c_void_p,
                                        C.POINTER(abi.Counters)]
         L.drt_render_device.argtypes = [C.c_void_p, C.POINTER(abi.Settings), C.POINTER(abi.Tile), C.POINTER(abi.Counters)]
+        L.drt_render_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.POINTER(abi.Settings), C.POINTER(abi.Tile), C.c_void_p,
+                                       C.POINTER(abi.Counters)]
         L.drt_write_ppm.argtypes = [C.c_char_p, C.c_int32, C.c_int32, C.c_void_p]
         L.drt_abi_sizes.argtypes = [C.POINTER(C.c_int32)]
         L.drt_debug_rng.argtypes = [C.c_uint32] * 5
@@ -156,6 +158,20 @@ class DeviceScene:
         tile = self._tile(settings, tile)
         _check(lib().drt_render_device(self.handle, C.byref(settings), C.byref(tile),
                                        C.byref(counters) if counters is not None else None))
+
+
+def render_multi(handles, settings, out=None, tile=None, counters=False):
+    """drt_render_multi: ONE frame on all of `handles` (DeviceScene objects of the same scene, normally one per GPU;
+    handles[0]'s GPU gathers).  Returns the uint8 (h, w, 3) frame, or (frame, [abi.Counters per handle]) with counters=True."""
+    if tile is None:
+        tile = abi.Tile(0, 0, settings.xRes, settings.yRes, handles[0].device)
+    if out is None:
+        out = np.empty((tile.height, tile.width, 3), dtype=np.uint8)
+    check_frame_buffer(out, tile.height, tile.width)
+    arr = (C.c_void_p * len(handles))(*[h.handle for h in handles])
+    cnt = (abi.Counters * len(handles))() if counters else None
+    _check(lib().drt_render_multi(arr, len(handles), C.byref(settings), C.byref(tile), out.ctypes.data, cnt))
+    return (out, list(cnt)) if counters else out
 
 
 MOCAP_SCALE = 0.06   # types.h:6

@@ -82,19 +82,34 @@ def render_frame_blocks(handles, settings, frame_rgb, rows=15):
 class FrameGroup:
     """One scene replicated on several GPUs of a box, for rendering single frames on all of them (BASELINE configs 3 and 5;
     SURVEY.md 8e).  `render` returns the wall-clock seconds of one frame, written into `frame_rgb` ((yRes, xRes, 3) uint8,
-    PPM row order; pinned memory keeps the device-to-host copies asynchronous)."""
+    PPM row order; pinned memory keeps the device-to-host copy asynchronous).
 
-    def __init__(self, scene, devices, streams_per_gpu=2, rows=15):
+    method "steal": drt_render_multi -- one persistent kernel per GPU, all claiming ~1024-sample units from one counter
+    in GPU 0's memory, pixels resolved into GPU 0's frame over NVLink, one copy to the host.
+    method "blocks": the fallback without peer access -- row blocks claimed by host threads (render_frame_blocks)."""
+
+    def __init__(self, scene, devices, method="steal", streams_per_gpu=2, rows=15):
         from .runtime import DeviceScene
         self.devices = list(devices)
         self.rows = rows
-        self.handles = [[DeviceScene(scene, d) for _ in range(streams_per_gpu)] for d in self.devices]
-        self.method = (f"row blocks of {rows} rows claimed dynamically by one host thread per scene handle, "
+        self.kind = method
+        per = 1 if method == "steal" else streams_per_gpu
+        self.handles = [[DeviceScene(scene, d) for _ in range(per)] for d in self.devices]
+        self.method = ("drt_render_multi: one launch per GPU, pixel-aligned ~1024-sample units stolen from one counter in GPU 0's "
+                       "memory, resolved into GPU 0's frame over NVLink" if method == "steal" else
+                       f"row blocks of {rows} rows claimed dynamically by one host thread per scene handle, "
                        f"{streams_per_gpu} handles (streams) per GPU")
 
     def render(self, settings, frame_rgb, gpus=None):
+        import time
         use = self.handles[:gpus] if gpus else self.handles
-        return render_frame_blocks([h for g in use for h in g], settings, frame_rgb, self.rows)
+        flat = [h for g in use for h in g]
+        if self.kind == "steal":
+            from .runtime import render_multi
+            t0 = time.perf_counter()
+            render_multi(flat, settings, out=frame_rgb)
+            return time.perf_counter() - t0
+        return render_frame_blocks(flat, settings, frame_rgb, self.rows)
 
     def close(self):
         for g in self.handles:

@@ -345,6 +345,18 @@ int drt_render_float(const drt_scene* scene, const drt_settings* settings, const
 int drt_render_device(const drt_scene* scene, const drt_settings* settings, const drt_tile* tile,
                       drt_counters* counters);
 
+/* Render ONE frame (or tile) on several devices at once: the single-frame partition of BASELINE configs 3 and 5
+ * (SURVEY.md 8e).  `scenes` are n_scenes handles holding the SAME scene, normally one per device; scenes[0]'s device
+ * gathers.  One persistent kernel per device claims pixel-aligned units of ~1024 camera samples from ONE counter in the
+ * gathering device's memory (system-scope atomics over NVLink / NVSwitch peer access), so the devices balance at unit
+ * granularity whatever the cost profile of the frame; every device resolves the pixels it rendered straight into the
+ * gathering device's frame (peer stores), and one device-to-host copy delivers `out_rgb` (layout as drt_render).  No
+ * collective.  The image is byte-identical to drt_render's on one device.  `tile->device` is ignored; `counters` is NULL
+ * or an array of n_scenes entries (kernel_ms = each device's own kernel time).  Needs peer access from every device to
+ * scenes[0]'s (DRT_ERR_UNSUPPORTED otherwise: cut the frame into tiles and call drt_render per device instead). */
+int drt_render_multi(drt_scene* const* scenes, int32_t n_scenes, const drt_settings* settings, const drt_tile* tile,
+                     uint8_t* out_rgb, drt_counters* counters);
+
 /* Writes a binary P6 PPM exactly as helpers.h:174-195 does. */
 int drt_write_ppm(const char* filename, int32_t width, int32_t height, const uint8_t* rgb);
 
