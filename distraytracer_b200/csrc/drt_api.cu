@@ -571,16 +571,34 @@ struct MultiCtx {
   unsigned char* gather_u8;       // the gathering device's frame buffer: every device's resolve writes its own pixels there
 };
 
+// What one render call launches on one scene handle, split into stages so that drt_render_multi can interleave the
+// stages of several handles: plan (allocations, kernel parameters) -> per row chunk: render, background, resolve.
+struct LaunchPlan {
+  bool f32 = false;
+  Params<double> Pd; Params<float> Pf;
+  bool collect = false, perlin = false, cloud_only = false;
+  int tile_h = 0, rows_per_chunk = 1, n_chunks = 1;
+  long long per_row = 0;
+  size_t n_corners = 0;
+  int feat = 0, wave_blocks = 0, launches = 0, variant = -1;
+};
+template <typename R> Params<R>& planParams(LaunchPlan& lp);
+template <> Params<double>& planParams<double>(LaunchPlan& lp) { return lp.Pd; }
+template <> Params<float>& planParams<float>(LaunchPlan& lp) { return lp.Pf; }
+
 template <typename R>
-int launchAll(drt_scene* s, const DevScene<R>& ds, const drt_settings& st, const CameraD& cam, const drt_tile& tile, int pool_cap,
-              bool want_f32, drt_counters* counters, const MultiCtx* mc = nullptr) {
-  Params<R> P;
+int planLaunch(drt_scene* s, const DevScene<R>& ds, const drt_settings& st, const CameraD& cam, const drt_tile& tile, int pool_cap,
+               bool want_f32, drt_counters* counters, const MultiCtx* mc, LaunchPlan& lp) {
+  Params<R>& P = planParams<R>(lp);
+  lp.f32 = sizeof(R) == 4;
   fillParams<R>(P, s, ds, st, cam, tile);
-  const bool collect = counters && counters->collect;
-  const long long per_row = (long long)tile.width * P.spp;
-  int rows_per_chunk = st.cloud_only ? tile.height : (int)std::max<long long>(1, std::min<long long>(tile.height, maxChunkSamples() / std::max<long long>(1, per_row)));
-  const size_t n_corners = (size_t)(tile.width + 1) * (tile.height + 1);
-  int rc = ensureScratch(s, st.cloud_only ? 1 : (size_t)rows_per_chunk * per_row, n_corners, (size_t)tile.width * tile.height * 3);
+  lp.collect = counters && counters->collect;
+  lp.perlin = st.perlin_cloud && !st.cloud_only; lp.cloud_only = st.cloud_only; lp.tile_h = tile.height;
+  lp.per_row = (long long)tile.width * P.spp;
+  lp.rows_per_chunk = st.cloud_only ? tile.height : (int)std::max<long long>(1, std::min<long long>(tile.height, maxChunkSamples() / std::max<long long>(1, lp.per_row)));
+  lp.n_chunks = (tile.height + lp.rows_per_chunk - 1) / lp.rows_per_chunk;
+  lp.n_corners = (size_t)(tile.width + 1) * (tile.height + 1);
+  int rc = ensureScratch(s, st.cloud_only ? 1 : (size_t)lp.rows_per_chunk * lp.per_row, lp.n_corners, (size_t)tile.width * tile.height * 3);
   if (rc) return rc;
   P.samples = s->samples; P.need = s->need; P.bg = s->bg; P.out_u8 = s->out_u8; P.out_f32 = want_f32 ? s->out_f32 : nullptr;
   // claim units: one batch on a single device; whole pixels (at least one batch's worth) when devices share the frame
@@ -588,8 +606,8 @@ int launchAll(drt_scene* s, const DevScene<R>& ds, const drt_settings& st, const
   if (mc) {
     const int unit_pixels = std::max(1, (DRT_CTA_SLOTS + P.spp - 1) / P.spp);
     P.unit_samples = unit_pixels * P.spp;
-    const size_t n_units = ((size_t)rows_per_chunk * per_row + P.unit_samples - 1) / P.unit_samples;
-    if ((tile.height + rows_per_chunk - 1) / rows_per_chunk > DRT_MULTI_MAX_CHUNKS) return fail(DRT_ERR_UNSUPPORTED, "frame cut into too many row chunks");
+    const size_t n_units = ((size_t)lp.rows_per_chunk * lp.per_row + P.unit_samples - 1) / P.unit_samples;
+    if (lp.n_chunks > DRT_MULTI_MAX_CHUNKS) return fail(DRT_ERR_UNSUPPORTED, "frame cut into too many row chunks");
     if (n_units > s->owned_cap) {
       if (s->owned) cudaFree(s->owned);
       s->owned = nullptr; s->owned_cap = 0;
@@ -598,9 +616,10 @@ int launchAll(drt_scene* s, const DevScene<R>& ds, const drt_settings& st, const
     }
     P.steal = 1; P.owned = s->owned; P.out_u8 = mc->gather_u8; P.out_f32 = nullptr;
   }
-  P.counts = collect ? s->counts : nullptr;
+  P.counts = lp.collect ? s->counts : nullptr;
   int& wave_blocks = sizeof(R) == 8 ? s->wave_blocks_f64 : s->wave_blocks_f32;
   if (!wave_blocks) wave_blocks = waveGridBlocks<R>();
+  lp.wave_blocks = wave_blocks;
   const size_t pool_bytes = wavePoolBytes<R>(wave_blocks, pool_cap);
   if (!st.cloud_only && pool_bytes > s->pool_cap) {
     if (s->pool) cudaFree(s->pool);
@@ -621,33 +640,74 @@ int launchAll(drt_scene* s, const DevScene<R>& ds, const drt_settings& st, const
   if (s->any_tex) feat |= FT_TEX;
   if (ds.n_geoms > DRT_SMEM_GEOMS) feat |= FT_BIG;
   if (const char* e = getenv("DRT_WAVE_FEAT")) feat |= atoi(e);      // tuning: force a larger instantiation (63 = generic)
-  int variant = -1;
+  lp.feat = feat;
+  return DRT_OK;
+}
+
+// first launches of a call: counters, timing start, background map reset
+int stageBegin(drt_scene* s, LaunchPlan& lp) {
   cudaStream_t q = s->stream;
-  int launches = 0;
-  if (collect) CK(cudaMemsetAsync(s->counts, 0, sizeof(Counts), q));
+  if (lp.collect) CK(cudaMemsetAsync(s->counts, 0, sizeof(Counts), q));
   CK(cudaEventRecord(s->ev0, q));
-  if (st.perlin_cloud && !st.cloud_only) CK(cudaMemsetAsync(s->need, 0, n_corners, q));
+  if (lp.perlin) CK(cudaMemsetAsync(s->need, 0, lp.n_corners, q));
+  return DRT_OK;
+}
+template <typename R>
+int stageRender(drt_scene* s, LaunchPlan& lp, int chunk, const MultiCtx* mc) {
+  Params<R>& P = planParams<R>(lp);
+  cudaStream_t q = s->stream;
+  const int row0 = chunk * lp.rows_per_chunk, rows = std::min(lp.rows_per_chunk, lp.tile_h - row0);
+  P.sample_base = (long long)row0 * lp.per_row;
+  P.sample_count = (long long)rows * lp.per_row;
+  if (mc) {
+    P.batch_counter = mc->counters + chunk;
+    CK(cudaMemsetAsync(s->owned, 0, ((size_t)P.sample_count + P.unit_samples - 1) / P.unit_samples, q));
+  } else CK(cudaMemsetAsync(s->batch_counter, 0, sizeof(unsigned long long), q));
+  lp.variant = launchRenderSamples<R>(P, lp.collect, lp.feat, lp.wave_blocks, q); lp.launches++;
+  return DRT_OK;
+}
+// background colours of the pixel corners marked so far.  `shared`: the marks and colours live in the gathering device's
+// maps and all devices claim blocks of corners from `corner_counter` there (drt_render_multi).
+template <typename R>
+int stageCloud(drt_scene* s, LaunchPlan& lp, unsigned char* need, float4* bg, unsigned long long* corner_counter) {
+  Params<R> P = planParams<R>(lp);
+  P.need = need; P.bg = bg; P.corner_counter = corner_counter;
+  launchCloudCorners<R>(P, s->stream); lp.launches++;
+  return DRT_OK;
+}
+template <typename R>
+int stageResolve(drt_scene* s, LaunchPlan& lp, int chunk) {
+  Params<R>& P = planParams<R>(lp);
+  const int row0 = chunk * lp.rows_per_chunk, rows = std::min(lp.rows_per_chunk, lp.tile_h - row0);
+  launchResolve<R>(P, row0, rows, s->stream); lp.launches++;
+  return DRT_OK;
+}
+int stageEnd(drt_scene* s, LaunchPlan& lp, drt_counters* counters) {
+  CK(cudaEventRecord(s->ev1, s->stream));
+  CK(cudaGetLastError());
+  if (counters) { counters->kernel_launches = lp.launches; counters->kernel_variant = lp.variant; }
+  return DRT_OK;
+}
+#define DRT_BY_PRECISION(lp, call_d, call_f) ((lp).f32 ? (call_f) : (call_d))
+
+template <typename R>
+int launchAll(drt_scene* s, const DevScene<R>& ds, const drt_settings& st, const CameraD& cam, const drt_tile& tile, int pool_cap,
+              bool want_f32, drt_counters* counters) {
+  LaunchPlan lp;
+  int rc = planLaunch<R>(s, ds, st, cam, tile, pool_cap, want_f32, counters, nullptr, lp);
+  if (rc) return rc;
+  if ((rc = stageBegin(s, lp))) return rc;
   if (st.cloud_only) {
-    launchCloudCorners<R>(P, q); launches++;
-    launchResolve<R>(P, 0, tile.height, q); launches++;
+    if ((rc = stageCloud<R>(s, lp, s->need, s->bg, nullptr))) return rc;
+    if ((rc = stageResolve<R>(s, lp, 0))) return rc;
   } else {
-    for (int row0 = 0; row0 < tile.height; row0 += rows_per_chunk) {
-      const int rows = std::min(rows_per_chunk, tile.height - row0);
-      P.sample_base = (long long)row0 * per_row;
-      P.sample_count = (long long)rows * per_row;
-      if (mc) {
-        P.batch_counter = mc->counters + row0 / rows_per_chunk;
-        CK(cudaMemsetAsync(s->owned, 0, ((size_t)P.sample_count + P.unit_samples - 1) / P.unit_samples, q));
-      } else CK(cudaMemsetAsync(s->batch_counter, 0, sizeof(unsigned long long), q));
-      variant = launchRenderSamples<R>(P, collect, feat, wave_blocks, q); launches++;
-      if (st.perlin_cloud) { launchCloudCorners<R>(P, q); launches++; }
-      launchResolve<R>(P, row0, rows, q); launches++;
+    for (int c = 0; c < lp.n_chunks; c++) {
+      if ((rc = stageRender<R>(s, lp, c, nullptr))) return rc;
+      if (lp.perlin && (rc = stageCloud<R>(s, lp, s->need, s->bg, nullptr))) return rc;
+      if ((rc = stageResolve<R>(s, lp, c))) return rc;
     }
   }
-  CK(cudaEventRecord(s->ev1, q));
-  CK(cudaGetLastError());
-  if (counters) { counters->kernel_launches = launches; counters->kernel_variant = variant; }
-  return DRT_OK;
+  return stageEnd(s, lp, counters);
 }
 
 // Validation shared by every render entry point; sizes the CTA ray pools and builds the camera.
@@ -680,9 +740,9 @@ int planRender(drt_scene* s, const drt_settings* st, const drt_tile* tile, int& 
 }
 
 int launchFor(drt_scene* s, const drt_settings* st, const CameraD& cam, const drt_tile* tile, int pool_cap, bool want_f32,
-              drt_counters* counters, const MultiCtx* mc) {
-  if (st->precision == DRT_PRECISION_FP32) return launchAll<float>(s, s->df, *st, cam, *tile, pool_cap, want_f32, counters, mc);
-  return launchAll<double>(s, s->dd, *st, cam, *tile, pool_cap, want_f32, counters, mc);
+              drt_counters* counters) {
+  if (st->precision == DRT_PRECISION_FP32) return launchAll<float>(s, s->df, *st, cam, *tile, pool_cap, want_f32, counters);
+  return launchAll<double>(s, s->dd, *st, cam, *tile, pool_cap, want_f32, counters);
 }
 
 // After the scene's stream has been synchronised: overflow flag, timing, event counters (`hc` already copied back).
@@ -719,7 +779,7 @@ int renderCommon(const drt_scene* cs, const drt_settings* st, const drt_tile* ti
   if (tile->device != s->device) return fail(DRT_ERR_INVALID, "tile.device differs from the scene's device");
   CK(cudaSetDevice(s->device));
   const bool want_f32 = out_f32 != nullptr;
-  rc = launchFor(s, st, cam, tile, pool_cap, want_f32, counters, nullptr);
+  rc = launchFor(s, st, cam, tile, pool_cap, want_f32, counters);
   if (rc) return rc;
   const size_t n_out = (size_t)tile->width * tile->height * 3;
   if (copy_back) {
@@ -767,18 +827,79 @@ int renderMulti(drt_scene* const* scenes, int n, const drt_settings* st, const d
     int rc = ensureScratch(g, (size_t)rows_per_chunk * per_row, (size_t)(tile->width + 1) * (tile->height + 1), n_out);
     if (rc) return rc;
   }
-  if (!g->steal_counters) CK(cudaMalloc(&g->steal_counters, sizeof(unsigned long long) * DRT_MULTI_MAX_CHUNKS));
-  CK(cudaMemsetAsync(g->steal_counters, 0, sizeof(unsigned long long) * DRT_MULTI_MAX_CHUNKS, g->stream));
+  // [0, MAX_CHUNKS): unit counters of the row chunks; [MAX_CHUNKS, 2 MAX_CHUNKS): corner-block counters of the background passes
+  if (!g->steal_counters) CK(cudaMalloc(&g->steal_counters, sizeof(unsigned long long) * 2 * DRT_MULTI_MAX_CHUNKS));
+  CK(cudaMemsetAsync(g->steal_counters, 0, sizeof(unsigned long long) * 2 * DRT_MULTI_MAX_CHUNKS, g->stream));
   for (int i = 0; i < n; i++) if (!scenes[i]->ev_sync) { CK(cudaSetDevice(scenes[i]->device)); CK(cudaEventCreateWithFlags(&scenes[i]->ev_sync, cudaEventDisableTiming)); }
   CK(cudaSetDevice(g->device));
   CK(cudaEventRecord(g->ev_sync, g->stream));                  // counters zeroed, frame buffer allocated
   MultiCtx mc; mc.counters = g->steal_counters; mc.gather_u8 = g->out_u8;
+  std::vector<LaunchPlan> plans(n);
   for (int i = 0; i < n; i++) {
     drt_scene* s = scenes[i];
     CK(cudaSetDevice(s->device));
     if (i) CK(cudaStreamWaitEvent(s->stream, g->ev_sync, 0));
     drt_tile t = *tile; t.device = s->device;
-    int rc = launchFor(s, st, cam, &t, pool_cap[i], false, counters ? &counters[i] : nullptr, &mc);
+    int rc = (st->precision == DRT_PRECISION_FP32)
+                 ? planLaunch<float>(s, s->df, *st, cam, t, pool_cap[i], false, counters ? &counters[i] : nullptr, &mc, plans[i])
+                 : planLaunch<double>(s, s->dd, *st, cam, t, pool_cap[i], false, counters ? &counters[i] : nullptr, &mc, plans[i]);
+    if (rc) return rc;
+    if ((rc = stageBegin(s, plans[i]))) return rc;
+    if (i == 0) CK(cudaEventRecord(g->ev_sync, g->stream));    // ... and the shared background map is reset
+  }
+  // every stream waits for every other stream's work so far (events only: the host does not block)
+  auto barrier = [&]() -> int {
+    for (int i = 0; i < n; i++) { CK(cudaSetDevice(scenes[i]->device)); CK(cudaEventRecord(scenes[i]->ev_sync, scenes[i]->stream)); }
+    for (int i = 0; i < n; i++) {
+      CK(cudaSetDevice(scenes[i]->device));
+      for (int k = 0; k < n; k++) if (k != i) CK(cudaStreamWaitEvent(scenes[i]->stream, scenes[k]->ev_sync, 0));
+    }
+    return DRT_OK;
+  };
+  const LaunchPlan& lp0 = plans[0];
+  for (int c = 0; c < lp0.n_chunks; c++) {
+    for (int i = 0; i < n; i++) {
+      CK(cudaSetDevice(scenes[i]->device));
+      int rc = DRT_BY_PRECISION(plans[i], stageRender<double>(scenes[i], plans[i], c, &mc), stageRender<float>(scenes[i], plans[i], c, &mc));
+      if (rc) return rc;
+    }
+    if (lp0.perlin) {
+      // The background of a missed sample is a 200-step noise march per pixel CORNER, shared by the four pixels around it:
+      // with the frame dealt out in small units every device would evaluate the corners of its own pixels, up to 4x the
+      // work.  Instead the devices' corner marks are merged in the gathering device's map, all devices claim blocks of
+      // marked corners from one counter, write the colours there, and pull the finished map back before resolving.
+      int rc;
+      for (int i = 1; i < n; i++) {
+        CK(cudaSetDevice(scenes[i]->device));
+        launchNeedPush(scenes[i]->need, g->need, lp0.n_corners, scenes[i]->stream); plans[i].launches++;
+      }
+      CK(cudaSetDevice(g->device));
+      CK(cudaMemsetAsync(g->steal_counters + DRT_MULTI_MAX_CHUNKS + c, 0, sizeof(unsigned long long), g->stream));
+      if ((rc = barrier())) return rc;
+      for (int i = 0; i < n; i++) {
+        CK(cudaSetDevice(scenes[i]->device));
+        unsigned long long* cc = g->steal_counters + DRT_MULTI_MAX_CHUNKS + c;
+        rc = DRT_BY_PRECISION(plans[i], stageCloud<double>(scenes[i], plans[i], g->need, g->bg, cc), stageCloud<float>(scenes[i], plans[i], g->need, g->bg, cc));
+        if (rc) return rc;
+      }
+      if ((rc = barrier())) return rc;
+      for (int i = 1; i < n; i++) {
+        CK(cudaSetDevice(scenes[i]->device));
+        CK(cudaMemcpyAsync(scenes[i]->need, g->need, lp0.n_corners, cudaMemcpyDeviceToDevice, scenes[i]->stream));
+        CK(cudaMemcpyAsync(scenes[i]->bg, g->bg, lp0.n_corners * sizeof(float4), cudaMemcpyDeviceToDevice, scenes[i]->stream));
+      }
+    }
+    for (int i = 0; i < n; i++) {
+      CK(cudaSetDevice(scenes[i]->device));
+      int rc = DRT_BY_PRECISION(plans[i], stageResolve<double>(scenes[i], plans[i], c), stageResolve<float>(scenes[i], plans[i], c));
+      if (rc) return rc;
+    }
+    // the next chunk's marks and colours go into the gathering device's maps: its resolve must have read them first
+    if (lp0.perlin && c + 1 < lp0.n_chunks) { int rc = barrier(); if (rc) return rc; }
+  }
+  for (int i = 0; i < n; i++) {
+    CK(cudaSetDevice(scenes[i]->device));
+    int rc = stageEnd(scenes[i], plans[i], counters ? &counters[i] : nullptr);
     if (rc) return rc;
   }
   // the gathering stream waits for everyone's pixels, then one copy to the host

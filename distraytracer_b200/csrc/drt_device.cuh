@@ -205,6 +205,7 @@ struct Params {
   int unit_samples;
   int steal;                // 1: batch_counter is shared between devices
   unsigned char* owned;     // nullptr unless stealing
+  unsigned long long* corner_counter;   // cloud_corners: nullptr, or the counter all devices claim blocks of corners from
   int* overflow;
 };
 

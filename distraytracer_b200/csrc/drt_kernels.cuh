@@ -1725,27 +1725,49 @@ __device__ void cloudColor(const Params<R>& P, const Vec<R>& ray, float frame, d
   for (int c = 0; c < 3; c++) out[c] = (double)(1 + P.saturation) * col[c] - (double)P.saturation * (0.33 * s);
 }
 
-// One thread per pixel corner of the tile's (w+1)x(h+1) grid.
+// One thread per pixel corner of the tile's (w+1)x(h+1) grid, in blocks of 128 corners.  A block is either the CTA's own
+// (blockIdx) or -- one frame on several GPUs -- claimed from a counter all devices share, the marks and colours then
+// living in the gathering device's maps (peer loads / stores).
 template <typename R>
 __global__ void __launch_bounds__(128) cloud_corners(const __grid_constant__ Params<R> P) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int gw = P.w + 1, gh = P.h + 1;
-  if (idx >= gw * gh) return;
-  if (!P.cloud_only && P.need[idx] != 1) return;   // 0: not wanted, 2: already computed by an earlier row chunk
-  const int cx = idx % gw, cy = idx / gw;
-  const int x = P.x0 + cx, y = P.y0 + cy;
-  const Vec<R> rayDir = eyeRay<R>(P, x, y);
-  Vec<R> point;
-  if (P.cloud_only) point = mulPoint<R>(P.cloud_mcam, rayDir + P.eye);             // renderImageCloud :1265-1268
-  else {
-    const Vec<R> focalPoint = P.eye + (R)P.focal_length * rayDir;
-    point = (P.frame >= P.frame_cloud) ? mulPoint<R>(P.new_mcam, focalPoint) : mulPoint<R>(P.mcam, focalPoint);   // :1079-1087
+  const int n_blocks = (gw * gh + 127) / 128;
+  __shared__ int s_blk;
+  for (int blk = blockIdx.x;; ) {
+    if (P.corner_counter) {
+      __syncthreads();
+      if (threadIdx.x == 0) s_blk = (int)min(atomicAdd_system(P.corner_counter, 1ull), (unsigned long long)n_blocks);
+      __syncthreads();
+      blk = s_blk;
+    }
+    if (blk >= n_blocks) return;
+    const int idx = blk * 128 + threadIdx.x;
+    // 0: not wanted, 2: already computed by an earlier row chunk
+    if (idx < gw * gh && (P.cloud_only || P.need[idx] == 1)) {
+      const int cx = idx % gw, cy = idx / gw;
+      const int x = P.x0 + cx, y = P.y0 + cy;
+      const Vec<R> rayDir = eyeRay<R>(P, x, y);
+      Vec<R> point;
+      if (P.cloud_only) point = mulPoint<R>(P.cloud_mcam, rayDir + P.eye);             // renderImageCloud :1265-1268
+      else {
+        const Vec<R> focalPoint = P.eye + (R)P.focal_length * rayDir;
+        point = (P.frame >= P.frame_cloud) ? mulPoint<R>(P.new_mcam, focalPoint) : mulPoint<R>(P.mcam, focalPoint);   // :1079-1087
+      }
+      double c[3];
+      cloudColor<R>(P, point, (float)P.frame, c);
+      P.bg[idx] = make_float4((float)c[0], (float)c[1], (float)c[2], 0.f);
+      if (!P.cloud_only) P.need[idx] = 2;
+      if (P.counts) atomicAdd(&P.counts->noise_evals, 200ull);
+    }
+    if (!P.corner_counter) return;
   }
-  double c[3];
-  cloudColor<R>(P, point, (float)P.frame, c);
-  P.bg[idx] = make_float4((float)c[0], (float)c[1], (float)c[2], 0.f);
-  if (!P.cloud_only) P.need[idx] = 2;
-  if (P.counts) atomicAdd(&P.counts->noise_evals, 200ull);
+}
+
+// drt_render_multi: a device's corner marks of the current row chunk -> the gathering device's map (peer stores).
+// `mine` holds 0 / 1 / 2 like the shared map, 2 only where the shared map already has it.
+static __global__ void need_push(const unsigned char* __restrict__ mine, unsigned char* shared, const size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && mine[i] == 1) shared[i] = 1;
 }
 
 // One thread per pixel: (:1213-1217) + writePPM's truncation (helpers.h:178-179).

@@ -65,4 +65,5 @@ template <typename R> using WaveFnT = void (*)(Params<R>);
 template <typename R, int GROUP> WaveFnT<R> waveKernelOfGroup(int feat, bool collect);
 template <typename R> void launchCloudCorners(const Params<R>& P, cudaStream_t q);
 template <typename R> void launchResolve(const Params<R>& P, int row0, int rows, cudaStream_t q);
+void launchNeedPush(const unsigned char* mine, unsigned char* shared, size_t n, cudaStream_t q);
 }  // namespace drt

@@ -1,6 +1,7 @@
 // Included by drt_kernels_{f64,f32}_g{0,1,2}.cu with DRT_REAL and DRT_GROUP defined.  The render_wave instantiations of
 // one precision are spread over three translation units (they compile in parallel); group 0 also holds the launchers and
 // the two small kernels.
+#include <algorithm>
 #include "drt_kernels.cuh"
 #include "drt_launch.h"
 
@@ -63,8 +64,20 @@ template <> int launchRenderSamples<DRT_REAL>(const Params<DRT_REAL>& P, bool co
 }
 template <> void launchCloudCorners<DRT_REAL>(const Params<DRT_REAL>& P, cudaStream_t q) {
   const int n = (P.w + 1) * (P.h + 1);
-  cloud_corners<DRT_REAL><<<(n + 127) / 128, 128, 0, q>>>(P);
+  int blocks = (n + 127) / 128;
+  if (P.corner_counter) {             // blocks of corners are claimed from a shared counter: a resident grid is enough
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    blocks = std::min(blocks, sms * 16);
+  }
+  cloud_corners<DRT_REAL><<<blocks, 128, 0, q>>>(P);
 }
+#ifdef DRT_DEFINE_SHARED_LAUNCHERS
+void launchNeedPush(const unsigned char* mine, unsigned char* shared, size_t n, cudaStream_t q) {
+  need_push<<<(unsigned)((n + 255) / 256), 256, 0, q>>>(mine, shared, n);
+}
+#endif
 template <> void launchResolve<DRT_REAL>(const Params<DRT_REAL>& P, int row0, int rows, cudaStream_t q) {
   resolve<DRT_REAL><<<(P.w * rows + 255) / 256, 256, 0, q>>>(P, row0, rows);
 }
