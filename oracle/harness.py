@@ -150,11 +150,14 @@ ORACLE_KEYED, ORACLE_STREAM = 0, 1
 class Oracle:
     """The CPU restatement (oracle/drt_oracle.cpp) over a POD scene."""
 
-    def __init__(self, scene):
+    def __init__(self, scene, builder=0):
+        """builder 0: the reference's SAH tree (candidate order included); 1: the median-split stand-in for scenes the
+        reference's O(n^2) build cannot handle (conservative gather, one primitive per leaf).  A scene's mesh is
+        expanded into individual Triangle primitives on the C++ side."""
         self.lib = C.CDLL(ORACLE_SO)
         L = self.lib
         L.drt_oracle_last_error.restype = C.c_char_p
-        L.drt_oracle_scene_create.argtypes = [C.POINTER(abi.SceneDesc), C.POINTER(C.c_void_p)]
+        L.drt_oracle_scene_create_ex.argtypes = [C.POINTER(abi.SceneDesc), C.c_int, C.POINTER(C.c_void_p)]
         L.drt_oracle_scene_destroy.argtypes = [C.c_void_p]
         L.drt_oracle_render.argtypes = [C.c_void_p, C.POINTER(abi.Settings), C.POINTER(abi.Tile), C.c_int,
                                         C.POINTER(C.c_float), C.POINTER(C.c_uint8), C.POINTER(abi.Counters),
@@ -164,7 +167,7 @@ class Oracle:
         self.scene = scene
         self._desc = scene.desc()
         self.handle = C.c_void_p()
-        rc = L.drt_oracle_scene_create(C.byref(self._desc), C.byref(self.handle))
+        rc = L.drt_oracle_scene_create_ex(C.byref(self._desc), int(builder), C.byref(self.handle))
         if rc != 0:
             raise RuntimeError(f"oracle scene_create failed ({rc}): {L.drt_oracle_last_error().decode()}")
 

@@ -67,3 +67,30 @@ def test_oracle_rejects_what_the_path_does_not_cover(oracle_lib):
     ball.flags |= abi.FLAG_TEXTURE; ball.tex_frame = 0
     with pytest.raises(RuntimeError, match="getUV"):
         Oracle(Scene(prims, scene.lights, scene.textures))
+
+
+def test_fast_builder_gathers_what_the_reference_tree_gathers(oracle_lib):
+    """oracle/drt_oracle.cpp FastBuilder (median split, one primitive per leaf, tight-box traversal + the reference's leaf
+    test) stands in for the reference's O(n^2) generateBVH on the 10^6-triangle scene.  On a mesh both can build -- textured
+    terrain, DOF, a sphere with velocity blur, shadow rays -- it must produce the image the reference-order tree produces,
+    and the image a brute-force visit of every leaf produces (DRT_ORACLE_NOCULL), bit for bit."""
+    import os, subprocess, sys
+    from distraytracer_b200 import scenes
+    from distraytracer_b200.scene import Scene
+    from oracle.harness import Oracle, ORACLE_KEYED
+    scene, s = scenes.config5(n=24, xres=160, yres=90, spp=4)
+    flat = Scene(list(scene.prims) + scenes.mesh_to_prims(scene.mesh), scene.lights, scene.textures)
+    want, wab, _, _ = Oracle(flat).render(s, mode=ORACLE_KEYED)            # individual Triangle prims, reference tree
+    mesh_ref, _, _, _ = Oracle(scene).render(s, mode=ORACLE_KEYED)         # mesh expanded by the oracle, reference tree
+    fast, fab, _, _ = Oracle(scene, builder=1).render(s, mode=ORACLE_KEYED)
+    assert np.array_equal(want, mesh_ref)
+    assert np.array_equal(want, fast) and np.array_equal(wab, fab) and want.std() > 5
+    code = ("import sys, numpy as np; sys.path.insert(0, %r);"
+            "from distraytracer_b200 import scenes; from oracle.harness import Oracle, ORACLE_KEYED;"
+            "scene, s = scenes.config5(n=12, xres=64, yres=36, spp=4);"
+            "a = Oracle(scene, builder=1).render(s, mode=ORACLE_KEYED)[0]; np.save(sys.argv[1], a)") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        for env, name in (({}, "cull.npy"), ({"DRT_ORACLE_NOCULL": "1"}, "brute.npy")):
+            subprocess.check_call([sys.executable, "-c", code, os.path.join(td, name)], env={**os.environ, **env})
+        assert np.array_equal(np.load(os.path.join(td, "cull.npy")), np.load(os.path.join(td, "brute.npy")))
