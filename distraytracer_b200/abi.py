@@ -5,15 +5,17 @@ struct sizes against the values the shared library reports.
 """
 import ctypes as C
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # drt_status
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_NO_DEVICE, ERR_CUDA, ERR_SCENE = 0, -1, -2, -3, -4, -5
 
 # drt_prim_type
 (PRIM_SPHERE, PRIM_CYLINDER, PRIM_TRIANGLE, PRIM_RECTANGLE, PRIM_RECTPRISMV2,
- PRIM_CHECKERBOARD, PRIM_CHECKERBOARD_HOLE, PRIM_CHECKER_CYLINDER) = range(8)
-PRIM_TYPE_COUNT = 8
+ PRIM_CHECKERBOARD, PRIM_CHECKERBOARD_HOLE, PRIM_CHECKER_CYLINDER,
+ PRIM_RECTPRISM, PRIM_RECTPRISM_CYL, PRIM_RECTPRISM_HOLES) = range(11)
+PRIM_TYPE_COUNT = 11
+MAX_HOLES = 4
 # drt_name
 NAME_OTHER, NAME_RECTANGLE, NAME_SPHERELIGHT, NAME_RECTANGLELIGHT = range(4)
 # drt_material
@@ -33,6 +35,10 @@ D3 = C.c_double * 3
 D2 = C.c_double * 2
 
 
+class Hole(C.Structure):
+    _fields_ = [("type", C.c_int32), ("pad_", C.c_int32), ("c1", D3), ("c2", D3), ("radius", C.c_double), ("color", D3)]
+
+
 class Prim(C.Structure):
     _fields_ = [
         ("type", C.c_int32), ("name", C.c_int32), ("material", C.c_int32), ("model", C.c_int32),
@@ -43,7 +49,11 @@ class Prim(C.Structure):
         ("c1", D3), ("c2", D3), ("uvA", D2), ("uvB", D2), ("uvC", D2), ("mesh_normal", D3),
         ("S", C.c_double), ("borderwidth", C.c_double), ("color1", D3), ("color2", D3),
         ("hole", D3 * 4), ("velocity", D3),
+        ("n_holes", C.c_int32), ("pad_", C.c_int32), ("holes", Hole * MAX_HOLES),
     ]
+
+
+PRIM_BYTES_V1 = 624     # sizeof(drt_prim) of ABI version 1 (no holes): fixtures written then are padded on load
 
 
 class Light(C.Structure):

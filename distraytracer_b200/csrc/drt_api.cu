@@ -36,6 +36,7 @@ D3 V(const double* p) { return mk<double>(p[0], p[1], p[2]); }
 template <typename R> Vec<R> cv(const D3& v) { return mk<R>((R)v.x, (R)v.y, (R)v.z); }
 void f3(float* o, const double* p) { o[0] = (float)p[0]; o[1] = (float)p[1]; o[2] = (float)p[2]; }
 
+void rows3x4(double* out, const D3& r0, const D3& r1, const D3& r2, const D3& eye);
 struct RectD { D3 A, nrm, e1, e2; double len1, len2; };
 RectD makeRect(const D3& A, const D3& B, const D3& C, const D3& D) {
   RectD r;
@@ -107,7 +108,7 @@ void primBounds(const drt_prim& p, double lo[3], double hi[3]) {
       }
       break;
     case DRT_PRIM_TRIANGLE: acc(p.A, true); acc(p.B, false); acc(p.C, false); break;
-    case DRT_PRIM_RECTPRISMV2:
+    case DRT_PRIM_RECTPRISMV2: case DRT_PRIM_RECTPRISM: case DRT_PRIM_RECTPRISM_CYL: case DRT_PRIM_RECTPRISM_HOLES:
       acc(p.A, true); acc(p.B, false); acc(p.C, false); acc(p.D, false); acc(p.E, false); acc(p.F, false); acc(p.G, false); acc(p.H, false);
       break;
     default: acc(p.A, true); acc(p.B, false); acc(p.C, false); acc(p.D, false); break;
@@ -213,6 +214,47 @@ int flatten(const drt_prim* prims, int n_prims, const drt_light* lights, int n_l
             q.hlen1 = (R)hr.len1; q.hlen2 = (R)hr.len2;
           }
         }
+        break; }
+      case DRT_PRIM_RECTPRISM: case DRT_PRIM_RECTPRISM_CYL: case DRT_PRIM_RECTPRISM_HOLES: {
+        // the slab-box prisms (geometry.cpp:950-2246): ONE geom, the world AABB of the corners (getBounds overwrites the
+        // object-space bounds, :987-988); the class, the holes and the normals live in the shading record
+        if (p.type != DRT_PRIM_RECTPRISM) {
+          if (p.n_holes < 0 || p.n_holes > DRT_MAX_HOLES)
+            return fail(DRT_ERR_UNSUPPORTED, "primitive " + std::to_string(i) + ": more than DRT_MAX_HOLES holes");
+          for (int k = 0; k < p.n_holes; k++) {
+            const int ht = p.holes[k].type;
+            if (!(ht == DRT_PRIM_CYLINDER || (ht == DRT_PRIM_SPHERE && p.type == DRT_PRIM_RECTPRISM_HOLES)))
+              return fail(DRT_ERR_UNSUPPORTED, "primitive " + std::to_string(i) + ": hole of a class the reference has no intersectCap / intersectMax for");
+          }
+        }
+        q.n0 = cv<R>(-normalized(cross(F - E, H - E)));                  // normbot   geometry.cpp:1325
+        q.n1 = cv<R>(normalized(cross(E - A, D - A)));                   // normright
+        q.n2 = cv<R>(normalized(cross(B - A, E - A)));                   // normfront
+        q.pA = cv<R>(A); q.pG = cv<R>(G);
+        setUVRect(A, C, D);                                              // RectPrism::getUV geometry.cpp:1440-1461
+        q.height = (float)norm(E - A);
+        { double m[12]; rows3x4(m, normalized(B - A), normalized(D - A), normalized(E - A), V(p.center)); for (int k = 0; k < 12; k++) q.objM[k] = (R)m[k]; }   // :975-984
+        q.n_holes = p.type == DRT_PRIM_RECTPRISM ? 0 : p.n_holes;
+        for (int k = 0; k < q.n_holes; k++) {
+          const drt_hole& hh = p.holes[k];
+          HoleD<R>& o = q.holes[k];
+          o.type = hh.type == DRT_PRIM_SPHERE ? G_SPHERE : G_CYL;
+          o.c1 = cv<R>(V(hh.c1)); o.c2 = cv<R>(V(hh.c2)); o.axis = cv<R>(normalized(V(hh.c2) - V(hh.c1)));
+          o.radius = (float)hh.radius; f3(o.color, hh.color);
+        }
+        Geom<R> g; memset(&g, 0, sizeof(g));
+        g.type = G_BOX; g.owner = i; g.vel = cv<R>(vel);
+        const D3 cs[8] = {A, B, C, D, E, F, G, H};
+        D3 lo = A, hi = A;
+        for (const D3& c8 : cs) {
+          lo = mk<double>(std::min(lo.x, c8.x), std::min(lo.y, c8.y), std::min(lo.z, c8.z));
+          hi = mk<double>(std::max(hi.x, c8.x), std::max(hi.y, c8.y), std::max(hi.z, c8.z));
+        }
+        g.p0 = cv<R>(lo); g.p1 = cv<R>(hi);
+        // never culled by the fp32 filter: a hole can stick out of the box (the hit is then nearer than the box), and
+        // RectPrismWithCylinder::intersectShadow reports boxes BEYOND the light as occluders (:1744)
+        g.blo = make_float4(-1e30f, -1e30f, -1e30f, 0.f); g.bhi = make_float4(1e30f, 1e30f, 1e30f, 0.f);
+        hs.geoms.push_back(g);
         break; }
       case DRT_PRIM_RECTPRISMV2: {
         q.n0 = cv<R>(-normalized(cross(F - E, H - E)));                  // normbot   geometry.cpp:866
@@ -401,7 +443,7 @@ int waveFeatPick(int need) {
 struct drt_scene {
   int device = 0;
   std::vector<drt_prim> prims; std::vector<drt_light> lights; int n_textures = 0;
-  bool any_glass = false, any_tex = false, any_motion = false;
+  bool any_glass = false, any_tex = false, any_motion = false, any_box = false;
   DevScene<double> dd; DevScene<float> df;
   std::vector<cudaArray_t> tex_arrays; std::vector<cudaTextureObject_t> tex_objs;
   cudaTextureObject_t* d_tex = nullptr; int2* d_texdims = nullptr;
@@ -452,8 +494,9 @@ int flattenAndUpload(drt_scene* s) {
   rc = s->stage.reserve(uploadBytes(hd) + uploadBytes(hf)); if (rc) return rc;
   rc = upload(hd, s->dd, s->stage, s->stream); if (rc) return rc;
   rc = upload(hf, s->df, s->stage, s->stream); if (rc) return rc;
-  s->any_glass = s->any_tex = s->any_motion = false;
+  s->any_glass = s->any_tex = s->any_motion = s->any_box = false;
   auto scan = [&](const drt_prim& p) {
+    if (p.type == DRT_PRIM_RECTPRISM || p.type == DRT_PRIM_RECTPRISM_CYL || p.type == DRT_PRIM_RECTPRISM_HOLES) s->any_box = true;
     if (p.material == DRT_MAT_GLASS) s->any_glass = true;
     if (p.flags & DRT_FLAG_TEXTURE) s->any_tex = true;
     if (p.flags & DRT_FLAG_MOTION) s->any_motion = true;
@@ -639,6 +682,7 @@ int planLaunch(drt_scene* s, const DevScene<R>& ds, const drt_settings& st, cons
   if (s->any_glass && st.reflect) feat |= FT_GLASS;
   if (s->any_tex) feat |= FT_TEX;
   if (ds.n_geoms > DRT_SMEM_GEOMS) feat |= FT_BIG;
+  if (s->any_box) feat |= FT_BOX;
   if (const char* e = getenv("DRT_WAVE_FEAT")) feat |= atoi(e);      // tuning: force a larger instantiation (63 = generic)
   lp.feat = feat;
   return DRT_OK;
@@ -764,6 +808,7 @@ int finishRender(drt_scene* s, const drt_settings* st, drt_counters* counters, c
       counters->prim_tests[DRT_PRIM_CYLINDER] = hc.geom_tests[G_CYL];
       counters->prim_tests[DRT_PRIM_TRIANGLE] = hc.geom_tests[G_TRI];
       counters->prim_tests[DRT_PRIM_RECTANGLE] = hc.geom_tests[G_RECT] + hc.geom_tests[G_CHECKER];   // rectangle tests incl. prism faces
+      counters->prim_tests[DRT_PRIM_RECTPRISM] = hc.geom_tests[G_BOX];                              // all three slab-box classes
     }
   }
   return DRT_OK;

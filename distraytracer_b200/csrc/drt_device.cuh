@@ -71,7 +71,7 @@ template <typename R> __host__ __device__ inline Vec<R> cmul(Vec<R> a, Vec<R> b)
 template <typename R> __host__ __device__ inline bool isZero(Vec<R> a) { return !(dot(a, a) > R(0)) && dot(a, a) == dot(a, a); }
 
 // ---------------------------------------------------------------------------
-enum GeomType { G_SPHERE = 0, G_CYL = 1, G_TRI = 2, G_RECT = 3, G_CHECKER = 4, G_HOLE = 5 };
+enum GeomType { G_SPHERE = 0, G_CYL = 1, G_TRI = 2, G_RECT = 3, G_CHECKER = 4, G_HOLE = 5, G_BOX = 6 };
 enum GeomFlags {
   GF_NAME_RECTANGLE = 1,  // moves in y during reference-mode motion blur (render_final_project.cpp:1116)
   GF_HAS_HOLE = 2,        // next record is this checkerboard's hole rectangle
@@ -88,6 +88,7 @@ struct alignas(16) Geom {
   // cyl    : p0 c1, p1 c2, p2 axis                       f0 radius
   // tri    : p0 A,  p1 B-A, p2 C-A, p3 mesh_normal
   // rect   : p0 A,  p1 unit normal, p2 (B-A)^, p3 (D-A)^ len1 |B-A|, len2 |D-A|, f2 S
+  // box    : p0 lbound, p1 ubound (world AABB of the prism's corners); holes and the class live in prims[owner]
   Vec<R> p0, p1, p2, p3;
   float f0, f1, f2, f3;
   Vec<R> vel;   // DRT_BLUR_VELOCITY displacement per unit time
@@ -106,6 +107,16 @@ struct alignas(16) NodeD {
   int left, right;
   int parent;        // -1 at the root
   int pad_[2];
+};
+
+// One hole of RectPrismWithCylinder / RectPrismWithHoles (geometry.h:195, 216)
+template <typename R>
+struct alignas(16) HoleD {
+  Vec<R> c1, c2, axis;   // sphere: c1 = centre
+  float radius;
+  int type;              // G_SPHERE or G_CYL
+  float color[3];
+  float pad_;
 };
 
 template <typename R>
@@ -132,6 +143,9 @@ struct alignas(16) PrimD {
   // emissive (render_final_project.cpp:775-789)
   Vec<R> center, eA, eB, eC, eD; R e_den;
   Vec<R> vel;
+  // slab-box prisms (types 8-10): objM above holds cob * origin (geometry.cpp:975-984)
+  float height; int n_holes;
+  HoleD<R> holes[4];
 };
 
 // one mesh triangle for the exact test + texture coordinates (drt_lbvh.cuh)
@@ -152,7 +166,7 @@ struct alignas(16) LightD {
 };
 
 struct Counts {
-  unsigned long long samples, rays, shadow_rays, geom_tests[6], shade_evals, noise_evals, node_tests;
+  unsigned long long samples, rays, shadow_rays, geom_tests[7], shade_evals, noise_evals, node_tests;
 };
 
 template <typename R>

@@ -155,6 +155,257 @@ __device__ inline bool boxHit(const NodeD<R>& nd, const Vec<R>& ray, const Vec<R
   return tmax > 0;
 }
 
+
+template <typename R>
+__device__ inline Vec<R> mulPoint(const R* m, const Vec<R>& p) {  // (M*(p,1)).head<3>(), 4-term sums as (a+b)+(c+d)
+  return mk<R>((m[0] * p.x + m[1] * p.y) + (m[2] * p.z + m[3]), (m[4] * p.x + m[5] * p.y) + (m[6] * p.z + m[7]),
+               (m[8] * p.x + m[9] * p.y) + (m[10] * p.z + m[11]));
+}
+
+// ---- the slab-box prisms: RectPrism / RectPrismWithCylinder / RectPrismWithHoles (geometry.cpp:950-2246) --------------
+// Only in instantiations with FT_BOX.  The box is the WORLD AABB of the corners (geometry.cpp:987-988); the three classes
+// open with the BoundingVolume-style slab test and differ in how an axis-parallel ray is detected and whether a start point
+// ON the bound counts:
+//   kind 0 RectPrism::intersect             isinf(1/ray)  lbound <= start <= ubound   :998-1069
+//   kind 1 RectPrismWithCylinder::intersect |ray| < eps   lbound <= start <= ubound   :1517-1588
+//   kind 2 the intersectShadow of both      |ray| < eps   lbound <  start <  ubound   :1093-1164, 1683-1754
+//   kind 3 RectPrismWithHoles (both)        isinf(1/ray)  no start test               :1893-1955, 2062-2118
+template <typename R>
+__device__ inline bool prismSlabs(const Vec<R>& lb, const Vec<R>& ub, const Vec<R>& ray, const Vec<R>& start, const int kind,
+                                  const float eps, float& tmin, float& tmax) {
+  const R rr[3] = {ray.x, ray.y, ray.z}, ss[3] = {start.x, start.y, start.z}, lo3[3] = {lb.x, lb.y, lb.z}, hi3[3] = {ub.x, ub.y, ub.z};
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    const R inv = R(1) / rr[a];
+    const bool parallel = (kind == 0 || kind == 3) ? (bool)isinf(inv) : (fabs(rr[a]) < (R)eps);
+    float lo, hi;
+    if (parallel) {
+      if (kind == 0 || kind == 1) { if (!(ss[a] >= lo3[a] && ss[a] <= hi3[a])) return false; }
+      else if (kind == 2) { if (!(ss[a] > lo3[a] && ss[a] < hi3[a])) return false; }
+      lo = FLT_MIN; hi = FLT_MAX;
+    } else if (rr[a] < R(0)) { lo = (float)((hi3[a] - ss[a]) * inv); hi = (float)((lo3[a] - ss[a]) * inv); }
+    else { lo = (float)((lo3[a] - ss[a]) * inv); hi = (float)((hi3[a] - ss[a]) * inv); }
+    if (a == 0) { tmin = lo; tmax = hi; }
+    else {
+      if (tmin > hi || lo > tmax) return false;
+      if (lo > tmin) tmin = lo;
+      if (hi < tmax) tmax = hi;
+    }
+  }
+  return true;
+}
+// Sphere::intersect (geometry.cpp:106-140) / Cylinder::intersect (242-295) on a hole
+template <typename R>
+__device__ inline bool holeIntersect(const HoleD<R>& h, const Vec<R>& ray, const Vec<R>& start, float& t, int& inside) {
+  if (h.type == G_SPHERE) {
+    const Vec<R> sc = start - h.c1;
+    float A = (float)dot(ray, ray);
+    float B = (float)(R(2) * dot(ray, sc));
+    float C = (float)(dot(sc, sc) - (R)((double)h.radius * (double)h.radius));
+    float disc = (float)((double)B * (double)B - (double)(4 * A * C));
+    if (disc < 0) return false;
+    float sq = sqrtf(disc);
+    float t0 = (-B + sq) / (2 * A), t1 = (-B - sq) / (2 * A);
+    if (t0 <= 0.001f && t1 <= 0.001f) { inside = 0; return false; }
+    else if (t0 <= 0.001f || t1 <= 0.001f) { t = fmaxf(t0, t1); inside = 1; return true; }
+    t = fminf(t0, t1); inside = 0; return true;
+  }
+  const float eps = 1e-3f;
+  const Vec<R> axis = h.axis;
+  Vec<R> ray_a_proj = ray - dot(ray, axis) * axis;
+  Vec<R> sc = start - h.c1;
+  Vec<R> constant = sc - dot(sc, axis) * axis;
+  float A = (float)dot(ray_a_proj, ray_a_proj);
+  float B = (float)(R(2) * dot(ray_a_proj, constant));
+  float C = (float)(dot(constant, constant) - (R)((double)h.radius * (double)h.radius));
+  float disc = (float)((double)B * (double)B - (double)(4 * A * C));
+  if (!(disc >= 0)) return false;
+  float sq = sqrtf(disc);
+  float t1_body = (-B + sq) / (2 * A), t2_body = (-B - sq) / (2 * A);
+  if (t1_body <= eps && t2_body <= eps) { inside = 0; return false; }
+  float tc; int ins;
+  if (t1_body <= eps || t2_body <= eps) { tc = t1_body; ins = 1; } else { tc = t2_body; ins = 0; }
+  Vec<R> pt = start + (R)tc * ray;
+  if (dot(axis, pt - h.c1) > R(0) && dot(axis, pt - h.c2) < R(0)) { t = tc; inside = ins; return true; }
+  return false;
+}
+// Cylinder::intersectCap (geometry.cpp:297-324): the two cap PLANES, no radius test
+template <typename R>
+__device__ inline bool holeIntersectCap(const HoleD<R>& h, const Vec<R>& ray, const Vec<R>& start, float& t, int& inside) {
+  const float eps = 1e-3f;
+  inside = 0;
+  float rdota = (float)dot(ray, h.axis);
+  if (rdota == 0.0f) return false;
+  float t1 = (float)((dot(h.c1, h.axis) - dot(start, h.axis)) / (R)rdota);
+  float t2 = (float)((dot(h.c2, h.axis) - dot(start, h.axis)) / (R)rdota);
+  if (t1 < eps && t2 < eps) return false;
+  else if (t1 < eps || t2 < eps) { inside = 1; t = fmaxf(t1, t2); return true; }
+  t = fminf(t1, t2); return true;
+}
+// Sphere::intersectMax (geometry.cpp:142-171) / Cylinder::intersectMax (326-366): the far root of a double intersection
+template <typename R>
+__device__ inline bool holeIntersectMax(const HoleD<R>& h, const Vec<R>& ray, const Vec<R>& start, float& t) {
+  if (h.type == G_SPHERE) {
+    const Vec<R> sc = start - h.c1;
+    float A = (float)dot(ray, ray);
+    float B = (float)(R(2) * dot(ray, sc));
+    float C = (float)(dot(sc, sc) - (R)((double)h.radius * (double)h.radius));
+    float disc = (float)((double)B * (double)B - (double)(4 * A * C));
+    if (disc < 0) return false;
+    float sq = sqrtf(disc);
+    float t0 = (-B + sq) / (2 * A), t1 = (-B - sq) / (2 * A);
+    if (t0 <= 0.001f || t1 <= 0.001f) return false;
+    t = fmaxf(t0, t1);
+    return true;
+  }
+  const float eps = 1e-3f;
+  const Vec<R> axis = h.axis;
+  Vec<R> ray_a_proj = ray - dot(ray, axis) * axis;
+  Vec<R> sc = start - h.c1;
+  Vec<R> constant = sc - dot(sc, axis) * axis;
+  float A = (float)dot(ray_a_proj, ray_a_proj);
+  float B = (float)(R(2) * dot(ray_a_proj, constant));
+  float C = (float)(dot(constant, constant) - (R)((double)h.radius * (double)h.radius));
+  float disc = (float)((double)B * (double)B - (double)(4 * A * C));
+  if (!(disc >= 0)) return false;
+  float sq = sqrtf(disc);
+  float t1_body = (-B + sq) / (2 * A), t2_body = (-B - sq) / (2 * A);
+  if (t1_body <= eps || t2_body <= eps) return false;
+  Vec<R> pt = start + (R)t2_body * ray;
+  if (dot(axis, pt - h.c1) > R(0) && dot(axis, pt - h.c2) < R(0)) { t = t1_body; return true; }
+  return false;
+}
+template <typename R>
+__device__ inline Vec<R> holeNorm(const HoleD<R>& h, const Vec<R>& point) {   // Sphere / Cylinder::getNorm
+  if (h.type == G_SPHERE) { Vec<R> n = point - h.c1; return n / norm(n); }
+  Vec<R> pc = point - h.c1;
+  return normalized(pc - dot(pc, h.axis) * h.axis);
+}
+template <typename R>
+__device__ inline bool vecApprox(const Vec<R>& a, const Vec<R>& b) {   // Eigen isApprox: |a-b|^2 <= 1e-24 min(|a|^2, |b|^2)
+  const Vec<R> d = a - b;
+  return dot(d, d) <= R(1e-24) * fmin(dot(a, a), dot(b, b));
+}
+// RectPrismWithHoles::getNorm (geometry.cpp:2204-2246): the hole's normal when the last intersect() recorded one, else the
+// face picked in object coordinates -- only three faces are recognised, anything else throws (`aborted`, quirk Q15)
+template <typename R>
+__device__ inline Vec<R> prismHolesNorm(const PrimD<R>& pr, const Vec<R>& point, const int last_hit, bool& aborted) {
+  if (last_hit >= 0) return holeNorm<R>(pr.holes[last_hit], point);
+  const Vec<R> pObj = mulPoint<R>(pr.objM, point);
+  const float eps = 1e-3f;
+  if (fabs(pObj.y - (R)(pr.height / 2)) <= (R)eps) return (pObj.y < R(0)) ? pr.n0 : -pr.n0;     // -+ (F-E)x(H-E)^ ; n0 = -(F-E)x(H-E)^
+  if (fabs(pObj.x - (R)(pr.length / 2)) <= (R)eps) return (pObj.x < R(0)) ? -pr.n1 : pr.n1;
+  if (fabs(pObj.z - (R)(pr.width / 2)) <= (R)eps) return (pObj.z < R(0)) ? -pr.n2 : pr.n2;
+  aborted = true;
+  return mk<R>(R(0), R(0), R(0));
+}
+// intersect() of the three classes.  `sel`: 0 keeps the prism's colour, 3 + i takes hole i's (and, for RectPrismWithHoles,
+// records lastHit = i for getNorm).  The reference WRITES the hole's colour into the prism for good (geometry.cpp:1650,
+// 2005, 2044), which makes its picture depend on pixel order; here the colour belongs to the hit (pinned, DESIGN Q19).
+template <typename R>
+__device__ __noinline__ bool boxIntersect(const PrimD<R>& pr, const Vec<R>& lb, const Vec<R>& ub, const Vec<R>& ray, const Vec<R>& start,
+                                          float& t, int& inside, int& sel) {
+  float tmin, tmax;
+  inside = 0; sel = 0;
+  if (pr.type == 8) {                                                    // RectPrism :990-1085
+    const float eps = 1e-6f;
+    if (!prismSlabs<R>(lb, ub, ray, start, 0, eps, tmin, tmax)) return false;
+    const R nr = norm(ray);
+    if (tmin < eps && tmax > eps) { t = (float)(((R)tmax * nr) / nr); inside = 1; return true; }
+    if (tmax <= eps) return false;
+    t = (float)(((R)tmin * nr) / nr);
+    return true;
+  }
+  const float eps = 1e-4f;
+  if (pr.type == 9) {                                                    // RectPrismWithCylinder :1509-1657
+    if (!prismSlabs<R>(lb, ub, ray, start, 1, eps, tmin, tmax)) return false;
+    if (tmax <= eps) return false;
+    if (tmin < eps && tmax > eps) inside = 1;
+    t = tmin;                                                            // (sic) :1600
+    float tcyl = FLT_MAX;
+    int inside_cyl = 0, hit_cyl = -1;
+    bool hit = false, cap_hit = false;                                   // uninitialised in the reference: pinned false (Q18)
+    for (int i = 0; i < pr.n_holes; i++) {
+      float t_tmp; int in_tmp = 0;
+      if (holeIntersect<R>(pr.holes[i], ray, start, t_tmp, in_tmp)) { hit = true; if (t_tmp <= tcyl) { hit_cyl = i; inside_cyl = in_tmp; tcyl = t_tmp; } }
+      if (holeIntersectCap<R>(pr.holes[i], ray, start, t_tmp, in_tmp)) { hit = true; if (t_tmp <= tcyl) { hit_cyl = i; cap_hit = true; inside_cyl = in_tmp; tcyl = t_tmp; } }
+    }
+    if (hit && tcyl <= t) {
+      if (cap_hit) return false;
+      inside = inside_cyl; t = tcyl; sel = 3 + hit_cyl;
+    }
+    return true;
+  }
+  // RectPrismWithHoles :1883-2053
+  if (!prismSlabs<R>(lb, ub, ray, start, 3, eps, tmin, tmax)) return false;
+  if (tmin < eps && tmax > eps) { t = tmax; inside = 1; }
+  else { if (tmax <= eps) return false; t = tmin; }
+  float tmin_tmp = FLT_MAX, t_tmp;
+  int last = -1, in_tmp;
+  for (int i = 0; i < pr.n_holes; i++) {
+    if (inside) { if (holeIntersect<R>(pr.holes[i], ray, start, t_tmp, in_tmp) && t_tmp <= tmin_tmp) { tmin_tmp = t_tmp; last = i; } }
+    else if (holeIntersectMax<R>(pr.holes[i], ray, start, t_tmp) && t_tmp < tmin_tmp) { tmin_tmp = t_tmp; last = i; }
+  }
+  if (last >= 0) {
+    // (sic) `ray + t * start`; getNorm answers with the HOLE's normal because lastHit is already set
+    const Vec<R> checknorm = holeNorm<R>(pr.holes[last], ray + (R)t * start);
+    const Vec<R> shapenorm = holeNorm<R>(pr.holes[last], ray + (R)tmin_tmp * start);
+    if (vecApprox<R>(checknorm, shapenorm) || vecApprox<R>(checknorm, -shapenorm)) return false;
+    if (inside && tmin_tmp > t) return true;
+    sel = 3 + last; t = tmin_tmp;
+  }
+  return true;
+}
+// intersectShadow() of the three classes; `aborted`: RectPrismWithHoles::getNorm threw
+template <typename R>
+__device__ __noinline__ bool boxShadow(const PrimD<R>& pr, const Vec<R>& lb, const Vec<R>& ub, const Vec<R>& ray, const Vec<R>& start,
+                                       const float t_max, bool& aborted) {
+  float tmin, tmax;
+  if (pr.type == 8) {                                                    // :1087-1180
+    const float eps = 1e-6f;
+    if (!prismSlabs<R>(lb, ub, ray, start, 2, eps, tmin, tmax)) return false;
+    if (tmin < eps && tmax > eps) return t_max > tmax;
+    if (tmax <= eps) return false;
+    return t_max > tmin;
+  }
+  const float eps = 1e-4f;
+  if (pr.type == 9) {                                                    // :1659-1794
+    if (!prismSlabs<R>(lb, ub, ray, start, 2, eps, tmin, tmax)) return false;
+    if (tmax <= eps) return false;
+    if (tmin < eps && tmax > eps) { if (tmax >= t_max) return false; }
+    const float t = tmin;                                                // (sic) :1744; tmin is never compared with t_max
+    float tcyl = FLT_MAX;
+    bool hit = false, cap_hit = false;                                   // uninitialised in the reference: pinned false (Q18)
+    for (int i = 0; i < pr.n_holes; i++) {
+      float t_tmp = FLT_MIN; int in_tmp = 0;
+      if (holeIntersect<R>(pr.holes[i], ray, start, t_tmp, in_tmp) && t_tmp > eps && t_tmp < t_max) { hit = true; if (t_tmp <= tcyl) tcyl = t_tmp; }
+      if (holeIntersectCap<R>(pr.holes[i], ray, start, t_tmp, in_tmp) && t_tmp > eps && t_tmp < t_max) { hit = true; if (t_tmp <= tcyl) { cap_hit = true; tcyl = t_tmp; } }
+    }
+    if (hit && tcyl <= t && tcyl > eps && tcyl < t_max && cap_hit) return false;
+    return true;
+  }
+  // RectPrismWithHoles :2055-2202
+  bool inside = false;
+  float t;
+  if (!prismSlabs<R>(lb, ub, ray, start, 3, eps, tmin, tmax)) return false;
+  if (tmin < eps && tmax > eps) { if (tmax >= t_max) return false; t = tmax; inside = true; }
+  else { if (tmax <= eps || tmin >= t_max) return false; t = tmin; }
+  float tmin_tmp = FLT_MAX, t_tmp;
+  int last = -1, in_tmp;
+  for (int i = 0; i < pr.n_holes; i++) {
+    if (inside) { if (holeIntersect<R>(pr.holes[i], ray, start, t_tmp, in_tmp) && t_tmp <= tmin_tmp) { tmin_tmp = t_tmp; last = i; } }
+    else if (holeIntersectMax<R>(pr.holes[i], ray, start, t_tmp) && t_tmp < tmin_tmp) { tmin_tmp = t_tmp; last = i; }
+  }
+  if (last >= 0) {
+    // lastHit stays -1 in intersectShadow, so getNorm picks a prism face in object coordinates -- or throws
+    const Vec<R> checknorm = prismHolesNorm<R>(pr, ray + (R)t * start, -1, aborted);
+    if (aborted) return false;
+    const Vec<R> shapenorm = holeNorm<R>(pr.holes[last], ray + (R)tmin_tmp * start);
+    if (vecApprox<R>(checknorm, shapenorm) || vecApprox<R>(checknorm, -shapenorm)) return false;
+  }
+  return true;
+}
+
 struct HitRec {
   float t;
   int geom;
@@ -168,7 +419,9 @@ __device__ inline bool geomIntersect(const Params<R>& P, const Geom<R>& g, int g
                                      const Vec<R>& ray, const Vec<R>& start, float& t_hit, int& inside, int& sel) {
   bool ok = false;
   inside = 0; sel = 0;
-    if (type == G_RECT || type == G_CHECKER) {
+    if ((F & FT_BOX) && type == G_BOX) {
+      return boxIntersect<R>(P.prims[g.owner], shiftPoint<R, F>(mv, 0, g.vel, g.p0), shiftPoint<R, F>(mv, 0, g.vel, g.p1), ray, start, t_hit, inside, sel);
+    } else if (type == G_RECT || type == G_CHECKER) {
       Vec<R> A = shiftPoint<R, F>(mv, g.flags, g.vel, g.p0);
       if (type == G_CHECKER) {  // exact-zero edge path pinned to "no hit" (quirk Q17)
         if (dot(g.p1, ray) == R(0)) return false;
@@ -435,9 +688,12 @@ __device__ inline void closestHit(const Params<R>& P, const float4* __restrict__
 // `ray` is normalised, `start` already offset by 1e-3 along it.
 template <typename R, int F>
 __device__ inline bool geomShadow(const Params<R>& P, const Geom<R>& g, int gi, const int type, const Moved<R>& mv,
-                                  const Vec<R>& ray, const Vec<R>& start, const float t_max, float& t_occ) {
+                                  const Vec<R>& ray, const Vec<R>& start, const float t_max, float& t_occ, bool& aborted) {
     t_occ = 0.0f;   // on success: a ray parameter at which the ray certainly touches the geom
-    if (type == G_RECT || type == G_CHECKER) {
+    if ((F & FT_BOX) && type == G_BOX) {
+      // t_occ stays 0: these classes report occlusion without a touch point, so the reference gather is always replayed
+      return boxShadow<R>(P.prims[g.owner], shiftPoint<R, F>(mv, 0, g.vel, g.p0), shiftPoint<R, F>(mv, 0, g.vel, g.p1), ray, start, t_max, aborted);
+    } else if (type == G_RECT || type == G_CHECKER) {
       Vec<R> A = shiftPoint<R, F>(mv, g.flags, g.vel, g.p0);
       // Checkerboard inherits Rectangle::intersectShadow (eps 1e-4); CheckerboardWithHole
       // has its own with eps 1e-3 (geometry.cpp:2446-2498)
@@ -518,7 +774,7 @@ __device__ inline bool geomShadow(const Params<R>& P, const Geom<R>& g, int gi, 
 template <typename R, int F, bool COUNT>
 __device__ inline bool anyHit(const Params<R>& P, const float4* __restrict__ gb, const Moved<R>& mv, const Vec<R>& gather_ray,
                               const Vec<R>& gather_start, const Vec<R>& ray, const Vec<R>& start, float t_max, int skip_owner,
-                              Counts& cnt) {
+                              Counts& cnt, bool& aborted) {
   const Vec<R> inv_ray = mk<R>(R(1) / gather_ray.x, R(1) / gather_ray.y, R(1) / gather_ray.z);   // sray.cwiseInverse() :813
   if ((!(F & FT_REFBLUR) || mv.val == 0.0f) && !DRT_FORCE_TREE) {
     const float ix = 1.0f / (float)ray.x, iy = 1.0f / (float)ray.y, iz = 1.0f / (float)ray.z;
@@ -541,7 +797,7 @@ __device__ inline bool anyHit(const Params<R>& P, const float4* __restrict__ gb,
         if (type == G_HOLE || g.owner == skip_owner) continue;   // an area light never shadows itself (832-837)
         if (COUNT) cnt.geom_tests[type]++;
         float t_occ;
-        if (!geomShadow<R, F>(P, g, gi, type, mv, ray, start, t_max, t_occ)) continue;
+        if (!geomShadow<R, F>(P, g, gi, type, mv, ray, start, t_max, t_occ, aborted)) { if ((F & FT_BOX) && aborted) return false; continue; }
         if ((F & FT_VEL) && mv.velocity_mode) return true;          // time-displaced geometry: no reference tree to consult
         // The occluder touches the ray at distance t_occ from the test origin.  If that point
         // lies ahead of the gather origin it is inside the geom's leaf box and every ancestor
@@ -575,7 +831,8 @@ __device__ inline bool anyHit(const Params<R>& P, const float4* __restrict__ gb,
       if (g.owner == skip_owner) continue;
       if (COUNT) cnt.geom_tests[type]++;
       float t_occ;
-      if (geomShadow<R, F>(P, g, gi, type, mv, ray, start, t_max, t_occ)) return true;
+      if (geomShadow<R, F>(P, g, gi, type, mv, ray, start, t_max, t_occ, aborted)) return true;
+      if ((F & FT_BOX) && aborted) return false;
     }
   }
   return false;
@@ -677,11 +934,6 @@ __device__ inline Vec<R> rectSample(const Vec<R>& A, const Vec<R>& B, const Vec<
   return A + (R)x * (B - A) + (R)y * (D - A);
 }
 
-template <typename R>
-__device__ inline Vec<R> mulPoint(const R* m, const Vec<R>& p) {  // (M*(p,1)).head<3>(), 4-term sums as (a+b)+(c+d)
-  return mk<R>((m[0] * p.x + m[1] * p.y) + (m[2] * p.z + m[3]), (m[4] * p.x + m[5] * p.y) + (m[6] * p.z + m[7]),
-               (m[8] * p.x + m[9] * p.y) + (m[10] * p.z + m[11]));
-}
 
 template <typename R>
 __device__ inline Vec<R> eyeRay(const Params<R>& P, int i, int j) {  // getPerspEyeRay helpers.h:320-324
@@ -885,7 +1137,17 @@ __device__ void shadeA(const Params<R>& P, const Task<R>& T, const HitRec& h, Ta
     } else if (pr.type == 1 || pr.type == 7) {                          // Cylinder geometry.cpp:419-425
       Vec<R> pc = isectP - shiftPoint<R, F>(mv, 0, pr.vel, pr.pA);
       normal = normalized(pc - dot(pc, pr.pG) * pr.pG);
-    } else if (pr.type == 4) {                                          // RectPrismV2 geometry.cpp:863-920
+    } else if ((F & FT_BOX) && pr.type == 9) {                          // RectPrismWithCylinder geometry.cpp:1796-1821 (lastHit is -1 by now)
+      const float eps = 1e-3f;
+      const Vec<R> pa = isectP - shiftPoint<R, F>(mv, 0, pr.vel, pr.pA);
+      if (dot(pa, pr.n0) <= (R)eps) normal = pr.n0;
+      else if (dot(pa, pr.n1) <= (R)eps) normal = pr.n1;
+      else if (dot(pa, pr.n2) <= (R)eps) normal = pr.n2;
+      else { aborted = true; break; }                                   // throws :1819-1820
+    } else if ((F & FT_BOX) && pr.type == 10) {                         // RectPrismWithHoles geometry.cpp:2204-2246
+      normal = prismHolesNorm<R>(pr, isectP, h.checker_sel >= 3 ? h.checker_sel - 3 : -1, aborted);
+      if (aborted) break;
+    } else if (pr.type == 4 || ((F & FT_BOX) && pr.type == 8)) {        // RectPrismV2 geometry.cpp:863-920, RectPrism 1279-1379
       const float eps = 1e-3f;
       Vec<R> dA = normalized(isectP - shiftPoint<R, F>(mv, 0, pr.vel, pr.pA));
       Vec<R> dG = normalized(isectP - shiftPoint<R, F>(mv, 0, pr.vel, pr.pG));
@@ -913,6 +1175,10 @@ __device__ void shadeA(const Params<R>& P, const Task<R>& T, const HitRec& h, Ta
     float shape_color[3];
     if (h.checker_sel == 1) { shape_color[0] = pr.color1[0]; shape_color[1] = pr.color1[1]; shape_color[2] = pr.color1[2]; }
     else if (h.checker_sel == 2) { shape_color[0] = pr.color2[0]; shape_color[1] = pr.color2[1]; shape_color[2] = pr.color2[2]; }
+    else if ((F & FT_BOX) && h.checker_sel >= 3) {                      // the wall of a prism's hole: the hole's own colour
+      const HoleD<R>& hd = pr.holes[h.checker_sel - 3];
+      shape_color[0] = hd.color[0]; shape_color[1] = hd.color[1]; shape_color[2] = hd.color[2];
+    }
     else { shape_color[0] = pr.color[0]; shape_color[1] = pr.color[1]; shape_color[2] = pr.color[2]; }
 
     // ---- reflection / refraction children (:574-769) ---------------------------
@@ -1060,7 +1326,9 @@ __device__ void shadowPair(const Params<R>& P, const float4* __restrict__ gb, co
   if (COUNT) cnt.shadow_rays++;
   // candidates are gathered along the UNNORMALISED sray from isectP + sray*1e-3 (:814),
   // occlusion is tested along the normalised one from isectP + s^*1e-3 (:838)
-  bool occluded = anyHit<R, F, COUNT>(P, gb, mv, sray, isectP + sray * R(1e-3), sdir, isectP + sdir * R(1e-3), t_max, L.prim_index, cnt);
+  bool threw = false;
+  bool occluded = anyHit<R, F, COUNT>(P, gb, mv, sray, isectP + sray * R(1e-3), sdir, isectP + sdir * R(1e-3), t_max, L.prim_index, cnt, threw);
+  if ((F & FT_BOX) && threw) { out.state[oi] = 2; return; }             // RectPrismWithHoles::getNorm threw inside intersectShadow
   if ((F & FT_MESH) && !occluded && P.n_mesh_tris > 0)
     occluded = meshTraverse<R, F, COUNT, false>(P, sdir, isectP + sdir * R(1e-3), t_max, nullptr, sray, isectP + sray * R(1e-3), cnt);
   out.state[oi] = occluded ? 0 : 1;
@@ -1087,6 +1355,13 @@ __device__ void shadeB(const Params<R>& P, ShadeState<R>& S, const PairOut<R>& r
           u = (float)(norm(cross(S.isectP - uA, pr.uv_ad)) / pr.uv_den_u);
           v = (float)(norm(cross(S.isectP - uD, pr.uv_dc)) / pr.uv_den_v);
           type = 1;
+        } else if ((F & FT_BOX) && pr.type >= 8 && pr.type <= 10) {     // RectPrism::getUV geometry.cpp:1440-1461
+          const Vec<R> uA = shiftPoint<R, F>(S.mv, 0, pr.vel, pr.uvA), uD = shiftPoint<R, F>(S.mv, 0, pr.vel, pr.uvD);
+          if (fabs(dot(cross(pr.uv_ad, pr.uv_dc), S.isectP)) <= R(1e-5)) {
+            u = (float)(norm(cross(S.isectP - uA, pr.uv_ad)) / pr.uv_den_u);
+            v = (float)(norm(cross(S.isectP - uD, pr.uv_dc)) / pr.uv_den_v);
+            type = 1;
+          } else type = 0;
         } else if (pr.type == 6) {                                      // CheckerboardWithHole::getUV geometry.cpp:2500-2561
           Vec<R> V_hit = S.isectP - pr.rA;
           float check1 = (float)dot(pr.re1, V_hit), check2 = (float)dot(pr.re2, V_hit);
@@ -1328,7 +1603,7 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
 
   Counts cnt;
   if (COUNT) { cnt.samples = 0; cnt.rays = 0; cnt.shadow_rays = 0; cnt.shade_evals = 0; cnt.noise_evals = 0; cnt.node_tests = 0;
-               for (int i = 0; i < 6; i++) cnt.geom_tests[i] = 0; }
+               for (int i = 0; i < 7; i++) cnt.geom_tests[i] = 0; }
 
   // s_state: 0 = no batch, 1 = primary trees in flight, 2 = blur re-traces in flight, 3 = all batches done
   if (tid == 0) { s_count = 0; s_nhits = 0; s_state = 0; s_nvalid = 0; s_idx0 = 0; s_unit_next = 0; s_unit_end = 0; }
@@ -1607,7 +1882,7 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
     atomicAdd(&P.counts->samples, cnt.samples); atomicAdd(&P.counts->rays, cnt.rays);
     atomicAdd(&P.counts->shadow_rays, cnt.shadow_rays); atomicAdd(&P.counts->shade_evals, cnt.shade_evals);
     atomicAdd(&P.counts->node_tests, cnt.node_tests);
-    for (int i = 0; i < 6; i++) if (cnt.geom_tests[i]) atomicAdd(&P.counts->geom_tests[i], cnt.geom_tests[i]);
+    for (int i = 0; i < 7; i++) if (cnt.geom_tests[i]) atomicAdd(&P.counts->geom_tests[i], cnt.geom_tests[i]);
   }
 }
 

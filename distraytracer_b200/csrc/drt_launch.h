@@ -43,7 +43,8 @@ enum WaveFeat {
   FT_GLASS = 8,     // some primitive is glass (refraction children)
   FT_TEX = 16,      // some primitive is textured
   FT_BIG = 32,      // more geoms than the shared-memory slab table holds (DRT_SMEM_GEOMS)
-  FT_ALL = 63
+  FT_BOX = 64,      // slab-box prisms (RectPrism / RectPrismWithCylinder / RectPrismWithHoles) are present
+  FT_ALL = 127
 };
 
 // the instantiated masks (drt_launch_impl.cuh must hold one DRT_WAVE_CASE per entry); FT_ALL last

@@ -154,6 +154,37 @@ class RectPrismV2 : public GeoPrimitive {
   int drtType() const override { return DRT_PRIM_RECTPRISMV2; }
 };
 
+// The slab-box prisms (geometry.h:159-217, geometry.cpp:950-2246): the box tested is the WORLD axis-aligned bounding box
+// of the eight corners.
+class RectPrism : public GeoPrimitive {
+ public:
+  RectPrism() {}
+  RectPrism(VEC3 a, VEC3 b, VEC3 c, VEC3 d, VEC3 e, VEC3 f, VEC3 g, VEC3 h, VEC3 col, std::string material = "",
+            bool in_motion = false, int texframe = -1, std::string shader = "lambert") {
+    A = a; B = b; C = c; D = d; E = e; F = f; G = g; H = h;
+    length = (float)(b - a).norm(); width = (float)(d - a).norm(); height = (float)(e - a).norm(); color = col;
+    reflect_params.material = material; dims = 3; motion = in_motion; model = shader;
+    center = (A + B + C + D + E + F + G + H) / 8; name = "rectprism"; if (texframe >= 0) tex_frame = texframe;
+  }
+  int drtType() const override { return DRT_PRIM_RECTPRISM; }
+};
+class RectPrismWithCylinder : public RectPrism {
+ public:
+  RectPrismWithCylinder(VEC3 a, VEC3 b, VEC3 c, VEC3 d, VEC3 e, VEC3 f, VEC3 g, VEC3 h, VEC3 col, std::string material = "",
+                        bool in_motion = false, int texframe = -1, std::string shader = "lambert")
+      : RectPrism(a, b, c, d, e, f, g, h, col, material, in_motion, texframe, shader) { name = "RectPrismWithCylinder"; }
+  int drtType() const override { return DRT_PRIM_RECTPRISM_CYL; }
+  std::vector<std::shared_ptr<Cylinder>> holes;
+};
+class RectPrismWithHoles : public RectPrism {
+ public:
+  RectPrismWithHoles(VEC3 a, VEC3 b, VEC3 c, VEC3 d, VEC3 e, VEC3 f, VEC3 g, VEC3 h, VEC3 col, std::string material = "",
+                     bool in_motion = false, int texframe = -1, std::string shader = "lambert")
+      : RectPrism(a, b, c, d, e, f, g, h, col, material, in_motion, texframe, shader) {}
+  int drtType() const override { return DRT_PRIM_RECTPRISM_HOLES; }
+  std::vector<std::shared_ptr<GeoPrimitive>> holes;   // Sphere or Cylinder: the classes with an intersectMax (geometry.h:37)
+};
+
 class Checkerboard : public Rectangle {
  public:
   Checkerboard(VEC3 a, VEC3 b, VEC3 c, VEC3 d, VEC3 col1, VEC3 col2, float S_square, std::string material = "",
@@ -311,6 +342,14 @@ inline drt_prim flattenPrim(const GeoPrimitive& s) {
     put3(p.hole[0], c->hole->A); put3(p.hole[1], c->hole->B); put3(p.hole[2], c->hole->C); put3(p.hole[3], c->hole->D);
   }
   if (auto* c = dynamic_cast<const CheckerCylinder*>(&s)) { p.S = c->S; p.borderwidth = c->borderwidth; }
+  auto put_hole = [&](const GeoPrimitive& h) {
+    if (p.n_holes >= DRT_MAX_HOLES) throw std::runtime_error("more holes than DRT_MAX_HOLES");
+    drt_hole& o = p.holes[p.n_holes++];
+    o.type = h.drtType(); o.radius = h.radius; put3(o.color, h.color);
+    if (o.type == DRT_PRIM_SPHERE) put3(o.c1, h.center); else { put3(o.c1, h.c1); put3(o.c2, h.c2); }
+  };
+  if (auto* c = dynamic_cast<const RectPrismWithCylinder*>(&s)) for (auto& h : c->holes) put_hole(*h);
+  if (auto* c = dynamic_cast<const RectPrismWithHoles*>(&s)) for (auto& h : c->holes) put_hole(*h);
   return p;
 }
 

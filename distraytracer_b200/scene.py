@@ -69,8 +69,10 @@ class Scene:
 
     @staticmethod
     def from_npz_dict(z):
-        assert int(z["abi_version"]) == abi.ABI_VERSION, "fixture written for another ABI version"
-        prims = _bytes_to_structs(z["prims"], abi.Prim)
+        version = int(z["abi_version"])
+        assert version in (1, abi.ABI_VERSION), "fixture written for another ABI version"
+        # version 1 records are a prefix of version 2's (the holes of the slab-box prisms were appended)
+        prims = _bytes_to_structs(z["prims"], abi.Prim, abi.PRIM_BYTES_V1 if version == 1 else None)
         lights = _bytes_to_structs(z["lights"], abi.Light)
         texs = [z[f"tex{i}"] for i in range(int(z["n_textures"]))]
         return Scene(prims, lights, texs)
@@ -83,11 +85,13 @@ def _structs_to_bytes(items, typ):
     return np.frombuffer(buf.getvalue(), dtype=np.uint8).copy()
 
 
-def _bytes_to_structs(arr, typ):
+def _bytes_to_structs(arr, typ, record_bytes=None):
     raw = np.asarray(arr, dtype=np.uint8).tobytes()
     sz = C.sizeof(typ)
-    assert len(raw) % sz == 0
-    return [typ.from_buffer_copy(raw[i * sz:(i + 1) * sz]) for i in range(len(raw) // sz)]
+    rec = record_bytes or sz
+    assert len(raw) % rec == 0 and rec <= sz
+    pad = bytes(sz - rec)
+    return [typ.from_buffer_copy(raw[i * rec:(i + 1) * rec] + pad) for i in range(len(raw) // rec)]
 
 
 def settings_to_bytes(s):

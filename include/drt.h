@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define DRT_ABI_VERSION 1
+#define DRT_ABI_VERSION 2
 
 typedef enum drt_status {
   DRT_OK = 0,
@@ -56,11 +56,25 @@ typedef enum drt_prim_type {
   DRT_PRIM_CHECKERBOARD = 5,      /* geometry.h:220  Checkerboard              */
   DRT_PRIM_CHECKERBOARD_HOLE = 6, /* geometry.h:232  CheckerboardWithHole      */
   DRT_PRIM_CHECKER_CYLINDER = 7,  /* geometry.h:248  CheckerCylinder           */
-  DRT_PRIM_TYPE_COUNT = 8
-  /* RectPrism / RectPrismWithCylinder / RectPrismWithHoles (geometry.h:159-217)
-   * are not instantiated by any scene reachable from the hot path's named
-   * configurations and are rejected with DRT_ERR_UNSUPPORTED. */
+  /* The slab-box prisms (geometry.cpp:950-2246).  Their box is the WORLD axis-aligned bounding box of
+   * the eight corners (getBounds overwrites the object-space bounds, geometry.cpp:987-988), so only
+   * axis-aligned prisms look like prisms -- reproduced as is. */
+  DRT_PRIM_RECTPRISM = 8,         /* geometry.h:159  RectPrism                 */
+  DRT_PRIM_RECTPRISM_CYL = 9,     /* geometry.h:182  RectPrismWithCylinder: drt_prim.holes are Cylinders   */
+  DRT_PRIM_RECTPRISM_HOLES = 10,  /* geometry.h:200  RectPrismWithHoles: holes are Spheres / Cylinders    */
+  DRT_PRIM_TYPE_COUNT = 11
 } drt_prim_type;
+
+#define DRT_MAX_HOLES 4
+/* One entry of RectPrismWithCylinder::holes / RectPrismWithHoles::holes (geometry.h:195, 216). */
+typedef struct drt_hole {
+  int32_t type;      /* DRT_PRIM_SPHERE or DRT_PRIM_CYLINDER */
+  int32_t pad_;
+  double c1[3];      /* cylinder end point, or the sphere's centre */
+  double c2[3];      /* cylinder end point */
+  double radius;
+  double color[3];   /* the hole's own colour (a hit on the hole's wall is shaded with it) */
+} drt_hole;
 
 /* GeoPrimitive::name (geometry.h:46).  Only these values change behaviour:
  * "spherelight"/"rectanglelight" select the emissive formula
@@ -132,6 +146,10 @@ typedef struct drt_prim {
    * SURVEY.md 8(f)1; the reference's own "rectangle" translation is selected by
    * drt_settings.blur_mode instead and does not read this field. */
   double velocity[3];
+  /* RectPrismWithCylinder / RectPrismWithHoles only (ABI version 2) */
+  int32_t n_holes;
+  int32_t pad_;
+  drt_hole holes[DRT_MAX_HOLES];
 } drt_prim;
 
 typedef enum drt_light_type {

@@ -233,6 +233,7 @@ int drtref_build_scene(const char* name_c, float frame) {
     else if (n == "rectprism") buildRectPrismV2Test(frame);
     else if (n == "checkercylinder") buildSceneCylinder(frame);
     else if (n == "hw4") buildSceneHW4(frame);
+    else if (n == "prismcyl") BuildScenePrismCylinder(frame);
     else if (n == "chkpt2") { if (!g_mocap_loaded) return fail(-1, "mocap not loaded"); buildSceneChkpt2(frame); }
     else if (n == "boundary") { if (!g_mocap_loaded) return fail(-1, "mocap not loaded"); buildSceneBoundary(frame); }
     else if (n == "scene") { if (!g_mocap_loaded) return fail(-1, "mocap not loaded"); buildScene(frame); }
@@ -315,6 +316,27 @@ int drtref_export_scene(drt_prim* prims, drt_light* out_lights, drt_texture* tex
       p.type = DRT_PRIM_RECTPRISMV2;
       v3(p.A, s->A); v3(p.B, s->B); v3(p.C, s->C); v3(p.D, s->D);
       v3(p.E, s->E); v3(p.F, s->F); v3(p.G, s->G); v3(p.H, s->H);
+    } else if (dynamic_cast<RectPrism*>(s)) {
+      // the slab-box prisms; the derived classes first
+      v3(p.A, s->A); v3(p.B, s->B); v3(p.C, s->C); v3(p.D, s->D);
+      v3(p.E, s->E); v3(p.F, s->F); v3(p.G, s->G); v3(p.H, s->H);
+      auto put_hole = [&](GeoPrimitive* h) -> int {
+        if (p.n_holes >= DRT_MAX_HOLES) return fail(-2, "more holes than DRT_MAX_HOLES");
+        drt_hole& o = p.holes[p.n_holes];
+        if (dynamic_cast<Cylinder*>(h)) { o.type = DRT_PRIM_CYLINDER; v3(o.c1, h->c1); v3(o.c2, h->c2); }
+        else if (dynamic_cast<Sphere*>(h)) { o.type = DRT_PRIM_SPHERE; v3(o.c1, h->center); }
+        else return fail(-2, "hole of a class without intersectMax");
+        o.radius = h->radius; v3(o.color, h->color);
+        p.n_holes++;
+        return 0;
+      };
+      if (auto* c = dynamic_cast<RectPrismWithCylinder*>(s)) {
+        p.type = DRT_PRIM_RECTPRISM_CYL;
+        for (auto& h : c->holes) { int rc = put_hole(h.get()); if (rc) return rc; }
+      } else if (auto* c = dynamic_cast<RectPrismWithHoles*>(s)) {
+        p.type = DRT_PRIM_RECTPRISM_HOLES;
+        for (auto& h : c->holes) { int rc = put_hole(h.get()); if (rc) return rc; }
+      } else p.type = DRT_PRIM_RECTPRISM;
     } else {
       return fail(-2, "unsupported primitive class at index " + std::to_string(i) + " (" + s->name + ")");
     }
@@ -399,6 +421,28 @@ int drtref_load_scene(const drt_scene_desc* d) {
         auto c = make_shared<CheckerboardWithHole>(V3(p.A), V3(p.B), V3(p.C), V3(p.D), V3(p.color1), V3(p.color2),
                                                    (float)p.S, hole, mat, mo, model);
         c->borderwidth = p.borderwidth; s = c; break; }
+      case DRT_PRIM_RECTPRISM:
+        s = make_shared<RectPrism>(V3(p.A), V3(p.B), V3(p.C), V3(p.D), V3(p.E), V3(p.F), V3(p.G), V3(p.H),
+                                   V3(p.color), mat, mo, p.tex_frame, model);
+        break;
+      case DRT_PRIM_RECTPRISM_CYL: {
+        auto c = make_shared<RectPrismWithCylinder>(V3(p.A), V3(p.B), V3(p.C), V3(p.D), V3(p.E), V3(p.F), V3(p.G), V3(p.H),
+                                                    V3(p.color), mat, mo, p.tex_frame, model);
+        for (int k = 0; k < p.n_holes; k++) {
+          if (p.holes[k].type != DRT_PRIM_CYLINDER) return fail(-2, "RectPrismWithCylinder holes are cylinders");
+          c->holes.push_back(make_shared<Cylinder>(V3(p.holes[k].c1), V3(p.holes[k].c2), (float)p.holes[k].radius, V3(p.holes[k].color)));
+        }
+        s = c; break; }
+      case DRT_PRIM_RECTPRISM_HOLES: {
+        auto c = make_shared<RectPrismWithHoles>(V3(p.A), V3(p.B), V3(p.C), V3(p.D), V3(p.E), V3(p.F), V3(p.G), V3(p.H),
+                                                 V3(p.color), mat, mo, p.tex_frame, model);
+        for (int k = 0; k < p.n_holes; k++) {
+          const drt_hole& h = p.holes[k];
+          if (h.type == DRT_PRIM_CYLINDER) c->holes.push_back(make_shared<Cylinder>(V3(h.c1), V3(h.c2), (float)h.radius, V3(h.color)));
+          else if (h.type == DRT_PRIM_SPHERE) c->holes.push_back(make_shared<Sphere>(V3(h.c1), (float)h.radius, V3(h.color)));
+          else return fail(-2, "hole of a class without intersectMax");
+        }
+        s = c; break; }
       default: return fail(-2, "unsupported primitive type");
     }
     std::string keep = s->name;

@@ -13,7 +13,15 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 GOLDEN_CASES = [
     "hw4", "reflectance", "dof", "spherelight", "spheres_blur", "checkertexture", "checkertexture_nogloss",
     "texture", "textureog", "window", "staircase", "rectprism", "checkercylinder", "chkpt2_mocap", "boundary_mocap",
+    # the slab-box prism classes: the reference's own `prismcyl` scene, and scenes that put RectPrism /
+    # RectPrismWithCylinder / RectPrismWithHoles in front of its constructors (tests/golden/make_golden.py)
+    "prismcyl", "prism_box", "prism_cyl", "prism_cyl_side", "prism_holes", "prism_holes_back",
 ]
+# In the reference a hit on the wall of a prism's hole WRITES the hole's colour into the prism for good (geometry.cpp:1650,
+# 2005, 2044): every later ray sees it, so its picture depends on the order the pixels are rendered in.  The oracle
+# reproduces that to the bit under DRT_ORACLE_Q19=persist (sequential mode only); by default -- and in the CUDA path -- the
+# colour belongs to the hit that set it.
+Q19_CASES = {"prism_cyl", "prism_cyl_side", "prism_holes", "prism_holes_back"}
 
 
 def pytest_configure(config):

@@ -338,16 +338,22 @@ def test_update_lights_equals_a_fresh_scene(oracle_lib):
 @pytest.mark.gpu
 def test_out_of_scope_inputs_are_rejected_not_rendered(oracle_lib):
     """What the hot path does not cover fails loudly with DRT_ERR_UNSUPPORTED (never a silent approximation): primitive
-    classes outside drt_prim_type (RectPrism / RectPrismWithCylinder / RectPrismWithHoles), a textured
+    classes outside drt_prim_type, holes of a class the reference has no cap / far-root test for, a textured
     sphere (GeoPrimitive::getUV has no body, geometry.h:36), recursion deeper than 32, more glossy lobes than the ray
     pool is sized for."""
     from distraytracer_b200 import abi, runtime
     from distraytracer_b200.scene import Scene
     scene, settings, _ = load_case("checkertexture")
     prims = [abi.copy_struct(p) for p in scene.prims]
-    prims[0].type = abi.PRIM_TYPE_COUNT                     # e.g. a RectPrismWithCylinder
+    prims[0].type = abi.PRIM_TYPE_COUNT                     # no such class
     with pytest.raises(runtime.DrtError) as e:
         runtime.DeviceScene(Scene(prims, scene.lights, scene.textures), 0)
+    assert e.value.code == abi.ERR_UNSUPPORTED
+    prism, _, _ = load_case("prism_cyl")
+    prims = [abi.copy_struct(p) for p in prism.prims]
+    prims[0].holes[0].type = abi.PRIM_SPHERE                # RectPrismWithCylinder::holes are Cylinders (intersectCap)
+    with pytest.raises(runtime.DrtError) as e:
+        runtime.DeviceScene(Scene(prims, prism.lights, prism.textures), 0)
     assert e.value.code == abi.ERR_UNSUPPORTED
     prims = [abi.copy_struct(p) for p in scene.prims]
     ball = next(p for p in prims if p.type == abi.PRIM_SPHERE)
