@@ -59,6 +59,8 @@ static int drtref_printf(const char* fmt, ...) {
 #include "render_final_project.cpp"  // resolved through -I /root/reference
 #undef main
 #undef printf
+#include "../integration/drt_flatten.h"
+using namespace drt_integration;
 
 namespace {
 
@@ -86,61 +88,7 @@ struct QuietCout {
 std::string g_err;
 int fail(int code, const std::string& m) { g_err = m; return code; }
 
-void v3(double* o, const VEC3& v) { o[0] = v[0]; o[1] = v[1]; o[2] = v[2]; }
-VEC3 V3(const double* p) { return VEC3(p[0], p[1], p[2]); }
-
-int materialTag(const std::string& m) {
-  if (m == "glass") return DRT_MAT_GLASS;
-  if (m == "steel") return DRT_MAT_STEEL;
-  if (m == "aluminum") return DRT_MAT_ALUMINUM;
-  if (m == "water") return DRT_MAT_WATER;
-  if (m == "linoleum") return DRT_MAT_LINOLEUM;
-  return DRT_MAT_NONE;
-}
-const char* materialName(int t) {
-  switch (t) {
-    case DRT_MAT_GLASS: return "glass"; case DRT_MAT_STEEL: return "steel";
-    case DRT_MAT_ALUMINUM: return "aluminum"; case DRT_MAT_WATER: return "water";
-    case DRT_MAT_LINOLEUM: return "linoleum"; default: return "";
-  }
-}
-int modelTag(const std::string& m) {
-  if (m == "oren-nayar") return DRT_MODEL_OREN_NAYAR;
-  if (m == "cook-torrance") return DRT_MODEL_COOK_TORRANCE;
-  if (m == "raw") return DRT_MODEL_RAW;
-  return DRT_MODEL_LAMBERT;
-}
-const char* modelName(int t) {
-  switch (t) {
-    case DRT_MODEL_OREN_NAYAR: return "oren-nayar"; case DRT_MODEL_COOK_TORRANCE: return "cook-torrance";
-    case DRT_MODEL_RAW: return "raw"; default: return "lambert";
-  }
-}
-int nameTag(const std::string& n) {
-  if (n == "rectangle") return DRT_NAME_RECTANGLE;
-  if (n == "spherelight") return DRT_NAME_SPHERELIGHT;
-  if (n == "rectanglelight") return DRT_NAME_RECTANGLELIGHT;
-  return DRT_NAME_OTHER;
-}
-
-std::vector<std::vector<uint8_t>> g_tex_bytes;  // exported texture payloads
 bool g_mocap_loaded = false;
-
-void commonFields(drt_prim& p, GeoPrimitive* s) {
-  p.name = nameTag(s->name);
-  p.material = materialTag(s->reflect_params.material);
-  p.model = modelTag(s->model);
-  p.flags = (s->light ? DRT_FLAG_LIGHT : 0) | (s->motion ? DRT_FLAG_MOTION : 0) |
-            (s->texture ? DRT_FLAG_TEXTURE : 0) | (s->reflect_params.glossy ? DRT_FLAG_GLOSSY : 0) |
-            (s->mesh ? DRT_FLAG_MESH : 0) | (s->uv_verts ? DRT_FLAG_UV_VERTS : 0);
-  p.tex_frame = s->texture ? s->tex_frame : -1;
-  v3(p.color, s->color); v3(p.bordercolor, s->bordercolor);
-  // roughness is an uninitialised float for shapes that never set it; only the
-  // Oren-Nayar / Cook-Torrance models read it (render_final_project.cpp:896,925)
-  p.roughness = (p.model == DRT_MODEL_OREN_NAYAR || p.model == DRT_MODEL_COOK_TORRANCE) ? s->reflect_params.roughness : 0.0;
-  p.refr[0] = s->reflect_params.refr[0]; p.refr[1] = s->reflect_params.refr[1];
-  v3(p.center, s->center);
-}
 
 void applyCommon(GeoPrimitive* s, const drt_prim& p) {
   s->light = (p.flags & DRT_FLAG_LIGHT) != 0;
@@ -242,21 +190,7 @@ int drtref_build_scene(const char* name_c, float frame) {
   return 0;
 }
 
-void drtref_get_settings(drt_settings* s) {
-  memset(s, 0, sizeof(*s));
-  s->xRes = xRes; s->yRes = yRes;
-  v3(s->eye, eye); v3(s->lookingAt, lookingAt); v3(s->up, up);
-  s->aspect = aspect; s->near_plane = near; s->fov = fov; s->aperture = aperture; s->focal_length = focal_length;
-  s->nogloss = nogloss; s->refr_air = refr_air; s->refr_glass = refr_glass; s->max_depth = max_depth; s->phong = phong;
-  s->antialias_samples = antialias_samples; s->brdf_samples = brdf_samples; s->blur_samples = blur_samples;
-  s->frame_range = frame_range; s->frame_prism = frame_prism; s->frame_cloud = frame_cloud; s->frame_blur = frame_blur;
-  s->move_per_frame = move_per_frame; s->accel_t = accel_t;
-  v3(s->sundir, sundir); s->perlin_cloud = perlin_cloud; s->saturation = saturation; s->clouddist = clouddist;
-  s->cloudhoff = cloudhoff;
-  v3(s->sun_outer, sun_outer); v3(s->sun_inner, sun_inner); v3(s->sun_core, sun_core);
-  v3(s->bluesky, bluesky); v3(s->redsky, redsky);
-  s->reflect = reflect;
-}
+void drtref_get_settings(drt_settings* s) { drt_integration::drt_flatten_settings(s); }
 
 void drtref_set_settings(const drt_settings* s) {
   xRes = s->xRes; yRes = s->yRes;
@@ -277,98 +211,13 @@ void drtref_scene_counts(int* n_prims, int* n_lights, int* n_textures) {
   *n_prims = (int)shapes.size(); *n_lights = (int)lights.size(); *n_textures = (int)texture_frames.size();
 }
 
-// Flatten the reference's shapes/lights/textures.  `prims`, `lights`, `textures`
-// must have room for the counts reported by drtref_scene_counts.  Texture byte
+// Flatten the reference's shapes/lights/textures (integration/drt_flatten.h: the walk a drop-in renderImage performs).
+// `prims`, `lights`, `textures` must have room for the counts reported by drtref_scene_counts.  Texture byte
 // pointers stay valid until the next export.
 int drtref_export_scene(drt_prim* prims, drt_light* out_lights, drt_texture* textures) {
-  for (size_t i = 0; i < shapes.size(); i++) {
-    GeoPrimitive* s = shapes[i].get();
-    drt_prim& p = prims[i];
-    memset(&p, 0, sizeof(p));
-    commonFields(p, s);
-    if (auto* c = dynamic_cast<CheckerboardWithHole*>(s)) {
-      p.type = DRT_PRIM_CHECKERBOARD_HOLE;
-      v3(p.A, c->A); v3(p.B, c->B); v3(p.C, c->C); v3(p.D, c->D);
-      p.S = c->S; p.borderwidth = c->borderwidth; v3(p.color1, c->color1); v3(p.color2, c->color2);
-      v3(p.hole[0], c->hole->A); v3(p.hole[1], c->hole->B); v3(p.hole[2], c->hole->C); v3(p.hole[3], c->hole->D);
-    } else if (auto* c = dynamic_cast<Checkerboard*>(s)) {
-      p.type = DRT_PRIM_CHECKERBOARD;
-      v3(p.A, c->A); v3(p.B, c->B); v3(p.C, c->C); v3(p.D, c->D);
-      p.S = c->S; v3(p.color1, c->color1); v3(p.color2, c->color2);
-    } else if (dynamic_cast<Rectangle*>(s)) {
-      p.type = DRT_PRIM_RECTANGLE;
-      v3(p.A, s->A); v3(p.B, s->B); v3(p.C, s->C); v3(p.D, s->D);
-    } else if (auto* c = dynamic_cast<CheckerCylinder*>(s)) {
-      p.type = DRT_PRIM_CHECKER_CYLINDER;
-      v3(p.c1, c->c1); v3(p.c2, c->c2); p.radius = c->radius; p.S = c->S; p.borderwidth = c->borderwidth;
-    } else if (dynamic_cast<Cylinder*>(s)) {
-      p.type = DRT_PRIM_CYLINDER;
-      v3(p.c1, s->c1); v3(p.c2, s->c2); p.radius = s->radius;
-    } else if (dynamic_cast<Sphere*>(s)) {
-      p.type = DRT_PRIM_SPHERE; p.radius = s->radius;
-    } else if (dynamic_cast<Triangle*>(s)) {
-      p.type = DRT_PRIM_TRIANGLE;
-      v3(p.A, s->A); v3(p.B, s->B); v3(p.C, s->C);
-      p.uvA[0] = s->uvA[0]; p.uvA[1] = s->uvA[1]; p.uvB[0] = s->uvB[0]; p.uvB[1] = s->uvB[1];
-      p.uvC[0] = s->uvC[0]; p.uvC[1] = s->uvC[1];
-      if (s->mesh) v3(p.mesh_normal, s->mesh_normal);
-    } else if (dynamic_cast<RectPrismV2*>(s)) {
-      p.type = DRT_PRIM_RECTPRISMV2;
-      v3(p.A, s->A); v3(p.B, s->B); v3(p.C, s->C); v3(p.D, s->D);
-      v3(p.E, s->E); v3(p.F, s->F); v3(p.G, s->G); v3(p.H, s->H);
-    } else if (dynamic_cast<RectPrism*>(s)) {
-      // the slab-box prisms; the derived classes first
-      v3(p.A, s->A); v3(p.B, s->B); v3(p.C, s->C); v3(p.D, s->D);
-      v3(p.E, s->E); v3(p.F, s->F); v3(p.G, s->G); v3(p.H, s->H);
-      auto put_hole = [&](GeoPrimitive* h) -> int {
-        if (p.n_holes >= DRT_MAX_HOLES) return fail(-2, "more holes than DRT_MAX_HOLES");
-        drt_hole& o = p.holes[p.n_holes];
-        if (dynamic_cast<Cylinder*>(h)) { o.type = DRT_PRIM_CYLINDER; v3(o.c1, h->c1); v3(o.c2, h->c2); }
-        else if (dynamic_cast<Sphere*>(h)) { o.type = DRT_PRIM_SPHERE; v3(o.c1, h->center); }
-        else return fail(-2, "hole of a class without intersectMax");
-        o.radius = h->radius; v3(o.color, h->color);
-        p.n_holes++;
-        return 0;
-      };
-      if (auto* c = dynamic_cast<RectPrismWithCylinder*>(s)) {
-        p.type = DRT_PRIM_RECTPRISM_CYL;
-        for (auto& h : c->holes) { int rc = put_hole(h.get()); if (rc) return rc; }
-      } else if (auto* c = dynamic_cast<RectPrismWithHoles*>(s)) {
-        p.type = DRT_PRIM_RECTPRISM_HOLES;
-        for (auto& h : c->holes) { int rc = put_hole(h.get()); if (rc) return rc; }
-      } else p.type = DRT_PRIM_RECTPRISM;
-    } else {
-      return fail(-2, "unsupported primitive class at index " + std::to_string(i) + " (" + s->name + ")");
-    }
-  }
-  for (size_t i = 0; i < lights.size(); i++) {
-    LightPrimitive* l = lights[i].get();
-    drt_light& o = out_lights[i];
-    memset(&o, 0, sizeof(o));
-    o.prim_index = -1;
-    v3(o.color, l->color); v3(o.center, l->center);
-    shared_ptr<void> lv = dynamic_pointer_cast<void>(lights[i]);
-    for (size_t k = 0; k < shapes.size(); k++)
-      if (dynamic_pointer_cast<void>(shapes[k]) == lv) { o.prim_index = (int)k; break; }
-    if (auto* sl = dynamic_cast<sphereLight*>(l)) {
-      o.type = DRT_LIGHT_SPHERE; o.radius = sl->radius; v3(o.baxis, sl->baxis);
-      v3(o.center, sl->Sphere::center);
-    } else if (auto* rl = dynamic_cast<rectangleLight*>(l)) {
-      o.type = DRT_LIGHT_RECT; v3(o.A, rl->A); v3(o.B, rl->B); v3(o.C, rl->C); v3(o.D, rl->D);
-    } else {
-      o.type = DRT_LIGHT_POINT;
-    }
-  }
-  g_tex_bytes.assign(texture_frames.size(), std::vector<uint8_t>());
-  for (size_t i = 0; i < texture_frames.size(); i++) {
-    const std::vector<VEC3>& t = texture_frames[i];
-    g_tex_bytes[i].resize(t.size() * 3);
-    for (size_t k = 0; k < t.size(); k++)
-      for (int c = 0; c < 3; c++) g_tex_bytes[i][3 * k + c] = (uint8_t)lround(t[k][c] * 255.0);
-    textures[i].width = (int)texture_dims[i][0]; textures[i].height = (int)texture_dims[i][1];
-    textures[i].rgb = g_tex_bytes[i].data();
-  }
-  return 0;
+  std::string err;
+  const int rc = drt_integration::drt_flatten_scene(prims, out_lights, textures, err);
+  return rc ? fail(rc, err) : 0;
 }
 
 // Inverse of drtref_export_scene: rebuild the reference's object graph from PODs

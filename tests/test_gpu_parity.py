@@ -185,7 +185,8 @@ def test_cuda_mesh_full_size_matches_oracle_on_crops(oracle_lib):
     dev = _gpu(scene)
     crops = [abi.Tile(1600, 1060, 640, 20, 0),     # through the sphere: velocity-blur re-traces, its shadow on the terrain
              abi.Tile(1904, 700, 32, 700, 0),      # a column from the near terrain up over the sphere to the far edge
-             abi.Tile(40, 300, 96, 54, 0), abi.Tile(3700, 1500, 96, 54, 0), abi.Tile(900, 1900, 128, 36, 0)]
+             abi.Tile(40, 300, 96, 54, 0),         # the left edge of the terrain against the empty background
+             abi.Tile(2700, 1200, 96, 54, 0), abi.Tile(1000, 600, 96, 54, 0), abi.Tile(2900, 500, 96, 54, 0)]
     total = bad = 0
     for tile in crops:
         want, _, _, _ = oracle.render(s, tile, mode=ORACLE_KEYED)
@@ -193,7 +194,7 @@ def test_cuda_mesh_full_size_matches_oracle_on_crops(oracle_lib):
         st = compare(want, got)
         assert st["frac_within_1"] >= TOL_FRAC, ((tile.x0, tile.y0), st)
         total += tile.width * tile.height; bad += st["n_bad"]
-        assert want.std() > 0.5 or tile.y0 > 1800, "crop shows nothing"
+        assert want.std() > 0.5, "crop shows nothing"
     assert total >= 50000 and bad <= total * (1 - TOL_FRAC)
 
 
