@@ -73,6 +73,7 @@ class Mesh(C.Structure):
         ("n_vertices", C.c_int64), ("n_triangles", C.c_int64),
         ("vertices", C.POINTER(C.c_float)), ("indices", C.POINTER(C.c_int32)),
         ("texcoords", C.POINTER(C.c_float)), ("material", Prim),
+        ("n_materials", C.c_int32), ("pad_", C.c_int32), ("materials", C.POINTER(Prim)), ("material_ids", C.POINTER(C.c_int32)),
     ]
 
 

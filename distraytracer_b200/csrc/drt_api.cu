@@ -459,7 +459,8 @@ struct drt_scene {
   unsigned char* owned = nullptr; size_t owned_cap = 0;         // drt_render_multi: units of the current chunk this device rendered
   cudaEvent_t ev_sync = nullptr;                                // cross-device ordering (drt_render_multi)
   int wave_blocks_f64 = 0, wave_blocks_f32 = 0;
-  MeshBuffers mesh; bool has_mesh = false; drt_prim mesh_material;
+  MeshBuffers mesh; bool has_mesh = false;
+  std::vector<drt_prim> mesh_materials;   // the mesh's material table (one entry when all triangles share drt_mesh.material)
   PinnedStage stage;
 };
 
@@ -487,8 +488,10 @@ int flattenAndUpload(drt_scene* s) {
   rc = flatten<float>(s->prims.data(), (int)s->prims.size(), s->lights.data(), (int)s->lights.size(), s->n_textures, hf);
   if (rc) return rc;
   if (s->has_mesh) {
-    rc = addMeshMaterial<double>(s->mesh_material, s->n_textures, hd); if (rc) return rc;
-    rc = addMeshMaterial<float>(s->mesh_material, s->n_textures, hf); if (rc) return rc;
+    for (const drt_prim& m : s->mesh_materials) {
+      rc = addMeshMaterial<double>(m, s->n_textures, hd); if (rc) return rc;
+      rc = addMeshMaterial<float>(m, s->n_textures, hf); if (rc) return rc;
+    }
   }
   CK(cudaStreamSynchronize(s->stream));                     // the stage may still feed the previous update's copies
   rc = s->stage.reserve(uploadBytes(hd) + uploadBytes(hf)); if (rc) return rc;
@@ -502,7 +505,7 @@ int flattenAndUpload(drt_scene* s) {
     if (p.flags & DRT_FLAG_MOTION) s->any_motion = true;
   };
   for (const drt_prim& p : s->prims) scan(p);
-  if (s->has_mesh) scan(s->mesh_material);
+  if (s->has_mesh) for (const drt_prim& m : s->mesh_materials) scan(m);
   return DRT_OK;
 }
 
@@ -565,6 +568,7 @@ void fillParams(Params<R>& P, const drt_scene* s, const DevScene<R>& ds, const d
   if (s->has_mesh) {
     P.mesh_nodes = s->mesh.nodes; P.n_mesh_tris = s->mesh.n_tris; P.mesh_prim = (int)s->prims.size();
     P.mesh_tris = (const MeshTri<R>*)(sizeof(R) == 8 ? s->mesh.tris_f64 : s->mesh.tris_f32);
+    P.mesh_mat = s->mesh.mat_ids;
   }
 }
 
@@ -1057,12 +1061,14 @@ int drt_scene_create(const drt_scene_desc* d, int device, drt_scene** out) {
       return bail(fail(DRT_ERR_CUDA, "texture table upload failed"));
   }
   if (d->mesh) {
-    if ((d->mesh->material.flags & DRT_FLAG_TEXTURE) && !d->mesh->texcoords)
-      return bail(fail(DRT_ERR_INVALID, "textured mesh without texcoords"));
+    if (d->mesh->n_materials > 0 && d->mesh->materials) s->mesh_materials.assign(d->mesh->materials, d->mesh->materials + d->mesh->n_materials);
+    else s->mesh_materials.assign(1, d->mesh->material);
+    for (const drt_prim& m : s->mesh_materials)
+      if ((m.flags & DRT_FLAG_TEXTURE) && !d->mesh->texcoords) return bail(fail(DRT_ERR_INVALID, "textured mesh without texcoords"));
     std::string err;
     int mrc = buildMesh(d->mesh, &s->mesh, err);
     if (mrc) return bail(fail(mrc, err));
-    s->has_mesh = true; s->mesh_material = d->mesh->material;
+    s->has_mesh = true;
   }
   int rc = flattenAndUpload(s);
   if (rc) return bail(rc);

@@ -1050,6 +1050,12 @@ struct alignas(16) HitTask {
   int checker_sel;
 };
 
+// shading record of mesh triangle `tri`: the mesh's material table follows the analytic primitives
+template <typename R>
+__device__ __forceinline__ int meshOwner(const Params<R>& P, const int tri) {
+  return P.mesh_prim + (P.mesh_mat ? (int)__ldg(P.mesh_mat + tri) : 0);
+}
+
 // Returns true when the ray hit something (h filled in).  `motion` is -1 unless this task is
 // on the "last invocation" chain that decides in_motion (quirk Q4), else the new flag value.
 template <typename R, int F, bool COUNT>
@@ -1065,7 +1071,7 @@ __device__ inline bool traceRay(const Params<R>& P, const float4* __restrict__ g
   if ((F & (FT_VEL | FT_REFBLUR)) && (T.bits & TASK_CHAIN)) motion = 0;             // :519
   if (h.geom < 0) return false;                                         // :541-544
   if ((F & (FT_VEL | FT_REFBLUR)) && (T.bits & TASK_CHAIN)) {
-    const int owner = h.geom >= P.n_geoms ? P.mesh_prim : P.geoms[h.geom].owner;
+    const int owner = h.geom >= P.n_geoms ? meshOwner(P, h.geom - P.n_geoms) : P.geoms[h.geom].owner;
     motion = (P.prims[owner].flags & 2) ? 1 : 0;                        // DRT_FLAG_MOTION, :564
   }
   return true;
@@ -1125,7 +1131,7 @@ __device__ void shadeA(const Params<R>& P, const Task<R>& T, const HitRec& h, Ta
     const Vec<R> ray = T.dir, eye = T.org;
     const float k = T.k;
     const int mesh_tri = ((F & FT_MESH) && h.geom >= P.n_geoms) ? h.geom - P.n_geoms : -1;
-    const int owner = mesh_tri >= 0 ? P.mesh_prim : P.geoms[h.geom].owner;
+    const int owner = mesh_tri >= 0 ? meshOwner(P, mesh_tri) : P.geoms[h.geom].owner;
     const PrimD<R>& pr = P.prims[owner];
 
     const Vec<R> isectP = eye + (R)h.t * ray;                           // :548

@@ -19,6 +19,7 @@ void freeMesh(MeshBuffers* m) {
   if (m->nodes) cudaFree(m->nodes);
   if (m->tris_f64) cudaFree(m->tris_f64);
   if (m->tris_f32) cudaFree(m->tris_f32);
+  if (m->mat_ids) cudaFree(m->mat_ids);
   *m = MeshBuffers();
 }
 
@@ -28,6 +29,12 @@ int buildMesh(const drt_mesh* mesh, MeshBuffers* out, std::string& err) {
   if (nt > (1ll << 30)) { err = "mesh too large"; return DRT_ERR_UNSUPPORTED; }
   for (long long i = 0; i < 3 * nt; i++)
     if (mesh->indices[i] < 0 || mesh->indices[i] >= nv) { err = "mesh index out of range"; return DRT_ERR_INVALID; }
+  if (mesh->n_materials < 0 || mesh->n_materials > 65535) { err = "mesh material table larger than 65535 entries"; return DRT_ERR_UNSUPPORTED; }
+  if (mesh->n_materials > 0) {
+    if (!mesh->materials || !mesh->material_ids) { err = "mesh material table without ids"; return DRT_ERR_INVALID; }
+    for (long long t = 0; t < nt; t++)
+      if (mesh->material_ids[t] < 0 || mesh->material_ids[t] >= mesh->n_materials) { err = "mesh material id out of range"; return DRT_ERR_INVALID; }
+  }
   const int n = (int)nt;
   // scene bounds of the centroids' support (host: one pass over the vertices)
   float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
@@ -63,6 +70,12 @@ int buildMesh(const drt_mesh* mesh, MeshBuffers* out, std::string& err) {
   MCK(cudaMalloc(&mb.nodes, sizeof(float4) * 4 * std::max(1, n - 1)));
   MCK(cudaMalloc(&mb.tris_f64, sizeof(MeshTri<double>) * n));
   MCK(cudaMalloc(&mb.tris_f32, sizeof(MeshTri<float>) * n));
+  if (mesh->n_materials > 0) {
+    std::vector<unsigned short> ids((size_t)n);
+    for (int t = 0; t < n; t++) ids[t] = (unsigned short)mesh->material_ids[t];
+    MCK(cudaMalloc(&mb.mat_ids, sizeof(unsigned short) * n));
+    MCK(cudaMemcpy(mb.mat_ids, ids.data(), sizeof(unsigned short) * n, cudaMemcpyHostToDevice));
+  }
   MCK(cudaEventCreate(&e0)); MCK(cudaEventCreate(&e1));
   MCK(cudaEventRecord(e0));
   lbvh_tri_setup<<<G, B>>>(n, d_verts, d_idx, slo, sinv, tlo, thi, codes, ids);

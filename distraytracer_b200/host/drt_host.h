@@ -31,6 +31,7 @@
 #include <condition_variable>
 #include <deque>
 #include <fstream>
+#include <iostream>
 #include <map>
 #include <mutex>
 #include <sstream>
@@ -288,6 +289,11 @@ struct Globals {
   std::vector<float> mesh_vertices, mesh_texcoords;
   std::vector<int32_t> mesh_indices;
   std::shared_ptr<GeoPrimitive> mesh_material;
+  std::vector<float> mesh_face_roughness;     // optional: Reflectance::roughness per face (faceRoughnessFromMap, scene.h:372-378)
+  std::vector<int32_t> mesh_material_ids;     // derived by flattenScene
+  // loadTexture(path) decodes binary PPM (P6) itself; any other format goes through this hook (path -> width, height,
+  // RGB bytes as stbi_load returns them), e.g. a wrapper around the stb_image.h the reference vendors
+  std::function<bool(const std::string&, int&, int&, std::vector<uint8_t>&)> decode_image;
 };
 inline Globals& globals() { static Globals g; return g; }
 
@@ -297,6 +303,54 @@ inline int addTexture(int width, int height, const uint8_t* rgb) {
   g.texture_frames.emplace_back(rgb, rgb + (size_t)width * height * 3);
   g.texture_dims.push_back(VEC2(width, height));
   return (int)g.texture_frames.size() - 1;
+}
+
+struct VEC3I { int v[3]; int& operator[](int i) { return v[i]; } int operator[](int i) const { return v[i]; } };
+// loadTexture (helpers.h:92-113): push one image onto texture_frames / texture_dims.  The reference decodes with stb_image;
+// this mirror reads binary PPM itself and leaves every other format to Globals::decode_image.  Prints and throws like
+// the reference when the image cannot be loaded.
+inline int loadTexture(const std::string& f) {
+  Globals& g = globals();
+  int width = 0, height = 0;
+  std::vector<uint8_t> rgb;
+  bool ok = false;
+  {
+    std::ifstream in(f, std::ios::binary);
+    std::string magic;
+    if (in && (in >> magic) && magic == "P6") {
+      auto next_int = [&]() { int v = -1; for (;;) { in >> std::ws; if (in.peek() == '#') { std::string c; std::getline(in, c); } else break; } in >> v; return v; };
+      width = next_int(); height = next_int();
+      const int maxval = next_int();
+      in.get();                                               // the single whitespace after maxval
+      if (width > 0 && height > 0 && maxval == 255) {
+        rgb.resize((size_t)width * height * 3);
+        in.read((char*)rgb.data(), (std::streamsize)rgb.size());
+        ok = (size_t)in.gcount() == rgb.size();
+      }
+    }
+  }
+  if (!ok && g.decode_image) ok = g.decode_image(f, width, height, rgb) && width > 0 && height > 0 && rgb.size() == (size_t)width * height * 3;
+  if (!ok) { std::cout << "Image loading failed for: " << f << std::endl; throw std::runtime_error("Image loading failed for: " + f); }
+  return addTexture(width, height, rgb.data());
+}
+
+// The per-face roughness the reference's model builders assign (scene.h:372-378): the roughness map is indexed with the
+// ORIGINAL texcoords of the three corners as `map[int(u * int(w-1) + v * int(h-1) * (w-1))]` -- a byte offset into the
+// decoded image, channel count ignored, exactly as written there -- and the face gets (r1 + r2 + r3) / (3 * 255).
+inline std::vector<float> faceRoughnessFromMap(const std::vector<VEC2>& texcoords, const std::vector<VEC3I>& t_indices,
+                                               const uint8_t* map_bytes, size_t map_size, int width, int height) {
+  std::vector<float> out;
+  for (const VEC3I& t : t_indices) {
+    float r[3];
+    for (int k = 0; k < 3; k++) {
+      const VEC2& uv = texcoords[t[k]];
+      const long long at = (long long)(int)(uv[0] * (int)(width - 1) + uv[1] * (int)(height - 1) * (width - 1));
+      if (at < 0 || (size_t)at >= map_size) throw std::runtime_error("roughness map lookup outside the image");   // the reference reads out of bounds
+      r[k] = map_bytes[at];
+    }
+    out.push_back((r[0] + r[1] + r[2]) / (3 * 255));
+  }
+  return out;
 }
 
 // ---- flattening ---------------------------------------------------------------------------
@@ -354,6 +408,7 @@ inline drt_prim flattenPrim(const GeoPrimitive& s) {
 }
 
 struct FlatScene {
+  std::vector<drt_prim> mesh_materials;
   std::vector<drt_prim> prims;
   std::vector<drt_light> lights;
   std::vector<drt_texture> textures;
@@ -390,6 +445,24 @@ inline void flattenScene(FlatScene& f) {
     f.mesh.vertices = g.mesh_vertices.data(); f.mesh.indices = g.mesh_indices.data();
     f.mesh.texcoords = g.mesh_texcoords.empty() ? nullptr : g.mesh_texcoords.data();
     f.mesh.material = flattenPrim(*g.mesh_material);
+    f.mesh.n_materials = 0; f.mesh.materials = nullptr; f.mesh.material_ids = nullptr;
+    if (!g.mesh_face_roughness.empty()) {
+      // one material per distinct per-face roughness (scene.h:372-378: at most 766 values), triangle -> table index
+      if (g.mesh_face_roughness.size() * 3 != g.mesh_indices.size()) throw std::runtime_error("setMesh: one roughness per face expected");
+      std::map<float, int> table;
+      g.mesh_material_ids.clear(); f.mesh_materials.clear();
+      for (float r : g.mesh_face_roughness) {
+        auto it = table.find(r);
+        if (it == table.end()) {
+          it = table.emplace(r, (int)f.mesh_materials.size()).first;
+          drt_prim m = f.mesh.material; m.roughness = r;
+          f.mesh_materials.push_back(m);
+        }
+        g.mesh_material_ids.push_back(it->second);
+      }
+      f.mesh.n_materials = (int32_t)f.mesh_materials.size(); f.mesh.materials = f.mesh_materials.data();
+      f.mesh.material_ids = g.mesh_material_ids.data();
+    }
     f.desc.mesh = &f.mesh;
   }
 }
@@ -484,7 +557,6 @@ inline void renderImage(const std::string& filename, const int frame, const std:
 }
 
 // ---- mesh ingest ------------------------------------------------------
-struct VEC3I { int v[3]; int& operator[](int i) { return v[i]; } int operator[](int i) const { return v[i]; } };
 
 // loadObj (objHelper.h:6-85) without tiny_obj_loader: positions, texcoords and per-face index
 // triples, polygons as triangle fans (tiny_obj_loader's default triangulation), indices 0-based,
@@ -537,9 +609,11 @@ inline void loadObj(const std::string& path, std::vector<VEC3>& vertices, std::v
 // `material` is the Triangle the reference would copy per face (colour, model, roughness, texture).
 inline void setMesh(const std::vector<VEC3>& vertices, const std::vector<VEC3I>& v_indices, const std::vector<VEC2>& texcoords,
                     const std::vector<VEC3I>& t_indices, std::shared_ptr<GeoPrimitive> material, const double* M = nullptr,
-                    bool wrap_uv = true, bool flip_v = true) {
+                    bool wrap_uv = true, bool flip_v = true, const std::vector<float>* face_roughness = nullptr) {
   Globals& g = globals();
   g.mesh_vertices.clear(); g.mesh_texcoords.clear(); g.mesh_indices.clear();
+  g.mesh_face_roughness.clear();
+  if (face_roughness) g.mesh_face_roughness = *face_roughness;
   bool has_uv = !texcoords.empty();
   for (const VEC3I& t : t_indices) for (int k = 0; k < 3; k++) if (t[k] < 0) has_uv = false;
   std::vector<VEC2> uv = texcoords;

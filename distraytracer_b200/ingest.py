@@ -70,8 +70,27 @@ def parse_obj(text):
     }
 
 
-def mesh_from_obj(obj, material, transform=None, wrap_uv=True, flip_v=True):
+def face_roughness_from_map(obj, roughness_map):
+    """Reflectance::roughness per face as the reference's model builders assign it (scene.h:372-378): the roughness map
+    (uint8 array as stbi_load returns it, (H, W) or (H, W, C)) is indexed with the ORIGINAL texcoords of the three corners as
+    `map[int(u * int(W-1) + v * int(H-1) * (W-1))]` -- a byte offset into the decoded buffer, channel count ignored, exactly
+    as written there -- and the face gets float32 (r1 + r2 + r3) / (3 * 255): at most 766 distinct values."""
+    img = np.ascontiguousarray(roughness_map, dtype=np.uint8)
+    h, w = img.shape[0], img.shape[1]
+    flat = img.reshape(-1)
+    uv = obj["texcoords"].astype(np.float64)[obj["t_indices"]]                  # (T, 3, 2)
+    at = (uv[..., 0] * int(w - 1) + uv[..., 1] * int(h - 1) * (w - 1)).astype(np.int64)   # C++ int(): truncation
+    if (obj["t_indices"] < 0).any() or (at < 0).any() or (at >= flat.size).any():
+        raise ObjError("roughness map lookup outside the image")               # the reference reads out of bounds there
+    r = flat[at].astype(np.float32)
+    return ((r[:, 0] + r[:, 1]) + r[:, 2]) / np.float32(3 * 255)
+
+
+def mesh_from_obj(obj, material, transform=None, wrap_uv=True, flip_v=True, face_roughness=None):
     """OBJ arrays -> dict(vertices, indices, texcoords, material) for `Scene(mesh=...)`.
+
+    face_roughness : optional float32 (T,), one Reflectance::roughness per face (face_roughness_from_map); the mesh then
+                carries a material table with one entry per distinct value (`materials`, `material_ids`).
 
     transform : optional 4x4 applied to the positions as `(M * (v,1)).head<3>()` (scene.h:301-307).
     wrap_uv   : `if (uv > 1) uv -= int(uv)` per component (scene.h:335-340).
@@ -83,8 +102,21 @@ def mesh_from_obj(obj, material, transform=None, wrap_uv=True, flip_v=True):
         V = (np.concatenate([V, np.ones((len(V), 1))], axis=1) @ M.T)[:, :3]
     vi, ti = obj["v_indices"], obj["t_indices"]
     has_uv = len(obj["texcoords"]) > 0 and (ti >= 0).all()
+    extra = {}
+    if face_roughness is not None:
+        from . import abi
+        fr = np.asarray(face_roughness, dtype=np.float32)
+        if fr.shape != (len(vi),):
+            raise ObjError("face_roughness needs one value per face")
+        values, ids = np.unique(fr, return_inverse=True)
+        mats = []
+        for v in values:
+            m = abi.copy_struct(material)
+            m.roughness = float(v)
+            mats.append(m)
+        extra = {"materials": mats, "material_ids": ids.astype(np.int32)}
     if not has_uv:
-        return {"vertices": V.astype(np.float32), "indices": vi.astype(np.int32), "texcoords": None, "material": material}
+        return {"vertices": V.astype(np.float32), "indices": vi.astype(np.int32), "texcoords": None, "material": material, **extra}
     UV = obj["texcoords"].astype(np.float64).copy()
     if wrap_uv:
         over = UV > 1
@@ -102,7 +134,7 @@ def mesh_from_obj(obj, material, transform=None, wrap_uv=True, flip_v=True):
         "vertices": V[uniq[:, 0]].astype(np.float32),
         "indices": inverse.reshape(-1, 3).astype(np.int32),
         "texcoords": UV[uniq[:, 1]].astype(np.float32),
-        "material": material,
+        "material": material, **extra,
     }
 
 

@@ -12,7 +12,7 @@ from . import abi
 class Scene:
     """prims: list[abi.Prim]; lights: list[abi.Light]; textures: list[np.uint8 (H,W,3)];
     mesh: optional dict(vertices float32 (V,3), indices int32 (T,3), texcoords float32 (V,2)|None,
-    material abi.Prim)."""
+    material abi.Prim [, materials list[abi.Prim], material_ids int32 (T,)])."""
 
     def __init__(self, prims=None, lights=None, textures=None, mesh=None):
         self.prims = list(prims or [])
@@ -50,8 +50,18 @@ class Scene:
                 tc = np.ascontiguousarray(tc, dtype=np.float32)
                 m.texcoords = tc.ctypes.data_as(C.POINTER(C.c_float))
             m.material = self.mesh["material"]
+            mats = self.mesh.get("materials")
+            mids = None
+            if mats:
+                # per-triangle materials: triangle t uses materials[material_ids[t]]
+                marr = (abi.Prim * len(mats))(*mats)
+                mids = np.ascontiguousarray(self.mesh["material_ids"], dtype=np.int32)
+                assert mids.shape == (idx.shape[0],)
+                m.n_materials, m.materials = len(mats), marr
+                m.material_ids = mids.ctypes.data_as(C.POINTER(C.c_int32))
+                keep.append(marr)
             d.mesh = C.pointer(m)
-            keep += [m, v, idx, tc]
+            keep += [m, v, idx, tc, mids]
         self._keep = keep
         return d
 

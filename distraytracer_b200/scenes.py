@@ -240,9 +240,10 @@ def mesh_to_prims(mesh):
     T = mesh["indices"]
     tc = mesh.get("texcoords")
     mat = mesh["material"]
+    mats, mids = mesh.get("materials"), mesh.get("material_ids")
     out = []
-    for t in T:
-        p = abi.copy_struct(mat)
+    for ti, t in enumerate(T):
+        p = abi.copy_struct(mats[mids[ti]] if mats else mat)
         p.type = abi.PRIM_TRIANGLE
         _v(p.A, V[t[0]]); _v(p.B, V[t[1]]); _v(p.C, V[t[2]])
         _v(p.center, (V[t[0]] + V[t[1]] + V[t[2]]) / 3)

@@ -179,13 +179,21 @@ typedef struct drt_texture {
 
 /* Optional indexed triangle mesh (objHelper.h:6-85 output shape): when given,
  * its triangles are appended after `prims` and traversed through the
- * device-built LBVH.  All triangles share one material record. */
+ * device-built LBVH.  Vertices are single precision (what tiny_obj_loader hands the reference, objHelper.h:40-46; the
+ * reference then transforms them in double, scene.h:297-307 -- a mesh that needs that is transformed by the caller).
+ * Materials: every triangle uses `material`, unless `materials` is given -- then triangle t uses
+ * materials[material_ids[t]].  That is how the reference's per-face roughness (one value per Triangle, looked up in a
+ * roughness map, scene.h:372-378: at most 766 distinct values) travels without a material record per triangle. */
 typedef struct drt_mesh {
   int64_t n_vertices, n_triangles;
   const float* vertices;   /* 3 floats per vertex               */
   const int32_t* indices;  /* 3 vertex indices per triangle     */
   const float* texcoords;  /* 2 floats per vertex, or NULL      */
   drt_prim material;       /* type must be DRT_PRIM_TRIANGLE; A/B/C ignored */
+  int32_t n_materials;     /* 0: `material` for all triangles; else 1..65535 entries in `materials` */
+  int32_t pad_;
+  const drt_prim* materials;
+  const int32_t* material_ids;  /* n_triangles entries in [0, n_materials) */
 } drt_mesh;
 
 typedef struct drt_scene_desc {

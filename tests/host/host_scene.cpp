@@ -64,14 +64,21 @@ static void buildSceneMocap(float frame) {
   g.eye = VEC3(-6, 0.5, 1) + (VEC3(0.49, 10, 1) - VEC3(-6, 0.5, 1)) * (float)(frame / 320);
 }
 
-// host_scene mesh <in.obj> <out.bin>: loadObj + setMesh (column transform of scene.h:296-299), dumps the
-// unified arrays: int64 n_vertices, n_triangles, has_uv; float vertices[3V]; int32 indices[3T]; float texcoords[2V]
-static int meshMode(const std::string& in, const std::string& out) {
+// host_scene mesh <in.obj> <out.bin> [roughness.ppm]: loadObj + setMesh (column transform of scene.h:296-299), dumps the
+// unified arrays: int64 n_vertices, n_triangles, has_uv; float vertices[3V]; int32 indices[3T]; float texcoords[2V];
+// with a roughness map (loadTexture: binary PPM) also int64 n_materials; int32 material_ids[T]; double roughness[n_materials]
+static int meshMode(const std::string& in, const std::string& out, const char* rough_ppm) {
   std::vector<VEC3> vertices; std::vector<VEC3I> v_inds, t_inds; std::vector<VEC2> texcoords;
   loadObj(in, vertices, v_inds, texcoords, t_inds);
   const double M[12] = {3, 0, 0, 3, 0, 3, 0, -1, 0, 0, 3, 5};
   auto mat = make_shared<Triangle>(VEC3(0, 0, 0), VEC3(1, 0, 0), VEC3(0, 1, 0), VEC3(0.75, 0.75, 0.75), "marble", false, "oren-nayar");
-  setMesh(vertices, v_inds, texcoords, t_inds, mat, M);
+  std::vector<float> rough;
+  if (rough_ppm) {
+    const int tex = loadTexture(rough_ppm);                          // helpers.h:92-113
+    const std::vector<uint8_t>& img = globals().texture_frames[tex];
+    rough = faceRoughnessFromMap(texcoords, t_inds, img.data(), img.size(), (int)globals().texture_dims[tex][0], (int)globals().texture_dims[tex][1]);
+  }
+  setMesh(vertices, v_inds, texcoords, t_inds, mat, M, true, true, rough_ppm ? &rough : nullptr);
   Globals& g = globals();
   FlatScene f; flattenScene(f);
   if (!f.desc.mesh) return 1;
@@ -81,6 +88,12 @@ static int meshMode(const std::string& in, const std::string& out) {
   o.write((const char*)g.mesh_vertices.data(), g.mesh_vertices.size() * sizeof(float));
   o.write((const char*)g.mesh_indices.data(), g.mesh_indices.size() * sizeof(int32_t));
   o.write((const char*)g.mesh_texcoords.data(), g.mesh_texcoords.size() * sizeof(float));
+  if (rough_ppm) {
+    int64_t nm = f.mesh.n_materials;
+    o.write((const char*)&nm, sizeof(nm));
+    o.write((const char*)f.mesh.material_ids, f.mesh.n_triangles * sizeof(int32_t));
+    for (int k = 0; k < f.mesh.n_materials; k++) o.write((const char*)&f.mesh.materials[k].roughness, sizeof(double));
+  }
   return 0;
 }
 
@@ -88,7 +101,7 @@ int main(int argc, char** argv) {
   if (argc < 4) { fprintf(stderr, "usage: host_scene dump|render|video hw4|reflectance <out> | mesh <in.obj> <out.bin>\n"); return 2; }
   std::string mode = argv[1], scene = argv[2], out = argv[3];
   if (mode == "mesh") {
-    try { return meshMode(scene, out); } catch (const std::exception& e) { fprintf(stderr, "host_scene: %s\n", e.what()); return 1; }
+    try { return meshMode(scene, out, argc > 4 ? argv[4] : nullptr); } catch (const std::exception& e) { fprintf(stderr, "host_scene: %s\n", e.what()); return 1; }
   }
   Globals& g = globals();
   g.xRes = 160; g.yRes = 120; g.seed = 7;

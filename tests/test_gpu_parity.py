@@ -159,6 +159,36 @@ def test_cuda_mesh_lbvh_matches_oracle(oracle_lib):
     assert st["frac_within_1"] >= TOL_FRAC, st
 
 
+def test_cuda_mesh_per_triangle_materials_match_oracle(oracle_lib):
+    """The reference's model builders give every Triangle its own roughness from a roughness map (scene.h:372-378).  The
+    mesh carries that as a material table + one index per triangle; the picture must be the oracle's, which gets one
+    Triangle primitive per face with its own roughness."""
+    from distraytracer_b200 import scenes, abi
+    from distraytracer_b200.scene import Scene
+    from oracle.harness import Oracle, ORACLE_KEYED, compare
+    scene, s = scenes.config5(n=24, xres=160, yres=90, spp=4)
+    rng = np.random.default_rng(11)
+    nt = len(scene.mesh["indices"])
+    fr = (rng.integers(0, 766, size=nt) / np.float32(3 * 255)).astype(np.float32)     # what face_roughness_from_map yields
+    values, ids = np.unique(fr, return_inverse=True)
+    mats = []
+    for v in values:
+        m = abi.copy_struct(scene.mesh["material"]); m.roughness = float(v); mats.append(m)
+    mesh = dict(scene.mesh, materials=mats, material_ids=ids.astype(np.int32))
+    tabled = Scene(scene.prims, scene.lights, scene.textures, mesh=mesh)
+    flat = Scene(list(scene.prims) + scenes.mesh_to_prims(mesh), scene.lights, scene.textures)
+    want, _, _, _ = Oracle(flat).render(s, mode=ORACLE_KEYED)
+    got, _ = _gpu(tabled).render_float(s)
+    st = compare(want, got)
+    assert st["frac_within_1"] >= TOL_FRAC, st
+    # ... and it is not the picture of the single-material mesh
+    one, _ = _gpu(scene).render_float(s)
+    assert compare(one, got)["mae"] > 0.05
+    # the oracle's own mesh expansion reads the same table
+    via_mesh, _, _, _ = Oracle(tabled).render(s, mode=ORACLE_KEYED)
+    assert np.array_equal(want, via_mesh)
+
+
 def test_cuda_obj_ingest_renders_like_the_direct_mesh(oracle_lib):
     """A mesh that went through the OBJ text format and `ingest.mesh_from_obj` (vertex unification, no
     UV rewrite) renders byte-identically to the mesh it was written from."""

@@ -130,3 +130,33 @@ def test_mocap_through_host_mirror(host_bin, tmp_path):
     frames = [read_ppm(prefix + ".%04d.ppm" % f) for f in range(30, 34)]
     assert np.array_equal(frames[0], read_ppm(single))
     assert any(not np.array_equal(frames[0], f) for f in frames[1:])             # the figure moves
+
+
+def test_host_roughness_map_and_loadTexture_match_python_ingest(host_bin, tmp_path):
+    """The per-face roughness of the reference's model builders (scene.h:372-378) through the C++ mirror -- loadTexture of a
+    binary PPM, faceRoughnessFromMap, setMesh building the material table -- equals distraytracer_b200.ingest's."""
+    from distraytracer_b200 import ingest, runtime
+    rng = np.random.default_rng(5)
+    n = 9
+    lines = ["v %g %g %g" % (i, j, 0.1 * i * j) for i in range(n) for j in range(n)]
+    lines += ["vt %.6f %.6f" % (i / (n - 1), j / (n - 1)) for i in range(n) for j in range(n)]
+    for i in range(n - 1):
+        for j in range(n - 1):
+            a, b, c, d = i * n + j + 1, (i + 1) * n + j + 1, (i + 1) * n + j + 2, i * n + j + 2
+            lines += ["f %d/%d %d/%d %d/%d" % (a, a, b, b, c, c), "f %d/%d %d/%d %d/%d" % (a, a, c, c, d, d)]
+    text = "\n".join(lines) + "\n"
+    obj_path, ppm, out = str(tmp_path / "g.obj"), str(tmp_path / "rough.ppm"), str(tmp_path / "mesh.bin")
+    open(obj_path, "w").write(text)
+    img = rng.integers(0, 256, size=(7, 11, 3), dtype=np.uint8)
+    runtime.write_ppm(ppm, img)
+    subprocess.check_call([host_bin, "mesh", obj_path, out, ppm])
+    raw = open(out, "rb").read()
+    nv, nt, has_uv = np.frombuffer(raw[:24], dtype=np.int64)
+    off = 24 + 12 * nv + 12 * nt + 8 * nv
+    nm = int(np.frombuffer(raw[off: off + 8], dtype=np.int64)[0]); off += 8
+    ids = np.frombuffer(raw[off: off + 4 * nt], dtype=np.int32); off += 4 * nt
+    rough = np.frombuffer(raw[off: off + 8 * nm], dtype=np.float64)
+    obj = ingest.parse_obj(text)
+    want = ingest.face_roughness_from_map(obj, img)
+    assert nt == len(want) and 1 < nm <= 766
+    assert np.array_equal(rough[ids].astype(np.float32), want)

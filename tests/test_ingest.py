@@ -65,3 +65,29 @@ def test_parse_obj_errors():
         ingest.parse_obj("v 0 0 0\nf 1 2 3\n")
     with pytest.raises(ingest.ObjError):
         ingest.parse_obj("v 0 0\n")
+
+
+def test_roughness_map_gives_a_material_table_like_the_reference_builders():
+    """scene.h:372-378: each Triangle gets roughness (r1 + r2 + r3) / (3 * 255), r_k the roughness-map byte at
+    int(u * int(W-1) + v * int(H-1) * (W-1)) for the ORIGINAL texcoords of its corners.  The mesh carries one material per
+    distinct value (at most 766) and a per-triangle index."""
+    from distraytracer_b200 import abi
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, size=(13, 17), dtype=np.uint8)              # a grey JPEG decodes to one channel
+    obj = ingest.parse_obj(CUBE_FACE.replace("vt 2.25 0\n", "vt 0.75 0\n").replace("vt 2.25 0.5", "vt 0.75 0.5"))
+    fr = ingest.face_roughness_from_map(obj, img)
+    flat, w, h = img.reshape(-1), 17, 13
+    for t, tri in enumerate(obj["t_indices"]):
+        r = [np.float32(flat[int(float(obj["texcoords"][k][0]) * int(w - 1) + float(obj["texcoords"][k][1]) * int(h - 1) * (w - 1))]) for k in tri]
+        assert fr[t] == np.float32((r[0] + r[1] + r[2]) / np.float32(3 * 255))
+    mat = scenes.mesh_material(model=abi.MODEL_OREN_NAYAR)
+    mesh = ingest.mesh_from_obj(obj, mat, face_roughness=fr)
+    assert len(mesh["materials"]) == len(np.unique(fr)) <= 766
+    got = np.array([mesh["materials"][i].roughness for i in mesh["material_ids"]], dtype=np.float32)
+    assert np.array_equal(got, fr)
+    assert all(m.model == abi.MODEL_OREN_NAYAR and m.type == mat.type for m in mesh["materials"])
+    with pytest.raises(ingest.ObjError):
+        ingest.face_roughness_from_map(ingest.parse_obj(CUBE_FACE), img[:1, :2])   # texcoord 2.25 indexes past a 1x2 map (the reference reads out of bounds)
+    # the flat list of Triangle primitives the oracle consumes carries the same per-face roughness
+    prims = scenes.mesh_to_prims(mesh)
+    assert np.array_equal(np.array([p.roughness for p in prims], dtype=np.float32), fr)
