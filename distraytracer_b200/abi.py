@@ -23,7 +23,7 @@ MAT_NONE, MAT_GLASS, MAT_STEEL, MAT_ALUMINUM, MAT_WATER, MAT_LINOLEUM = range(6)
 # drt_model
 MODEL_LAMBERT, MODEL_OREN_NAYAR, MODEL_COOK_TORRANCE, MODEL_RAW = range(4)
 # drt_prim_flags
-FLAG_LIGHT, FLAG_MOTION, FLAG_TEXTURE, FLAG_GLOSSY, FLAG_MESH, FLAG_UV_VERTS = (1 << i for i in range(6))
+FLAG_LIGHT, FLAG_MOTION, FLAG_TEXTURE, FLAG_GLOSSY, FLAG_MESH, FLAG_UV_VERTS, FLAG_VERTEX_MOTION = (1 << i for i in range(7))
 # drt_light_type
 LIGHT_POINT, LIGHT_SPHERE, LIGHT_RECT = range(3)
 # drt_sample_mode / drt_blur_mode
@@ -49,7 +49,7 @@ class Prim(C.Structure):
         ("c1", D3), ("c2", D3), ("uvA", D2), ("uvB", D2), ("uvC", D2), ("mesh_normal", D3),
         ("S", C.c_double), ("borderwidth", C.c_double), ("color1", D3), ("color2", D3),
         ("hole", D3 * 4), ("velocity", D3),
-        ("n_holes", C.c_int32), ("pad_", C.c_int32), ("holes", Hole * MAX_HOLES),
+        ("n_holes", C.c_int32), ("pad_", C.c_int32), ("holes", Hole * MAX_HOLES), ("velocity2", D3),
     ]
 
 

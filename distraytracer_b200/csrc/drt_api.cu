@@ -37,6 +37,7 @@ template <typename R> Vec<R> cv(const D3& v) { return mk<R>((R)v.x, (R)v.y, (R)v
 void f3(float* o, const double* p) { o[0] = (float)p[0]; o[1] = (float)p[1]; o[2] = (float)p[2]; }
 
 void rows3x4(double* out, const D3& r0, const D3& r1, const D3& r2, const D3& eye);
+#define DRT_SWEPT_FRAMES 1   // the slab-filter boxes of moving geoms cover time offsets up to this many frames
 struct RectD { D3 A, nrm, e1, e2; double len1, len2; };
 RectD makeRect(const D3& A, const D3& B, const D3& C, const D3& D) {
   RectD r;
@@ -142,6 +143,8 @@ int flatten(const drt_prim* prims, int n_prims, const drt_light* lights, int n_l
     const drt_prim& p = prims[i];
     if (p.type < 0 || p.type >= DRT_PRIM_TYPE_COUNT)
       return fail(DRT_ERR_UNSUPPORTED, "primitive " + std::to_string(i) + ": unsupported type " + std::to_string(p.type));
+    if ((p.flags & DRT_FLAG_VERTEX_MOTION) && p.type != DRT_PRIM_CYLINDER)
+      return fail(DRT_ERR_UNSUPPORTED, "primitive " + std::to_string(i) + ": DRT_FLAG_VERTEX_MOTION is for cylinders only");
     if ((p.flags & DRT_FLAG_TEXTURE) && (p.type == DRT_PRIM_SPHERE || p.type == DRT_PRIM_CYLINDER))
       return fail(DRT_ERR_UNSUPPORTED, "textured Sphere/Cylinder: GeoPrimitive::getUV has no body (geometry.h:36)");
     if ((p.flags & DRT_FLAG_TEXTURE) && (p.tex_frame < 0 || p.tex_frame >= n_textures))
@@ -179,8 +182,12 @@ int flatten(const drt_prim* prims, int n_prims, const drt_light* lights, int n_l
         D3 axis = normalized(c2 - c1);                                   // geometry.cpp:231
         q.pA = cv<R>(c1); q.pG = cv<R>(axis); q.axis_norm = (float)norm(axis);
         if (p.type == DRT_PRIM_CHECKER_CYLINDER) objMatrix<R>(q.objM, axis, c1);
+        if ((p.flags & DRT_FLAG_VERTEX_MOTION) && p.type != DRT_PRIM_CYLINDER)
+          return fail(DRT_ERR_UNSUPPORTED, "DRT_FLAG_VERTEX_MOTION: cylinders only");
+        q.pC2 = cv<R>(c2); q.vel2 = cv<R>(V(p.velocity2));
         Geom<R> g; memset(&g, 0, sizeof(g));
         g.type = G_CYL; g.owner = i; g.p0 = cv<R>(c1); g.p1 = cv<R>(c2); g.p2 = cv<R>(axis); g.f0 = (float)p.radius; g.vel = cv<R>(vel);
+        if (p.flags & DRT_FLAG_VERTEX_MOTION) { g.flags |= GF_VERTEX_MOTION; g.vel2 = cv<R>(V(p.velocity2)); }
         { const D3 pts[2] = {c1, c2}; setBounds(g, pts, 2, (double)(float)p.radius); }
         hs.geoms.push_back(g);
         break; }
@@ -270,6 +277,22 @@ int flatten(const drt_prim* prims, int n_prims, const drt_light* lights, int n_l
     hs.prims[i] = q;
   }
   geom_start[n_prims] = (int)hs.geoms.size();
+  // DRT_BLUR_VELOCITY: the filter boxes of moving geoms cover their whole path over one frame (time offsets lie in
+  // [0, frame_range), frame_range <= DRT_SWEPT_FRAMES) -- every point of a translated shape, and of a cylinder whose end
+  // points move linearly, stays inside the union of its boxes at the two ends of the path -- so re-traces keep the filter
+  for (Geom<R>& g : hs.geoms) {
+    if (g.type == G_BOX) continue;
+    const drt_prim& p = prims[g.owner];
+    const D3 v1 = V(p.velocity), v2 = (p.flags & DRT_FLAG_VERTEX_MOTION) ? V(p.velocity2) : v1;
+    if (!(dot(v1, v1) > 0) && !(dot(v2, v2) > 0)) continue;
+    const double T = DRT_SWEPT_FRAMES;
+    for (int a = 0; a < 3; a++) {
+      const double d1 = (&v1.x)[a] * T, d2 = (&v2.x)[a] * T;
+      const double lo = std::min(0.0, std::min(d1, d2)), hi = std::max(0.0, std::max(d1, d2));
+      (&g.blo.x)[a] = std::nextafterf((float)((double)(&g.blo.x)[a] + lo * (1 + 1e-6) - 1e-6), -INFINITY);
+      (&g.bhi.x)[a] = std::nextafterf((float)((double)(&g.bhi.x)[a] + hi * (1 + 1e-6) + 1e-6), INFINITY);
+    }
+  }
   hs.nodes.clear();
   for (const RefNode& rn : bvh.nodes) {
     NodeD<R> nd; memset(&nd, 0, sizeof(nd));
@@ -558,6 +581,7 @@ void fillParams(Params<R>& P, const drt_scene* s, const DevScene<R>& ds, const d
   P.frame = st.frame; P.frame_prism = st.frame_prism; P.frame_blur = st.frame_blur; P.frame_cloud = st.frame_cloud;
   P.move_per_frame = st.move_per_frame; P.accel_t = st.accel_t; P.refr_air = st.refr_air; P.refr_glass = st.refr_glass;
   P.phong = st.phong; P.seed = st.seed; P.blur_mode = st.blur_mode;
+  P.swept_cull = (st.blur_mode == DRT_BLUR_VELOCITY && st.frame_range <= DRT_SWEPT_FRAMES) ? 1 : 0;
   P.sun = cv<R>(normalized(V(st.sundir)));
   f3(P.sun_outer, st.sun_outer); f3(P.sun_inner, st.sun_inner); f3(P.sun_core, st.sun_core);
   f3(P.bluesky, st.bluesky); f3(P.redsky, st.redsky);
@@ -1185,9 +1209,11 @@ int drt_scene_pose_skeleton(drt_scene* s, const drt_skeleton* skel, int32_t fram
     for (int i = 0; i < 3; i++) {
       p.c1[i] = c1[i]; p.c2[i] = c2[i];
       p.center[i] = (c1[i] + c2[i]) / 2;
-      p.velocity[i] = set_velocity ? ((n1[i] + n2[i]) - (c1[i] + c2[i])) / 2 : 0.0;
+      if (set_velocity == 2) { p.velocity[i] = n1[i] - c1[i]; p.velocity2[i] = n2[i] - c2[i]; }   // each end point to its own next pose
+      else { p.velocity[i] = set_velocity ? ((n1[i] + n2[i]) - (c1[i] + c2[i])) / 2 : 0.0; p.velocity2[i] = 0.0; }
     }
     if (set_velocity) p.flags |= DRT_FLAG_MOTION;
+    if (set_velocity == 2) p.flags |= DRT_FLAG_VERTEX_MOTION; else p.flags &= ~DRT_FLAG_VERTEX_MOTION;
   }
   const int rc = flattenAndUpload(s);
   if (rc) s->prims = before;

@@ -75,7 +75,8 @@ enum GeomType { G_SPHERE = 0, G_CYL = 1, G_TRI = 2, G_RECT = 3, G_CHECKER = 4, G
 enum GeomFlags {
   GF_NAME_RECTANGLE = 1,  // moves in y during reference-mode motion blur (render_final_project.cpp:1116)
   GF_HAS_HOLE = 2,        // next record is this checkerboard's hole rectangle
-  GF_MESH = 4             // Triangle::mesh (inside test against mesh_normal)
+  GF_MESH = 4,            // Triangle::mesh (inside test against mesh_normal)
+  GF_VERTEX_MOTION = 8    // cylinder whose end points move independently (DRT_FLAG_VERTEX_MOTION): p1 moves by vel2
 };
 
 template <typename R>
@@ -92,6 +93,7 @@ struct alignas(16) Geom {
   Vec<R> p0, p1, p2, p3;
   float f0, f1, f2, f3;
   Vec<R> vel;   // DRT_BLUR_VELOCITY displacement per unit time
+  Vec<R> vel2;  // GF_VERTEX_MOTION: displacement of the cylinder's second end point per unit time
   R len1, len2, pad_;
   float4 blo, bhi;   // padded single-precision bounds for the slab filter
   int leaf;          // reference BVH leaf holding this geom
@@ -143,6 +145,7 @@ struct alignas(16) PrimD {
   // emissive (render_final_project.cpp:775-789)
   Vec<R> center, eA, eB, eC, eD; R e_den;
   Vec<R> vel;
+  Vec<R> pC2, vel2;        // DRT_FLAG_VERTEX_MOTION cylinders: second end point and its velocity
   // slab-box prisms (types 8-10): objM above holds cob * origin (geometry.cpp:975-984)
   float height; int n_holes;
   HoleD<R> holes[4];
@@ -181,6 +184,7 @@ struct Params {
   int brdf_samples, blur_samples, frame_range, max_depth;
   int reflect, nogloss, perlin_cloud, cloud_only;
   int frame, frame_prism, frame_blur, frame_cloud;
+  int swept_cull;           // velocity-mode re-traces may use the slab filter: its boxes cover the motion over frame_range
   float move_per_frame, accel_t, refr_air, refr_glass, phong;
   uint32_t seed;
   int blur_mode;

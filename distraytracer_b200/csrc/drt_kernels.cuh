@@ -459,7 +459,11 @@ __device__ inline bool geomIntersect(const Params<R>& P, const Geom<R>& g, int g
     } else if (type == G_CYL) {  // Cylinder::intersect geometry.cpp:242-295
       const float eps = 1e-3f;
       Vec<R> c1 = shiftPoint<R, F>(mv, g.flags, g.vel, g.p0), c2 = shiftPoint<R, F>(mv, g.flags, g.vel, g.p1);
-      const Vec<R> axis = g.p2;
+      Vec<R> axis = g.p2;
+      if ((F & FT_VEL) && (g.flags & GF_VERTEX_MOTION) && mv.velocity_mode) {   // two poses: the axis follows the end points
+        c2 = g.p1 + g.vel2 * mv.time;
+        axis = normalized(c2 - c1);
+      }
       Vec<R> ray_a_proj = ray - dot(ray, axis) * axis;
       Vec<R> sc = start - c1;
       Vec<R> constant = sc - dot(sc, axis) * axis;
@@ -637,7 +641,7 @@ __device__ inline void closestHit(const Params<R>& P, const float4* __restrict__
     const float ix = 1.0f / (float)ray.x, iy = 1.0f / (float)ray.y, iz = 1.0f / (float)ray.z;
     const float ox = -(float)start.x * ix, oy = -(float)start.y * iy, oz = -(float)start.z * iz;   // slabMayHit's hoisted terms
     const float serr = 4e-7f * (fabsf(ox) + fabsf(oy) + fabsf(oz));
-    const bool cull = !((F & FT_VEL) && mv.velocity_mode);
+    const bool cull = !((F & FT_VEL) && mv.velocity_mode) || P.swept_cull;
     const bool smem = !(F & FT_BIG) || P.n_geoms <= DRT_SMEM_GEOMS;     // CTA-uniform: the table is staged in shared memory
     const SlabRay sr = slabRay(ix, iy, iz, ox, oy, oz, FLT_MAX);
     const int n = P.n_geoms;
@@ -727,7 +731,11 @@ __device__ inline bool geomShadow(const Params<R>& P, const Geom<R>& g, int gi, 
     } else if (type == G_CYL) {  // geometry.cpp:368-417
       const float eps = 1e-3f;
       Vec<R> c1 = shiftPoint<R, F>(mv, g.flags, g.vel, g.p0), c2 = shiftPoint<R, F>(mv, g.flags, g.vel, g.p1);
-      const Vec<R> axis = g.p2;
+      Vec<R> axis = g.p2;
+      if ((F & FT_VEL) && (g.flags & GF_VERTEX_MOTION) && mv.velocity_mode) {   // two poses: the axis follows the end points
+        c2 = g.p1 + g.vel2 * mv.time;
+        axis = normalized(c2 - c1);
+      }
       Vec<R> ray_a_proj = ray - dot(ray, axis) * axis;
       Vec<R> sc = start - c1;
       Vec<R> constant = sc - dot(sc, axis) * axis;
@@ -779,7 +787,7 @@ __device__ inline bool anyHit(const Params<R>& P, const float4* __restrict__ gb,
   if ((!(F & FT_REFBLUR) || mv.val == 0.0f) && !DRT_FORCE_TREE) {
     const float ix = 1.0f / (float)ray.x, iy = 1.0f / (float)ray.y, iz = 1.0f / (float)ray.z;
     const float ox = -(float)start.x * ix, oy = -(float)start.y * iy, oz = -(float)start.z * iz;   // slabMayHit's hoisted terms
-    const bool cull = !((F & FT_VEL) && mv.velocity_mode);
+    const bool cull = !((F & FT_VEL) && mv.velocity_mode) || P.swept_cull;
     // distance by which the reference's gather origin runs ahead of the test origin
     const float gather_lead = t_max * 1e-3f;
     const int n = P.n_geoms;
@@ -1141,8 +1149,11 @@ __device__ void shadeA(const Params<R>& P, const Task<R>& T, const HitRec& h, Ta
       Vec<R> nn = isectP - shiftPoint<R, F>(mv, 0, pr.vel, pr.pA);
       normal = nn / norm(nn);
     } else if (pr.type == 1 || pr.type == 7) {                          // Cylinder geometry.cpp:419-425
-      Vec<R> pc = isectP - shiftPoint<R, F>(mv, 0, pr.vel, pr.pA);
-      normal = normalized(pc - dot(pc, pr.pG) * pr.pG);
+      const Vec<R> c1 = shiftPoint<R, F>(mv, 0, pr.vel, pr.pA);
+      Vec<R> axis = pr.pG;
+      if ((F & FT_VEL) && (pr.flags & 64) && mv.velocity_mode) axis = normalized((pr.pC2 + pr.vel2 * mv.time) - c1);   // DRT_FLAG_VERTEX_MOTION
+      Vec<R> pc = isectP - c1;
+      normal = normalized(pc - dot(pc, axis) * axis);
     } else if ((F & FT_BOX) && pr.type == 9) {                          // RectPrismWithCylinder geometry.cpp:1796-1821 (lastHit is -1 by now)
       const float eps = 1e-3f;
       const Vec<R> pa = isectP - shiftPoint<R, F>(mv, 0, pr.vel, pr.pA);

@@ -127,9 +127,10 @@ class DeviceScene:
         _check(lib().drt_scene_update_lights(self.handle, arr, len(lights)))
 
     def pose_skeleton(self, skeleton, frame, first_prim, drop_y=0.0, set_velocity=True):
-        """drt_scene_pose_skeleton: bone cylinders prims[first_prim...] take the pose of mocap frame `frame`."""
+        """drt_scene_pose_skeleton: bone cylinders prims[first_prim...] take the pose of mocap frame `frame`.
+        set_velocity: 0 / False static, 1 / True one translation per bone, 2 both end points to their own next pose."""
         _check(lib().drt_scene_pose_skeleton(self.handle, skeleton.handle, int(frame), int(first_prim), float(drop_y),
-                                             int(bool(set_velocity))))
+                                             int(set_velocity)))
 
     def _tile(self, settings, tile):
         if tile is None:

@@ -177,10 +177,11 @@ def config3(xres=1920, yres=1080, spp=256):
     return Scene(prims, scene.lights, scene.textures), settings
 
 
-def config4_frame(frame, xres=1920, yres=1080, spp=16, bones=None):
+def config4_frame(frame, xres=1920, yres=1080, spp=16, bones=None, two_pose=False):
     """BASELINE config 4: mocap skeleton (29-30 bone cylinders, scene.h:637-659) over a
     checkerboard floor with two sphere lights (buildSceneChkpt2 layout, scene.h:3557-3666),
-    bones flagged `motion` and given the velocity to their pose one frame later."""
+    bones flagged `motion` and given the velocity to their pose one frame later: one translation per bone, or
+    (two_pose) each end point to its own next position (DRT_FLAG_VERTEX_MOTION)."""
     scene, settings, _ = load_fixture(data_path("chkpt2_mocap_scene.npz"))
     if bones is None:
         bones = np.load(data_path("mocap_bones_0_119.npy"))
@@ -193,7 +194,11 @@ def config4_frame(frame, xres=1920, yres=1080, spp=16, bones=None):
             c1, c2 = bones[f0, k, 0], bones[f0, k, 1]
             n1, n2 = bones[f1, k, 0], bones[f1, k, 1]
             _v(q.c1, c1); _v(q.c2, c2); _v(q.center, (c1 + c2) / 2)
-            _v(q.velocity, ((n1 + n2) - (c1 + c2)) / 2)
+            if two_pose:
+                _v(q.velocity, n1 - c1); _v(q.velocity2, n2 - c2)
+                q.flags |= abi.FLAG_VERTEX_MOTION
+            else:
+                _v(q.velocity, ((n1 + n2) - (c1 + c2)) / 2)
             q.flags |= abi.FLAG_MOTION
             k += 1
         prims.append(q)

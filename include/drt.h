@@ -112,7 +112,10 @@ enum drt_prim_flags {
   DRT_FLAG_TEXTURE = 1 << 2,  /* GeoPrimitive::texture (geometry.h:48)          */
   DRT_FLAG_GLOSSY = 1 << 3,   /* Reflectance::glossy   (geometry.h:23)          */
   DRT_FLAG_MESH = 1 << 4,     /* GeoPrimitive::mesh    (geometry.h:56)          */
-  DRT_FLAG_UV_VERTS = 1 << 5  /* GeoPrimitive::uv_verts(geometry.h:42)          */
+  DRT_FLAG_UV_VERTS = 1 << 5, /* GeoPrimitive::uv_verts(geometry.h:42)          */
+  DRT_FLAG_VERTEX_MOTION = 1 << 6 /* DRT_BLUR_VELOCITY, cylinders only: the two end points move independently --
+                               * c1 by `velocity`, c2 by `velocity2` -- and the axis is re-derived per time sample: a
+                               * bone between its poses at frame and frame + 1 */
 };
 
 /* One GeoPrimitive, flattened.  Doubles because the reference's host surface is
@@ -150,6 +153,7 @@ typedef struct drt_prim {
   int32_t n_holes;
   int32_t pad_;
   drt_hole holes[DRT_MAX_HOLES];
+  double velocity2[3];           /* DRT_FLAG_VERTEX_MOTION: velocity of c2 (`velocity` is then c1's) */
 } drt_prim;
 
 typedef enum drt_light_type {
@@ -346,8 +350,11 @@ int drt_skeleton_bones(const drt_skeleton* skel, int32_t frame0, int32_t n_frame
 /* Re-pose the n_cylinders DRT_PRIM_CYLINDER primitives prims[first_prim ...] of `scene` to mocap
  * frame `frame` (clamped to the last frame like scene.h:117-121; negative is an error like
  * scene.h:111-115) and re-upload the scene.  Every end point is lowered by `drop_y`
- * (scene.h:646-650 drops the figure by frame-frame_cloud).  With set_velocity != 0 each
- * cylinder also gets drt_prim.velocity = its displacement to frame+1 (DRT_BLUR_VELOCITY). */
+ * (scene.h:646-650 drops the figure by frame-frame_cloud).  set_velocity (DRT_BLUR_VELOCITY):
+ *   0  static bones;
+ *   1  one translation per bone: velocity = displacement of the bone's midpoint to frame + 1;
+ *   2  two poses: c1 and c2 each move to their own position at frame + 1 (DRT_FLAG_VERTEX_MOTION), so a rotating
+ *      bone sweeps the pose in between. */
 int drt_scene_pose_skeleton(drt_scene* scene, const drt_skeleton* skel, int32_t frame, int32_t first_prim,
                             double drop_y, int32_t set_velocity);
 void drt_skeleton_destroy(drt_skeleton* skel);

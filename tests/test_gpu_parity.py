@@ -122,7 +122,7 @@ def test_scene_update_and_errors(oracle_lib):
     assert e.value.code == abi.ERR_SCENE
 
 
-@pytest.mark.parametrize("cfg", ["config1", "config2", "config3", "config4"])
+@pytest.mark.parametrize("cfg", ["config1", "config2", "config3", "config4", "config4_two_pose", "config4_long_shutter"])
 def test_cuda_matches_oracle_on_baseline_configs(oracle_lib, cfg):
     """The BASELINE.json workloads at reduced resolution / spp (the oracle finishes in seconds):
     C2 exercises DOF + glossy floor + rectangle-light soft shadows + glass refraction (NaN
@@ -136,8 +136,17 @@ def test_cuda_matches_oracle_on_baseline_configs(oracle_lib, cfg):
         scene, s = scenes.config2(240, 135, 16)
     elif cfg == "config3":
         scene, s = scenes.config3(96, 54, 4)
-    else:
+    elif cfg == "config4":
         scene, s = scenes.config4_frame(37, 160, 90, 4)
+    elif cfg == "config4_two_pose":
+        # every bone between its poses at frame and frame + 1: end points on their own paths, axis re-derived per time
+        # sample (DRT_FLAG_VERTEX_MOTION); the slab filter keeps culling through the swept boxes
+        scene, s = scenes.config4_frame(37, 160, 90, 4, two_pose=True)
+        s.blur_samples = 3
+    else:
+        # a shutter longer than the swept boxes cover (frame_range 3 > 1): re-traces fall back to testing every geom
+        scene, s = scenes.config4_frame(37, 160, 90, 4, two_pose=True)
+        s.frame_range = 3
     want, _, _, _ = Oracle(scene).render(s, mode=ORACLE_KEYED)
     got, _ = _gpu(scene).render_float(s)
     st = compare(want, got)

@@ -102,6 +102,15 @@ def test_cuda_posed_scene_renders_like_the_reference_bones(oracle_lib):
         dev.pose_skeleton(skel, frame, first, 0.0, True)
         got, _ = dev.render_float(st)
         assert np.array_equal(np.nan_to_num(got), np.nan_to_num(want)), frame
+    # two poses (set_velocity 2): each end point heads for its own position at frame + 1
+    two, st2 = scenes.config4_frame(57, 160, 90, 4, two_pose=True)
+    want2, _ = runtime.DeviceScene(two, 0).render_float(st2)
+    dev.pose_skeleton(skel, 57, first, 0.0, 2)
+    got2, _ = dev.render_float(st2)
+    assert np.array_equal(np.nan_to_num(got2), np.nan_to_num(want2))
+    dev.pose_skeleton(skel, 57, first, 0.0, True)
+    one2, _ = dev.render_float(st2)
+    assert not np.array_equal(np.nan_to_num(one2), np.nan_to_num(got2))    # rotating bones sweep differently than translated ones
     # clamped past the clip, rejected below it and when the target primitives are not cylinders
     dev.pose_skeleton(skel, 10_000, first)
     a, _ = dev.render_float(st)
