@@ -301,7 +301,7 @@ def run_configs(local):
     def c4():
         n_frames, xres, yres, spp = 120, 1920, 1080, 16
         t0 = time.perf_counter()
-        skel = runtime.DeviceSkeleton(scenes.data_path("mocap_90.asf"), scenes.data_path("mocap_90_16_first121.amc"), device=local)
+        skel = runtime.DeviceSkeleton(scenes.data_path("mocap_90.asf"), scenes.data_path("mocap_90_16_frames880_1000.amc"), device=local)
         t_load = time.perf_counter() - t0
         scene, st = scenes.config4_frame(0, xres, yres, spp)
         first = next(i for i, p in enumerate(scene.prims) if p.type == abi.PRIM_CYLINDER)

@@ -184,7 +184,7 @@ def config4_frame(frame, xres=1920, yres=1080, spp=16, bones=None, two_pose=Fals
     (two_pose) each end point to its own next position (DRT_FLAG_VERTEX_MOTION)."""
     scene, settings, _ = load_fixture(data_path("chkpt2_mocap_scene.npz"))
     if bones is None:
-        bones = np.load(data_path("mocap_bones_0_119.npy"))
+        bones = np.load(data_path("mocap_bones_880_999.npy"))
     f0 = int(frame) % bones.shape[0]
     f1 = min(f0 + 1, bones.shape[0] - 1)
     prims, k = [], 0

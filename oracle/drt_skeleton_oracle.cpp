@@ -19,7 +19,7 @@
 // p0+(p1+p2) for 3-vectors).
 //
 // Pin: bit-identical to the compiled reference (oracle/_ref, drtref_mocap_bones) on
-// tests/golden/mocap_bones_0_119.npy (frames 0..119 of 90.asf / 90_16_v3.amc) and, when
+// tests/golden/mocap_bones_880_999.npy (frames 0..119 of 90.asf / 90_16_v3.amc) and, when
 // the reference tree is present, on frames sampled over the whole clip
 // (tests/test_skeleton.py).
 #include <cmath>

@@ -28,6 +28,7 @@ from distraytracer_b200.scene import save_fixture  # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
 W, H, SEED = 160, 120, 7
+MOCAP_START = 880
 
 # (case name, reference builder, frame, antialias_samples, overrides)
 CASES = [
@@ -101,6 +102,8 @@ PRISM_CASES = [("prism_box", "PRIM_RECTPRISM", (-3, 2.5, 5)), ("prism_cyl", "PRI
 
 def main():
     r = Ref(mocap=True)
+    if os.environ.get("GOLDEN_ONLY_MOCAP"):
+        return mocap_and_cloud(r)
     for case, builder, frame, aa, kw in CASES:
         if os.environ.get("GOLDEN_ONLY_PRISMS") and case != "prismcyl":
             continue
@@ -133,10 +136,15 @@ def main():
         print(f"{case:24s} prims={len(scene.prims):3d} lights={len(scene.lights)} aborted={int(aborted.sum())} mean={img.mean():.2f} ref {sec:.2f}s")
     if os.environ.get("GOLDEN_ONLY_PRISMS"):
         return
+    mocap_and_cloud(r)
 
-    # mocap bone end points for frames 0..119 (BASELINE config 4), scene.h:637-659
-    bones = np.stack([r.mocap_bones(f) for f in range(120)])
-    np.save(os.path.join(OUT, "mocap_bones_0_119.npy"), bones.astype(np.float64))
+
+def mocap_and_cloud(r):
+
+    # mocap bone end points (BASELINE config 4), scene.h:637-659.  The clip holds its first pose for 560 frames; the window
+    # MOCAP_START .. MOCAP_START + 120 is the middle of the acrobatic sequence, where every bone moves.
+    bones = np.stack([r.mocap_bones(MOCAP_START + f) for f in range(120)])
+    np.save(os.path.join(OUT, "mocap_bones_880_999.npy"), bones.astype(np.float64))
     print("mocap bones", bones.shape)
     # the clip itself for the ASF/AMC ingest tests: the skeleton file and the first 121 frames of the motion
     # (3 header lines + 121 x 30 lines), copied as DATA fixtures
@@ -147,8 +155,13 @@ def main():
         amc_lines = f.read().split(b"\n")
     with open(os.path.join(OUT, "mocap_90.asf"), "wb") as f:
         f.write(asf)
-    with open(os.path.join(OUT, "mocap_90_16_first121.amc"), "wb") as f:
-        f.write(b"\n".join(amc_lines[:3 + 121 * 30]) + b"\n")
+    # the same 121 frames, renumbered from 1 (3 header lines, then a frame-number line + 29 bone lines per frame)
+    window = amc_lines[3 + MOCAP_START * 30: 3 + (MOCAP_START + 121) * 30]
+    for k in range(121):
+        assert int(window[k * 30]) == MOCAP_START + k + 1
+        window[k * 30] = str(k + 1).encode()
+    with open(os.path.join(OUT, "mocap_90_16_frames880_1000.amc"), "wb") as f:
+        f.write(b"\n".join(amc_lines[:3] + window) + b"\n")
 
     # value-noise known answers (noise.h) through the reference's renderImageCloud
     r.reset()

@@ -100,7 +100,7 @@ def test_scene_update_and_errors(oracle_lib):
     from oracle.harness import Oracle, ORACLE_KEYED, compare
     from distraytracer_b200.scene import Scene
     scene, settings, _ = load_case("chkpt2_mocap")
-    bones = np.load(GOLDEN + "/mocap_bones_0_119.npy")
+    bones = np.load(GOLDEN + "/mocap_bones_880_999.npy")
     dev = _gpu(scene)
     prims = [abi.copy_struct(p) for p in scene.prims]
     k = 0

@@ -112,7 +112,7 @@ def test_mocap_through_host_mirror(host_bin, tmp_path):
     from distraytracer_b200 import abi
     from oracle.harness import read_ppm
     from conftest import GOLDEN
-    clip = [os.path.join(GOLDEN, "mocap_90.asf"), os.path.join(GOLDEN, "mocap_90_16_first121.amc")]
+    clip = [os.path.join(GOLDEN, "mocap_90.asf"), os.path.join(GOLDEN, "mocap_90_16_frames880_1000.amc")]
     out = str(tmp_path / "dump.bin")
     subprocess.check_call([host_bin, "dump", "mocap", out] + clip)
     raw = open(out, "rb").read()

@@ -28,7 +28,7 @@ def _run_dir(tmp_path):
     for f in os.listdir(os.path.join(GOLDEN, "textures")):
         shutil.copyfile(os.path.join(GOLDEN, "textures", f), tmp_path / "textures" / f)
     shutil.copyfile(os.path.join(GOLDEN, "mocap_90.asf"), tmp_path / "90.asf")
-    shutil.copyfile(os.path.join(GOLDEN, "mocap_90_16_first121.amc"), tmp_path / "90_16_v3.amc")
+    shutil.copyfile(os.path.join(GOLDEN, "mocap_90_16_frames880_1000.amc"), tmp_path / "90_16_v3.amc")
     for d in ("checkertexture", "prismcyl", "reflectance"):
         os.makedirs(tmp_path / "test_frames" / d)
     return str(tmp_path)

@@ -1,7 +1,7 @@
 """ASF/AMC mocap ingest + forward kinematics (BASELINE config 4).
 
 CPU: the oracle's restatement (oracle/drt_skeleton_oracle.cpp) is pinned bit-for-bit on the bone end points
-the compiled reference produced (tests/golden/mocap_bones_0_119.npy, written by make_golden.py through
+the compiled reference produced (tests/golden/mocap_bones_880_999.npy, written by make_golden.py through
 drtref_mocap_bones) and, where the reference tree is present, on frames over the whole clip.
 GPU: the device table of drt_skeleton_create (kernel skeleton_fk) is bit-identical to the oracle, and a scene
 re-posed from it renders the same image as one given the reference's bones."""
@@ -13,7 +13,7 @@ import pytest
 from conftest import GOLDEN
 
 ASF = os.path.join(GOLDEN, "mocap_90.asf")
-AMC = os.path.join(GOLDEN, "mocap_90_16_first121.amc")
+AMC = os.path.join(GOLDEN, "mocap_90_16_frames880_1000.amc")
 
 
 def _clip():
@@ -28,7 +28,7 @@ def test_oracle_fk_is_pinned_on_the_reference_bones(oracle_lib):
     from oracle.harness import SkeletonOracle
     sk = SkeletonOracle(*_clip())
     assert (sk.n_cylinders, sk.n_frames) == (30, 121)
-    gold = np.load(os.path.join(GOLDEN, "mocap_bones_0_119.npy"))
+    gold = np.load(os.path.join(GOLDEN, "mocap_bones_880_999.npy"))
     got = np.stack([sk.bones(f) for f in range(120)])
     assert np.array_equal(got, gold)                      # bit-exact, all 120 x 30 x 6 doubles
     # past the clip the reference clamps to the last frame (scene.h:117-121); negative frames are fatal (:111-115)
@@ -73,7 +73,7 @@ def test_cuda_fk_table_is_bit_identical_to_the_oracle(oracle_lib):
     got = dev.bones()
     want = np.stack([orc.bones(f) for f in range(orc.n_frames)])
     assert np.array_equal(got, want)
-    assert np.array_equal(got[:120], np.load(os.path.join(GOLDEN, "mocap_bones_0_119.npy")))
+    assert np.array_equal(got[:120], np.load(os.path.join(GOLDEN, "mocap_bones_880_999.npy")))
     # file-path entry point, and a sub-range read
     dev2 = runtime.DeviceSkeleton(ASF, AMC)
     assert np.array_equal(dev2.bones(7, 3), want[7:10])

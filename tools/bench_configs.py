@@ -36,7 +36,7 @@ def mocap_video(n_frames=120, xres=1920, yres=1080, spp=16):
     import threading
     golden = os.path.join(ROOT, "tests", "golden")
     t0 = time.time()
-    skel = runtime.DeviceSkeleton(os.path.join(golden, "mocap_90.asf"), os.path.join(golden, "mocap_90_16_first121.amc"))
+    skel = runtime.DeviceSkeleton(os.path.join(golden, "mocap_90.asf"), os.path.join(golden, "mocap_90_16_frames880_1000.amc"))
     t_load = time.time() - t0
     scene, st0 = scenes.config4_frame(0, xres, yres, spp)
     first = next(i for i, p in enumerate(scene.prims) if p.type == abi.PRIM_CYLINDER)

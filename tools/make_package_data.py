@@ -10,6 +10,6 @@ os.makedirs(D, exist_ok=True)
 for name in ("checkertexture", "reflectance", "chkpt2_mocap"):
     scene, settings, _ = load_fixture(os.path.join(G, name + ".npz"))
     save_fixture(os.path.join(D, name + "_scene.npz"), scene, settings)
-for f in ("mocap_90.asf", "mocap_90_16_first121.amc", "mocap_bones_0_119.npy"):
+for f in ("mocap_90.asf", "mocap_90_16_frames880_1000.amc", "mocap_bones_880_999.npy"):
     shutil.copyfile(os.path.join(G, f), os.path.join(D, f))
 print(sorted(os.listdir(D)))
