@@ -45,7 +45,7 @@ CASES = [
     ("staircase", "staircase", 5, 1, {"aperture": 0.0}),
     ("rectprism", "rectprism", 13, 1, {"aperture": 0.0}),
     ("checkercylinder", "checkercylinder", 0, 4, {"aperture": 0.0}),
-    ("chkpt2_mocap", "chkpt2", 30, 4, {}),                         # 29 bone cylinders + 2 sphere lights
+    ("chkpt2_mocap", "chkpt2", 910, 4, {}),                        # 29 bone cylinders + 2 sphere lights; clip frame 910 = frame 30 of the stored window
     ("boundary_mocap", "boundary", 1, 4, {"aperture": 0.0}),       # rect lights + sphere light + glossy
     ("prismcyl", "prismcyl", 7, 1, {"aperture": 0.0}),             # `./render prismcyl 7` (scene.h:3227-3263): RectPrismWithCylinder
 ]
@@ -107,6 +107,8 @@ def main():
     for case, builder, frame, aa, kw in CASES:
         if os.environ.get("GOLDEN_ONLY_PRISMS") and case != "prismcyl":
             continue
+        if os.environ.get("GOLDEN_ONLY") and case not in os.environ["GOLDEN_ONLY"].split(","):
+            continue
         r.reset()
         r.build(builder, frame)
         s = r.settings()
@@ -122,6 +124,8 @@ def main():
         print(f"{case:24s} prims={len(scene.prims):3d} lights={len(scene.lights)} tex={len(scene.textures)} "
               f"aborted={int(aborted.sum())} ref {sec:.2f}s")
 
+    if os.environ.get("GOLDEN_ONLY"):
+        return
     from distraytracer_b200 import abi
     for case, kind, eye in PRISM_CASES:
         scene = prism_scene(getattr(abi, kind))
