@@ -1974,30 +1974,48 @@ __device__ inline double interpolatedNoise3D(int ip, double x, double y, double 
   return i1 * (1 - gz) + i2 * gz;
 }
 
-__device__ inline double valueNoise3D(double x, double y, double z) {         // noise.h:124-136
-  double total = 0, frequency = 16, amplitude = 0.0625;
-  for (int i = 0; i < 4; ++i) {
-    frequency /= 2; amplitude /= 0.5;
-    total += interpolatedNoise3D(i % 10, x * frequency, y * frequency, z * frequency) * amplitude;
-  }
-  return total;
-}
-
+// skyColor / cloudColor (:146-192) for one pixel corner, evaluated by a QUAD of lanes.
+// The reference marches the ray back to front through ~200 steps (z = clouddist, z -= 0.05 in float, while z > 0); each
+// step costs one ValueNoise_3D = four octaves of InterpolatedNoise3D (64 lattice hashes each), and the compositing
+// `col = (1 - d) col + d cloud` makes the steps sequential.  With a thread per corner that is a ~5 ms serial chain, which
+// is what limits a frame shared by several GPUs (the background pass of 10^6 corners is only a couple of such chains
+// long per SM, so the last wave runs half empty).  Here lane 4q + o evaluates octave o of corner q's current step; the
+// four octaves are summed in the reference's order after a shuffle and all four lanes replay the (cheap) compositing.
+// Same arithmetic per step, a 4x shorter chain, 8 corners per warp.  `active` false: the quad only takes part in the
+// shuffles.
 template <typename R>
-__device__ void cloudColor(const Params<R>& P, const Vec<R>& ray, float frame, double (&out)[3]) {   // :146-192
-  Vec<R> rnorm = normalized(ray);
-  float sundot = clampf((float)dot(rnorm, P.sun));
-  double sky[3], col[3];
-  double p1 = pow((double)sundot, 1.0), p2 = pow((double)sundot, 2.0), p256 = pow((double)sundot, 256.0), p8 = pow((double)sundot, 8.0);
-  for (int c = 0; c < 3; c++) {
-    double cc = (0.05 * P.sun_outer[c]) * p1 + (0.1 * P.sun_inner[c]) * p2 + (0.9 * P.sun_core[c]) * p256;
-    double sk = P.bluesky[c] * (1 - 1.5 * p8) + (P.redsky[c] * 1.5) * p8;
-    sky[c] = cc + sk * (1.0 - 0.8 * (double)rnorm.y);
-    col[c] = sky[c];
+__device__ void cloudColorQuad(const Params<R>& P, const bool active, const Vec<R>& ray, float frame, double (&out)[3], int& steps) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31, octave = lane & 3, quad0 = lane & ~3;
+  double sky[3] = {0, 0, 0}, col[3] = {0, 0, 0};
+  if (active) {
+    Vec<R> rnorm = normalized(ray);
+    float sundot = clampf((float)dot(rnorm, P.sun));
+    double p1 = pow((double)sundot, 1.0), p2 = pow((double)sundot, 2.0), p256 = pow((double)sundot, 256.0), p8 = pow((double)sundot, 8.0);
+    for (int c = 0; c < 3; c++) {
+      double cc = (0.05 * P.sun_outer[c]) * p1 + (0.1 * P.sun_inner[c]) * p2 + (0.9 * P.sun_core[c]) * p256;
+      double sk = P.bluesky[c] * (1 - 1.5 * p8) + (P.redsky[c] * 1.5) * p8;
+      sky[c] = cc + sk * (1.0 - 0.8 * (double)rnorm.y);
+      col[c] = sky[c];
+    }
   }
-  for (float z = P.clouddist; z > 0; z = (float)((double)z - 0.05)) {
-    double px = (double)z * (double)ray.x, py = (double)z * (double)ray.y, pz = (double)z * (double)ray.z;
-    float noise = (float)(0.7 * valueNoise3D(px, py, pz + (double)frame));
+  // ValueNoise_3D (noise.h:124-136): frequency 8, 4, 2, 1 and amplitude 1/8, 1/4, 1/2, 1 for octaves 0..3
+  const double frequency = (double)(8 >> octave), amplitude = 0.125 * (double)(1 << octave);
+  steps = 0;
+  for (float z = P.clouddist; z > 0; z = (float)((double)z - 0.05)) {      // the same z sequence on every lane
+    double v = 0.0;
+    const double py = (double)z * (double)ray.y;
+    if (active) {
+      const double px = (double)z * (double)ray.x, pz = (double)z * (double)ray.z + (double)frame;
+      v = interpolatedNoise3D(octave, px * frequency, py * frequency, pz * frequency) * amplitude;
+    }
+    const double v0 = __shfl_sync(FULL, v, quad0), v1 = __shfl_sync(FULL, v, quad0 + 1);
+    const double v2 = __shfl_sync(FULL, v, quad0 + 2), v3 = __shfl_sync(FULL, v, quad0 + 3);
+    steps++;
+    if (!active) continue;
+    double total = 0;
+    total += v0; total += v1; total += v2; total += v3;
+    float noise = (float)(0.7 * total);
     float clouddistance = (float)((py + (double)noise) + (double)P.cloudhoff);
     if (clouddistance < 0) {
       float density = clampf(fabsf(clouddistance));
@@ -2017,13 +2035,14 @@ __device__ void cloudColor(const Params<R>& P, const Vec<R>& ray, float frame, d
   for (int c = 0; c < 3; c++) out[c] = (double)(1 + P.saturation) * col[c] - (double)P.saturation * (0.33 * s);
 }
 
-// One thread per pixel corner of the tile's (w+1)x(h+1) grid, in blocks of 128 corners.  A block is either the CTA's own
-// (blockIdx) or -- one frame on several GPUs -- claimed from a counter all devices share, the marks and colours then
-// living in the gathering device's maps (peer loads / stores).
+// One quad of lanes per pixel corner of the tile's (w+1)x(h+1) grid: a CTA of 128 threads takes a block of 32 corners.  A
+// block is either the CTA's own (blockIdx) or -- one frame on several GPUs -- claimed from a counter all devices share,
+// the marks and colours then living in the gathering device's maps (peer loads / stores).
+#define DRT_CLOUD_BLOCK 32
 template <typename R>
 __global__ void __launch_bounds__(128) cloud_corners(const __grid_constant__ Params<R> P) {
   const int gw = P.w + 1, gh = P.h + 1;
-  const int n_blocks = (gw * gh + 127) / 128;
+  const int n_blocks = (gw * gh + DRT_CLOUD_BLOCK - 1) / DRT_CLOUD_BLOCK;
   __shared__ int s_blk;
   for (int blk = blockIdx.x;; ) {
     if (P.corner_counter) {
@@ -2033,23 +2052,29 @@ __global__ void __launch_bounds__(128) cloud_corners(const __grid_constant__ Par
       blk = s_blk;
     }
     if (blk >= n_blocks) return;
-    const int idx = blk * 128 + threadIdx.x;
+    const int idx = blk * DRT_CLOUD_BLOCK + (threadIdx.x >> 2);
     // 0: not wanted, 2: already computed by an earlier row chunk
-    if (idx < gw * gh && (P.cloud_only || P.need[idx] == 1)) {
-      const int cx = idx % gw, cy = idx / gw;
-      const int x = P.x0 + cx, y = P.y0 + cy;
-      const Vec<R> rayDir = eyeRay<R>(P, x, y);
-      Vec<R> point;
-      if (P.cloud_only) point = mulPoint<R>(P.cloud_mcam, rayDir + P.eye);             // renderImageCloud :1265-1268
-      else {
-        const Vec<R> focalPoint = P.eye + (R)P.focal_length * rayDir;
-        point = (P.frame >= P.frame_cloud) ? mulPoint<R>(P.new_mcam, focalPoint) : mulPoint<R>(P.mcam, focalPoint);   // :1079-1087
+    const bool wanted = idx < gw * gh && (P.cloud_only || P.need[idx] == 1);
+    if (__ballot_sync(0xffffffffu, wanted)) {                          // some corner of this warp's eight is wanted
+      Vec<R> point = mk<R>(R(0), R(0), R(0));
+      if (wanted) {
+        const int cx = idx % gw, cy = idx / gw;
+        const int x = P.x0 + cx, y = P.y0 + cy;
+        const Vec<R> rayDir = eyeRay<R>(P, x, y);
+        if (P.cloud_only) point = mulPoint<R>(P.cloud_mcam, rayDir + P.eye);             // renderImageCloud :1265-1268
+        else {
+          const Vec<R> focalPoint = P.eye + (R)P.focal_length * rayDir;
+          point = (P.frame >= P.frame_cloud) ? mulPoint<R>(P.new_mcam, focalPoint) : mulPoint<R>(P.mcam, focalPoint);   // :1079-1087
+        }
       }
       double c[3];
-      cloudColor<R>(P, point, (float)P.frame, c);
-      P.bg[idx] = make_float4((float)c[0], (float)c[1], (float)c[2], 0.f);
-      if (!P.cloud_only) P.need[idx] = 2;
-      if (P.counts) atomicAdd(&P.counts->noise_evals, 200ull);
+      int steps;
+      cloudColorQuad<R>(P, wanted, point, (float)P.frame, c, steps);
+      if (wanted && (threadIdx.x & 3) == 0) {
+        P.bg[idx] = make_float4((float)c[0], (float)c[1], (float)c[2], 0.f);
+        if (!P.cloud_only) P.need[idx] = 2;
+        if (P.counts) atomicAdd(&P.counts->noise_evals, (unsigned long long)steps);
+      }
     }
     if (!P.corner_counter) return;
   }

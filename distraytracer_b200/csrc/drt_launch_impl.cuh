@@ -64,7 +64,7 @@ template <> int launchRenderSamples<DRT_REAL>(const Params<DRT_REAL>& P, bool co
 }
 template <> void launchCloudCorners<DRT_REAL>(const Params<DRT_REAL>& P, cudaStream_t q) {
   const int n = (P.w + 1) * (P.h + 1);
-  int blocks = (n + 127) / 128;
+  int blocks = (n + DRT_CLOUD_BLOCK - 1) / DRT_CLOUD_BLOCK;
   if (P.corner_counter) {             // blocks of corners are claimed from a shared counter: a resident grid is enough
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
