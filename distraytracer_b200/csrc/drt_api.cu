@@ -184,10 +184,13 @@ int flatten(const drt_prim* prims, int n_prims, const drt_light* lights, int n_l
         if (p.type == DRT_PRIM_CHECKER_CYLINDER) objMatrix<R>(q.objM, axis, c1);
         if ((p.flags & DRT_FLAG_VERTEX_MOTION) && p.type != DRT_PRIM_CYLINDER)
           return fail(DRT_ERR_UNSUPPORTED, "DRT_FLAG_VERTEX_MOTION: cylinders only");
-        q.pC2 = cv<R>(c2); q.vel2 = cv<R>(V(p.velocity2));
+        if (p.flags & DRT_FLAG_VERTEX_MOTION) { q.n1 = cv<R>(c2); q.n2 = cv<R>(V(p.velocity2)); }   // see PrimD::vel
         Geom<R> g; memset(&g, 0, sizeof(g));
         g.type = G_CYL; g.owner = i; g.p0 = cv<R>(c1); g.p1 = cv<R>(c2); g.p2 = cv<R>(axis); g.f0 = (float)p.radius; g.vel = cv<R>(vel);
-        if (p.flags & DRT_FLAG_VERTEX_MOTION) { g.flags |= GF_VERTEX_MOTION; g.vel2 = cv<R>(V(p.velocity2)); }
+        if (p.flags & DRT_FLAG_VERTEX_MOTION) {
+          g.flags |= GF_VERTEX_MOTION;
+          g.len1 = (R)p.velocity2[0]; g.len2 = (R)p.velocity2[1]; g.pad_ = (R)p.velocity2[2];   // Geom::cylV2
+        }
         { const D3 pts[2] = {c1, c2}; setBounds(g, pts, 2, (double)(float)p.radius); }
         hs.geoms.push_back(g);
         break; }

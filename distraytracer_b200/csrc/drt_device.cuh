@@ -93,8 +93,10 @@ struct alignas(16) Geom {
   Vec<R> p0, p1, p2, p3;
   float f0, f1, f2, f3;
   Vec<R> vel;   // DRT_BLUR_VELOCITY displacement per unit time
-  Vec<R> vel2;  // GF_VERTEX_MOTION: displacement of the cylinder's second end point per unit time
+  // rectangles: edge lengths |B-A|, |D-A|.  Cylinders with GF_VERTEX_MOTION keep the displacement of their second end
+  // point per unit time in the same three words (cylV2): the record stays 224 bytes.
   R len1, len2, pad_;
+  __host__ __device__ Vec<R> cylV2() const { return mk<R>(len1, len2, pad_); }
   float4 blo, bhi;   // padded single-precision bounds for the slab filter
   int leaf;          // reference BVH leaf holding this geom
   int pad2_[3];
@@ -144,8 +146,7 @@ struct alignas(16) PrimD {
   R objM[12];
   // emissive (render_final_project.cpp:775-789)
   Vec<R> center, eA, eB, eC, eD; R e_den;
-  Vec<R> vel;
-  Vec<R> pC2, vel2;        // DRT_FLAG_VERTEX_MOTION cylinders: second end point and its velocity
+  Vec<R> vel;              // DRT_FLAG_VERTEX_MOTION cylinders keep c2 in n1 and its velocity in n2 (prism normals otherwise)
   // slab-box prisms (types 8-10): objM above holds cob * origin (geometry.cpp:975-984)
   float height; int n_holes;
   HoleD<R> holes[4];

@@ -461,7 +461,7 @@ __device__ inline bool geomIntersect(const Params<R>& P, const Geom<R>& g, int g
       Vec<R> c1 = shiftPoint<R, F>(mv, g.flags, g.vel, g.p0), c2 = shiftPoint<R, F>(mv, g.flags, g.vel, g.p1);
       Vec<R> axis = g.p2;
       if ((F & FT_VEL) && (g.flags & GF_VERTEX_MOTION) && mv.velocity_mode) {   // two poses: the axis follows the end points
-        c2 = g.p1 + g.vel2 * mv.time;
+        c2 = g.p1 + g.cylV2() * mv.time;
         axis = normalized(c2 - c1);
       }
       Vec<R> ray_a_proj = ray - dot(ray, axis) * axis;
@@ -733,7 +733,7 @@ __device__ inline bool geomShadow(const Params<R>& P, const Geom<R>& g, int gi, 
       Vec<R> c1 = shiftPoint<R, F>(mv, g.flags, g.vel, g.p0), c2 = shiftPoint<R, F>(mv, g.flags, g.vel, g.p1);
       Vec<R> axis = g.p2;
       if ((F & FT_VEL) && (g.flags & GF_VERTEX_MOTION) && mv.velocity_mode) {   // two poses: the axis follows the end points
-        c2 = g.p1 + g.vel2 * mv.time;
+        c2 = g.p1 + g.cylV2() * mv.time;
         axis = normalized(c2 - c1);
       }
       Vec<R> ray_a_proj = ray - dot(ray, axis) * axis;
@@ -905,6 +905,7 @@ __device__ bool meshTraverse(const Params<R>& P, const Vec<R>& ray, const Vec<R>
       if (ch[k] >= 0) {                                                   // internal child
         if (next == -0x7fffffff) next = ch[k];
         else if (sp < DRT_NODE_STACK) stack[sp++] = ch[k];
+        else *P.overflow = 1;                                           // deeper than any 30-bit Morton tree can be: the frame is rejected, not wrong
       } else {                                                            // leaf: exact test
         const int tri = -ch[k] - 1;
         if (COUNT) cnt.geom_tests[G_TRI]++;
@@ -1151,7 +1152,7 @@ __device__ void shadeA(const Params<R>& P, const Task<R>& T, const HitRec& h, Ta
     } else if (pr.type == 1 || pr.type == 7) {                          // Cylinder geometry.cpp:419-425
       const Vec<R> c1 = shiftPoint<R, F>(mv, 0, pr.vel, pr.pA);
       Vec<R> axis = pr.pG;
-      if ((F & FT_VEL) && (pr.flags & 64) && mv.velocity_mode) axis = normalized((pr.pC2 + pr.vel2 * mv.time) - c1);   // DRT_FLAG_VERTEX_MOTION
+      if ((F & FT_VEL) && (pr.flags & 64) && mv.velocity_mode) axis = normalized((pr.n1 + pr.n2 * mv.time) - c1);   // DRT_FLAG_VERTEX_MOTION: n1 = c2, n2 = its velocity
       Vec<R> pc = isectP - c1;
       normal = normalized(pc - dot(pc, axis) * axis);
     } else if ((F & FT_BOX) && pr.type == 9) {                          // RectPrismWithCylinder geometry.cpp:1796-1821 (lastHit is -1 by now)
