@@ -905,7 +905,7 @@ __device__ bool meshTraverse(const Params<R>& P, const Vec<R>& ray, const Vec<R>
       if (ch[k] >= 0) {                                                   // internal child
         if (next == -0x7fffffff) next = ch[k];
         else if (sp < DRT_NODE_STACK) stack[sp++] = ch[k];
-        else *P.overflow = 1;                                           // deeper than any 30-bit Morton tree can be: the frame is rejected, not wrong
+        else *P.overflow = 1;                                           // deeper than the stack (degenerate input only: coincident centroids): the frame is rejected, not wrong
       } else {                                                            // leaf: exact test
         const int tri = -ch[k] - 1;
         if (COUNT) cnt.geom_tests[G_TRI]++;

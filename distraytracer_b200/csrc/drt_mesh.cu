@@ -41,11 +41,11 @@ int buildMesh(const drt_mesh* mesh, MeshBuffers* out, std::string& err) {
   for (long long v = 0; v < nv; v++)
     for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], mesh->vertices[3 * v + a]); hi[a] = std::max(hi[a], mesh->vertices[3 * v + a]); }
   float3 slo = make_float3(lo[0], lo[1], lo[2]);
-  float3 sinv = make_float3(1.0f / std::max(hi[0] - lo[0], 1e-20f), 1.0f / std::max(hi[1] - lo[1], 1e-20f), 1.0f / std::max(hi[2] - lo[2], 1e-20f));
+  const float sinv = 1.0f / std::max(std::max(hi[0] - lo[0], hi[1] - lo[1]), std::max(hi[2] - lo[2], 1e-20f));   // cubic Morton cells
 
   float *d_verts = nullptr, *d_tc = nullptr; int* d_idx = nullptr;
   float4 *tlo = nullptr, *thi = nullptr, *nlo = nullptr, *nhi = nullptr;
-  uint32_t *codes = nullptr, *codes2 = nullptr; int *ids = nullptr, *ids2 = nullptr;
+  uint64_t *codes = nullptr, *codes2 = nullptr; int *ids = nullptr, *ids2 = nullptr;
   int *left = nullptr, *right = nullptr, *pin = nullptr, *pleaf = nullptr, *visits = nullptr;
   void* tmp = nullptr; size_t tmp_bytes = 0;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -62,7 +62,7 @@ int buildMesh(const drt_mesh* mesh, MeshBuffers* out, std::string& err) {
   }
   MCK(cudaMalloc(&tlo, sizeof(float4) * n)); MCK(cudaMalloc(&thi, sizeof(float4) * n));
   MCK(cudaMalloc(&nlo, sizeof(float4) * std::max(1, n - 1))); MCK(cudaMalloc(&nhi, sizeof(float4) * std::max(1, n - 1)));
-  MCK(cudaMalloc(&codes, sizeof(uint32_t) * n)); MCK(cudaMalloc(&codes2, sizeof(uint32_t) * n));
+  MCK(cudaMalloc(&codes, sizeof(uint64_t) * n)); MCK(cudaMalloc(&codes2, sizeof(uint64_t) * n));
   MCK(cudaMalloc(&ids, sizeof(int) * n)); MCK(cudaMalloc(&ids2, sizeof(int) * n));
   MCK(cudaMalloc(&left, sizeof(int) * std::max(1, n - 1))); MCK(cudaMalloc(&right, sizeof(int) * std::max(1, n - 1)));
   MCK(cudaMalloc(&pin, sizeof(int) * std::max(1, n - 1))); MCK(cudaMalloc(&pleaf, sizeof(int) * n));
@@ -82,9 +82,9 @@ int buildMesh(const drt_mesh* mesh, MeshBuffers* out, std::string& err) {
   lbvh_tri_records<double><<<G, B>>>(n, d_verts, d_idx, d_tc, (MeshTri<double>*)mb.tris_f64);
   lbvh_tri_records<float><<<G, B>>>(n, d_verts, d_idx, d_tc, (MeshTri<float>*)mb.tris_f32);
   if (n > 1) {
-    MCK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, codes, codes2, ids, ids2, n, 0, 30));
+    MCK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, codes, codes2, ids, ids2, n, 0, 63));
     MCK(cudaMalloc(&tmp, tmp_bytes));
-    MCK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, codes, codes2, ids, ids2, n, 0, 30));
+    MCK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, codes, codes2, ids, ids2, n, 0, 63));
     MCK(cudaMemset(visits, 0, sizeof(int) * (n - 1)));
     lbvh_karras<<<(n - 1 + B - 1) / B, B>>>(n, codes2, left, right, pin, pleaf);
     lbvh_refit<<<G, B>>>(n, ids2, tlo, thi, left, right, pin, pleaf, nlo, nhi, visits);
