@@ -864,73 +864,108 @@ __device__ __forceinline__ float meshTriT(const MeshTri<R>& tr, const Vec<R>& ra
   return (float)((double)dot(r2, DA0) * (double)invdet);
 }
 
-// Ordered, t-pruned stack traversal.  CLOSEST: keeps the nearest hit with t > 1e-4 (strict `<`
-// against the best so far, so analytic primitives -- tested first -- win ties).  !CLOSEST:
-// any hit with 1e-3 < t < t_max (Triangle::intersectShadow geometry.cpp:555-586) that the
-// reference would also have gathered (its gather origin runs ahead by |sray|*1e-3, :814; a
-// mesh triangle stands in its own leaf box: bounds +- 1e-2, geometry.cpp:2653-2654).
+// One pair record of the slab filter (see slabMask) -> pass flags and entry distances of its two boxes.
+__device__ __forceinline__ void slabPair(const float4 A, const float4 B, const float4 C, const SlabRay& r, bool& ok0, bool& ok1,
+                                         float& tn0, float& tn1) {
+  const float2 mx = __ffma2_rn(make_float2(A.x, A.y), r.i[0], r.no[0]);
+  const float2 my = __ffma2_rn(make_float2(A.z, A.w), r.i[1], r.no[1]);
+  const float2 mz = __ffma2_rn(make_float2(B.x, B.y), r.i[2], r.no[2]);
+  const float2 hx = make_float2(B.z, B.w), hy = make_float2(C.x, C.y), hz = make_float2(C.z, C.w);
+  const float2 nx = __ffma2_rn(hx, r.nai[0], mx), fx = __ffma2_rn(hx, r.ai[0], mx);
+  const float2 ny = __ffma2_rn(hy, r.nai[1], my), fy = __ffma2_rn(hy, r.ai[1], my);
+  const float2 nz = __ffma2_rn(hz, r.nai[2], mz), fz = __ffma2_rn(hz, r.ai[2], mz);
+  tn0 = fmaxf(fmaxf(nx.x, ny.x), nz.x); tn1 = fmaxf(fmaxf(nx.y, ny.y), nz.y);
+  const float2 tf = __ffma2_rn(make_float2(fminf(fminf(fx.x, fy.x), fz.x), fminf(fminf(fx.y, fy.y), fz.y)), r.grow, r.slack);
+  ok0 = !(fmaxf(tn0, r.floor_t) > fminf(tf.x, r.lim));
+  ok1 = !(fmaxf(tn1, r.floor_t) > fminf(tf.y, r.lim));
+}
+
+// Traversal of the 4-wide LBVH (drt_lbvh.cuh), "while-while": a lane first descends through internal nodes until the
+// next thing it has to do is an exact triangle test (or nothing), and only then -- together with the other lanes of the
+// warp that reached a leaf -- runs the reference's Moeller-Trumbore test in the vector precision.  With the test inline in
+// the node loop it ran with ~4 of 32 lanes (profiles/r1_ncu_full_band_c5_mesh.txt).  A node visit tests its four child
+// boxes with the packed slab test of the analytic filter, descends into the nearest one that passes and pushes the others
+// with their entry distances; an entry whose distance lies beyond the best hit found meanwhile is dropped when popped.
+// CLOSEST: keeps the nearest hit with t > 1e-4 (strict `<` against the best so far, so analytic primitives -- tested
+// first -- win ties).  !CLOSEST: any hit with 1e-3 < t < t_max (Triangle::intersectShadow geometry.cpp:555-586) that the
+// reference would also have gathered (its gather origin runs ahead by |sray|*1e-3, :814; a mesh triangle stands in its
+// own leaf box: bounds +- 1e-2, geometry.cpp:2653-2654).
+#define DRT_MESH_DONE ((int)0x80000000)
 template <typename R, int F, bool COUNT, bool CLOSEST>
 __device__ bool meshTraverse(const Params<R>& P, const Vec<R>& ray, const Vec<R>& start, float t_limit, HitRec* h,
                              const Vec<R>& gather_ray, const Vec<R>& gather_start, Counts& cnt) {
-  const float ox = (float)start.x, oy = (float)start.y, oz = (float)start.z;
   const float ix = 1.0f / (float)ray.x, iy = 1.0f / (float)ray.y, iz = 1.0f / (float)ray.z;
-  int stack[DRT_NODE_STACK];
+  const float nox = -(float)start.x * ix, noy = -(float)start.y * iy, noz = -(float)start.z * iz;
+  const float serr = 4e-7f * (fabsf(nox) + fabsf(noy) + fabsf(noz));           // as in slabRay
+  SlabRay sr = slabRay(ix, iy, iz, nox, noy, noz, (t_limit < FLT_MAX) ? t_limit * 1.0001f + 1e-4f : FLT_MAX);
+  int2 stack[DRT_NODE_STACK];                                                   // (child reference, entry distance bits)
   int sp = 0;
-  int node = 0;
+  int cur = 0;
   bool found = false;
   for (;;) {
-    const float4 n0 = __ldg(&P.mesh_nodes[4 * node]), n1 = __ldg(&P.mesh_nodes[4 * node + 1]);
-    const float4 n2 = __ldg(&P.mesh_nodes[4 * node + 2]), n3 = __ldg(&P.mesh_nodes[4 * node + 3]);
-    if (COUNT) cnt.node_tests += 2;
-    const float lim = (t_limit < FLT_MAX) ? t_limit * 1.0001f + 1e-4f : FLT_MAX;
-    float tn[2]; bool hit[2];
-    {
-      float t0 = (n0.x - ox) * ix, t1 = (n1.x - ox) * ix; float a = fminf(t0, t1), b = fmaxf(t0, t1);
-      t0 = (n0.y - oy) * iy; t1 = (n1.y - oy) * iy; a = fmaxf(a, fminf(t0, t1)); b = fminf(b, fmaxf(t0, t1));
-      t0 = (n0.z - oz) * iz; t1 = (n1.z - oz) * iz; a = fmaxf(a, fminf(t0, t1)); b = fminf(b, fmaxf(t0, t1));
-      tn[0] = a; hit[0] = !(a > b * 1.0001f + 1e-4f) && !(b < 0.0f) && !(a > lim);
-    }
-    {
-      float t0 = (n2.x - ox) * ix, t1 = (n3.x - ox) * ix; float a = fminf(t0, t1), b = fmaxf(t0, t1);
-      t0 = (n2.y - oy) * iy; t1 = (n3.y - oy) * iy; a = fmaxf(a, fminf(t0, t1)); b = fminf(b, fmaxf(t0, t1));
-      t0 = (n2.z - oz) * iz; t1 = (n3.z - oz) * iz; a = fmaxf(a, fminf(t0, t1)); b = fminf(b, fmaxf(t0, t1));
-      tn[1] = a; hit[1] = !(a > b * 1.0001f + 1e-4f) && !(b < 0.0f) && !(a > lim);
-    }
-    int ch[2] = {__float_as_int(n0.w), __float_as_int(n1.w)};
-    if (hit[0] && hit[1] && tn[1] < tn[0]) { int c = ch[0]; ch[0] = ch[1]; ch[1] = c; }   // nearer child first
-    else if (!hit[0]) { ch[0] = ch[1]; hit[0] = hit[1]; hit[1] = false; }
-    int next = -0x7fffffff;
-    for (int k = 0; k < 2; k++) {
-      if (!hit[k]) continue;
-      if (ch[k] >= 0) {                                                   // internal child
-        if (next == -0x7fffffff) next = ch[k];
-        else if (sp < DRT_NODE_STACK) stack[sp++] = ch[k];
-        else *P.overflow = 1;                                           // deeper than the stack (degenerate input only: coincident centroids): the frame is rejected, not wrong
-      } else {                                                            // leaf: exact test
-        const int tri = -ch[k] - 1;
-        if (COUNT) cnt.geom_tests[G_TRI]++;
-        const MeshTri<R>& tr = P.mesh_tris[tri];
-        const float t = meshTriT<R>(tr, ray, start);
-        if (CLOSEST) {
-          if (t > 0.0001f && t < h->t) { h->t = t; h->geom = P.n_geoms + tri; h->inside = 0; h->checker_sel = 0; t_limit = t; found = true; }
-        } else if (t > 0.001f && t < t_limit) {
-          if (t > t_limit * 1e-3f * 1.001f + 2e-3f) return true;          // touch point ahead of the gather origin
-          NodeD<R> nd;                                                    // its own leaf box, BoundingVolume semantics
-          nd.lo = mk<R>(fmin(fmin(tr.A.x, tr.B.x), tr.C.x) - R(1e-2), fmin(fmin(tr.A.y, tr.B.y), tr.C.y) - R(1e-2),
-                        fmin(fmin(tr.A.z, tr.B.z), tr.C.z) - R(1e-2));
-          nd.hi = mk<R>(fmax(fmax(fmax(tr.A.x, tr.B.x), tr.C.x), (R)FLT_MIN) + R(1e-2),
-                        fmax(fmax(fmax(tr.A.y, tr.B.y), tr.C.y), (R)FLT_MIN) + R(1e-2),
-                        fmax(fmax(fmax(tr.A.z, tr.B.z), tr.C.z), (R)FLT_MIN) + R(1e-2));
-          nd.leaf = 1;
-          Moved<R> still; still.val = 0; still.time = 0; still.velocity_mode = 0;
-          const Vec<R> inv = mk<R>(R(1) / gather_ray.x, R(1) / gather_ray.y, R(1) / gather_ray.z);
-          if (boxHit<R, F>(nd, gather_ray, inv, gather_start, still)) return true;
+    while (cur >= 0) {                                                          // ---- internal nodes
+      const float4* nd = P.mesh_nodes + 8 * (size_t)cur;
+      const float4 A0 = __ldg(nd), B0 = __ldg(nd + 1), C0 = __ldg(nd + 2), A1 = __ldg(nd + 3), B1 = __ldg(nd + 4), C1 = __ldg(nd + 5);
+      const float4 K = __ldg(nd + 6);
+      if (COUNT) cnt.node_tests += 4;
+      bool ok0, ok1, ok2, ok3; float t0, t1, t2, t3;
+      slabPair(A0, B0, C0, sr, ok0, ok1, t0, t1);
+      slabPair(A1, B1, C1, sr, ok2, ok3, t2, t3);
+      const int r0 = __float_as_int(K.x), r1 = __float_as_int(K.y), r2 = __float_as_int(K.z), r3 = __float_as_int(K.w);
+      ok2 = ok2 && r2 != DRT_MESH_DONE; ok3 = ok3 && r3 != DRT_MESH_DONE;       // empty slots (NaN slab terms of an axis-parallel ray pass the test)
+      // nearest passing child
+      float bt = FLT_MAX; int bk = -1;
+      if (ok0) { bt = t0; bk = 0; }
+      if (ok1 && (bk < 0 || t1 < bt)) { bt = t1; bk = 1; }
+      if (ok2 && (bk < 0 || t2 < bt)) { bt = t2; bk = 2; }
+      if (ok3 && (bk < 0 || t3 < bt)) { bt = t3; bk = 3; }
+      const int np = (int)ok0 + (int)ok1 + (int)ok2 + (int)ok3 - (bk >= 0 ? 1 : 0);
+      if (sp + np > DRT_NODE_STACK) { *P.overflow = 1; cur = DRT_MESH_DONE; break; }   // degenerate input only: the frame is rejected, not wrong
+      if (ok0 && bk != 0) stack[sp++] = make_int2(r0, __float_as_int(t0));
+      if (ok1 && bk != 1) stack[sp++] = make_int2(r1, __float_as_int(t1));
+      if (ok2 && bk != 2) stack[sp++] = make_int2(r2, __float_as_int(t2));
+      if (ok3 && bk != 3) stack[sp++] = make_int2(r3, __float_as_int(t3));
+      if (bk >= 0) cur = bk == 0 ? r0 : bk == 1 ? r1 : bk == 2 ? r2 : r3;
+      else {
+        cur = DRT_MESH_DONE;
+        while (sp > 0) {
+          const int2 e = stack[--sp];
+          if (CLOSEST && __int_as_float(e.y) > sr.lim) continue;
+          cur = e.x; break;
         }
       }
     }
-    if (next != -0x7fffffff) { node = next; continue; }
-    if (sp == 0) break;
-    node = stack[--sp];
+    if (cur == DRT_MESH_DONE) break;
+    {                                                                           // ---- leaf: exact test
+      const int tri = -cur - 1;
+      if (COUNT) cnt.geom_tests[G_TRI]++;
+      const MeshTri<R>& tr = P.mesh_tris[tri];
+      const float t = meshTriT<R>(tr, ray, start);
+      if (CLOSEST) {
+        if (t > 0.0001f && t < h->t) {
+          h->t = t; h->geom = P.n_geoms + tri; h->inside = 0; h->checker_sel = 0; found = true;
+          sr.lim = (t * 1.0001f + 1e-4f) + serr;
+        }
+      } else if (t > 0.001f && t < t_limit) {
+        if (t > t_limit * 1e-3f * 1.001f + 2e-3f) return true;                  // touch point ahead of the gather origin
+        NodeD<R> nd;                                                            // its own leaf box, BoundingVolume semantics
+        nd.lo = mk<R>(fmin(fmin(tr.A.x, tr.B.x), tr.C.x) - R(1e-2), fmin(fmin(tr.A.y, tr.B.y), tr.C.y) - R(1e-2),
+                      fmin(fmin(tr.A.z, tr.B.z), tr.C.z) - R(1e-2));
+        nd.hi = mk<R>(fmax(fmax(fmax(tr.A.x, tr.B.x), tr.C.x), (R)FLT_MIN) + R(1e-2),
+                      fmax(fmax(fmax(tr.A.y, tr.B.y), tr.C.y), (R)FLT_MIN) + R(1e-2),
+                      fmax(fmax(fmax(tr.A.z, tr.B.z), tr.C.z), (R)FLT_MIN) + R(1e-2));
+        nd.leaf = 1;
+        Moved<R> still; still.val = 0; still.time = 0; still.velocity_mode = 0;
+        const Vec<R> inv = mk<R>(R(1) / gather_ray.x, R(1) / gather_ray.y, R(1) / gather_ray.z);
+        if (boxHit<R, F>(nd, gather_ray, inv, gather_start, still)) return true;
+      }
+      cur = DRT_MESH_DONE;
+      while (sp > 0) {
+        const int2 e = stack[--sp];
+        if (CLOSEST && __int_as_float(e.y) > sr.lim) continue;
+        cur = e.x; break;
+      }
+    }
   }
   return found;
 }

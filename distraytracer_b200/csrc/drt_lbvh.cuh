@@ -5,11 +5,17 @@
 // primitives.  Build = Morton codes of triangle centroids (63 bit, cubic cells), radix sort
 // (cub::DeviceRadixSort -- the one library call, build-time plumbing, never per ray), Karras
 // 2012 binary radix tree, bottom-up refit with one atomic counter per internal node, then a
-// repack into 64-byte nodes that hold BOTH children's boxes so one node fetch (4 x LDG.128)
-// decides both descents.
+// collapse into 4-WIDE nodes: every binary node at even depth becomes a traversal node whose children are its
+// grandchildren (or a child that is a leaf), so a ray takes half as many dependent node fetches.
 //
-// Node layout (float4 x 4):  { lo0.xyz, child0 } { hi0.xyz, child1 } { lo1.xyz, - } { hi1.xyz, - }
-// child >= 0: internal node index; child < 0: leaf, triangle id = -child - 1.
+// Traversal node (float4 x 8 = 128 B, one cache line), children boxes as CENTRE / HALF-EXTENT in the pair-record layout
+// of the analytic slab filter (drt_kernels.cuh: slabPair), so both levels share the packed FFMA2 test:
+//   [0..2] {cx0 cx1 cy0 cy1} {cz0 cz1 hx0 hx1} {hy0 hy1 hz0 hz1}   children 0, 1
+//   [3..5] the same for children 2, 3
+//   [6]    child references as int bits: >= 0 traversal node index; < 0 leaf, triangle id = -ref - 1
+//   [7]    padding
+// An empty slot (children 2 and 3 only) has half-extent -1e30 and the reference 0x80000000: it never passes, not even for
+// an axis-parallel ray whose slab terms are NaN.
 #pragma once
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
@@ -121,22 +127,49 @@ __global__ void lbvh_refit(int n, const int* __restrict__ ids, const float4* __r
   }
 }
 
-// repack into the 64-byte traversal nodes
-__global__ void lbvh_pack(int n, const int* __restrict__ ids, const float4* __restrict__ tlo, const float4* __restrict__ thi,
-                          const int* __restrict__ left, const int* __restrict__ right, const float4* __restrict__ nlo,
-                          const float4* __restrict__ nhi, float4* __restrict__ nodes) {
+// centre / half-extent of [lo, hi], rounded so that [c - h, c + h] contains it
+__device__ __forceinline__ void lbvh_centre_half(const float lo, const float hi, float& c, float& h) {
+  c = (float)(0.5 * ((double)lo + (double)hi));
+  const double hd = fmax((double)hi - (double)c, (double)c - (double)lo);
+  h = nextafterf(__double2float_ru(hd), INFINITY);
+}
+
+// collapse into the 128-byte 4-wide traversal nodes: one thread per binary internal node, even depths only
+__global__ void lbvh_pack4(int n, const int* __restrict__ ids, const float4* __restrict__ tlo, const float4* __restrict__ thi,
+                           const int* __restrict__ left, const int* __restrict__ right, const int* __restrict__ parent_internal,
+                           const float4* __restrict__ nlo, const float4* __restrict__ nhi, float4* __restrict__ nodes) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n - 1) return;
-  const int ch[2] = {left[i], right[i]};
-  float4 lo[2], hi[2]; int ref[2];
+  int depth = 0;
+  for (int k = i; k != 0; k = parent_internal[k]) depth++;             // node 0 is the root of Karras' tree
+  if (depth & 1) return;
+  int c[4], m = 0;
+  const int side[2] = {left[i], right[i]};
   for (int k = 0; k < 2; k++) {
-    if (ch[k] >= 0) { lo[k] = nlo[ch[k]]; hi[k] = nhi[ch[k]]; ref[k] = ch[k]; }
-    else { const int t = ids[-ch[k] - 1]; lo[k] = tlo[t]; hi[k] = thi[t]; ref[k] = -(t + 1); }
+    if (side[k] < 0) c[m++] = side[k];
+    else { c[m++] = left[side[k]]; c[m++] = right[side[k]]; }
   }
-  nodes[4 * i + 0] = make_float4(lo[0].x, lo[0].y, lo[0].z, __int_as_float(ref[0]));
-  nodes[4 * i + 1] = make_float4(hi[0].x, hi[0].y, hi[0].z, __int_as_float(ref[1]));
-  nodes[4 * i + 2] = make_float4(lo[1].x, lo[1].y, lo[1].z, 0.f);
-  nodes[4 * i + 3] = make_float4(hi[1].x, hi[1].y, hi[1].z, 0.f);
+  float cc[4][3], hh[4][3]; int ref[4];
+  for (int k = 0; k < 4; k++) {
+    ref[k] = (int)0x80000000;
+    for (int a = 0; a < 3; a++) { cc[k][a] = 0.f; hh[k][a] = -1e30f; }
+    if (k >= m) continue;
+    float4 lo, hi;
+    if (c[k] >= 0) { lo = nlo[c[k]]; hi = nhi[c[k]]; ref[k] = c[k]; }
+    else { const int t = ids[-c[k] - 1]; lo = tlo[t]; hi = thi[t]; ref[k] = -(t + 1); }
+    lbvh_centre_half(lo.x, hi.x, cc[k][0], hh[k][0]);
+    lbvh_centre_half(lo.y, hi.y, cc[k][1], hh[k][1]);
+    lbvh_centre_half(lo.z, hi.z, cc[k][2], hh[k][2]);
+  }
+  float4* nd = nodes + 8 * (size_t)i;
+  for (int p = 0; p < 2; p++) {
+    const int a = 2 * p, b = 2 * p + 1;
+    nd[3 * p + 0] = make_float4(cc[a][0], cc[b][0], cc[a][1], cc[b][1]);
+    nd[3 * p + 1] = make_float4(cc[a][2], cc[b][2], hh[a][0], hh[b][0]);
+    nd[3 * p + 2] = make_float4(hh[a][1], hh[b][1], hh[a][2], hh[b][2]);
+  }
+  nd[6] = make_float4(__int_as_float(ref[0]), __int_as_float(ref[1]), __int_as_float(ref[2]), __int_as_float(ref[3]));
+  nd[7] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // exact-test records: the three vertices in the vector scalar R (the reference recomputes B-A,

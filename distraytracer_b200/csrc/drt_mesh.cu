@@ -67,7 +67,7 @@ int buildMesh(const drt_mesh* mesh, MeshBuffers* out, std::string& err) {
   MCK(cudaMalloc(&left, sizeof(int) * std::max(1, n - 1))); MCK(cudaMalloc(&right, sizeof(int) * std::max(1, n - 1)));
   MCK(cudaMalloc(&pin, sizeof(int) * std::max(1, n - 1))); MCK(cudaMalloc(&pleaf, sizeof(int) * n));
   MCK(cudaMalloc(&visits, sizeof(int) * std::max(1, n - 1)));
-  MCK(cudaMalloc(&mb.nodes, sizeof(float4) * 4 * std::max(1, n - 1)));
+  MCK(cudaMalloc(&mb.nodes, sizeof(float4) * 8 * std::max(1, n - 1)));
   MCK(cudaMalloc(&mb.tris_f64, sizeof(MeshTri<double>) * n));
   MCK(cudaMalloc(&mb.tris_f32, sizeof(MeshTri<float>) * n));
   if (mesh->n_materials > 0) {
@@ -88,17 +88,29 @@ int buildMesh(const drt_mesh* mesh, MeshBuffers* out, std::string& err) {
     MCK(cudaMemset(visits, 0, sizeof(int) * (n - 1)));
     lbvh_karras<<<(n - 1 + B - 1) / B, B>>>(n, codes2, left, right, pin, pleaf);
     lbvh_refit<<<G, B>>>(n, ids2, tlo, thi, left, right, pin, pleaf, nlo, nhi, visits);
-    lbvh_pack<<<(n - 1 + B - 1) / B, B>>>(n, ids2, tlo, thi, left, right, nlo, nhi, mb.nodes);
+    lbvh_pack4<<<(n - 1 + B - 1) / B, B>>>(n, ids2, tlo, thi, left, right, pin, nlo, nhi, mb.nodes);
   } else {
-    // single triangle: one node, second child empty (lo > hi never passes the slab test)
+    // single triangle: one node
     float4 h_lo, h_hi;
     MCK(cudaMemcpy(&h_lo, tlo, sizeof(float4), cudaMemcpyDeviceToHost));
     MCK(cudaMemcpy(&h_hi, thi, sizeof(float4), cudaMemcpyDeviceToHost));
-    int leaf = -1, none = -1;
-    float4 nd[4];
-    nd[0] = h_lo; memcpy(&nd[0].w, &leaf, 4);
-    nd[1] = h_hi; memcpy(&nd[1].w, &none, 4);
-    nd[2] = make_float4(1e30f, 1e30f, 1e30f, 0.f); nd[3] = make_float4(-1e30f, -1e30f, -1e30f, 0.f);
+    float c[3], h[3];
+    const float l3[3] = {h_lo.x, h_lo.y, h_lo.z}, u3[3] = {h_hi.x, h_hi.y, h_hi.z};
+    for (int a = 0; a < 3; a++) {
+      c[a] = (float)(0.5 * ((double)l3[a] + (double)u3[a]));
+      const double hd = std::max((double)u3[a] - (double)c[a], (double)c[a] - (double)l3[a]);
+      float hf = (float)hd;
+      if ((double)hf < hd) hf = nextafterf(hf, INFINITY);
+      h[a] = nextafterf(hf, INFINITY);
+    }
+    const float E = -1e30f;
+    const int leaf = -1, none = (int)0x80000000;
+    float4 nd[8];
+    // slots 0 and 1 both hold the triangle (only slots 2 and 3 may be empty); a second test of it changes nothing
+    nd[0] = make_float4(c[0], c[0], c[1], c[1]); nd[1] = make_float4(c[2], c[2], h[0], h[0]); nd[2] = make_float4(h[1], h[1], h[2], h[2]);
+    nd[3] = make_float4(0.f, 0.f, 0.f, 0.f); nd[4] = make_float4(0.f, 0.f, E, E); nd[5] = make_float4(E, E, E, E);
+    memcpy(&nd[6].x, &leaf, 4); memcpy(&nd[6].y, &leaf, 4); memcpy(&nd[6].z, &none, 4); memcpy(&nd[6].w, &none, 4);
+    nd[7] = make_float4(0.f, 0.f, 0.f, 0.f);
     MCK(cudaMemcpy(mb.nodes, nd, sizeof(nd), cudaMemcpyHostToDevice));
   }
   MCK(cudaEventRecord(e1));
