@@ -902,6 +902,15 @@ __device__ bool meshTraverse(const Params<R>& P, const Vec<R>& ray, const Vec<R>
   int sp = 0;
   int cur = 0;
   bool found = false;
+  // next entry of the stack that can still hold a closer hit, or DONE
+  auto pop = [&]() -> int {
+    while (sp > 0) {
+      const int2 e = stack[--sp];
+      if (CLOSEST && __int_as_float(e.y) > sr.lim) continue;
+      return e.x;
+    }
+    return DRT_MESH_DONE;
+  };
   for (;;) {
     while (cur >= 0) {                                                          // ---- internal nodes
       const float4* nd = P.mesh_nodes + 8 * (size_t)cur;
@@ -912,27 +921,32 @@ __device__ bool meshTraverse(const Params<R>& P, const Vec<R>& ray, const Vec<R>
       slabPair(A0, B0, C0, sr, ok0, ok1, t0, t1);
       slabPair(A1, B1, C1, sr, ok2, ok3, t2, t3);
       const int r0 = __float_as_int(K.x), r1 = __float_as_int(K.y), r2 = __float_as_int(K.z), r3 = __float_as_int(K.w);
-      ok2 = ok2 && r2 != DRT_MESH_DONE; ok3 = ok3 && r3 != DRT_MESH_DONE;       // empty slots (NaN slab terms of an axis-parallel ray pass the test)
-      // nearest passing child
-      float bt = FLT_MAX; int bk = -1;
-      if (ok0) { bt = t0; bk = 0; }
-      if (ok1 && (bk < 0 || t1 < bt)) { bt = t1; bk = 1; }
-      if (ok2 && (bk < 0 || t2 < bt)) { bt = t2; bk = 2; }
-      if (ok3 && (bk < 0 || t3 < bt)) { bt = t3; bk = 3; }
-      const int np = (int)ok0 + (int)ok1 + (int)ok2 + (int)ok3 - (bk >= 0 ? 1 : 0);
-      if (sp + np > DRT_NODE_STACK) { *P.overflow = 1; cur = DRT_MESH_DONE; break; }   // degenerate input only: the frame is rejected, not wrong
-      if (ok0 && bk != 0) stack[sp++] = make_int2(r0, __float_as_int(t0));
-      if (ok1 && bk != 1) stack[sp++] = make_int2(r1, __float_as_int(t1));
-      if (ok2 && bk != 2) stack[sp++] = make_int2(r2, __float_as_int(t2));
-      if (ok3 && bk != 3) stack[sp++] = make_int2(r3, __float_as_int(t3));
-      if (bk >= 0) cur = bk == 0 ? r0 : bk == 1 ? r1 : bk == 2 ? r2 : r3;
-      else {
-        cur = DRT_MESH_DONE;
-        while (sp > 0) {
-          const int2 e = stack[--sp];
-          if (CLOSEST && __int_as_float(e.y) > sr.lim) continue;
-          cur = e.x; break;
+      ok2 = ok2 && r2 != DRT_MESH_DONE; ok3 = ok3 && r3 != DRT_MESH_DONE;     // empty slots (NaN slab terms of an axis-parallel ray pass the test)
+      if (sp > DRT_NODE_STACK - 4) { *P.overflow = 1; cur = DRT_MESH_DONE; break; }   // degenerate input only: the frame is rejected, not wrong
+      if (CLOSEST) {
+        // descend into the nearest passing child: order key = entry distance (clamped at 0, low two mantissa bits = slot)
+        const int k0 = ok0 ? ((__float_as_int(fmaxf(t0, 0.f)) & ~3) | 0) : 0x7fffffff;
+        const int k1 = ok1 ? ((__float_as_int(fmaxf(t1, 0.f)) & ~3) | 1) : 0x7fffffff;
+        const int k2 = ok2 ? ((__float_as_int(fmaxf(t2, 0.f)) & ~3) | 2) : 0x7fffffff;
+        const int k3 = ok3 ? ((__float_as_int(fmaxf(t3, 0.f)) & ~3) | 3) : 0x7fffffff;
+        const int kb = min(min(k0, k1), min(k2, k3));
+        if (kb == 0x7fffffff) cur = pop();
+        else {
+          if (ok0 && k0 != kb) stack[sp++] = make_int2(r0, __float_as_int(t0));
+          if (ok1 && k1 != kb) stack[sp++] = make_int2(r1, __float_as_int(t1));
+          if (ok2 && k2 != kb) stack[sp++] = make_int2(r2, __float_as_int(t2));
+          if (ok3 && k3 != kb) stack[sp++] = make_int2(r3, __float_as_int(t3));
+          const int bk = kb & 3;
+          cur = bk == 0 ? r0 : bk == 1 ? r1 : bk == 2 ? r2 : r3;
         }
+      } else {
+        // any hit: the order does not matter -- the last passing child is next, the others wait
+        int nxt = DRT_MESH_DONE;
+        if (ok0) nxt = r0;
+        if (ok1) { if (nxt != DRT_MESH_DONE) stack[sp++] = make_int2(nxt, 0); nxt = r1; }
+        if (ok2) { if (nxt != DRT_MESH_DONE) stack[sp++] = make_int2(nxt, 0); nxt = r2; }
+        if (ok3) { if (nxt != DRT_MESH_DONE) stack[sp++] = make_int2(nxt, 0); nxt = r3; }
+        cur = (nxt != DRT_MESH_DONE) ? nxt : pop();
       }
     }
     if (cur == DRT_MESH_DONE) break;
@@ -959,13 +973,8 @@ __device__ bool meshTraverse(const Params<R>& P, const Vec<R>& ray, const Vec<R>
         const Vec<R> inv = mk<R>(R(1) / gather_ray.x, R(1) / gather_ray.y, R(1) / gather_ray.z);
         if (boxHit<R, F>(nd, gather_ray, inv, gather_start, still)) return true;
       }
-      cur = DRT_MESH_DONE;
-      while (sp > 0) {
-        const int2 e = stack[--sp];
-        if (CLOSEST && __int_as_float(e.y) > sr.lim) continue;
-        cur = e.x; break;
-      }
     }
+    cur = pop();
   }
   return found;
 }
