@@ -306,10 +306,10 @@ int flatten(const drt_prim* prims, int n_prims, const drt_light* lights, int n_l
     hs.nodes.push_back(nd);
   }
   // slab-filter table (drt_kernels.cuh: slabMask): centre / half-extent of the padded fp32 boxes, two geoms per
-  // record of three float4 {cx0 cx1 cy0 cy1} {cz0 cz1 hx0 hx1} {hy0 hy1 hz0 hz1}; holes and the odd-count padding
-  // entry get a negative half-extent so that they never pass
+  // record of three float4 {cx0 cx1 cy0 cy1} {cz0 cz1 hx0 hx1} {hy0 hy1 hz0 hz1}, padded to whole groups of 8 geoms
+  // (slabPairWords); holes and the padding entries get a negative half-extent so that they never pass
   hs.gbounds.clear();
-  for (size_t p = 0; p < (hs.geoms.size() + 1) / 2; p++) {
+  for (size_t p = 0; p < 4 * ((hs.geoms.size() + 7) / 8); p++) {
     float c[2][3], h[2][3];
     for (int k = 0; k < 2; k++) {
       const size_t gi = 2 * p + k;

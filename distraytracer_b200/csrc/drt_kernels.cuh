@@ -550,15 +550,21 @@ __device__ __forceinline__ SlabRay slabRay(const float ix, const float iy, const
 __device__ __forceinline__ unsigned int slabAll(const int g0, const int g1) {   // every geom of the group [g0, g1)
   return (g1 - g0 >= 32) ? 0xffffffffu : ((1u << (g1 - g0)) - 1u);
 }
+// The table is addressed by a byte offset from `tab`: a 32-bit shared-window address when the CTA staged it in shared
+// memory (explicit ld.shared.v4 with the record offsets folded into the instruction), a global pointer otherwise.
+struct SlabTab {
+  const float4* g;      // global table (P.gbounds)
+  unsigned s;           // the same table in the CTA's shared memory (shared-window address)
+};
 template <bool SMEM>
-__device__ __forceinline__ float4 slabLoad(const float4* p) {
+__device__ __forceinline__ float4 slabLoad(const SlabTab tab, const int word) {   // word = index of the float4
   if (SMEM) {
     float4 v;
-    // volatile: must not be speculated above the `smem` test (the pointer is a global address otherwise)
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"((unsigned)__cvta_generic_to_shared(p)));
+    // volatile: must not be speculated above the `smem` test
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(tab.s + 16u * (unsigned)word));
     return v;
   }
-  return __ldg(p);
+  return __ldg(tab.g + word);
 }
 // Bit k of the result: geom g0 + k may be hit.  inf/NaN terms (axis-parallel rays) drop out of
 // the min/max chains or make the final compare false, i.e. never reject.
@@ -566,9 +572,8 @@ __device__ __forceinline__ float4 slabLoad(const float4* p) {
 // neighbours in the reference's BVH order, and a prism's 6 faces are consecutive).  A lane runs a group's records only
 // if its ray may hit the group box -- the branch is per lane, so the warp skips the block when no lane needs it, which
 // is the common case now that a warp's rays leave from one surface (geom-sorted SHADE, child-index-major pushes).
-#ifndef DRT_GROUP_SKIP
-#define DRT_GROUP_SKIP 1
-#endif
+// The pair records are padded to whole groups (never-passing entries), so a group is always four records.
+__host__ __device__ constexpr int slabPairWords(const int n_geoms) { return 3 * 4 * ((n_geoms + 7) / 8); }   // float4 words before the group boxes
 __device__ __forceinline__ bool slabGroupMayHit(const float4 G0, const float4 G1, const SlabRay& r) {
   const float mx = fmaf(G0.x, r.i[0].x, r.no[0].x), my = fmaf(G0.y, r.i[1].x, r.no[1].x), mz = fmaf(G0.z, r.i[2].x, r.no[2].x);
   const float tn = fmaxf(fmaxf(fmaf(G0.w, r.nai[0].x, mx), fmaf(G1.x, r.nai[1].x, my)), fmaf(G1.y, r.nai[2].x, mz));
@@ -576,46 +581,33 @@ __device__ __forceinline__ bool slabGroupMayHit(const float4 G0, const float4 G1
   return !(fmaxf(tn, r.floor_t) > fminf(fmaf(tf, r.grow.x, r.slack.x), r.lim));
 }
 template <bool SMEM>
-__device__ __forceinline__ unsigned int slabMask(const float4* __restrict__ tab, const int n_geoms, const int g0, const int g1,
-                                                 const SlabRay& r) {
+__device__ __forceinline__ unsigned int slabMask(const SlabTab tab, const int n_geoms, const int g0, const int g1, const SlabRay& r) {
   unsigned int mask = 0;
-#if DRT_GROUP_SKIP
-  const float4* gtab = tab + 3 * ((n_geoms + 1) >> 1);            // group boxes follow the pair records
+  const int gw = slabPairWords(n_geoms);                          // group boxes follow the pair records
   for (int q0 = g0; q0 < g1; q0 += 8) {
-    const float4 G0 = slabLoad<SMEM>(gtab + 2 * (q0 >> 3)), G1 = slabLoad<SMEM>(gtab + 2 * (q0 >> 3) + 1);
+    const int grp = q0 >> 3;
+    const float4 G0 = slabLoad<SMEM>(tab, gw + 2 * grp), G1 = slabLoad<SMEM>(tab, gw + 2 * grp + 1);
     if (!slabGroupMayHit(G0, G1, r)) continue;
-    const int p0 = q0 >> 1, p1 = (min(q0 + 8, g1) + 1) >> 1;
     unsigned int sub = 0;
 #pragma unroll
-    for (int p = p0; p < p0 + 4; p++) {
-      if (p >= p1) break;
-#else
-  const int p0 = g0 >> 1, p1 = (g1 + 1) >> 1;
-#pragma unroll 4
-  for (int p = p0; p < p1; p++) {
-#endif
-    const float4 A = slabLoad<SMEM>(tab + 3 * p), B = slabLoad<SMEM>(tab + 3 * p + 1), C = slabLoad<SMEM>(tab + 3 * p + 2);
-    const float2 mx = __ffma2_rn(make_float2(A.x, A.y), r.i[0], r.no[0]);
-    const float2 my = __ffma2_rn(make_float2(A.z, A.w), r.i[1], r.no[1]);
-    const float2 mz = __ffma2_rn(make_float2(B.x, B.y), r.i[2], r.no[2]);
-    const float2 hx = make_float2(B.z, B.w), hy = make_float2(C.x, C.y), hz = make_float2(C.z, C.w);
-    const float2 nx = __ffma2_rn(hx, r.nai[0], mx), fx = __ffma2_rn(hx, r.ai[0], mx);
-    const float2 ny = __ffma2_rn(hy, r.nai[1], my), fy = __ffma2_rn(hy, r.ai[1], my);
-    const float2 nz = __ffma2_rn(hz, r.nai[2], mz), fz = __ffma2_rn(hz, r.ai[2], mz);
-    const float tn0 = fmaxf(fmaxf(nx.x, ny.x), nz.x), tn1 = fmaxf(fmaxf(nx.y, ny.y), nz.y);
-    const float2 tf = __ffma2_rn(make_float2(fminf(fminf(fx.x, fy.x), fz.x), fminf(fminf(fx.y, fy.y), fz.y)), r.grow, r.slack);
-    const bool ok0 = !(fmaxf(tn0, r.floor_t) > fminf(tf.x, r.lim));
-    const bool ok1 = !(fmaxf(tn1, r.floor_t) > fminf(tf.y, r.lim));
-#if DRT_GROUP_SKIP
-      sub |= ((ok0 ? 1u : 0u) | (ok1 ? 2u : 0u)) << (2 * (p - p0));
+    for (int k = 0; k < 4; k++) {
+      const int w = 12 * grp + 3 * k;
+      const float4 A = slabLoad<SMEM>(tab, w), B = slabLoad<SMEM>(tab, w + 1), C = slabLoad<SMEM>(tab, w + 2);
+      const float2 mx = __ffma2_rn(make_float2(A.x, A.y), r.i[0], r.no[0]);
+      const float2 my = __ffma2_rn(make_float2(A.z, A.w), r.i[1], r.no[1]);
+      const float2 mz = __ffma2_rn(make_float2(B.x, B.y), r.i[2], r.no[2]);
+      const float2 hx = make_float2(B.z, B.w), hy = make_float2(C.x, C.y), hz = make_float2(C.z, C.w);
+      const float2 nx = __ffma2_rn(hx, r.nai[0], mx), fx = __ffma2_rn(hx, r.ai[0], mx);
+      const float2 ny = __ffma2_rn(hy, r.nai[1], my), fy = __ffma2_rn(hy, r.ai[1], my);
+      const float2 nz = __ffma2_rn(hz, r.nai[2], mz), fz = __ffma2_rn(hz, r.ai[2], mz);
+      const float tn0 = fmaxf(fmaxf(nx.x, ny.x), nz.x), tn1 = fmaxf(fmaxf(nx.y, ny.y), nz.y);
+      const float2 tf = __ffma2_rn(make_float2(fminf(fminf(fx.x, fy.x), fz.x), fminf(fminf(fx.y, fy.y), fz.y)), r.grow, r.slack);
+      if (!(fmaxf(tn0, r.floor_t) > fminf(tf.x, r.lim))) sub |= 1u << (2 * k);
+      if (!(fmaxf(tn1, r.floor_t) > fminf(tf.y, r.lim))) sub |= 2u << (2 * k);
     }
     mask |= sub << (q0 - g0);
   }
-#else
-    mask |= ((ok0 ? 1u : 0u) | (ok1 ? 2u : 0u)) << (2 * (p - p0));
-  }
-#endif
-  // a ray with an infinite error bound (exactly axis-parallel) passes everything, the padding entry included
+  // a ray with an infinite error bound (exactly axis-parallel) passes everything, the padding entries included
   return mask & slabAll(g0, g1);
 }
 
@@ -630,7 +622,7 @@ __device__ __forceinline__ unsigned int slabMask(const float4* __restrict__ tab,
 // blur (mv.val != 0) is the reference tree walked node by node: bumpBVH widens leaf
 // boxes but not interior ones (quirk Q14), which can cull a moved rectangle.
 template <typename R, int F, bool COUNT>
-__device__ inline void closestHit(const Params<R>& P, const float4* __restrict__ gb, const Moved<R>& mv, const Vec<R>& ray,
+__device__ inline void closestHit(const Params<R>& P, const SlabTab gb, const Moved<R>& mv, const Vec<R>& ray,
                                   const Vec<R>& start, HitRec& h, Counts& cnt) {
   h.t = FLT_MAX; h.geom = -1; h.inside = 0; h.checker_sel = 0;
   if ((!(F & FT_REFBLUR) || mv.val == 0.0f) && !DRT_FORCE_TREE) {
@@ -780,7 +772,7 @@ __device__ inline bool geomShadow(const Params<R>& P, const Geom<R>& g, int gi, 
 // class test) and only a geom that DOES occlude is checked against the reference
 // gather, by running BoundingVolume::intersect on its leaf and every ancestor.
 template <typename R, int F, bool COUNT>
-__device__ inline bool anyHit(const Params<R>& P, const float4* __restrict__ gb, const Moved<R>& mv, const Vec<R>& gather_ray,
+__device__ inline bool anyHit(const Params<R>& P, const SlabTab gb, const Moved<R>& mv, const Vec<R>& gather_ray,
                               const Vec<R>& gather_start, const Vec<R>& ray, const Vec<R>& start, float t_max, int skip_owner,
                               Counts& cnt, bool& aborted) {
   const Vec<R> inv_ray = mk<R>(R(1) / gather_ray.x, R(1) / gather_ray.y, R(1) / gather_ray.z);   // sray.cwiseInverse() :813
@@ -1112,7 +1104,7 @@ __device__ __forceinline__ int meshOwner(const Params<R>& P, const int tri) {
 // Returns true when the ray hit something (h filled in).  `motion` is -1 unless this task is
 // on the "last invocation" chain that decides in_motion (quirk Q4), else the new flag value.
 template <typename R, int F, bool COUNT>
-__device__ inline bool traceRay(const Params<R>& P, const float4* __restrict__ gb, const Task<R>& T, HitRec& h, int& motion,
+__device__ inline bool traceRay(const Params<R>& P, const SlabTab gb, const Task<R>& T, HitRec& h, int& motion,
                                 Counts& cnt) {
   motion = -1;
   if (T.depth == 0) return false;                                       // :489
@@ -1146,6 +1138,7 @@ struct ShadeState {
   Moved<R> mv;
   float shape_color[3];
   float k;
+  uint32_t path;   // the invocation's key in the sample stream (light samples are drawn from it)
   int prim;
   int tri;         // mesh triangle id, or -1
   bool lights;     // the hit is not a light shape: the light loop has to run
@@ -1161,16 +1154,19 @@ struct PairIn {   // what a shadow pair needs to know about its hit (kept in the
   float val, dt;
   int want;
 };
-// Results of the (hit, light) pairs of one warp pass, structure-of-arrays in the warp's global scratch, index
-// light * 32 + hit: the 32 pair lanes of a pass write neighbouring words of each array and the 32 hit lanes read
-// neighbouring words back (as 32-byte records at a 256-byte stride 70-85 % of the sectors moved were waste).
+// Results of the (hit, light) pairs of one warp pass, index light * 32 + hit.  The visibility flag goes through the warp's
+// slice of shared memory.  The light vector `sray` is NOT passed on for point and rectangle lights: the hit lane draws it
+// again from the keyed stream (the same expression, so the same bits) -- cheaper than a 24-byte round trip through global
+// memory per pair, every byte of which also reached DRAM (28 GB of the 135 GB a bench frame wrote).  Only the sphere
+// light, whose sampler is a rejection loop over acos / sin / cos, hands its sample over in global structure-of-arrays
+// scratch (the 32 pair lanes of a pass write neighbouring words, the 32 hit lanes read neighbouring words back).
 template <typename R>
 struct PairOut {
-  R* x; R* y; R* z;   // sray
-  int* state;         // 0 occluded, 1 visible, 2 the light sampler aborted (reference throws)
+  R* x; R* y; R* z;          // sray of sphere-light pairs (global scratch)
+  unsigned char* state;      // shared memory: 0 occluded, 1 visible, 2 the light sampler aborted (reference throws)
 };
 template <typename R>
-__host__ __device__ constexpr size_t pairOutBytes() { return (size_t)32 * DRT_PAIR_LIGHTS * (3 * sizeof(R) + sizeof(int)); }
+__host__ __device__ constexpr size_t pairOutBytes() { return (size_t)32 * DRT_PAIR_LIGHTS * 3 * sizeof(R); }
 
 template <typename R, int F, bool COUNT>
 __device__ void shadeA(const Params<R>& P, const Task<R>& T, const HitRec& h, Task<R>* stack, int& n_out, double (&add)[3],
@@ -1363,14 +1359,14 @@ __device__ void shadeA(const Params<R>& P, const Task<R>& T, const HitRec& h, Ta
 
     S.isectP = isectP; S.normal = normal; S.e = normalized(eye - isectP);   // :795
     S.shape_color[0] = shape_color[0]; S.shape_color[1] = shape_color[1]; S.shape_color[2] = shape_color[2];
-    S.k = k; S.prim = owner; S.tri = mesh_tri; S.lights = true;
+    S.k = k; S.path = T.path; S.prim = owner; S.tri = mesh_tri; S.lights = true;
   } while (0);
   n_out = sp;
 }
 
 // LightPrimitive::sampleRay (:802) + the shadow test (:806-855) for one (hit, light) pair.
 template <typename R, int F, bool COUNT>
-__device__ void shadowPair(const Params<R>& P, const float4* __restrict__ gb, const PairIn<R>& in, int li, const PairOut<R>& out, const int oi,
+__device__ void shadowPair(const Params<R>& P, const SlabTab gb, const PairIn<R>& in, int li, const PairOut<R>& out, const int oi,
                            Counts& cnt) {
   const LightD<R>& L = P.lights[li];
   const Vec<R> isectP = in.isectP;
@@ -1381,8 +1377,10 @@ __device__ void shadowPair(const Params<R>& P, const float4* __restrict__ gb, co
   Vec<R> sray;
   if (L.type == 0) sray = L.center - isectP;                        // pointLight geometry.cpp:2751-2754
   else if (L.type == 2) sray = rectSample<R>(L.A, L.B, L.D, in.path, rng_dim_light(li, 0)) - isectP;   // :2845-2849
-  else if (!sampleSphereLight<R>(L, isectP, in.path, li, sray)) { out.state[oi] = 2; return; }   // (returns the POINT, Q10)
-  out.x[oi] = sray.x; out.y[oi] = sray.y; out.z[oi] = sray.z;
+  else {
+    if (!sampleSphereLight<R>(L, isectP, in.path, li, sray)) { out.state[oi] = 2; return; }   // (returns the POINT, Q10)
+    out.x[oi] = sray.x; out.y[oi] = sray.y; out.z[oi] = sray.z;
+  }
   const float t_max = (float)norm(sray);                            // :804
   const Vec<R> sdir = normalized(sray);
   if (COUNT) cnt.shadow_rays++;
@@ -1406,7 +1404,10 @@ __device__ void shadeB(const Params<R>& P, ShadeState<R>& S, const PairOut<R>& r
     if (state == 2) { S.aborted = true; break; }                     // throws geometry.cpp:2785-2789
     if (state == 0) continue;                                         // shadowed :852-855
     const LightD<R>& L = P.lights[li];
-    const Vec<R> sray = mk<R>(res.x[oi], res.y[oi], res.z[oi]);
+    Vec<R> sray;                                                      // as shadowPair drew it
+    if (L.type == 0) sray = L.center - S.isectP;
+    else if (L.type == 2) sray = rectSample<R>(L.A, L.B, L.D, S.path, rng_dim_light(li, 0)) - S.isectP;
+    else sray = mk<R>(res.x[oi], res.y[oi], res.z[oi]);
     const Vec<R> sdir = normalized(sray);
       // ---- texture (:859-893) ---------------------------------------------------
       if ((F & FT_TEX) && (pr.flags & 4)) {
@@ -1645,10 +1646,10 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
   __shared__ long long s_idx0, s_unit_next, s_unit_end;
   // slab-filter table of the whole scene, staged once per persistent CTA (48 B per pair of geoms)
   __shared__ float4 s_gb[3 * DRT_SMEM_GEOMS / 2 + 2 * DRT_SMEM_GEOMS / 8];
-  const float4* gb = P.gbounds;
+  SlabTab gb; gb.g = P.gbounds; gb.s = 0u;
   if (!(F & FT_BIG) || P.n_geoms <= DRT_SMEM_GEOMS) {
-    for (int i = threadIdx.x; i < 3 * ((P.n_geoms + 1) / 2) + 2 * ((P.n_geoms + 7) / 8); i += blockDim.x) s_gb[i] = P.gbounds[i];
-    gb = s_gb;
+    for (int i = threadIdx.x; i < slabPairWords(P.n_geoms) + 2 * ((P.n_geoms + 7) / 8); i += blockDim.x) s_gb[i] = P.gbounds[i];
+    gb.s = (unsigned)__cvta_generic_to_shared(s_gb);
   }
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, tid = threadIdx.x;
@@ -1657,8 +1658,9 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
   HitTask<R>* hits = (HitTask<R>*)(cbase + (size_t)P.pool_cap * sizeof(Task<R>));
   char* wbase = (char*)(hits + DRT_CTA_HITS) + (size_t)wib * pairOutBytes<R>();
   PairOut<R> pairout;
+  __shared__ unsigned char s_pstate[DRT_WAVE_WARPS * 32 * DRT_PAIR_LIGHTS];
   pairout.x = (R*)wbase; pairout.y = pairout.x + 32 * DRT_PAIR_LIGHTS; pairout.z = pairout.y + 32 * DRT_PAIR_LIGHTS;
-  pairout.state = (int*)(pairout.z + 32 * DRT_PAIR_LIGHTS);
+  pairout.state = s_pstate + wib * 32 * DRT_PAIR_LIGHTS;
   unsigned long long(*acc)[3] = s_acc;
   unsigned int* sfl = s_flags;
   const long long n_units = (P.sample_count + P.unit_samples - 1) / P.unit_samples;
