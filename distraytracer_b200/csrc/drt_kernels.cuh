@@ -775,7 +775,6 @@ template <typename R, int F, bool COUNT>
 __device__ inline bool anyHit(const Params<R>& P, const SlabTab gb, const Moved<R>& mv, const Vec<R>& gather_ray,
                               const Vec<R>& gather_start, const Vec<R>& ray, const Vec<R>& start, float t_max, int skip_owner,
                               Counts& cnt, bool& aborted) {
-  const Vec<R> inv_ray = mk<R>(R(1) / gather_ray.x, R(1) / gather_ray.y, R(1) / gather_ray.z);   // sray.cwiseInverse() :813
   if ((!(F & FT_REFBLUR) || mv.val == 0.0f) && !DRT_FORCE_TREE) {
     const float ix = 1.0f / (float)ray.x, iy = 1.0f / (float)ray.y, iz = 1.0f / (float)ray.z;
     const float ox = -(float)start.x * ix, oy = -(float)start.y * iy, oz = -(float)start.z * iz;   // slabMayHit's hoisted terms
@@ -806,6 +805,7 @@ __device__ inline bool anyHit(const Params<R>& P, const SlabTab gb, const Moved<
         // exact replay of the reference's box tests.
         if (t_occ > gather_lead * 1.001f + 2e-3f) return true;
         bool gathered = true;
+        const Vec<R> inv_ray = mk<R>(R(1) / gather_ray.x, R(1) / gather_ray.y, R(1) / gather_ray.z);   // sray.cwiseInverse() :813 (rare path: three divisions)
         for (int ni = g.leaf; ni >= 0 && gathered; ni = P.nodes[ni].parent) {
           if (COUNT) cnt.node_tests++;
           gathered = boxHit<R, F>(P.nodes[ni], gather_ray, inv_ray, gather_start, mv);
@@ -818,6 +818,7 @@ __device__ inline bool anyHit(const Params<R>& P, const SlabTab gb, const Moved<
   int stack[DRT_NODE_STACK];
   int sp = 0;
   stack[sp++] = 0;
+  const Vec<R> inv_ray = mk<R>(R(1) / gather_ray.x, R(1) / gather_ray.y, R(1) / gather_ray.z);   // sray.cwiseInverse() :813
   while (sp > 0) {
     const NodeD<R>& nd = P.nodes[stack[--sp]];
     if (COUNT) cnt.node_tests++;
