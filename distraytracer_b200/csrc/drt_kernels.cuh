@@ -18,6 +18,7 @@
 #pragma once
 #include "drt_device.cuh"
 #include "drt_launch.h"
+#include <cstddef>
 
 #ifndef DRT_FORCE_TREE
 #define DRT_FORCE_TREE 0   // diagnostic: 1 walks the replayed reference tree for every ray
@@ -27,7 +28,8 @@ namespace drt {
 
 
 // One pending rayColor invocation: 64 bytes in the reference precision (48 in single), four 16-byte words.  Every ray
-// is written to the CTA pool once and read once, and again inside its hit record, so the record size is DRAM traffic.
+// is written to the CTA pool once and stays in its slot until it is finished: TRACE reads it, and when it hit something
+// SHADE reads it again through the 16-byte hit record (HitRef) -- the record size is DRAM traffic.
 template <typename R>
 struct alignas(16) Task {
   Vec<R> org, dir;
@@ -42,28 +44,30 @@ struct alignas(16) Task {
 #define TASK_CHAIN 1
 #define TASK_ROOT 2
 static_assert(sizeof(Task<double>) == 64 && sizeof(Task<float>) == 48, "ray records are whole 16-byte words");
+static_assert(offsetof(Task<double>, depth) >= 48 && offsetof(Task<float>, depth) >= 32, "depth lives in the last word (poolStoreEmpty)");
 
-// The CTA ray pool and hit buffer are stored as planes of 16-byte words: word w of record i lives at plane w, slot i.
-// Warps pop and push runs of neighbouring slots, so every load / store instruction of a warp covers 512 contiguous
-// bytes (whole sectors) instead of 32 half-used sectors at a 64-byte stride.  The records are written once and read
-// once, so they bypass the L1, which is better spent on the geom / material records and the local-memory frames.
-// stores keep the record in the L2 under the normal policy (it is read back within a pass or two), the one load
-// marks it evict-first; neither allocates in the L1
-#ifndef DRT_POOL_LD
-#define DRT_POOL_LD __ldcs
-#define DRT_POOL_ST __stcg
-#endif
-template <typename T>
+// The CTA ray pool is stored as planes of 16-byte words: word w of record i lives at plane w, slot i.  Warps pop and push
+// runs of neighbouring slots, so every load / store instruction of a warp covers 512 contiguous bytes (whole sectors)
+// instead of 32 half-used sectors at a 64-byte stride.  The records bypass the L1, which is better spent on the geom /
+// material records and the local-memory frames: stores keep the record in the L2 under the normal policy (it is read back
+// within a pass or two), the loads are streaming ones (measured: TRACE's load with the normal policy, so that SHADE's
+// second read of a ray that hit finds it in the L2 more often, 740-742 vs 744-746 Msamples/s).
+template <typename T, bool STREAM>
 __device__ __forceinline__ void poolLoad(T& dst, const uint4* planes, const size_t cap, const int i) {
   uint4* d = reinterpret_cast<uint4*>(&dst);
 #pragma unroll
-  for (int w = 0; w < (int)(sizeof(T) / 16); w++) d[w] = DRT_POOL_LD(planes + w * cap + i);
+  for (int w = 0; w < (int)(sizeof(T) / 16); w++) d[w] = STREAM ? __ldcs(planes + w * cap + i) : __ldcg(planes + w * cap + i);
 }
 template <typename T>
 __device__ __forceinline__ void poolStore(uint4* planes, const size_t cap, const int i, const T& src) {
   const uint4* q = reinterpret_cast<const uint4*>(&src);
 #pragma unroll
-  for (int w = 0; w < (int)(sizeof(T) / 16); w++) DRT_POOL_ST(planes + w * cap + i, q[w]);
+  for (int w = 0; w < (int)(sizeof(T) / 16); w++) __stcg(planes + w * cap + i, q[w]);
+}
+// an empty slot of a partly filled chunk: only the last word (it holds `depth`) is written; depth 0 makes TRACE skip it
+template <typename T>
+__device__ __forceinline__ void poolStoreEmpty(uint4* planes, const size_t cap, const int i) {
+  __stcg(planes + (sizeof(T) / 16 - 1) * cap + i, make_uint4(0u, 0u, 0u, 0u));
 }
 
 template <typename R>
@@ -1087,13 +1091,12 @@ __device__ __noinline__ void evalBRDF(const PrimD<R>& pr, const float* Lcolor, c
 // Every invocation ADDS exactly one k-weighted term to the sample's colour (emissive
 // term or the hits-averaged light sum) and spawns up to brdf_samples+1 child rays; the
 // children are returned to the caller, which owns the scheduling.
-template <typename R>
-struct alignas(16) HitTask {
-  Task<R> T;
+// What TRACE leaves for SHADE about a ray that hit: 16 bytes.  The ray itself stays in its pool slot.
+struct alignas(16) HitRef {
   float t;
   int geom;
-  int inside;
-  int checker_sel;
+  int inside_sel;   // inside | checker_sel << 1
+  int slot;         // pool slot of the ray
 };
 
 // shading record of mesh triangle `tri`: the mesh's material table follows the analytic primitives
@@ -1608,9 +1611,10 @@ __device__ __noinline__ void primaryRay(const Params<R>& P, long long gidx, cons
   dir = focalPoint - eye_sample;
 }
 
-// Scratch of one persistent CTA in global memory (L1/L2 resident):
-//   [ pool_cap ray tasks | DRT_CTA_HITS hit tasks | per warp: 32 x DRT_PAIR_LIGHTS shadow-pair results ]
-// pool_cap (Params::pool_cap) is sized per render on the host from brdf_samples / max_depth / blur_samples.
+// Scratch of one persistent CTA in global memory (L2 resident):
+//   [ pool_cap ray slots | DRT_CTA_HITS hit references | per warp: sphere-light samples of 32 x DRT_PAIR_LIGHTS shadow pairs |
+//     three u32 tables of pool_cap / 32 chunk ids: stack, free list, in flight ]
+// pool_cap (Params::pool_cap, a multiple of 32) is sized per render on the host from brdf_samples / max_depth / blur_samples.
 #ifndef DRT_WAVE_CTAS_PER_SM
 #define DRT_WAVE_CTAS_PER_SM 1
 #endif
@@ -1618,8 +1622,8 @@ __device__ __noinline__ void primaryRay(const Params<R>& P, long long gidx, cons
 __host__ __device__ constexpr size_t waveDynSmemBytes() { return (size_t)DRT_CTA_SLOTS * 28 + (size_t)DRT_CTA_HITS * 3; }
 template <typename R>
 __host__ __device__ constexpr size_t waveScratchBytes(int pool_cap) {
-  return (size_t)pool_cap * sizeof(Task<R>) + DRT_CTA_HITS * sizeof(HitTask<R>) +
-         DRT_WAVE_WARPS * pairOutBytes<R>();
+  return (size_t)pool_cap * sizeof(Task<R>) + DRT_CTA_HITS * sizeof(HitRef) + DRT_WAVE_WARPS * pairOutBytes<R>() +
+         3 * (size_t)(pool_cap / 32) * sizeof(uint32_t);
 }
 
 // render_wave -- phase-locked persistent CTA with CTA-wide work pools.
@@ -1629,11 +1633,19 @@ __host__ __device__ constexpr size_t waveScratchBytes(int pool_cap) {
 // hold one phase's code: with free-running warps the 14k-instruction kernel saturated the GPC
 // instruction cache (ncu: gcc__cache_requests_type_instruction 95 % of peak,
 // sm__icc_request_hit_rate 62 %, 43 % of stall samples "no_instructions").
-// Pending rays and hits of the CTA's current batch (DRT_CTA_SLOTS camera samples) live in ONE
-// LIFO pool / hit buffer per CTA; inside a phase every warp keeps grabbing the next 32 items
-// from the top through a shared-memory cursor until the phase's work is gone, so all lanes of
-// all warps stay busy and a phase ends within one 32-item chunk of the last warp (with
-// warp-private pools 27 % of the stall samples were barrier waits).
+// Pending rays of the CTA's current batch (DRT_CTA_SLOTS camera samples) live in ONE pool per CTA; inside a phase every
+// warp keeps grabbing the next 32 items through a shared-memory cursor until the phase's work is gone, so all lanes of
+// all warps stay busy and a phase ends within one 32-item bite of the last warp (with warp-private pools 27 % of the
+// stall samples were barrier waits).
+//
+// The pool is managed in CHUNKS of 32 slots (one bite of a warp).  A LIFO stack of chunk ids says which chunks hold
+// pending rays, a free list which ones are empty.  TRACE pops a chunk and traces its rays; a ray that hit something STAYS
+// in its slot and only a 16-byte reference (HitRef) goes to the hit buffer, so a chunk with hits is "in flight" until SHADE
+// has consumed them (a chunk without hits is free at once).  SHADE writes the children into chunks taken from the free
+// list -- every warp fills its own open chunk and pushes it when it is full -- and when the phase ends the chunks in
+// flight return to the free list.  (Round 1 copied every ray that hit into an 80-byte hit record: 64 more bytes
+// written to DRAM per hit, ~45 GB per bench frame.)  Slots a warp leaves unfilled in its last chunk of a phase are marked
+// empty (depth 0, which TRACE skips like the reference's `depth == 0` return).
 template <typename R, int F, bool COUNT>
 __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) render_wave(const __grid_constant__ Params<R> P) {
   // dynamic shared memory (waveDynSmemBytes): [ acc: slots x 3 x u64 | flags: slots x u32 | order: hits x u16 | hkey: hits x u8 ]
@@ -1642,7 +1654,9 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
   unsigned int* s_flags = (unsigned int*)(s_dyn + (size_t)DRT_CTA_SLOTS * 24);
   unsigned short* s_order = (unsigned short*)(s_dyn + (size_t)DRT_CTA_SLOTS * 28);
   unsigned char* s_hkey = s_dyn + (size_t)DRT_CTA_SLOTS * 28 + (size_t)DRT_CTA_HITS * 2;
-  __shared__ int s_count, s_nhits, s_grab, s_state, s_nvalid;
+  // s_nst: chunks on the stack; s_nfree: chunks on the free list; s_ninfl: chunks in flight; s_npush: chunks SHADE pushed so far;
+  // s_count: rays generated by a blur re-trace pass
+  __shared__ int s_nst, s_nfree, s_ninfl, s_npush, s_count, s_nhits, s_grab, s_state, s_nvalid;
   __shared__ int s_hist[DRT_HIT_BUCKETS];                 // SHADE order: counting sort of the hit buffer by geom
   __shared__ long long s_idx0, s_unit_next, s_unit_end;
   // slab-filter table of the whole scene, staged once per persistent CTA (48 B per pair of geoms)
@@ -1654,10 +1668,15 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
   }
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, tid = threadIdx.x;
+  const size_t cap = (size_t)P.pool_cap;
+  const int n_chunks = P.pool_cap >> 5;
   char* cbase = (char*)P.pool_raw + (size_t)blockIdx.x * waveScratchBytes<R>(P.pool_cap);
   uint4* pool = (uint4*)cbase;                                         // planes of 16-byte words, see poolLoad
-  HitTask<R>* hits = (HitTask<R>*)(cbase + (size_t)P.pool_cap * sizeof(Task<R>));
+  uint4* hits = (uint4*)(cbase + cap * sizeof(Task<R>));               // HitRef records
   char* wbase = (char*)(hits + DRT_CTA_HITS) + (size_t)wib * pairOutBytes<R>();
+  uint32_t* stk = (uint32_t*)((char*)(hits + DRT_CTA_HITS) + (size_t)DRT_WAVE_WARPS * pairOutBytes<R>());
+  uint32_t* fre = stk + n_chunks;
+  uint32_t* infl = fre + n_chunks;
   PairOut<R> pairout;
   __shared__ unsigned char s_pstate[DRT_WAVE_WARPS * 32 * DRT_PAIR_LIGHTS];
   pairout.x = (R*)wbase; pairout.y = pairout.x + 32 * DRT_PAIR_LIGHTS; pairout.z = pairout.y + 32 * DRT_PAIR_LIGHTS;
@@ -1670,16 +1689,20 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
   if (COUNT) { cnt.samples = 0; cnt.rays = 0; cnt.shadow_rays = 0; cnt.shade_evals = 0; cnt.noise_evals = 0; cnt.node_tests = 0;
                for (int i = 0; i < 7; i++) cnt.geom_tests[i] = 0; }
 
+  // every chunk starts on the free list, lowest id on top
+  for (int i = tid; i < n_chunks; i += blockDim.x) __stcg(fre + i, (uint32_t)(n_chunks - 1 - i));
   // s_state: 0 = no batch, 1 = primary trees in flight, 2 = blur re-traces in flight, 3 = all batches done
-  if (tid == 0) { s_count = 0; s_nhits = 0; s_state = 0; s_nvalid = 0; s_idx0 = 0; s_unit_next = 0; s_unit_end = 0; }
+  if (tid == 0) { s_nst = 0; s_nfree = n_chunks; s_ninfl = 0; s_npush = 0; s_count = 0; s_nhits = 0; s_state = 0; s_nvalid = 0;
+                  s_idx0 = 0; s_unit_next = 0; s_unit_end = 0; }
   __syncthreads();
 
   for (;;) {
     // ================= GEN: batch bookkeeping (rare) =================================
-    if (s_count == 0 && s_nhits == 0) {                                  // CTA-uniform: the current trees are drained
+    if (s_nst == 0 && s_nhits == 0) {                                    // CTA-uniform: the current trees are drained
       const int state = s_state;
       const int n_valid = s_nvalid;
       const long long idx0 = s_idx0;
+      const int f0 = s_nfree;                                            // every chunk is free here: f0 == n_chunks
       __syncthreads();
       bool finalize = false;
       if ((F & (FT_VEL | FT_REFBLUR)) && state == 1 && P.blur_samples > 0) {
@@ -1700,10 +1723,17 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
               float frame_sample = (float)((double)(float)P.frame + (double)rng_u01(skey, (uint32_t)m) * (double)P.frame_range);
               T.dt = frame_sample - (float)P.frame;
               T.path = rng_key_child(skey, 1 + m);
-              poolStore(pool, (size_t)P.pool_cap, at + m, T);                                         // <= DRT_CTA_SLOTS * blur_samples, validated on the host
+              // ray number at + m goes to lane (at + m) % 32 of the ((at + m) / 32)-th chunk from the top of the free list
+              // (<= DRT_CTA_SLOTS * blur_samples rays, within the pool by the host's sizing)
+              const int q = at + m;
+              poolStore(pool, cap, (int)__ldcg(fre + f0 - 1 - (q >> 5)) * 32 + (q & 31), T);
             }
           }
-          if (tid == 0) s_state = 2;
+          __syncthreads();
+          const int total = s_count, nch = (total + 31) >> 5;
+          for (int q = total + tid; q < nch * 32; q += blockDim.x) poolStoreEmpty<Task<R>>(pool, cap, (int)__ldcg(fre + f0 - 1 - (q >> 5)) * 32 + (q & 31));
+          for (int c = tid; c < nch; c += blockDim.x) __stcg(stk + c, __ldcg(fre + f0 - 1 - c));
+          if (tid == 0) { s_state = 2; s_nst = nch; s_nfree = f0 - nch; s_count = 0; }
         } else finalize = true;
       } else if (state == 1 || state == 2) finalize = true;
       if (finalize) {
@@ -1766,60 +1796,70 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
         // the hit-sort scratch is idle while the pool is empty: it holds the swap targets of the batch's lens-sample shuffles
         const bool have_perm = lensSwapTargetsFill<R>(P, P.sample_base + i0, nv, s_order, DRT_CTA_HITS);
         const int perm_pt0 = (int)((P.sample_base + i0) / P.spp);
-        for (int s2 = tid; s2 < nv; s2 += blockDim.x) {                  // primary rays -> pool[0..nv)
+        const int nch = (nv + 31) >> 5;                                  // primary rays -> the first nch chunks of the free list
+        for (int s2 = tid; s2 < nch * 32; s2 += blockDim.x) {
+          const uint32_t id = __ldcg(fre + f0 - 1 - (s2 >> 5));
+          if ((s2 & 31) == 0) __stcg(stk + (s2 >> 5), id);
+          if (s2 >= nv) { poolStoreEmpty<Task<R>>(pool, cap, (int)id * 32 + (s2 & 31)); continue; }
           Task<R> T; uint32_t skey; int pi, pj, px, py;
           primaryRay<R>(P, P.sample_base + i0 + s2, have_perm ? s_order : nullptr, perm_pt0, true, T.org, T.dir, skey, pi, pj, px, py);
           T.k = 1.0f; T.path = rng_key_child(skey, 0); T.dt = 0.f; T.depth = (unsigned char)P.max_depth;
           T.bits = TASK_CHAIN | TASK_ROOT; T.slot = (unsigned short)s2;
-          poolStore(pool, (size_t)P.pool_cap, s2, T);
+          poolStore(pool, cap, (int)id * 32 + (s2 & 31), T);
           if (COUNT) cnt.samples++;
         }
-        if (tid == 0) s_count = nv;
+        if (tid == 0) { s_nst = nch; s_nfree = f0 - nch; }
       }
       __syncthreads();
     }
 
-    // ================= TRACE: closest hits; the HITS are compacted into the hit buffer ====
+    // ================= TRACE: closest hits; a ray that hit stays in its slot, its reference goes to the hit buffer ====
     // (rays that miss are finished: they only update the in_motion chain flag)
-    if (tid == 0) s_grab = s_count;
+    const int nst0 = s_nst;
+    if (tid == 0) s_grab = nst0;
     __syncthreads();
     for (;;) {
       if (((volatile int*)&s_nhits)[0] >= DRT_TRACE_HITS_TARGET) break;  // enough hits for a full SHADE pass are waiting
-      int end = 0;
-      if (lane == 0) end = atomicSub(&s_grab, 32);
-      end = __shfl_sync(FULL, end, 0);
-      if (end <= 0) break;
-      const int begin = max(end - 32, 0);
-      const bool active = begin + lane < end;
+      int top = 0;
+      uint32_t id = 0;
+      if (lane == 0) { top = atomicSub(&s_grab, 1); if (top > 0) id = __ldcg(stk + top - 1); }
+      top = __shfl_sync(FULL, top, 0);
+      if (top <= 0) break;
+      id = __shfl_sync(FULL, id, 0);
+      const int slot = (int)id * 32 + lane;
       bool hit = false;
-      HitTask<R> H;
-      if (active) {
-        poolLoad(H.T, pool, (size_t)P.pool_cap, end - 1 - lane);
-        const unsigned int f = ((volatile unsigned int*)sfl)[H.T.slot];
-        if (!(f & SF_ABORT)) {                                          // an aborted sample spawns no more work (Q15)
-          HitRec h; int motion;
-          hit = traceRay<R, F, COUNT>(P, gb, H.T, h, motion, cnt);
+      HitRec h; h.t = 0.f; h.geom = -1; h.inside = 0; h.checker_sel = 0;
+      {
+        Task<R> T;
+        poolLoad<Task<R>, true>(T, pool, cap, slot);
+        if (T.depth != 0 && !(((volatile unsigned int*)sfl)[T.slot] & SF_ABORT)) {   // empty slot / an aborted sample spawns no more work (Q15)
+          int motion;
+          hit = traceRay<R, F, COUNT>(P, gb, T, h, motion, cnt);
           unsigned int orf = 0;
-          if ((H.T.bits & TASK_ROOT) && hit) orf |= SS_HIT;
+          if ((T.bits & TASK_ROOT) && hit) orf |= SS_HIT;
           if (motion == 1) orf |= SS_MOTION;
-          if (orf) atomicOr(&sfl[H.T.slot], orf);
-          if (motion == 0) atomicAnd(&sfl[H.T.slot], ~SS_MOTION);
-          H.t = h.t; H.geom = h.geom; H.inside = h.inside; H.checker_sel = h.checker_sel;
+          if (orf) atomicOr(&sfl[T.slot], orf);
+          if (motion == 0) atomicAnd(&sfl[T.slot], ~SS_MOTION);
         }
       }
       const unsigned int hm = __ballot_sync(FULL, hit);
       int hbase = 0;
-      if (lane == 0 && hm) hbase = atomicAdd(&s_nhits, __popc(hm));
+      if (lane == 0) {
+        if (hm) { hbase = atomicAdd(&s_nhits, __popc(hm)); __stcg(infl + atomicAdd(&s_ninfl, 1), id); }   // in flight until SHADE is done
+        else __stcg(fre + atomicAdd(&s_nfree, 1), id);                                                  // nothing left in it
+      }
       hbase = __shfl_sync(FULL, hbase, 0);
       if (hit) {
         const int at = hbase + __popc(hm & ((1u << lane) - 1u));
-        poolStore((uint4*)hits, (size_t)DRT_CTA_HITS, at, H);
-        s_hkey[at] = (unsigned char)min(H.geom, DRT_HIT_BUCKETS - 1);
+        __stcg(hits + at, make_uint4(__float_as_uint(h.t), (unsigned)h.geom, (unsigned)(h.inside | (h.checker_sel << 1)), (unsigned)slot));
+        s_hkey[at] = (unsigned char)min(h.geom, DRT_HIT_BUCKETS - 1);
       }
     }
     __syncthreads();
     const int nh = s_nhits;
-    if (tid == 0) { s_count = max(s_grab, 0); s_grab = nh; }             // untouched rays stay at the bottom of the pool
+    const int nst_base = max(s_grab, 0);                                 // untouched chunks stay at the bottom of the stack
+    __syncthreads();
+    if (tid == 0) s_grab = nh;
     // ---- counting sort of the waiting hits by geom: the 32 hits a warp shades together then share
     // the material / model / texture branches of shadeA, evalBRDF and shadeB, and their shadow rays
     // leave from the same surface
@@ -1852,6 +1892,7 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
     __syncthreads();
 
     // ================= SHADE: waiting hits -> radiance terms + child rays ====================
+    int open_id = -1, open_fill = 0;                                     // the warp's partly filled chunk of children (warp-uniform)
     for (;;) {
       int end = 0;
       if (lane == 0) end = atomicSub(&s_grab, 32);
@@ -1868,12 +1909,13 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
       // -- step A (lane = hit): normal, children, emissive term
       PairIn<R> pin; pin.want = 0; pin.isectP = mk<R>(R(0), R(0), R(0)); pin.path = 0u; pin.val = 0.f; pin.dt = 0.f;
       if (active) {
-        HitTask<R> H;
-        poolLoad(H, (const uint4*)hits, (size_t)DRT_CTA_HITS, (int)s_order[end - 1 - lane]);
-        HitRec h; h.t = H.t; h.geom = H.geom; h.inside = H.inside; h.checker_sel = H.checker_sel;
-        slot = H.T.slot;
-        shadeA<R, F, COUNT>(P, H.T, h, kids, nk, add, has_add, aborted, S, cnt);
-        if (!aborted && S.lights) { pin.isectP = S.isectP; pin.path = H.T.path; pin.val = S.mv.val; pin.dt = H.T.dt; pin.want = 1; }
+        const uint4 hr = __ldcs(hits + (int)s_order[end - 1 - lane]);
+        Task<R> T;
+        poolLoad<Task<R>, true>(T, pool, cap, (int)hr.w);
+        HitRec h; h.t = __uint_as_float(hr.x); h.geom = (int)hr.y; h.inside = (int)(hr.z & 1u); h.checker_sel = (int)(hr.z >> 1);
+        slot = T.slot;
+        shadeA<R, F, COUNT>(P, T, h, kids, nk, add, has_add, aborted, S, cnt);
+        if (!aborted && S.lights) { pin.isectP = S.isectP; pin.path = T.path; pin.val = S.mv.val; pin.dt = T.dt; pin.want = 1; }
       }
       // -- step B (lane = (hit, light) pair): light sample + shadow ray, DRT_PAIR_LIGHTS lights at a time; a pair lane
       //    fetches its hit's point from the hit lane by shuffle
@@ -1916,30 +1958,55 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
           if (orf) atomicOr(&sfl[slot], orf);
         }
       }
-      // compact the children onto the top of the CTA pool, child-index-major: the j-th children of the
-      // warp's 32 (geom-sorted) hits -- the same kind of ray leaving the same surface -- end up adjacent,
-      // so a later TRACE warp works on rays with similar candidates
-      unsigned int kb[DRT_MAX_CHILDREN];
-      int total = 0;
-#pragma unroll
-      for (int j = 0; j < DRT_MAX_CHILDREN; j++) { kb[j] = __ballot_sync(FULL, nk > j); total += __popc(kb[j]); }
-      int pbase = 0;
-      if (lane == 0 && total) pbase = atomicAdd(&s_count, total);
-      pbase = __shfl_sync(FULL, pbase, 0);
-      if (pbase + total > P.pool_cap) {                               // cannot happen within the validated bounds
-        if (nk) atomicOr(&sfl[kids[0].slot], SF_ABORT);
-        if (lane == 0) { *P.overflow = 1; atomicSub(&s_count, total); }
-      } else {
-        int base = pbase;
-#pragma unroll
-        for (int j = 0; j < DRT_MAX_CHILDREN; j++) {
-          if (nk > j) poolStore(pool, (size_t)P.pool_cap, base + __popc(kb[j] & ((1u << lane) - 1u)), kids[j]);
-          base += __popc(kb[j]);
+      // the children go into the warp's open chunk and on into fresh chunks from the free list, child-index-major: the
+      // j-th children of the warp's 32 (geom-sorted) hits -- the same kind of ray leaving the same surface -- end up
+      // adjacent, so a later TRACE warp works on rays with similar candidates
+      const int total = __reduce_add_sync(FULL, nk);
+      if (total) {
+        const int have = open_id >= 0 ? 1 : 0;                            // open_fill is 0 without an open chunk
+        const int touched = (open_fill + total + 31) >> 5;                // chunks written to: the open one (if any), then new ones
+        const int fresh = touched - have;
+        int f = 0;
+        if (lane == 0 && fresh) f = atomicSub(&s_nfree, fresh);
+        f = __shfl_sync(FULL, f, 0);
+        if (fresh && f < fresh) {                                         // cannot happen within the validated bounds
+          if (nk) atomicOr(&sfl[kids[0].slot], SF_ABORT);
+          if (lane == 0) { *P.overflow = 1; atomicAdd(&s_nfree, fresh); }
+        } else {
+          int myid = -1;                                                  // lane k: id of the k-th chunk written to
+          if (lane < touched) myid = (have && lane == 0) ? open_id : (int)__ldcg(fre + f - 1 - (lane - have));
+          int base = open_fill;
+#pragma unroll 1
+          for (int j = 0; j < DRT_MAX_CHILDREN; j++) {                    // a rolled loop: the bench workload has at most 3 children per hit
+            const unsigned int kbj = __ballot_sync(FULL, nk > j);
+            if (!kbj) break;
+            const int g = base + __popc(kbj & ((1u << lane) - 1u));
+            const int cid = __shfl_sync(FULL, myid, (nk > j) ? (g >> 5) : 0);
+            if (nk > j) poolStore(pool, cap, cid * 32 + (g & 31), kids[j]);
+            base += __popc(kbj);
+          }
+          const int full = base >> 5;                                     // chunks completed by this bite
+          int pp = 0;
+          if (lane == 0 && full) pp = atomicAdd(&s_npush, full);
+          pp = __shfl_sync(FULL, pp, 0);
+          if (lane < full) __stcg(stk + nst_base + pp + lane, (uint32_t)myid);
+          open_fill = base & 31;
+          open_id = __shfl_sync(FULL, myid, min(full, 31));
+          if (!open_fill) open_id = -1;
         }
       }
     }
+    if (open_id >= 0) {                                                  // the warp's last chunk of this pass: mark the unused slots, push it
+      if (lane >= open_fill) poolStoreEmpty<Task<R>>(pool, cap, open_id * 32 + lane);
+      if (lane == 0) __stcg(stk + nst_base + atomicAdd(&s_npush, 1), (uint32_t)open_id);
+    }
     __syncthreads();
-    if (tid == 0) s_nhits = 0;
+    {                                                                    // the chunks in flight are consumed: back to the free list
+      const int ninfl = s_ninfl, f = s_nfree;
+      for (int i = tid; i < ninfl; i += blockDim.x) __stcg(fre + f + i, __ldcg(infl + i));
+      __syncthreads();
+      if (tid == 0) { s_nfree = f + ninfl; s_ninfl = 0; s_nst = nst_base + s_npush; s_npush = 0; s_nhits = 0; }
+    }
     __syncthreads();
   }
 

@@ -1,7 +1,5 @@
 #!/bin/bash
-# A/B of the non-headline configurations: tools/ab_configs.sh <variant name> [configs...]
+# A/B of the other BASELINE configurations: in-tree library vs variants/*.so (same box)
 cd "$(dirname "$0")/.."
-v=$1; shift
-cfgs="$@"; [ -z "$cfgs" ] && cfgs="c4 c5"
-echo "== in-tree"; python tools/bench_configs.py $cfgs 2>/dev/null | python -c "import sys,json; [print(json.loads(l)['config'][:40], round(json.loads(l)['ms'],2)) for l in sys.stdin]"
-echo "== $v"; DRT_LIB=$PWD/variants/libdrt_$v.so python tools/bench_configs.py $cfgs 2>/dev/null | python -c "import sys,json; [print(json.loads(l)['config'][:40], round(json.loads(l)['ms'],2)) for l in sys.stdin]"
+echo "== in-tree"; python tools/bench_configs.py c1 c3 c4 c5 2>&1 | grep '"config"' | python -c "import sys,json; [print('  ', d['config'][:40], round(d['ms'],2)) for d in map(json.loads, sys.stdin)]"
+for v in variants/*.so; do echo "== $v"; DRT_LIB=$PWD/$v python tools/bench_configs.py c1 c3 c4 c5 2>&1 | grep '"config"' | python -c "import sys,json; [print('  ', d['config'][:40], round(d['ms'],2)) for d in map(json.loads, sys.stdin)]"; done
