@@ -120,6 +120,7 @@ template <typename R>
 struct HostScene {
   std::vector<NodeD<R>> nodes;
   std::vector<float4> gbounds;
+  int geom_tree = -1;       // word offset of the geom tree appended to gbounds, or -1
   std::vector<Geom<R>> geoms;
   std::vector<PrimD<R>> prims;
   std::vector<LightD<R>> lights;
@@ -349,6 +350,79 @@ int flatten(const drt_prim* prims, int n_prims, const drt_light* lights, int n_l
     hs.gbounds.push_back(make_float4(c[0], c[1], c[2], h[0]));
     hs.gbounds.push_back(make_float4(h[1], h[2], 0.f, 0.f));
   }
+  // ... and, for scenes with more geoms than the shared-memory table holds, by a 4-wide tree over the geoms in the node
+  // format of the mesh LBVH (drt_lbvh.cuh): closestHit / anyHit then gather candidates in O(log n) instead of running the
+  // filter over all n.  Median splits of the box centres along the widest axis, twice per node; leaf = one geom
+  // (reference -(geom + 1)).  Not built when a slab-box prism is present: its intersectShadow can throw, and which
+  // pixels then abort depends on the reference's candidate ORDER, which only the linear walk keeps.
+  hs.geom_tree = -1;
+  {
+    std::vector<int> items;
+    bool any_box = false;
+    for (size_t gi = 0; gi < hs.geoms.size(); gi++) {
+      if (hs.geoms[gi].type == G_BOX) any_box = true;
+      if (hs.geoms[gi].type != G_HOLE) items.push_back((int)gi);
+    }
+    if ((int)hs.geoms.size() > DRT_SMEM_GEOMS && !any_box && items.size() >= 2) {
+      struct Box { float lo[3], hi[3]; };
+      auto boxOf = [&](const int* first, const int* last) {
+        Box b; for (int a = 0; a < 3; a++) { b.lo[a] = FLT_MAX; b.hi[a] = -FLT_MAX; }
+        for (const int* it = first; it != last; ++it)
+          for (int a = 0; a < 3; a++) { b.lo[a] = std::min(b.lo[a], (&hs.geoms[*it].blo.x)[a]); b.hi[a] = std::max(b.hi[a], (&hs.geoms[*it].bhi.x)[a]); }
+        return b;
+      };
+      auto halve = [&](int* first, int* last) {            // median split along the widest axis of the box centres
+        float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+        auto centre = [&](int gi, int a) { return 0.5f * ((&hs.geoms[gi].blo.x)[a] + (&hs.geoms[gi].bhi.x)[a]); };
+        for (int* it = first; it != last; ++it) for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], centre(*it, a)); hi[a] = std::max(hi[a], centre(*it, a)); }
+        int ax = 0; for (int a = 1; a < 3; a++) if (hi[a] - lo[a] > hi[ax] - lo[ax]) ax = a;
+        int* mid = first + (last - first) / 2;
+        std::nth_element(first, mid, last, [&](int x, int y) { const float cx = centre(x, ax), cy = centre(y, ax); return cx < cy || (cx == cy && x < y); });
+        return mid;
+      };
+      const size_t base = hs.gbounds.size();
+      std::vector<float4> tree;
+      // iterative build: a work list of (node index, item range); node 0 is the root
+      struct Work { int node; int* first; int* last; };
+      std::vector<Work> work;
+      tree.resize(8);
+      work.push_back({0, items.data(), items.data() + items.size()});
+      while (!work.empty()) {
+        const Work w = work.back(); work.pop_back();
+        int* cuts[5] = {w.first, nullptr, nullptr, nullptr, w.last};
+        cuts[2] = halve(w.first, w.last);
+        cuts[1] = (cuts[2] - cuts[0] >= 2) ? halve(cuts[0], cuts[2]) : cuts[0];
+        cuts[3] = (cuts[4] - cuts[2] >= 2) ? halve(cuts[2], cuts[4]) : cuts[2];
+        float cc[4][3], hh[4][3]; int ref[4]; int m = 0;
+        for (int k = 0; k < 4; k++) {
+          if (cuts[k + 1] == cuts[k]) continue;
+          const Box b = boxOf(cuts[k], cuts[k + 1]);
+          for (int a = 0; a < 3; a++) {
+            const float cf = (float)(0.5 * ((double)b.lo[a] + (double)b.hi[a]));
+            const double hd = std::max((double)b.hi[a] - (double)cf, (double)cf - (double)b.lo[a]);
+            float hf = (float)hd;
+            if ((double)hf < hd) hf = nextafterf(hf, INFINITY);
+            cc[m][a] = cf; hh[m][a] = nextafterf(hf, INFINITY);
+          }
+          if (cuts[k + 1] - cuts[k] == 1) ref[m] = -(*cuts[k] + 1);
+          else { ref[m] = (int)(tree.size() / 8); tree.resize(tree.size() + 8); work.push_back({ref[m], cuts[k], cuts[k + 1]}); }
+          m++;
+        }
+        for (int k = m; k < 4; k++) { ref[k] = (int)0x80000000; for (int a = 0; a < 3; a++) { cc[k][a] = 0.f; hh[k][a] = -1e30f; } }
+        float4* nd = tree.data() + 8 * (size_t)w.node;
+        for (int p2 = 0; p2 < 2; p2++) {
+          const int a = 2 * p2, b = 2 * p2 + 1;
+          nd[3 * p2 + 0] = make_float4(cc[a][0], cc[b][0], cc[a][1], cc[b][1]);
+          nd[3 * p2 + 1] = make_float4(cc[a][2], cc[b][2], hh[a][0], hh[b][0]);
+          nd[3 * p2 + 2] = make_float4(hh[a][1], hh[b][1], hh[a][2], hh[b][2]);
+        }
+        float4 refs; memcpy(&refs.x, &ref[0], 4); memcpy(&refs.y, &ref[1], 4); memcpy(&refs.z, &ref[2], 4); memcpy(&refs.w, &ref[3], 4);
+        nd[6] = refs; nd[7] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      hs.geom_tree = (int)base;
+      hs.gbounds.insert(hs.gbounds.end(), tree.begin(), tree.end());
+    }
+  }
   for (size_t k = 0; k < hs.nodes.size(); k++) {
     NodeD<R>& nd = hs.nodes[k];
     if (nd.leaf) { for (int gi = nd.first; gi < nd.first + nd.count; gi++) hs.geoms[gi].leaf = (int)k; }
@@ -382,7 +456,8 @@ int flatten(const drt_prim* prims, int n_prims, const drt_light* lights, int n_l
 template <typename R>
 struct DevScene {
   Geom<R>* geoms = nullptr; PrimD<R>* prims = nullptr; LightD<R>* lights = nullptr; NodeD<R>* nodes = nullptr;
-  float4* gbounds = nullptr;
+  float4* gbounds = nullptr; size_t gbounds_words = 0;
+  int geom_tree = -1;       // word offset of the 4-wide tree over the geoms inside gbounds, or -1 (HostScene::geom_tree)
   int n_geoms = 0, n_prims = 0, n_lights = 0, n_nodes = 0;
 };
 
@@ -424,10 +499,13 @@ int upload(const HostScene<R>& hs, DevScene<R>& ds, PinnedStage& stage, cudaStre
     if (ds.geoms) cudaFree(ds.geoms);
     CK(cudaMalloc(&ds.geoms, sizeof(Geom<R>) * std::max<size_t>(1, hs.geoms.size())));
   }
-  if ((int)hs.geoms.size() != ds.n_geoms || !ds.gbounds) {
+  if (hs.gbounds.size() != ds.gbounds_words || !ds.gbounds) {
     if (ds.gbounds) cudaFree(ds.gbounds);
+    ds.gbounds = nullptr;
     CK(cudaMalloc(&ds.gbounds, sizeof(float4) * std::max<size_t>(3, hs.gbounds.size())));
+    ds.gbounds_words = hs.gbounds.size();
   }
+  ds.geom_tree = hs.geom_tree;
   { int rc = stage.push(ds.gbounds, hs.gbounds.data(), sizeof(float4) * hs.gbounds.size(), q); if (rc) return rc; }
   if ((int)hs.prims.size() != ds.n_prims || !ds.prims) {
     if (ds.prims) cudaFree(ds.prims);
@@ -590,7 +668,7 @@ void fillParams(Params<R>& P, const drt_scene* s, const DevScene<R>& ds, const d
   f3(P.bluesky, st.bluesky); f3(P.redsky, st.redsky);
   P.saturation = st.saturation; P.clouddist = st.clouddist; P.cloudhoff = st.cloudhoff;
   P.x0 = tile.x0; P.y0 = tile.y0; P.w = tile.width; P.h = tile.height;
-  P.geoms = ds.geoms; P.n_geoms = ds.n_geoms; P.gbounds = ds.gbounds; P.nodes = ds.nodes; P.n_nodes = ds.n_nodes; P.prims = ds.prims; P.lights = ds.lights; P.n_lights = ds.n_lights;
+  P.geoms = ds.geoms; P.n_geoms = ds.n_geoms; P.gbounds = ds.gbounds; P.geom_tree = ds.geom_tree >= 0 ? ds.gbounds + ds.geom_tree : nullptr; P.nodes = ds.nodes; P.n_nodes = ds.n_nodes; P.prims = ds.prims; P.lights = ds.lights; P.n_lights = ds.n_lights;
   P.tex = s->d_tex; P.texdims = s->d_texdims;
   if (s->has_mesh) {
     P.mesh_nodes = s->mesh.nodes; P.n_mesh_tris = s->mesh.n_tris; P.mesh_prim = (int)s->prims.size();

@@ -198,6 +198,7 @@ struct Params {
   // scene
   const Geom<R>* geoms; int n_geoms;
   const float4* gbounds;    // slab-filter table: 3 float4 per PAIR of geoms (centre / half-extent, see slabMask)
+  const float4* geom_tree;  // 4-wide tree over the geoms (128-byte nodes as in drt_lbvh.cuh) for scenes beyond DRT_SMEM_GEOMS, or nullptr
   const NodeD<R>* nodes; int n_nodes;
   const PrimD<R>* prims;
   const LightD<R>* lights; int n_lights;

@@ -615,6 +615,70 @@ __device__ __forceinline__ unsigned int slabMask(const SlabTab tab, const int n_
   return mask & slabAll(g0, g1);
 }
 
+// One pair record of the slab filter (see slabMask) -> pass flags and entry distances of its two boxes.
+__device__ __forceinline__ void slabPair(const float4 A, const float4 B, const float4 C, const SlabRay& r, bool& ok0, bool& ok1,
+                                         float& tn0, float& tn1) {
+  const float2 mx = __ffma2_rn(make_float2(A.x, A.y), r.i[0], r.no[0]);
+  const float2 my = __ffma2_rn(make_float2(A.z, A.w), r.i[1], r.no[1]);
+  const float2 mz = __ffma2_rn(make_float2(B.x, B.y), r.i[2], r.no[2]);
+  const float2 hx = make_float2(B.z, B.w), hy = make_float2(C.x, C.y), hz = make_float2(C.z, C.w);
+  const float2 nx = __ffma2_rn(hx, r.nai[0], mx), fx = __ffma2_rn(hx, r.ai[0], mx);
+  const float2 ny = __ffma2_rn(hy, r.nai[1], my), fy = __ffma2_rn(hy, r.ai[1], my);
+  const float2 nz = __ffma2_rn(hz, r.nai[2], mz), fz = __ffma2_rn(hz, r.ai[2], mz);
+  tn0 = fmaxf(fmaxf(nx.x, ny.x), nz.x); tn1 = fmaxf(fmaxf(nx.y, ny.y), nz.y);
+  const float2 tf = __ffma2_rn(make_float2(fminf(fminf(fx.x, fy.x), fz.x), fminf(fminf(fx.y, fy.y), fz.y)), r.grow, r.slack);
+  ok0 = !(fmaxf(tn0, r.floor_t) > fminf(tf.x, r.lim));
+  ok1 = !(fmaxf(tn1, r.floor_t) > fminf(tf.y, r.lim));
+}
+
+// ---- 4-wide tree traversal (the mesh LBVH of drt_lbvh.cuh, and the tree over the analytic geoms of big scenes) ------------
+// A node visit tests its four child boxes with the packed slab test, descends into the nearest one that passes (CLOSEST)
+// and pushes the others with their entry distances; an entry whose distance lies beyond the best hit found meanwhile is
+// dropped when popped.  Without CLOSEST (any hit) the order does not matter: the last passing child is next.
+#define DRT_MESH_DONE ((int)0x80000000)
+template <bool CLOSEST>
+__device__ __forceinline__ int bvh4Pop(const int2* stack, int& sp, const float lim) {
+  while (sp > 0) {
+    const int2 e = stack[--sp];
+    if (CLOSEST && __int_as_float(e.y) > lim) continue;
+    return e.x;
+  }
+  return DRT_MESH_DONE;
+}
+template <bool CLOSEST>
+__device__ __forceinline__ int bvh4Visit(const float4* __restrict__ nodes, const int cur, const SlabRay& sr, int2* stack, int& sp, int* overflow) {
+  const float4* nd = nodes + 8 * (size_t)cur;
+  const float4 A0 = __ldg(nd), B0 = __ldg(nd + 1), C0 = __ldg(nd + 2), A1 = __ldg(nd + 3), B1 = __ldg(nd + 4), C1 = __ldg(nd + 5);
+  const float4 K = __ldg(nd + 6);
+  bool ok0, ok1, ok2, ok3; float t0, t1, t2, t3;
+  slabPair(A0, B0, C0, sr, ok0, ok1, t0, t1);
+  slabPair(A1, B1, C1, sr, ok2, ok3, t2, t3);
+  const int r0 = __float_as_int(K.x), r1 = __float_as_int(K.y), r2 = __float_as_int(K.z), r3 = __float_as_int(K.w);
+  ok2 = ok2 && r2 != DRT_MESH_DONE; ok3 = ok3 && r3 != DRT_MESH_DONE;     // empty slots (NaN slab terms of an axis-parallel ray pass the test)
+  if (sp > DRT_NODE_STACK - 4) { *overflow = 1; sp = 0; return DRT_MESH_DONE; }   // degenerate input only: the frame is rejected, not wrong
+  if (CLOSEST) {
+    // descend into the nearest passing child: order key = entry distance (clamped at 0, low two mantissa bits = slot)
+    const int k0 = ok0 ? ((__float_as_int(fmaxf(t0, 0.f)) & ~3) | 0) : 0x7fffffff;
+    const int k1 = ok1 ? ((__float_as_int(fmaxf(t1, 0.f)) & ~3) | 1) : 0x7fffffff;
+    const int k2 = ok2 ? ((__float_as_int(fmaxf(t2, 0.f)) & ~3) | 2) : 0x7fffffff;
+    const int k3 = ok3 ? ((__float_as_int(fmaxf(t3, 0.f)) & ~3) | 3) : 0x7fffffff;
+    const int kb = min(min(k0, k1), min(k2, k3));
+    if (kb == 0x7fffffff) return bvh4Pop<CLOSEST>(stack, sp, sr.lim);
+    if (ok0 && k0 != kb) stack[sp++] = make_int2(r0, __float_as_int(t0));
+    if (ok1 && k1 != kb) stack[sp++] = make_int2(r1, __float_as_int(t1));
+    if (ok2 && k2 != kb) stack[sp++] = make_int2(r2, __float_as_int(t2));
+    if (ok3 && k3 != kb) stack[sp++] = make_int2(r3, __float_as_int(t3));
+    const int bk = kb & 3;
+    return bk == 0 ? r0 : bk == 1 ? r1 : bk == 2 ? r2 : r3;
+  }
+  int nxt = DRT_MESH_DONE;
+  if (ok0) nxt = r0;
+  if (ok1) { if (nxt != DRT_MESH_DONE) stack[sp++] = make_int2(nxt, 0); nxt = r1; }
+  if (ok2) { if (nxt != DRT_MESH_DONE) stack[sp++] = make_int2(nxt, 0); nxt = r2; }
+  if (ok3) { if (nxt != DRT_MESH_DONE) stack[sp++] = make_int2(nxt, 0); nxt = r3; }
+  return (nxt != DRT_MESH_DONE) ? nxt : bvh4Pop<CLOSEST>(stack, sp, sr.lim);
+}
+
 // Closest hit over all flattened primitives (the candidate loop of rayColor,
 // render_final_project.cpp:522-538, with each class's intersect()).
 //
@@ -639,6 +703,28 @@ __device__ inline void closestHit(const Params<R>& P, const SlabTab gb, const Mo
     const float serr = 4e-7f * (fabsf(ox) + fabsf(oy) + fabsf(oz));
     const bool cull = !((F & FT_VEL) && mv.velocity_mode) || P.swept_cull;
     const bool smem = !(F & FT_BIG) || P.n_geoms <= DRT_SMEM_GEOMS;     // CTA-uniform: the table is staged in shared memory
+    if ((F & FT_BIG) && cull && P.geom_tree) {
+      // more geoms than the filter table in shared memory holds: candidates come from the 4-wide tree over the geoms.  The
+      // tree hands them over in its own order, so a tie of t goes to the lower geom index explicitly (:531 keeps the first)
+      SlabRay st = slabRay(ix, iy, iz, ox, oy, oz, FLT_MAX);
+      int2 stack[DRT_NODE_STACK];
+      int sp = 0, cur = 0;
+      for (;;) {
+        while (cur >= 0) { if (COUNT) cnt.node_tests += 4; cur = bvh4Visit<true>(P.geom_tree, cur, st, stack, sp, P.overflow); }
+        if (cur == DRT_MESH_DONE) break;
+        const int gi = -cur - 1;
+        const Geom<R>& g = P.geoms[gi];
+        const int type = g.type;
+        if (COUNT) cnt.geom_tests[type]++;
+        float t_hit; int inside, sel;
+        if (geomIntersect<R, F>(P, g, gi, type, mv, ray, start, t_hit, inside, sel) && (t_hit < h.t || (t_hit == h.t && gi < h.geom))) {
+          h.t = t_hit; h.geom = gi; h.inside = inside; h.checker_sel = sel;
+          st.lim = (t_hit * 1.0001f + 1e-4f) + serr;
+        }
+        cur = bvh4Pop<true>(stack, sp, st.lim);
+      }
+      return;
+    }
     const SlabRay sr = slabRay(ix, iy, iz, ox, oy, oz, FLT_MAX);
     const int n = P.n_geoms;
     for (int g0 = 0; g0 < n; g0 += 32) {
@@ -788,6 +874,40 @@ __device__ inline bool anyHit(const Params<R>& P, const SlabTab gb, const Moved<
     const int n = P.n_geoms;
     const bool smem = !(F & FT_BIG) || n <= DRT_SMEM_GEOMS;
     const SlabRay sr = slabRay(ix, iy, iz, ox, oy, oz, t_max * 1.0001f + 1e-4f);
+    // one candidate: 1 = the ray is occluded, -1 = the reference throws (slab-box prisms), 0 = go on
+    auto candidate = [&](const int gi) -> int {
+      const Geom<R>& g = P.geoms[gi];
+      const int type = g.type;
+      if (type == G_HOLE || g.owner == skip_owner) return 0;     // an area light never shadows itself (832-837)
+      if (COUNT) cnt.geom_tests[type]++;
+      float t_occ;
+      if (!geomShadow<R, F>(P, g, gi, type, mv, ray, start, t_max, t_occ, aborted)) return ((F & FT_BOX) && aborted) ? -1 : 0;
+      if ((F & FT_VEL) && mv.velocity_mode) return 1;            // time-displaced geometry: no reference tree to consult
+      // The occluder touches the ray at distance t_occ from the test origin.  If that point
+      // lies ahead of the gather origin it is inside the geom's leaf box and every ancestor
+      // box (they are padded supersets), so BoundingVolume::intersect returns tmax > 0 for all
+      // of them and the reference does gather this geom.  Only nearer occluders need the
+      // exact replay of the reference's box tests.
+      if (t_occ > gather_lead * 1.001f + 2e-3f) return 1;
+      bool gathered = true;
+      const Vec<R> inv_ray = mk<R>(R(1) / gather_ray.x, R(1) / gather_ray.y, R(1) / gather_ray.z);   // sray.cwiseInverse() :813 (rare path: three divisions)
+      for (int ni = g.leaf; ni >= 0 && gathered; ni = P.nodes[ni].parent) {
+        if (COUNT) cnt.node_tests++;
+        gathered = boxHit<R, F>(P.nodes[ni], gather_ray, inv_ray, gather_start, mv);
+      }
+      return gathered ? 1 : 0;
+    };
+    if ((F & FT_BIG) && cull && P.geom_tree) {                    // big scenes: candidates from the tree over the geoms (see closestHit)
+      int2 stack[DRT_NODE_STACK];
+      int sp = 0, cur = 0;
+      for (;;) {
+        while (cur >= 0) { if (COUNT) cnt.node_tests += 4; cur = bvh4Visit<false>(P.geom_tree, cur, sr, stack, sp, P.overflow); }
+        if (cur == DRT_MESH_DONE) break;
+        if (candidate(-cur - 1) == 1) return true;
+        cur = bvh4Pop<false>(stack, sp, sr.lim);
+      }
+      return false;
+    }
     for (int g0 = 0; g0 < n; g0 += 32) {
       const int g1 = min(n, g0 + 32);
       // lock-step, branch-free slab filter -> per-lane candidate mask
@@ -795,26 +915,9 @@ __device__ inline bool anyHit(const Params<R>& P, const SlabTab gb, const Moved<
       while (mask) {                                // each lane walks its own candidates
         const int gi = g0 + __ffs(mask) - 1;
         mask &= mask - 1;
-        const Geom<R>& g = P.geoms[gi];
-        const int type = g.type;
-        if (type == G_HOLE || g.owner == skip_owner) continue;   // an area light never shadows itself (832-837)
-        if (COUNT) cnt.geom_tests[type]++;
-        float t_occ;
-        if (!geomShadow<R, F>(P, g, gi, type, mv, ray, start, t_max, t_occ, aborted)) { if ((F & FT_BOX) && aborted) return false; continue; }
-        if ((F & FT_VEL) && mv.velocity_mode) return true;          // time-displaced geometry: no reference tree to consult
-        // The occluder touches the ray at distance t_occ from the test origin.  If that point
-        // lies ahead of the gather origin it is inside the geom's leaf box and every ancestor
-        // box (they are padded supersets), so BoundingVolume::intersect returns tmax > 0 for all
-        // of them and the reference does gather this geom.  Only nearer occluders need the
-        // exact replay of the reference's box tests.
-        if (t_occ > gather_lead * 1.001f + 2e-3f) return true;
-        bool gathered = true;
-        const Vec<R> inv_ray = mk<R>(R(1) / gather_ray.x, R(1) / gather_ray.y, R(1) / gather_ray.z);   // sray.cwiseInverse() :813 (rare path: three divisions)
-        for (int ni = g.leaf; ni >= 0 && gathered; ni = P.nodes[ni].parent) {
-          if (COUNT) cnt.node_tests++;
-          gathered = boxHit<R, F>(P.nodes[ni], gather_ray, inv_ray, gather_start, mv);
-        }
-        if (gathered) return true;
+        const int c = candidate(gi);
+        if (c == 1) return true;
+        if ((F & FT_BOX) && c == -1) return false;
       }
     }
     return false;
@@ -861,33 +964,14 @@ __device__ __forceinline__ float meshTriT(const MeshTri<R>& tr, const Vec<R>& ra
   return (float)((double)dot(r2, DA0) * (double)invdet);
 }
 
-// One pair record of the slab filter (see slabMask) -> pass flags and entry distances of its two boxes.
-__device__ __forceinline__ void slabPair(const float4 A, const float4 B, const float4 C, const SlabRay& r, bool& ok0, bool& ok1,
-                                         float& tn0, float& tn1) {
-  const float2 mx = __ffma2_rn(make_float2(A.x, A.y), r.i[0], r.no[0]);
-  const float2 my = __ffma2_rn(make_float2(A.z, A.w), r.i[1], r.no[1]);
-  const float2 mz = __ffma2_rn(make_float2(B.x, B.y), r.i[2], r.no[2]);
-  const float2 hx = make_float2(B.z, B.w), hy = make_float2(C.x, C.y), hz = make_float2(C.z, C.w);
-  const float2 nx = __ffma2_rn(hx, r.nai[0], mx), fx = __ffma2_rn(hx, r.ai[0], mx);
-  const float2 ny = __ffma2_rn(hy, r.nai[1], my), fy = __ffma2_rn(hy, r.ai[1], my);
-  const float2 nz = __ffma2_rn(hz, r.nai[2], mz), fz = __ffma2_rn(hz, r.ai[2], mz);
-  tn0 = fmaxf(fmaxf(nx.x, ny.x), nz.x); tn1 = fmaxf(fmaxf(nx.y, ny.y), nz.y);
-  const float2 tf = __ffma2_rn(make_float2(fminf(fminf(fx.x, fy.x), fz.x), fminf(fminf(fx.y, fy.y), fz.y)), r.grow, r.slack);
-  ok0 = !(fmaxf(tn0, r.floor_t) > fminf(tf.x, r.lim));
-  ok1 = !(fmaxf(tn1, r.floor_t) > fminf(tf.y, r.lim));
-}
-
 // Traversal of the 4-wide LBVH (drt_lbvh.cuh), "while-while": a lane first descends through internal nodes until the
 // next thing it has to do is an exact triangle test (or nothing), and only then -- together with the other lanes of the
 // warp that reached a leaf -- runs the reference's Moeller-Trumbore test in the vector precision.  With the test inline in
-// the node loop it ran with ~4 of 32 lanes (profiles/r1_ncu_full_band_c5_mesh.txt).  A node visit tests its four child
-// boxes with the packed slab test of the analytic filter, descends into the nearest one that passes and pushes the others
-// with their entry distances; an entry whose distance lies beyond the best hit found meanwhile is dropped when popped.
+// the node loop it ran with ~4 of 32 lanes (profiles/r1_ncu_full_band_c5_mesh.txt).  Node visits: bvh4Visit.
 // CLOSEST: keeps the nearest hit with t > 1e-4 (strict `<` against the best so far, so analytic primitives -- tested
 // first -- win ties).  !CLOSEST: any hit with 1e-3 < t < t_max (Triangle::intersectShadow geometry.cpp:555-586) that the
 // reference would also have gathered (its gather origin runs ahead by |sray|*1e-3, :814; a mesh triangle stands in its
 // own leaf box: bounds +- 1e-2, geometry.cpp:2653-2654).
-#define DRT_MESH_DONE ((int)0x80000000)
 template <typename R, int F, bool COUNT, bool CLOSEST>
 __device__ bool meshTraverse(const Params<R>& P, const Vec<R>& ray, const Vec<R>& start, float t_limit, HitRec* h,
                              const Vec<R>& gather_ray, const Vec<R>& gather_start, Counts& cnt) {
@@ -899,52 +983,10 @@ __device__ bool meshTraverse(const Params<R>& P, const Vec<R>& ray, const Vec<R>
   int sp = 0;
   int cur = 0;
   bool found = false;
-  // next entry of the stack that can still hold a closer hit, or DONE
-  auto pop = [&]() -> int {
-    while (sp > 0) {
-      const int2 e = stack[--sp];
-      if (CLOSEST && __int_as_float(e.y) > sr.lim) continue;
-      return e.x;
-    }
-    return DRT_MESH_DONE;
-  };
   for (;;) {
     while (cur >= 0) {                                                          // ---- internal nodes
-      const float4* nd = P.mesh_nodes + 8 * (size_t)cur;
-      const float4 A0 = __ldg(nd), B0 = __ldg(nd + 1), C0 = __ldg(nd + 2), A1 = __ldg(nd + 3), B1 = __ldg(nd + 4), C1 = __ldg(nd + 5);
-      const float4 K = __ldg(nd + 6);
       if (COUNT) cnt.node_tests += 4;
-      bool ok0, ok1, ok2, ok3; float t0, t1, t2, t3;
-      slabPair(A0, B0, C0, sr, ok0, ok1, t0, t1);
-      slabPair(A1, B1, C1, sr, ok2, ok3, t2, t3);
-      const int r0 = __float_as_int(K.x), r1 = __float_as_int(K.y), r2 = __float_as_int(K.z), r3 = __float_as_int(K.w);
-      ok2 = ok2 && r2 != DRT_MESH_DONE; ok3 = ok3 && r3 != DRT_MESH_DONE;     // empty slots (NaN slab terms of an axis-parallel ray pass the test)
-      if (sp > DRT_NODE_STACK - 4) { *P.overflow = 1; cur = DRT_MESH_DONE; break; }   // degenerate input only: the frame is rejected, not wrong
-      if (CLOSEST) {
-        // descend into the nearest passing child: order key = entry distance (clamped at 0, low two mantissa bits = slot)
-        const int k0 = ok0 ? ((__float_as_int(fmaxf(t0, 0.f)) & ~3) | 0) : 0x7fffffff;
-        const int k1 = ok1 ? ((__float_as_int(fmaxf(t1, 0.f)) & ~3) | 1) : 0x7fffffff;
-        const int k2 = ok2 ? ((__float_as_int(fmaxf(t2, 0.f)) & ~3) | 2) : 0x7fffffff;
-        const int k3 = ok3 ? ((__float_as_int(fmaxf(t3, 0.f)) & ~3) | 3) : 0x7fffffff;
-        const int kb = min(min(k0, k1), min(k2, k3));
-        if (kb == 0x7fffffff) cur = pop();
-        else {
-          if (ok0 && k0 != kb) stack[sp++] = make_int2(r0, __float_as_int(t0));
-          if (ok1 && k1 != kb) stack[sp++] = make_int2(r1, __float_as_int(t1));
-          if (ok2 && k2 != kb) stack[sp++] = make_int2(r2, __float_as_int(t2));
-          if (ok3 && k3 != kb) stack[sp++] = make_int2(r3, __float_as_int(t3));
-          const int bk = kb & 3;
-          cur = bk == 0 ? r0 : bk == 1 ? r1 : bk == 2 ? r2 : r3;
-        }
-      } else {
-        // any hit: the order does not matter -- the last passing child is next, the others wait
-        int nxt = DRT_MESH_DONE;
-        if (ok0) nxt = r0;
-        if (ok1) { if (nxt != DRT_MESH_DONE) stack[sp++] = make_int2(nxt, 0); nxt = r1; }
-        if (ok2) { if (nxt != DRT_MESH_DONE) stack[sp++] = make_int2(nxt, 0); nxt = r2; }
-        if (ok3) { if (nxt != DRT_MESH_DONE) stack[sp++] = make_int2(nxt, 0); nxt = r3; }
-        cur = (nxt != DRT_MESH_DONE) ? nxt : pop();
-      }
+      cur = bvh4Visit<CLOSEST>(P.mesh_nodes, cur, sr, stack, sp, P.overflow);
     }
     if (cur == DRT_MESH_DONE) break;
     {                                                                           // ---- leaf: exact test
@@ -971,7 +1013,7 @@ __device__ bool meshTraverse(const Params<R>& P, const Vec<R>& ray, const Vec<R>
         if (boxHit<R, F>(nd, gather_ray, inv, gather_start, still)) return true;
       }
     }
-    cur = pop();
+    cur = bvh4Pop<CLOSEST>(stack, sp, sr.lim);
   }
   return found;
 }

@@ -208,6 +208,35 @@ def config4_frame(frame, xres=1920, yres=1080, spp=16, bones=None, two_pose=Fals
 
 
 # ---------------------------------------------------------------------------
+
+def many_shapes(nx=24, nz=14, xres=160, yres=90, spp=4):
+    """More analytic shapes than the shared-memory slab table holds (DRT_SMEM_GEOMS = 256): a field of nx * nz small
+    spheres and short cylinders (every seventh sphere a steel mirror) over a steel floor, a rectangle light and a point
+    light.  Exercises the geom-tree path of closestHit / anyHit (FT_BIG) against the oracle's reference-order walk."""
+    base, settings, _ = load_fixture(data_path("checkertexture_scene.npz"))
+    prims = [rectangle((-8, 0, 4), (8, 0, 4), (8, 0, -12), (-8, 0, -12), (0.7, 0.7, 0.75), material=abi.MAT_STEEL, name=abi.NAME_OTHER)]
+    k = 0
+    for i in range(nx):
+        for j in range(nz):
+            x, z = -6.9 + 0.6 * i, 2.0 - 0.9 * j
+            y = 0.25 + 0.12 * ((i * 7 + j * 3) % 5)
+            col = (0.3 + 0.1 * (i % 7), 0.9 - 0.1 * (j % 6), 0.4 + 0.05 * ((i + j) % 9))
+            if k % 3 == 2:
+                prims.append(cylinder((x - 0.15, y, z), (x + 0.15, y + 0.2, z - 0.1), 0.08, col))
+            else:
+                prims.append(sphere((x, y, z), 0.2, col, material=abi.MAT_STEEL if k % 7 == 0 else abi.MAT_NONE,
+                                    model=abi.MODEL_OREN_NAYAR if k % 5 == 1 else abi.MODEL_LAMBERT))
+            k += 1
+    lp, ll = rectangle_light((-1, 5, -3), (1, 5, -3), (1, 5, -5), (-1, 5, -5), (1.0, 1.0, 0.9), len(prims))
+    prims.append(lp)
+    lights = [ll, point_light((3.0, 4.0, 3.0), (0.6, 0.6, 0.7))]
+    s = abi.copy_struct(settings)
+    s.eye[:] = [0.0, 3.5, 6.0]; s.lookingAt[:] = [0.0, 0.3, -3.0]; s.up[:] = [0, 1, 0]
+    s.xRes, s.yRes, s.antialias_samples, s.aperture, s.focal_length = xres, yres, spp, 0.1, 9.0
+    s.max_depth, s.brdf_samples, s.blur_samples = 4, 2, 0
+    return Scene(prims, lights, base.textures), s
+
+
 def terrain_mesh(n=708, size=12.0, height=1.2, origin=(-6.0, -0.5, -6.0)):
     """Procedural grid mesh for BASELINE config 5: n x n vertices -> 2 (n-1)^2 triangles
     (n = 708 gives 999 698), heights from a fixed analytic function (no RNG), UV = grid / (n-1)

@@ -290,6 +290,22 @@ def test_production_spp_mae_against_high_spp_reference(oracle_lib):
         assert ours_single <= 1.2 * ref_self + 0.05, (case, ours_single, ref_self)
 
 
+def test_cuda_many_shapes_match_oracle(oracle_lib):
+    """337 analytic shapes (more geoms than the shared-memory slab table holds): the CUDA path gathers candidates through
+    its own tree over the geoms, the oracle through the reference-order BVH -- same image, ties of t included (the steel
+    floor and the spheres' mirror reflections see every shape)."""
+    from distraytracer_b200 import scenes
+    from oracle.harness import Oracle, ORACLE_KEYED, compare
+    scene, s = scenes.many_shapes()
+    assert len(scene.prims) > 300
+    want, _, _, _ = Oracle(scene).render(s, mode=ORACLE_KEYED)
+    dev = _gpu(scene)
+    got, _ = dev.render_float(s)
+    st = compare(want, got)
+    assert st["frac_within_1"] >= TOL_FRAC, st
+    assert float(np.abs(want).max()) > 0.2                    # not a black frame
+
+
 @pytest.mark.parametrize("variant", ["one_pixel", "edge_tile", "depth1", "noreflect", "nogloss", "no_lights", "aa2", "blur_ref_mode",
                                      "brdf5_depth4", "depth32", "dof_aa10", "dof_aa24", "dof_scan_fallback"])
 def test_cuda_edge_cases_match_oracle(oracle_lib, variant):

@@ -4,8 +4,9 @@ import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from distraytracer_b200 import runtime, abi, scenes
-cfg = os.environ.get("BAND_CONFIG", "c2")        # c2: the bench workload; c5: the 999 698-triangle terrain at 4K (LBVH traversal)
-scene, st = scenes.config5() if cfg == "c5" else scenes.config2(1920, 1080, 64)
+cfg = os.environ.get("BAND_CONFIG", "c2")        # c2: the bench workload; c5: the 999 698-triangle terrain at 4K (LBVH traversal); c3, c4
+scene, st = (scenes.config5() if cfg == "c5" else scenes.config3() if cfg == "c3" else scenes.config4_frame(30) if cfg == "c4"
+             else scenes.config2(1920, 1080, 64))
 st.precision = int(os.environ.get("DRT_PRECISION", "0"))
 dev = runtime.DeviceScene(scene, 0)
 y0 = int(os.environ.get("BAND_Y0", "1000" if cfg == "c5" else "470")); h = int(os.environ.get("BAND_H", "16" if cfg == "c5" else "48"))
@@ -13,7 +14,7 @@ tile = abi.Tile(0, y0, st.xRes, h, 0)
 cnt = abi.Counters()
 for i in range(3):
     dev.render_device(st, tile, cnt)
-    print(f"band y0={y0} h={h}: kernel {cnt.kernel_ms:.3f} ms, {st.xRes*h*64/cnt.kernel_ms/1e3:.1f} Msamples/s", flush=True)
+    print(f"band y0={y0} h={h}: kernel {cnt.kernel_ms:.3f} ms, {cnt.kernel_launches} launches", flush=True)
 if os.environ.get("BAND_COUNT"):
     c2 = abi.Counters(); c2.collect = 1
     dev.render_device(st, tile, c2)
