@@ -73,8 +73,28 @@ Geom<R> rectGeom(int type, int owner, int flags, float eps, const RectD& r, floa
   g.len1 = (R)r.len1; g.len2 = (R)r.len2; g.f0 = (float)r.len1; g.f1 = (float)r.len2; g.f2 = S;
   g.vel = cv<R>(vel);
   const D3 u = r.e1 * r.len1, v = r.e2 * r.len2;
-  const D3 pts[4] = {r.A, r.A + u, r.A + v, r.A + u + v};
-  setBounds(g, pts, 4, 0.0);
+  D3 pts[8] = {r.A, r.A + u, r.A + v, r.A + u + v};
+  int n_pts = 4;
+  // Rectangle::intersect accepts a point P of the plane when 0 <= e1.(P - A) <= |B - A| and 0 <= e2.(P - A) <= |D - A|
+  // (geometry.cpp:681-686).  For orthogonal edges that is the rectangle.  Several of the reference's own builders list
+  // the corners of a wall as (a, b, c, d) with d DIAGONALLY opposite a, so that D - A is a diagonal: the accepted region is
+  // then a long parallelogram reaching far beyond the vertices.  The filter box has to hold that region (corners: the
+  // solutions of the two projections at their bounds), and the reference finds such a hit only when its BVH gather reaches
+  // the leaf -- GF_SPILL makes closestHit / anyHit replay that gather for every hit on this geom.
+  const double c = dot(r.e1, r.e2);
+  bool unbounded = false;
+  if (std::fabs(c) > 1e-12 || std::fabs(dot(r.e2, r.nrm)) > 1e-9 || std::fabs(dot(r.e1, r.nrm)) > 1e-9) {
+    g.flags |= GF_SPILL;
+    const double den = 1.0 - c * c;
+    if (den < 1e-9 || std::fabs(dot(r.e2, r.nrm)) > 1e-9 || std::fabs(dot(r.e1, r.nrm)) > 1e-9) unbounded = true;   // (nearly) parallel edges / a corner off the plane
+    else
+      for (int k = 0; k < 4; k++) {
+        const double d1 = (k & 1) ? r.len1 : 0.0, d2 = (k & 2) ? r.len2 : 0.0;
+        pts[n_pts++] = r.A + r.e1 * ((d1 - c * d2) / den) + r.e2 * ((d2 - c * d1) / den);
+      }
+  }
+  setBounds(g, pts, n_pts, 0.0);
+  if (unbounded) { g.blo = make_float4(-1e30f, -1e30f, -1e30f, 0.f); g.bhi = make_float4(1e30f, 1e30f, 1e30f, 0.f); }
   return g;
 }
 
@@ -547,7 +567,7 @@ int waveFeatPick(int need) {
 struct drt_scene {
   int device = 0;
   std::vector<drt_prim> prims; std::vector<drt_light> lights; int n_textures = 0;
-  bool any_glass = false, any_tex = false, any_motion = false, any_box = false;
+  bool any_glass = false, any_tex = false, any_motion = false, any_box = false, any_spill = false;
   DevScene<double> dd; DevScene<float> df;
   std::vector<cudaArray_t> tex_arrays; std::vector<cudaTextureObject_t> tex_objs;
   cudaTextureObject_t* d_tex = nullptr; int2* d_texdims = nullptr;
@@ -601,7 +621,8 @@ int flattenAndUpload(drt_scene* s) {
   rc = s->stage.reserve(uploadBytes(hd) + uploadBytes(hf)); if (rc) return rc;
   rc = upload(hd, s->dd, s->stage, s->stream); if (rc) return rc;
   rc = upload(hf, s->df, s->stage, s->stream); if (rc) return rc;
-  s->any_glass = s->any_tex = s->any_motion = s->any_box = false;
+  s->any_glass = s->any_tex = s->any_motion = s->any_box = s->any_spill = false;
+  for (const auto& g : hd.geoms) if (g.flags & GF_SPILL) s->any_spill = true;
   auto scan = [&](const drt_prim& p) {
     if (p.type == DRT_PRIM_RECTPRISM || p.type == DRT_PRIM_RECTPRISM_CYL || p.type == DRT_PRIM_RECTPRISM_HOLES) s->any_box = true;
     if (p.material == DRT_MAT_GLASS) s->any_glass = true;
@@ -706,12 +727,13 @@ int ensureScratch(drt_scene* s, size_t n_samples, size_t n_corners, size_t n_out
   return DRT_OK;
 }
 
-// Samples held in HBM at once: 2^28 float4 = 4 GiB, so that a 1080p 64 spp frame (132.7 M samples) is ONE launch of the
-// persistent kernel -- every extra launch pays one more drain (the last batches finish with few warps busy) and ramp.
-// DRT_CHUNK_LOG2 overrides the bound (tuning / tests of the multi-chunk path).
+// Samples held in HBM at once: up to 2^29 float4 = 8 GiB of the B200's 180 (the buffer is sized by what a frame needs), so
+// that a 1080p 256 spp or 4K 64 spp frame (530.8 M samples) is ONE launch of the persistent kernel -- every extra launch
+// pays one more drain (the last batches finish with few warps busy) and ramp, and on several GPUs one more round of
+// barriers.  DRT_CHUNK_LOG2 overrides the bound (smaller GPUs / tests of the multi-chunk path).
 long long maxChunkSamples() {
   const char* e = getenv("DRT_CHUNK_LOG2");
-  int b = e ? atoi(e) : 28;
+  int b = e ? atoi(e) : 29;
   b = std::max(12, std::min(30, b));
   return 1ll << b;
 }
@@ -792,7 +814,8 @@ int planLaunch(drt_scene* s, const DevScene<R>& ds, const drt_settings& st, cons
   if (s->any_tex) feat |= FT_TEX;
   if (ds.n_geoms > DRT_SMEM_GEOMS) feat |= FT_BIG;
   if (s->any_box) feat |= FT_BOX;
-  if (const char* e = getenv("DRT_WAVE_FEAT")) feat |= atoi(e);      // tuning: force a larger instantiation (63 = generic)
+  if (s->any_spill) feat |= FT_SPILL;
+  if (const char* e = getenv("DRT_WAVE_FEAT")) feat |= atoi(e);      // tuning: force a larger instantiation (255 = generic)
   lp.feat = feat;
   return DRT_OK;
 }

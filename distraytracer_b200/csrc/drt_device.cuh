@@ -76,7 +76,9 @@ enum GeomFlags {
   GF_NAME_RECTANGLE = 1,  // moves in y during reference-mode motion blur (render_final_project.cpp:1116)
   GF_HAS_HOLE = 2,        // next record is this checkerboard's hole rectangle
   GF_MESH = 4,            // Triangle::mesh (inside test against mesh_normal)
-  GF_VERTEX_MOTION = 8    // cylinder whose end points move independently (DRT_FLAG_VERTEX_MOTION): p1 moves by vel2
+  GF_VERTEX_MOTION = 8,   // cylinder whose end points move independently (DRT_FLAG_VERTEX_MOTION): p1 moves by vel2
+  GF_SPILL = 16           // rectangle whose edges B-A, D-A are not orthogonal: Rectangle::intersect accepts points outside the
+                          // vertices' bounding box, and whether the reference finds such a hit depends on its BVH gather
 };
 
 template <typename R>

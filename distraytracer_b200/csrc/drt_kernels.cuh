@@ -679,6 +679,18 @@ __device__ __forceinline__ int bvh4Visit(const float4* __restrict__ nodes, const
   return (nxt != DRT_MESH_DONE) ? nxt : bvh4Pop<CLOSEST>(stack, sp, sr.lim);
 }
 
+// Would the reference's BVH walk along (ray, start) have gathered this geom?  BoundingVolume::intersect on its leaf and
+// every ancestor (the walk descends only through nodes whose box test passes, render_final_project.cpp:492-512).
+template <typename R, int F, bool COUNT>
+__device__ __noinline__ bool gatherReplay(const Params<R>& P, const int leaf, const Vec<R> ray, const Vec<R> start, const Moved<R> mv, Counts& cnt) {   // by value: no addressable copies at the call sites
+  const Vec<R> inv_ray = mk<R>(R(1) / ray.x, R(1) / ray.y, R(1) / ray.z);   // ray.cwiseInverse() :499, :813
+  for (int ni = leaf; ni >= 0; ni = P.nodes[ni].parent) {
+    if (COUNT) cnt.node_tests++;
+    if (!boxHit<R, F>(P.nodes[ni], ray, inv_ray, start, mv)) return false;
+  }
+  return true;
+}
+
 // Closest hit over all flattened primitives (the candidate loop of rayColor,
 // render_final_project.cpp:522-538, with each class's intersect()).
 //
@@ -717,7 +729,8 @@ __device__ inline void closestHit(const Params<R>& P, const SlabTab gb, const Mo
         const int type = g.type;
         if (COUNT) cnt.geom_tests[type]++;
         float t_hit; int inside, sel;
-        if (geomIntersect<R, F>(P, g, gi, type, mv, ray, start, t_hit, inside, sel) && (t_hit < h.t || (t_hit == h.t && gi < h.geom))) {
+        if (geomIntersect<R, F>(P, g, gi, type, mv, ray, start, t_hit, inside, sel) && (t_hit < h.t || (t_hit == h.t && gi < h.geom)) &&
+            (!(F & FT_SPILL) || !(g.flags & GF_SPILL) || ((F & FT_VEL) && mv.velocity_mode) || gatherReplay<R, F, COUNT>(P, g.leaf, ray, start, mv, cnt))) {
           h.t = t_hit; h.geom = gi; h.inside = inside; h.checker_sel = sel;
           st.lim = (t_hit * 1.0001f + 1e-4f) + serr;
         }
@@ -740,7 +753,9 @@ __device__ inline void closestHit(const Params<R>& P, const SlabTab gb, const Mo
         if (cull && h.t < FLT_MAX && !slabMayHit(g.blo, g.bhi, ox, oy, oz, ix, iy, iz, h.t * 1.0001f + 1e-4f, serr)) continue;
         if (COUNT) cnt.geom_tests[type]++;
         float t_hit; int inside, sel;
-        if (geomIntersect<R, F>(P, g, gi, type, mv, ray, start, t_hit, inside, sel) && t_hit < h.t) {
+        // (a hit on a GF_SPILL rectangle counts only if the reference's gather reaches its leaf, see rectGeom in drt_api.cu)
+        if (geomIntersect<R, F>(P, g, gi, type, mv, ray, start, t_hit, inside, sel) && t_hit < h.t &&
+            (!(F & FT_SPILL) || !(g.flags & GF_SPILL) || ((F & FT_VEL) && mv.velocity_mode) || gatherReplay<R, F, COUNT>(P, g.leaf, ray, start, mv, cnt))) {
           h.t = t_hit; h.geom = gi; h.inside = inside; h.checker_sel = sel;
         }
       }
@@ -888,14 +903,9 @@ __device__ inline bool anyHit(const Params<R>& P, const SlabTab gb, const Moved<
       // box (they are padded supersets), so BoundingVolume::intersect returns tmax > 0 for all
       // of them and the reference does gather this geom.  Only nearer occluders need the
       // exact replay of the reference's box tests.
-      if (t_occ > gather_lead * 1.001f + 2e-3f) return 1;
-      bool gathered = true;
-      const Vec<R> inv_ray = mk<R>(R(1) / gather_ray.x, R(1) / gather_ray.y, R(1) / gather_ray.z);   // sray.cwiseInverse() :813 (rare path: three divisions)
-      for (int ni = g.leaf; ni >= 0 && gathered; ni = P.nodes[ni].parent) {
-        if (COUNT) cnt.node_tests++;
-        gathered = boxHit<R, F>(P.nodes[ni], gather_ray, inv_ray, gather_start, mv);
-      }
-      return gathered ? 1 : 0;
+      // (not so for a GF_SPILL rectangle, whose touch point can lie outside its box: always replayed)
+      if (t_occ > gather_lead * 1.001f + 2e-3f && !((F & FT_SPILL) && (g.flags & GF_SPILL))) return 1;
+      return gatherReplay<R, F, COUNT>(P, g.leaf, gather_ray, gather_start, mv, cnt) ? 1 : 0;   // rare path: three divisions
     };
     if ((F & FT_BIG) && cull && P.geom_tree) {                    // big scenes: candidates from the tree over the geoms (see closestHit)
       int2 stack[DRT_NODE_STACK];
@@ -1640,7 +1650,11 @@ __device__ __noinline__ void primaryRay(const Params<R>& P, long long gidx, cons
                                         : lensIndexScan(pkey, s, P.antialias_samples));
     float r = (float)((double)(P.aperture / 2) * (double)rng_u01(pkey, 4u * li));
     float theta = (float)(2 * DRT_PI * (double)rng_u01(pkey, 4u * li + 1));
-    eye_sample = P.eye + (R)(r * cosf(theta)) * P.X + (R)(r * sinf(theta)) * P.Y;
+    // cos / sin of the float angle, correctly rounded to float through the double-precision functions: the reference calls
+    // the host's cosf / sinf, which CUDA's single-precision versions (1 ulp) miss in several percent of the arguments -- a
+    // lens point an ulp off is invisible, except where it flips a grazing shadow test (3 pixels of one fuzz scene)
+    const float cs = (float)cos((double)theta), sn = (float)sin((double)theta);
+    eye_sample = P.eye + (R)(r * cs) * P.X + (R)(r * sn) * P.Y;
   }
   // jitter (:1048-1056): computed, then truncated by getPerspEyeRay(int,int) (Q1)
   const int ii = s / P.n, jj = s % P.n;

@@ -44,7 +44,8 @@ enum WaveFeat {
   FT_TEX = 16,      // some primitive is textured
   FT_BIG = 32,      // more geoms than the shared-memory slab table holds (DRT_SMEM_GEOMS)
   FT_BOX = 64,      // slab-box prisms (RectPrism / RectPrismWithCylinder / RectPrismWithHoles) are present
-  FT_ALL = 127
+  FT_SPILL = 128,   // a rectangle whose edges B-A, D-A are not orthogonal is present (GF_SPILL: hits need the reference's gather replayed)
+  FT_ALL = 255
 };
 
 // the instantiated masks (drt_launch_impl.cuh must hold one DRT_WAVE_CASE per entry); FT_ALL last
