@@ -449,7 +449,7 @@ def test_row_chunking_does_not_change_the_image(oracle_lib):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("seed", range(14))
+@pytest.mark.parametrize("seed", list(range(14)) + [43, 151])   # 43, 151: depth of field past a wall whose corners are listed diagonally (GF_SPILL)
 def test_cuda_matches_oracle_on_mutated_scenes(oracle_lib, seed):
     """Fuzz: fixture scenes with random motion flags, BRDF models, roughness, reflective materials, glossy flags and
     settings (tests/fuzz_cases.py); the oracle is pinned on the compiled reference for the same kind of mutations by
