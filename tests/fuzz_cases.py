@@ -1,6 +1,7 @@
 """Mutated fixture scenes for the GPU-vs-oracle fuzz (tests/test_gpu_parity.py, tools/gpu_fuzz.py): stored fixture
-scenes with random motion flags, BRDF models, roughness, reflective materials, glossy flags and settings.  The CPU twin
-(tests/test_oracle_fuzz.py) pins the oracle on the compiled reference for the same kind of mutations."""
+scenes with random motion flags, BRDF models, roughness, reflective materials, glossy flags and settings, and random scenes
+no builder of the reference ever produced.  The CPU twin (tests/test_oracle_fuzz.py) pins the oracle on the compiled
+reference for the same mutations and the same random scenes."""
 import numpy as np
 
 from conftest import GOLDEN_CASES, load_case
@@ -39,3 +40,58 @@ def mutated_case(seed):
             if rng.random() < 0.5:
                 p.flags ^= abi.FLAG_GLOSSY
     return case, Scene(prims, scene.lights, scene.textures), s
+
+
+def random_scene(seed):
+    """A scene the reference never built: random spheres, cylinders, triangles, rectangles (corners in any order, so some
+    are the diagonal kind) and checkerboards around the origin, random materials / models, one to three lights."""
+    import numpy as np
+    from distraytracer_b200 import abi, scenes
+    from distraytracer_b200.scene import Scene
+    rng = np.random.default_rng(55000 + seed)
+    base, settings, _ = load_case("checkertexture")
+    P = lambda s=3.0: rng.uniform(-s, s, 3)
+    col = lambda: tuple(rng.uniform(0.2, 1.0, 3))
+    mat = lambda: int(rng.choice([abi.MAT_NONE, abi.MAT_NONE, abi.MAT_STEEL, abi.MAT_ALUMINUM]))
+    mod = lambda: int(rng.choice([abi.MODEL_LAMBERT, abi.MODEL_OREN_NAYAR, abi.MODEL_COOK_TORRANCE]))
+    prims = []
+    for _ in range(int(rng.integers(3, 14))):
+        kind = int(rng.integers(5))
+        if kind == 0:
+            p = scenes.sphere(P(), float(rng.uniform(0.2, 1.2)), col(), material=mat(), model=mod())
+        elif kind == 1:
+            a = P(); p = scenes.cylinder(a, a + rng.normal(0, 1.0, 3), float(rng.uniform(0.1, 0.5)), col(), material=mat(), model=mod())
+        elif kind == 2:
+            a = P(); p = scenes.triangle(a, a + rng.normal(0, 1.5, 3), a + rng.normal(0, 1.5, 3), col(), material=mat(), model=mod())
+        else:
+            a = P(4.0); u = rng.normal(0, 2.0, 3); v = np.cross(u, rng.normal(0, 1, 3)); v *= float(rng.uniform(0.5, 3.0)) / max(np.linalg.norm(v), 1e-9)
+            corners = [a, a + u, a + u + v, a + v]
+            if rng.random() < 0.35:
+                corners = [corners[i] for i in rng.permutation(4)]       # any corner order: the reference takes what it is given
+            if kind == 3:
+                p = scenes.rectangle(*corners, col(), material=mat(), model=mod(), name=int(rng.choice([abi.NAME_RECTANGLE, abi.NAME_OTHER])))
+            else:
+                p = scenes.checkerboard(*corners, col(), col(), float(rng.uniform(0.2, 1.0)), material=mat(), model=mod())
+        p.roughness = float(np.float32(rng.uniform(0.1, 0.9))); p.refr[0], p.refr[1] = 0.958, 6.69
+        if rng.random() < 0.3: p.flags |= abi.FLAG_GLOSSY
+        prims.append(p)
+    lights = []
+    for _ in range(int(rng.integers(1, 4))):
+        kind = int(rng.integers(3))
+        if kind == 0:
+            lights.append(scenes.point_light(P(6.0) + np.array([0, 4, 0]), col()))
+        elif kind == 1:
+            a = P(3.0) + np.array([0, 5, 0]); u = np.array([float(rng.uniform(0.5, 2)), 0, 0]); v = np.array([0, 0, float(rng.uniform(0.5, 2))])
+            lp, ll = scenes.rectangle_light(a, a + u, a + u + v, a + v, col(), len(prims)); prims.append(lp); lights.append(ll)
+        else:
+            lp, ll = scenes.sphere_light(P(4.0) + np.array([0, 5, 0]), float(rng.uniform(0.2, 0.8)), col(), len(prims)); prims.append(lp); lights.append(ll)
+    s = abi.copy_struct(settings)
+    s.xRes, s.yRes = int(rng.integers(24, 65)), int(rng.integers(18, 49))
+    s.antialias_samples = int(rng.choice([1, 4, 9])); s.aperture = float(rng.choice([0.0, 0.2]))
+    s.brdf_samples = int(rng.integers(1, 4)); s.max_depth = int(rng.integers(1, 6)); s.blur_samples = 0
+    s.seed = int(rng.integers(1, 1 << 30))
+    v = rng.normal(0, 1, 3); v /= np.linalg.norm(v)
+    eye = v * float(rng.uniform(5, 9)); eye[1] = abs(eye[1]) * 0.6
+    s.eye[:] = [float(x) for x in eye]; s.lookingAt[:] = [float(x) for x in rng.uniform(-0.5, 0.5, 3)]; s.up[:] = [0, 1, 0]
+    s.focal_length = float(np.linalg.norm(eye))
+    return "random_scene", Scene(prims, lights, base.textures), s

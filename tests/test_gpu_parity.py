@@ -463,6 +463,21 @@ def test_cuda_matches_oracle_on_mutated_scenes(oracle_lib, seed):
     assert st["frac_within_1"] >= TOL_FRAC, (case, st)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(16))
+def test_cuda_matches_oracle_on_random_scenes(oracle_lib, seed):
+    """Scenes no reference builder produced (fuzz_cases.random_scene; the oracle is pinned on the compiled reference for
+    the same scenes in tests/test_oracle_fuzz.py): random shapes of every analytic class, rectangles with their corners in
+    any order, all three light kinds, random cameras.  tools/gpu_fuzz.py N scenes runs more seeds (600 were bit-identical)."""
+    from fuzz_cases import random_scene
+    from oracle.harness import Oracle, ORACLE_KEYED, compare
+    _, scene, s = random_scene(seed)
+    want, _, _, _ = Oracle(scene).render(s, mode=ORACLE_KEYED)
+    got, _ = _gpu(scene).render_float(s)
+    st = compare(want, got)
+    assert st["frac_within_1"] >= TOL_FRAC, (seed, st)
+
+
 @pytest.mark.parametrize("variant", ["c2", "perlin_aa10", "chunks"])
 def test_render_multi_equals_the_single_device_frame(oracle_lib, variant, monkeypatch):
     """drt_render_multi (one frame on several scene handles, units of ~1024 samples claimed from one shared counter, every

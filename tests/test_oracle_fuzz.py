@@ -99,6 +99,27 @@ def test_restatement_matches_reference_on_mutated_scenes(oracle_lib, seed):
     assert np.array_equal(ref_img, img, equal_nan=True), (builder, frame, float(np.nanmax(np.abs(ref_img - img))))
 
 
+@pytest.mark.parametrize("seed", range(30))
+def test_restatement_matches_reference_on_random_scenes(oracle_lib, seed):
+    """Scenes no builder of the reference produces (fuzz_cases.random_scene: random spheres, cylinders, triangles,
+    rectangles with their corners in ANY order -- a third of them therefore with D - A a diagonal, Q20 -- checkerboards,
+    all three light kinds) loaded INTO the compiled reference: the restatement reproduces them to the bit."""
+    if not _have_reference():
+        pytest.skip("reference tree not present (GPU box): pinned by the stored fixtures instead")
+    from fuzz_cases import random_scene
+    from oracle.harness import Ref, Oracle, ORACLE_STREAM
+    _, scene, s = random_scene(seed)
+    r = Ref(mocap=False)
+    r.reset()
+    r.load(scene)
+    r.set_settings(s)
+    r.rng(1, s.seed, 0)
+    ref_img, ref_ab, _ = r.render_loop(int(s.frame), reset_policy=1, seed=s.seed)
+    img, ab, _, _ = Oracle(scene).render(s, mode=ORACLE_STREAM)
+    assert (ab == ref_ab).all(), (seed, "abort masks differ")
+    assert np.array_equal(ref_img, img, equal_nan=True), (seed, float(np.nanmax(np.abs(ref_img - img))))
+
+
 @pytest.mark.parametrize("cfg", ["config1", "config2", "config3"])
 def test_restatement_matches_reference_on_the_bench_workloads(oracle_lib, cfg):
     """The BASELINE configurations themselves (distraytracer_b200.scenes: config 2 is what bench.py times -- glass
