@@ -95,3 +95,57 @@ def random_scene(seed):
     s.eye[:] = [float(x) for x in eye]; s.lookingAt[:] = [float(x) for x in rng.uniform(-0.5, 0.5, 3)]; s.up[:] = [0, 1, 0]
     s.focal_length = float(np.linalg.norm(eye))
     return "random_scene", Scene(prims, lights, base.textures), s
+
+
+def random_mesh_scene(seed):
+    """A random triangle mesh (a bumpy grid with random holes, or a soup of random triangles; 40 to ~2000 triangles, with
+    texcoords and, half of the time, a per-triangle material table) plus a sphere or two, one or two lights, depth of
+    field.  -> (name, Scene with the mesh -- what the CUDA path takes, through its device-built 4-wide LBVH --, the same
+    scene with the triangles as Triangle primitives -- what the oracle's reference-order walk takes --, settings)."""
+    import numpy as np
+    from distraytracer_b200 import abi, scenes
+    from distraytracer_b200.scene import Scene
+    rng = np.random.default_rng(66000 + seed)
+    base, settings, _ = load_case("checkertexture")
+    if rng.random() < 0.6:
+        n = int(rng.integers(6, 33))
+        mesh = scenes.terrain_mesh(n, size=float(rng.uniform(3, 10)), height=float(rng.uniform(0.2, 2.0)))
+        keep = rng.random(len(mesh["indices"])) > float(rng.uniform(0.0, 0.3))
+        mesh["indices"] = np.ascontiguousarray(mesh["indices"][keep])
+    else:
+        nt = int(rng.integers(40, 400))
+        a = rng.uniform(-4, 4, (nt, 1, 3)); a[:, :, 1] *= 0.3
+        verts = (a + rng.normal(0, float(rng.uniform(0.2, 1.0)), (nt, 3, 3))).reshape(-1, 3).astype(np.float32)
+        mesh = {"vertices": verts, "indices": np.arange(3 * nt, dtype=np.int32).reshape(nt, 3),
+                "texcoords": rng.uniform(0, 1, (3 * nt, 2)).astype(np.float32)}
+    textured = rng.random() < 0.5
+    mesh["material"] = scenes.mesh_material(tex_frame=2 if textured else -1,
+                                            model=int(rng.choice([abi.MODEL_LAMBERT, abi.MODEL_OREN_NAYAR, abi.MODEL_COOK_TORRANCE])),
+                                            roughness=float(rng.uniform(0.2, 0.8)))
+    mesh["material"].refr[0], mesh["material"].refr[1] = 0.958, 6.69
+    if rng.random() < 0.5:
+        mats = []
+        for v in rng.uniform(0.1, 0.9, 5):
+            m = abi.copy_struct(mesh["material"]); m.roughness = float(np.float32(v)); m.color[0] = float(v); mats.append(m)
+        mesh["materials"] = mats
+        mesh["material_ids"] = rng.integers(0, 5, len(mesh["indices"])).astype(np.int32)
+    prims = [scenes.sphere(rng.uniform(-2, 2, 3) + np.array([0, 1.5, 0]), float(rng.uniform(0.3, 0.9)), tuple(rng.uniform(0.2, 1, 3)),
+                           material=int(rng.choice([abi.MAT_NONE, abi.MAT_STEEL])))]
+    if rng.random() < 0.5:
+        prims.append(scenes.rectangle((-6, -1.5, 6), (6, -1.5, 6), (6, -1.5, -6), (-6, -1.5, -6), (0.6, 0.6, 0.6), name=abi.NAME_OTHER))
+    lights = [scenes.point_light(rng.uniform(-5, 5, 3) + np.array([0, 7, 0]), (1.0, 1.0, 1.0))]
+    if rng.random() < 0.5:
+        lp, ll = scenes.sphere_light(rng.uniform(-3, 3, 3) + np.array([0, 6, 0]), 0.5, (0.8, 0.8, 1.0), len(prims))
+        prims.append(lp); lights.append(ll)
+    s = abi.copy_struct(settings)
+    s.xRes, s.yRes = int(rng.integers(24, 65)), int(rng.integers(18, 49))
+    s.antialias_samples = int(rng.choice([1, 4])); s.aperture = float(rng.choice([0.0, 0.2]))
+    s.brdf_samples = int(rng.integers(1, 3)); s.max_depth = int(rng.integers(1, 5)); s.blur_samples = 0
+    s.seed = int(rng.integers(1, 1 << 30))
+    v = rng.normal(0, 1, 3); v /= np.linalg.norm(v)
+    eye = v * float(rng.uniform(6, 11)); eye[1] = abs(eye[1]) * 0.7 + 1.0
+    s.eye[:] = [float(x) for x in eye]; s.lookingAt[:] = [0.0, 0.0, 0.0]; s.up[:] = [0, 1, 0]
+    s.focal_length = float(np.linalg.norm(eye))
+    with_mesh = Scene(prims, lights, base.textures, mesh=mesh)
+    flat = Scene(list(prims) + scenes.mesh_to_prims(mesh), lights, base.textures)
+    return "random_mesh", with_mesh, flat, s

@@ -1,6 +1,6 @@
 """GPU vs oracle on mutated fixture scenes, any number of seeds (tests/test_gpu_parity.py runs the first 14).
   python tools/gpu_fuzz.py [n_cases] [cam]
-`scenes`: random scenes instead of mutated fixtures (random_scene).  `cam`: the camera is moved as well (eye / lookingAt jittered, focal length and aperture redrawn), so rays reach the scenes
+`scenes`: random scenes instead of mutated fixtures (random_scene); `meshes`: random triangle meshes (random_mesh_scene).  `cam`: the camera is moved as well (eye / lookingAt jittered, focal length and aperture redrawn), so rays reach the scenes
 from directions the reference's builders never look from -- grazing walls, looking along an axis, from inside a prism.
 """
 import os
@@ -8,16 +8,19 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
-from fuzz_cases import mutated_case, random_scene  # noqa: E402
+from fuzz_cases import mutated_case, random_scene, random_mesh_scene  # noqa: E402
 from distraytracer_b200 import runtime  # noqa: E402
 from oracle.harness import Oracle, ORACLE_KEYED, compare  # noqa: E402
 
 n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 40
 move_camera = len(sys.argv) > 2 and sys.argv[2] == "cam"
 random_scenes = len(sys.argv) > 2 and sys.argv[2] == "scenes"
+random_meshes = len(sys.argv) > 2 and sys.argv[2] == "meshes"
 bad = 0
 for seed in range(n_cases):
-    case, sc, s = random_scene(seed) if random_scenes else mutated_case(seed)
+    flat = None
+    if random_meshes: case, sc, flat, s = random_mesh_scene(seed)
+    else: case, sc, s = random_scene(seed) if random_scenes else mutated_case(seed)
     if move_camera:
         import numpy as np
         rng = np.random.default_rng(77000 + seed)
@@ -35,7 +38,7 @@ for seed in range(n_cases):
             eye = look + (eye - look) * float(rng.uniform(0.02, 0.3))
         s.eye[:] = [float(x) for x in eye]; s.lookingAt[:] = [float(x) for x in look]
         s.aperture = float(rng.choice([0.0, 0.05, 0.4])); s.focal_length = float(rng.uniform(0.5, 2.0) * d)
-    want, _, _, _ = Oracle(sc).render(s, mode=ORACLE_KEYED)
+    want, _, _, _ = Oracle(flat if flat is not None else sc).render(s, mode=ORACLE_KEYED)   # meshes: the oracle takes Triangle primitives
     got, _ = runtime.DeviceScene(sc, 0).render_float(s)
     st = compare(want, got)
     ok = st["frac_within_1"] >= 0.999
