@@ -149,3 +149,26 @@ def random_mesh_scene(seed):
     with_mesh = Scene(prims, lights, base.textures, mesh=mesh)
     flat = Scene(list(prims) + scenes.mesh_to_prims(mesh), lights, base.textures)
     return "random_mesh", with_mesh, flat, s
+
+
+def random_motion_scene(seed):
+    """random_scene with the library's own blur mode (DRT_BLUR_VELOCITY, SURVEY 8(f)1: the reference has no counterpart, the
+    oracle twin is the checker): random velocities on flagged primitives, cylinders partly with two-pose end points."""
+    import numpy as np
+    from distraytracer_b200 import abi
+    from distraytracer_b200.scene import Scene
+    case, scene, s = random_scene(seed)
+    rng = np.random.default_rng(88000 + seed)
+    prims = [abi.copy_struct(p) for p in scene.prims]
+    for p in prims:
+        if (p.flags & abi.FLAG_LIGHT) or rng.random() < 0.5:
+            continue
+        p.flags |= abi.FLAG_MOTION
+        v = rng.normal(0, 0.6, 3)
+        p.velocity[0], p.velocity[1], p.velocity[2] = (float(x) for x in v)
+        if p.type == abi.PRIM_CYLINDER and rng.random() < 0.6:
+            p.flags |= abi.FLAG_VERTEX_MOTION
+            w = rng.normal(0, 0.6, 3)
+            p.velocity2[0], p.velocity2[1], p.velocity2[2] = (float(x) for x in w)
+    s.blur_mode, s.blur_samples, s.frame_range = abi.BLUR_VELOCITY, int(rng.integers(1, 4)), 1
+    return "random_motion", Scene(prims, scene.lights, scene.textures), s

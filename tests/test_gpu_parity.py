@@ -493,6 +493,21 @@ def test_cuda_matches_oracle_on_random_meshes(oracle_lib, seed):
     assert st["frac_within_1"] >= TOL_FRAC, (seed, st)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 31, 72, 93, 249])
+def test_cuda_matches_oracle_on_random_scenes_in_velocity_blur(oracle_lib, seed):
+    """DRT_BLUR_VELOCITY (the library's own blur mode) on random scenes: random velocities, two-pose
+    cylinders, rectangles of the diagonal kind (Q20: in a velocity re-trace every primitive is a candidate, there is no
+    reference gather to replay -- seeds 31 ... 249 are the ones on which the oracle twin once culled such a rectangle)."""
+    from fuzz_cases import random_motion_scene
+    from oracle.harness import Oracle, ORACLE_KEYED, compare
+    _, scene, s = random_motion_scene(seed)
+    want, _, _, _ = Oracle(scene).render(s, mode=ORACLE_KEYED)
+    got, _ = _gpu(scene).render_float(s)
+    st = compare(want, got)
+    assert st["frac_within_1"] >= TOL_FRAC, (seed, st)
+
+
 @pytest.mark.parametrize("variant", ["c2", "perlin_aa10", "chunks"])
 def test_render_multi_equals_the_single_device_frame(oracle_lib, variant, monkeypatch):
     """drt_render_multi (one frame on several scene handles, units of ~1024 samples claimed from one shared counter, every
