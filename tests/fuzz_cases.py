@@ -172,3 +172,48 @@ def random_motion_scene(seed):
             p.velocity2[0], p.velocity2[1], p.velocity2[2] = (float(x) for x in w)
     s.blur_mode, s.blur_samples, s.frame_range = abi.BLUR_VELOCITY, int(rng.integers(1, 4)), 1
     return "random_motion", Scene(prims, scene.lights, scene.textures), s
+
+
+def random_big_scene(seed):
+    """More analytic shapes than the CUDA path's shared-memory filter table holds (257 .. 700): small spheres, cylinders and
+    rectangles scattered over a floor -- the CUDA path gathers through its 4-wide tree over the geoms."""
+    import numpy as np
+    from distraytracer_b200 import abi, scenes
+    from distraytracer_b200.scene import Scene
+    rng = np.random.default_rng(99000 + seed)
+    base, settings, _ = load_case("checkertexture")
+    prims = [scenes.rectangle((-9, 0, 9), (9, 0, 9), (9, 0, -9), (-9, 0, -9), (0.7, 0.7, 0.7),
+                              material=int(rng.choice([abi.MAT_NONE, abi.MAT_STEEL])), name=abi.NAME_OTHER)]
+    for _ in range(int(rng.integers(257, 700))):
+        c = rng.uniform(-8, 8, 3); c[1] = float(rng.uniform(0.1, 2.5))
+        col = tuple(rng.uniform(0.2, 1.0, 3))
+        kind = int(rng.integers(3))
+        if kind == 0:
+            prims.append(scenes.sphere(c, float(rng.uniform(0.08, 0.35)), col, material=int(rng.choice([abi.MAT_NONE, abi.MAT_NONE, abi.MAT_STEEL]))))
+        elif kind == 1:
+            prims.append(scenes.cylinder(c, c + rng.normal(0, 0.4, 3), float(rng.uniform(0.05, 0.15)), col))
+        else:
+            u = rng.normal(0, 0.4, 3); v = np.cross(u, rng.normal(0, 1, 3)); v *= 0.4 / max(np.linalg.norm(v), 1e-9)
+            prims.append(scenes.rectangle(c, c + u, c + u + v, c + v, col, name=abi.NAME_OTHER))
+    lp, ll = scenes.rectangle_light((-1, 6, -1), (1, 6, -1), (1, 6, 1), (-1, 6, 1), (1.0, 1.0, 0.9), len(prims))
+    prims.append(lp)
+    lights = [ll, scenes.point_light(rng.uniform(-6, 6, 3) + np.array([0, 8, 0]), (0.7, 0.7, 0.7))]
+    s = abi.copy_struct(settings)
+    s.xRes, s.yRes = int(rng.integers(24, 65)), int(rng.integers(18, 49))
+    s.antialias_samples = int(rng.choice([1, 4])); s.aperture = float(rng.choice([0.0, 0.2]))
+    s.brdf_samples = int(rng.integers(1, 3)); s.max_depth = int(rng.integers(1, 5)); s.blur_samples = 0
+    s.seed = int(rng.integers(1, 1 << 30))
+    v = rng.normal(0, 1, 3); v /= np.linalg.norm(v)
+    eye = v * float(rng.uniform(7, 14)); eye[1] = abs(eye[1]) * 0.6 + 1.5
+    s.eye[:] = [float(x) for x in eye]; s.lookingAt[:] = [0.0, 0.5, 0.0]; s.up[:] = [0, 1, 0]
+    s.focal_length = float(np.linalg.norm(eye))
+    return "random_big", Scene(prims, lights, base.textures), s
+
+
+def sky_case(seed):
+    """mutated_case with the value-noise cloud background switched on (perlin_cloud: cloud_corners + the per-sample corner
+    offsets) at a small size -- the oracle marches 200 noise steps per pixel corner."""
+    case, scene, s = mutated_case(seed)
+    s.perlin_cloud = 1
+    s.xRes, s.yRes = min(s.xRes, 40), min(s.yRes, 28)
+    return case + "+sky", scene, s

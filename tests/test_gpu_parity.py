@@ -508,6 +508,20 @@ def test_cuda_matches_oracle_on_random_scenes_in_velocity_blur(oracle_lib, seed)
     assert st["frac_within_1"] >= TOL_FRAC, (seed, st)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,seed", [("big", 0), ("big", 1), ("big", 2), ("big", 3), ("sky", 0), ("sky", 1), ("sky", 2), ("sky", 3)])
+def test_cuda_matches_oracle_on_big_scenes_and_cloud_backgrounds(oracle_lib, kind, seed):
+    """fuzz_cases.random_big_scene (257..700 shapes: the tree over the geoms) and fuzz_cases.sky_case (mutated fixtures in
+    front of the value-noise clouds: cloud_corners + per-sample corner offsets); tools/gpu_fuzz.py ran 300 / 200 seeds."""
+    from fuzz_cases import random_big_scene, sky_case
+    from oracle.harness import Oracle, ORACLE_KEYED, compare
+    _, scene, s = (random_big_scene if kind == "big" else sky_case)(seed)
+    want, _, _, _ = Oracle(scene).render(s, mode=ORACLE_KEYED)
+    got, _ = _gpu(scene).render_float(s)
+    st = compare(want, got)
+    assert st["frac_within_1"] >= TOL_FRAC, (kind, seed, st)
+
+
 @pytest.mark.parametrize("variant", ["c2", "perlin_aa10", "chunks"])
 def test_render_multi_equals_the_single_device_frame(oracle_lib, variant, monkeypatch):
     """drt_render_multi (one frame on several scene handles, units of ~1024 samples claimed from one shared counter, every

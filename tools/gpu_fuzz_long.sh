@@ -1,4 +1,6 @@
 #!/bin/bash
-# a long GPU-vs-oracle fuzz (mutated fixture scenes; with "cam" the camera moves too); prints only the mismatching seeds
+# long GPU-vs-oracle fuzz runs; prints only the mismatching seeds.  usage: tools/gpu_fuzz_long.sh "<n> <mode>" ["<n> <mode>" ...]
 cd "$(dirname "$0")/.."
-timeout 2400 python tools/gpu_fuzz.py ${1:-1000} $2 2>&1 | grep -i "mismatch\|error\|Traceback" | head -40
+for spec in "$@"; do
+  echo "== $spec"; timeout 2400 python tools/gpu_fuzz.py $spec 2>&1 | grep -i "mismatch\|error\|Traceback" | head -30
+done
