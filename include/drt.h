@@ -314,7 +314,12 @@ void drt_prim_default(drt_prim* p);
 /* Validate + repack the scene into device SoA buffers on `device`, upload the
  * textures, and build the BVH there.  Replaces generateBVH
  * (render_final_project.cpp:980, helpers.h:381-472).  The scene is immutable
- * afterwards except through drt_scene_update_prims. */
+ * afterwards except through drt_scene_update_prims.
+ * Size: any number of analytic primitives (up to 256 intersectable pieces are culled by a
+ * filter table in shared memory, larger scenes through a tree over the pieces) plus one
+ * optional triangle mesh of up to 2^30 triangles.  Device memory: the scene tables, and per
+ * render call the sample records (16 bytes per camera sample of a launch, at most 8 GiB) and
+ * the ray pools of the persistent kernel (about 25 MB per SM at max_depth 10, brdf_samples 2). */
 int drt_scene_create(const drt_scene_desc* desc, int device, drt_scene** out);
 /* Replace the analytic primitives in place (same count and types), e.g. the
  * re-posed bone cylinders of the next mocap frame (scene.h:637-659). */
