@@ -695,7 +695,9 @@ void fillParams(Params<R>& P, const drt_scene* s, const DevScene<R>& ds, const d
     P.mesh_nodes = s->mesh.nodes; P.n_mesh_tris = s->mesh.n_tris; P.mesh_prim = (int)s->prims.size();
     P.mesh_tris = (const MeshTri<R>*)(sizeof(R) == 8 ? s->mesh.tris_f64 : s->mesh.tris_f32);
     P.mesh_mat = s->mesh.mat_ids;
-  }
+    const drt_prim& m0 = s->mesh_materials[0];
+    P.mesh_vel = mk<R>((R)m0.velocity[0], (R)m0.velocity[1], (R)m0.velocity[2]);
+  } else P.mesh_vel = mk<R>(R(0), R(0), R(0));
 }
 
 int ensureScratch(drt_scene* s, size_t n_samples, size_t n_corners, size_t n_out) {
@@ -1197,8 +1199,13 @@ int drt_scene_create(const drt_scene_desc* d, int device, drt_scene** out) {
   if (d->mesh) {
     if (d->mesh->n_materials > 0 && d->mesh->materials) s->mesh_materials.assign(d->mesh->materials, d->mesh->materials + d->mesh->n_materials);
     else s->mesh_materials.assign(1, d->mesh->material);
-    for (const drt_prim& m : s->mesh_materials)
+    for (const drt_prim& m : s->mesh_materials) {
       if ((m.flags & DRT_FLAG_TEXTURE) && !d->mesh->texcoords) return bail(fail(DRT_ERR_INVALID, "textured mesh without texcoords"));
+      // DRT_BLUR_VELOCITY moves a mesh rigidly: the traversal shifts the ray instead of a million triangles
+      for (int a = 0; a < 3; a++)
+        if (m.velocity[a] != s->mesh_materials[0].velocity[a]) return bail(fail(DRT_ERR_UNSUPPORTED, "mesh materials with different velocities (a mesh moves as a whole)"));
+      if (m.flags & DRT_FLAG_VERTEX_MOTION) return bail(fail(DRT_ERR_UNSUPPORTED, "DRT_FLAG_VERTEX_MOTION on a mesh material"));
+    }
     std::string err;
     int mrc = buildMesh(d->mesh, &s->mesh, err);
     if (mrc) return bail(fail(mrc, err));

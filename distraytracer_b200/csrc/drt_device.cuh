@@ -207,6 +207,7 @@ struct Params {
   // triangle mesh (optional): LBVH nodes (4 float4 each), exact-test records, material = prims[mesh_prim]
   const float4* mesh_nodes; const MeshTri<R>* mesh_tris; int n_mesh_tris; int mesh_prim;
   const unsigned short* mesh_mat;   // per-triangle material: prims[mesh_prim + mesh_mat[tri]]; nullptr: prims[mesh_prim]
+  Vec<R> mesh_vel;                  // DRT_BLUR_VELOCITY: the mesh moves as a whole by mesh_vel * time (its materials' common velocity)
   const cudaTextureObject_t* tex; const int2* texdims;
   // buffers
   float4* samples;          // [pixel_in_tile * spp + s] : rgb + flag bits

@@ -959,13 +959,13 @@ __device__ inline bool anyHit(const Params<R>& P, const SlabTab gb, const Moved<
 // ---- triangle mesh: LBVH traversal (drt_lbvh.cuh) ------------------------------------------
 // Triangle::intersect (geometry.cpp:488-553) on a mesh triangle; returns t or a negative value.
 template <typename R>
-__device__ __forceinline__ float meshTriT(const MeshTri<R>& tr, const Vec<R>& ray, const Vec<R>& start) {
-  const Vec<R> r1 = tr.B - tr.A, r2 = tr.C - tr.A;
+__device__ __forceinline__ float meshTriT(const Vec<R>& tA, const Vec<R>& tB, const Vec<R>& tC, const Vec<R>& ray, const Vec<R>& start) {
+  const Vec<R> r1 = tB - tA, r2 = tC - tA;
   const Vec<R> hh = cross(ray, r2);
   const float det = (float)dot(r1, hh);
   const float invdet = 1.0f / det;   // == (float)(1.0 / (double)det) up to double rounding on float ties
   if (det >= -0.0001f && det <= 0.0001f) return -1.f;
-  const Vec<R> A0 = start - tr.A;
+  const Vec<R> A0 = start - tA;
   const float u = (float)((double)invdet * (double)dot(A0, hh));
   if (u < 0 || u > 1) return -1.f;
   const Vec<R> DA0 = cross(A0, r1);
@@ -984,9 +984,17 @@ __device__ __forceinline__ float meshTriT(const MeshTri<R>& tr, const Vec<R>& ra
 // own leaf box: bounds +- 1e-2, geometry.cpp:2653-2654).
 template <typename R, int F, bool COUNT, bool CLOSEST>
 __device__ bool meshTraverse(const Params<R>& P, const Vec<R>& ray, const Vec<R>& start, float t_limit, HitRec* h,
-                             const Vec<R>& gather_ray, const Vec<R>& gather_start, Counts& cnt) {
+                             const Vec<R>& gather_ray, const Vec<R>& gather_start, const bool vel_retrace, const R time, Counts& cnt) {
+  // A velocity re-trace at time offset `time` displaces the whole mesh by mesh_vel * time.  The tree stays as built and is
+  // walked with the ray moved the other way (its boxes are padded far beyond the rounding of that); the exact test runs
+  // on the displaced vertices, as the oracle twin's per-triangle walk does.  (Only the time is carried through the walk.)
+  const bool disp = (F & FT_VEL) && vel_retrace && (P.mesh_vel.x != R(0) || P.mesh_vel.y != R(0) || P.mesh_vel.z != R(0));
   const float ix = 1.0f / (float)ray.x, iy = 1.0f / (float)ray.y, iz = 1.0f / (float)ray.z;
-  const float nox = -(float)start.x * ix, noy = -(float)start.y * iy, noz = -(float)start.z * iz;
+  float nox = -(float)start.x * ix, noy = -(float)start.y * iy, noz = -(float)start.z * iz;
+  if (disp) {
+    const Vec<R> shift = P.mesh_vel * time;
+    nox = -(float)(start.x - shift.x) * ix; noy = -(float)(start.y - shift.y) * iy; noz = -(float)(start.z - shift.z) * iz;
+  }
   const float serr = 4e-7f * (fabsf(nox) + fabsf(noy) + fabsf(noz));           // as in slabRay
   SlabRay sr = slabRay(ix, iy, iz, nox, noy, noz, (t_limit < FLT_MAX) ? t_limit * 1.0001f + 1e-4f : FLT_MAX);
   int2 stack[DRT_NODE_STACK];                                                   // (child reference, entry distance bits)
@@ -1003,13 +1011,16 @@ __device__ bool meshTraverse(const Params<R>& P, const Vec<R>& ray, const Vec<R>
       const int tri = -cur - 1;
       if (COUNT) cnt.geom_tests[G_TRI]++;
       const MeshTri<R>& tr = P.mesh_tris[tri];
-      const float t = meshTriT<R>(tr, ray, start);
+      float t;
+      if (disp) { const Vec<R> shift = P.mesh_vel * time; t = meshTriT<R>(tr.A + shift, tr.B + shift, tr.C + shift, ray, start); }
+      else t = meshTriT<R>(tr.A, tr.B, tr.C, ray, start);
       if (CLOSEST) {
         if (t > 0.0001f && t < h->t) {
           h->t = t; h->geom = P.n_geoms + tri; h->inside = 0; h->checker_sel = 0; found = true;
           sr.lim = (t * 1.0001f + 1e-4f) + serr;
         }
       } else if (t > 0.001f && t < t_limit) {
+        if ((F & FT_VEL) && vel_retrace) return true;                           // a velocity re-trace has no reference gather: every triangle is a candidate
         if (t > t_limit * 1e-3f * 1.001f + 2e-3f) return true;                  // touch point ahead of the gather origin
         NodeD<R> nd;                                                            // its own leaf box, BoundingVolume semantics
         nd.lo = mk<R>(fmin(fmin(tr.A.x, tr.B.x), tr.C.x) - R(1e-2), fmin(fmin(tr.A.y, tr.B.y), tr.C.y) - R(1e-2),
@@ -1167,7 +1178,9 @@ __device__ inline bool traceRay(const Params<R>& P, const SlabTab gb, const Task
   if (COUNT) cnt.rays++;
   const Moved<R> mv = makeMoved<R, F>(P, T.dt);
   closestHit<R, F, COUNT>(P, gb, mv, T.dir, T.org, h, cnt);
-  if ((F & FT_MESH) && P.n_mesh_tris > 0) meshTraverse<R, F, COUNT, true>(P, T.dir, T.org, h.t, &h, T.dir, T.org, cnt);
+  if ((F & FT_MESH) && P.n_mesh_tris > 0) {
+    meshTraverse<R, F, COUNT, true>(P, T.dir, T.org, h.t, &h, T.dir, T.org, (F & FT_VEL) && mv.velocity_mode, mv.time, cnt);
+  }
   // the in_motion chain only matters when a blur re-trace can follow
   if ((F & (FT_VEL | FT_REFBLUR)) && (T.bits & TASK_CHAIN)) motion = 0;             // :519
   if (h.geom < 0) return false;                                         // :541-544
@@ -1279,7 +1292,8 @@ __device__ void shadeA(const Params<R>& P, const Task<R>& T, const HitRec& h, Ta
       }
     } else if (mesh_tri >= 0) {                                         // Triangle::getNorm geometry.cpp:588-594
       const MeshTri<R>& tr = P.mesh_tris[mesh_tri];
-      normal = normalized(cross(tr.B - tr.A, tr.C - tr.A));
+      const Vec<R> tA = shiftPoint<R, F>(mv, 0, P.mesh_vel, tr.A), tB = shiftPoint<R, F>(mv, 0, P.mesh_vel, tr.B), tC = shiftPoint<R, F>(mv, 0, P.mesh_vel, tr.C);
+      normal = normalized(cross(tB - tA, tC - tA));
     } else {
       normal = pr.n0;                                                   // Triangle / Rectangle family
     }
@@ -1446,7 +1460,8 @@ __device__ void shadowPair(const Params<R>& P, const SlabTab gb, const PairIn<R>
   bool occluded = anyHit<R, F, COUNT>(P, gb, mv, sray, isectP + sray * R(1e-3), sdir, isectP + sdir * R(1e-3), t_max, L.prim_index, cnt, threw);
   if ((F & FT_BOX) && threw) { out.state[oi] = 2; return; }             // RectPrismWithHoles::getNorm threw inside intersectShadow
   if ((F & FT_MESH) && !occluded && P.n_mesh_tris > 0)
-    occluded = meshTraverse<R, F, COUNT, false>(P, sdir, isectP + sdir * R(1e-3), t_max, nullptr, sray, isectP + sray * R(1e-3), cnt);
+    occluded = meshTraverse<R, F, COUNT, false>(P, sdir, isectP + sdir * R(1e-3), t_max, nullptr, sray, isectP + sray * R(1e-3),
+                                                (F & FT_VEL) && mv.velocity_mode, mv.time, cnt);
   out.state[oi] = occluded ? 0 : 1;
 }
 
@@ -1522,7 +1537,11 @@ __device__ void shadeB(const Params<R>& P, ShadeState<R>& S, const PairOut<R>& r
         } else if (pr.type == 2) {                                      // Triangle::getUV geometry.cpp:447-486
           Vec<R> tA = shiftPoint<R, F>(S.mv, 0, pr.vel, pr.tA), tB = shiftPoint<R, F>(S.mv, 0, pr.vel, pr.tB), tC = shiftPoint<R, F>(S.mv, 0, pr.vel, pr.tC);
           const float* tuv = pr.tuv;
-          if ((F & FT_MESH) && S.tri >= 0) { const MeshTri<R>& tr = P.mesh_tris[S.tri]; tA = tr.A; tB = tr.B; tC = tr.C; tuv = tr.uv; }
+          if ((F & FT_MESH) && S.tri >= 0) {
+            const MeshTri<R>& tr = P.mesh_tris[S.tri];
+            tA = shiftPoint<R, F>(S.mv, 0, P.mesh_vel, tr.A); tB = shiftPoint<R, F>(S.mv, 0, P.mesh_vel, tr.B); tC = shiftPoint<R, F>(S.mv, 0, P.mesh_vel, tr.C);
+            tuv = tr.uv;
+          }
           Vec<R> nn = cross(tB - tA, tC - tA);
           Vec<R> n_a = cross(tC - tB, S.isectP - tB), n_b = cross(tA - tC, S.isectP - tC);
           float n_sq = (float)dot(nn, nn);

@@ -187,7 +187,9 @@ typedef struct drt_texture {
  * reference then transforms them in double, scene.h:297-307 -- a mesh that needs that is transformed by the caller).
  * Materials: every triangle uses `material`, unless `materials` is given -- then triangle t uses
  * materials[material_ids[t]].  That is how the reference's per-face roughness (one value per Triangle, looked up in a
- * roughness map, scene.h:372-378: at most 766 distinct values) travels without a material record per triangle. */
+ * roughness map, scene.h:372-378: at most 766 distinct values) travels without a material record per triangle.
+ * Motion (DRT_BLUR_VELOCITY): a mesh moves as a whole -- DRT_FLAG_MOTION and `velocity` of its material(s), which must
+ * agree; the traversal moves the ray instead of the triangles. */
 typedef struct drt_mesh {
   int64_t n_vertices, n_triangles;
   const float* vertices;   /* 3 floats per vertex               */

@@ -217,3 +217,29 @@ def sky_case(seed):
     s.perlin_cloud = 1
     s.xRes, s.yRes = min(s.xRes, 40), min(s.yRes, 28)
     return case + "+sky", scene, s
+
+
+def random_moving_mesh_scene(seed):
+    """random_mesh_scene in velocity-blur mode with the MESH in motion (DRT_BLUR_VELOCITY moves a mesh as a whole by its
+    materials' common velocity) and, half of the time, the sphere too."""
+    import numpy as np
+    from distraytracer_b200 import abi, scenes
+    from distraytracer_b200.scene import Scene
+    case, with_mesh, flat, s = random_mesh_scene(seed)
+    rng = np.random.default_rng(44000 + seed)
+    vel = rng.normal(0, 0.5, 3)
+    mesh = dict(with_mesh.mesh)
+    def move(m):
+        m = abi.copy_struct(m); m.flags |= abi.FLAG_MOTION
+        m.velocity[0], m.velocity[1], m.velocity[2] = (float(x) for x in vel)
+        return m
+    mesh["material"] = move(mesh["material"])
+    if mesh.get("materials"):
+        mesh["materials"] = [move(m) for m in mesh["materials"]]
+    prims = [abi.copy_struct(p) for p in with_mesh.prims]
+    if rng.random() < 0.5:
+        prims[0].flags |= abi.FLAG_MOTION
+        w = rng.normal(0, 0.5, 3); prims[0].velocity[0], prims[0].velocity[1], prims[0].velocity[2] = (float(x) for x in w)
+    s.blur_mode, s.blur_samples, s.frame_range = abi.BLUR_VELOCITY, int(rng.integers(1, 4)), 1
+    return ("random_moving_mesh", Scene(prims, with_mesh.lights, with_mesh.textures, mesh=mesh),
+            Scene(list(prims) + scenes.mesh_to_prims(mesh), with_mesh.lights, with_mesh.textures), s)

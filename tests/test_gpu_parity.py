@@ -522,6 +522,21 @@ def test_cuda_matches_oracle_on_big_scenes_and_cloud_backgrounds(oracle_lib, kin
     assert st["frac_within_1"] >= TOL_FRAC, (kind, seed, st)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(6))
+def test_cuda_matches_oracle_on_moving_meshes(oracle_lib, seed):
+    """A mesh in motion (DRT_BLUR_VELOCITY: the whole mesh by its material's velocity -- the traversal moves the ray through
+    the static tree, the exact test runs on the displaced vertices) against the oracle twin, which moves every triangle
+    (fuzz_cases.random_moving_mesh_scene; tools/gpu_fuzz.py ran 300 seeds bit-identical)."""
+    from fuzz_cases import random_moving_mesh_scene
+    from oracle.harness import Oracle, ORACLE_KEYED, compare
+    _, scene, flat, s = random_moving_mesh_scene(seed)
+    want, _, _, _ = Oracle(flat).render(s, mode=ORACLE_KEYED)
+    got, _ = _gpu(scene).render_float(s)
+    st = compare(want, got)
+    assert st["frac_within_1"] >= TOL_FRAC, (seed, st)
+
+
 @pytest.mark.parametrize("variant", ["c2", "perlin_aa10", "chunks"])
 def test_render_multi_equals_the_single_device_frame(oracle_lib, variant, monkeypatch):
     """drt_render_multi (one frame on several scene handles, units of ~1024 samples claimed from one shared counter, every
