@@ -243,3 +243,49 @@ def random_moving_mesh_scene(seed):
     s.blur_mode, s.blur_samples, s.frame_range = abi.BLUR_VELOCITY, int(rng.integers(1, 4)), 1
     return ("random_moving_mesh", Scene(prims, with_mesh.lights, with_mesh.textures, mesh=mesh),
             Scene(list(prims) + scenes.mesh_to_prims(mesh), with_mesh.lights, with_mesh.textures), s)
+
+
+def random_prism_scene(seed):
+    """The slab-box prism classes (RectPrism / RectPrismWithCylinder / RectPrismWithHoles) with random
+    extents and random holes (spheres and cylinders, inside, across and outside the box), over a floor, next to a sphere,
+    under random lights, seen from anywhere -- including from inside the prism."""
+    import numpy as np
+    from distraytracer_b200 import abi, scenes
+    from distraytracer_b200.scene import Scene
+    rng = np.random.default_rng(33000 + seed)
+    base, settings, _ = load_case("checkertexture")
+    prims = [scenes.rectangle((-6, -2.2, -6), (8, -2.2, -6), (8, -2.2, 6), (-6, -2.2, 6), (0.7, 0.7, 0.7), name=abi.NAME_OTHER),
+             scenes.sphere((3.0, 0.0, 2.6), 0.8, (0.2, 0.9, 0.3), material=int(rng.choice([abi.MAT_NONE, abi.MAT_STEEL])))]
+    for _ in range(int(rng.integers(1, 3))):
+        kind = int(rng.choice([abi.PRIM_RECTPRISM, abi.PRIM_RECTPRISM_CYL, abi.PRIM_RECTPRISM_HOLES]))
+        lo = rng.uniform(-3, 1, 3); hi = lo + rng.uniform(0.6, 3.5, 3)
+        p = scenes.new_prim(); p.type = kind
+        A = np.array([lo[0], lo[1], lo[2]]); B = np.array([lo[0], lo[1], hi[2]]); C = np.array([lo[0], hi[1], hi[2]]); D = np.array([lo[0], hi[1], lo[2]])
+        back = np.array([hi[0] - lo[0], 0, 0])
+        for dst, v in zip((p.A, p.B, p.C, p.D, p.E, p.F, p.G, p.H), (A, B, C, D, A + back, B + back, C + back, D + back)):
+            dst[:] = list(v)
+        p.color[:] = list(rng.uniform(0.2, 1.0, 3)); p.center[:] = list((lo + hi) / 2)
+        p.material = int(rng.choice([abi.MAT_NONE, abi.MAT_NONE, abi.MAT_STEEL]))
+        p.model = int(rng.choice([abi.MODEL_LAMBERT, abi.MODEL_OREN_NAYAR])); p.roughness = float(np.float32(rng.uniform(0.2, 0.8)))
+        if kind != abi.PRIM_RECTPRISM:
+            p.n_holes = int(rng.integers(1, 4))
+            for k in range(p.n_holes):
+                sph = kind == abi.PRIM_RECTPRISM_HOLES and rng.random() < 0.5
+                c1 = rng.uniform(lo - 0.5, hi + 0.5)
+                p.holes[k].type = abi.PRIM_SPHERE if sph else abi.PRIM_CYLINDER
+                p.holes[k].c1[:] = list(c1); p.holes[k].c2[:] = list(c1 + rng.normal(0, 1.2, 3))
+                p.holes[k].radius = float(np.float32(rng.uniform(0.2, 1.0))); p.holes[k].color[:] = list(rng.uniform(0, 1, 3))
+        prims.append(p)
+    lights = [scenes.point_light(rng.uniform(-6, 6, 3) + np.array([0, 5, 0]), (1, 1, 1))]
+    if rng.random() < 0.5:
+        lights.append(scenes.point_light(rng.uniform(-6, 6, 3) + np.array([0, 4, 0]), (0.6, 0.6, 0.9)))
+    s = abi.copy_struct(settings)
+    s.xRes, s.yRes = int(rng.integers(24, 65)), int(rng.integers(18, 49))
+    s.antialias_samples = int(rng.choice([1, 4])); s.aperture = float(rng.choice([0.0, 0.2]))
+    s.brdf_samples = int(rng.integers(1, 3)); s.max_depth = int(rng.integers(1, 5)); s.blur_samples = 0
+    s.seed = int(rng.integers(1, 1 << 30))
+    v = rng.normal(0, 1, 3); v /= np.linalg.norm(v)
+    eye = v * float(rng.uniform(0.5, 9)); eye[1] = abs(eye[1]) * 0.7
+    s.eye[:] = [float(x) for x in eye]; s.lookingAt[:] = [float(x) for x in rng.uniform(-1, 1, 3)]; s.up[:] = [0, 1, 0]
+    s.focal_length = float(max(np.linalg.norm(eye), 1.0))
+    return "random_prism", Scene(prims, lights, base.textures), s
