@@ -289,3 +289,24 @@ def random_prism_scene(seed):
     s.eye[:] = [float(x) for x in eye]; s.lookingAt[:] = [float(x) for x in rng.uniform(-1, 1, 3)]; s.up[:] = [0, 1, 0]
     s.focal_length = float(max(np.linalg.norm(eye), 1.0))
     return "random_prism", Scene(prims, lights, base.textures), s
+
+
+def random_glass_scene(seed):
+    """random_scene plus one or two closed blocks of glass triangles (the reference's refraction path is only reachable on
+    `mesh` triangles): Fresnel split, total internal reflection, rays starting inside the glass."""
+    import numpy as np
+    from distraytracer_b200 import abi, scenes
+    from distraytracer_b200.scene import Scene
+    case, scene, s = random_scene(seed)
+    rng = np.random.default_rng(22000 + seed)
+    prims = [abi.copy_struct(p) for p in scene.prims]
+    lights = [abi.copy_struct(l) for l in scene.lights]
+    extra = []
+    for _ in range(int(rng.integers(1, 3))):
+        lo = rng.uniform(-2.5, 1.5, 3); hi = lo + rng.uniform(0.5, 2.0, 3)
+        extra.extend(scenes.glass_block(lo, hi))
+    # area lights point at their shapes by index: the blocks go in front, the indices move up
+    for l in lights:
+        if l.prim_index >= 0: l.prim_index += len(extra)
+    s.max_depth = int(rng.integers(2, 8))
+    return "random_glass", Scene(extra + prims, lights, scene.textures), s

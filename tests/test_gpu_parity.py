@@ -539,6 +539,20 @@ def test_cuda_matches_oracle_on_moving_meshes(oracle_lib, seed):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("seed", range(6))
+def test_cuda_matches_oracle_on_random_glass(oracle_lib, seed):
+    """Random scenes with closed blocks of glass triangles: Fresnel split, total internal reflection, rays that start
+    inside the glass, deeper recursion (fuzz_cases.random_glass_scene; tools/gpu_fuzz.py ran 400 seeds bit-identical)."""
+    from fuzz_cases import random_glass_scene
+    from oracle.harness import Oracle, ORACLE_KEYED, compare
+    _, scene, s = random_glass_scene(seed)
+    want, _, _, _ = Oracle(scene).render(s, mode=ORACLE_KEYED)
+    got, _ = _gpu(scene).render_float(s)
+    st = compare(want, got)
+    assert st["frac_within_1"] >= TOL_FRAC, (seed, st)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(6))
 def test_cuda_matches_oracle_on_random_prisms(oracle_lib, seed):
     """Random slab-box prisms (RectPrism / RectPrismWithCylinder / RectPrismWithHoles with random holes, a14), seen from
     anywhere, the inside included (fuzz_cases.random_prism_scene; tools/gpu_fuzz.py ran 400 seeds bit-identical; about 9 %
