@@ -310,3 +310,26 @@ def random_glass_scene(seed):
         if l.prim_index >= 0: l.prim_index += len(extra)
     s.max_depth = int(rng.integers(2, 8))
     return "random_glass", Scene(extra + prims, lights, scene.textures), s
+
+
+def random_refblur_scene(seed):
+    """random_scene in the REFERENCE's blur mode after frame_prism: shapes named "rectangle" move in y during the blur
+    re-traces of samples that hit a primitive flagged `motion` (render_final_project.cpp:1095-1210), leaf boxes are widened
+    but interior ones are not (bumpBVH, Q14) -- on random geometry, rectangles of the diagonal kind included."""
+    import numpy as np
+    from distraytracer_b200 import abi
+    from distraytracer_b200.scene import Scene
+    case, scene, s = random_scene(seed)
+    rng = np.random.default_rng(11000 + seed)
+    prims = [abi.copy_struct(p) for p in scene.prims]
+    for p in prims:
+        if not (p.flags & abi.FLAG_LIGHT) and rng.random() < 0.5:
+            p.flags |= abi.FLAG_MOTION
+        # the reference's Rectangle constructor names every rectangle and checkerboard "rectangle" (geometry.cpp:618,636):
+        # those are the shapes its blur moves.  The library takes the name as data; the reference cannot build the others.
+        if p.type in (abi.PRIM_RECTANGLE, abi.PRIM_CHECKERBOARD, abi.PRIM_CHECKERBOARD_HOLE) and p.name == abi.NAME_OTHER:
+            p.name = abi.NAME_RECTANGLE
+    s.blur_mode = abi.BLUR_REFERENCE
+    s.blur_samples, s.frame_range = int(rng.integers(1, 4)), int(rng.integers(1, 9))
+    s.frame = int(rng.integers(0, 2000)); s.frame_prism = 0; s.frame_blur = int(rng.choice([0, 100000]))
+    return "random_refblur", Scene(prims, scene.lights, scene.textures), s

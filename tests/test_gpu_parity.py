@@ -538,6 +538,21 @@ def test_cuda_matches_oracle_on_moving_meshes(oracle_lib, seed):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(8))
+def test_cuda_matches_oracle_on_random_scenes_with_the_reference_blur(oracle_lib, seed):
+    """fuzz_cases.random_refblur_scene: random scenes in the reference's own blur mode (moving "rectangle" shapes, bumped
+    leaf boxes: the node-by-node walk of the replayed reference tree); the oracle is pinned on the compiled reference for
+    these scenes in tests/test_oracle_fuzz.py; tools/gpu_fuzz.py ran 400 seeds bit-identical."""
+    from fuzz_cases import random_refblur_scene
+    from oracle.harness import Oracle, ORACLE_KEYED, compare
+    _, scene, s = random_refblur_scene(seed)
+    want, _, _, _ = Oracle(scene).render(s, mode=ORACLE_KEYED)
+    got, _ = _gpu(scene).render_float(s)
+    st = compare(want, got)
+    assert st["frac_within_1"] >= TOL_FRAC, (seed, st)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("seed", range(6))
 def test_cuda_matches_oracle_on_random_glass(oracle_lib, seed):
     """Random scenes with closed blocks of glass triangles: Fresnel split, total internal reflection, rays that start
