@@ -2104,18 +2104,31 @@ __constant__ int kNoisePrimes[10][3] = {{995615039, 600173719, 701464987}, {8317
                                         {405493717, 291031019, 391950901}, {458904767, 676625681, 424452397},
                                         {531736441, 939683957, 810651871}, {997169939, 842027887, 423882827}};
 
-__device__ inline double noise3D(int i_prime, int x, int y, int z) {   // noise.h:31-39, int32 wrap-around explicit
-  int n = (int)((double)(x + y * 57) + (double)z * 3249.0);
+// Noise3D (noise.h:31-39) of one lattice point, int32 wrap-around explicit.  The reference forms the lattice index in
+// double (`x + y * 57 + z * pow(57, 2)`) and converts it back to int, converts the hash to double and divides; the
+// conversions (I2F / F2I / F2F) all run on the SM's conversion unit, which the first version of this kernel kept 77 % busy
+// (profiles: cloud_corners, XU pipe) while the FP64 pipe idled.  Here the index is integer arithmetic -- the same number
+// while |x + 57 y + 3249 z| < 2^31, i.e. for every lattice point within ~600 000 units of the origin; beyond that the
+// reference's double -> int conversion is undefined behaviour and this wraps --, the hash becomes a double through the 2^52
+// trick, and lattice values widen back to double by bit manipulation: exact replacements that leave one conversion per
+// lattice point.
+__device__ __forceinline__ float noiseLattice(const uint32_t a, const uint32_t b, const uint32_t c, const int n) {
   uint32_t un = (uint32_t)n;
   un = (un << 13) ^ un;
-  uint32_t a = (uint32_t)kNoisePrimes[i_prime][0], b = (uint32_t)kNoisePrimes[i_prime][1], c = (uint32_t)kNoisePrimes[i_prime][2];
-  int t = (int)((un * (un * un * a + b) + c) & 0x7fffffffu);
+  const int t = (int)((un * (un * un * a + b) + c) & 0x7fffffffu);
+  const double td = __hiloint2double(0x43300000, t) - 4503599627370496.0;   // (double)t, exact for 0 <= t < 2^31
   // the reference divides by denom = 1073741823; the product with the reciprocal differs from the
-  // correctly rounded quotient by at most an ulp of a value that is then narrowed to float below,
+  // correctly rounded quotient by at most an ulp of a value that is then narrowed to float,
   // and spares a software double division per lattice hash (204 800 per background evaluation)
-  return 1.0 - (double)t * (1.0 / 1073741823.0);
+  return (float)(1.0 - td * (1.0 / 1073741823.0));
 }
-
+// float -> double, exact, for the lattice values (zero or normal, |v| <= 1): exponent rebias + mantissa shift
+__device__ __forceinline__ double latticeWiden(const float f) {
+  const uint32_t u = __float_as_uint(f);
+  const uint32_t hi = (u & 0x80000000u) | (((u >> 3) & 0x0fffffffu) + 0x38000000u);
+  const double d = __hiloint2double((int)hi, (int)(u << 29));
+  return (u << 1) ? d : 0.0;
+}
 __device__ inline double cosInterp(double a, double b, double x) {     // noise.h:25-29
   double f = (1 - cos(x * DRT_PI)) * 0.5;
   return a * (1 - f) + b * f;
@@ -2127,12 +2140,15 @@ __device__ inline double interpolatedNoise3D(int ip, double x, double y, double 
   int iZ = (int)z; double fZ = z - iZ;
   // lattice block [iX-1, iX+2] x [iY-1, iY+2] x [iZ-1, iZ+2]
   float lat[4][4][4];
+  const uint32_t pa = (uint32_t)kNoisePrimes[ip][0], pb = (uint32_t)kNoisePrimes[ip][1], pc = (uint32_t)kNoisePrimes[ip][2];
+  const int base = (iX - 1) + (iY - 1) * 57 + (iZ - 1) * 3249;
 #pragma unroll
   for (int a = 0; a < 4; a++)
 #pragma unroll
     for (int b = 0; b < 4; b++)
 #pragma unroll
-      for (int c = 0; c < 4; c++) lat[a][b][c] = (float)noise3D(ip, iX - 1 + a, iY - 1 + b, iZ - 1 + c);
+      for (int c = 0; c < 4; c++)
+        lat[a][b][c] = noiseLattice(pa, pb, pc, base + a + 57 * b + 3249 * c);
   const double alpha = 9.0 / 18, beta = 2.0 / (8 * 18), gamma = 4.0 / (6 * 18), delta = 3.0 / (12 * 18);
   double v[2][2][2];
 #pragma unroll
@@ -2148,16 +2164,18 @@ __device__ inline double interpolatedNoise3D(int ip, double x, double y, double 
           for (int b = -1; b <= 1; b++)
 #pragma unroll
             for (int c = -1; c <= 1; c++) {
-              double val = lat[1 + dx + a][1 + dy + b][1 + dz + c];
+              const double val = latticeWiden(lat[1 + dx + a][1 + dy + b][1 + dz + c]);
               int nz = (a != 0) + (b != 0) + (c != 0);
               if (nz == 3) corners += val; else if (nz == 1) sides += val; else if (nz == 2) dg += val;
             }
-        double center = lat[1 + dx][1 + dy][1 + dz];
+        const double center = latticeWiden(lat[1 + dx][1 + dy][1 + dz]);
         v[dx][dy][dz] = alpha * center + beta * corners + gamma * sides + delta * dg;
       }
   // cosInterpolate (noise.h:25-29): the blend factor depends only on the axis fraction, so it is
   // evaluated once per axis (3 cosines) instead of once per call (7)
-  const double gx = (1 - cos(fX * DRT_PI)) * 0.5, gy = (1 - cos(fY * DRT_PI)) * 0.5, gz = (1 - cos(fZ * DRT_PI)) * 0.5;
+  // cospi(f) for the reference's cos(f * M_PI): the same function of f to within an ulp of a value that ends up in a float
+  // a few operations later, without the multiplication's rounding and the general-argument reduction (config 3: 198 -> 193 ms)
+  const double gx = (1 - cospi(fX)) * 0.5, gy = (1 - cospi(fY)) * 0.5, gz = (1 - cospi(fZ)) * 0.5;
   const double w3 = v[0][0][0] * (1 - gx) + v[1][0][0] * gx, w4 = v[0][1][0] * (1 - gx) + v[1][1][0] * gx;
   const double w1 = v[0][0][1] * (1 - gx) + v[1][0][1] * gx, w2 = v[0][1][1] * (1 - gx) + v[1][1][1] * gx;
   const double i1 = w3 * (1 - gy) + w4 * gy, i2 = w1 * (1 - gy) + w2 * gy;
@@ -2229,8 +2247,11 @@ __device__ void cloudColorQuad(const Params<R>& P, const bool active, const Vec<
 // block is either the CTA's own (blockIdx) or -- one frame on several GPUs -- claimed from a counter all devices share,
 // the marks and colours then living in the gathering device's maps (peer loads / stores).
 #define DRT_CLOUD_BLOCK 32
+#ifndef DRT_CLOUD_MIN_BLOCKS
+#define DRT_CLOUD_MIN_BLOCKS 3   // 142 registers: three CTAs of four warps per SM (1 -> 208 registers, two CTAs: 205 vs 198 ms on config 3)
+#endif
 template <typename R>
-__global__ void __launch_bounds__(128) cloud_corners(const __grid_constant__ Params<R> P) {
+__global__ void __launch_bounds__(128, DRT_CLOUD_MIN_BLOCKS) cloud_corners(const __grid_constant__ Params<R> P) {
   const int gw = P.w + 1, gh = P.h + 1;
   const int n_blocks = (gw * gh + DRT_CLOUD_BLOCK - 1) / DRT_CLOUD_BLOCK;
   __shared__ int s_blk;
