@@ -1808,7 +1808,7 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
           const int total = s_count, nch = (total + 31) >> 5;
           for (int q = total + tid; q < nch * 32; q += blockDim.x) poolStoreEmpty<Task<R>>(pool, cap, (int)__ldcg(fre + f0 - 1 - (q >> 5)) * 32 + (q & 31));
           for (int c = tid; c < nch; c += blockDim.x) __stcg(stk + c, __ldcg(fre + f0 - 1 - c));
-          if (tid == 0) { s_state = 2; s_nst = nch; s_nfree = f0 - nch; s_count = 0; }
+          if (tid == 0) { s_state = 2; s_nst = nch; s_nfree = f0 - nch; }   // (s_count is reset behind the next barrier: other warps may still be reading it)
         } else finalize = true;
       } else if (state == 1 || state == 2) finalize = true;
       if (finalize) {
@@ -1891,7 +1891,7 @@ __global__ void __launch_bounds__(32 * DRT_WAVE_WARPS, DRT_WAVE_CTAS_PER_SM) ren
     // ================= TRACE: closest hits; a ray that hit stays in its slot, its reference goes to the hit buffer ====
     // (rays that miss are finished: they only update the in_motion chain flag)
     const int nst0 = s_nst;
-    if (tid == 0) s_grab = nst0;
+    if (tid == 0) { s_grab = nst0; s_count = 0; }
     __syncthreads();
     for (;;) {
       if (((volatile int*)&s_nhits)[0] >= DRT_TRACE_HITS_TARGET) break;  // enough hits for a full SHADE pass are waiting
