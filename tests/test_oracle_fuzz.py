@@ -141,6 +141,26 @@ def test_restatement_matches_reference_on_random_scenes_with_its_own_blur(oracle
     assert np.array_equal(ref_img, img, equal_nan=True), (seed, float(np.nanmax(np.abs(ref_img - img))))
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_restatement_matches_reference_on_big_random_scenes(oracle_lib, seed):
+    """fuzz_cases.random_big_scene: 257 .. 700 small shapes over a floor (the scenes on which the CUDA path gathers through
+    its tree over the geoms) loaded INTO the compiled reference: reproduced to the bit."""
+    if not _have_reference():
+        pytest.skip("reference tree not present (GPU box): pinned by the stored fixtures instead")
+    from fuzz_cases import random_big_scene
+    from oracle.harness import Ref, Oracle, ORACLE_STREAM
+    _, scene, s = random_big_scene(seed)
+    r = Ref(mocap=False)
+    r.reset()
+    r.load(scene)
+    r.set_settings(s)
+    r.rng(1, s.seed, 0)
+    ref_img, ref_ab, _ = r.render_loop(int(s.frame), reset_policy=1, seed=s.seed)
+    img, ab, _, _ = Oracle(scene).render(s, mode=ORACLE_STREAM)
+    assert (ab == ref_ab).all(), (seed, "abort masks differ")
+    assert np.array_equal(ref_img, img, equal_nan=True), (seed, float(np.nanmax(np.abs(ref_img - img))))
+
+
 @pytest.mark.parametrize("cfg", ["config1", "config2", "config3"])
 def test_restatement_matches_reference_on_the_bench_workloads(oracle_lib, cfg):
     """The BASELINE configurations themselves (distraytracer_b200.scenes: config 2 is what bench.py times -- glass
