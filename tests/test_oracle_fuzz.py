@@ -161,6 +161,26 @@ def test_restatement_matches_reference_on_big_random_scenes(oracle_lib, seed):
     assert np.array_equal(ref_img, img, equal_nan=True), (seed, float(np.nanmax(np.abs(ref_img - img))))
 
 
+@pytest.mark.parametrize("seed", range(4))
+def test_restatement_matches_reference_with_the_cloud_background(oracle_lib, seed):
+    """fuzz_cases.sky_case: mutated fixture scenes in front of the value-noise clouds (perlin_cloud: cloudColor per missed
+    sample, noise.h) loaded INTO the compiled reference: reproduced to the bit."""
+    if not _have_reference():
+        pytest.skip("reference tree not present (GPU box): pinned by the stored fixtures instead")
+    from fuzz_cases import sky_case
+    from oracle.harness import Ref, Oracle, ORACLE_STREAM
+    _, scene, s = sky_case(seed)
+    r = Ref(mocap=False)
+    r.reset()
+    r.load(scene)
+    r.set_settings(s)
+    r.rng(1, s.seed, 0)
+    ref_img, ref_ab, _ = r.render_loop(int(s.frame), reset_policy=1, seed=s.seed)
+    img, ab, _, _ = Oracle(scene).render(s, mode=ORACLE_STREAM)
+    assert (ab == ref_ab).all(), (seed, "abort masks differ")
+    assert np.array_equal(ref_img, img, equal_nan=True), (seed, float(np.nanmax(np.abs(ref_img - img))))
+
+
 @pytest.mark.parametrize("cfg", ["config1", "config2", "config3"])
 def test_restatement_matches_reference_on_the_bench_workloads(oracle_lib, cfg):
     """The BASELINE configurations themselves (distraytracer_b200.scenes: config 2 is what bench.py times -- glass
