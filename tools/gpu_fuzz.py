@@ -46,6 +46,7 @@ for seed in range(n_cases):
             eye = look + (eye - look) * float(rng.uniform(0.02, 0.3))
         s.eye[:] = [float(x) for x in eye]; s.lookingAt[:] = [float(x) for x in look]
         s.aperture = float(rng.choice([0.0, 0.05, 0.4])); s.focal_length = float(rng.uniform(0.5, 2.0) * d)
+    s.precision = int(os.environ.get("DRT_FUZZ_PRECISION", "0"))     # 1: the single-precision build (same bar; rounding-fragile scenes may miss it)
     want, _, _, _ = Oracle(flat if flat is not None else sc).render(s, mode=ORACLE_KEYED)   # meshes: the oracle takes Triangle primitives
     got, _ = runtime.DeviceScene(sc, 0).render_float(s)
     st = compare(want, got)
